@@ -1,0 +1,114 @@
+/* pfc.h -- C ABI of libpfc_b200.so: B200-native contact-wrench evaluation for pressure-field
+ * contact (drop-in for the hot path of ryanelandt/PressureFieldContact.jl).
+ *
+ * The boundary replaces the reference's forceAllElasticIntersections!(m, tm)
+ * (src/contact_algorithms_non_friction.jl:60-68) as called from calcXd! (:18-38), which is the
+ * function MechanismScenario.de holds (src/mechanism_scenario.jl:175,181,196) and Radau calls with
+ * Vector{Float64} (src/radau/radau_functions.jl:67) and Vector{Dual{Nothing,Float64,6}} (:9).
+ * Rigid-body kinematics before it (refreshBodyBodyTransform!/refreshBodyBodyCache!, :103-134) and
+ * the J' * wrench epilogue after it (addGeneralizedForcesThirdLaw!, :267-286) stay with the
+ * caller (RigidBodyDynamics on the Julia side); INTEGRATION.md shows the ccall shim.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative PFC_E_* code;
+ *     pfc_last_error() returns a thread-local message for the last failure on this thread.
+ *   - the caller owns every host buffer; the library copies on entry and never keeps a caller
+ *     pointer after the call returns.  Device memory and the CUDA stream belong to the context.
+ *   - a context is not thread-safe: one context per host thread / per GPU.
+ *   - indices are 0-based int32 (the reference uses 1-based Int64).
+ *   - matrices: 4x4 transforms are column-major (Julia SMatrix layout); twists and wrenches are
+ *     [angular(3); linear(3)] (as_static_vector, src/utility.jl:13-14).
+ *   - the wrench returned for an instruction is about the origin of mesh_2's frame r2, expressed
+ *     in r2, applied TO body 2; the normal points into body 2; the relative velocity is v2 - v1
+ *     (src/contact_algorithms_non_friction.jl:10-17).
+ */
+#ifndef PFC_H
+#define PFC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pfc_ctx pfc_ctx;
+
+enum {
+    PFC_OK = 0,
+    PFC_E_ARG = -1,       /* bad argument / call order */
+    PFC_E_CUDA = -2,      /* CUDA runtime error (message has the CUDA string) */
+    PFC_E_CAPACITY = -3,  /* a fixed capacity was exceeded and could not be grown */
+    PFC_E_NONFINITE = -4, /* the reference's error("Non-finite vertex likely"), src/clip/static_clip.jl:52 */
+    PFC_E_MESH = -5       /* invalid mesh (inverted tetrahedron, src/obb/obb_construction.jl:30; bad tree) */
+};
+
+/* per-(environment, instruction) flag bits */
+enum { PFC_FLAG_CONTACT = 1, PFC_FLAG_NONFINITE = 2, PFC_FLAG_BAD_ARITY = 4, PFC_FLAG_OVERFLOW = 8 };
+
+/* MechanismScenario() -- src/mechanism_scenario.jl:181-198.  Creates an empty scene on CUDA device `device`. */
+int pfc_create(int device, pfc_ctx** out);
+int pfc_destroy(pfc_ctx* ctx);
+
+/* add_contact! / MeshCache -- src/mechanism_scenario.jl:298-314, src/structs.jl:33-54.
+ * kind: 0 = triangle mesh (eps == NULL, Ebar ignored), 1 = tetrahedral mesh (eps per point, Ebar =
+ * ContactProperties.E).  idx: n_prim x 3 or n_prim x 4.  The bounding-volume tree is the host-built
+ * bin_BB_Tree (src/obb/tree_types.jl:1-16) flattened into arrays: node 0 is the root; node_R is
+ * column-major 3x3 per node; node_left/right are node indices (-1 for a leaf); node_leaf_id is
+ * the 0-based primitive index for leaves and -1 for internal nodes (the reference's id == -9999). */
+int pfc_add_mesh(pfc_ctx* ctx, int kind, int64_t n_point, const double* xyz, int64_t n_prim, const int32_t* idx, const double* eps, double Ebar,
+                 int64_t n_node, const double* node_c, const double* node_e, const double* node_R, const int32_t* node_left,
+                 const int32_t* node_right, const int32_t* node_leaf_id, int* mesh_id_out);
+
+/* ContactInstructions + add_friction_regularize! / add_friction_bristle! -- src/mechanism_scenario.jl:36-49, 365-416.
+ * mesh_2 must be a tetrahedral mesh (the caller applies the Tri/Tet ordering rule, :399-416).
+ * model 0 = Regularized, params = {mu_s, mu_d, v_c}; model 1 = Bristle, params = {tau, k_bar, mu_s, mu_d, magic};
+ * bristle ids are assigned in call order.  n_quad_rule in {1, 2} (:45). */
+int pfc_add_instruction(pfc_ctx* ctx, int mesh_1, int mesh_2, double chi, int model, const double* params, int n_quad_rule, int* ins_id_out);
+
+/* finalize! -- src/mechanism_scenario.jl:206-231: uploads the static scene and sizes the per-batch buffers for max_env environments. */
+int pfc_finalize(pfc_ctx* ctx, int64_t max_env);
+
+/* forceAllElasticIntersections!, Float64 mode -- src/contact_algorithms_non_friction.jl:60-84, for n_env independent states of the scene.
+ *   X_r2_r1 [env][ins][16]  b.x_r2_r1.mat (:112)          twist_r2 [env][ins][6]  b.twist_r2_r1_r2 (:128)
+ *   s       [env][bristle][6] bristle state (tm.s)         sdot     [env][bristle][6] tm.s-dot   (both may be NULL without bristles)
+ *   wrench_r2 [env][ins][6]  the wrench yes_contact! returns (zero when no contact)
+ *   n_pairs [env][ins] length(m.TT_Cache) (:74)            flags    [env][ins] PFC_FLAG_* bits         (either may be NULL)
+ * Host pointers; copies in and out are part of the call; synchronous at return. */
+int pfc_eval_f64(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2, double* sdot,
+                 int64_t* n_pairs, int32_t* flags);
+
+/* Same evaluation on buffers already resident in device memory (all pointers are device pointers,
+ * none may be NULL except s/sdot without bristles); enqueued on the context's stream, asynchronous. */
+int pfc_eval_f64_device(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2,
+                        double* sdot, int64_t* n_pairs, int32_t* flags);
+
+/* forceAllElasticIntersections!, Dual{Nothing,Float64,6} mode (the Jacobian chunks of src/radau/radau_functions.jl:2-26).
+ * Every Dual scalar is 7 doubles: value, then 6 partials.  X_bp is the Float64 transform the broad phase uses: the reference always
+ * traverses with m.float's state (src/contact_algorithms_non_friction.jl:94-101); pass NULL to reuse the pair lists of the previous
+ * pfc_eval_f64 call on this context. */
+int pfc_eval_dual6(pfc_ctx* ctx, int64_t n_env, const double* X_bp, const double* X7_r2_r1, const double* twist7_r2, const double* s7,
+                   double* wrench7_r2, double* sdot7, int64_t* n_pairs, int32_t* flags);
+
+/* Debug / parity: keep the candidate-pair lists (TT_Cache, src/obb/tree_types.jl:32-50) of subsequent evaluations. */
+int pfc_set_debug(pfc_ctx* ctx, int keep_pairs);
+/* Pair list of (env, ins) from the last evaluation, in the reference's traversal order: pairs[2k] = primitive of mesh_1, pairs[2k+1] = of mesh_2. */
+int pfc_get_pairs(pfc_ctx* ctx, int64_t env, int ins, int32_t* pairs, int64_t cap, int64_t* n_out);
+/* TractionCache (src/mechanism_scenario.jl:51-58) of (env, ins) from the last evaluation: 8 doubles per point: n(3), r_cart(3), dA, p. */
+int pfc_get_traction(pfc_ctx* ctx, int64_t env, int ins, double* out, int64_t cap_points, int64_t* n_out);
+
+/* Multi-GPU for one very large scene: this context evaluates only slice `rank` of `world` of every
+ * large instruction's sorted pair list; the caller sums wrench_r2 across ranks (NCCL allreduce). */
+int pfc_set_shard(pfc_ctx* ctx, int rank, int world);
+
+/* Plumbing */
+int pfc_sync(pfc_ctx* ctx);
+void* pfc_stream(pfc_ctx* ctx);            /* the cudaStream_t kernels are launched on (for CUDA-event timing) */
+int64_t pfc_launch_count(pfc_ctx* ctx);   /* kernels launched by this context so far */
+int pfc_counters(pfc_ctx* ctx, int64_t* n_node_pairs_tested, int64_t* n_candidate_pairs);
+const char* pfc_last_error(void);
+const char* pfc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFC_H */

@@ -1,0 +1,197 @@
+"""ctypes binding of libpfc_b200.so -- the same symbols a Julia ``ccall`` shim binds.
+
+There is no CPU fallback: if the CUDA library is missing this module raises at load time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpfc_b200.so")
+_LIB = None
+
+_d = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_i64 = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+# every symbol include/pfc.h declares
+SYMBOLS = [
+    "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
+    "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_sync", "pfc_stream",
+    "pfc_launch_count", "pfc_counters", "pfc_last_error", "pfc_version",
+]
+
+
+class PfcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pfc error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback for the contact-wrench path)")
+        L = C.CDLL(LIB_PATH)
+        L.pfc_create.argtypes = [C.c_int, C.POINTER(_vp)]
+        L.pfc_destroy.argtypes = [_vp]
+        L.pfc_add_mesh.argtypes = [_vp, C.c_int, C.c_int64, _d, C.c_int64, _i32, _vp, C.c_double, C.c_int64, _d, _d, _d, _i32, _i32, _i32,
+                                   C.POINTER(C.c_int)]
+        L.pfc_add_instruction.argtypes = [_vp, C.c_int, C.c_int, C.c_double, C.c_int, _d, C.c_int, C.POINTER(C.c_int)]
+        L.pfc_finalize.argtypes = [_vp, C.c_int64]
+        L.pfc_eval_f64.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_eval_f64_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_eval_dual6.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_set_debug.argtypes = [_vp, C.c_int]
+        L.pfc_get_pairs.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.pfc_get_traction.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.pfc_set_shard.argtypes = [_vp, C.c_int, C.c_int]
+        L.pfc_sync.argtypes = [_vp]
+        L.pfc_stream.argtypes = [_vp]
+        L.pfc_stream.restype = _vp
+        L.pfc_launch_count.argtypes = [_vp]
+        L.pfc_launch_count.restype = C.c_int64
+        L.pfc_counters.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.pfc_last_error.restype = C.c_char_p
+        L.pfc_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise PfcError(rc, lib().pfc_last_error().decode())
+
+
+def _a(x, dt=np.float64):
+    return np.ascontiguousarray(x, dtype=dt)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+class Context:
+    """One scene on one GPU.  Same protocol as the scenario backends: add_mesh, add_instruction,
+    finalize, eval_f64, eval_dual6, get_pairs, get_traction."""
+
+    name = "cuda"
+
+    def __init__(self, device: int = 0):
+        self._h = _vp()
+        _check(lib().pfc_create(device, C.byref(self._h)))
+        self.device = device
+        self.n_ins = 0
+        self.n_bristle = 0
+
+    def close(self):
+        if self._h:
+            lib().pfc_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene ---------------------------------------------------------------------------------------
+    def add_mesh(self, kind, xyz, idx, eps, Ebar, tree) -> int:
+        xyz = _a(xyz).reshape(-1, 3)
+        idx = _a(idx, np.int32)
+        eps_a = None if eps is None else _a(eps)
+        out = C.c_int(-1)
+        _check(lib().pfc_add_mesh(self._h, kind, len(xyz), xyz, len(idx), idx, _p(eps_a), float(Ebar or 0.0), tree.n_node, _a(tree.c), _a(tree.e),
+                                  _a(tree.R), _a(tree.left, np.int32), _a(tree.right, np.int32), _a(tree.leaf_id, np.int32), C.byref(out)))
+        return out.value
+
+    def add_instruction(self, mesh_1, mesh_2, chi, model, params, n_quad_rule) -> int:
+        out = C.c_int(-1)
+        _check(lib().pfc_add_instruction(self._h, mesh_1, mesh_2, float(chi), model, _a(params), n_quad_rule, C.byref(out)))
+        self.n_ins = out.value + 1
+        if model == 1:
+            self.n_bristle += 1
+        return out.value
+
+    def finalize(self, max_env: int = 1):
+        _check(lib().pfc_finalize(self._h, max_env))
+
+    def set_debug(self, keep_pairs: bool = True):
+        _check(lib().pfc_set_debug(self._h, int(keep_pairs)))
+
+    def set_shard(self, rank: int, world: int):
+        _check(lib().pfc_set_shard(self._h, rank, world))
+
+    # ---- evaluation ----------------------------------------------------------------------------------
+    def eval_f64(self, X, twist, s=None, keep=False, out=None):
+        """Host arrays in, host arrays out (copies inside the call)."""
+        if keep:
+            self.set_debug(True)
+        X = _a(X).reshape(-1, self.n_ins, 16)
+        n_env = X.shape[0]
+        twist = _a(twist).reshape(n_env, self.n_ins, 6)
+        nb = self.n_bristle
+        s_a = _a(s).reshape(n_env, nb, 6) if nb else None
+        if out is None:
+            out = dict(wrench=np.zeros((n_env, self.n_ins, 6)), sdot=np.zeros((n_env, nb, 6)) if nb else None,
+                       n_pairs=np.zeros((n_env, self.n_ins), np.int64), flags=np.zeros((n_env, self.n_ins), np.int32))
+        _check(lib().pfc_eval_f64(self._h, n_env, _p(X), _p(twist), _p(s_a), _p(out["wrench"]), _p(out["sdot"]), _p(out["n_pairs"]),
+                                  _p(out["flags"])))
+        return out
+
+    def eval_f64_ptr(self, n_env, X, twist, s, wrench, sdot, n_pairs, flags):
+        """Host pointers given as integers (e.g. pinned torch tensors' data_ptr())."""
+        _check(lib().pfc_eval_f64(self._h, n_env, X, twist, s, wrench, sdot, n_pairs, flags))
+
+    def eval_f64_device(self, n_env, X, twist, s, wrench, sdot, n_pairs, flags):
+        """Device pointers given as integers; asynchronous on self.stream."""
+        _check(lib().pfc_eval_f64_device(self._h, n_env, X, twist, s, wrench, sdot, n_pairs, flags))
+
+    def eval_dual6(self, X_bp, X7, twist7, s7=None):
+        n_env = _a(X7).reshape(-1, self.n_ins, 16, 7).shape[0]
+        X7 = _a(X7).reshape(n_env, self.n_ins, 16, 7)
+        X_bp_a = None if X_bp is None else _a(X_bp).reshape(n_env, self.n_ins, 16)
+        twist7 = _a(twist7).reshape(n_env, self.n_ins, 6, 7)
+        nb = self.n_bristle
+        s_a = _a(s7).reshape(n_env, nb, 6, 7) if nb else None
+        out = dict(wrench=np.zeros((n_env, self.n_ins, 6, 7)), sdot=np.zeros((n_env, nb, 6, 7)) if nb else None,
+                   n_pairs=np.zeros((n_env, self.n_ins), np.int64), flags=np.zeros((n_env, self.n_ins), np.int32))
+        _check(lib().pfc_eval_dual6(self._h, n_env, _p(X_bp_a), _p(X7), _p(twist7), _p(s_a), _p(out["wrench"]), _p(out["sdot"]),
+                                    _p(out["n_pairs"]), _p(out["flags"])))
+        return out
+
+    # ---- debug / parity --------------------------------------------------------------------------------
+    def get_pairs(self, env: int, ins: int) -> np.ndarray:
+        n = C.c_int64(0)
+        _check(lib().pfc_get_pairs(self._h, env, ins, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 2), np.int32)
+        _check(lib().pfc_get_pairs(self._h, env, ins, _p(out), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def get_traction(self, env: int, ins: int, cap: int = 1 << 16) -> np.ndarray:
+        n = C.c_int64(0)
+        out = np.zeros((cap, 8))
+        _check(lib().pfc_get_traction(self._h, env, ins, _p(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    # ---- plumbing ------------------------------------------------------------------------------------
+    def sync(self):
+        _check(lib().pfc_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().pfc_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(lib().pfc_launch_count(self._h))
+
+    def counters(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(lib().pfc_counters(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value

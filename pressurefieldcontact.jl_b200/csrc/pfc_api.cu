@@ -1,0 +1,460 @@
+// pfc_api.cu -- the C ABI of include/pfc.h: scene container, one-time upload, evaluation entry points.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pfc.h"
+#include "pfc_launch.h"
+
+using namespace pfc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(PFC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct HostMesh {
+    int kind;
+    int64_t n_point, n_prim;
+    std::vector<double> xyz, eps;
+    std::vector<int32_t> idx;
+    double Ebar;
+    std::vector<NodeRec> nodes;  // pre-order, mesh-local links
+    std::vector<int32_t> leaf_depth;     // per primitive: depth of its leaf node
+    std::vector<uint64_t> leaf_path;     // per primitive: root-to-leaf turns, MSB-first in the low `depth` bits
+    int depth;                           // max leaf depth
+    int node_base, prim_base;
+};
+
+struct HostIns {
+    int mesh_1, mesh_2, model, n_quad_rule, bristle_id;
+    double chi, params[5];
+};
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct pfc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool finalized = false;
+    std::vector<HostMesh> mesh;
+    std::vector<HostIns> ins;
+    int n_bristle = 0;
+    int64_t max_env = 0;
+    // static scene on the device
+    DevBuf<NodeRec> d_nodes;
+    DevBuf<TetRec> d_tets;
+    DevBuf<TriRec> d_tris;
+    DevBuf<InsDev> d_ins;
+    DevBuf<int32_t> d_small;
+    std::vector<InsDev> h_ins;
+    SceneDev scene{};
+    // per-batch staging (host-pointer entry points)
+    DevBuf<double> d_X, d_tw, d_s, d_w, d_sd;
+    DevBuf<long long> d_np;
+    DevBuf<int> d_fl;
+    // debug
+    bool keep_pairs = false;
+    DevBuf<int> d_dbg_pairs;
+    int dbg_cap = 0;
+    int64_t dbg_n_env = 0;
+    DevBuf<long long> d_last_np;   // n_pairs of the last evaluation (device copy kept for get_pairs)
+    const double* last_X = nullptr; const double* last_tw = nullptr;  // device pointers of the last evaluation
+    int64_t launches = 0;
+    int shard_rank = 0, shard_world = 1;
+};
+
+namespace {
+
+// inverse of A = [v0 v1 v2 v3; 1 1 1 1] (columns are the homogeneous vertices) by the adjugate,
+// using 2x2 sub-determinants; row-major output.
+bool invert_tet_matrix(const double v[12], double inv[16]) {
+    double a[16];  // row-major a[4*i+j]
+    for (int j = 0; j < 4; ++j) { a[0 + j] = v[3 * j]; a[4 + j] = v[3 * j + 1]; a[8 + j] = v[3 * j + 2]; a[12 + j] = 1.0; }
+    const double s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
+    const double s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
+    const double c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
+    const double c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
+    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    if (!(det != 0.0) || !std::isfinite(det)) return false;
+    const double id = 1.0 / det;
+    inv[0] = (a[5] * c5 - a[6] * c4 + a[7] * c3) * id;
+    inv[1] = (-a[1] * c5 + a[2] * c4 - a[3] * c3) * id;
+    inv[2] = (a[13] * s5 - a[14] * s4 + a[15] * s3) * id;
+    inv[3] = (-a[9] * s5 + a[10] * s4 - a[11] * s3) * id;
+    inv[4] = (-a[4] * c5 + a[6] * c2 - a[7] * c1) * id;
+    inv[5] = (a[0] * c5 - a[2] * c2 + a[3] * c1) * id;
+    inv[6] = (-a[12] * s5 + a[14] * s2 - a[15] * s1) * id;
+    inv[7] = (a[8] * s5 - a[10] * s2 + a[11] * s1) * id;
+    inv[8] = (a[4] * c4 - a[5] * c2 + a[7] * c0) * id;
+    inv[9] = (-a[0] * c4 + a[1] * c2 - a[3] * c0) * id;
+    inv[10] = (a[12] * s4 - a[13] * s2 + a[15] * s0) * id;
+    inv[11] = (-a[8] * s4 + a[9] * s2 - a[11] * s0) * id;
+    inv[12] = (-a[4] * c3 + a[5] * c1 - a[6] * c0) * id;
+    inv[13] = (a[0] * c3 - a[1] * c1 + a[2] * c0) * id;
+    inv[14] = (-a[12] * s3 + a[13] * s1 - a[14] * s0) * id;
+    inv[15] = (a[8] * s3 - a[9] * s1 + a[10] * s0) * id;
+    return true;
+}
+
+double tet_volume6(const double v[12]) {  // 6 * signed volume, positive for the reference's orientation
+    const double* a = v; const double* b = v + 3; const double* c = v + 6; const double* d = v + 9;
+    double V = (b[0] - a[0]) * (c[1] * d[2] - c[2] * d[1]);
+    V += (b[1] - a[1]) * (c[2] * d[0] - c[0] * d[2]);
+    V += (b[2] - a[2]) * (c[0] * d[1] - c[1] * d[0]);
+    V += (c[0] - d[0]) * (a[2] * b[1] - a[1] * b[2]);
+    V += (c[1] - d[1]) * (a[0] * b[2] - a[2] * b[0]);
+    V += (c[2] - d[2]) * (a[1] * b[0] - a[0] * b[1]);
+    return V;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pfc_last_error(void) { return g_err.c_str(); }
+const char* pfc_version(void) { return "pfc-b200 0.1 (sm_100a)"; }
+
+int pfc_create(int device, pfc_ctx** out) {
+    if (!out) return fail(PFC_E_ARG, "pfc_create: out is NULL");
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(PFC_E_ARG, "pfc_create: no such CUDA device");
+    CU(cudaSetDevice(device));
+    pfc_ctx* c = new pfc_ctx();
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(PFC_E_CUDA, cudaGetErrorString(e)); }
+    *out = c;
+    return PFC_OK;
+}
+
+int pfc_destroy(pfc_ctx* c) {
+    if (!c) return PFC_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release();
+    c->d_X.release(); c->d_tw.release(); c->d_s.release(); c->d_w.release(); c->d_sd.release(); c->d_np.release(); c->d_fl.release();
+    c->d_dbg_pairs.release(); c->d_last_np.release();
+    delete c;
+    return PFC_OK;
+}
+
+int pfc_add_mesh(pfc_ctx* c, int kind, int64_t n_point, const double* xyz, int64_t n_prim, const int32_t* idx, const double* eps, double Ebar,
+                 int64_t n_node, const double* node_c, const double* node_e, const double* node_R, const int32_t* node_left,
+                 const int32_t* node_right, const int32_t* node_leaf_id, int* mesh_id_out) {
+    if (!c || c->finalized) return fail(PFC_E_ARG, "pfc_add_mesh: context missing or already finalized");
+    if (kind != 0 && kind != 1) return fail(PFC_E_ARG, "pfc_add_mesh: kind must be 0 (tri) or 1 (tet)");
+    if (!xyz || !idx || n_point <= 0 || n_prim <= 0) return fail(PFC_E_ARG, "pfc_add_mesh: empty mesh");
+    if (kind == 1 && !eps) return fail(PFC_E_ARG, "pfc_add_mesh: tet mesh needs eps");
+    if (n_node != 2 * n_prim - 1) return fail(PFC_E_MESH, "pfc_add_mesh: a binary tree over n_prim leaves has 2 n_prim - 1 nodes");
+    const int w = kind == 0 ? 3 : 4;
+    HostMesh m;
+    m.kind = kind; m.n_point = n_point; m.n_prim = n_prim; m.Ebar = Ebar;
+    m.xyz.assign(xyz, xyz + 3 * n_point);
+    m.idx.assign(idx, idx + w * n_prim);
+    if (kind == 1) m.eps.assign(eps, eps + n_point);
+    for (int64_t k = 0; k < w * n_prim; ++k)
+        if (idx[k] < 0 || idx[k] >= n_point) return fail(PFC_E_MESH, "pfc_add_mesh: vertex index out of range");
+    // re-flatten the tree in pre-order from node 0, recording each leaf's root-to-leaf path
+    m.nodes.resize(n_node);
+    m.leaf_depth.assign(n_prim, -1);
+    m.leaf_path.assign(n_prim, 0);
+    m.depth = 0;
+    struct Item { int32_t src; int32_t parent_dst; int side; int depth; uint64_t path; };
+    std::vector<Item> stack;
+    stack.push_back({0, -1, 0, 0, 0});
+    int32_t next = 0;
+    std::vector<char> seen(n_node, 0);
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        if (it.src < 0 || it.src >= n_node || seen[it.src]) return fail(PFC_E_MESH, "pfc_add_mesh: tree links are not a tree");
+        seen[it.src] = 1;
+        const int32_t dst = next++;
+        NodeRec& nd = m.nodes[dst];
+        for (int i = 0; i < 3; ++i) {
+            nd.c[i] = node_c[3 * it.src + i];
+            nd.e[i] = node_e[3 * it.src + i];
+            for (int j = 0; j < 3; ++j) nd.R[3 * i + j] = node_R[9 * it.src + 3 * j + i];  // column-major in, row-major stored
+        }
+        if (it.parent_dst >= 0) { if (it.side == 0) m.nodes[it.parent_dst].left = dst; else m.nodes[it.parent_dst].right = dst; }
+        const int32_t leaf = node_leaf_id[it.src];
+        if (leaf >= 0) {
+            if (leaf >= n_prim || m.leaf_depth[leaf] >= 0) return fail(PFC_E_MESH, "pfc_add_mesh: leaf ids are not a permutation of the primitives");
+            nd.left = -1; nd.right = leaf;
+            m.leaf_depth[leaf] = it.depth;
+            m.leaf_path[leaf] = it.path;
+            if (it.depth > m.depth) m.depth = it.depth;
+        } else {
+            if (it.depth >= 62) return fail(PFC_E_MESH, "pfc_add_mesh: tree deeper than 62 levels");
+            nd.left = nd.right = -1;
+            stack.push_back({node_right[it.src], dst, 1, it.depth + 1, (it.path << 1) | 1u});
+            stack.push_back({node_left[it.src], dst, 0, it.depth + 1, (it.path << 1)});
+        }
+    }
+    if (next != n_node) return fail(PFC_E_MESH, "pfc_add_mesh: unreachable tree nodes");
+    if (kind == 1) {
+        for (int64_t k = 0; k < n_prim; ++k) {
+            double v[12];
+            for (int j = 0; j < 4; ++j) for (int i = 0; i < 3; ++i) v[3 * j + i] = xyz[3 * idx[4 * k + j] + i];
+            if (!(0.0 < tet_volume6(v))) return fail(PFC_E_MESH, "pfc_add_mesh: inverted tetrahedron");
+        }
+    }
+    c->mesh.push_back(std::move(m));
+    if (mesh_id_out) *mesh_id_out = int(c->mesh.size()) - 1;
+    return PFC_OK;
+}
+
+int pfc_add_instruction(pfc_ctx* c, int mesh_1, int mesh_2, double chi, int model, const double* params, int n_quad_rule, int* ins_id_out) {
+    if (!c || c->finalized) return fail(PFC_E_ARG, "pfc_add_instruction: context missing or already finalized");
+    const int nm = int(c->mesh.size());
+    if (mesh_1 < 0 || mesh_1 >= nm || mesh_2 < 0 || mesh_2 >= nm) return fail(PFC_E_ARG, "pfc_add_instruction: no such mesh");
+    if (c->mesh[mesh_2].kind != 1) return fail(PFC_E_ARG, "pfc_add_instruction: mesh_2 must be a tetrahedral mesh (add_friction! ordering rule)");
+    if (model != 0 && model != 1) return fail(PFC_E_ARG, "pfc_add_instruction: model must be 0 (regularized) or 1 (bristle)");
+    if (n_quad_rule < 1 || n_quad_rule > 2) return fail(PFC_E_ARG, "only quadrature rules 1 (first order) and 2 (second? order) are currently implemented");
+    if (!params) return fail(PFC_E_ARG, "pfc_add_instruction: params is NULL");
+    HostIns h{};
+    h.mesh_1 = mesh_1; h.mesh_2 = mesh_2; h.model = model; h.n_quad_rule = n_quad_rule; h.chi = chi;
+    const int np = model == 0 ? 3 : 5;
+    for (int k = 0; k < np; ++k) h.params[k] = params[k];
+    h.bristle_id = model == 1 ? c->n_bristle++ : -1;
+    c->ins.push_back(h);
+    if (ins_id_out) *ins_id_out = int(c->ins.size()) - 1;
+    return PFC_OK;
+}
+
+int pfc_finalize(pfc_ctx* c, int64_t max_env) {
+    if (!c || c->finalized) return fail(PFC_E_ARG, "pfc_finalize: context missing or already finalized");
+    if (c->ins.empty()) return fail(PFC_E_ARG, "pfc_finalize: no contact instructions");
+    if (max_env < 1) max_env = 1;
+    CU(cudaSetDevice(c->device));
+    std::vector<NodeRec> nodes;
+    std::vector<TetRec> tets;
+    std::vector<TriRec> tris;
+    for (auto& m : c->mesh) {
+        m.node_base = int(nodes.size());
+        nodes.insert(nodes.end(), m.nodes.begin(), m.nodes.end());
+        if (m.kind == 1) {
+            m.prim_base = int(tets.size());
+            for (int64_t k = 0; k < m.n_prim; ++k) {
+                TetRec t;
+                double e4[4];
+                for (int j = 0; j < 4; ++j) {
+                    const int32_t vi = m.idx[4 * k + j];
+                    for (int i = 0; i < 3; ++i) t.v[3 * j + i] = m.xyz[3 * vi + i];
+                    e4[j] = m.eps[vi];
+                }
+                if (!invert_tet_matrix(t.v, t.inv)) return fail(PFC_E_MESH, "pfc_finalize: degenerate tetrahedron");
+                for (int j = 0; j < 4; ++j) t.eps_r[j] = e4[0] * t.inv[j] + e4[1] * t.inv[4 + j] + e4[2] * t.inv[8 + j] + e4[3] * t.inv[12 + j];
+                tets.push_back(t);
+            }
+        } else {
+            m.prim_base = int(tris.size());
+            for (int64_t k = 0; k < m.n_prim; ++k) {
+                TriRec t;
+                for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) t.v[3 * j + i] = m.xyz[3 * m.idx[3 * k + j] + i];
+                // triangleNormal = normalize(cross(v2 - v1, v3 - v2) * 0.5)
+                const double ax = t.v[3] - t.v[0], ay = t.v[4] - t.v[1], az = t.v[5] - t.v[2];
+                const double bx = t.v[6] - t.v[3], by = t.v[7] - t.v[4], bz = t.v[8] - t.v[5];
+                const double nx = (ay * bz - az * by) * 0.5, ny = (az * bx - ax * bz) * 0.5, nz = (ax * by - ay * bx) * 0.5;
+                const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+                t.n[0] = nx / len; t.n[1] = ny / len; t.n[2] = nz / len;
+                tris.push_back(t);
+            }
+        }
+    }
+    c->h_ins.clear();
+    std::vector<int32_t> small;
+    for (size_t k = 0; k < c->ins.size(); ++k) {
+        const HostIns& h = c->ins[k];
+        const HostMesh& m1 = c->mesh[h.mesh_1];
+        const HostMesh& m2 = c->mesh[h.mesh_2];
+        InsDev d{};
+        d.kind1 = m1.kind; d.model = h.model; d.n_quad = h.n_quad_rule == 1 ? 1 : 3; d.bristle_id = h.bristle_id;
+        d.node_base1 = m1.node_base; d.node_base2 = m2.node_base; d.prim_base1 = m1.prim_base; d.prim_base2 = m2.prim_base;
+        d.n_leaf1 = int(m1.n_prim); d.n_leaf2 = int(m2.n_prim);
+        d.key_bits = m1.depth + m2.depth;
+        if (d.key_bits > 64) return fail(PFC_E_MESH, "pfc_finalize: tree depths sum to more than 64 levels");
+        d.small = (m1.n_prim * m2.n_prim <= kSmallCap && m1.n_prim < 16384 && m2.n_prim < 16384) ? 1 : 0;
+        d.chi = h.chi; d.Ebar1 = m1.kind == 1 ? m1.Ebar : 0.0; d.Ebar2 = m2.Ebar;
+        if (h.model == 0) { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = 2 * h.params[2]; d.p[4] = 3 * h.params[2]; }
+        else { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = h.params[3]; d.p[4] = 2 * h.params[2]; d.p[5] = 3 * h.params[2]; d.p[6] = h.params[4]; }
+        if (d.small) small.push_back(int32_t(k));
+        c->h_ins.push_back(d);
+    }
+    CU(c->d_nodes.ensure(nodes.size()));
+    CU(c->d_tets.ensure(std::max<size_t>(tets.size(), 1)));
+    CU(c->d_tris.ensure(std::max<size_t>(tris.size(), 1)));
+    CU(c->d_ins.ensure(c->h_ins.size()));
+    CU(c->d_small.ensure(std::max<size_t>(small.size(), 1)));
+    CU(cudaMemcpy(c->d_nodes.p, nodes.data(), nodes.size() * sizeof(NodeRec), cudaMemcpyHostToDevice));
+    if (!tets.empty()) CU(cudaMemcpy(c->d_tets.p, tets.data(), tets.size() * sizeof(TetRec), cudaMemcpyHostToDevice));
+    if (!tris.empty()) CU(cudaMemcpy(c->d_tris.p, tris.data(), tris.size() * sizeof(TriRec), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_ins.p, c->h_ins.data(), c->h_ins.size() * sizeof(InsDev), cudaMemcpyHostToDevice));
+    if (!small.empty()) CU(cudaMemcpy(c->d_small.p, small.data(), small.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    c->scene.nodes = c->d_nodes.p; c->scene.tets = c->d_tets.p; c->scene.tris = c->d_tris.p; c->scene.ins = c->d_ins.p;
+    c->scene.small_ins = c->d_small.p;
+    c->scene.n_ins = int(c->h_ins.size()); c->scene.n_small = int(small.size()); c->scene.n_bristle = c->n_bristle;
+    c->max_env = max_env;
+    c->finalized = true;
+    return PFC_OK;
+}
+
+static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
+    EvalIO io = io_in;
+    const int n_ins = c->scene.n_ins;
+    if (c->scene.n_small != n_ins) return fail(PFC_E_ARG, "large-scene path not built yet");
+    if (c->keep_pairs) {
+        c->dbg_cap = kSmallCap;
+        CU(c->d_dbg_pairs.ensure(size_t(2) * c->dbg_cap * io.n_env * n_ins));
+        io.dbg_pairs = c->d_dbg_pairs.p;
+        io.dbg_cap = c->dbg_cap;
+        c->dbg_n_env = io.n_env;
+    } else { io.dbg_pairs = nullptr; io.dbg_cap = 0; }
+    int nl = 0;
+    CU(launch_eval_small_f64(c->scene, io, c->stream, &nl));
+    c->launches += nl;
+    c->last_X = io.X; c->last_tw = io.twist;
+    if (c->keep_pairs) {
+        CU(c->d_last_np.ensure(size_t(io.n_env) * n_ins));
+        CU(cudaMemcpyAsync(c->d_last_np.p, io.n_pairs, sizeof(long long) * io.n_env * n_ins, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return PFC_OK;
+}
+
+int pfc_eval_f64_device(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
+                        int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_f64_device: context not finalized");
+    if (n_env < 0 || !X || !twist || !wrench || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_f64_device: NULL buffer");
+    if (c->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_eval_f64_device: bristle instructions need s and sdot");
+    CU(cudaSetDevice(c->device));
+    EvalIO io{};
+    io.n_env = n_env; io.X = X; io.twist = twist; io.s = s; io.wrench = wrench; io.sdot = sdot;
+    io.n_pairs = reinterpret_cast<long long*>(n_pairs); io.flags = flags;
+    return eval_device(c, io);
+}
+
+int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot, int64_t* n_pairs,
+                 int32_t* flags) {
+    if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_f64: context not finalized");
+    if (n_env < 0 || !X || !twist || !wrench) return fail(PFC_E_ARG, "pfc_eval_f64: NULL buffer");
+    if (c->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_eval_f64: bristle instructions need s and sdot");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
+    CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni));
+    CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+    if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_sd.ensure(6 * ne * nb)); }
+    CU(cudaMemcpyAsync(c->d_X.p, X, sizeof(double) * 16 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_tw.p, twist, sizeof(double) * 6 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+    if (nb) CU(cudaMemcpyAsync(c->d_s.p, s, sizeof(double) * 6 * ne * nb, cudaMemcpyHostToDevice, c->stream));
+    EvalIO io{};
+    io.n_env = n_env; io.X = c->d_X.p; io.twist = c->d_tw.p; io.s = nb ? c->d_s.p : nullptr; io.wrench = c->d_w.p;
+    io.sdot = nb ? c->d_sd.p : nullptr; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
+    int rc = eval_device(c, io);
+    if (rc != PFC_OK) return rc;
+    CU(cudaMemcpyAsync(wrench, c->d_w.p, sizeof(double) * 6 * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    if (nb) CU(cudaMemcpyAsync(sdot, c->d_sd.p, sizeof(double) * 6 * ne * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int32_t> fl_local;
+    int32_t* fl = flags;
+    if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
+    CU(cudaMemcpyAsync(fl, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < ne * ni; ++k) {
+        if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
+        if (fl[k] & PFC_FLAG_OVERFLOW) return fail(PFC_E_CAPACITY, "candidate-pair capacity exceeded");
+    }
+    return PFC_OK;
+}
+
+int pfc_eval_dual6(pfc_ctx*, int64_t, const double*, const double*, const double*, const double*, double*, double*, int64_t*, int32_t*) {
+    return fail(PFC_E_ARG, "pfc_eval_dual6: not built yet");
+}
+
+int pfc_set_debug(pfc_ctx* c, int keep_pairs) {
+    if (!c) return fail(PFC_E_ARG, "pfc_set_debug: NULL context");
+    c->keep_pairs = keep_pairs != 0;
+    return PFC_OK;
+}
+
+int pfc_get_pairs(pfc_ctx* c, int64_t env, int ins, int32_t* pairs, int64_t cap, int64_t* n_out) {
+    if (!c || !c->finalized || !c->keep_pairs || !c->d_dbg_pairs.p) return fail(PFC_E_ARG, "pfc_get_pairs: call pfc_set_debug(ctx, 1) before evaluating");
+    if (env < 0 || env >= c->dbg_n_env || ins < 0 || ins >= c->scene.n_ins) return fail(PFC_E_ARG, "pfc_get_pairs: index out of range");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const int64_t ei = env * c->scene.n_ins + ins;
+    long long n = 0;
+    CU(cudaMemcpy(&n, c->d_last_np.p + ei, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
+    const int64_t m = std::min<int64_t>(std::min<int64_t>(n, cap), c->dbg_cap);
+    if (pairs && m > 0) CU(cudaMemcpy(pairs, c->d_dbg_pairs.p + 2 * int64_t(c->dbg_cap) * ei, sizeof(int32_t) * 2 * m, cudaMemcpyDeviceToHost));
+    return PFC_OK;
+}
+
+int pfc_get_traction(pfc_ctx* c, int64_t env, int ins, double* out, int64_t cap_points, int64_t* n_out) {
+    if (!c || !c->finalized || !c->keep_pairs || !c->d_dbg_pairs.p) return fail(PFC_E_ARG, "pfc_get_traction: call pfc_set_debug(ctx, 1) before evaluating");
+    if (env < 0 || env >= c->dbg_n_env || ins < 0 || ins >= c->scene.n_ins) return fail(PFC_E_ARG, "pfc_get_traction: index out of range");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const int64_t ei = env * c->scene.n_ins + ins;
+    long long n = 0;
+    CU(cudaMemcpy(&n, c->d_last_np.p + ei, sizeof(long long), cudaMemcpyDeviceToHost));
+    const int cap = int(std::max<int64_t>(cap_points, 1));
+    DevBuf<double> d_out; DevBuf<int> d_n;
+    CU(d_out.ensure(size_t(8) * cap)); CU(d_n.ensure(1));
+    EvalIO io{};
+    io.X = c->last_X; io.twist = c->last_tw;
+    CU(launch_dump_traction(c->scene, io, env, ins, c->d_dbg_pairs.p + 2 * int64_t(c->dbg_cap) * ei, n, d_out.p, cap, d_n.p, c->stream));
+    c->launches += 1;
+    int np = 0;
+    CU(cudaMemcpyAsync(&np, d_n.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_out) *n_out = np;
+    const int m = std::min(np, cap);
+    if (out && m > 0 && cap_points > 0) CU(cudaMemcpy(out, d_out.p, sizeof(double) * 8 * m, cudaMemcpyDeviceToHost));
+    d_out.release(); d_n.release();
+    return PFC_OK;
+}
+
+int pfc_set_shard(pfc_ctx* c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return fail(PFC_E_ARG, "pfc_set_shard: bad rank/world");
+    c->shard_rank = rank; c->shard_world = world;
+    return PFC_OK;
+}
+
+int pfc_sync(pfc_ctx* c) {
+    if (!c) return fail(PFC_E_ARG, "pfc_sync: NULL context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return PFC_OK;
+}
+
+void* pfc_stream(pfc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t pfc_launch_count(pfc_ctx* c) { return c ? c->launches : 0; }
+int pfc_counters(pfc_ctx*, int64_t* a, int64_t* b) { if (a) *a = 0; if (b) *b = 0; return PFC_OK; }
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// pfc_launch.h -- host-side launchers of the kernels (implemented in the .cu files).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pfc_types.cuh"
+
+namespace pfc {
+
+struct EvalIO {
+    long long n_env;
+    const double* X;      // [env][ins][16] col-major x_r2_r1
+    const double* twist;  // [env][ins][6]  angular, linear
+    const double* s;      // [env][bristle][6] or nullptr
+    double* wrench;       // [env][ins][6]
+    double* sdot;         // [env][bristle][6] or nullptr
+    long long* n_pairs;   // [env][ins]
+    int* flags;           // [env][ins]
+    int* dbg_pairs;       // optional [env*n_ins][dbg_cap][2] (prim ids, DFS order) or nullptr
+    int dbg_cap;
+};
+
+constexpr int kSmallCap = 512;      // frontier / pair capacity of the fused small path
+constexpr int kSmallWarps = 4;      // warps (= instructions in flight) per CTA
+
+cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, cudaStream_t stream, int* n_launches);
+
+// single-thread debug kernel: re-runs the narrow phase of one (env, ins) over a given pair list in
+// order and writes the traction points (8 doubles each) -- the reference's TractionCache.
+cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long env, int ins, const int* pairs, long long n_pairs, double* out,
+                                 int cap_points, int* n_points, cudaStream_t stream);
+
+}  // namespace pfc

@@ -1,0 +1,253 @@
+// pfc_patch.cuh -- per-pair narrow phase: clip -> polygon fan -> pressure quadrature -> traction.
+//
+// Reference (paths relative to /root/reference):
+//   tri-tet pair ....... integrate_over!  src/contact_algorithms_non_friction.jl:196-215
+//   tet-tet pair ....... integrate_over!  src/contact_algorithms_non_friction.jl:166-194
+//   polygon fan ........ integrate_over_polygon_patch!  :217-234,  centroid  src/clip/poly_eight.jl:35-52
+//   pressure law ....... fillTractionCacheInnerLoop!  :251-265
+//   regularized law .... traction / yes_contact!  src/contact_algorithms_friction.jl:13-30, 50-72
+//   bristle passes ..... normal_wrench_cop  src/contact_algorithms_normal.jl:17-34,
+//                        calc_patch_spatial_stiffness!  friction.jl:147-169,
+//                        calc_spatial_bristle_force  friction.jl:171-201, traction(::Bristle) :32-48
+// The reference materialises a TractionCache list between the narrow phase and friction; here
+// every quadrature point is consumed immediately by an accumulator (Accum::point) so nothing is
+// written to memory.  The bristle model needs three passes over the points (centre of pressure ->
+// stiffness -> friction); the passes re-run the narrow phase with a different accumulator mode.
+#pragma once
+#include "pfc_clip.cuh"
+#include "pfc_math.cuh"
+#include "pfc_types.cuh"
+
+namespace pfc {
+
+// XiaoGimbutas triangle rules 1 and 2 (src/clip/quadrature.jl:21-41)
+#define PFC_Q1 0.33333333333333331483
+#define PFC_QA 0.16666666666666674068
+#define PFC_QB 0.66666666666666651864
+
+enum AccMode { ACC_REGULARIZED = 0, ACC_COP = 1, ACC_STIFFNESS = 2, ACC_BRISTLE = 3, ACC_DUMP = 4 };
+
+// per (environment, instruction) data in mode T
+template <class T> struct PatchCtx {
+    Xform<T> x21;   // x_r2_r1: mesh-1 frame -> mesh-2 frame
+    Xform<T> x12;   // its inverse (tet-tet only)
+    Vec3<T> w_ang, w_lin;  // twist of r2 w.r.t. r1, expressed in r2
+    double chi, Ebar1, Ebar2;
+    int n_quad;
+};
+
+template <class T> PFC_D T clamped_piecewise(const T& x, double x1, double x2, double y1, double y2) {
+    const double k = (y2 - y1) / (x2 - x1);
+    const T y = y1 + (x - x1) * k;
+    if (val(y) > y1) return T(y1);  // clamp(y, y2, y1): y2 <= y1
+    if (val(y) < y2) return T(y2);
+    return y;
+}
+
+template <class T> PFC_D Vec3<T> sub_proj(const Vec3<T>& v, const Vec3<T>& n) {  // vec_sub_vec_proj (muladd form)
+    const T t = -dot(v, n);
+    return mk<T>(fma_(t, n.x, v.x), fma_(t, n.y, v.y), fma_(t, n.z, v.z));
+}
+
+template <class T> struct Accum {
+    int mode;
+    int n_points;
+    T a[21];
+    const double* fp;   // friction parameters (InsDev::p)
+    Vec3<T> w_ang, w_lin;
+    Vec3<T> cop;
+    T delta[6];         // bristle deformation (angular, linear)
+    double* dump;       // ACC_DUMP: 8 doubles per point
+    int dump_cap;
+
+    PFC_D void reset(int m) {
+        mode = m; n_points = 0;
+#pragma unroll
+        for (int k = 0; k < 21; ++k) a[k] = T(0.0);
+    }
+
+    PFC_D void point(const Vec3<T>& n, const Vec3<T>& r, const T& dA, const T& p) {
+        const T p_dA = p * dA;
+        if (mode == ACC_REGULARIZED) {
+            const Vec3<T> vel = w_lin + cross(w_ang, r);
+            const Vec3<T> vt = sub_proj(vel, n);
+            const T mag2 = dot(vt, vt);
+            const double mu_s = fp[0], v_c = fp[2];
+            Vec3<T> Tc;
+            if (val(mag2) < v_c * v_c) {
+                const double s = -mu_s;
+                Tc = mk<T>(vt.x * s / v_c, vt.y * s / v_c, vt.z * s / v_c);
+            } else {
+                const T mag = sqrt_(mag2);
+                const T mu = -clamped_piecewise(mag, fp[3], fp[4], mu_s, fp[1]);
+                Tc = mk<T>(mu * vt.x / mag, mu * vt.y / mag, mu * vt.z / mag);
+            }
+            const Vec3<T> tk = mk<T>(p_dA * n.x + Tc.x * p_dA, p_dA * n.y + Tc.y * p_dA, p_dA * n.z + Tc.z * p_dA);
+            const Vec3<T> m = cross(r, tk);
+            a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += tk.x; a[4] += tk.y; a[5] += tk.z;
+        } else if (mode == ACC_COP) {
+            const Vec3<T> lam = n * p_dA;
+            const Vec3<T> m = cross(r, lam);
+            a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += lam.x; a[4] += lam.y; a[5] += lam.z;
+            a[6] += p_dA;
+            a[7] += p_dA * r.x; a[8] += p_dA * r.y; a[9] += p_dA * r.z;
+        } else if (mode == ACC_STIFFNESS) {
+            // K11 upper (0..5), K12 full row-major (6..14), K22 upper (15..20); k_bar applied by the caller
+            const Vec3<T> q = r - cop;
+            const Vec3<T> c = cross(q, n);
+            const T q0 = q.x * q.x, q1 = q.y * q.y, q2 = q.z * q.z;
+            // K11 -= p_dA * ([q]x^2 + c c')
+            a[0] -= p_dA * ((-q1 - q2) + c.x * c.x);
+            a[1] -= p_dA * (q.x * q.y + c.x * c.y);
+            a[2] -= p_dA * (q.x * q.z + c.x * c.z);
+            a[3] -= p_dA * ((-q0 - q2) + c.y * c.y);
+            a[4] -= p_dA * (q.y * q.z + c.y * c.z);
+            a[5] -= p_dA * ((-q0 - q1) + c.z * c.z);
+            // K12 += p_dA * ([q]x - c n')
+            a[6] += p_dA * (-(c.x * n.x));
+            a[7] += p_dA * (-q.z - c.x * n.y);
+            a[8] += p_dA * (q.y - c.x * n.z);
+            a[9] += p_dA * (q.z - c.y * n.x);
+            a[10] += p_dA * (-(c.y * n.y));
+            a[11] += p_dA * (-q.x - c.y * n.z);
+            a[12] += p_dA * (-q.y - c.z * n.x);
+            a[13] += p_dA * (q.x - c.z * n.y);
+            a[14] += p_dA * (-(c.z * n.z));
+            // K22 += p_dA * (I - n n')
+            a[15] += p_dA * (1.0 - n.x * n.x);
+            a[16] += p_dA * (-(n.x * n.y));
+            a[17] += p_dA * (-(n.x * n.z));
+            a[18] += p_dA * (1.0 - n.y * n.y);
+            a[19] += p_dA * (-(n.y * n.z));
+            a[20] += p_dA * (1.0 - n.z * n.z);
+        } else if (mode == ACC_BRISTLE) {
+            // fp: tau, k_bar, mu_s, mu_d, Ts_mu_s, Ts_mu_d, magic
+            const Vec3<T> x2 = r - cop;
+            const Vec3<T> d_ang = mk<T>(delta[0], delta[1], delta[2]);
+            const Vec3<T> d_lin = mk<T>(delta[3], delta[4], delta[5]);
+            const Vec3<T> dl = d_lin + cross(d_ang, x2);
+            const Vec3<T> rd = w_lin + cross(w_ang, r);
+            const double tau = fp[0], nk = -fp[1], mu_s = fp[2];
+            Vec3<T> Ts = mk<T>((dl.x + rd.x * tau) * nk, (dl.y + rd.y * tau) * nk, (dl.z + rd.z * tau) * nk);
+            Ts = sub_proj(Ts, n);
+            const T mag2 = dot(Ts, Ts);
+            Vec3<T> Tc;
+            if (val(mag2) < mu_s * mu_s) {
+                Tc = Ts;
+            } else {
+                const T mag = sqrt_(mag2);
+                const T mu = clamped_piecewise(mag, fp[4], fp[5], mu_s, fp[3]);
+                Tc = mk<T>(mu * Ts.x / mag, mu * Ts.y / mag, mu * Ts.z / mag);
+            }
+            Tc = Tc * p_dA;
+            const Vec3<T> m = cross(x2, Tc);
+            a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += Tc.x; a[4] += Tc.y; a[5] += Tc.z;
+        } else {  // ACC_DUMP (debug / parity): n(3) r(3) dA p, values only
+            if (n_points < dump_cap) {
+                double* o = dump + 8 * n_points;
+                o[0] = val(n.x); o[1] = val(n.y); o[2] = val(n.z); o[3] = val(r.x); o[4] = val(r.y); o[5] = val(r.z);
+                o[6] = val(dA); o[7] = val(p);
+            }
+        }
+        ++n_points;
+    }
+};
+
+// Polygon (tetrahedral coordinates of tet 2) -> centroid fan -> quadrature points
+template <class T> __device__ __noinline__ void integrate_polygon(const Zeta<T>* z, int n, const Vec3<T>& nrm, const TetRec& tet, const PatchCtx<T>& cx,
+                                                                  Accum<T>& acc) {
+    Vec3<T> pr[8];
+    for (int k = 0; k < n; ++k) {  // mul_then_un_pad(x_r2_zeta2, .)
+        const T z0 = z[k].c[0], z1 = z[k].c[1], z2 = z[k].c[2], z3 = z[k].c[3];
+        pr[k] = mk<T>(tet.v[0] * z0 + tet.v[3] * z1 + tet.v[6] * z2 + tet.v[9] * z3, tet.v[1] * z0 + tet.v[4] * z1 + tet.v[7] * z2 + tet.v[10] * z3,
+                      tet.v[2] * z0 + tet.v[5] * z1 + tet.v[8] * z2 + tet.v[11] * z3);
+    }
+    // area-weighted centroid, fan from vertex 0
+    T cum_sum = T(0.0);
+    Vec3<T> cum = mk<T>(T(0.0), T(0.0), T(0.0));
+    for (int k = 2; k < n; ++k) {
+        const Vec3<T> a = pr[0], b = pr[k - 1], c = pr[k];
+        const T area = dot(nrm, cross(b - a, c - b) * 0.5);
+        const Vec3<T> cen = (a + b + c) * (1.0 / 3.0);
+        cum = cum + cen * area;
+        cum_sum += area;
+    }
+    Vec3<T> cen = pr[0];
+    if (val(cum_sum) != 0.0) { const T inv = 1.0 / cum_sum; cen = mk<T>(cum.x * inv, cum.y * inv, cum.z * inv); }
+    const Vec3<double> grad = mk<double>(tet.eps_r[0], tet.eps_r[1], tet.eps_r[2]);
+    Vec3<T> v2 = pr[n - 1];
+    for (int k = 0; k < n; ++k) {
+        const Vec3<T> v1 = v2;
+        v2 = pr[k];
+        const T area = dot(nrm, cross(v2 - v1, cen - v2) * 0.5);
+        if (!(0.0 < val(area))) continue;
+        for (int q = 0; q < cx.n_quad; ++q) {
+            double za, zb, zc, w;
+            if (cx.n_quad == 1) { za = zb = zc = PFC_Q1; w = 1.0; }
+            else { za = (q == 1) ? PFC_QB : PFC_QA; zb = (q == 0) ? PFC_QB : PFC_QA; zc = (q == 2) ? PFC_QB : PFC_QA; w = PFC_Q1; }
+            const Vec3<T> r = mk<T>(v1.x * za + v2.x * zb + cen.x * zc, v1.y * za + v2.y * zb + cen.y * zc, v1.z * za + v2.z * zb + cen.z * zc);
+            T eps = fma_(grad.x, r.x, tet.eps_r[3]);
+            eps = fma_(grad.y, r.y, eps);
+            eps = fma_(grad.z, r.z, eps);
+            const Vec3<T> rd = cx.w_lin + cross(cx.w_ang, r);
+            const T ee = -(grad.x * rd.x + grad.y * rd.y + grad.z * rd.z);
+            T damp = 1.0 + cx.chi * ee;
+            if (val(damp) < 0.0) damp = T(0.0);
+            const T p = eps * cx.Ebar2 * damp;
+            if (0.0 < val(p)) acc.point(nrm, r, w * area, p);
+        }
+    }
+}
+
+// ---- triangle (mesh 1) against tetrahedron (mesh 2) --------------------------------------------------------
+template <class T> PFC_D void narrow_tri_tet(const TriRec& tri, const TetRec& tet, const PatchCtx<T>& cx, Accum<T>& acc, int& flags) {
+    Zeta<T> z[8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const Vec3<T> p = apply_d(cx.x21, mk<double>(tri.v[3 * k], tri.v[3 * k + 1], tri.v[3 * k + 2]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z[k].c[i] = tet.inv[4 * i] * p.x + tet.inv[4 * i + 1] * p.y + tet.inv[4 * i + 2] * p.z + tet.inv[4 * i + 3];
+    }
+    const int n = clip_tet(z, 3, flags);
+    if (n >= 3) {
+        const Vec3<T> nrm = rot_d(cx.x21, mk<double>(tri.n[0], tri.n[1], tri.n[2]));
+        integrate_polygon(z, n, nrm, tet, cx, acc);
+    }
+}
+
+// ---- tetrahedron (mesh 1) against tetrahedron (mesh 2) -----------------------------------------------------
+template <class T> PFC_D void narrow_tet_tet(const TetRec& t1, const TetRec& t2, const PatchCtx<T>& cx, Accum<T>& acc, int& flags) {
+    // plane of equal pressure in r2: E2 eps2 x_zeta2_r2 - E1 eps1 x_zeta1_r1 x_r1_r2
+    T plane[4];
+    {
+        const double g0 = cx.Ebar1 * t1.eps_r[0], g1 = cx.Ebar1 * t1.eps_r[1], g2 = cx.Ebar1 * t1.eps_r[2], g3 = cx.Ebar1 * t1.eps_r[3];
+        const Xform<T>& Y = cx.x12;
+        const T p0 = g0 * Y.r[0] + g1 * Y.r[3] + g2 * Y.r[6];
+        const T p1 = g0 * Y.r[1] + g1 * Y.r[4] + g2 * Y.r[7];
+        const T p2 = g0 * Y.r[2] + g1 * Y.r[5] + g2 * Y.r[8];
+        const T p3 = g0 * Y.t[0] + g1 * Y.t[1] + g2 * Y.t[2] + g3;
+        plane[0] = cx.Ebar2 * t2.eps_r[0] - p0;
+        plane[1] = cx.Ebar2 * t2.eps_r[1] - p1;
+        plane[2] = cx.Ebar2 * t2.eps_r[2] - p2;
+        plane[3] = cx.Ebar2 * t2.eps_r[3] - p3;
+    }
+    Vec3<T> v[4], poly[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = apply_d(cx.x21, mk<double>(t1.v[3 * k], t1.v[3 * k + 1], t1.v[3 * k + 2]));
+    const int n0 = plane_tet(plane, v, poly);
+    if (n0 < 3) return;
+    Zeta<T> z[8];
+    for (int k = 0; k < n0; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            z[k].c[i] = t2.inv[4 * i] * poly[k].x + t2.inv[4 * i + 1] * poly[k].y + t2.inv[4 * i + 2] * poly[k].z + t2.inv[4 * i + 3];
+    zero_small(z, n0);
+    const int n = clip_tet(z, n0, flags);
+    if (n >= 3) {
+        const T inv_len = 1.0 / sqrt_(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);
+        const Vec3<T> nrm = mk<T>(plane[0] * inv_len, plane[1] * inv_len, plane[2] * inv_len);
+        integrate_polygon(z, n, nrm, t2, cx, acc);
+    }
+}
+
+}  // namespace pfc

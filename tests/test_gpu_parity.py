@@ -1,0 +1,238 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bars: candidate-pair lists bit-exact (same pairs, same order); flags equal;
+wrenches and bristle state derivatives within 1e-9 relative (SURVEY.md H7 definition: per force /
+torque 3-vector, ||delta||_inf / ||ref||_inf, with an absolute floor for halves that vanish by symmetry)."""
+import numpy as np
+import pytest
+
+import pfc_b200  # noqa: F401
+from helpers import boxes_env_states, rot_z, scene_boxes, wrench_rel_err
+from oracle import orc
+from pfc_b200 import geometry as G
+from pfc_b200 import scenario as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-9
+
+
+def _ctx():
+    from pfc_b200 import capi
+    return capi.Context(0)
+
+
+def _both(build, n_env=1):
+    m_gpu = build(_ctx(), n_env)
+    m_cpu = build(orc.OracleContext(), n_env)
+    return m_gpu, m_cpu
+
+
+def _compare(m_gpu, m_cpu, X, tw, s=None, pairs=True, floor=1e-9):
+    g = m_gpu.backend.eval_f64(X, tw, s, keep=pairs)
+    c = m_cpu.backend.eval_f64(X, tw, s, keep=pairs)
+    assert (g["n_pairs"] == c["n_pairs"]).all()
+    assert (g["flags"] == c["flags"]).all()
+    scale = max(np.abs(c["wrench"]).max(), 1e-300)
+    assert wrench_rel_err(g["wrench"], c["wrench"], floor=floor * scale) <= TOL
+    if s is not None:
+        sc = max(np.abs(c["sdot"]).max(), 1e-300)
+        assert wrench_rel_err(g["sdot"], c["sdot"], floor=floor * sc) <= TOL
+    if pairs:
+        n_env, n_ins = c["n_pairs"].shape
+        for e in range(min(n_env, 16)):
+            for k in range(n_ins):
+                assert (m_gpu.backend.get_pairs(e, k) == m_cpu.backend.get_pairs(e, k)).all(), (e, k)
+    return g, c
+
+
+def test_boxes_batch_parity():
+    """Config C1/C3: test/boxes.jl scene, randomized settled-stack states."""
+    n_env = 256
+    m_gpu, m_cpu = _both(lambda b, n: scene_boxes(b, n)[0], n_env)
+    x = boxes_env_states(m_gpu, n_env)
+    X, tw, _ = S.boundary_arrays(m_gpu, x)
+    g, c = _compare(m_gpu, m_cpu, X, tw)
+    assert (c["flags"] & 1).sum() > n_env  # plenty of contacts in the sample
+    assert c["n_pairs"].max() <= 144
+    # traction lists (the reference's TractionCache) of one environment, point by point
+    for k in range(4):
+        tg, tc = m_gpu.backend.get_traction(3, k), m_cpu.backend.get_traction(3, k)
+        assert tg.shape == tc.shape
+        if len(tc):
+            assert np.allclose(tg, tc, rtol=1e-9, atol=1e-12 * np.abs(tc).max())
+
+
+def test_boxes_initial_state_no_contact():
+    """test/boxes.jl:42-45 initial state: boxes spaced 3 r apart, nothing touches; wrenches are zero."""
+    m_gpu, m_cpu = _both(lambda b, n: scene_boxes(b, n)[0])
+    X, tw, _ = S.boundary_arrays(m_gpu, S.get_state(m_gpu))
+    g, c = _compare(m_gpu, m_cpu, X, tw)
+    assert (g["wrench"] == 0).all() and (g["flags"] == 0).all()
+
+
+def _normal_scene(k_quad_rule):
+    def build(backend, n_env):
+        r = 0.05
+        m = S.MechanismScenario()
+        id_plane = S.add_contact(m, "plane", G.as_tet_eMesh(G.eMesh_half_plane()), c_prop=S.ContactProperties(1.0e9))
+        eM_box = G.transform(G.as_tri_eMesh(G.eMesh_box(r)), t=(0.0, 0.0, r))
+        body, _, id_box = S.add_body_contact(m, "box", eM_box, i_prop=S.InertiaProperties(400.0, d=0.09))
+        S.add_friction_bristle(m, id_box, id_plane, mu_d=0.3, chi=0.6, k_bar=1.0e6, tau=0.03, n_quad_rule=k_quad_rule)
+        S.finalize(m, backend, n_env)
+        m.box_body = body
+        return m
+    return build
+
+
+@pytest.mark.parametrize("k_quad_rule", [1, 2])
+def test_normal_wrench_kat_on_gpu(k_quad_rule):
+    """test/test_normal.jl through the CUDA path: analytic answer AND oracle parity (bristle model)."""
+    m_gpu, m_cpu = _both(_normal_scene(k_quad_rule))
+    r, p_pos = 0.05, (0.1, 0.2)
+    pene = 0.1 * r
+    for m in (m_gpu, m_cpu):
+        S.set_state_spq(m, m.box_body, trans=(p_pos[0], p_pos[1], -pene))
+    X, tw, s = S.boundary_arrays(m_gpu, S.get_state(m_gpu))
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, 1, 6))
+    check = 1.0e9 * pene * r ** 2 * 4
+    f3 = np.array([0.0, 0.0, check])
+    assert np.allclose(g["wrench"][0, 0], -np.concatenate([np.cross([p_pos[0], p_pos[1], 0.0], f3), f3]), rtol=1e-10)
+
+
+def test_bristle_sliding_batch():
+    """Bristle friction with non-zero bristle state, sliding and spinning box: wrench and s-dot."""
+    n_env = 64
+    m_gpu, m_cpu = _both(_normal_scene(2), n_env)
+    rng = np.random.default_rng(42)
+    x = np.zeros((n_env, S.num_x(m_gpu)))
+    r = 0.05
+    for e in range(n_env):
+        x[e, 0:3] = rng.uniform(-0.03, 0.03, 3)
+        x[e, 3:6] = [rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), -rng.uniform(0.0, 0.1) * r]
+        x[e, 6:9] = rng.uniform(-1, 1, 3)
+        x[e, 9:12] = rng.uniform(-0.1, 0.1, 3)
+        x[e, 12:18] = rng.uniform(-1, 1, 6) * np.array([1e-3, 1e-3, 1e-3, 1e-5, 1e-5, 1e-5])
+    x[0, 3:6] = [0, 0, 0.01]  # one environment out of contact: no_contact!(::Bristle)
+    X, tw, s = S.boundary_arrays(m_gpu, x)
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
+    assert c["flags"][0, 0] == 0 and np.allclose(g["sdot"][0, 0], -x[0, 12:18] / 0.03)
+    assert (c["flags"][1:, 0] & 1).all()
+
+
+def _tet_tet_scene(backend, n_env):
+    r = 0.05
+    c_prop = S.ContactProperties(1.0e6)
+    m = S.MechanismScenario()
+    id_plane = S.add_contact(m, "plane", G.as_tet_eMesh(G.eMesh_half_plane()), c_prop=c_prop)
+    b1 = S.add_body_contact(m, "box_1", G.as_tet_eMesh(G.eMesh_box(r)), i_prop=S.InertiaProperties(400.0), c_prop=c_prop)
+    b2 = S.add_body_contact(m, "box_2", G.as_tet_eMesh(G.eMesh_box(r)), i_prop=S.InertiaProperties(400.0), c_prop=S.ContactProperties(3.0e6))
+    S.add_friction_regularize(m, id_plane, b1[2], mu_d=0.0, chi=0.0, n_quad_rule=2)
+    S.add_friction_regularize(m, b1[2], b2[2], mu_s=0.4, mu_d=0.3, chi=0.7, v_tol=1e-3, n_quad_rule=2)
+    S.add_friction_bristle(m, b2[2], b1[2], mu_d=0.3, chi=0.3, k_bar=1.0e5, tau=0.02, n_quad_rule=1)
+    S.finalize(m, backend, n_env)
+    return m
+
+
+def test_tet_tet_batch_parity():
+    """test/test_vol_vol.jl-style volumetric contact (tet-tet), regularized and bristle."""
+    n_env = 128
+    m_gpu, m_cpu = _both(_tet_tet_scene, n_env)
+    rng = np.random.default_rng(7)
+    r = 0.05
+    x = np.zeros((n_env, S.num_x(m_gpu)))
+    nq = m_gpu.nq
+    for e in range(n_env):
+        x[e, 0:3] = rng.uniform(-0.05, 0.05, 3)
+        x[e, 3:6] = [rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01), r - rng.uniform(0, 0.004)]
+        x[e, 6:9] = rng.uniform(-0.05, 0.05, 3)
+        x[e, 9:12] = [rng.uniform(-0.03, 0.03), rng.uniform(-0.03, 0.03), 3 * r - rng.uniform(0, 0.008)]
+        x[e, nq:nq + 12] = rng.uniform(-1, 1, 12) * 0.2
+        x[e, nq + 12:] = rng.uniform(-1, 1, 6) * 1e-4
+    X, tw, s = S.boundary_arrays(m_gpu, x)
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
+    assert (c["flags"] & 1).sum() > n_env
+
+
+def _single_pair_scene(kind1):
+    """One primitive against one tetrahedron: every environment is one random clip problem."""
+    def build(backend, n_env):
+        rng = np.random.default_rng(2024)
+        m = S.MechanismScenario()
+        while True:
+            t2 = rng.standard_normal((4, 3)) * 0.1
+            if G.tet_volume(t2) > 1e-5:
+                break
+        tet2 = G.eMesh(t2, None, [[0, 1, 2, 3]], [0.0, 0.0, 0.0, 1.0])
+        id2 = S.add_contact(m, "tet2", tet2, c_prop=S.ContactProperties(1.0e6))
+        if kind1 == 0:
+            tri = G.eMesh(rng.standard_normal((3, 3)) * 0.2, [[0, 1, 2]])
+            b = S.add_body_contact(m, "tri", tri, i_prop=S.InertiaProperties(400.0, d=0.01), tree=G.eMesh_to_tree(tri))
+        else:
+            while True:
+                t1 = rng.standard_normal((4, 3)) * 0.1
+                if G.tet_volume(t1) > 1e-5:
+                    break
+            b = S.add_body_contact(m, "tet1", G.eMesh(t1, None, [[0, 1, 2, 3]], [0.0, 1.0, 0.0, 0.0]), i_prop=S.InertiaProperties(400.0),
+                                   c_prop=S.ContactProperties(2.0e6))
+        S.add_friction_regularize(m, b[2], id2, mu_s=0.5, mu_d=0.3, chi=0.4, v_tol=1e-2, n_quad_rule=2)
+        S.finalize(m, backend, n_env)
+        return m
+    return build
+
+
+@pytest.mark.parametrize("kind1", [0, 1])
+def test_random_single_pair_clip_stress(kind1):
+    """Thousands of random relative poses of one triangle / tetrahedron against one tetrahedron:
+    exercises every arity of the clipper (3..8 vertices) and every plane-tet case."""
+    n_env = 8192
+    m_gpu, m_cpu = _both(_single_pair_scene(kind1), n_env)
+    rng = np.random.default_rng(99)
+    x = np.zeros((n_env, S.num_x(m_gpu)))
+    x[:, 0:3] = rng.uniform(-0.6, 0.6, (n_env, 3))
+    x[:, 3:6] = rng.uniform(-0.12, 0.12, (n_env, 3))
+    x[:, 6:12] = rng.uniform(-1, 1, (n_env, 6))
+    X, tw, _ = S.boundary_arrays(m_gpu, x)
+    g, c = _compare(m_gpu, m_cpu, X, tw, pairs=False, floor=1e-7)
+    assert (c["flags"] & 1).sum() > n_env // 20
+    assert (c["n_pairs"] == 0).any() and (c["n_pairs"] == 1).any()
+
+
+def test_sphere_small_path():
+    """Curved meshes on the small path: icosahedron-level spheres (20 x 20 leaf pairs), tri-tet and tet-tet."""
+    def build(backend, n_env):
+        m = S.MechanismScenario()
+        sph = G.eMesh_sphere(0.05, 1)
+        ground = S.add_contact(m, "ground", G.as_tet_eMesh(G.eMesh_sphere(0.08, 1)), c_prop=S.ContactProperties(2.0e6))
+        b1 = S.add_body_contact(m, "s_tri", G.as_tri_eMesh(sph), i_prop=S.InertiaProperties(400.0, d=0.01))
+        b2 = S.add_body_contact(m, "s_tet", G.as_tet_eMesh(sph), i_prop=S.InertiaProperties(400.0), c_prop=S.ContactProperties(1.0e6))
+        S.add_friction_regularize(m, b1[2], ground, mu_d=0.3, chi=0.5, n_quad_rule=1)
+        S.add_friction_regularize(m, b2[2], ground, mu_d=0.3, chi=0.5, n_quad_rule=2)
+        S.add_friction_bristle(m, b1[2], b2[2], mu_d=0.4, k_bar=2.0e4, tau=0.05, n_quad_rule=2)
+        S.finalize(m, backend, n_env)
+        return m
+    n_env = 96
+    m_gpu, m_cpu = _both(build, n_env)
+    rng = np.random.default_rng(5)
+    x = np.zeros((n_env, S.num_x(m_gpu)))
+    nq = m_gpu.nq
+    for e in range(n_env):
+        d1 = rng.standard_normal(3); d1 /= np.linalg.norm(d1)
+        d2 = rng.standard_normal(3); d2 /= np.linalg.norm(d2)
+        x[e, 0:3] = rng.uniform(-0.3, 0.3, 3)
+        x[e, 3:6] = d1 * rng.uniform(0.10, 0.128)
+        x[e, 6:9] = rng.uniform(-0.3, 0.3, 3)
+        x[e, 9:12] = x[e, 3:6] + d2 * rng.uniform(0.07, 0.098) if e % 2 else d2 * rng.uniform(0.10, 0.128)
+        x[e, nq:nq + 12] = rng.uniform(-1, 1, 12) * 0.3
+        x[e, nq + 12:] = rng.uniform(-1, 1, 6) * 1e-4
+    X, tw, s = S.boundary_arrays(m_gpu, x)
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
+    assert (c["flags"] & 1).sum() > n_env // 2
+
+
+def test_determinism_bitwise():
+    """Fixed-order reduction: two evaluations of the same batch are bitwise identical."""
+    n_env = 512
+    m_gpu = scene_boxes(_ctx(), n_env)[0]
+    X, tw, _ = S.boundary_arrays(m_gpu, boxes_env_states(m_gpu, n_env))
+    a = m_gpu.backend.eval_f64(X, tw, None)
+    b = m_gpu.backend.eval_f64(X, tw, None)
+    assert (a["wrench"].view(np.int64) == b["wrench"].view(np.int64)).all()
