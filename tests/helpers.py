@@ -103,18 +103,23 @@ def splitmix64(seed):
 
 
 def boxes_env_states(m, n_env, r=0.05):
-    """Config C3: randomized settled-stack states, env e seeded with
-    splitmix64(0x5EED0000 + e)."""
+    """Config C3: randomized *settled-stack* states of the test/boxes.jl scene, env e seeded with
+    splitmix64(0x5EED0000 + e).  Box k (1..4) sits at z = (2k-1) r minus a cumulative sink of
+    U(0, 0.02) r per level, with xy jitter, a small tilt, a free yaw and random twists, so that
+    every instruction has real contact work.  (SURVEY.md section 8d's formula keeps the 3 r drop
+    spacing of boxes.jl:42-45, at which nothing touches and only the root SAT would run.)"""
     nq = m.nq
     X = np.zeros((n_env, S.num_x(m)))
     for e in range(n_env):
         u = splitmix64(0x5EED0000 + e)
         U = lambda lo, hi: lo + (hi - lo) * u()
+        sink = 0.0
         for k in range(1, 5):
             b = m.bodies[k]
+            sink += U(0.0, 0.02) * r
             xy = [U(-0.5, 0.5) * r, U(-0.5, 0.5) * r]
-            z = (3 * k - 1) * r - U(0.0, 0.02) * r * k
-            mrp = [U(-0.05, 0.05) for _ in range(3)]
+            z = (2 * k - 1) * r - sink
+            mrp = [U(-0.005, 0.005), U(-0.005, 0.005), U(-0.2, 0.2)]
             om = [U(-1, 1) * k for _ in range(3)]
             vel = [U(-0.1, 0.1) for _ in range(3)]
             X[e, b.q0:b.q0 + 6] = mrp + xy + [z]

@@ -26,16 +26,54 @@ def _both(build, n_env=1):
     return m_gpu, m_cpu
 
 
-def _compare(m_gpu, m_cpu, X, tw, s=None, pairs=True, floor=1e-9):
+def _sdot_metric_err(m_cpu, c, g, n_env):
+    """s-dot parity with a conditioning-aware bar (worst error / allowed; <= 1 passes).
+
+    s-dot = -(Kb^-1/2 S^-1 w + s) / tau with Kb^-1/2 = V diag(1 / sqrt(max(lambda, 1e-16 lambda_max))) V'
+    (friction.jl:85-96).  Kb's entries carry eps-level rounding, so an eigenvalue rho * lambda_max is
+    known to a relative eps / rho only; and decompose_K! scales the rotational block by magic^2 =
+    1e-6, so rho_min <= ~1e-6 for EVERY patch.  Flat or tiny patches are rank deficient: their noise
+    eigenvalues hit the 1e-16 clamp (sigma = 1e8 / sqrt(lambda_max)) and eps-level eigenvector
+    rotations leak that 1e8 into every component.  tests/test_oracle_scene.py::
+    test_sdot_reproducibility_vs_lapack measures this on the CPU: a numpy/LAPACK restatement of the
+    reference's formula (LAPACK is what the reference itself calls) differs from the oracle by up to
+    ~1e-5 relative on such patches.  The bar is therefore 1e-9 + 1e3 eps / rho_min for full-rank
+    patches and 1e-4 for rank-deficient ones (rho_min < 1e-13); the wrench is always held to 1e-9."""
+    eps = np.finfo(float).eps
+    worst = 0.0
+    for k, ci in enumerate(m_cpu.ContactInstructions):
+        fm = ci.friction_model
+        if fm.model != 1:
+            continue
+        for e in range(n_env):
+            sg, sc = g["sdot"][e, fm.bristle_id], c["sdot"][e, fm.bristle_id]
+            if not (c["flags"][e, k] & 1):
+                assert np.allclose(sg, sc, rtol=1e-14, atol=0)
+                continue
+            _, _, K = orc.patch_stiffness(m_cpu.backend.get_traction(e, k), fm.k_bar)
+            Sinv, _ = orc.decompose_K(K, fm.magic)
+            Kf = np.triu(K) + np.triu(K, 1).T
+            lam = np.linalg.eigvalsh(np.diag(Sinv) @ Kf @ np.diag(Sinv))
+            rho_min = lam.min() / lam.max()
+            allowed = 1e-4 if rho_min < 1e-13 else TOL + 1e3 * eps / rho_min
+            worst = max(worst, np.abs(sg - sc).max() / max(np.abs(sc).max(), 1e-300) / allowed)
+    return worst
+
+
+def _compare(m_gpu, m_cpu, X, tw, s=None, pairs=True, floor=1e-9, sdot_metric=False):
+    keep = pairs or sdot_metric
     g = m_gpu.backend.eval_f64(X, tw, s, keep=pairs)
-    c = m_cpu.backend.eval_f64(X, tw, s, keep=pairs)
+    c = m_cpu.backend.eval_f64(X, tw, s, keep=keep)
     assert (g["n_pairs"] == c["n_pairs"]).all()
     assert (g["flags"] == c["flags"]).all()
     scale = max(np.abs(c["wrench"]).max(), 1e-300)
     assert wrench_rel_err(g["wrench"], c["wrench"], floor=floor * scale) <= TOL
     if s is not None:
-        sc = max(np.abs(c["sdot"]).max(), 1e-300)
-        assert wrench_rel_err(g["sdot"], c["sdot"], floor=floor * sc) <= TOL
+        if sdot_metric:
+            assert _sdot_metric_err(m_cpu, c, g, c["n_pairs"].shape[0]) <= 1.0
+        else:
+            sc = max(np.abs(c["sdot"]).max(), 1e-300)
+            assert wrench_rel_err(g["sdot"], c["sdot"], floor=floor * sc) <= TOL
     if pairs:
         n_env, n_ins = c["n_pairs"].shape
         for e in range(min(n_env, 16)):
@@ -148,7 +186,8 @@ def test_tet_tet_batch_parity():
         x[e, nq:nq + 12] = rng.uniform(-1, 1, 12) * 0.2
         x[e, nq + 12:] = rng.uniform(-1, 1, 6) * 1e-4
     X, tw, s = S.boundary_arrays(m_gpu, x)
-    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
+    # nearly flat box-box patches: stiffness eigenvalues ~1e-9 of the largest => conditioning-aware bar (_sdot_metric_err)
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6), sdot_metric=True)
     assert (c["flags"] & 1).sum() > n_env
 
 
@@ -224,7 +263,7 @@ def test_sphere_small_path():
         x[e, nq:nq + 12] = rng.uniform(-1, 1, 12) * 0.3
         x[e, nq + 12:] = rng.uniform(-1, 1, 6) * 1e-4
     X, tw, s = S.boundary_arrays(m_gpu, x)
-    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6), sdot_metric=True)  # tiny patches: rank-deficient stiffness
     assert (c["flags"] & 1).sum() > n_env // 2
 
 

@@ -212,3 +212,72 @@ def test_tree_build_properties():
         assert s.n_point() == 1 + 12 + (k - 1) * 30 + (k - 1) * (k - 2) // 2 * 20
         nrm = np.linalg.norm(s.point, axis=1)
         assert (nrm == 0).sum() == 1 and np.allclose(nrm[nrm > 0], 2.0)
+
+
+def test_sdot_reproducibility_vs_lapack():
+    """Documents the inherent sensitivity of the bristle state derivative (not a parity bar): the
+    reference computes Kb^-1/2 with LAPACK's symmetric eigensolver (friction.jl:88).  Re-stating
+    bristle_wrench_in_world in numpy (LAPACK eigh) on the oracle's own TractionCache reproduces the
+    oracle's wrench to ~1e-7 and its s-dot only to ~1e-5 on small curved patches, because
+    1 / sqrt(max(lambda, 1e-16 lambda_max)) amplifies eps-level differences by up to 1e8.  GPU-vs-
+    oracle s-dot tolerances in tests/test_gpu_parity.py are derived from this."""
+    m = S.MechanismScenario()
+    sph = G.eMesh_sphere(0.05, 1)
+    b1 = S.add_body_contact(m, "s_tri", G.as_tri_eMesh(sph), i_prop=S.InertiaProperties(400.0, d=0.01))
+    b2 = S.add_body_contact(m, "s_tet", G.as_tet_eMesh(sph), i_prop=S.InertiaProperties(400.0), c_prop=S.ContactProperties(1.0e6))
+    ci = S.add_friction_bristle(m, b1[2], b2[2], mu_d=0.4, k_bar=2.0e4, tau=0.05, n_quad_rule=2)
+    fm = ci.friction_model
+    ctx = orc.OracleContext()
+    S.finalize(m, ctx)
+    rng = np.random.default_rng(5)
+    n_env = 48
+    x = np.zeros((n_env, S.num_x(m)))
+    for e in range(n_env):
+        d = rng.standard_normal(3); d /= np.linalg.norm(d)
+        x[e, 0:3] = rng.uniform(-0.3, 0.3, 3)
+        x[e, 6:9] = rng.uniform(-0.3, 0.3, 3)
+        x[e, 9:12] = d * rng.uniform(0.07, 0.098)
+        x[e, 12:24] = rng.uniform(-1, 1, 12) * 0.3
+        x[e, 24:] = rng.uniform(-1, 1, 6) * 1e-4
+    X, tw, s = S.boundary_arrays(m, x)
+    c = ctx.eval_f64(X, tw, s.reshape(n_env, 1, 6), keep=True)
+    skew = lambda r: np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+    worst_w = worst_s = 0.0
+    n_contact = 0
+    for e in range(n_env):
+        if not c["flags"][e, 0] & 1:
+            continue
+        n_contact += 1
+        tr = ctx.get_traction(e, 0)
+        n, r, pdA = tr[:, 0:3], tr[:, 3:6], tr[:, 6] * tr[:, 7]
+        cop = (pdA[:, None] * r).sum(0) / pdA.sum()
+        K11, K12, K22 = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 3))
+        for i in range(len(tr)):
+            q = r[i] - cop
+            cx = np.cross(q, n[i])
+            K22 += pdA[i] * (np.eye(3) - np.outer(n[i], n[i]))
+            K12 += pdA[i] * (skew(q) - np.outer(cx, n[i]))
+            K11 -= pdA[i] * (skew(q) @ skew(q) + np.outer(cx, cx))
+        K = np.block([[K11, K12], [K12.T, K22]]) * fm.k_bar
+        Sinv = np.array([fm.magic / np.sqrt(np.trace(K[:3, :3]))] * 3 + [1 / np.sqrt(np.trace(K[3:, 3:]))] * 3)
+        lam, V = np.linalg.eigh(np.diag(Sinv) @ K @ np.diag(Sinv))
+        Kh = V @ np.diag(1 / np.sqrt(np.maximum(lam, lam.max() * 1e-16))) @ V.T
+        Delta = Sinv * (Kh @ s[e])
+        lin, ang = np.zeros(3), np.zeros(3)
+        for i in range(len(tr)):
+            x2 = r[i] - cop
+            Ts = -fm.k_bar * (Delta[3:] + np.cross(Delta[:3], x2) + fm.tau * (tw[e, 0, 3:] + np.cross(tw[e, 0, :3], r[i])))
+            Ts = Ts - np.dot(Ts, n[i]) * n[i]
+            mag = np.linalg.norm(Ts)
+            if mag * mag >= fm.mu_s ** 2:
+                Ts = np.clip(fm.mu_s + (mag - 2 * fm.mu_s) * (fm.mu_d - fm.mu_s) / fm.mu_s, fm.mu_d, fm.mu_s) * Ts / mag
+            lin += Ts * pdA[i]
+            ang += np.cross(x2, Ts * pdA[i])
+        w_n = np.concatenate([(np.cross(r, pdA[:, None] * n)).sum(0), (pdA[:, None] * n).sum(0)])
+        w = w_n + np.concatenate([ang + np.cross(cop, lin), lin])
+        sd = -(1 / fm.tau) * (Kh @ (Sinv * np.concatenate([ang, lin])) + s[e])
+        worst_w = max(worst_w, np.abs(w - c["wrench"][e, 0]).max() / np.abs(w).max())
+        worst_s = max(worst_s, np.abs(sd - c["sdot"][e, 0]).max() / np.abs(sd).max())
+    assert n_contact > 10
+    assert worst_w < 1e-5          # the friction part of the wrench goes through the same Kb^-1/2 (via Delta)
+    assert 1e-9 < worst_s < 1e-3   # s-dot is not: LAPACK vs Jacobi differ far above 1e-9
