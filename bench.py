@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- contact-wrench evaluations per second on the batched-environments workload.
+
+Workload (config C3 of BASELINE.json / SURVEY.md section 8d): 4096 independent copies of the
+reference's test/boxes.jl scene (1-tet half-space + 4 boxes alternately rigid/tri and
+compliant/tet, 4 regularized-friction contact instructions, quadrature rule 2) at randomized
+settled-stack states (tests/helpers.py::boxes_env_states).  One "step" = one pass of the hot
+path (forceAllElasticIntersections!, Float64 mode) over the whole batch; one "eval" = one
+environment.  Weak scaling: every GPU gets its own 4096 environments, no collective on the path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events on the
+library's stream, L2 flushed between steps); `e2e` = the same metric through pfc_eval_f64 with
+pinned HOST buffers (H2D + kernel + D2H inside the timed region); `roofline` = the fused kernel
+against the FP64 peak measured in this process; `cpu_baseline` = the CPU oracle (a C++ port of
+the reference algorithm, NOT Julia) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "contact_wrench_evals_per_sec"
+UNIT = "evals/s"
+
+
+def build_inputs(n_env, rank=0):
+    """Scene description (host mirror) + boundary arrays for n_env environments of this rank."""
+    import pfc_b200  # noqa: F401
+    from helpers import boxes_env_states, scene_boxes, splitmix64  # noqa: F401
+    from pfc_b200 import scenario as S
+    m, _ = scene_boxes(None)
+    # rank r gets environments [r * n_env, (r + 1) * n_env): seeds are a function of the global env index
+    x_all = boxes_env_states(m, n_env, start=rank * n_env)
+    X, tw, s = S.boundary_arrays(m, x_all)
+    return m, np.ascontiguousarray(X), np.ascontiguousarray(tw)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia
+    (not installable here, no Julia in the image), so this arm times the CPU oracle -- a literal C++
+    port of the same algorithm -- with all host threads, on the same workload, metric and unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import orc
+    from pfc_b200 import scenario as S
+    n_env = args.envs
+    m, X, tw = build_inputs(n_env)
+    cores = orc.lib().orc_max_threads()
+    ctx = orc.OracleContext(n_threads=cores)
+    S.attach_backend(m, ctx)
+    # each step = a bounded sample of the workload: the first `sample` environments of the batch
+    sample = min(n_env, 1024)
+    Xs, tws = X[:sample], tw[:sample]
+    for _ in range(args.warmup):
+        ctx.eval_f64(Xs, tws)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.eval_f64(Xs, tws)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"C3: {n_env} x test/boxes.jl environments (4 contact instructions each)", "envs_per_gpu": n_env},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} of the {n_env} environments per step, {args.steps} steps, C++ port of the Julia reference (Julia is not in the image)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--impl", default="pfc", choices=["pfc", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the contact-wrench path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from pfc_b200 import capi
+    from pfc_b200 import scenario as S
+
+    n_env = args.envs
+    m, X_h, tw_h = build_inputs(n_env, rank)
+    ctx = capi.Context(local_rank)
+    S.attach_backend(m, ctx, max_env=n_env)
+    n_ins = ctx.n_ins
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # device-resident buffers
+    X_d = torch.from_numpy(X_h).to(dev)
+    tw_d = torch.from_numpy(tw_h).to(dev)
+    w_d = torch.zeros((n_env, n_ins, 6), dtype=torch.float64, device=dev)
+    np_d = torch.zeros((n_env, n_ins), dtype=torch.int64, device=dev)
+    fl_d = torch.zeros((n_env, n_ins), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.eval_f64_device(n_env, X_d.data_ptr(), tw_d.data_ptr(), None, w_d.data_ptr(), None, np_d.data_ptr(), fl_d.data_ptr())
+
+    # pinned host buffers for the end-to-end leg
+    X_p = torch.from_numpy(X_h).pin_memory()
+    tw_p = torch.from_numpy(tw_h).pin_memory()
+    w_p = torch.zeros((n_env, n_ins, 6), dtype=torch.float64).pin_memory()
+    np_p = torch.zeros((n_env, n_ins), dtype=torch.int64).pin_memory()
+    fl_p = torch.zeros((n_env, n_ins), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        ctx.eval_f64_ptr(n_env, X_p.data_ptr(), tw_p.data_ptr(), None, w_p.data_ptr(), None, np_p.data_ptr(), fl_p.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = ctx.measure_fp64_peak()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_e2e()
+    ctx.sync()
+
+    # ---- timed region 1: device-resident, CUDA events on the library's stream, L2 flushed between steps ----
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = ctx.launch_count()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        for k in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            ev0[k].record(stream)
+            step_device()
+            ev1[k].record(stream)
+        barrier()
+        launches = ctx.launch_count() - launches0
+        dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+        # ---- timed region 2: end to end through pfc_eval_f64 with pinned host buffers (wall clock; the call is synchronous) ----
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step_e2e()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+
+    # correctness guard: the timed outputs are real (contacts found, finite wrench)
+    w_host = w_d.cpu().numpy()
+    assert np.isfinite(w_host).all() and int((fl_d.cpu().numpy() & 1).sum()) > n_env, "benchmark produced no contact work"
+    assert np.array_equal(w_host, w_p.numpy()), "device-resident and host-pointer entry points disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    evals = n_env * world * args.steps
+    value = evals / (dev_ms * 1e-3)
+    ms_per_step = dev_ms / args.steps
+
+    # ---- algorithmic work (instrumented oracle, counted on a sample) + CPU baseline ----
+    from oracle import orc
+    octx = orc.OracleContext(n_threads=1)
+    S.attach_backend(m, octx)
+    n_count = min(n_env, 512)
+    work = octx.count_work(X_h[:n_count], tw_h[:n_count])
+    flops_per_eval = (work["flops_broad"] + work["flops_narrow"]) / n_count
+    pairs_per_eval = work["candidate_pairs"] / n_count
+    node_pairs_per_eval = work["node_pairs"] / n_count
+    achieved_tflops = flops_per_eval * n_env / (ms_per_step * 1e-3) * 1e-12
+    bytes_per_eval = n_ins * (16 + 6 + 6) * 8 + n_ins * 12  # boundary arrays in + wrench, n_pairs, flags out
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    cpu_sample = min(n_env, 1024)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        octx.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
+        reps += 1
+        if time.perf_counter() - t0 > args.cpu_seconds or reps >= 200:
+            break
+    cpu_1 = cpu_sample * reps / (time.perf_counter() - t0)
+    cores = orc.lib().orc_max_threads()
+    octx_mt = orc.OracleContext(n_threads=cores)
+    S.attach_backend(m, octx_mt)
+    octx_mt.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
+    t0 = time.perf_counter()
+    for _ in range(5):
+        octx_mt.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
+    cpu_mt = cpu_sample * 5 / (time.perf_counter() - t0)
+
+    h2d = int(X_h.nbytes + tw_h.nbytes)
+    d2h = int(w_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3: {n_env} x test/boxes.jl environments per GPU (4 regularized-friction contact instructions each, quad rule 2), "
+                               "randomized settled-stack states", "envs_per_gpu": n_env, "instructions_per_env": n_ins,
+                   "candidate_pairs_per_eval": pairs_per_eval, "node_pairs_per_eval": node_pairs_per_eval,
+                   "l2": "256 MiB flush between timed steps", "parallelism": f"env-sharded x{world}, no collective"},
+        "candidate_pairs_per_sec": pairs_per_eval * value,
+        "e2e": {"value": evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                "api": "pfc_eval_f64 (host pointers, pinned)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak if fp64_peak else None,
+                     "traffic": None, "kernel": "eval_small_f64_kernel (fused broad phase + clip + quadrature + friction + reduction)",
+                     "flops_per_eval": flops_per_eval, "peak_source": "DFMA micro-benchmark in this process (pfc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                     "hbm": {"achieved": bytes_per_eval * n_env / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": bytes_per_eval * n_env / (ms_per_step * 1e-3) * 1e-9 / hbm_peak, "bytes_per_eval": bytes_per_eval,
+                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}},
+        "cpu_baseline": {"value": cpu_1, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{cpu_sample} of the {n_env} environments x {reps} repetitions, single thread (the reference is single-threaded); "
+                                   "C++ port of the Julia reference, not Julia",
+                         "all_cores": {"value": cpu_mt, "cores": cores}},
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,8 @@ int pfc_set_shard(pfc_ctx* ctx, int rank, int world);
 int pfc_sync(pfc_ctx* ctx);
 void* pfc_stream(pfc_ctx* ctx);            /* the cudaStream_t kernels are launched on (for CUDA-event timing) */
 int64_t pfc_launch_count(pfc_ctx* ctx);   /* kernels launched by this context so far */
+/* FP64 (DFMA) throughput of the context's device in TFLOP/s: the roofline denominator of the clip/quadrature kernels. */
+int pfc_measure_fp64_peak(pfc_ctx* ctx, double* tflops);
 int pfc_counters(pfc_ctx* ctx, int64_t* n_node_pairs_tested, int64_t* n_candidate_pairs);
 const char* pfc_last_error(void);
 const char* pfc_version(void);

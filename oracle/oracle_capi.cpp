@@ -41,7 +41,7 @@ int orc_sat(const double* a_c, const double* a_e, const double* a_R, const doubl
     M3<double> R; V3<double> t;
     for (int k = 0; k < 9; ++k) R.m[k] = R_a_b[k];
     for (int k = 0; k < 3; ++k) t[k] = t_a_b[k];
-    return BB_BB_intersect(R, t, a, b) ? 1 : 0;
+    return BB_BB_intersect<double>(R, t, a, b) ? 1 : 0;
 }
 
 // zeta_in: n_in x 4 (row per vertex); zeta_out: 8 x 4.  Returns vertex count, or -1/-2 on the
@@ -264,6 +264,36 @@ int orc_eval_dual6(void* h, int64_t n_env, const double* X_bp, const double* X7,
             if (flags) flags[ei] = f;
         }
     });
+    return 0;
+}
+
+// ALGORITHMIC work of the reference algorithm for one batch, counted with the instrumented scalar:
+// out[0] broad-phase FLOPs, out[1] narrow-phase + friction FLOPs, out[2] node pairs visited,
+// out[3] candidate pairs, out[4] traction points (quadrature points with p > 0).
+int orc_count_work(void* h, int64_t n_env, const double* X, const double* twist, const double* s, int64_t* out) {
+    Scene& sc = *static_cast<Scene*>(h);
+    const int n_ins = int(sc.ins.size());
+    const int nb = sc.n_bristle;
+    for (int k = 0; k < 5; ++k) out[k] = 0;
+    std::vector<std::pair<int32_t, int32_t>> pairs;
+    for (int64_t e = 0; e < n_env; ++e) {
+        for (int k = 0; k < n_ins; ++k) {
+            const int64_t ei = e * n_ins + k;
+            Counted Xc[16], tw[6], w[6];
+            std::vector<Counted> sv(6 * std::max(nb, 1)), sd(6 * std::max(nb, 1));
+            for (int i = 0; i < 16; ++i) Xc[i] = Counted(X[16 * ei + i]);
+            for (int i = 0; i < 6; ++i) tw[i] = Counted(twist[6 * ei + i]);
+            for (int i = 0; i < 6 * nb; ++i) sv[i] = Counted(s[6 * nb * e + i]);
+            flop_counter() = 0;
+            int64_t broad = 0, visited = 0, points = 0;
+            force_single_elastic_intersection<Counted>(sc, sc.ins[k], X + 16 * ei, Xc, tw, sv.data(), w, sd.data(), pairs, nullptr, visited, &broad, &points);
+            out[0] += broad;
+            out[1] += flop_counter() - broad;
+            out[2] += visited;
+            out[3] += int64_t(pairs.size());
+            out[4] += points;
+        }
+    }
     return 0;
 }
 

@@ -84,6 +84,8 @@ def lib():
         L.orc_get_traction.restype = C.c_int64
         L.orc_get_traction.argtypes = [C.c_void_p, C.c_int64, C.c_int, _d, C.c_int64]
         L.orc_max_threads.restype = C.c_int
+        L.orc_count_work.restype = C.c_int
+        L.orc_count_work.argtypes = [C.c_void_p, C.c_int64, _d, _d, C.c_void_p, _i64]
         _LIB = L
     return _LIB
 
@@ -273,6 +275,17 @@ class OracleContext:
         out = np.zeros((max(n, 1), 8))
         lib().orc_get_traction(self._h, env, ins, out, n)
         return out[:n]
+
+    def count_work(self, X, twist, s=None):
+        """Algorithmic work of the reference algorithm for this batch (instrumented scalar)."""
+        X = _a(X).reshape(-1, self.n_ins, 16)
+        n_env = X.shape[0]
+        twist = _a(twist).reshape(n_env, self.n_ins, 6)
+        s_a = None if self.n_bristle == 0 else _a(s).reshape(n_env, self.n_bristle, 6)
+        out = np.zeros(5, np.int64)
+        lib().orc_count_work(self._h, n_env, X, twist, _ptr(s_a), out)
+        return dict(flops_broad=int(out[0]), flops_narrow=int(out[1]), node_pairs=int(out[2]), candidate_pairs=int(out[3]),
+                    traction_points=int(out[4]))
 
     def n_visited(self) -> int:
         return lib().orc_n_visited(self._h)

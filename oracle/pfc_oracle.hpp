@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <string>
 #include <utility>
 #include <vector>
@@ -88,6 +89,37 @@ template <class T> inline T clamp_(const T& x, double lo, double hi) {
     if (value(x) < lo) return T(lo);
     return x;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Counted: a double that counts floating-point operations (+ - * / sqrt = 1, muladd = 2;
+// negation, abs, comparisons and conversions are free).  Used by orc_count_flops to publish the
+// ALGORITHMIC FLOP count of the reference algorithm per evaluation (SURVEY.md section 8d asks for
+// the constants to be re-counted from the oracle with an instrumented scalar type).
+// ----------------------------------------------------------------------------------------------
+inline int64_t& flop_counter() { static thread_local int64_t c = 0; return c; }
+inline void count_flops(int64_t n) { flop_counter() += n; }
+struct Counted {
+    double v;
+    Counted() : v(0.0) {}
+    Counted(double x) : v(x) {}
+};
+inline double value(const Counted& x) { return x.v; }
+inline Counted operator-(const Counted& a) { return Counted(-a.v); }
+#define ORC_COUNTED_BINOP(op)                                                                              \
+    inline Counted operator op(const Counted& a, const Counted& b) { count_flops(1); return Counted(a.v op b.v); } \
+    inline Counted operator op(const Counted& a, double b) { count_flops(1); return Counted(a.v op b); }           \
+    inline Counted operator op(double a, const Counted& b) { count_flops(1); return Counted(a op b.v); }
+ORC_COUNTED_BINOP(+)
+ORC_COUNTED_BINOP(-)
+ORC_COUNTED_BINOP(*)
+ORC_COUNTED_BINOP(/)
+#undef ORC_COUNTED_BINOP
+inline Counted sqrt_(const Counted& a) { count_flops(1); return Counted(std::sqrt(a.v)); }
+inline Counted muladd_(const Counted& a, const Counted& b, const Counted& c) { count_flops(2); return Counted(std::fma(a.v, b.v, c.v)); }
+inline Counted muladd_(double a, const Counted& b, double c) { count_flops(2); return Counted(std::fma(a, b.v, c)); }
+inline Counted muladd_(double a, const Counted& b, const Counted& c) { count_flops(2); return Counted(std::fma(a, b.v, c.v)); }
+inline double abs_(double x) { return std::fabs(x); }
+inline Counted abs_(const Counted& x) { return Counted(std::fabs(x.v)); }
 
 // ----------------------------------------------------------------------------------------------
 // Small static vectors / matrices (StaticArrays 0.10.3 semantics: column-major, products are
@@ -164,6 +196,7 @@ inline M4<double> inv44(const M4<double>& A) {
     inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
     inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
     inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    count_flops(296);  // 16 cofactors x 17 + determinant 7 + 1 division + 16 scalings
     double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
     double idet = 1.0 / det;
     M4<double> R;
@@ -433,30 +466,30 @@ inline TriQuadRule getTriQuadRule(int n_rule) {
 struct OBB { V3<double> c, e; M3<double> R; };
 
 // src/obb/bb_intersection.jl:17-74
-inline bool BB_BB_intersect_sat(const V3<double>& e_a, const V3<double>& e_b, const V3<double>& t, const M3<double>& R, const M3<double>& abs_R) {
-    auto any_lt = [](const V3<double>& a, const V3<double>& b) { return (a[0] < b[0]) || (a[1] < b[1]) || (a[2] < b[2]); };
-    auto abs3 = [](const V3<double>& a) { return mk3<double>(std::fabs(a[0]), std::fabs(a[1]), std::fabs(a[2])); };
-    auto s221 = [](const V3<double>& r) { return mk3<double>(r[2], r[2], r[1]); };
-    auto s100 = [](const V3<double>& r) { return mk3<double>(r[1], r[0], r[0]); };
-    auto had = [](const V3<double>& a, const V3<double>& b) { return mk3<double>(a[0] * b[0], a[1] * b[1], a[2] * b[2]); };
-    V3<double> R0 = mk3<double>(R.m[0], R.m[3], R.m[6]);
-    V3<double> R1 = mk3<double>(R.m[1], R.m[4], R.m[7]);
-    V3<double> R2 = mk3<double>(R.m[2], R.m[5], R.m[8]);
-    V3<double> aR0 = mk3<double>(abs_R.m[0], abs_R.m[3], abs_R.m[6]);
-    V3<double> aR1 = mk3<double>(abs_R.m[1], abs_R.m[4], abs_R.m[7]);
-    V3<double> aR2 = mk3<double>(abs_R.m[2], abs_R.m[5], abs_R.m[8]);
+template <class S> inline bool BB_BB_intersect_sat(const V3<S>& e_a, const V3<S>& e_b, const V3<S>& t, const M3<S>& R, const M3<S>& abs_R) {
+    auto any_lt = [](const V3<S>& a, const V3<S>& b) { return (value(a[0]) < value(b[0])) || (value(a[1]) < value(b[1])) || (value(a[2]) < value(b[2])); };
+    auto abs3 = [](const V3<S>& a) { return mk3<S>(abs_(a[0]), abs_(a[1]), abs_(a[2])); };
+    auto s221 = [](const V3<S>& r) { return mk3<S>(r[2], r[2], r[1]); };
+    auto s100 = [](const V3<S>& r) { return mk3<S>(r[1], r[0], r[0]); };
+    auto had = [](const V3<S>& a, const V3<S>& b) { return mk3<S>(a[0] * b[0], a[1] * b[1], a[2] * b[2]); };
+    V3<S> R0 = mk3<S>(R.m[0], R.m[3], R.m[6]);
+    V3<S> R1 = mk3<S>(R.m[1], R.m[4], R.m[7]);
+    V3<S> R2 = mk3<S>(R.m[2], R.m[5], R.m[8]);
+    V3<S> aR0 = mk3<S>(abs_R.m[0], abs_R.m[3], abs_R.m[6]);
+    V3<S> aR1 = mk3<S>(abs_R.m[1], abs_R.m[4], abs_R.m[7]);
+    V3<S> aR2 = mk3<S>(abs_R.m[2], abs_R.m[5], abs_R.m[8]);
     // face test 1/2
-    V3<double> T_dot_L = abs3(t);
-    V3<double> r_a = e_a;
-    V3<double> r_b = mul3v(abs_R, e_b);
+    V3<S> T_dot_L = abs3(t);
+    V3<S> r_a = e_a;
+    V3<S> r_b = mul3v(abs_R, e_b);
     if (any_lt(r_a + r_b, T_dot_L)) return false;
     // face test 2/2
     T_dot_L = abs3(mul3tv(R, t));
     r_a = mul3tv(abs_R, e_a);
     r_b = e_b;
     if (any_lt(r_a + r_b, T_dot_L)) return false;
-    V3<double> eb_100 = s100(e_b), eb_221 = s221(e_b);
-    double t0 = t[0], t1 = t[1], t2 = t[2], ea0 = e_a[0], ea1 = e_a[1], ea2 = e_a[2];
+    V3<S> eb_100 = s100(e_b), eb_221 = s221(e_b);
+    S t0 = t[0], t1 = t[1], t2 = t[2], ea0 = e_a[0], ea1 = e_a[1], ea2 = e_a[2];
     // cross test 1/3
     T_dot_L = abs3(scale(R1, t2) - scale(R2, t1));
     r_a = scale(aR2, ea1) + scale(aR1, ea2);
@@ -476,28 +509,32 @@ inline bool BB_BB_intersect_sat(const V3<double>& e_a, const V3<double>& e_b, co
 }
 
 // basic_dh(R, t): src/math_kernel/basic_dh.jl:52-59
-inline M4<double> basic_dh(const M3<double>& R, const V3<double>& t) {
-    M4<double> m;
-    for (int c = 0; c < 3; ++c) { for (int r = 0; r < 3; ++r) m(r, c) = R(r, c); m(3, c) = 0.0; }
-    m(0, 3) = t[0]; m(1, 3) = t[1]; m(2, 3) = t[2]; m(3, 3) = 1.0;
+template <class S> inline M4<S> basic_dh(const M3<S>& R, const V3<S>& t) {
+    M4<S> m;
+    for (int c = 0; c < 3; ++c) { for (int r = 0; r < 3; ++r) m(r, c) = R(r, c); m(3, c) = S(0.0); }
+    m(0, 3) = t[0]; m(1, 3) = t[1]; m(2, 3) = t[2]; m(3, 3) = S(1.0);
     return m;
 }
 
 // src/obb/bb_intersection.jl:2-12
-inline bool BB_BB_intersect(const M3<double>& R_a_b, const V3<double>& t_a_b, const OBB& a, const OBB& b) {
-    M3<double> aRt;
+template <class S> inline bool BB_BB_intersect(const M3<double>& R_a_b_d, const V3<double>& t_a_b_d, const OBB& a_d, const OBB& b_d) {
+    struct { V3<S> c, e; M3<S> R; } a, b;
+    M3<S> R_a_b; V3<S> t_a_b;
+    for (int k = 0; k < 3; ++k) { a.c[k] = S(a_d.c[k]); a.e[k] = S(a_d.e[k]); b.c[k] = S(b_d.c[k]); b.e[k] = S(b_d.e[k]); t_a_b[k] = S(t_a_b_d[k]); }
+    for (int k = 0; k < 9; ++k) { a.R.m[k] = S(a_d.R.m[k]); b.R.m[k] = S(b_d.R.m[k]); R_a_b.m[k] = S(R_a_b_d.m[k]); }
+    M3<S> aRt;
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) aRt(r, c) = a.R(c, r);
-    M3<double> naRt;  // -a.R' (unary minus binds first in `-a.R' * a.c`)
+    M3<S> naRt;  // -a.R' (unary minus binds first in `-a.R' * a.c`)
     for (int k = 0; k < 9; ++k) naRt.m[k] = -aRt.m[k];
-    M4<double> i_dh_a = basic_dh(aRt, mul3v(naRt, a.c));
-    M4<double> dh_a_b = basic_dh(R_a_b, t_a_b);
-    M4<double> dh_b = basic_dh(b.R, b.c);
-    M4<double> dh_final = mul44<double, double, double>(mul44<double, double, double>(i_dh_a, dh_a_b), dh_b);
-    M3<double> R_tot, abs_R_tot;
+    M4<S> i_dh_a = basic_dh<S>(aRt, mul3v(naRt, a.c));
+    M4<S> dh_a_b = basic_dh<S>(R_a_b, t_a_b);
+    M4<S> dh_b = basic_dh<S>(b.R, b.c);
+    M4<S> dh_final = mul44<S, S, S>(mul44<S, S, S>(i_dh_a, dh_a_b), dh_b);
+    M3<S> R_tot, abs_R_tot;
     for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) R_tot(r, c) = dh_final(r, c);
-    V3<double> t = mk3<double>(dh_final(0, 3), dh_final(1, 3), dh_final(2, 3));
-    for (int k = 0; k < 9; ++k) abs_R_tot.m[k] = std::fabs(R_tot.m[k]) + 1.0e-14;
-    return BB_BB_intersect_sat(a.e, b.e, t, R_tot, abs_R_tot);
+    V3<S> t = mk3<S>(dh_final(0, 3), dh_final(1, 3), dh_final(2, 3));
+    for (int k = 0; k < 9; ++k) abs_R_tot.m[k] = abs_(R_tot.m[k]) + 1.0e-14;
+    return BB_BB_intersect_sat<S>(a.e, b.e, t, R_tot, abs_R_tot);
 }
 
 // src/obb/util.jl:17-51, src/obb/box_types.jl:11-15
@@ -586,28 +623,28 @@ struct Tree {
 };
 
 // src/obb/tree_types.jl:88-111
-inline void tree_tree_intersect(std::vector<std::pair<int32_t, int32_t>>& vc, int64_t& n_visited, const M3<double>& R_a_b,
+template <class S = double> inline void tree_tree_intersect(std::vector<std::pair<int32_t, int32_t>>& vc, int64_t& n_visited, const M3<double>& R_a_b,
                                 const V3<double>& t_a_b, const Tree& t1, int n1, const Tree& t2, int n2) {
     ++n_visited;
-    if (!BB_BB_intersect(R_a_b, t_a_b, t1.box[n1], t2.box[n2])) return;
+    if (!BB_BB_intersect<S>(R_a_b, t_a_b, t1.box[n1], t2.box[n2])) return;
     bool is_leaf_1 = t1.leaf_id[n1] >= 0;
     bool is_leaf_2 = t2.leaf_id[n2] >= 0;
     if (is_leaf_1) {
         if (is_leaf_2) {
             vc.emplace_back(t1.leaf_id[n1], t2.leaf_id[n2]);
         } else {
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, n1, t2, t2.left[n2]);
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, n1, t2, t2.right[n2]);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, n1, t2, t2.left[n2]);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, n1, t2, t2.right[n2]);
         }
     } else {
         if (is_leaf_2) {
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, t1.left[n1], t2, n2);
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, t1.right[n1], t2, n2);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, t1.left[n1], t2, n2);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, t1.right[n1], t2, n2);
         } else {
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, t1.left[n1], t2, t2.left[n2]);
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, t1.right[n1], t2, t2.left[n2]);
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, t1.left[n1], t2, t2.right[n2]);
-            tree_tree_intersect(vc, n_visited, R_a_b, t_a_b, t1, t1.right[n1], t2, t2.right[n2]);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, t1.left[n1], t2, t2.left[n2]);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, t1.right[n1], t2, t2.left[n2]);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, t1.left[n1], t2, t2.right[n2]);
+            tree_tree_intersect<S>(vc, n_visited, R_a_b, t_a_b, t1, t1.right[n1], t2, t2.right[n2]);
         }
     }
 }
@@ -699,6 +736,15 @@ inline void calc_Kbar_sqrt_inv(SpatialStiffness<double>& s) {
             for (int k = 0; k < 6; ++k) acc += (V[i][k] * sig[k]) * V[j][k];
             s.Kbar_sqrt_inv[i][j] = acc;
         }
+}
+inline void calc_Kbar_sqrt_inv(SpatialStiffness<Counted>& s) {
+    // flop accounting only: LAPACK's dsyev on a 6x6 is ~9 n^3 = 1944 FLOPs (estimate), the two
+    // mul! of friction.jl:94-95 are 36 + 396
+    SpatialStiffness<double> d;
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) d.Kbar[i][j] = s.Kbar[i][j].v;
+    calc_Kbar_sqrt_inv(d);
+    count_flops(1944 + 36 + 396 + 18);
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) s.Kbar_sqrt_inv[i][j] = Counted(d.Kbar_sqrt_inv[i][j]);
 }
 template <int N> inline void calc_Kbar_sqrt_inv(SpatialStiffness<Dual<N>>& s) {
     double A[6][6], V[6][6], lam[6];
@@ -845,6 +891,7 @@ template <class T> inline void integrate_over_tri_tet(int i_1, int i_2, BodyBody
     M4<double> x_r2_z2 = asMatOnePad4(vert_2);
     M4<double> x_z2_r2 = inv44(x_r2_z2);
     V4<double> eps_r2 = mulrow4<double, double, double>(eps2, x_z2_r2);
+    count_flops(28);  // the Float64-only row product above
     M4<T> x_z2_r1 = mul44<double, T, T>(x_z2_r2, b.x_r2_r1);
     V4<T> z[3];
     for (int k = 0; k < 3; ++k) {
@@ -854,6 +901,7 @@ template <class T> inline void integrate_over_tri_tet(int i_1, int i_2, BodyBody
     Poly<4, T> poly_z2 = clip_in_tet_coordinates(z[0], z[1], z[2], b.clip_status);
     if (3 <= poly_z2.n) {
         V3<double> n_r1 = triangleNormal(vert_1[0], vert_1[1], vert_1[2]);
+        count_flops(27);  // Float64-only: 2 differences, cross, scaling, dot, sqrt, 3 divisions
         V3<T> n2 = mul3v(rot_of(b.x_r2_r1), lift3<T>(n_r1));  // transform(::FreeVector3D, x) = R * v
         integrate_over_polygon_patch(b, n2, poly_z2, x_r2_z2, eps_r2);
     }
@@ -874,6 +922,7 @@ template <class T> inline void integrate_over_tet_tet(int i_1, int i_2, BodyBody
     V4<T> eps_plane_1_r2 = mulrow4<double, T, T>(E1e, x_z1_r2);
     V4<double> eps_r2 = mulrow4<double, double, double>(eps2, x_z2_r2);
     V4<double> eps_plane_2_r2 = mulrow4<double, double, double>(E2e, x_z2_r2);
+    count_flops(8 + 28 + 28);  // Float64-only: E * eps (x2), two row products
     V4<T> eps_plane_r2;
     for (int k = 0; k < 4; ++k) eps_plane_r2[k] = eps_plane_2_r2[k] - eps_plane_1_r2[k];
     M4<T> x_r2_z1 = mul44<T, double, T>(b.x_r2_r1, x_r1_z1);
@@ -1039,7 +1088,7 @@ struct Scene {
 template <class T>
 inline int force_single_elastic_intersection(const Scene& sc, const Instruction& ci, const double* X_bp, const T* X, const T* twist, const T* s_in,
                                              T* wrench_out, T* sdot_out, std::vector<std::pair<int32_t, int32_t>>& pairs,
-                                             std::vector<double>* traction_dump, int64_t& n_visited) {
+                                             std::vector<double>* traction_dump, int64_t& n_visited, int64_t* broad_flops = nullptr, int64_t* n_points = nullptr) {
     const Mesh& m1 = sc.mesh[ci.id_1];
     const Mesh& m2 = sc.mesh[ci.id_2];
     // calcTriTetIntersections! : broad phase always on the Float64 transform
@@ -1048,7 +1097,12 @@ inline int force_single_elastic_intersection(const Scene& sc, const Instruction&
     M3<double> R_a_b = rot_of(x_r1_r2_f);
     V3<double> t_a_b = mk3<double>(x_r1_r2_f(0, 3), x_r1_r2_f(1, 3), x_r1_r2_f(2, 3));
     pairs.clear();
-    tree_tree_intersect(pairs, n_visited, R_a_b, t_a_b, m1.tree, m1.tree.root, m2.tree, m2.tree.root);
+    {
+        const int64_t before = flop_counter();
+        if (std::is_same<T, Counted>::value) tree_tree_intersect<Counted>(pairs, n_visited, R_a_b, t_a_b, m1.tree, m1.tree.root, m2.tree, m2.tree.root);
+        else tree_tree_intersect<double>(pairs, n_visited, R_a_b, t_a_b, m1.tree, m1.tree.root, m2.tree, m2.tree.root);
+        if (broad_flops) *broad_flops += flop_counter() - before;
+    }
     for (int k = 0; k < 6; ++k) wrench_out[k] = T(0.0);
     int flags = 0;
     bool contact = false;
@@ -1074,6 +1128,7 @@ inline int force_single_elastic_intersection(const Scene& sc, const Instruction&
                 traction_dump->push_back(value(tc.p));
             }
         }
+        if (n_points) *n_points += int64_t(b.traction.size());
         if (!b.traction.empty()) {
             contact = true;
             V6<T> w;

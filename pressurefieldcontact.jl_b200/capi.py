@@ -22,7 +22,7 @@ _vp = C.c_void_p
 SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
     "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_sync", "pfc_stream",
-    "pfc_launch_count", "pfc_counters", "pfc_last_error", "pfc_version",
+    "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_last_error", "pfc_version",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
         L.pfc_launch_count.argtypes = [_vp]
         L.pfc_launch_count.restype = C.c_int64
         L.pfc_counters.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.pfc_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
         L.pfc_last_error.restype = C.c_char_p
         L.pfc_version.restype = C.c_char_p
         _LIB = L
@@ -190,6 +191,11 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().pfc_launch_count(self._h))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        _check(lib().pfc_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
 
     def counters(self):
         a, b = C.c_int64(0), C.c_int64(0)

@@ -453,6 +453,14 @@ int pfc_sync(pfc_ctx* c) {
     return PFC_OK;
 }
 
+int pfc_measure_fp64_peak(pfc_ctx* c, double* tflops) {
+    if (!c || !tflops) return fail(PFC_E_ARG, "pfc_measure_fp64_peak: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(measure_fp64_peak(c->stream, tflops));
+    c->launches += 5;
+    return PFC_OK;
+}
+
 void* pfc_stream(pfc_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t pfc_launch_count(pfc_ctx* c) { return c ? c->launches : 0; }
 int pfc_counters(pfc_ctx*, int64_t* a, int64_t* b) { if (a) *a = 0; if (b) *b = 0; return PFC_OK; }

@@ -29,4 +29,7 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, cudaStre
 cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long env, int ins, const int* pairs, long long n_pairs, double* out,
                                  int cap_points, int* n_points, cudaStream_t stream);
 
+// FP64 DFMA throughput of the current device in TFLOP/s (best of a few bursts).
+cudaError_t measure_fp64_peak(cudaStream_t stream, double* tflops);
+
 }  // namespace pfc

@@ -102,7 +102,7 @@ def splitmix64(seed):
     return nxt
 
 
-def boxes_env_states(m, n_env, r=0.05):
+def boxes_env_states(m, n_env, r=0.05, start=0):
     """Config C3: randomized *settled-stack* states of the test/boxes.jl scene, env e seeded with
     splitmix64(0x5EED0000 + e).  Box k (1..4) sits at z = (2k-1) r minus a cumulative sink of
     U(0, 0.02) r per level, with xy jitter, a small tilt, a free yaw and random twists, so that
@@ -111,7 +111,7 @@ def boxes_env_states(m, n_env, r=0.05):
     nq = m.nq
     X = np.zeros((n_env, S.num_x(m)))
     for e in range(n_env):
-        u = splitmix64(0x5EED0000 + e)
+        u = splitmix64(0x5EED0000 + start + e)
         U = lambda lo, hi: lo + (hi - lo) * u()
         sink = 0.0
         for k in range(1, 5):
