@@ -300,8 +300,10 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
         if (d.key_bits > 64) return fail(PFC_E_MESH, "pfc_finalize: tree depths sum to more than 64 levels");
         d.small = (m1.n_prim * m2.n_prim <= kSmallCap && m1.n_prim < 16384 && m2.n_prim < 16384) ? 1 : 0;
         d.chi = h.chi; d.Ebar1 = m1.kind == 1 ? m1.Ebar : 0.0; d.Ebar2 = m2.Ebar;
-        if (h.model == 0) { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = 2 * h.params[2]; d.p[4] = 3 * h.params[2]; }
-        else { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = h.params[3]; d.p[4] = 2 * h.params[2]; d.p[5] = 3 * h.params[2]; d.p[6] = h.params[4]; }
+        if (h.model == 0) { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = 2 * h.params[2]; d.p[4] = 3 * h.params[2];
+            d.p[5] = (d.p[1] - d.p[0]) / (d.p[4] - d.p[3]); d.p[6] = 1.0 / d.p[2]; }
+        else { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = h.params[3]; d.p[4] = 2 * h.params[2]; d.p[5] = 3 * h.params[2]; d.p[6] = h.params[4];
+            d.p[7] = (d.p[3] - d.p[2]) / (d.p[5] - d.p[4]); }
         if (d.small) small.push_back(int32_t(k));
         c->h_ins.push_back(d);
     }

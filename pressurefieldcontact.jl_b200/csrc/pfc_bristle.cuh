@@ -51,9 +51,11 @@ __device__ __noinline__ void jacobi6(double* A, double* V, double* lam) {
 }
 
 // a21: K11 upper (0..5), K12 row-major (6..14), K22 upper (15..20), already multiplied by k_bar.
-// Outputs: Sinv (6) and Khalf = K̄^(-1/2) (36, row-major).
-__device__ __noinline__ void decompose_K(const double* a21, double magic, double* Sinv, double* Khalf) {
-    double K[36];
+// Outputs: Sinv (6) and Khalf = K̄^(-1/2) (36, row-major).  scratch: 108 doubles of (shared) memory.
+__device__ __noinline__ void decompose_K(const double* a21, double magic, double* Sinv, double* Khalf, double* scratch) {
+    double* K = scratch;
+    double* A = scratch + 36;
+    double* V = scratch + 72;
     {
         // K11
         K[0] = a21[0]; K[1] = a21[1]; K[2] = a21[2]; K[7] = a21[3]; K[8] = a21[4]; K[14] = a21[5];
@@ -69,7 +71,7 @@ __device__ __noinline__ void decompose_K(const double* a21, double magic, double
     const double t2 = K[21] + K[28] + K[35];
     const double s1 = 1.0 / sqrt(t1), s2 = 1.0 / sqrt(t2);
     for (int k = 0; k < 3; ++k) { Sinv[k] = s1 * magic; Sinv[3 + k] = s2; }
-    double A[36], V[36], lam[6];
+    double lam[6];
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) A[6 * i + j] = Sinv[i] * K[6 * i + j] * Sinv[j];
     jacobi6(A, V, lam);

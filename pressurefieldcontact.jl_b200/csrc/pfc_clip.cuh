@@ -21,8 +21,8 @@ template <class T> struct Zeta { T c[4]; };
 // weightPoly (src/math_kernel/utility.jl:21-26) on tetrahedral coordinates
 template <class T> PFC_D Zeta<T> clip_node(const Zeta<T>& z_non, const Zeta<T>& z_pos, int i) {
     const T w1 = z_non.c[i], w2 = z_pos.c[i];
-    const T s = w1 - w2;
-    const T c1 = w1 / s, c2 = w2 / s;
+    const T inv = 1.0 / (w1 - w2);
+    const T c1 = w1 * inv, c2 = w2 * inv;
     Zeta<T> r;
 #pragma unroll
     for (int k = 0; k < 4; ++k) r.c[k] = c1 * z_pos.c[k] - c2 * z_non.c[k];
@@ -86,8 +86,8 @@ template <class T> PFC_D void zero_small(Zeta<T>* z, int n) {
 
 // weightPoly on Cartesian points
 template <class T> PFC_D Vec3<T> weight_poly(const Vec3<T>& p1, const Vec3<T>& p2, const T& w1, const T& w2) {
-    const T s = w1 - w2;
-    const T c1 = w1 / s, c2 = w2 / s;
+    const T inv = 1.0 / (w1 - w2);
+    const T c1 = w1 * inv, c2 = w2 * inv;
     return mk<T>(c1 * p2.x - c2 * p1.x, c1 * p2.y - c2 * p1.y, c1 * p2.z - c2 * p1.z);
 }
 

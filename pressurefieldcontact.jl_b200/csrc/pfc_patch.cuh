@@ -11,8 +11,12 @@
 //                        calc_spatial_bristle_force  friction.jl:171-201, traction(::Bristle) :32-48
 // The reference materialises a TractionCache list between the narrow phase and friction; here
 // every quadrature point is consumed immediately by an accumulator (Accum::point) so nothing is
-// written to memory.  The bristle model needs three passes over the points (centre of pressure ->
-// stiffness -> friction); the passes re-run the narrow phase with a different accumulator mode.
+// written to memory.  The work is split in two stages so that a warp can keep its lanes busy:
+//   stage A  clip_pair():        one candidate pair -> a PolyRec (clipped polygon in frame r2, its
+//                                normal, centroid and the tet's pressure gradient), or nothing;
+//   stage B  integrate_subtri(): one (polygon, edge) sub-triangle -> its 1 or 3 quadrature points.
+// Most candidate pairs die in stage A; stage B is where the quadrature + friction FLOPs are, and
+// its work items are dense.  integrate_pair() composes both for one-thread-per-pair callers.
 #pragma once
 #include "pfc_clip.cuh"
 #include "pfc_math.cuh"
@@ -36,9 +40,17 @@ template <class T> struct PatchCtx {
     int n_quad;
 };
 
-template <class T> PFC_D T clamped_piecewise(const T& x, double x1, double x2, double y1, double y2) {
-    const double k = (y2 - y1) / (x2 - x1);
-    const T y = y1 + (x - x1) * k;
+// A clipped contact polygon, ready for quadrature (stage A output / stage B input).
+template <class T> struct PolyRec {
+    Vec3<T> v[8];     // vertices in r2
+    Vec3<T> nrm;      // unit normal, pointing into body 2
+    Vec3<T> cen;      // area-weighted centroid
+    double eps_r[4];  // pressure field of tet 2: gradient (0..2), offset (3)
+    int n;
+};
+
+template <class T> PFC_D T clamped_piecewise(const T& x, double x1, double slope, double y1, double y2) {
+    const T y = y1 + (x - x1) * slope;
     if (val(y) > y1) return T(y1);  // clamp(y, y2, y1): y2 <= y1
     if (val(y) < y2) return T(y2);
     return y;
@@ -69,20 +81,19 @@ template <class T> struct Accum {
     PFC_D void point(const Vec3<T>& n, const Vec3<T>& r, const T& dA, const T& p) {
         const T p_dA = p * dA;
         if (mode == ACC_REGULARIZED) {
+            // fp: mu_s, mu_d, v_c, v_mu_s, v_mu_d, slope, 1 / v_c
             const Vec3<T> vel = w_lin + cross(w_ang, r);
             const Vec3<T> vt = sub_proj(vel, n);
             const T mag2 = dot(vt, vt);
             const double mu_s = fp[0], v_c = fp[2];
-            Vec3<T> Tc;
+            T coef;
             if (val(mag2) < v_c * v_c) {
-                const double s = -mu_s;
-                Tc = mk<T>(vt.x * s / v_c, vt.y * s / v_c, vt.z * s / v_c);
+                coef = T(-mu_s * fp[6]) * p_dA;
             } else {
                 const T mag = sqrt_(mag2);
-                const T mu = -clamped_piecewise(mag, fp[3], fp[4], mu_s, fp[1]);
-                Tc = mk<T>(mu * vt.x / mag, mu * vt.y / mag, mu * vt.z / mag);
+                coef = (clamped_piecewise(mag, fp[3], fp[5], mu_s, fp[1]) / mag) * (-p_dA);
             }
-            const Vec3<T> tk = mk<T>(p_dA * n.x + Tc.x * p_dA, p_dA * n.y + Tc.y * p_dA, p_dA * n.z + Tc.z * p_dA);
+            const Vec3<T> tk = mk<T>(p_dA * n.x + vt.x * coef, p_dA * n.y + vt.y * coef, p_dA * n.z + vt.z * coef);
             const Vec3<T> m = cross(r, tk);
             a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += tk.x; a[4] += tk.y; a[5] += tk.z;
         } else if (mode == ACC_COP) {
@@ -121,7 +132,7 @@ template <class T> struct Accum {
             a[19] += p_dA * (-(n.y * n.z));
             a[20] += p_dA * (1.0 - n.z * n.z);
         } else if (mode == ACC_BRISTLE) {
-            // fp: tau, k_bar, mu_s, mu_d, Ts_mu_s, Ts_mu_d, magic
+            // fp: tau, k_bar, mu_s, mu_d, Ts_mu_s, Ts_mu_d, magic, slope
             const Vec3<T> x2 = r - cop;
             const Vec3<T> d_ang = mk<T>(delta[0], delta[1], delta[2]);
             const Vec3<T> d_lin = mk<T>(delta[3], delta[4], delta[5]);
@@ -131,15 +142,12 @@ template <class T> struct Accum {
             Vec3<T> Ts = mk<T>((dl.x + rd.x * tau) * nk, (dl.y + rd.y * tau) * nk, (dl.z + rd.z * tau) * nk);
             Ts = sub_proj(Ts, n);
             const T mag2 = dot(Ts, Ts);
-            Vec3<T> Tc;
-            if (val(mag2) < mu_s * mu_s) {
-                Tc = Ts;
-            } else {
+            T coef = p_dA;
+            if (!(val(mag2) < mu_s * mu_s)) {
                 const T mag = sqrt_(mag2);
-                const T mu = clamped_piecewise(mag, fp[4], fp[5], mu_s, fp[3]);
-                Tc = mk<T>(mu * Ts.x / mag, mu * Ts.y / mag, mu * Ts.z / mag);
+                coef = (clamped_piecewise(mag, fp[4], fp[7], mu_s, fp[3]) / mag) * p_dA;
             }
-            Tc = Tc * p_dA;
+            const Vec3<T> Tc = Ts * coef;
             const Vec3<T> m = cross(x2, Tc);
             a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += Tc.x; a[4] += Tc.y; a[5] += Tc.z;
         } else {  // ACC_DUMP (debug / parity): n(3) r(3) dA p, values only
@@ -153,54 +161,54 @@ template <class T> struct Accum {
     }
 };
 
-// Polygon (tetrahedral coordinates of tet 2) -> centroid fan -> quadrature points
-template <class T> __device__ __noinline__ void integrate_polygon(const Zeta<T>* z, int n, const Vec3<T>& nrm, const TetRec& tet, const PatchCtx<T>& cx,
-                                                                  Accum<T>& acc) {
-    Vec3<T> pr[8];
-    for (int k = 0; k < n; ++k) {  // mul_then_un_pad(x_r2_zeta2, .)
-        const T z0 = z[k].c[0], z1 = z[k].c[1], z2 = z[k].c[2], z3 = z[k].c[3];
-        pr[k] = mk<T>(tet.v[0] * z0 + tet.v[3] * z1 + tet.v[6] * z2 + tet.v[9] * z3, tet.v[1] * z0 + tet.v[4] * z1 + tet.v[7] * z2 + tet.v[10] * z3,
-                      tet.v[2] * z0 + tet.v[5] * z1 + tet.v[8] * z2 + tet.v[11] * z3);
-    }
-    // area-weighted centroid, fan from vertex 0
-    T cum_sum = T(0.0);
-    Vec3<T> cum = mk<T>(T(0.0), T(0.0), T(0.0));
-    for (int k = 2; k < n; ++k) {
-        const Vec3<T> a = pr[0], b = pr[k - 1], c = pr[k];
-        const T area = dot(nrm, cross(b - a, c - b) * 0.5);
-        const Vec3<T> cen = (a + b + c) * (1.0 / 3.0);
-        cum = cum + cen * area;
-        cum_sum += area;
-    }
-    Vec3<T> cen = pr[0];
-    if (val(cum_sum) != 0.0) { const T inv = 1.0 / cum_sum; cen = mk<T>(cum.x * inv, cum.y * inv, cum.z * inv); }
-    const Vec3<double> grad = mk<double>(tet.eps_r[0], tet.eps_r[1], tet.eps_r[2]);
-    Vec3<T> v2 = pr[n - 1];
-    for (int k = 0; k < n; ++k) {
-        const Vec3<T> v1 = v2;
-        v2 = pr[k];
-        const T area = dot(nrm, cross(v2 - v1, cen - v2) * 0.5);
-        if (!(0.0 < val(area))) continue;
-        for (int q = 0; q < cx.n_quad; ++q) {
-            double za, zb, zc, w;
-            if (cx.n_quad == 1) { za = zb = zc = PFC_Q1; w = 1.0; }
-            else { za = (q == 1) ? PFC_QB : PFC_QA; zb = (q == 0) ? PFC_QB : PFC_QA; zc = (q == 2) ? PFC_QB : PFC_QA; w = PFC_Q1; }
-            const Vec3<T> r = mk<T>(v1.x * za + v2.x * zb + cen.x * zc, v1.y * za + v2.y * zb + cen.y * zc, v1.z * za + v2.z * zb + cen.z * zc);
-            T eps = fma_(grad.x, r.x, tet.eps_r[3]);
-            eps = fma_(grad.y, r.y, eps);
-            eps = fma_(grad.z, r.z, eps);
-            const Vec3<T> rd = cx.w_lin + cross(cx.w_ang, r);
-            const T ee = -(grad.x * rd.x + grad.y * rd.y + grad.z * rd.z);
-            T damp = 1.0 + cx.chi * ee;
-            if (val(damp) < 0.0) damp = T(0.0);
-            const T p = eps * cx.Ebar2 * damp;
-            if (0.0 < val(p)) acc.point(nrm, r, w * area, p);
-        }
+// ---- stage B: one sub-triangle (v1, v2, centroid) of a contact polygon ------------------------------------
+template <class T> PFC_D void integrate_subtri(const Vec3<T>& v1, const Vec3<T>& v2, const Vec3<T>& cen, const Vec3<T>& nrm, const double* eps_r,
+                                               const PatchCtx<T>& cx, Accum<T>& acc) {
+    const T area = dot(nrm, cross(v2 - v1, cen - v2) * 0.5);
+    if (!(0.0 < val(area))) return;
+    const double g0 = eps_r[0], g1 = eps_r[1], g2 = eps_r[2], g3 = eps_r[3];
+    for (int q = 0; q < cx.n_quad; ++q) {
+        double za, zb, zc, w;
+        if (cx.n_quad == 1) { za = zb = zc = PFC_Q1; w = 1.0; }
+        else { za = (q == 1) ? PFC_QB : PFC_QA; zb = (q == 0) ? PFC_QB : PFC_QA; zc = (q == 2) ? PFC_QB : PFC_QA; w = PFC_Q1; }
+        const Vec3<T> r = mk<T>(v1.x * za + v2.x * zb + cen.x * zc, v1.y * za + v2.y * zb + cen.y * zc, v1.z * za + v2.z * zb + cen.z * zc);
+        T eps = fma_(g0, r.x, g3);
+        eps = fma_(g1, r.y, eps);
+        eps = fma_(g2, r.z, eps);
+        const Vec3<T> rd = cx.w_lin + cross(cx.w_ang, r);
+        const T ee = -(g0 * rd.x + g1 * rd.y + g2 * rd.z);
+        T damp = 1.0 + cx.chi * ee;
+        if (val(damp) < 0.0) damp = T(0.0);
+        const T p = eps * cx.Ebar2 * damp;
+        if (0.0 < val(p)) acc.point(nrm, r, w * area, p);
     }
 }
 
-// ---- triangle (mesh 1) against tetrahedron (mesh 2) --------------------------------------------------------
-template <class T> PFC_D void narrow_tri_tet(const TriRec& tri, const TetRec& tet, const PatchCtx<T>& cx, Accum<T>& acc, int& flags) {
+// polygon in tetrahedral coordinates of tet 2 -> Cartesian vertices in r2 + area-weighted centroid
+template <class T> PFC_D void finish_polygon(const Zeta<T>* z, int n, const TetRec& tet, PolyRec<T>& out) {
+    out.n = n;
+    for (int k = 0; k < n; ++k) {  // mul_then_un_pad(x_r2_zeta2, .)
+        const T z0 = z[k].c[0], z1 = z[k].c[1], z2 = z[k].c[2], z3 = z[k].c[3];
+        out.v[k] = mk<T>(tet.v[0] * z0 + tet.v[3] * z1 + tet.v[6] * z2 + tet.v[9] * z3, tet.v[1] * z0 + tet.v[4] * z1 + tet.v[7] * z2 + tet.v[10] * z3,
+                         tet.v[2] * z0 + tet.v[5] * z1 + tet.v[8] * z2 + tet.v[11] * z3);
+    }
+    T cum_sum = T(0.0);
+    Vec3<T> cum = mk<T>(T(0.0), T(0.0), T(0.0));
+    for (int k = 2; k < n; ++k) {  // fan from vertex 0 (poly_eight.jl:35-52)
+        const Vec3<T> a = out.v[0], b = out.v[k - 1], c = out.v[k];
+        const T area = dot(out.nrm, cross(b - a, c - b) * 0.5);
+        cum = cum + ((a + b + c) * (1.0 / 3.0)) * area;
+        cum_sum += area;
+    }
+    out.cen = out.v[0];
+    if (val(cum_sum) != 0.0) { const T inv = 1.0 / cum_sum; out.cen = mk<T>(cum.x * inv, cum.y * inv, cum.z * inv); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out.eps_r[k] = tet.eps_r[k];
+}
+
+// ---- stage A -----------------------------------------------------------------------------------------------------
+// triangle (mesh 1) against tetrahedron (mesh 2); returns false when the pair contributes nothing
+template <class T> PFC_D bool clip_tri_tet(const TriRec& tri, const TetRec& tet, const PatchCtx<T>& cx, PolyRec<T>& out, int& flags) {
     Zeta<T> z[8];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -209,14 +217,14 @@ template <class T> PFC_D void narrow_tri_tet(const TriRec& tri, const TetRec& te
         for (int i = 0; i < 4; ++i) z[k].c[i] = tet.inv[4 * i] * p.x + tet.inv[4 * i + 1] * p.y + tet.inv[4 * i + 2] * p.z + tet.inv[4 * i + 3];
     }
     const int n = clip_tet(z, 3, flags);
-    if (n >= 3) {
-        const Vec3<T> nrm = rot_d(cx.x21, mk<double>(tri.n[0], tri.n[1], tri.n[2]));
-        integrate_polygon(z, n, nrm, tet, cx, acc);
-    }
+    if (n < 3) return false;
+    out.nrm = rot_d(cx.x21, mk<double>(tri.n[0], tri.n[1], tri.n[2]));
+    finish_polygon(z, n, tet, out);
+    return true;
 }
 
-// ---- tetrahedron (mesh 1) against tetrahedron (mesh 2) -----------------------------------------------------
-template <class T> PFC_D void narrow_tet_tet(const TetRec& t1, const TetRec& t2, const PatchCtx<T>& cx, Accum<T>& acc, int& flags) {
+// tetrahedron (mesh 1) against tetrahedron (mesh 2)
+template <class T> PFC_D bool clip_tet_tet(const TetRec& t1, const TetRec& t2, const PatchCtx<T>& cx, PolyRec<T>& out, int& flags) {
     // plane of equal pressure in r2: E2 eps2 x_zeta2_r2 - E1 eps1 x_zeta1_r1 x_r1_r2
     T plane[4];
     {
@@ -235,7 +243,7 @@ template <class T> PFC_D void narrow_tet_tet(const TetRec& t1, const TetRec& t2,
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = apply_d(cx.x21, mk<double>(t1.v[3 * k], t1.v[3 * k + 1], t1.v[3 * k + 2]));
     const int n0 = plane_tet(plane, v, poly);
-    if (n0 < 3) return;
+    if (n0 < 3) return false;
     Zeta<T> z[8];
     for (int k = 0; k < n0; ++k)
 #pragma unroll
@@ -243,10 +251,29 @@ template <class T> PFC_D void narrow_tet_tet(const TetRec& t1, const TetRec& t2,
             z[k].c[i] = t2.inv[4 * i] * poly[k].x + t2.inv[4 * i + 1] * poly[k].y + t2.inv[4 * i + 2] * poly[k].z + t2.inv[4 * i + 3];
     zero_small(z, n0);
     const int n = clip_tet(z, n0, flags);
-    if (n >= 3) {
-        const T inv_len = 1.0 / sqrt_(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);
-        const Vec3<T> nrm = mk<T>(plane[0] * inv_len, plane[1] * inv_len, plane[2] * inv_len);
-        integrate_polygon(z, n, nrm, t2, cx, acc);
+    if (n < 3) return false;
+    const T inv_len = 1.0 / sqrt_(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);
+    out.nrm = mk<T>(plane[0] * inv_len, plane[1] * inv_len, plane[2] * inv_len);
+    finish_polygon(z, n, t2, out);
+    return true;
+}
+
+// stage A dispatch on the kind of mesh 1
+template <class T> PFC_D bool clip_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx, PolyRec<T>& out, int& flags) {
+    const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
+    if (ins.kind1 == 0) return clip_tri_tet(sc.tris[ins.prim_base1 + prim1], t2, cx, out, flags);
+    return clip_tet_tet(sc.tets[ins.prim_base1 + prim1], t2, cx, out, flags);
+}
+
+// stages A + B for one pair on one thread, sub-triangles in the reference's order (previous vertex = last first)
+template <class T> PFC_D void integrate_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx, Accum<T>& acc, int& flags) {
+    PolyRec<T> pr;
+    if (!clip_pair(sc, ins, prim1, prim2, cx, pr, flags)) return;
+    Vec3<T> v2 = pr.v[pr.n - 1];
+    for (int k = 0; k < pr.n; ++k) {
+        const Vec3<T> v1 = v2;
+        v2 = pr.v[k];
+        integrate_subtri(v1, v2, pr.cen, pr.nrm, pr.eps_r, cx, acc);
     }
 }
 

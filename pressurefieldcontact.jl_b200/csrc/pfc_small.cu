@@ -7,15 +7,17 @@
 //   calcTriTetIntersections! (dual-tree traversal, src/obb/tree_types.jl:88-111)
 //   integrate_over!          (loop over candidate pairs, :136-143)
 //   yes_contact!/no_contact! (src/contact_algorithms_friction.jl:50-81, 119-143)
-// -- is done by one warp without leaving the SM:
+// -- is done by one warp of a persistent grid without leaving the SM:
 //   1. Broad phase: warp-cooperative in-place expansion of the node-pair frontier held in shared
 //      memory.  Each round every lane tests one node pair (15-axis SAT, bit-exact) and the
 //      survivors' children replace it *in order* through a warp prefix sum, so when the frontier
 //      holds only leaf pairs it is exactly the reference's recursion (DFS) order -- no atomics, no
 //      sort, deterministic.
-//   2. Narrow phase: lane l takes pairs l, l+32, ...: clip in registers/local memory, quadrature,
-//      friction traction, accumulated per lane in pair order.
-//   3. Fixed-order xor-butterfly warp reduction of the per-lane partial wrenches (bitwise
+//   2. Narrow phase in chunks of 32 candidate pairs: (A) each lane clips one pair and, if a polygon
+//      survives, leaves it in its shared-memory slot; (B) the chunk's (polygon, edge) sub-triangles
+//      are dealt out one per lane for quadrature + friction.  Most pairs die in (A); (B) keeps the
+//      lanes dense where the FLOPs are.
+//   3. Fixed-order xor-butterfly warp reduction of the per-lane partial sums (bitwise
 //      reproducible; no floating-point atomics).  Bristle friction runs the three passes of
 //      bristle_wrench_in_world with a warp reduction between passes.
 // HBM traffic per instruction is the boundary data only: 22 doubles in, 6 doubles + 2 words out.
@@ -36,6 +38,11 @@ PFC_D int dec_b(unsigned e) { return int(e & 0x7fffu); }
 PFC_D int warp_sum_int(int x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+PFC_D int warp_incl_scan(int x, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += v; }
     return x;
 }
 
@@ -59,20 +66,45 @@ PFC_D void broad_phase_xform(const Xform<double>& x21, double* Rab, double* tab)
     }
 }
 
-template <class T> PFC_D void run_pairs(const SceneDev& sc, const InsDev& ins, const unsigned* pairs, int n, int lane, const PatchCtx<T>& cx,
-                                        Accum<T>& acc, int& flags) {
-    for (int i = lane; i < n; i += 32) {
-        const unsigned e = pairs[i];
-        const TetRec& t2 = sc.tets[ins.prim_base2 + dec_b(e)];
-        if (ins.kind1 == 0) narrow_tri_tet(sc.tris[ins.prim_base1 + dec_a(e)], t2, cx, acc, flags);
-        else narrow_tet_tet(sc.tets[ins.prim_base1 + dec_a(e)], t2, cx, acc, flags);
+// per-warp shared memory
+template <int CAP> struct WarpSmem {
+    PolyRec<double> poly[32];   // stage A output, one slot per lane
+    unsigned frontier[2][CAP];
+    unsigned char items[256];   // stage B work list: (slot << 3) | edge
+    double bris[42];            // bristle: Sinv (6) + K̄^(-1/2) (36), kept across the friction pass
+};
+
+// Narrow phase over the warp's pair list for one accumulator mode.
+template <int CAP>
+PFC_D void run_pairs(const SceneDev& sc, const InsDev& ins, WarpSmem<CAP>& sm, const unsigned* pairs, int n, int lane, const PatchCtx<double>& cx,
+                     Accum<double>& acc, int& flags) {
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        int nv = 0;
+        if (i < n) {
+            const unsigned e = pairs[i];
+            if (clip_pair(sc, ins, dec_a(e), dec_b(e), cx, sm.poly[lane], flags)) nv = sm.poly[lane].n;
+        }
+        const int incl = warp_incl_scan(nv, lane);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int k = 0; k < nv; ++k) sm.items[incl - nv + k] = (unsigned char)((lane << 3) | k);
+        __syncwarp();
+        for (int it = lane; it < total; it += 32) {
+            const int code = sm.items[it];
+            const PolyRec<double>& pr = sm.poly[code >> 3];
+            const int k = code & 7;
+            const int kp = (k == 0) ? pr.n - 1 : k - 1;
+            integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, acc);
+        }
+        __syncwarp();
     }
 }
 
 template <int WARPS, int CAP>
 __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc, EvalIO io) {
-    __shared__ unsigned frontier[WARPS][2][CAP];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpSmem<CAP>& sm = reinterpret_cast<WarpSmem<CAP>*>(smem_raw)[wib];
     const long long n_prob = io.n_env * sc.n_small;
     for (long long prob = (long long)blockIdx.x * WARPS + wib; prob < n_prob; prob += (long long)gridDim.x * WARPS) {
         const long long env = prob / sc.n_small;
@@ -86,8 +118,8 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
         broad_phase_xform(cx.x21, Rab, tab);
 
         // ---- 1. broad phase ---------------------------------------------------------------------------
-        unsigned* cur = frontier[wib][0];
-        unsigned* nxt = frontier[wib][1];
+        unsigned* cur = sm.frontier[0];
+        unsigned* nxt = sm.frontier[1];
         int n = 1;
         int flags = 0;
         if (lane == 0) cur[0] = enc(0, 0);
@@ -118,9 +150,7 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
                         }
                     }
                 }
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const int incl = warp_incl_scan(cnt, lane);
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 const int at = n_out + incl - cnt;
                 if (at + cnt <= CAP) {
@@ -155,13 +185,13 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
             acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
             if (ins.model == PFC_MODEL_REGULARIZED) {
                 acc.reset(ACC_REGULARIZED);
-                run_pairs(sc, ins, cur, n, lane, cx, acc, flags);
+                run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
                 contact = warp_sum_int(acc.n_points) > 0;
 #pragma unroll
                 for (int j = 0; j < 6; ++j) w[j] = warp_sum(acc.a[j]);
             } else {
                 acc.reset(ACC_COP);
-                run_pairs(sc, ins, cur, n, lane, cx, acc, flags);
+                run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
                 contact = warp_sum_int(acc.n_points) > 0;
                 if (contact) {
                     double c[10];
@@ -170,21 +200,25 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
                     const Vec3<double> cop = mk<double>(c[7] / c[6], c[8] / c[6], c[9] / c[6]);
                     acc.cop = cop;
                     acc.reset(ACC_STIFFNESS);
-                    run_pairs(sc, ins, cur, n, lane, cx, acc, flags);
-                    double K21[21];
+                    run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
+                    // lane 0 factors the 6x6 stiffness using the (now idle) polygon slots as scratch
+                    double* scr = reinterpret_cast<double*>(sm.poly);
+                    double* K21 = scr + 108;
+                    double* Sinv = sm.bris;
+                    double* Kh = sm.bris + 6;
 #pragma unroll
-                    for (int j = 0; j < 21; ++j) K21[j] = warp_sum(acc.a[j]) * ins.p[1];
-                    double Sinv[6], Kh[36], s[6], tmp[6];
-                    decompose_K(K21, ins.p[6], Sinv, Kh);
+                    for (int j = 0; j < 21; ++j) { const double v = warp_sum(acc.a[j]) * ins.p[1]; if (lane == 0) K21[j] = v; }
+                    if (lane == 0) decompose_K(K21, ins.p[6], Sinv, Kh, scr);
+                    __syncwarp();
+                    double s[6];
                     for (int j = 0; j < 6; ++j) s[j] = sv[j];
                     for (int i = 0; i < 6; ++i) {
                         double t = 0.0;
                         for (int j = 0; j < 6; ++j) t += Kh[6 * i + j] * s[j];
-                        tmp[i] = t;
+                        acc.delta[i] = Sinv[i] * t;
                     }
-                    for (int i = 0; i < 6; ++i) acc.delta[i] = Sinv[i] * tmp[i];
                     acc.reset(ACC_BRISTLE);
-                    run_pairs(sc, ins, cur, n, lane, cx, acc, flags);
+                    run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
                     double f[6];
 #pragma unroll
                     for (int j = 0; j < 6; ++j) f[j] = warp_sum(acc.a[j]);
@@ -205,7 +239,7 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
                 }
             }
         }
-        flags = __reduce_or_sync(0xffffffffu, flags);
+        flags = (int)__reduce_or_sync(0xffffffffu, (unsigned)flags);
         if (lane == 0) {
             if (!contact) {
 #pragma unroll
@@ -240,23 +274,32 @@ __global__ void dump_traction_kernel(SceneDev sc, EvalIO io, long long env, int 
     acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = out; acc.dump_cap = cap;
     acc.reset(ACC_DUMP);
     int flags = 0;
-    for (long long i = 0; i < n_pairs; ++i) {
-        const TetRec& t2 = sc.tets[ins.prim_base2 + pairs[2 * i + 1]];
-        if (ins.kind1 == 0) narrow_tri_tet(sc.tris[ins.prim_base1 + pairs[2 * i]], t2, cx, acc, flags);
-        else narrow_tet_tet(sc.tets[ins.prim_base1 + pairs[2 * i]], t2, cx, acc, flags);
-    }
+    for (long long i = 0; i < n_pairs; ++i) integrate_pair(sc, ins, pairs[2 * i], pairs[2 * i + 1], cx, acc, flags);
     *n_points = acc.n_points;
 }
+
+int g_small_blocks = 0;
 
 }  // namespace
 
 cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, cudaStream_t stream, int* n_launches) {
     const long long n_prob = io.n_env * sc.n_small;
     if (n_prob == 0) return cudaSuccess;
+    auto kern = eval_small_f64_kernel<kSmallWarps, kSmallCap>;
+    const size_t smem = sizeof(WarpSmem<kSmallCap>) * kSmallWarps;
+    if (g_small_blocks == 0) {  // persistent grid: as many CTAs as can be resident on the device
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, dev = 0, n_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSmallWarps * 32, smem);
+        if (e != cudaSuccess) return e;
+        g_small_blocks = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
     long long blocks = (n_prob + kSmallWarps - 1) / kSmallWarps;
-    const long long max_blocks = 148LL * 64;
-    if (blocks > max_blocks) blocks = max_blocks;
-    eval_small_f64_kernel<kSmallWarps, kSmallCap><<<(unsigned)blocks, kSmallWarps * 32, 0, stream>>>(sc, io);
+    if (blocks > g_small_blocks) blocks = g_small_blocks;
+    kern<<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io);
     if (n_launches) ++*n_launches;
     return cudaGetLastError();
 }

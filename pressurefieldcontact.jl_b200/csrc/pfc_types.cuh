@@ -48,9 +48,9 @@ struct InsDev {
     int32_t small;       // 1: handled by the fused warp-per-instruction kernel
     int32_t key_bits;    // max DFS-key length (depth1 + depth2) for the large path's sort
     double chi, Ebar1, Ebar2;
-    // regularized: mu_s, mu_d, v_c, v_mu_s, v_mu_d
-    // bristle:     tau, k_bar, mu_s, mu_d, Ts_mu_s, Ts_mu_d, magic
-    double p[7];
+    // regularized: mu_s, mu_d, v_c, v_mu_s, v_mu_d, slope = (mu_d - mu_s) / (v_mu_d - v_mu_s), 1 / v_c
+    // bristle:     tau, k_bar, mu_s, mu_d, Ts_mu_s, Ts_mu_d, magic, slope = (mu_d - mu_s) / (Ts_mu_d - Ts_mu_s)
+    double p[8];
 };
 
 // flags written per (env, instruction)
