@@ -104,6 +104,10 @@ int pfc_set_shard(pfc_ctx* ctx, int rank, int world);
 int pfc_sync(pfc_ctx* ctx);
 void* pfc_stream(pfc_ctx* ctx);            /* the cudaStream_t kernels are launched on (for CUDA-event timing) */
 int64_t pfc_launch_count(pfc_ctx* ctx);   /* kernels launched by this context so far */
+/* Per-kernel device timing (CUDA events on the context's stream): enable, evaluate, then read the durations in
+ * milliseconds of the last evaluation: ms[0] = broad-phase kernel, ms[1] = narrow-phase/friction/reduction kernel. */
+int pfc_set_timing(pfc_ctx* ctx, int on);
+int pfc_kernel_times(pfc_ctx* ctx, double* ms, int n);
 /* FP64 (DFMA) throughput of the context's device in TFLOP/s: the roofline denominator of the clip/quadrature kernels. */
 int pfc_measure_fp64_peak(pfc_ctx* ctx, double* tflops);
 int pfc_counters(pfc_ctx* ctx, int64_t* n_node_pairs_tested, int64_t* n_candidate_pairs);

@@ -22,7 +22,7 @@ _vp = C.c_void_p
 SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
     "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_sync", "pfc_stream",
-    "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_last_error", "pfc_version",
+    "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
 ]
 
 
@@ -59,6 +59,8 @@ def lib():
         L.pfc_launch_count.restype = C.c_int64
         L.pfc_counters.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.pfc_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
+        L.pfc_set_timing.argtypes = [_vp, C.c_int]
+        L.pfc_kernel_times.argtypes = [_vp, C.POINTER(C.c_double), C.c_int]
         L.pfc_last_error.restype = C.c_char_p
         L.pfc_version.restype = C.c_char_p
         _LIB = L
@@ -196,6 +198,15 @@ class Context:
         v = C.c_double(0.0)
         _check(lib().pfc_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+    def set_timing(self, on: bool = True):
+        _check(lib().pfc_set_timing(self._h, int(on)))
+
+    def kernel_times(self):
+        """(broad_ms, narrow_ms) of the last evaluation (needs set_timing(True))."""
+        ms = (C.c_double * 4)()
+        _check(lib().pfc_kernel_times(self._h, ms, 4))
+        return ms[0], ms[1]
 
     def counters(self):
         a, b = C.c_int64(0), C.c_int64(0)

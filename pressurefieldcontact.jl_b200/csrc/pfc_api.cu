@@ -84,6 +84,11 @@ struct pfc_ctx {
     const double* last_X = nullptr; const double* last_tw = nullptr;  // device pointers of the last evaluation
     int64_t launches = 0;
     int shard_rank = 0, shard_world = 1;
+    int small_max_pairs = 1;
+    DevBuf<unsigned> d_small_pairs;  // broad -> narrow pair lists of the small path: [env][ins][cap]
+    bool timing = false;
+    cudaEvent_t ev[8] = {};
+    bool ev_valid = false;
 };
 
 namespace {
@@ -157,7 +162,8 @@ int pfc_destroy(pfc_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release();
     c->d_X.release(); c->d_tw.release(); c->d_s.release(); c->d_w.release(); c->d_sd.release(); c->d_np.release(); c->d_fl.release();
-    c->d_dbg_pairs.release(); c->d_last_np.release();
+    c->d_dbg_pairs.release(); c->d_last_np.release(); c->d_small_pairs.release();
+    for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     delete c;
     return PFC_OK;
 }
@@ -304,7 +310,7 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
             d.p[5] = (d.p[1] - d.p[0]) / (d.p[4] - d.p[3]); d.p[6] = 1.0 / d.p[2]; }
         else { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = h.params[3]; d.p[4] = 2 * h.params[2]; d.p[5] = 3 * h.params[2]; d.p[6] = h.params[4];
             d.p[7] = (d.p[3] - d.p[2]) / (d.p[5] - d.p[4]); }
-        if (d.small) small.push_back(int32_t(k));
+        if (d.small) { small.push_back(int32_t(k)); c->small_max_pairs = std::max(c->small_max_pairs, int(m1.n_prim * m2.n_prim)); }
         c->h_ins.push_back(d);
     }
     CU(c->d_nodes.ensure(nodes.size()));
@@ -337,7 +343,9 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
         c->dbg_n_env = io.n_env;
     } else { io.dbg_pairs = nullptr; io.dbg_cap = 0; }
     int nl = 0;
-    CU(launch_eval_small_f64(c->scene, io, c->stream, &nl));
+    CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * n_ins));
+    CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, c->timing ? c->ev : nullptr));
+    c->ev_valid = c->timing;
     c->launches += nl;
     c->last_X = io.X; c->last_tw = io.twist;
     if (c->keep_pairs) {
@@ -460,6 +468,28 @@ int pfc_measure_fp64_peak(pfc_ctx* c, double* tflops) {
     CU(cudaSetDevice(c->device));
     CU(measure_fp64_peak(c->stream, tflops));
     c->launches += 5;
+    return PFC_OK;
+}
+
+int pfc_set_timing(pfc_ctx* c, int on) {
+    if (!c) return fail(PFC_E_ARG, "pfc_set_timing: NULL context");
+    CU(cudaSetDevice(c->device));
+    if (on && !c->ev[0]) for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&c->ev[k]));
+    c->timing = on != 0;
+    c->ev_valid = false;
+    return PFC_OK;
+}
+
+int pfc_kernel_times(pfc_ctx* c, double* ms, int n) {
+    if (!c || !ms || n < 2) return fail(PFC_E_ARG, "pfc_kernel_times: bad argument");
+    if (!c->ev_valid) return fail(PFC_E_ARG, "pfc_kernel_times: enable pfc_set_timing and evaluate first");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev[2]));
+    float a = 0, b = 0;
+    CU(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    CU(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    ms[0] = a; ms[1] = b;
+    for (int k = 2; k < n; ++k) ms[k] = 0.0;
     return PFC_OK;
 }
 

@@ -22,7 +22,10 @@ struct EvalIO {
 constexpr int kSmallCap = 512;      // frontier / pair capacity of the fused small path
 constexpr int kSmallWarps = 4;      // warps (= instructions in flight) per CTA
 
-cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, cudaStream_t stream, int* n_launches);
+int small_cap(int max_pairs);
+// ev: optional array of 3 events recorded before the broad kernel, between the two kernels and after the narrow kernel
+cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches,
+                                  cudaEvent_t* ev = nullptr);
 
 // single-thread debug kernel: re-runs the narrow phase of one (env, ins) over a given pair list in
 // order and writes the traction points (8 doubles each) -- the reference's TractionCache.

@@ -61,10 +61,10 @@ template <class T> PFC_D Vec3<T> sub_proj(const Vec3<T>& v, const Vec3<T>& n) { 
     return mk<T>(fma_(t, n.x, v.x), fma_(t, n.y, v.y), fma_(t, n.z, v.z));
 }
 
-template <class T> struct Accum {
+template <class T, int NA = 21> struct Accum {
     int mode;
     int n_points;
-    T a[21];
+    T a[NA];  // 6 suffice for regularized-only scenes, 21 for the bristle stiffness pass
     const double* fp;   // friction parameters (InsDev::p)
     Vec3<T> w_ang, w_lin;
     Vec3<T> cop;
@@ -72,10 +72,13 @@ template <class T> struct Accum {
     double* dump;       // ACC_DUMP: 8 doubles per point
     int dump_cap;
 
+    // constant-index access that stays in bounds when the unused modes are compiled for a small NA
+    PFC_D T& at(int i) { return a[i < NA ? i : NA - 1]; }
+
     PFC_D void reset(int m) {
         mode = m; n_points = 0;
 #pragma unroll
-        for (int k = 0; k < 21; ++k) a[k] = T(0.0);
+        for (int k = 0; k < NA; ++k) a[k] = T(0.0);
     }
 
     PFC_D void point(const Vec3<T>& n, const Vec3<T>& r, const T& dA, const T& p) {
@@ -96,42 +99,42 @@ template <class T> struct Accum {
             const Vec3<T> tk = mk<T>(p_dA * n.x + vt.x * coef, p_dA * n.y + vt.y * coef, p_dA * n.z + vt.z * coef);
             const Vec3<T> m = cross(r, tk);
             a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += tk.x; a[4] += tk.y; a[5] += tk.z;
-        } else if (mode == ACC_COP) {
+        } else if (NA >= 10 && mode == ACC_COP) {
             const Vec3<T> lam = n * p_dA;
             const Vec3<T> m = cross(r, lam);
-            a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += lam.x; a[4] += lam.y; a[5] += lam.z;
-            a[6] += p_dA;
-            a[7] += p_dA * r.x; a[8] += p_dA * r.y; a[9] += p_dA * r.z;
-        } else if (mode == ACC_STIFFNESS) {
+            at(0) += m.x; at(1) += m.y; at(2) += m.z; at(3) += lam.x; at(4) += lam.y; at(5) += lam.z;
+            at(6) += p_dA;
+            at(7) += p_dA * r.x; at(8) += p_dA * r.y; at(9) += p_dA * r.z;
+        } else if (NA >= 21 && mode == ACC_STIFFNESS) {
             // K11 upper (0..5), K12 full row-major (6..14), K22 upper (15..20); k_bar applied by the caller
             const Vec3<T> q = r - cop;
             const Vec3<T> c = cross(q, n);
             const T q0 = q.x * q.x, q1 = q.y * q.y, q2 = q.z * q.z;
             // K11 -= p_dA * ([q]x^2 + c c')
-            a[0] -= p_dA * ((-q1 - q2) + c.x * c.x);
-            a[1] -= p_dA * (q.x * q.y + c.x * c.y);
-            a[2] -= p_dA * (q.x * q.z + c.x * c.z);
-            a[3] -= p_dA * ((-q0 - q2) + c.y * c.y);
-            a[4] -= p_dA * (q.y * q.z + c.y * c.z);
-            a[5] -= p_dA * ((-q0 - q1) + c.z * c.z);
+            at(0) -= p_dA * ((-q1 - q2) + c.x * c.x);
+            at(1) -= p_dA * (q.x * q.y + c.x * c.y);
+            at(2) -= p_dA * (q.x * q.z + c.x * c.z);
+            at(3) -= p_dA * ((-q0 - q2) + c.y * c.y);
+            at(4) -= p_dA * (q.y * q.z + c.y * c.z);
+            at(5) -= p_dA * ((-q0 - q1) + c.z * c.z);
             // K12 += p_dA * ([q]x - c n')
-            a[6] += p_dA * (-(c.x * n.x));
-            a[7] += p_dA * (-q.z - c.x * n.y);
-            a[8] += p_dA * (q.y - c.x * n.z);
-            a[9] += p_dA * (q.z - c.y * n.x);
-            a[10] += p_dA * (-(c.y * n.y));
-            a[11] += p_dA * (-q.x - c.y * n.z);
-            a[12] += p_dA * (-q.y - c.z * n.x);
-            a[13] += p_dA * (q.x - c.z * n.y);
-            a[14] += p_dA * (-(c.z * n.z));
+            at(6) += p_dA * (-(c.x * n.x));
+            at(7) += p_dA * (-q.z - c.x * n.y);
+            at(8) += p_dA * (q.y - c.x * n.z);
+            at(9) += p_dA * (q.z - c.y * n.x);
+            at(10) += p_dA * (-(c.y * n.y));
+            at(11) += p_dA * (-q.x - c.y * n.z);
+            at(12) += p_dA * (-q.y - c.z * n.x);
+            at(13) += p_dA * (q.x - c.z * n.y);
+            at(14) += p_dA * (-(c.z * n.z));
             // K22 += p_dA * (I - n n')
-            a[15] += p_dA * (1.0 - n.x * n.x);
-            a[16] += p_dA * (-(n.x * n.y));
-            a[17] += p_dA * (-(n.x * n.z));
-            a[18] += p_dA * (1.0 - n.y * n.y);
-            a[19] += p_dA * (-(n.y * n.z));
-            a[20] += p_dA * (1.0 - n.z * n.z);
-        } else if (mode == ACC_BRISTLE) {
+            at(15) += p_dA * (1.0 - n.x * n.x);
+            at(16) += p_dA * (-(n.x * n.y));
+            at(17) += p_dA * (-(n.x * n.z));
+            at(18) += p_dA * (1.0 - n.y * n.y);
+            at(19) += p_dA * (-(n.y * n.z));
+            at(20) += p_dA * (1.0 - n.z * n.z);
+        } else if (NA >= 21 && mode == ACC_BRISTLE) {
             // fp: tau, k_bar, mu_s, mu_d, Ts_mu_s, Ts_mu_d, magic, slope
             const Vec3<T> x2 = r - cop;
             const Vec3<T> d_ang = mk<T>(delta[0], delta[1], delta[2]);
@@ -149,7 +152,7 @@ template <class T> struct Accum {
             }
             const Vec3<T> Tc = Ts * coef;
             const Vec3<T> m = cross(x2, Tc);
-            a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += Tc.x; a[4] += Tc.y; a[5] += Tc.z;
+            at(0) += m.x; at(1) += m.y; at(2) += m.z; at(3) += Tc.x; at(4) += Tc.y; at(5) += Tc.z;
         } else {  // ACC_DUMP (debug / parity): n(3) r(3) dA p, values only
             if (n_points < dump_cap) {
                 double* o = dump + 8 * n_points;
@@ -162,8 +165,8 @@ template <class T> struct Accum {
 };
 
 // ---- stage B: one sub-triangle (v1, v2, centroid) of a contact polygon ------------------------------------
-template <class T> PFC_D void integrate_subtri(const Vec3<T>& v1, const Vec3<T>& v2, const Vec3<T>& cen, const Vec3<T>& nrm, const double* eps_r,
-                                               const PatchCtx<T>& cx, Accum<T>& acc) {
+template <class T, int NA> PFC_D void integrate_subtri(const Vec3<T>& v1, const Vec3<T>& v2, const Vec3<T>& cen, const Vec3<T>& nrm, const double* eps_r,
+                                                       const PatchCtx<T>& cx, Accum<T, NA>& acc) {
     const T area = dot(nrm, cross(v2 - v1, cen - v2) * 0.5);
     if (!(0.0 < val(area))) return;
     const double g0 = eps_r[0], g1 = eps_r[1], g2 = eps_r[2], g3 = eps_r[3];
@@ -258,6 +261,44 @@ template <class T> PFC_D bool clip_tet_tet(const TetRec& t1, const TetRec& t2, c
     return true;
 }
 
+// Cheap, exact rejection before the full clip (stage A1).  A triangle whose three vertices all have
+// zeta_i <= 0 for one face i is clipped away whatever the other faces do: every vertex the clipper
+// creates is c1 * z_pos - c2 * z_non with c1 >= 0 >= c2, so its zeta_i stays <= 0 and the
+// reference returns the empty polygon at face i at the latest.  For tet-tet pairs the equal-pressure
+// plane must have tet-1 vertices strictly on both sides (plane_tet_intersection.jl:27-29).
+template <class T> PFC_D bool prefilter_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx) {
+    const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
+    if (ins.kind1 == 0) {
+        const TriRec& tri = sc.tris[ins.prim_base1 + prim1];
+        unsigned all_non_pos = 0xfu;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const Vec3<T> p = apply_d(cx.x21, mk<double>(tri.v[3 * k], tri.v[3 * k + 1], tri.v[3 * k + 2]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const T z = t2.inv[4 * i] * p.x + t2.inv[4 * i + 1] * p.y + t2.inv[4 * i + 2] * p.z + t2.inv[4 * i + 3];
+                if (!(val(z) <= 0.0)) all_non_pos &= ~(1u << i);
+            }
+        }
+        return all_non_pos == 0;
+    }
+    const TetRec& t1 = sc.tets[ins.prim_base1 + prim1];
+    const double g0 = cx.Ebar1 * t1.eps_r[0], g1 = cx.Ebar1 * t1.eps_r[1], g2 = cx.Ebar1 * t1.eps_r[2], g3 = cx.Ebar1 * t1.eps_r[3];
+    const Xform<T>& Y = cx.x12;
+    const T pl0 = cx.Ebar2 * t2.eps_r[0] - (g0 * Y.r[0] + g1 * Y.r[3] + g2 * Y.r[6]);
+    const T pl1 = cx.Ebar2 * t2.eps_r[1] - (g0 * Y.r[1] + g1 * Y.r[4] + g2 * Y.r[7]);
+    const T pl2 = cx.Ebar2 * t2.eps_r[2] - (g0 * Y.r[2] + g1 * Y.r[5] + g2 * Y.r[8]);
+    const T pl3 = cx.Ebar2 * t2.eps_r[3] - (g0 * Y.t[0] + g1 * Y.t[1] + g2 * Y.t[2] + g3);
+    int n_pos = 0, n_neg = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const Vec3<T> v = apply_d(cx.x21, mk<double>(t1.v[3 * k], t1.v[3 * k + 1], t1.v[3 * k + 2]));
+        const double pr = val(pl0 * v.x + pl1 * v.y + pl2 * v.z + pl3);
+        n_pos += (0.0 < pr); n_neg += (pr < 0.0);
+    }
+    return n_pos != 0 && n_neg != 0;
+}
+
 // stage A dispatch on the kind of mesh 1
 template <class T> PFC_D bool clip_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx, PolyRec<T>& out, int& flags) {
     const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
@@ -266,7 +307,7 @@ template <class T> PFC_D bool clip_pair(const SceneDev& sc, const InsDev& ins, i
 }
 
 // stages A + B for one pair on one thread, sub-triangles in the reference's order (previous vertex = last first)
-template <class T> PFC_D void integrate_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx, Accum<T>& acc, int& flags) {
+template <class T, int NA> PFC_D void integrate_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx, Accum<T, NA>& acc, int& flags) {
     PolyRec<T> pr;
     if (!clip_pair(sc, ins, prim1, prim2, cx, pr, flags)) return;
     Vec3<T> v2 = pr.v[pr.n - 1];

@@ -45,18 +45,21 @@ PFC_D bool sat_test(const SatA& A, const NodeRec& b) {
         t[i] = add_(add_(add_(mul_(A.R[3 * i], b.c[0]), mul_(A.R[3 * i + 1], b.c[1])), mul_(A.R[3 * i + 2], b.c[2])), A.t[i]);
     }
     const double ea0 = A.e[0], ea1 = A.e[1], ea2 = A.e[2], eb0 = b.e[0], eb1 = b.e[1], eb2 = b.e[2];
+    // All 15 axes are evaluated and OR-ed: the outcome equals the reference's early-exit chain, but
+    // the 15 short dependency chains are independent, which is what hides the FP64 latency.
+    bool sep = false;
     // face test 1/2: r_a = e_a, r_b = abs_R * e_b
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const double rb = add_(add_(mul_(aR[3 * i], eb0), mul_(aR[3 * i + 1], eb1)), mul_(aR[3 * i + 2], eb2));
-        if (add_(A.e[i], rb) < fabs(t[i])) return false;
+        sep |= add_(A.e[i], rb) < fabs(t[i]);
     }
     // face test 2/2: T = |R' t|, r_a = abs_R' * e_a, r_b = e_b
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const double T = fabs(add_(add_(mul_(R[j], t[0]), mul_(R[3 + j], t[1])), mul_(R[6 + j], t[2])));
         const double ra = add_(add_(mul_(aR[j], ea0), mul_(aR[3 + j], ea1)), mul_(aR[6 + j], ea2));
-        if (add_(ra, b.e[j]) < T) return false;
+        sep |= add_(ra, b.e[j]) < T;
     }
     // edge-edge tests.  R0/R1/R2 are the rows of R; s100(v) = (v1, v0, v0), s221(v) = (v2, v2, v1).
     const double eb100[3] = {eb1, eb0, eb0}, eb221[3] = {eb2, eb2, eb1};
@@ -67,7 +70,7 @@ PFC_D bool sat_test(const SatA& A, const NodeRec& b) {
         const double T = fabs(sub_(mul_(t[2], R[3 + j]), mul_(t[1], R[6 + j])));
         const double ra = add_(mul_(ea1, aR[6 + j]), mul_(ea2, aR[3 + j]));
         const double rb = add_(mul_(eb100[j], aR[i221[j]]), mul_(eb221[j], aR[i100[j]]));
-        if (add_(ra, rb) < T) return false;
+        sep |= add_(ra, rb) < T;
     }
     // cross 2/3: a1 x b_j
 #pragma unroll
@@ -75,7 +78,7 @@ PFC_D bool sat_test(const SatA& A, const NodeRec& b) {
         const double T = fabs(sub_(mul_(t[0], R[6 + j]), mul_(t[2], R[j])));
         const double ra = add_(mul_(ea0, aR[6 + j]), mul_(ea2, aR[j]));
         const double rb = add_(mul_(eb100[j], aR[3 + i221[j]]), mul_(eb221[j], aR[3 + i100[j]]));
-        if (add_(ra, rb) < T) return false;
+        sep |= add_(ra, rb) < T;
     }
     // cross 3/3: a2 x b_j
 #pragma unroll
@@ -83,9 +86,9 @@ PFC_D bool sat_test(const SatA& A, const NodeRec& b) {
         const double T = fabs(sub_(mul_(t[1], R[j]), mul_(t[0], R[3 + j])));
         const double ra = add_(mul_(ea0, aR[3 + j]), mul_(ea1, aR[j]));
         const double rb = add_(mul_(eb100[j], aR[6 + i221[j]]), mul_(eb221[j], aR[6 + i100[j]]));
-        if (add_(ra, rb) < T) return false;
+        sep |= add_(ra, rb) < T;
     }
-    return true;
+    return !sep;
 }
 
 }  // namespace pfc

@@ -7,7 +7,8 @@
 //   calcTriTetIntersections! (dual-tree traversal, src/obb/tree_types.jl:88-111)
 //   integrate_over!          (loop over candidate pairs, :136-143)
 //   yes_contact!/no_contact! (src/contact_algorithms_friction.jl:50-81, 119-143)
-// -- is done by one warp of a persistent grid without leaving the SM:
+// -- is done by two persistent-grid kernels (broad_small_kernel, narrow_small_kernel; split so that
+// the SAT-only kernel runs at high occupancy) in which a group of G lanes owns one instruction:
 //   1. Broad phase: warp-cooperative in-place expansion of the node-pair frontier held in shared
 //      memory.  Each round every lane tests one node pair (15-axis SAT, bit-exact) and the
 //      survivors' children replace it *in order* through a warp prefix sum, so when the frontier
@@ -21,6 +22,8 @@
 //      reproducible; no floating-point atomics).  Bristle friction runs the three passes of
 //      bristle_wrench_in_world with a warp reduction between passes.
 // HBM traffic per instruction is the boundary data only: 22 doubles in, 6 doubles + 2 words out.
+#include <cstdlib>
+
 #include "pfc_bristle.cuh"
 #include "pfc_launch.h"
 #include "pfc_patch.cuh"
@@ -66,69 +69,61 @@ PFC_D void broad_phase_xform(const Xform<double>& x21, double* Rab, double* tab)
     }
 }
 
-// per-warp shared memory
-template <int CAP> struct WarpSmem {
-    PolyRec<double> poly[32];   // stage A output, one slot per lane
-    unsigned frontier[2][CAP];
-    unsigned char items[256];   // stage B work list: (slot << 3) | edge
-    double bris[42];            // bristle: Sinv (6) + K̄^(-1/2) (36), kept across the friction pass
-};
+// A warp is split into 32 / G groups of G lanes; each group owns one (environment, instruction)
+// problem at a time.  Small frontiers (a 12 x 12-leaf box pair has at most 144 leaf pairs and
+// ~10-40 node pairs per level) leave most of a 32-lane warp idle; with G = 8 four problems share
+// the warp and the lanes stay dense.
 
-// Narrow phase over the warp's pair list for one accumulator mode.
-template <int CAP>
-PFC_D void run_pairs(const SceneDev& sc, const InsDev& ins, WarpSmem<CAP>& sm, const unsigned* pairs, int n, int lane, const PatchCtx<double>& cx,
-                     Accum<double>& acc, int& flags) {
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        int nv = 0;
-        if (i < n) {
-            const unsigned e = pairs[i];
-            if (clip_pair(sc, ins, dec_a(e), dec_b(e), cx, sm.poly[lane], flags)) nv = sm.poly[lane].n;
-        }
-        const int incl = warp_incl_scan(nv, lane);
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        for (int k = 0; k < nv; ++k) sm.items[incl - nv + k] = (unsigned char)((lane << 3) | k);
-        __syncwarp();
-        for (int it = lane; it < total; it += 32) {
-            const int code = sm.items[it];
-            const PolyRec<double>& pr = sm.poly[code >> 3];
-            const int k = code & 7;
-            const int kp = (k == 0) ? pr.n - 1 : k - 1;
-            integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, acc);
-        }
-        __syncwarp();
-    }
+// group-restricted collectives (gmask = the lanes of this group; width-G shuffles stay inside the segment)
+template <int G> PFC_D int group_incl_scan(unsigned gmask, int x, int gl) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) { const int v = __shfl_up_sync(gmask, x, o, G); if (gl >= o) x += v; }
+    return x;
+}
+template <int G> PFC_D int group_sum_int(unsigned gmask, int x) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o, G);
+    return x;
+}
+// fixed-order xor-butterfly: every lane of the group ends with the same bits
+template <int G> PFC_D double group_sum(unsigned gmask, double x) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o, G);
+    return x;
 }
 
-template <int WARPS, int CAP>
-__global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc, EvalIO io) {
+// ---- kernel 1: broad phase ------------------------------------------------------------------------------------
+// shared memory per warp: unsigned frontier[32/G][2][cap]
+template <int WARPS, int G, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) broad_small_kernel(SceneDev sc, EvalIO io, int cap, unsigned* __restrict__ pairs_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NG = 32 / G;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpSmem<CAP>& sm = reinterpret_cast<WarpSmem<CAP>*>(smem_raw)[wib];
+    const int grp = lane / G, gl = lane % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    unsigned* frontier = reinterpret_cast<unsigned*>(smem_raw) + (size_t)2 * cap * (wib * NG + grp);
     const long long n_prob = io.n_env * sc.n_small;
-    for (long long prob = (long long)blockIdx.x * WARPS + wib; prob < n_prob; prob += (long long)gridDim.x * WARPS) {
+    const long long stride = (long long)gridDim.x * WARPS * NG;
+    for (long long prob = ((long long)blockIdx.x * WARPS + wib) * NG + grp; prob < n_prob; prob += stride) {
         const long long env = prob / sc.n_small;
         const int k = sc.small_ins[prob - env * sc.n_small];
         const InsDev& ins = sc.ins[k];
         const long long ei = env * sc.n_ins + k;
-
-        PatchCtx<double> cx;
-        load_xform(io.X + 16 * ei, cx.x21);
+        Xform<double> x21;
+        load_xform(io.X + 16 * ei, x21);
         double Rab[9], tab[3];
-        broad_phase_xform(cx.x21, Rab, tab);
-
-        // ---- 1. broad phase ---------------------------------------------------------------------------
-        unsigned* cur = sm.frontier[0];
-        unsigned* nxt = sm.frontier[1];
+        broad_phase_xform(x21, Rab, tab);
+        unsigned* cur = frontier;
+        unsigned* nxt = frontier + cap;
         int n = 1;
         int flags = 0;
-        if (lane == 0) cur[0] = enc(0, 0);
-        __syncwarp();
+        if (gl == 0) cur[0] = enc(0, 0);
+        __syncwarp(gmask);
         for (;;) {
             int n_out = 0;
             bool open = false;
-            for (int base = 0; base < n; base += 32) {
-                const int i = base + lane;
+            for (int base = 0; base < n; base += G) {
+                const int i = base + gl;
                 int cnt = 0;
                 unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
                 if (i < n) {
@@ -150,66 +145,175 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
                         }
                     }
                 }
-                const int incl = warp_incl_scan(cnt, lane);
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int incl = group_incl_scan<G>(gmask, cnt, gl);
+                const int total = __shfl_sync(gmask, incl, G - 1, G);
                 const int at = n_out + incl - cnt;
-                if (at + cnt <= CAP) {
+                if (at + cnt <= cap) {
                     if (cnt > 0) nxt[at] = c0;
                     if (cnt > 1) nxt[at + 1] = c1;
                     if (cnt > 2) { nxt[at + 2] = c2; nxt[at + 3] = c3; }
                 } else if (cnt > 0) flags |= kFlagOverflow;
                 n_out += total;
             }
-            __syncwarp();
+            __syncwarp(gmask);
             unsigned* t = cur; cur = nxt; nxt = t;
-            n = n_out < CAP ? n_out : CAP;
-            if (!__any_sync(0xffffffffu, open)) break;
+            n = n_out < cap ? n_out : cap;
+            if (!(__ballot_sync(gmask, open) & gmask)) break;
         }
+        unsigned* po = pairs_out + (size_t)cap * ei;
+        for (int i = gl; i < n; i += G) po[i] = cur[i];
         if (io.dbg_pairs) {
             int* out = io.dbg_pairs + 2 * (long long)io.dbg_cap * ei;
-            for (int i = lane; i < n && i < io.dbg_cap; i += 32) { out[2 * i] = dec_a(cur[i]); out[2 * i + 1] = dec_b(cur[i]); }
+            for (int i = gl; i < n && i < io.dbg_cap; i += G) { out[2 * i] = dec_a(cur[i]); out[2 * i + 1] = dec_b(cur[i]); }
         }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) flags |= __shfl_xor_sync(gmask, flags, o, G);
+        if (gl == 0) { io.n_pairs[ei] = n; io.flags[ei] = flags; }
+        __syncwarp(gmask);
+    }
+}
 
-        // ---- 2 + 3. narrow phase, friction, fixed-order reduction ------------------------------------------
+// ---- kernel 2: narrow phase + friction + reduction ---------------------------------------------------------------
+// Per group and accumulator pass:
+//   A1  every lane pre-filters pairs with an exact, cheap rejection test; survivors are compacted
+//       (in pair order) into a shared-memory list -- about 2/3 of the candidates die here;
+//   A2  G survivors at a time are clipped, one per lane, each leaving its polygon in its slot;
+//   B   the round's (polygon, edge) sub-triangles are dealt out one per lane for quadrature + friction.
+// shared memory per warp:  PolyRec poly[32] | PatchCtx cx[32/G] | double bris[32/G][42] |
+//                          unsigned short surv[32/G][cap] | unsigned char items[32/G][8*G]
+template <int G> struct NarrowLayout {
+    static constexpr int NG = 32 / G;
+    __host__ __device__ static size_t bytes(int cap) {
+        return sizeof(PolyRec<double>) * 32 + (sizeof(PatchCtx<double>) + sizeof(double) * 42 + sizeof(unsigned short) * cap + 8 * G) * NG;
+    }
+};
+template <int G> struct GroupSmem {
+    PolyRec<double>* poly;   // this group's G slots (stage A2 output, one per lane)
+    PatchCtx<double>* cx;    // transforms, twist and material constants of the group's instruction
+    double* bris;            // bristle: Sinv (6) + K̄^(-1/2) (36), kept across the friction pass
+    unsigned short* surv;    // indices (into the pair list) of the pairs that survive the pre-filter
+    unsigned char* items;    // stage B work list: (slot-in-group << 3) | edge
+};
+
+template <int G, int NA>
+PFC_D void run_pairs(const SceneDev& sc, const InsDev& ins, const GroupSmem<G>& sm, unsigned gmask, const unsigned* __restrict__ pairs, int n_surv, int gl,
+                     Accum<double, NA>& acc, int& flags) {
+    const PatchCtx<double>& cx = *sm.cx;
+    for (int base = 0; base < n_surv; base += G) {
+        const int i = base + gl;
+        int nv = 0;
+        if (i < n_surv) {
+            const unsigned e = pairs[sm.surv[i]];
+            if (clip_pair(sc, ins, dec_a(e), dec_b(e), cx, sm.poly[gl], flags)) nv = sm.poly[gl].n;
+        }
+        const int incl = group_incl_scan<G>(gmask, nv, gl);
+        const int total = __shfl_sync(gmask, incl, G - 1, G);
+        for (int k = 0; k < nv; ++k) sm.items[incl - nv + k] = (unsigned char)((gl << 3) | k);
+        __syncwarp(gmask);
+        for (int it = gl; it < total; it += G) {
+            const int code = sm.items[it];
+            const PolyRec<double>& pr = sm.poly[code >> 3];
+            const int k = code & 7;
+            const int kp = (k == 0) ? pr.n - 1 : k - 1;
+            integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, acc);
+        }
+        __syncwarp(gmask);
+    }
+}
+
+// HB: the scene has bristle instructions (21 accumulators and the 3-pass code are compiled in)
+template <int WARPS, int G, int MINB, bool HB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) narrow_small_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NG = 32 / G;
+    constexpr int NA = HB ? 21 : 6;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / G, gl = lane % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    GroupSmem<G> sm;
+    {
+        unsigned char* base = smem_raw + NarrowLayout<G>::bytes(cap) * wib;
+        sm.poly = reinterpret_cast<PolyRec<double>*>(base) + grp * G;
+        base += sizeof(PolyRec<double>) * 32;
+        sm.cx = reinterpret_cast<PatchCtx<double>*>(base) + grp;
+        base += sizeof(PatchCtx<double>) * NG;
+        sm.bris = reinterpret_cast<double*>(base) + 42 * grp;
+        base += sizeof(double) * 42 * NG;
+        sm.surv = reinterpret_cast<unsigned short*>(base) + (size_t)cap * grp;
+        base += sizeof(unsigned short) * cap * NG;
+        sm.items = base + 8 * G * grp;
+    }
+    const long long n_prob = io.n_env * sc.n_small;
+    const long long stride = (long long)gridDim.x * WARPS * NG;
+    for (long long prob = ((long long)blockIdx.x * WARPS + wib) * NG + grp; prob < n_prob; prob += stride) {
+        const long long env = prob / sc.n_small;
+        const int k = sc.small_ins[prob - env * sc.n_small];
+        const InsDev& ins = sc.ins[k];
+        const long long ei = env * sc.n_ins + k;
+        const int n = (int)io.n_pairs[ei];
+        int flags = 0;
+        const unsigned* cur = pairs_in + (size_t)cap * ei;
+
         double w[6] = {0, 0, 0, 0, 0, 0};
         bool contact = false;
-        const double* sv = (ins.model == PFC_MODEL_BRISTLE) ? io.s + 6 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
-        double* sd = (ins.model == PFC_MODEL_BRISTLE) ? io.sdot + 6 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
+        const double* sv = (HB && ins.model == PFC_MODEL_BRISTLE) ? io.s + 6 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
+        double* sd = (HB && ins.model == PFC_MODEL_BRISTLE) ? io.sdot + 6 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
+        int n_surv = 0;
         if (n > 0) {
-            cx.x12 = inverse(cx.x21);
-            const double* tw = io.twist + 6 * ei;
-            cx.w_ang = mk<double>(tw[0], tw[1], tw[2]);
-            cx.w_lin = mk<double>(tw[3], tw[4], tw[5]);
-            cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
-            Accum<double> acc;
+            // the group's shared context (every lane would hold identical copies otherwise)
+            if (gl == 0) {
+                PatchCtx<double>& cx = *sm.cx;
+                load_xform(io.X + 16 * ei, cx.x21);
+                cx.x12 = inverse(cx.x21);
+                const double* tw = io.twist + 6 * ei;
+                cx.w_ang = mk<double>(tw[0], tw[1], tw[2]);
+                cx.w_lin = mk<double>(tw[3], tw[4], tw[5]);
+                cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
+            }
+            __syncwarp(gmask);
+            // A1: exact pre-filter + ordered compaction of the survivors
+            for (int base = 0; base < n; base += G) {
+                const int i = base + gl;
+                bool keep = false;
+                if (i < n) { const unsigned e = cur[i]; keep = prefilter_pair(sc, ins, dec_a(e), dec_b(e), *sm.cx); }
+                const unsigned m = __ballot_sync(gmask, keep) & gmask;
+                if (keep) sm.surv[n_surv + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+                n_surv += __popc(m);
+            }
+            __syncwarp(gmask);
+        }
+        if (n_surv > 0) {
+            const PatchCtx<double>& cx = *sm.cx;
+            Accum<double, NA> acc;
             acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
-            if (ins.model == PFC_MODEL_REGULARIZED) {
+            if (!HB || ins.model == PFC_MODEL_REGULARIZED) {
                 acc.reset(ACC_REGULARIZED);
-                run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
-                contact = warp_sum_int(acc.n_points) > 0;
+                run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
+                contact = group_sum_int<G>(gmask, acc.n_points) > 0;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) w[j] = warp_sum(acc.a[j]);
-            } else {
+                for (int j = 0; j < 6; ++j) w[j] = group_sum<G>(gmask, acc.a[j]);
+            } else if (HB) {
                 acc.reset(ACC_COP);
-                run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
-                contact = warp_sum_int(acc.n_points) > 0;
+                run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
+                contact = group_sum_int<G>(gmask, acc.n_points) > 0;
                 if (contact) {
                     double c[10];
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) c[j] = warp_sum(acc.a[j]);
+                    for (int j = 0; j < 10; ++j) c[j] = group_sum<G>(gmask, acc.at(j));
                     const Vec3<double> cop = mk<double>(c[7] / c[6], c[8] / c[6], c[9] / c[6]);
                     acc.cop = cop;
                     acc.reset(ACC_STIFFNESS);
-                    run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
-                    // lane 0 factors the 6x6 stiffness using the (now idle) polygon slots as scratch
+                    run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
+                    // the group's first lane factors the 6x6 stiffness using the (now idle) polygon slots as scratch
+                    // (G slots x 35 doubles >= 129 doubles needs G >= 4)
                     double* scr = reinterpret_cast<double*>(sm.poly);
                     double* K21 = scr + 108;
                     double* Sinv = sm.bris;
                     double* Kh = sm.bris + 6;
 #pragma unroll
-                    for (int j = 0; j < 21; ++j) { const double v = warp_sum(acc.a[j]) * ins.p[1]; if (lane == 0) K21[j] = v; }
-                    if (lane == 0) decompose_K(K21, ins.p[6], Sinv, Kh, scr);
-                    __syncwarp();
+                    for (int j = 0; j < 21; ++j) { const double v = group_sum<G>(gmask, acc.at(j)) * ins.p[1]; if (gl == 0) K21[j] = v; }
+                    if (gl == 0) decompose_K(K21, ins.p[6], Sinv, Kh, scr);
+                    __syncwarp(gmask);
                     double s[6];
                     for (int j = 0; j < 6; ++j) s[j] = sv[j];
                     for (int i = 0; i < 6; ++i) {
@@ -218,15 +322,15 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
                         acc.delta[i] = Sinv[i] * t;
                     }
                     acc.reset(ACC_BRISTLE);
-                    run_pairs(sc, ins, sm, cur, n, lane, cx, acc, flags);
+                    run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
                     double f[6];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) f[j] = warp_sum(acc.a[j]);
+                    for (int j = 0; j < 6; ++j) f[j] = group_sum<G>(gmask, acc.a[j]);
                     const Vec3<double> lin = mk<double>(f[3], f[4], f[5]);
                     const Vec3<double> shift = cross(cop, lin);
                     w[0] = c[0] + (f[0] + shift.x); w[1] = c[1] + (f[1] + shift.y); w[2] = c[2] + (f[2] + shift.z);
                     w[3] = c[3] + f[3]; w[4] = c[4] + f[4]; w[5] = c[5] + f[5];
-                    if (lane == 0) {
+                    if (gl == 0) {
                         const double ti = -(1.0 / ins.p[0]);
                         double sw[6];
                         for (int i = 0; i < 6; ++i) sw[i] = Sinv[i] * f[i];
@@ -239,12 +343,13 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
                 }
             }
         }
-        flags = (int)__reduce_or_sync(0xffffffffu, (unsigned)flags);
-        if (lane == 0) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) flags |= __shfl_xor_sync(gmask, flags, o, G);
+        if (gl == 0) {
             if (!contact) {
 #pragma unroll
                 for (int j = 0; j < 6; ++j) w[j] = 0.0;
-                if (ins.model == PFC_MODEL_BRISTLE) {  // no_contact!(::Bristle)
+                if (HB && ins.model == PFC_MODEL_BRISTLE) {  // no_contact!(::Bristle)
                     const double ti = -(1.0 / ins.p[0]);
                     for (int j = 0; j < 6; ++j) sd[j] = ti * sv[j];
                 }
@@ -252,10 +357,9 @@ __global__ void __launch_bounds__(WARPS * 32) eval_small_f64_kernel(SceneDev sc,
             double* wo = io.wrench + 6 * ei;
 #pragma unroll
             for (int j = 0; j < 6; ++j) wo[j] = w[j];
-            io.n_pairs[ei] = n;
-            io.flags[ei] = flags | (contact ? kFlagContact : 0);
+            io.flags[ei] |= flags | (contact ? kFlagContact : 0);
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
 }
 
@@ -278,30 +382,80 @@ __global__ void dump_traction_kernel(SceneDev sc, EvalIO io, long long env, int 
     *n_points = acc.n_points;
 }
 
-int g_small_blocks = 0;
+int persistent_blocks(const void* kern, int threads, size_t smem, cudaError_t* err) {
+    int per_sm = 0, dev = 0, n_sm = 0;
+    *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    *err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    return n_sm * (per_sm > 0 ? per_sm : 1);
+}
+
+template <int G, int MINB>
+cudaError_t launch_broad_g(const SceneDev& sc, const EvalIO& io, int cap, unsigned* pairs, cudaStream_t stream) {
+    static int cached_cap = -1, cached_blocks = 0;
+    auto kern = broad_small_kernel<kSmallWarps, G, MINB>;
+    const size_t smem = sizeof(unsigned) * 2 * cap * kSmallWarps * (32 / G);
+    if (cached_cap != cap) {
+        cudaError_t e;
+        cached_blocks = persistent_blocks((const void*)kern, kSmallWarps * 32, smem, &e);
+        if (e != cudaSuccess) return e;
+        cached_cap = cap;
+    }
+    constexpr int per_block = kSmallWarps * (32 / G);
+    long long blocks = (io.n_env * sc.n_small + per_block - 1) / per_block;
+    if (blocks > cached_blocks) blocks = cached_blocks;
+    kern<<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
+    return cudaGetLastError();
+}
+
+template <int G, int MINB>
+cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
+    static int cached_cap[2] = {-1, -1}, cached_blocks[2] = {0, 0};
+    const int hb = sc.n_bristle > 0 ? 1 : 0;
+    const void* kern = hb ? (const void*)narrow_small_kernel<kSmallWarps, G, MINB, true> : (const void*)narrow_small_kernel<kSmallWarps, G, MINB, false>;
+    const size_t smem = NarrowLayout<G>::bytes(cap) * kSmallWarps;
+    if (cached_cap[hb] != cap) {
+        cudaError_t e;
+        cached_blocks[hb] = persistent_blocks(kern, kSmallWarps * 32, smem, &e);
+        if (e != cudaSuccess) return e;
+        cached_cap[hb] = cap;
+    }
+    constexpr int per_block = kSmallWarps * (32 / G);
+    long long blocks = (io.n_env * sc.n_small + per_block - 1) / per_block;
+    if (blocks > cached_blocks[hb]) blocks = cached_blocks[hb];
+    if (hb) narrow_small_kernel<kSmallWarps, G, MINB, true><<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
+    else narrow_small_kernel<kSmallWarps, G, MINB, false><<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
+    return cudaGetLastError();
+}
+
+// group size is a run-time choice (three instantiations per kernel); the minimum-blocks hint (register cap) is fixed:
+// 4 CTAs/SM (<=128 registers) for the SAT kernel, 3 (<=168) for the clip/quadrature kernel -- measured best on B200.
+#define PFC_DISPATCH_G(fn, g, minb, ...) ((g) == 8 ? fn<8, minb>(__VA_ARGS__) : (g) == 16 ? fn<16, minb>(__VA_ARGS__) : fn<32, minb>(__VA_ARGS__))
 
 }  // namespace
 
-cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, cudaStream_t stream, int* n_launches) {
-    const long long n_prob = io.n_env * sc.n_small;
-    if (n_prob == 0) return cudaSuccess;
-    auto kern = eval_small_f64_kernel<kSmallWarps, kSmallCap>;
-    const size_t smem = sizeof(WarpSmem<kSmallCap>) * kSmallWarps;
-    if (g_small_blocks == 0) {  // persistent grid: as many CTAs as can be resident on the device
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0, dev = 0, n_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSmallWarps * 32, smem);
-        if (e != cudaSuccess) return e;
-        g_small_blocks = n_sm * (per_sm > 0 ? per_sm : 1);
-    }
-    long long blocks = (n_prob + kSmallWarps - 1) / kSmallWarps;
-    if (blocks > g_small_blocks) blocks = g_small_blocks;
-    kern<<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io);
-    if (n_launches) ++*n_launches;
-    return cudaGetLastError();
+// max_pairs: the largest n_leaf1 * n_leaf2 over the small instructions (frontier capacity needed);
+// pairs: scratch of n_env * n_ins * small_cap(max_pairs) words.
+int small_cap(int max_pairs) { return ((max_pairs > 1 ? max_pairs : 1) + 31) / 32 * 32; }
+
+cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches,
+                                  cudaEvent_t* ev) {
+    if (io.n_env * sc.n_small == 0) return cudaSuccess;
+    const int cap = small_cap(max_pairs);
+    int bg = cap <= 320 ? 16 : 32, ng = 32;
+    // tuning overrides (experiments only)
+    if (const char* e = getenv("PFC_BROAD_G")) bg = atoi(e);
+    if (const char* e = getenv("PFC_NARROW_G")) ng = atoi(e);
+    if (ev) cudaEventRecord(ev[0], stream);
+    cudaError_t e = PFC_DISPATCH_G(launch_broad_g, bg, 4, sc, io, cap, pairs, stream);
+    if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[1], stream);
+    e = PFC_DISPATCH_G(launch_narrow_g, ng, 3, sc, io, cap, pairs, stream);
+    if (ev) cudaEventRecord(ev[2], stream);
+    if (n_launches) *n_launches += 2;
+    return e;
 }
 
 cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long env, int ins, const int* pairs, long long n_pairs, double* out,
