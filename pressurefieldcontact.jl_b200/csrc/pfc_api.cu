@@ -1,4 +1,5 @@
 // pfc_api.cu -- the C ABI of include/pfc.h: scene container, one-time upload, evaluation entry points.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -6,6 +7,7 @@
 #include <vector>
 
 #include "../../include/pfc.h"
+#include "pfc_large.h"
 #include "pfc_launch.h"
 
 using namespace pfc;
@@ -31,7 +33,7 @@ struct HostMesh {
     std::vector<int32_t> leaf_depth;     // per primitive: depth of its leaf node
     std::vector<uint64_t> leaf_path;     // per primitive: root-to-leaf turns, MSB-first in the low `depth` bits
     int depth;                           // max leaf depth
-    int node_base, prim_base;
+    int node_base, prim_base, path_base;
 };
 
 struct HostIns {
@@ -86,6 +88,15 @@ struct pfc_ctx {
     int shard_rank = 0, shard_world = 1;
     int small_max_pairs = 1;
     DevBuf<unsigned> d_small_pairs;  // broad -> narrow pair lists of the small path: [env][ins][cap]
+    // large path
+    DevBuf<int32_t> d_large;
+    DevBuf<unsigned long long> d_leaf_path;
+    DevBuf<unsigned char> d_leaf_depth;
+    LargeScene large_scene{};
+    LargeBuffers* large_buf = nullptr;
+    std::vector<int32_t> large_ins_host;
+    int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
+    EvalIO sharded_io{};
     bool timing = false;
     cudaEvent_t ev[8] = {};
     bool ev_valid = false;
@@ -164,6 +175,8 @@ int pfc_destroy(pfc_ctx* c) {
     c->d_X.release(); c->d_tw.release(); c->d_s.release(); c->d_w.release(); c->d_sd.release(); c->d_np.release(); c->d_fl.release();
     c->d_dbg_pairs.release(); c->d_last_np.release(); c->d_small_pairs.release();
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    c->d_large.release(); c->d_leaf_path.release(); c->d_leaf_depth.release();
+    large_buffers_destroy(c->large_buf);
     delete c;
     return PFC_OK;
 }
@@ -293,7 +306,14 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
         }
     }
     c->h_ins.clear();
-    std::vector<int32_t> small;
+    std::vector<int32_t> small, large;
+    int large_key_bits = 0;
+    std::vector<unsigned long long> leaf_path;
+    std::vector<unsigned char> leaf_depth;
+    for (auto& m : c->mesh) {
+        m.path_base = int(leaf_path.size());
+        for (int64_t k = 0; k < m.n_prim; ++k) { leaf_path.push_back(m.leaf_path[k]); leaf_depth.push_back((unsigned char)m.leaf_depth[k]); }
+    }
     for (size_t k = 0; k < c->ins.size(); ++k) {
         const HostIns& h = c->ins[k];
         const HostMesh& m1 = c->mesh[h.mesh_1];
@@ -310,8 +330,26 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
             d.p[5] = (d.p[1] - d.p[0]) / (d.p[4] - d.p[3]); d.p[6] = 1.0 / d.p[2]; }
         else { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = h.params[3]; d.p[4] = 2 * h.params[2]; d.p[5] = 3 * h.params[2]; d.p[6] = h.params[4];
             d.p[7] = (d.p[3] - d.p[2]) / (d.p[5] - d.p[4]); }
+        d.path_base1 = m1.path_base; d.path_base2 = m2.path_base;
         if (d.small) { small.push_back(int32_t(k)); c->small_max_pairs = std::max(c->small_max_pairs, int(m1.n_prim * m2.n_prim)); }
+        else { large.push_back(int32_t(k)); large_key_bits = std::max(large_key_bits, d.key_bits); }
         c->h_ins.push_back(d);
+    }
+    // large path tables: per-primitive leaf paths (DFS keys) for every mesh
+    c->large_ins_host = large;
+    if (!large.empty()) {
+        CU(c->d_large.ensure(large.size()));
+        CU(cudaMemcpy(c->d_large.p, large.data(), large.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(c->d_leaf_path.ensure(leaf_path.size()));
+        CU(c->d_leaf_depth.ensure(leaf_depth.size()));
+        CU(cudaMemcpy(c->d_leaf_path.p, leaf_path.data(), leaf_path.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_leaf_depth.p, leaf_depth.data(), leaf_depth.size(), cudaMemcpyHostToDevice));
+        c->large_scene.large_ins = c->d_large.p;
+        c->large_scene.leaf_path = c->d_leaf_path.p;
+        c->large_scene.leaf_depth = c->d_leaf_depth.p;
+        c->large_scene.n_large = int(large.size());
+        c->large_scene.key_bits = large_key_bits;
+        if (!c->large_buf) c->large_buf = large_buffers_create();
     }
     CU(c->d_nodes.ensure(nodes.size()));
     CU(c->d_tets.ensure(std::max<size_t>(tets.size(), 1)));
@@ -331,10 +369,14 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
     return PFC_OK;
 }
 
+static bool scene_has_large_bristle(const pfc_ctx* c) {
+    for (int k : c->large_ins_host) if (c->h_ins[k].model == PFC_MODEL_BRISTLE) return true;
+    return false;
+}
+
 static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
     EvalIO io = io_in;
     const int n_ins = c->scene.n_ins;
-    if (c->scene.n_small != n_ins) return fail(PFC_E_ARG, "large-scene path not built yet");
     if (c->keep_pairs) {
         c->dbg_cap = kSmallCap;
         CU(c->d_dbg_pairs.ensure(size_t(2) * c->dbg_cap * io.n_env * n_ins));
@@ -343,9 +385,17 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
         c->dbg_n_env = io.n_env;
     } else { io.dbg_pairs = nullptr; io.dbg_cap = 0; }
     int nl = 0;
-    CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * n_ins));
-    CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, c->timing ? c->ev : nullptr));
-    c->ev_valid = c->timing;
+    if (c->scene.n_small > 0) {
+        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * n_ins));
+        CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, c->timing ? c->ev : nullptr));
+        c->ev_valid = c->timing;
+    }
+    if (c->large_scene.n_large > 0) {
+        if (c->shard_world > 1) return fail(PFC_E_ARG, "this context is sharded: use pfc_eval_sharded_begin / _step");
+        CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
+        const int n_stage = scene_has_large_bristle(c) ? 3 : 1;
+        for (int st = 0; st < n_stage; ++st) CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, st, 0, 1, 0, c->stream, &nl));
+    }
     c->launches += nl;
     c->last_X = io.X; c->last_tw = io.twist;
     if (c->keep_pairs) {
@@ -417,6 +467,13 @@ int pfc_get_pairs(pfc_ctx* c, int64_t env, int ins, int32_t* pairs, int64_t cap,
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     const int64_t ei = env * c->scene.n_ins + ins;
+    if (!c->h_ins[ins].small) {
+        const int li = int(std::find(c->large_ins_host.begin(), c->large_ins_host.end(), ins) - c->large_ins_host.begin());
+        long long nn = 0;
+        CU(large_get_pairs(c->large_buf, int(env * c->large_scene.n_large + li), pairs, cap, &nn, c->stream));
+        if (n_out) *n_out = nn;
+        return PFC_OK;
+    }
     long long n = 0;
     CU(cudaMemcpy(&n, c->d_last_np.p + ei, sizeof(long long), cudaMemcpyDeviceToHost));
     if (n_out) *n_out = n;
@@ -438,7 +495,18 @@ int pfc_get_traction(pfc_ctx* c, int64_t env, int ins, double* out, int64_t cap_
     CU(d_out.ensure(size_t(8) * cap)); CU(d_n.ensure(1));
     EvalIO io{};
     io.X = c->last_X; io.twist = c->last_tw;
-    CU(launch_dump_traction(c->scene, io, env, ins, c->d_dbg_pairs.p + 2 * int64_t(c->dbg_cap) * ei, n, d_out.p, cap, d_n.p, c->stream));
+    const int* d_pairs = c->d_dbg_pairs.p + 2 * int64_t(c->dbg_cap) * ei;
+    DevBuf<int> d_tmp;
+    if (!c->h_ins[ins].small) {  // large instruction: fetch its sorted pair list and stage it as (a, b) ints
+        const int li = int(std::find(c->large_ins_host.begin(), c->large_ins_host.end(), ins) - c->large_ins_host.begin());
+        std::vector<int> hp(size_t(2) * std::max<long long>(n, 1));
+        long long nn = 0;
+        CU(large_get_pairs(c->large_buf, int(env * c->large_scene.n_large + li), hp.data(), n, &nn, c->stream));
+        CU(d_tmp.ensure(hp.size()));
+        CU(cudaMemcpy(d_tmp.p, hp.data(), hp.size() * sizeof(int), cudaMemcpyHostToDevice));
+        d_pairs = d_tmp.p;
+    }
+    CU(launch_dump_traction(c->scene, io, env, ins, d_pairs, n, d_out.p, cap, d_n.p, c->stream));
     c->launches += 1;
     int np = 0;
     CU(cudaMemcpyAsync(&np, d_n.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -446,7 +514,7 @@ int pfc_get_traction(pfc_ctx* c, int64_t env, int ins, double* out, int64_t cap_
     if (n_out) *n_out = np;
     const int m = std::min(np, cap);
     if (out && m > 0 && cap_points > 0) CU(cudaMemcpy(out, d_out.p, sizeof(double) * 8 * m, cudaMemcpyDeviceToHost));
-    d_out.release(); d_n.release();
+    d_out.release(); d_n.release(); d_tmp.release();
     return PFC_OK;
 }
 
@@ -495,6 +563,11 @@ int pfc_kernel_times(pfc_ctx* c, double* ms, int n) {
 
 void* pfc_stream(pfc_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t pfc_launch_count(pfc_ctx* c) { return c ? c->launches : 0; }
-int pfc_counters(pfc_ctx*, int64_t* a, int64_t* b) { if (a) *a = 0; if (b) *b = 0; return PFC_OK; }
+int pfc_counters(pfc_ctx* c, int64_t* a, int64_t* b) {
+    if (!c) return fail(PFC_E_ARG, "pfc_counters: NULL context");
+    if (a) *a = c->large_buf ? (int64_t)large_last_tests(c->large_buf) : 0;
+    if (b) *b = c->large_buf ? (int64_t)large_last_pairs(c->large_buf) : 0;
+    return PFC_OK;
+}
 
 }  // extern "C"

@@ -13,7 +13,7 @@
 namespace pfc {
 
 // A: symmetric 6x6 (full storage, row-major), destroyed.  V: eigenvectors in columns.
-__device__ __noinline__ void jacobi6(double* A, double* V, double* lam) {
+static __device__ __noinline__ void jacobi6(double* A, double* V, double* lam) {
     for (int i = 0; i < 36; ++i) V[i] = 0.0;
     for (int i = 0; i < 6; ++i) V[7 * i] = 1.0;
     for (int sweep = 0; sweep < 40; ++sweep) {
@@ -52,7 +52,7 @@ __device__ __noinline__ void jacobi6(double* A, double* V, double* lam) {
 
 // a21: K11 upper (0..5), K12 row-major (6..14), K22 upper (15..20), already multiplied by k_bar.
 // Outputs: Sinv (6) and Khalf = K̄^(-1/2) (36, row-major).  scratch: 108 doubles of (shared) memory.
-__device__ __noinline__ void decompose_K(const double* a21, double magic, double* Sinv, double* Khalf, double* scratch) {
+static __device__ __noinline__ void decompose_K(const double* a21, double magic, double* Sinv, double* Khalf, double* scratch) {
     double* K = scratch;
     double* A = scratch + 36;
     double* V = scratch + 72;

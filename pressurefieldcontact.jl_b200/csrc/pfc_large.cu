@@ -1,0 +1,695 @@
+// pfc_large.cu -- contact-wrench evaluation for LARGE instructions (big trees, 1e5..1e6+ candidate
+// pairs per evaluation; configs C4/C5).  Multi-kernel pipeline over global work lists:
+//
+//   K1a broad_bfs_kernel   a few level-synchronous expansions of the node-pair frontier until there
+//                          are enough independent sub-problems (seeds) for the whole GPU
+//   K1b broad_dfs_kernel   persistent warps pull seeds from a global counter and run a warp-cooperative,
+//                          stack-based dual-tree traversal: the stack lives in shared memory, every
+//                          lane tests one node pair per iteration (bit-exact 15-axis SAT), children are
+//                          pushed with a warp prefix sum, leaf pairs are appended to the global pair
+//                          list with ONE atomicAdd per warp per iteration (warp-aggregated atomics)
+//   K1c key + radix sort   the pair list arrives in nondeterministic order; each pair gets the key of
+//                          its position in the reference's recursion (src/obb/tree_types.jl:88-111):
+//                          the root-to-leaf turns of both leaves interleaved, tree 2's turn first
+//                          (children are visited (1.1,2.1),(1.2,2.1),(1.1,2.2),(1.2,2.2)).  A stable
+//                          LSD radix sort on (problem, key) restores exactly the reference's order, so
+//                          the pair lists are bit-exact and every later sum has a fixed order.
+//   K2  narrow_large_kernel one thread per sorted pair (clip + quadrature + friction), fixed-order
+//                          block reduction per 256-pair chunk of a problem's segment
+//   K3  finish_large_kernel one warp per problem sums its chunk partials in order; bristle steps
+//                          (centre of pressure -> stiffness -> friction) run K2/K3 once per pass
+//
+// Reference: calcTriTetIntersections! + integrate_over! + yes_contact!/no_contact!
+// (/root/reference/src/contact_algorithms_non_friction.jl:70-143, src/contact_algorithms_friction.jl:50-143).
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "pfc_bristle.cuh"
+#include "pfc_large.h"
+#include "pfc_patch.cuh"
+#include "pfc_sat.cuh"
+
+namespace pfc {
+
+namespace {
+
+#define LCU(call)                         \
+    do {                                  \
+        cudaError_t e_ = (call);          \
+        if (e_ != cudaSuccess) return e_; \
+    } while (0)
+
+constexpr int kStackCap = 1024;   // node pairs per warp stack (8 KB)
+constexpr int kDfsWarps = 4;
+constexpr int kChunk = 256;       // pairs per reduction chunk (= narrow kernel block size)
+constexpr int kNA = 21;           // accumulator slots per chunk partial
+
+struct Counters {                 // device-resident
+    unsigned int frontier_n[2];   // BFS ping-pong frontier sizes
+    unsigned int seed_head;       // next seed to hand out
+    unsigned int n_pairs;         // leaf pairs appended
+    unsigned int overflow;        // bit0 frontier, bit1 pairs, bit2 stack
+    unsigned int n_units;         // narrow-phase work units
+    unsigned long long n_tests;   // node pairs tested (statistics)
+};
+
+struct Seed { int prob; int a; int b; };   // prob = index into the large-problem list; a, b mesh-local node ids
+
+PFC_D void load_xform_l(const double* __restrict__ X, Xform<double>& x) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x.r[3 * i + j] = X[4 * j + i];
+        x.t[i] = X[12 + i];
+    }
+}
+PFC_D void broad_xform_l(const double* __restrict__ X, double* Rab, double* tab) {
+    Xform<double> x21;
+    load_xform_l(X, x21);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Rab[3 * i + j] = x21.r[3 * j + i];
+        tab[i] = -add_(add_(mul_(x21.r[i], x21.t[0]), mul_(x21.r[3 + i], x21.t[1])), mul_(x21.r[6 + i], x21.t[2]));
+    }
+}
+
+// problem p of the large list -> (env, instruction)
+PFC_D void prob_to_ei(const SceneDev& sc, const LargeScene& ls, int p, long long& env, int& k) {
+    env = p / ls.n_large;
+    k = ls.large_ins[p - env * ls.n_large];
+}
+
+// Tests one node pair and classifies the outcome: returns the number of children (0, 2, 4) written to
+// ch[], or -1 for a leaf pair (prims in ch[0]); 0 also when the boxes are disjoint.
+PFC_D int expand_pair(const SceneDev& sc, const InsDev& ins, const double* Rab, const double* tab, int ia, int ib, int2* ch) {
+    const NodeRec& a = sc.nodes[ins.node_base1 + ia];
+    const NodeRec& b = sc.nodes[ins.node_base2 + ib];
+    SatA A;
+    sat_prepare_a(a, Rab, tab, A);
+    if (!sat_test(A, b)) return 0;
+    const int al = a.left, ar = a.right, bl = b.left, br = b.right;
+    if (al < 0) {
+        if (bl < 0) { ch[0] = make_int2(ar, br); return -1; }
+        ch[0] = make_int2(ia, bl); ch[1] = make_int2(ia, br); return 2;
+    }
+    if (bl < 0) { ch[0] = make_int2(al, ib); ch[1] = make_int2(ar, ib); return 2; }
+    ch[0] = make_int2(al, bl); ch[1] = make_int2(ar, bl); ch[2] = make_int2(al, br); ch[3] = make_int2(ar, br);
+    return 4;
+}
+
+__global__ void init_frontier_kernel(LargeScene ls, long long n_env, Seed* frontier, Counters* cnt) {
+    const long long n = n_env * ls.n_large;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) frontier[p] = Seed{(int)p, 0, 0};
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt->frontier_n[0] = (unsigned)n; cnt->frontier_n[1] = 0; cnt->seed_head = 0; cnt->n_pairs = 0; cnt->overflow = 0; cnt->n_units = 0;
+        cnt->n_tests = 0;
+    }
+}
+
+// K1a: one level of breadth-first expansion (order is irrelevant here: the sort restores it)
+__global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, const Seed* __restrict__ in, Seed* out,
+                                                        int src, unsigned cap_frontier, int3* pairs, unsigned cap_pairs, Counters* cnt) {
+    const unsigned n = cnt->frontier_n[src];
+    const int lane = threadIdx.x & 31;
+    for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = base + lane;
+        int r = 0;
+        int2 ch[4];
+        Seed s{};
+        if (i < n) {
+            s = in[i];
+            long long env; int k;
+            prob_to_ei(sc, ls, s.prob, env, k);
+            double Rab[9], tab[3];
+            broad_xform_l(X + 16 * (env * sc.n_ins + k), Rab, tab);
+            r = expand_pair(sc, sc.ins[k], Rab, tab, s.a, s.b, ch);
+        }
+        // warp-aggregated appends
+        const int n_child = r > 0 ? r : 0;
+        int incl = n_child;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned at = 0;
+        if (lane == 31 && tot > 0) at = atomicAdd(&cnt->frontier_n[src ^ 1], (unsigned)tot);
+        at = __shfl_sync(0xffffffffu, at, 31) + incl - n_child;
+        if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, ch[c].x, ch[c].y}; }
+        else if (n_child > 0) atomicOr(&cnt->overflow, 1u);
+        const unsigned leaf_mask = __ballot_sync(0xffffffffu, r < 0);
+        if (leaf_mask) {
+            unsigned pat = 0;
+            if (lane == 0) pat = atomicAdd(&cnt->n_pairs, (unsigned)__popc(leaf_mask));
+            pat = __shfl_sync(0xffffffffu, pat, 0) + __popc(leaf_mask & ((1u << lane) - 1u));
+            if (r < 0) { if (pat < cap_pairs) pairs[pat] = make_int3(s.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u); }
+        }
+    }
+}
+
+// K1b: warp-cooperative stack-based traversal of the seeds
+__global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, const Seed* __restrict__ seeds,
+                                                                   int src, int3* pairs, unsigned cap_pairs, Counters* cnt) {
+    __shared__ int2 stack_mem[kDfsWarps][kStackCap];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int2* stack = stack_mem[wib];
+    const unsigned n_seed = cnt->frontier_n[src];
+    unsigned long long tests = 0;
+    for (;;) {
+        unsigned si = 0;
+        if (lane == 0) si = atomicAdd(&cnt->seed_head, 1u);
+        si = __shfl_sync(0xffffffffu, si, 0);
+        if (si >= n_seed) break;
+        const Seed seed = seeds[si];
+        long long env; int k;
+        prob_to_ei(sc, ls, seed.prob, env, k);
+        const InsDev& ins = sc.ins[k];
+        double Rab[9], tab[3];
+        broad_xform_l(X + 16 * (env * sc.n_ins + k), Rab, tab);
+        int n = 1;
+        if (lane == 0) stack[0] = make_int2(seed.a, seed.b);
+        __syncwarp();
+        while (n > 0) {
+            // pop as many entries as the stack can absorb children for (each pops 1, pushes <= 4)
+            int take = n < 32 ? n : 32;
+            const int room = (kStackCap - n) / 3;
+            if (take > room) take = room > 0 ? room : 1;
+            int r = 0;
+            int2 ch[4];
+            if (lane < take) {
+                const int2 e = stack[n - 1 - lane];
+                r = expand_pair(sc, ins, Rab, tab, e.x, e.y, ch);
+                ++tests;
+            }
+            __syncwarp();
+            n -= take;
+            const int n_child = r > 0 ? r : 0;
+            int incl = n_child;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int at = n + incl - n_child;
+            if (n + tot <= kStackCap) { for (int c = 0; c < n_child; ++c) stack[at + c] = ch[c]; }
+            else if (lane == 0) atomicOr(&cnt->overflow, 4u);  // cannot happen: take was limited by room
+            n = (n + tot <= kStackCap) ? n + tot : n;
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, r < 0);
+            if (leaf_mask) {
+                unsigned pat = 0;
+                if (lane == 0) pat = atomicAdd(&cnt->n_pairs, (unsigned)__popc(leaf_mask));
+                pat = __shfl_sync(0xffffffffu, pat, 0) + __popc(leaf_mask & ((1u << lane) - 1u));
+                if (r < 0) { if (pat < cap_pairs) pairs[pat] = make_int3(seed.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u); }
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, o);
+    if (lane == 0 && tests) atomicAdd(&cnt->n_tests, tests);
+}
+
+// K1c: DFS-order key of every pair.  key = (prob << key_bits) | interleaved path bits (left-aligned in key_bits)
+__global__ void build_keys_kernel(SceneDev sc, LargeScene ls, const int3* __restrict__ pairs, unsigned n, unsigned long long* keys, unsigned* vals) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int3 p = pairs[i];
+        long long env; int k;
+        prob_to_ei(sc, ls, p.x, env, k);
+        const InsDev& ins = sc.ins[k];
+        const unsigned long long pa = ls.leaf_path[ins.path_base1 + p.y], pb = ls.leaf_path[ins.path_base2 + p.z];
+        const int da = ls.leaf_depth[ins.path_base1 + p.y], db = ls.leaf_depth[ins.path_base2 + p.z];
+        unsigned long long key = 0;
+        int nb = 0;
+        const int dm = da > db ? da : db;
+        for (int l = 0; l < dm; ++l) {
+            if (l < db) { key = (key << 1) | ((pb >> (db - 1 - l)) & 1ull); ++nb; }
+            if (l < da) { key = (key << 1) | ((pa >> (da - 1 - l)) & 1ull); ++nb; }
+        }
+        key <<= (ls.key_bits - nb);  // left-align: keys of different lengths compare like the recursion order
+        keys[i] = ((unsigned long long)(unsigned)p.x << ls.key_bits) | key;
+        vals[i] = i;
+    }
+}
+
+// ---- stable LSD radix sort, 8 bits per pass, one warp per 1024-element tile -------------------------------------
+constexpr int kTile = 1024;
+__global__ void __launch_bounds__(128) radix_hist_kernel(const unsigned long long* __restrict__ keys, unsigned n, int shift, unsigned* hist, unsigned n_tiles) {
+    __shared__ unsigned h[4][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned tile = blockIdx.x * 4 + wib;
+    for (int d = lane; d < 256; d += 32) h[wib][d] = 0;
+    __syncwarp();
+    if (tile < n_tiles) {
+        const unsigned beg = tile * kTile, end = min(beg + kTile, n);
+        for (unsigned i = beg + lane; i < end; i += 32) atomicAdd(&h[wib][(keys[i] >> shift) & 255u], 1u);
+        __syncwarp();
+        for (int d = lane; d < 256; d += 32) hist[(size_t)d * n_tiles + tile] = h[wib][d];  // digit-major for the scan
+    }
+}
+// exclusive scan of hist[256 * n_tiles] by one block (n_tiles <= a few thousand)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* hist, unsigned total) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (unsigned base = 0; base < total; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < total ? hist[i] : 0;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned s = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+            warp_sums[lane] = s;  // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned before = carry + (w > 0 ? warp_sums[w - 1] : 0) + incl - v;
+        if (i < total) hist[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned n, int shift,
+                                                            const unsigned* __restrict__ hist, unsigned n_tiles, unsigned long long* keys_out, unsigned* vals_out) {
+    __shared__ unsigned base[4][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned tile = blockIdx.x * 4 + wib;
+    if (tile >= n_tiles) return;
+    for (int d = lane; d < 256; d += 32) base[wib][d] = hist[(size_t)d * n_tiles + tile];
+    __syncwarp();
+    const unsigned beg = tile * kTile, end = min(beg + kTile, n);
+    for (unsigned c = beg; c < end; c += 32) {  // chunks in order, lanes in order => stable
+        const unsigned i = c + lane;
+        const bool valid = i < end;
+        unsigned long long key = 0; unsigned val = 0; unsigned d = 256 + lane;  // invalid lanes get unique digits
+        if (valid) { key = keys_in[i]; val = vals_in[i]; d = (unsigned)((key >> shift) & 255u); }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned pos = 0;
+        if (valid) pos = base[wib][d] + rank;
+        __syncwarp();
+        if (valid && rank == (unsigned)__popc(peers) - 1) base[wib][d] = pos + 1;  // the last peer advances the digit's cursor
+        __syncwarp();
+        if (valid) { keys_out[pos] = key; vals_out[pos] = val; }
+    }
+}
+
+// sorted order -> (prob, a, b) arrays + per-problem segments
+__global__ void gather_sorted_kernel(const int3* __restrict__ pairs, const unsigned* __restrict__ vals, unsigned n, int3* sorted, unsigned* seg_start, unsigned* seg_end) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int3 p = pairs[vals[i]];
+        sorted[i] = p;
+        const int prev = i > 0 ? pairs[vals[i - 1]].x : -1;
+        if (p.x != prev) { seg_start[p.x] = i; if (prev >= 0) seg_end[prev] = i; }
+        if (i == n - 1) seg_end[p.x] = n;
+    }
+}
+// unit_start[p] = sum_{q < p} ceil(len_q / kChunk); one block (problem counts on the large path are modest)
+__global__ void __launch_bounds__(1024) units_scan_kernel(const unsigned* __restrict__ seg_start, const unsigned* __restrict__ seg_end, unsigned n_prob, unsigned* unit_start,
+                                                          Counters* cnt, unsigned shard_rank, unsigned shard_world) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (unsigned base = 0; base < n_prob; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < n_prob ? (seg_end[i] - seg_start[i] + kChunk - 1) / kChunk : 0;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned s = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const unsigned before = carry + (w > 0 ? warp_sums[w - 1] : 0) + incl - v;
+        if (i < n_prob) unit_start[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { unit_start[n_prob] = carry; cnt->n_units = carry; }
+    (void)shard_rank; (void)shard_world;
+}
+
+// per-problem state carried between the bristle passes
+struct ProbState { double cop[3]; double delta[6]; double Sinv[6]; double Kh[36]; double c10[10]; int contact; int pad; };
+
+// K2: one thread per sorted pair; fixed-order block reduction per chunk
+__global__ void __launch_bounds__(kChunk) narrow_large_kernel(SceneDev sc, LargeScene ls, EvalIO io, const int3* __restrict__ sorted, const unsigned* __restrict__ seg_start,
+                                                              const unsigned* __restrict__ seg_end, const unsigned* __restrict__ unit_start, unsigned n_prob,
+                                                              const Counters* cnt, int mode_reg, int mode_bristle, const ProbState* __restrict__ ps, double* chunk_out,
+                                                              int* chunk_points, int* prob_flags, unsigned shard_rank, unsigned shard_world) {
+    __shared__ double red[kChunk / 32][kNA];
+    __shared__ int red_pts[kChunk / 32];
+    __shared__ int s_prob;
+    const unsigned n_units = cnt->n_units;
+    // this rank's contiguous slice of the unit list (multi-GPU split of one large scene)
+    const unsigned u_beg = (unsigned)((unsigned long long)n_units * shard_rank / shard_world);
+    const unsigned u_end = (unsigned)((unsigned long long)n_units * (shard_rank + 1) / shard_world);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (unsigned u = u_beg + blockIdx.x; u < u_end; u += gridDim.x) {
+        if (threadIdx.x == 0) {  // unit -> problem by binary search in unit_start
+            unsigned lo = 0, hi = n_prob;
+            while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (unit_start[mid] <= u) lo = mid; else hi = mid; }
+            s_prob = (int)lo;
+        }
+        __syncthreads();
+        const int p = s_prob;
+        long long env; int k;
+        prob_to_ei(sc, ls, p, env, k);
+        const InsDev& ins = sc.ins[k];
+        const long long ei = env * sc.n_ins + k;
+        const int mode = ins.model == PFC_MODEL_REGULARIZED ? mode_reg : mode_bristle;
+        Accum<double, kNA> acc;
+        acc.reset(mode < 0 ? ACC_REGULARIZED : mode);
+        int flags = 0;
+        const unsigned i = seg_start[p] + (u - unit_start[p]) * kChunk + threadIdx.x;
+        if (mode >= 0 && i < seg_end[p]) {
+            PatchCtx<double> cx;
+            load_xform_l(io.X + 16 * ei, cx.x21);
+            cx.x12 = inverse(cx.x21);
+            const double* tw = io.twist + 6 * ei;
+            cx.w_ang = mk<double>(tw[0], tw[1], tw[2]);
+            cx.w_lin = mk<double>(tw[3], tw[4], tw[5]);
+            cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
+            acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
+            if (mode == ACC_STIFFNESS || mode == ACC_BRISTLE) {
+                acc.cop = mk<double>(ps[p].cop[0], ps[p].cop[1], ps[p].cop[2]);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc.delta[j] = ps[p].delta[j];
+            }
+            const int3 pr = sorted[i];
+            integrate_pair(sc, ins, pr.y, pr.z, cx, acc, flags);
+        }
+        // fixed-order reduction: butterfly inside each warp, then warps 0..7 in order
+        const int n_acc = (mode == ACC_STIFFNESS) ? 21 : (mode == ACC_COP ? 10 : 6);
+        for (int j = 0; j < n_acc; ++j) { const double v = warp_sum(acc.a[j]); if (lane == 0) red[w][j] = v; }
+        int pts = acc.n_points;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { pts += __shfl_xor_sync(0xffffffffu, pts, o); flags |= __shfl_xor_sync(0xffffffffu, flags, o); }
+        if (lane == 0) { red_pts[w] = pts; if (flags) atomicOr(&prob_flags[p], flags); }
+        __syncthreads();
+        if (threadIdx.x < n_acc) {
+            double s = red[0][threadIdx.x];
+#pragma unroll
+            for (int ww = 1; ww < kChunk / 32; ++ww) s += red[ww][threadIdx.x];
+            chunk_out[(size_t)u * kNA + threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) { int s = 0; for (int ww = 0; ww < kChunk / 32; ++ww) s += red_pts[ww]; chunk_points[u] = s; }
+        __syncthreads();
+    }
+}
+
+// K3: one warp per problem: ordered sum of its chunk partials, then the model-specific step.
+//   stage 0: regularized -> wrench;  bristle pass 1 (COP) -> cop, normal wrench
+//   stage 1: bristle pass 2 (STIFFNESS) -> K -> Sinv, Kh, delta
+//   stage 2: bristle pass 3 (BRISTLE) -> friction wrench, s-dot, total wrench
+// In sharded (multi-GPU) mode the chunk sums of the other ranks are missing: `partial_only` makes the
+// kernel write the raw per-problem partial sums to part_out for the caller's allreduce instead.
+__global__ void __launch_bounds__(128) finish_large_kernel(SceneDev sc, LargeScene ls, EvalIO io, const unsigned* __restrict__ seg_start, const unsigned* __restrict__ seg_end,
+                                                           const unsigned* __restrict__ unit_start, unsigned n_prob, const Counters* cnt, int stage, ProbState* ps,
+                                                           const double* __restrict__ chunk_out, const int* __restrict__ chunk_points, const int* __restrict__ prob_flags,
+                                                           unsigned shard_rank, unsigned shard_world, double* part_out, int apply_parts) {
+    __shared__ double scratch[4][192];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned n_units = cnt->n_units;
+    const unsigned u_beg = (unsigned)((unsigned long long)n_units * shard_rank / shard_world);
+    const unsigned u_end = (unsigned)((unsigned long long)n_units * (shard_rank + 1) / shard_world);
+    for (unsigned p = blockIdx.x * 4 + wib; p < n_prob; p += gridDim.x * 4) {
+        long long env; int k;
+        prob_to_ei(sc, ls, (int)p, env, k);
+        const InsDev& ins = sc.ins[k];
+        const long long ei = env * sc.n_ins + k;
+        const bool bristle = ins.model == PFC_MODEL_BRISTLE;
+        if (!bristle && stage > 0) continue;
+        double sum[kNA];
+        int pts = 0;
+        const int n_acc = bristle ? (stage == 1 ? 21 : (stage == 0 ? 10 : 6)) : 6;
+        if (apply_parts) {  // sums were reduced across ranks by the caller: part_out[p][kNA + 1]
+            for (int j = 0; j < n_acc; ++j) sum[j] = part_out[(size_t)p * (kNA + 1) + j];
+            pts = (int)part_out[(size_t)p * (kNA + 1) + kNA];
+        } else {
+            // lane l sums chunks l, l+32, ... of this problem in order; then a fixed butterfly
+            unsigned c0 = unit_start[p], c1 = unit_start[p + 1];
+            if (c0 < u_beg) c0 = u_beg;
+            if (c1 > u_end) c1 = u_end;
+            for (int j = 0; j < n_acc; ++j) sum[j] = 0.0;
+            for (unsigned c = c0 + lane; c < c1; c += 32) {
+                for (int j = 0; j < n_acc; ++j) sum[j] += chunk_out[(size_t)c * kNA + j];
+                pts += chunk_points[c];
+            }
+            for (int j = 0; j < n_acc; ++j) sum[j] = warp_sum(sum[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(0xffffffffu, pts, o);
+            if (part_out) {  // sharded: hand the partial sums to the caller and stop here
+                if (lane == 0) { for (int j = 0; j < kNA; ++j) part_out[(size_t)p * (kNA + 1) + j] = j < n_acc ? sum[j] : 0.0; part_out[(size_t)p * (kNA + 1) + kNA] = (double)pts; }
+                continue;
+            }
+        }
+        const long long n_pairs = (long long)seg_end[p] - (long long)seg_start[p];
+        double* wo = io.wrench + 6 * ei;
+        if (!bristle) {
+            if (lane == 0) {
+                const bool contact = pts > 0;
+                for (int j = 0; j < 6; ++j) wo[j] = contact ? sum[j] : 0.0;
+                io.n_pairs[ei] = n_pairs;
+                io.flags[ei] = prob_flags[p] | (contact ? kFlagContact : 0);
+            }
+            continue;
+        }
+        const double* sv = io.s + 6 * ((long long)sc.n_bristle * env + ins.bristle_id);
+        double* sd = io.sdot + 6 * ((long long)sc.n_bristle * env + ins.bristle_id);
+        ProbState& st = ps[p];
+        if (stage == 0) {
+            if (lane == 0) {
+                const bool contact = pts > 0;
+                st.contact = contact;
+                io.n_pairs[ei] = n_pairs;
+                io.flags[ei] = prob_flags[p] | (contact ? kFlagContact : 0);
+                if (contact) {
+                    for (int j = 0; j < 10; ++j) st.c10[j] = sum[j];
+                    for (int j = 0; j < 3; ++j) st.cop[j] = sum[7 + j] / sum[6];
+                } else {  // no_contact!(::Bristle)
+                    const double ti = -(1.0 / ins.p[0]);
+                    for (int j = 0; j < 6; ++j) { wo[j] = 0.0; sd[j] = ti * sv[j]; }
+                }
+            }
+        } else if (stage == 1) {
+            if (lane == 0 && st.contact) {
+                double* scr = scratch[wib];
+                double* K21 = scr + 108;
+                for (int j = 0; j < 21; ++j) K21[j] = sum[j] * ins.p[1];
+                decompose_K(K21, ins.p[6], st.Sinv, st.Kh, scr);
+                for (int i = 0; i < 6; ++i) {
+                    double t = 0.0;
+                    for (int j = 0; j < 6; ++j) t += st.Kh[6 * i + j] * sv[j];
+                    st.delta[i] = st.Sinv[i] * t;
+                }
+            }
+        } else {
+            if (lane == 0 && st.contact) {
+                const double* c = st.c10;
+                const Vec3<double> cop = mk<double>(st.cop[0], st.cop[1], st.cop[2]);
+                const Vec3<double> shift = cross(cop, mk<double>(sum[3], sum[4], sum[5]));
+                wo[0] = c[0] + (sum[0] + shift.x); wo[1] = c[1] + (sum[1] + shift.y); wo[2] = c[2] + (sum[2] + shift.z);
+                wo[3] = c[3] + sum[3]; wo[4] = c[4] + sum[4]; wo[5] = c[5] + sum[5];
+                const double ti = -(1.0 / ins.p[0]);
+                double sw[6];
+                for (int i = 0; i < 6; ++i) sw[i] = st.Sinv[i] * sum[i];
+                for (int i = 0; i < 6; ++i) {
+                    double t = 0.0;
+                    for (int j = 0; j < 6; ++j) t += st.Kh[6 * i + j] * sw[j];
+                    sd[i] = ti * (t + sv[i]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void zero_int_kernel(int* p, unsigned n) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;
+}
+__global__ void init_segments_kernel(unsigned* seg_start, unsigned* seg_end, unsigned n) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { seg_start[i] = 0; seg_end[i] = 0; }
+}
+
+template <class T> cudaError_t ensure(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, need * sizeof(T));
+    if (e == cudaSuccess) cap = need;
+    return e;
+}
+
+}  // namespace
+
+struct LargeBuffers {
+    Counters* cnt = nullptr;
+    Seed* frontier[2] = {nullptr, nullptr}; size_t cap_frontier = 0;
+    int3* pairs = nullptr; int3* sorted = nullptr; size_t cap_pairs = 0;
+    unsigned long long* keys[2] = {nullptr, nullptr}; unsigned* vals[2] = {nullptr, nullptr}; size_t cap_keys = 0, cap_keys2 = 0, cap_vals = 0, cap_vals2 = 0, cap_sorted = 0;
+    unsigned* hist = nullptr; size_t cap_hist = 0;
+    unsigned* seg_start = nullptr; unsigned* seg_end = nullptr; unsigned* unit_start = nullptr; size_t cap_seg = 0, cap_seg2 = 0, cap_unit = 0;
+    ProbState* ps = nullptr; size_t cap_ps = 0;
+    int* prob_flags = nullptr; size_t cap_pf = 0;
+    double* chunk_out = nullptr; size_t cap_chunk = 0;
+    int* chunk_points = nullptr; size_t cap_cp = 0;
+    double* part = nullptr; size_t cap_part = 0;
+    size_t cf2 = 0;
+    unsigned last_n_pairs = 0;
+    unsigned long long last_n_tests = 0;
+};
+
+LargeBuffers* large_buffers_create() { return new LargeBuffers(); }
+void large_buffers_destroy(LargeBuffers* b) {
+    if (!b) return;
+    cudaFree(b->cnt); cudaFree(b->frontier[0]); cudaFree(b->frontier[1]); cudaFree(b->pairs); cudaFree(b->sorted);
+    cudaFree(b->keys[0]); cudaFree(b->keys[1]); cudaFree(b->vals[0]); cudaFree(b->vals[1]); cudaFree(b->hist);
+    cudaFree(b->seg_start); cudaFree(b->seg_end); cudaFree(b->unit_start); cudaFree(b->ps); cudaFree(b->prob_flags);
+    cudaFree(b->chunk_out); cudaFree(b->chunk_points); cudaFree(b->part);
+    delete b;
+}
+
+unsigned large_last_pairs(const LargeBuffers* b) { return b->last_n_pairs; }
+unsigned long long large_last_tests(const LargeBuffers* b) { return b->last_n_tests; }
+double* large_part_buffer(LargeBuffers* b) { return b->part; }
+
+// Copies the sorted pair list of problem `prob` (device -> host).
+cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, long long* n_out, cudaStream_t stream) {
+    unsigned se[2] = {0, 0};
+    LCU(cudaMemcpyAsync(&se[0], b->seg_start + prob, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    LCU(cudaMemcpyAsync(&se[1], b->seg_end + prob, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    LCU(cudaStreamSynchronize(stream));
+    const long long n = (long long)se[1] - se[0];
+    if (n_out) *n_out = n;
+    const long long m = std::min(n, cap);
+    if (out && m > 0) {
+        std::vector<int3> tmp(m);
+        LCU(cudaMemcpy(tmp.data(), b->sorted + se[0], sizeof(int3) * m, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < m; ++i) { out[2 * i] = tmp[i].y; out[2 * i + 1] = tmp[i].z; }
+    }
+    return cudaSuccess;
+}
+const int3* large_sorted_ptr(const LargeBuffers* b) { return b->sorted; }
+
+// Broad phase + sort + segments.  Synchronises once (reads the pair count) so that capacities can
+// grow like the reference's VectorCache (src/obb/vector_cache.jl:11-15): on overflow the buffers are
+// doubled and the traversal is re-run.
+cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches) {
+    const long long n_prob_ll = io.n_env * ls.n_large;
+    if (n_prob_ll <= 0) return cudaSuccess;
+    if (n_prob_ll > (1LL << 30)) return cudaErrorInvalidValue;
+    const unsigned n_prob = (unsigned)n_prob_ll;
+    if (!b->cnt) LCU(cudaMalloc(&b->cnt, sizeof(Counters)));
+    size_t want_frontier = std::max<size_t>(b->cap_frontier, std::max<size_t>(1u << 18, (size_t)n_prob * 4));
+    size_t want_pairs = std::max<size_t>(b->cap_pairs, 1u << 20);
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    // BFS levels until ~64 seeds per SM-resident warp slot could exist (4^L * n_prob >= target)
+    int levels = 0;
+    { double f = (double)n_prob; const double target = 64.0 * n_sm * 4; while (f < target && levels < 12) { f *= 4.0; ++levels; } }
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        LCU(ensure(b->frontier[0], b->cap_frontier, want_frontier));
+        LCU(ensure(b->frontier[1], b->cf2, want_frontier));
+        LCU(ensure(b->pairs, b->cap_pairs, want_pairs));
+        init_frontier_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(ls, io.n_env, b->frontier[0], b->cnt);
+        int src = 0;
+        for (int l = 0; l < levels; ++l) {
+            if (l > 0) { /* the level's output counter must start at zero */ }
+            broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, ls, io.X, b->frontier[src], b->frontier[src ^ 1], src, (unsigned)b->cap_frontier, b->pairs,
+                                                         (unsigned)b->cap_pairs, b->cnt);
+            // reset the consumed frontier's counter for its next use as an output
+            LCU(cudaMemsetAsync(&b->cnt->frontier_n[src], 0, sizeof(unsigned), stream));
+            src ^= 1;
+        }
+        broad_dfs_kernel<<<n_sm * 4, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], src, b->pairs, (unsigned)b->cap_pairs, b->cnt);
+        if (n_launches) *n_launches += 2 + levels;
+        Counters h;
+        LCU(cudaMemcpyAsync(&h, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        LCU(cudaStreamSynchronize(stream));
+        if (h.overflow & 4u) return cudaErrorAssert;
+        if (h.overflow & 1u) { want_frontier *= 2; continue; }
+        if (h.overflow & 2u) { want_pairs = std::max<size_t>(want_pairs * 2, (size_t)h.n_pairs + 1024); continue; }
+        b->last_n_pairs = h.n_pairs;
+        b->last_n_tests = h.n_tests;
+        break;
+    }
+    const unsigned n = b->last_n_pairs;
+    // segments + keys + sort
+    LCU(ensure(b->seg_start, b->cap_seg, (size_t)n_prob + 1));
+    LCU(ensure(b->seg_end, b->cap_seg2, (size_t)n_prob + 1));
+    LCU(ensure(b->unit_start, b->cap_unit, (size_t)n_prob + 2));
+    LCU(ensure(b->prob_flags, b->cap_pf, (size_t)n_prob));
+    LCU(ensure(b->ps, b->cap_ps, (size_t)n_prob));
+    init_segments_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(b->seg_start, b->seg_end, n_prob);
+    zero_int_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(b->prob_flags, n_prob);
+    if (n_launches) *n_launches += 2;
+    if (n > 0) {
+        LCU(ensure(b->keys[0], b->cap_keys, (size_t)n)); LCU(ensure(b->keys[1], b->cap_keys2, (size_t)n));
+        LCU(ensure(b->vals[0], b->cap_vals, (size_t)n)); LCU(ensure(b->vals[1], b->cap_vals2, (size_t)n));
+        LCU(ensure(b->sorted, b->cap_sorted, (size_t)n));
+        const unsigned n_tiles = (n + kTile - 1) / kTile;
+        LCU(ensure(b->hist, b->cap_hist, (size_t)256 * n_tiles));
+        const unsigned g = std::min<unsigned>((n + 255) / 256, (unsigned)n_sm * 16);
+        build_keys_kernel<<<g, 256, 0, stream>>>(sc, ls, b->pairs, n, b->keys[0], b->vals[0]);
+        int prob_bits = 0;
+        while ((1ull << prob_bits) < (unsigned long long)n_prob) ++prob_bits;
+        const int total_bits = ls.key_bits + prob_bits;
+        int cur = 0;
+        for (int shift = 0; shift < total_bits; shift += 8) {
+            radix_hist_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], n, shift, b->hist, n_tiles);
+            radix_scan_kernel<<<1, 1024, 0, stream>>>(b->hist, 256u * n_tiles);
+            radix_scatter_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->vals[cur], n, shift, b->hist, n_tiles, b->keys[cur ^ 1], b->vals[cur ^ 1]);
+            cur ^= 1;
+            if (n_launches) *n_launches += 3;
+        }
+        gather_sorted_kernel<<<g, 256, 0, stream>>>(b->pairs, b->vals[cur], n, b->sorted, b->seg_start, b->seg_end);
+        if (n_launches) *n_launches += 2;
+    }
+    units_scan_kernel<<<1, 1024, 0, stream>>>(b->seg_start, b->seg_end, n_prob, b->unit_start, b->cnt, 0, 1);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
+// Narrow phase + friction + reduction for the pair lists produced by large_broad_phase.
+// shard_world > 1: this context sums only its slice of the chunks and leaves per-problem partial sums
+// (kNA + 1 doubles each) in large_part_buffer() after each stage; the caller allreduces them and calls
+// large_narrow_stage again with apply_parts = 1.
+cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int shard_rank, int shard_world,
+                               int apply_parts, cudaStream_t stream, int* n_launches) {
+    const unsigned n_prob = (unsigned)(io.n_env * ls.n_large);
+    if (n_prob == 0) return cudaSuccess;
+    const unsigned n = b->last_n_pairs;
+    const size_t max_units = (size_t)(n / kChunk) + n_prob + 1;
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    LCU(ensure(b->chunk_out, b->cap_chunk, max_units * kNA));
+    LCU(ensure(b->chunk_points, b->cap_cp, max_units));
+    if (shard_world > 1) LCU(ensure(b->part, b->cap_part, (size_t)n_prob * (kNA + 1)));
+    const int mode_reg = stage == 0 ? ACC_REGULARIZED : -1;
+    const int mode_bri = stage == 0 ? ACC_COP : (stage == 1 ? ACC_STIFFNESS : ACC_BRISTLE);
+    if (!apply_parts) {
+        const unsigned grid = (unsigned)std::min<size_t>(max_units, (size_t)n_sm * 16);
+        narrow_large_kernel<<<grid, kChunk, 0, stream>>>(sc, ls, io, b->sorted, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, mode_reg, mode_bri, b->ps,
+                                                        b->chunk_out, b->chunk_points, b->prob_flags, (unsigned)shard_rank, (unsigned)shard_world);
+        if (n_launches) *n_launches += 1;
+    }
+    finish_large_kernel<<<std::min<unsigned>((n_prob + 3) / 4, (unsigned)n_sm * 8), 128, 0, stream>>>(
+        sc, ls, io, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, stage, b->ps, b->chunk_out, b->chunk_points, b->prob_flags, (unsigned)shard_rank,
+        (unsigned)shard_world, (shard_world > 1) ? b->part : nullptr, apply_parts);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace pfc

@@ -1,0 +1,33 @@
+// pfc_large.h -- host-side interface of the large-instruction pipeline (pfc_large.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pfc_launch.h"
+#include "pfc_types.cuh"
+
+namespace pfc {
+
+// device-resident tables of the large path
+struct LargeScene {
+    const int32_t* large_ins;             // instruction indices handled by the large path
+    const unsigned long long* leaf_path;  // per primitive (all meshes concatenated): root-to-leaf turns, MSB first in the low `depth` bits
+    const unsigned char* leaf_depth;      // per primitive: depth of its leaf
+    int32_t n_large;
+    int32_t key_bits;                     // max over large instructions of depth(tree 1) + depth(tree 2)
+};
+
+struct LargeBuffers;
+LargeBuffers* large_buffers_create();
+void large_buffers_destroy(LargeBuffers* b);
+
+cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches);
+// stage 0: regularized wrench / bristle centre of pressure; 1: bristle stiffness; 2: bristle friction
+cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int shard_rank, int shard_world,
+                               int apply_parts, cudaStream_t stream, int* n_launches);
+unsigned large_last_pairs(const LargeBuffers* b);
+unsigned long long large_last_tests(const LargeBuffers* b);
+double* large_part_buffer(LargeBuffers* b);     // [n_problem][22] partial sums of the last stage (sharded mode)
+constexpr int kLargePartStride = 22;
+cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, long long* n_out, cudaStream_t stream);
+
+}  // namespace pfc

@@ -44,6 +44,7 @@ struct InsDev {
     int32_t bristle_id;  // -1 for regularized
     int32_t node_base1, node_base2; // first node of each mesh in the node array (the root: trees are stored pre-order)
     int32_t prim_base1, prim_base2; // offsets into the tri / tet record arrays
+    int32_t path_base1, path_base2; // offsets into the per-primitive leaf path / depth tables (large path)
     int32_t n_leaf1, n_leaf2;
     int32_t small;       // 1: handled by the fused warp-per-instruction kernel
     int32_t key_bits;    // max DFS-key length (depth1 + depth2) for the large path's sort
