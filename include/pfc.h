@@ -99,6 +99,15 @@ int pfc_get_traction(pfc_ctx* ctx, int64_t env, int ins, double* out, int64_t ca
 /* Multi-GPU for one very large scene: this context evaluates only slice `rank` of `world` of every
  * large instruction's sorted pair list; the caller sums wrench_r2 across ranks (NCCL allreduce). */
 int pfc_set_shard(pfc_ctx* ctx, int rank, int world);
+/* Sharded evaluation protocol (device pointers, asynchronous on the context's stream):
+ *   begin:    traversal + sort (every rank, identical) and stage 0 over this rank's slice of the 256-pair chunks;
+ *   partials: the buffer the caller must sum over all ranks in place: count doubles (22 per (env, large instruction));
+ *   step:     applies the summed buffer (wrench / bristle state) and, if the friction model needs another pass
+ *             (bristle: centre of pressure -> stiffness -> friction), runs it and sets *more = 1. */
+int pfc_eval_sharded_begin(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2,
+                           double* sdot, int64_t* n_pairs, int32_t* flags);
+int pfc_eval_sharded_partials(pfc_ctx* ctx, double** dev_ptr, int64_t* count);
+int pfc_eval_sharded_step(pfc_ctx* ctx, int* more);
 
 /* Plumbing */
 int pfc_sync(pfc_ctx* ctx);

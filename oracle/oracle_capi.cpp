@@ -297,6 +297,38 @@ int orc_count_work(void* h, int64_t n_env, const double* X, const double* twist,
     return 0;
 }
 
+// Partial regularized wrench of one (env = 0) instruction over the slice of its candidate pairs that rank
+// `rank` of `world` owns under the product's sharding rule (contiguous runs of 256-pair chunks).  Used by the
+// world_size-2 gloo test of the multi-GPU host logic: the sum over ranks must equal the full wrench.
+int orc_eval_slice_regularized(void* h, const double* X, const double* twist, int ins, int rank, int world, double* wrench_out, int64_t* n_pairs_out) {
+    Scene& sc = *static_cast<Scene*>(h);
+    const Instruction& ci = sc.ins.at(ins);
+    if (ci.model != 0) return -1;
+    const Mesh& m1 = sc.mesh[ci.id_1];
+    const Mesh& m2 = sc.mesh[ci.id_2];
+    M4<double> xf; for (int k = 0; k < 16; ++k) xf.m[k] = X[16 * ins + k];
+    M4<double> x12 = inv_transform(xf);
+    std::vector<std::pair<int32_t, int32_t>> pairs;
+    int64_t visited = 0;
+    tree_tree_intersect<double>(pairs, visited, rot_of(x12), mk3<double>(x12(0, 3), x12(1, 3), x12(2, 3)), m1.tree, m1.tree.root, m2.tree, m2.tree.root);
+    const int64_t n = int64_t(pairs.size());
+    const int64_t n_units = (n + 255) / 256;
+    const int64_t lo = std::min<int64_t>(n, (n_units * rank / world) * 256), hi = std::min<int64_t>(n, (n_units * (rank + 1) / world) * 256);
+    BodyBodyCache<double> b;
+    b.mesh_1 = &m1; b.mesh_2 = &m2;
+    b.x_r2_r1 = xf; b.x_r1_r2 = x12;
+    for (int k = 0; k < 6; ++k) b.twist_r2_r1_r2[k] = twist[6 * ins + k];
+    b.chi = ci.chi; b.Ebar = m2.Ebar; b.quad = ci.quad;
+    for (int64_t k = lo; k < hi; ++k) {
+        if (m1.kind == 0) integrate_over_tri_tet(pairs[k].first, pairs[k].second, b);
+        else integrate_over_tet_tet(pairs[k].first, pairs[k].second, b);
+    }
+    V6<double> w = yes_contact_regularized(ci.reg, b);
+    for (int k = 0; k < 6; ++k) wrench_out[k] = w[k];
+    if (n_pairs_out) *n_pairs_out = n;
+    return 0;
+}
+
 int64_t orc_get_pairs(void* h, int64_t env, int ins, int32_t* pairs, int64_t cap) {
     Scene& sc = *static_cast<Scene*>(h);
     const int n_ins = int(sc.ins.size());

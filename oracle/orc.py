@@ -84,6 +84,8 @@ def lib():
         L.orc_get_traction.restype = C.c_int64
         L.orc_get_traction.argtypes = [C.c_void_p, C.c_int64, C.c_int, _d, C.c_int64]
         L.orc_max_threads.restype = C.c_int
+        L.orc_eval_slice_regularized.restype = C.c_int
+        L.orc_eval_slice_regularized.argtypes = [C.c_void_p, _d, _d, C.c_int, C.c_int, C.c_int, _d, _i64]
         L.orc_count_work.restype = C.c_int
         L.orc_count_work.argtypes = [C.c_void_p, C.c_int64, _d, _d, C.c_void_p, _i64]
         _LIB = L
@@ -286,6 +288,14 @@ class OracleContext:
         lib().orc_count_work(self._h, n_env, X, twist, _ptr(s_a), out)
         return dict(flops_broad=int(out[0]), flops_narrow=int(out[1]), node_pairs=int(out[2]), candidate_pairs=int(out[3]),
                     traction_points=int(out[4]))
+
+    def eval_slice_regularized(self, X, twist, ins, rank, world):
+        """Partial wrench of instruction `ins` (environment 0) over rank's slice of the pair list."""
+        w, n = np.zeros(6), np.zeros(1, np.int64)
+        rc = lib().orc_eval_slice_regularized(self._h, _a(X).reshape(-1), _a(twist).reshape(-1), ins, rank, world, w, n)
+        if rc != 0:
+            raise RuntimeError("slice evaluation needs a regularized instruction")
+        return w, int(n[0])
 
     def n_visited(self) -> int:
         return lib().orc_n_visited(self._h)

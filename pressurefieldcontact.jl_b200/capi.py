@@ -21,7 +21,7 @@ _vp = C.c_void_p
 # every symbol include/pfc.h declares
 SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
-    "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_sync", "pfc_stream",
+    "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_eval_sharded_begin", "pfc_eval_sharded_partials", "pfc_eval_sharded_step", "pfc_sync", "pfc_stream",
     "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
 ]
 
@@ -52,6 +52,9 @@ def lib():
         L.pfc_get_pairs.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.c_int64, C.POINTER(C.c_int64)]
         L.pfc_get_traction.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.c_int64, C.POINTER(C.c_int64)]
         L.pfc_set_shard.argtypes = [_vp, C.c_int, C.c_int]
+        L.pfc_eval_sharded_begin.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_eval_sharded_partials.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]
+        L.pfc_eval_sharded_step.argtypes = [_vp, C.POINTER(C.c_int)]
         L.pfc_sync.argtypes = [_vp]
         L.pfc_stream.argtypes = [_vp]
         L.pfc_stream.restype = _vp
@@ -155,6 +158,20 @@ class Context:
     def eval_f64_device(self, n_env, X, twist, s, wrench, sdot, n_pairs, flags):
         """Device pointers given as integers; asynchronous on self.stream."""
         _check(lib().pfc_eval_f64_device(self._h, n_env, X, twist, s, wrench, sdot, n_pairs, flags))
+
+    def eval_sharded_begin(self, n_env, X, twist, s, wrench, sdot, n_pairs, flags):
+        """Device pointers (integers).  See INTEGRATION.md for the protocol."""
+        _check(lib().pfc_eval_sharded_begin(self._h, n_env, X, twist, s, wrench, sdot, n_pairs, flags))
+
+    def eval_sharded_partials(self):
+        ptr, n = _vp(), C.c_int64(0)
+        _check(lib().pfc_eval_sharded_partials(self._h, C.byref(ptr), C.byref(n)))
+        return (ptr.value or 0), n.value
+
+    def eval_sharded_step(self) -> bool:
+        more = C.c_int(0)
+        _check(lib().pfc_eval_sharded_step(self._h, C.byref(more)))
+        return bool(more.value)
 
     def eval_dual6(self, X_bp, X7, twist7, s7=None):
         n_env = _a(X7).reshape(-1, self.n_ins, 16, 7).shape[0]

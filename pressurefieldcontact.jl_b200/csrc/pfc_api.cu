@@ -451,6 +451,58 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
     return PFC_OK;
 }
 
+// ---- one large scene split over several GPUs ------------------------------------------------------------------
+int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
+                           int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: context not finalized");
+    if (n_env < 0 || !X || !twist || !wrench || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: NULL buffer");
+    if (c->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: bristle instructions need s and sdot");
+    if (c->large_scene.n_large == 0) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: the scene has no large instruction to split");
+    CU(cudaSetDevice(c->device));
+    EvalIO io{};
+    io.n_env = n_env; io.X = X; io.twist = twist; io.s = s; io.wrench = wrench; io.sdot = sdot;
+    io.n_pairs = reinterpret_cast<long long*>(n_pairs); io.flags = flags;
+    int nl = 0;
+    if (c->scene.n_small > 0) {  // small instructions are cheap: every rank evaluates them completely
+        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins));
+        CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
+    }
+    CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
+    // world == 1 still goes through the partial buffer so that the protocol is identical
+    CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, 0, c->shard_rank, c->shard_world, 0, c->stream, &nl));
+    c->launches += nl;
+    c->sharded_io = io;
+    c->sharded_stage = 0;
+    c->last_X = io.X; c->last_tw = io.twist;
+    return PFC_OK;
+}
+
+int pfc_eval_sharded_partials(pfc_ctx* c, double** dev_ptr, int64_t* count) {
+    if (!c || c->sharded_stage < 0 || !dev_ptr || !count) return fail(PFC_E_ARG, "pfc_eval_sharded_partials: no sharded evaluation in flight");
+    *dev_ptr = c->shard_world > 1 ? large_part_buffer(c->large_buf) : nullptr;
+    *count = c->shard_world > 1 ? int64_t(kLargePartStride) * c->sharded_io.n_env * c->large_scene.n_large : 0;
+    return PFC_OK;
+}
+
+int pfc_eval_sharded_step(pfc_ctx* c, int* more) {
+    if (!c || c->sharded_stage < 0 || !more) return fail(PFC_E_ARG, "pfc_eval_sharded_step: no sharded evaluation in flight");
+    CU(cudaSetDevice(c->device));
+    int nl = 0;
+    const int n_stage = scene_has_large_bristle(c) ? 3 : 1;
+    if (c->shard_world > 1)  // the caller has summed the partial buffer over the ranks: apply it
+        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, c->shard_rank, c->shard_world, 1, c->stream, &nl));
+    if (c->sharded_stage + 1 < n_stage) {
+        ++c->sharded_stage;
+        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, c->shard_rank, c->shard_world, 0, c->stream, &nl));
+        *more = 1;
+    } else {
+        c->sharded_stage = -1;
+        *more = 0;
+    }
+    c->launches += nl;
+    return PFC_OK;
+}
+
 int pfc_eval_dual6(pfc_ctx*, int64_t, const double*, const double*, const double*, const double*, double*, double*, int64_t*, int32_t*) {
     return fail(PFC_E_ARG, "pfc_eval_dual6: not built yet");
 }

@@ -359,3 +359,65 @@ def test_large_path_no_contact_and_empty():
     X, tw, s = S.boundary_arrays(m_gpu, x)
     g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
     assert (g["n_pairs"] == 0).all() and (g["wrench"] == 0).all()
+
+
+def test_sharded_large_scene_two_ranks_on_one_gpu():
+    """The multi-GPU split of one large scene, emulated with two contexts (rank 0 and 1 of world 2) on
+    one GPU: each evaluates its slice of the chunks, the partial buffers are summed (what the NCCL
+    allreduce does), and both end with the same wrench / s-dot as the unsharded evaluation."""
+    import torch
+    from pfc_b200 import capi, parallel
+    n_env = 2
+    build = _sphere_scene(4, 3, with_small=True)
+    ref = build(capi.Context(0), n_env)
+    ranks = []
+    for r in range(2):
+        ctx = capi.Context(0)
+        ctx_m = build(ctx, n_env)
+        ctx.set_shard(r, 2)
+        ranks.append((ctx, ctx_m))
+    x = _sphere_states(ref, n_env, 21)
+    X, tw, s = S.boundary_arrays(ref, x)
+    full = ref.backend.eval_f64(X, tw, s.reshape(n_env, 1, 6))
+    dev = torch.device("cuda", 0)
+    n_ins = ref.backend.n_ins
+    bufs = []
+    for ctx, _ in ranks:
+        b = dict(X=torch.from_numpy(X).to(dev), tw=torch.from_numpy(tw).to(dev), s=torch.from_numpy(s.reshape(n_env, 1, 6).copy()).to(dev),
+                 w=torch.zeros((n_env, n_ins, 6), dtype=torch.float64, device=dev), sd=torch.zeros((n_env, 1, 6), dtype=torch.float64, device=dev),
+                 np_=torch.zeros((n_env, n_ins), dtype=torch.int64, device=dev), fl=torch.zeros((n_env, n_ins), dtype=torch.int32, device=dev))
+        bufs.append(b)
+        ctx.eval_sharded_begin(n_env, b["X"].data_ptr(), b["tw"].data_ptr(), b["s"].data_ptr(), b["w"].data_ptr(), b["sd"].data_ptr(),
+                               b["np_"].data_ptr(), b["fl"].data_ptr())
+    n_exchange = 0
+    while True:
+        parts = []
+        for ctx, _ in ranks:
+            ctx.sync()
+            ptr, count = ctx.eval_sharded_partials()
+            assert count == 22 * n_env * 3
+            parts.append((ptr, count))
+        # the "allreduce": sum the two device buffers and write the sum back into both
+        import ctypes
+        cudart = ctypes.CDLL("libcudart.so")
+        host = [np.zeros(c) for _, c in parts]
+        for h, (ptr, c) in zip(host, parts):
+            assert cudart.cudaMemcpy(h.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(ptr), ctypes.c_size_t(8 * c), 2) == 0
+        total = host[0] + host[1]
+        for ptr, c in parts:
+            assert cudart.cudaMemcpy(ctypes.c_void_p(ptr), total.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(8 * c), 1) == 0
+        n_exchange += 1
+        more = [ctx.eval_sharded_step() for ctx, _ in ranks]
+        assert more[0] == more[1]
+        if not more[0]:
+            break
+    assert n_exchange == 3  # bristle instruction present: centre of pressure, stiffness, friction
+    for (ctx, _), b in zip(ranks, bufs):
+        ctx.sync()
+        w = b["w"].cpu().numpy()
+        scale = np.abs(full["wrench"]).max()
+        assert wrench_rel_err(w, full["wrench"], floor=1e-9 * scale) <= 1e-12   # same chunk sums, different association only
+        assert (b["np_"].cpu().numpy() == full["n_pairs"]).all()
+        assert ((b["fl"].cpu().numpy() & 1) == (full["flags"] & 1)).all()
+        assert np.allclose(b["sd"].cpu().numpy(), full["sdot"], rtol=1e-6, atol=1e-9 * np.abs(full["sdot"]).max())
+    assert parallel.env_range(10, 1, 3) == (3, 6)
