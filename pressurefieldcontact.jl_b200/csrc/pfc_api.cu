@@ -97,6 +97,10 @@ struct pfc_ctx {
     std::vector<int32_t> large_ins_host;
     int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
     EvalIO sharded_io{};
+    // Jacobian mode staging + the pair lists it may reuse
+    DevBuf<double> d_X7, d_tw7, d_s7, d_w7, d_sd7;
+    DevBuf<int32_t> d_large_index;
+    int64_t lists_n_env = -1;   // n_env of the evaluation whose pair lists (d_small_pairs / large_buf, d_np, d_fl) are current
     bool timing = false;
     cudaEvent_t ev[8] = {};
     bool ev_valid = false;
@@ -176,6 +180,7 @@ int pfc_destroy(pfc_ctx* c) {
     c->d_dbg_pairs.release(); c->d_last_np.release(); c->d_small_pairs.release();
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     c->d_large.release(); c->d_leaf_path.release(); c->d_leaf_depth.release();
+    c->d_X7.release(); c->d_tw7.release(); c->d_s7.release(); c->d_w7.release(); c->d_sd7.release(); c->d_large_index.release();
     large_buffers_destroy(c->large_buf);
     delete c;
     return PFC_OK;
@@ -444,6 +449,7 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
     if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
     CU(cudaMemcpyAsync(fl, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->lists_n_env = n_env;  // d_np / d_fl / pair lists of this evaluation can be reused by pfc_eval_dual6(X_bp = NULL)
     for (size_t k = 0; k < ne * ni; ++k) {
         if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
         if (fl[k] & PFC_FLAG_OVERFLOW) return fail(PFC_E_CAPACITY, "candidate-pair capacity exceeded");
@@ -503,8 +509,57 @@ int pfc_eval_sharded_step(pfc_ctx* c, int* more) {
     return PFC_OK;
 }
 
-int pfc_eval_dual6(pfc_ctx*, int64_t, const double*, const double*, const double*, const double*, double*, double*, int64_t*, int32_t*) {
-    return fail(PFC_E_ARG, "pfc_eval_dual6: not built yet");
+int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* X7, const double* twist7, const double* s7, double* wrench7,
+                   double* sdot7, int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_dual6: context not finalized");
+    if (n_env < 0 || !X7 || !twist7 || !wrench7) return fail(PFC_E_ARG, "pfc_eval_dual6: NULL buffer");
+    if (c->n_bristle > 0 && (!s7 || !sdot7)) return fail(PFC_E_ARG, "pfc_eval_dual6: bristle instructions need s7 and sdot7");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
+    int nl = 0;
+    if (X_bp) {  // traverse with the Float64 transform (calcTriTetIntersections! always uses m.float)
+        CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+        CU(cudaMemcpyAsync(c->d_X.p, X_bp, sizeof(double) * 16 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+        EvalIO io{};
+        io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
+        if (c->scene.n_small > 0) {
+            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni));
+            CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
+        }
+        if (c->large_scene.n_large > 0) {
+            CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
+            CU(large_write_counts(c->scene, c->large_scene, io, c->large_buf, c->stream));
+            nl += 1;
+        }
+        c->lists_n_env = n_env;
+    } else if (c->lists_n_env != n_env) {
+        return fail(PFC_E_ARG, "pfc_eval_dual6: X_bp is NULL but no pair lists of a previous pfc_eval_f64 with the same n_env exist");
+    }
+    CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni));
+    if (nb) { CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
+    CU(cudaMemcpyAsync(c->d_X7.p, X7, sizeof(double) * 112 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_tw7.p, twist7, sizeof(double) * 42 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+    if (nb) CU(cudaMemcpyAsync(c->d_s7.p, s7, sizeof(double) * 42 * ne * nb, cudaMemcpyHostToDevice, c->stream));
+    std::vector<int32_t> large_index(ni, -1);
+    for (size_t k = 0; k < c->large_ins_host.size(); ++k) large_index[c->large_ins_host[k]] = int32_t(k);
+    CU(c->d_large_index.ensure(ni));
+    CU(cudaMemcpyAsync(c->d_large_index.p, large_index.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p,
+                         c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
+                         c->large_scene.n_large, c->stream));
+    c->launches += nl + 1;
+    CU(cudaMemcpyAsync(wrench7, c->d_w7.p, sizeof(double) * 42 * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    if (nb) CU(cudaMemcpyAsync(sdot7, c->d_sd7.p, sizeof(double) * 42 * ne * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int32_t> fl_local;
+    int32_t* fl = flags;
+    if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
+    CU(cudaMemcpyAsync(fl, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < ne * ni; ++k)
+        if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
+    return PFC_OK;
 }
 
 int pfc_set_debug(pfc_ctx* c, int keep_pairs) {

@@ -582,6 +582,26 @@ cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, 
     return cudaSuccess;
 }
 const int3* large_sorted_ptr(const LargeBuffers* b) { return b->sorted; }
+const unsigned* large_seg_start_ptr(const LargeBuffers* b) { return b->seg_start; }
+
+namespace {
+__global__ void write_counts_kernel(SceneDev sc, LargeScene ls, EvalIO io, const unsigned* seg_start, const unsigned* seg_end, unsigned n_prob) {
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n_prob; p += gridDim.x * blockDim.x) {
+        long long env; int k;
+        prob_to_ei(sc, ls, (int)p, env, k);
+        io.n_pairs[env * sc.n_ins + k] = (long long)seg_end[p] - (long long)seg_start[p];
+        io.flags[env * sc.n_ins + k] = 0;
+    }
+}
+}  // namespace
+
+// Broad phase only (Jacobian mode): publish the pair counts of the large instructions.
+cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream) {
+    const unsigned n_prob = (unsigned)(io.n_env * ls.n_large);
+    if (n_prob == 0) return cudaSuccess;
+    write_counts_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(sc, ls, io, b->seg_start, b->seg_end, n_prob);
+    return cudaGetLastError();
+}
 
 // Broad phase + sort + segments.  Synchronises once (reads the pair count) so that capacities can
 // grow like the reference's VectorCache (src/obb/vector_cache.jl:11-15): on overflow the buffers are

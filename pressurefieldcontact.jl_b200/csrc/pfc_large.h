@@ -24,10 +24,16 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
 // stage 0: regularized wrench / bristle centre of pressure; 1: bristle stiffness; 2: bristle friction
 cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int shard_rank, int shard_world,
                                int apply_parts, cudaStream_t stream, int* n_launches);
+cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream);
 unsigned large_last_pairs(const LargeBuffers* b);
 unsigned long long large_last_tests(const LargeBuffers* b);
 double* large_part_buffer(LargeBuffers* b);     // [n_problem][22] partial sums of the last stage (sharded mode)
 constexpr int kLargePartStride = 22;
 cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, long long* n_out, cudaStream_t stream);
+
+// Jacobian mode (pfc_dual.cu): narrow phase + friction + reduction on Dual<6> over existing pair lists.
+cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double* X7, const double* twist7, const double* s7, double* wrench7, double* sdot7,
+                              const long long* n_pairs, int* flags, const unsigned* small_pairs, int small_cap, const LargeBuffers* lb,
+                              const int32_t* large_index, int n_large, cudaStream_t stream);
 
 }  // namespace pfc

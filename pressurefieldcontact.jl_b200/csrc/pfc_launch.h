@@ -27,6 +27,9 @@ int small_cap(int max_pairs);
 cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches,
                                   cudaEvent_t* ev = nullptr);
 
+// broad phase of the small path only (Jacobian mode re-traverses with the Float64 state, then evaluates on Duals)
+cudaError_t launch_broad_small_only(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches);
+
 // single-thread debug kernel: re-runs the narrow phase of one (env, ins) over a given pair list in
 // order and writes the traction points (8 doubles each) -- the reference's TractionCache.
 cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long env, int ins, const int* pairs, long long n_pairs, double* out,

@@ -458,6 +458,14 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
     return e;
 }
 
+cudaError_t launch_broad_small_only(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches) {
+    if (io.n_env * sc.n_small == 0) return cudaSuccess;
+    const int cap = small_cap(max_pairs);
+    const int bg = cap <= 320 ? 16 : 32;
+    if (n_launches) *n_launches += 1;
+    return PFC_DISPATCH_G(launch_broad_g, bg, 4, sc, io, cap, pairs, stream);
+}
+
 cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long env, int ins, const int* pairs, long long n_pairs, double* out,
                                  int cap_points, int* n_points, cudaStream_t stream) {
     dump_traction_kernel<<<1, 1, 0, stream>>>(sc, io, env, ins, pairs, n_pairs, out, cap_points, n_points);

@@ -421,3 +421,77 @@ def test_sharded_large_scene_two_ranks_on_one_gpu():
         assert ((b["fl"].cpu().numpy() & 1) == (full["flags"] & 1)).all()
         assert np.allclose(b["sd"].cpu().numpy(), full["sdot"], rtol=1e-6, atol=1e-9 * np.abs(full["sdot"]).max())
     assert parallel.env_range(10, 1, 3) == (3, 6)
+
+
+# ---- Jacobian mode: Dual{Nothing,Float64,6} ---------------------------------------------------------------
+def _dual_inputs(m, x, seed_start):
+    X0, X7, tw7, s7 = S.boundary_arrays_dual6(m, x, seed_start)
+    return X0, X7, tw7, (s7 if m.n_bristle else None)
+
+
+def _rel7(a, b, floor):
+    """max relative error per 3-vector half; value and each partial are scaled separately, but a partial that is
+    pure rounding noise (below 1e-6 of the array's overall scale) is measured against that overall scale;
+    `floor` is the fraction of a partial's scale below which a force/torque half is measured against the scale itself"""
+    a, b = np.asarray(a), np.asarray(b)
+    worst = 0.0
+    overall = max(np.abs(b).max(), 1e-300)
+    for d in range(7):
+        worst = max(worst, wrench_rel_err(a[..., d], b[..., d], floor=floor * max(np.abs(b[..., d]).max(), 1e-6 * overall)))
+    return worst
+
+
+def test_dual6_boxes_matches_oracle_and_finite_differences():
+    """Jacobian chunks on the test/boxes.jl scene (regularized friction): value + 6 partials of every
+    wrench against the Dual oracle (1e-9) and against central differences of the Float64 path."""
+    m_gpu, m_cpu = _both(lambda b, n: scene_boxes(b, n)[0])
+    x = boxes_env_states(m_gpu, 3)[2]
+    for seed_start in (6, 27, 33):     # box 2 pose, box 1 velocity, box 2/3 velocity
+        X0, X7, tw7, _ = _dual_inputs(m_gpu, x, seed_start)
+        g = m_gpu.backend.eval_dual6(X0, X7, tw7)
+        c = m_cpu.backend.eval_dual6(X0, X7, tw7)
+        assert (g["n_pairs"] == c["n_pairs"]).all() and (g["flags"] == c["flags"]).all()
+        assert _rel7(g["wrench"], c["wrench"], 1e-3) <= TOL
+        assert np.abs(c["wrench"][..., 1:]).max() > 0
+        # finite differences of the Float64 path through the same C ABI
+        h = 1e-7
+        for d in range(6):
+            xp, xm = x.copy(), x.copy()
+            xp[seed_start + d] += h
+            xm[seed_start + d] -= h
+            Xp, twp, _ = S.boundary_arrays(m_gpu, xp)
+            Xm, twm, _ = S.boundary_arrays(m_gpu, xm)
+            fd = (m_gpu.backend.eval_f64(Xp, twp)["wrench"] - m_gpu.backend.eval_f64(Xm, twm)["wrench"]) / (2 * h)
+            an = g["wrench"][..., 1 + d]
+            assert np.allclose(an, fd, rtol=2e-4, atol=2e-5 * max(np.abs(fd).max(), 1.0)), (seed_start, d)
+    # reuse of the previous Float64 pair lists (X_bp = NULL): same answer
+    Xf, twf, _ = S.boundary_arrays(m_gpu, x)
+    m_gpu.backend.eval_f64(Xf, twf)
+    X0, X7, tw7, _ = _dual_inputs(m_gpu, x, 6)
+    g1 = m_gpu.backend.eval_dual6(None, X7, tw7)
+    g2 = m_gpu.backend.eval_dual6(X0, X7, tw7)
+    assert np.array_equal(g1["wrench"], g2["wrench"])
+
+
+def test_dual6_bristle_and_tet_tet():
+    """Dual mode through the bristle model (K̄^(-1/2) differentiated analytically) and tet-tet clipping."""
+    m_gpu, m_cpu = _both(_tet_tet_scene)
+    rng = np.random.default_rng(3)
+    r = 0.05
+    x = np.zeros(S.num_x(m_gpu))
+    nq = m_gpu.nq
+    x[0:3] = rng.uniform(-0.05, 0.05, 3)
+    x[3:6] = [0.004, -0.003, r - 0.003]
+    x[6:9] = rng.uniform(-0.05, 0.05, 3)
+    x[9:12] = [0.01, 0.02, 3 * r - 0.006]
+    x[nq:nq + 12] = rng.uniform(-1, 1, 12) * 0.2
+    x[nq + 12:] = rng.uniform(-1, 1, 6) * 1e-4
+    for seed_start in (0, 6, 18, 24):   # poses, velocities, bristle state
+        X0, X7, tw7, s7 = _dual_inputs(m_gpu, x, seed_start)
+        g = m_gpu.backend.eval_dual6(X0, X7, tw7, s7)
+        c = m_cpu.backend.eval_dual6(X0, X7, tw7, s7)
+        assert (g["n_pairs"] == c["n_pairs"]).all() and (g["flags"] == c["flags"]).all()
+        # regularized instructions (0, 1): 1e-9; the bristle instruction (2) inherits the conditioning of K̄^(-1/2)
+        assert _rel7(g["wrench"][:, :2], c["wrench"][:, :2], 1e-3) <= TOL
+        assert _rel7(g["wrench"][:, 2:], c["wrench"][:, 2:], 1e-3) <= 1e-5
+        assert _rel7(g["sdot"], c["sdot"], 1e-3) <= 1e-3
