@@ -28,7 +28,7 @@ import numpy as np
 
 __all__ = [
     "eMesh", "as_tri_eMesh", "as_tet_eMesh", "transform", "eMesh_box", "eMesh_half_plane", "eMesh_sphere",
-    "eMesh_grid_square", "extrude_mesh", "FlatTree", "eMesh_to_tree", "tet_volume", "fit_tri_obb", "fit_tet_obb",
+    "eMesh_grid_square", "extrude_mesh", "FlatTree", "eMesh_to_tree", "tet_volume", "fit_tri_obb", "fit_tet_obb", "fit_tri_obb_batch", "fit_tet_obb_batch",
 ]
 
 
@@ -364,6 +364,40 @@ def fit_tet_obb(p: np.ndarray, eps: np.ndarray):
     return boxes[2]
 
 
+def _make_obb_batch(p: np.ndarray, i_start: int):
+    """_make_obb for a batch p[n, N, 3] (same arithmetic, vectorised over the primitives)."""
+    i_next = (i_start % 3) + 1
+    d = p[:, i_next - 1] - p[:, i_start - 1]
+    e1 = d / np.sqrt((d * d).sum(axis=1, keepdims=True))
+    nrm = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 1]) * 0.5
+    e3 = nrm / np.sqrt((nrm * nrm).sum(axis=1, keepdims=True))
+    e2 = np.cross(e3, e1)
+    R = np.stack([e1, e2, e3], axis=2)                    # [n, 3, 3], columns are the axes
+    proj = np.einsum("nki,nij->nkj", p, R)
+    lo, hi = proj.min(axis=1), proj.max(axis=1)
+    c = (hi + lo) * 0.5
+    e = (hi - lo) * 0.5
+    return np.einsum("nij,nj->ni", R, c), e, R
+
+
+def fit_tri_obb_batch(p: np.ndarray):
+    return _make_obb_batch(np.asarray(p, dtype=np.float64), 1)
+
+
+def fit_tet_obb_batch(p: np.ndarray, eps: np.ndarray):
+    p = np.asarray(p, dtype=np.float64)
+    if not (0.0 < _vol(p[:, 0].T, p[:, 1].T, p[:, 2].T, p[:, 3].T)).all():
+        raise ValueError("inverted tet")
+    i = np.argmax(np.abs(eps), axis=1) + 1
+    perm = np.array([[k - 1 for k in _TET_PERM[j]] for j in (1, 2, 3, 4)])[i - 1]
+    p = np.take_along_axis(p, perm[:, :, None], axis=1)
+    boxes = [_make_obb_batch(p, s) for s in (1, 2, 3)]
+    area = np.stack([8 * (b[1][:, 0] * b[1][:, 1] + b[1][:, 1] * b[1][:, 2] + b[1][:, 2] * b[1][:, 0]) for b in boxes], axis=1)
+    pick = np.where(np.maximum(area[:, 1], area[:, 2]) <= area[:, 0], 0, np.where(np.maximum(area[:, 0], area[:, 2]) <= area[:, 1], 1, 2))
+    sel = lambda j: np.choose(pick.reshape((-1,) + (1,) * (boxes[0][j].ndim - 1)), [b[j] for b in boxes])
+    return sel(0), sel(1), sel(2)
+
+
 # ------------------------------------------------------------------------------------------------
 # Bounding-volume tree
 # ------------------------------------------------------------------------------------------------
@@ -577,16 +611,18 @@ def _flatten(root: _Node, m: eMesh, prims: np.ndarray) -> FlatTree:
     left = np.full(n, -1, np.int32)
     right = np.full(n, -1, np.int32)
     leaf_id = np.full(n, -1, np.int32)
+    leaf_nodes = np.array([k for k, nd in enumerate(order) if nd.leaf >= 0])
+    leaf_prims = np.array([order[k].leaf for k in leaf_nodes])
+    pts = m.point[prims[leaf_prims]]
+    if m.is_tri:
+        cb, eb, Rb = fit_tri_obb_batch(pts)
+    else:
+        cb, eb, Rb = fit_tet_obb_batch(pts, m.eps[prims[leaf_prims]])
+    c[leaf_nodes], e[leaf_nodes] = cb, eb
+    R[leaf_nodes] = np.transpose(Rb, (0, 2, 1)).reshape(-1, 9)  # column-major
+    leaf_id[leaf_nodes] = leaf_prims
     for k, nd in enumerate(order):
-        if nd.leaf >= 0:
-            p = m.point[prims[nd.leaf]]
-            if m.is_tri:
-                ck, ek, Rk = fit_tri_obb(p)
-            else:
-                ck, ek, Rk = fit_tet_obb(p, m.eps[prims[nd.leaf]])
-            c[k], e[k], R[k] = ck, ek, Rk.T.reshape(9)  # column-major
-            leaf_id[k] = nd.leaf
-        else:
+        if nd.leaf < 0:
             c[k] = (nd.hi + nd.lo) * 0.5
             e[k] = (nd.hi - nd.lo) * 0.5
             R[k] = np.eye(3).reshape(9)
