@@ -28,7 +28,7 @@ import numpy as np
 
 __all__ = [
     "eMesh", "as_tri_eMesh", "as_tet_eMesh", "transform", "eMesh_box", "eMesh_half_plane", "eMesh_sphere",
-    "eMesh_grid_square", "extrude_mesh", "FlatTree", "eMesh_to_tree", "tet_volume", "fit_tri_obb", "fit_tet_obb", "fit_tri_obb_batch", "fit_tet_obb_batch",
+    "eMesh_grid_square", "extrude_mesh", "create_swept_mesh", "f_swept_triv", "f_swept_circle", "FlatTree", "eMesh_to_tree", "tet_volume", "fit_tri_obb", "fit_tet_obb", "fit_tri_obb_batch", "fit_tet_obb_batch",
 ]
 
 
@@ -274,6 +274,80 @@ def eMesh_sphere(rad=1.0, n_div: int = 4) -> eMesh:
     eps = np.concatenate([np.zeros(n_vert), [1.0]])
     point = np.concatenate([surf.point, np.zeros((1, 3))])
     return eMesh(point, surf.tri, tet, eps)
+
+
+def f_swept_triv(theta: float):
+    """Straight path along +y (src/geometry/mesh_create_swept.jl:19-23): position, radial direction, path direction."""
+    n1 = np.array([0.0, 0.0, -1.0])
+    n2 = np.array([0.0, 1.0, 0.0])
+    return n2 * theta, n1, n2
+
+
+def f_swept_circle(r: float, theta: float):
+    """Circular path of radius r in the xy plane (src/geometry/mesh_create_swept.jl:8-12)."""
+    n1 = np.array([math.cos(theta), math.sin(theta), 0.0])
+    n2 = np.array([-math.sin(theta), math.cos(theta), 0.0])
+    return r * n1, n1, n2
+
+
+def _rodrigues(angle: float, axis: np.ndarray, v: np.ndarray) -> np.ndarray:
+    a = axis / np.linalg.norm(axis)
+    return v * math.cos(angle) + np.cross(a, v) * math.sin(angle) + a * float(a @ v) * (1.0 - math.cos(angle))
+
+
+def _remove_degenerate(m: eMesh, tol: float = 1.0e-6) -> None:
+    """remove_degenerate! (src/geometry/mesh.jl:242-255): drop primitives whose area / volume is below tol x the largest."""
+    if m.tet is not None and len(m.tet):
+        p = m.point[m.tet]
+        vol = _vol(p[:, 0].T, p[:, 1].T, p[:, 2].T, p[:, 3].T)
+        m.tet = m.tet[~(vol < vol.max() * tol)]
+    if m.tri is not None and len(m.tri):
+        p = m.point[m.tri]
+        area = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 1]), axis=1)
+        m.tri = m.tri[~(area < area.max() * tol)]
+
+
+def create_swept_mesh(fun_gen, lr, rad, n_side: int = 4, is_open: bool = True, rot_half: bool = True) -> eMesh:
+    """create_swept_mesh (src/geometry/mesh_create_swept.jl:76-108): an n_side-gon swept along the path fun_gen
+    through the arc-length nodes lr with (circumscribed-corrected) radii rad.  Each (path segment, side) adds 7
+    points, 2 surface triangles (+1 cap triangle at an open end) and 4 tets (add_rot_sym_segment!, :25-62);
+    eps = 1 on the path, 0 on the surface and at the open ends."""
+    lr = np.asarray(lr, dtype=np.float64)
+    rad = np.full(len(lr), float(rad)) if np.isscalar(rad) else np.asarray(rad, dtype=np.float64)
+    if len(rad) != len(lr):
+        raise ValueError("the length of lr and length of rad must be the same")
+    d_phi = 2.0 * math.pi / n_side
+    rad = rad / math.cos(d_phi / 2.0)
+    pts, tris, tets, eps = [], [], [], []
+    n_theta = len(lr) - 1
+    for k_theta in range(n_theta):
+        for k_phi in range(1, n_side + 1):
+            phi0 = d_phi * (k_phi - (0.5 if rot_half else 0.0))
+            phi1 = phi0 + d_phi
+            open_lo = is_open and k_theta == 0
+            open_hi = is_open and k_theta == n_theta - 1
+            pa, xa, ya = fun_gen(float(lr[k_theta]))
+            pb, xb, yb = fun_gen(float(lr[k_theta + 1]))
+            seg = [pa, pb, (pa + pb) * 0.5,
+                   pa + _rodrigues(phi0, ya, xa) * rad[k_theta], pb + _rodrigues(phi0, yb, xb) * rad[k_theta + 1],
+                   pa + _rodrigues(phi1, ya, xa) * rad[k_theta], pb + _rodrigues(phi1, yb, xb) * rad[k_theta + 1]]
+            o = len(pts)
+            pts += seg
+            tris += [(o + 3, o + 5, o + 6), (o + 3, o + 6, o + 4)]
+            tets += [(o + 0, o + 2, o + 3, o + 5), (o + 2, o + 1, o + 4, o + 6), (o + 2, o + 3, o + 5, o + 6), (o + 3, o + 2, o + 4, o + 6)]
+            e = [1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0]
+            if open_lo:
+                e[0] = 0.0
+                tris.append((o + 0, o + 5, o + 3))
+            if open_hi:
+                e[1] = 0.0
+                tris.append((o + 1, o + 4, o + 6))
+            eps += e
+    m = eMesh(np.array(pts), np.array(tris, dtype=np.int64), np.array(tets, dtype=np.int64), np.array(eps), check=False)
+    _remove_degenerate(m)
+    _dedupe_points(m)
+    _delete_opposing_triangles(m)
+    return m
 
 
 def eMesh_grid_square(side: float, n_cell: int) -> eMesh:

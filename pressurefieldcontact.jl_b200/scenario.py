@@ -16,7 +16,7 @@ Mirrors (names, argument meaning, defaults and error behaviour) -- paths relativ
 
 The reference delegates rigid-body kinematics to RigidBodyDynamics 1.4.0 (not vendored).  The
 subset needed at the boundary -- world-attached bodies, SPQuatFloating joints (q = [MRP; trans],
-v = [omega; vel] in the body frame) and Prismatic joints on the world -- is restated here in
+v = [omega; vel] in the body frame), Prismatic and Revolute joints, in chains -- is restated here in
 numpy; it runs on the host exactly where the reference runs it.
 The device work is done by a *backend* (pfc_b200.capi.Context in production).
 """
@@ -30,7 +30,7 @@ import numpy as np
 from .geometry import FlatTree, eMesh, eMesh_to_tree
 
 __all__ = [
-    "Regularized", "Bristle", "ContactProperties", "InertiaProperties", "ContactInstructions", "MeshCache", "Prismatic",
+    "Regularized", "Bristle", "ContactProperties", "InertiaProperties", "ContactInstructions", "MeshCache", "Prismatic", "Revolute", "add_body",
     "SPQuatFloating", "MechanismScenario", "add_contact", "add_body_contact", "add_friction_regularize", "add_friction_bristle",
     "finalize", "set_state_spq", "set_configuration", "get_state", "num_x", "boundary_arrays", "boundary_arrays_dual6",
     "force_all_elastic_intersections", "mrp_to_rotation", "rotation_to_mrp",
@@ -143,13 +143,21 @@ class Prismatic:
 
 
 @dataclass
+class Revolute:
+    axis: Sequence[float] = (0.0, 0.0, 1.0)
+    nq: int = 1
+    nv: int = 1
+
+
+@dataclass
 class Body:
     name: str
     joint: object            # None => the world (root) body
     q0: int = 0              # offset of this joint's q in the q vector
     v0: int = 0
-    pose_R: np.ndarray = field(default_factory=lambda: np.eye(3))   # joint_pose (parent = world)
+    pose_R: np.ndarray = field(default_factory=lambda: np.eye(3))   # joint_pose on the parent body
     pose_t: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    parent: int = 0          # index of the parent body (0 = world); bodies are stored parents first
 
 
 @dataclass
@@ -223,11 +231,12 @@ def add_contact(m: MechanismScenario, name: str, e_mesh: eMesh, c_prop: Optional
     return len(m.MeshCache) - 1
 
 
-def add_body(m: MechanismScenario, name: str, joint=None, pose_R=None, pose_t=None) -> int:
-    """add_body! restricted to what the contact path needs: the joint type and its pose on the
-    world (src/mechanism_scenario.jl:324-345; inertia stays with the caller's dynamics)."""
+def add_body(m: MechanismScenario, name: str, joint=None, pose_R=None, pose_t=None, body: Optional[int] = None) -> int:
+    """add_body! restricted to what the contact path needs: the joint type, its parent body
+    (``body``, default the world) and its pose on the parent (src/mechanism_scenario.jl:324-345;
+    inertia stays with the caller's dynamics)."""
     joint = SPQuatFloating() if joint is None else joint
-    b = Body(name, joint, q0=m.nq, v0=m.nv)
+    b = Body(name, joint, q0=m.nq, v0=m.nv, parent=0 if body is None else body)
     if pose_R is not None:
         b.pose_R = np.asarray(pose_R, dtype=np.float64)
     if pose_t is not None:
@@ -237,11 +246,11 @@ def add_body(m: MechanismScenario, name: str, joint=None, pose_R=None, pose_t=No
 
 
 def add_body_contact(m: MechanismScenario, name: str, e_mesh: eMesh, i_prop: Optional[InertiaProperties] = None,
-                     c_prop: Optional[ContactProperties] = None, joint=None, tree: Optional[FlatTree] = None):
-    """add_body_contact! (src/mechanism_scenario.jl:279-289).  Returns (body, joint, id)."""
-    body = add_body(m, name, joint)
-    mesh_id = add_contact(m, name, e_mesh, c_prop=c_prop, body=body, tree=tree)
-    return body, m.bodies[body].joint, mesh_id
+                     c_prop: Optional[ContactProperties] = None, joint=None, tree: Optional[FlatTree] = None, body: Optional[int] = None):
+    """add_body_contact! (src/mechanism_scenario.jl:279-289); ``body`` is the parent.  Returns (body, joint, id)."""
+    new_body = add_body(m, name, joint, body=body)
+    mesh_id = add_contact(m, name, e_mesh, c_prop=c_prop, body=new_body, tree=tree)
+    return new_body, m.bodies[new_body].joint, mesh_id
 
 
 def _add_friction(m: MechanismScenario, id_1: int, id_2: int, fric_model, chi: float, n_quad_rule: int) -> ContactInstructions:
@@ -364,8 +373,13 @@ def set_configuration(m: MechanismScenario, body: int, config) -> None:
 # --------------------------------------------------------------------------------------------------
 # kinematics at the boundary (RigidBodyDynamics restated for the supported joints)
 # --------------------------------------------------------------------------------------------------
+def _joint_axis(b: Body):
+    return np.asarray(b.joint.axis, dtype=np.float64)
+
+
 def _body_kinematics(m: MechanismScenario, q, v):
-    """Per body: (R, t) = transform_to_root, (ang, lin) = twist_wrt_world expressed in world."""
+    """Per body: (R, t) = transform_to_root, (ang, lin) = twist_wrt_world expressed in world (about
+    the world origin).  Bodies are stored parents first, so one forward sweep covers every chain."""
     dt = np.result_type(q.dtype, v.dtype)
     out = []
     for b in m.bodies:
@@ -376,17 +390,47 @@ def _body_kinematics(m: MechanismScenario, q, v):
             Rj = mrp_to_rotation(q[b.q0:b.q0 + 3])
             tj = q[b.q0 + 3:b.q0 + 6]
             om_b, vel_b = v[b.v0:b.v0 + 3], v[b.v0 + 3:b.v0 + 6]
+        elif isinstance(b.joint, Revolute):
+            ax = _joint_axis(b)
+            ax = ax / np.linalg.norm(ax)
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            th = q[b.q0]
+            Rj = np.eye(3, dtype=dt) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+            tj = np.zeros(3, dtype=dt)
+            om_b, vel_b = ax * v[b.v0], np.zeros(3, dtype=dt)
         else:  # Prismatic
-            ax = np.asarray(b.joint.axis, dtype=np.float64)
+            ax = _joint_axis(b)
             Rj = np.eye(3, dtype=dt)
             tj = ax * q[b.q0]
             om_b, vel_b = np.zeros(3, dtype=dt), ax * v[b.v0]
-        R = b.pose_R @ Rj
-        t = b.pose_R @ tj + b.pose_t
-        ang = R @ om_b
-        lin = R @ vel_b + np.cross(t, ang)
-        out.append((R, t, ang, lin))
+        Rp, tp, ap, lp = out[b.parent]
+        Rpose = Rp @ b.pose_R
+        R = Rpose @ Rj
+        t = Rpose @ tj + Rp @ b.pose_t + tp
+        ang_j = R @ om_b                                   # joint twist, body frame -> world, about the world origin
+        lin_j = R @ vel_b + np.cross(t, ang_j)
+        out.append((R, t, ap + ang_j, lp + lin_j))
     return out
+
+
+def _motion_subspace_world(m: MechanismScenario, kin, bid: int):
+    """Columns of the geometric Jacobian contributed by body bid's own joint: a list of
+    (velocity index, angular part, linear part about the world origin), in world."""
+    b = m.bodies[bid]
+    R, t, _, _ = kin[bid]
+    cols = []
+    if isinstance(b.joint, SPQuatFloating):
+        for k in range(3):
+            cols.append((b.v0 + k, R[:, k], np.cross(t, R[:, k])))
+        for k in range(3):
+            cols.append((b.v0 + 3 + k, np.zeros(3), R[:, k]))
+    elif isinstance(b.joint, Revolute):
+        ax = _joint_axis(b)
+        a_w = R @ (ax / np.linalg.norm(ax))
+        cols.append((b.v0, a_w, np.cross(t, a_w)))
+    else:
+        cols.append((b.v0, np.zeros(3), R @ _joint_axis(b)))
+    return cols
 
 
 def _ins_boundary(kin, id_body_1, id_body_2):
@@ -470,16 +514,10 @@ def generalized_forces(m: MechanismScenario, x: np.ndarray, wrench_r2: np.ndarra
         lin_w = R2 @ lin
         ang_w = R2 @ ang + np.cross(t2, lin_w)
         for bid, sign in ((b2, +1.0), (b1, -1.0)):
-            b = m.bodies[bid]
-            if b.joint is None:
-                continue  # jac == nothing: world-attached mesh
-            R, t, _, _ = kin[bid]
-            if isinstance(b.joint, SPQuatFloating):
-                f[b.v0:b.v0 + 3] += sign * (R.T @ (ang_w - np.cross(t, lin_w)))
-                f[b.v0 + 3:b.v0 + 6] += sign * (R.T @ lin_w)
-            else:
-                ax_w = b.pose_R @ np.asarray(b.joint.axis, dtype=np.float64)
-                f[b.v0] += sign * float(ax_w @ lin_w)
+            while bid != 0:  # world-attached meshes have jac == nothing; every joint on the path to the root gets J' w
+                for iv, s_ang, s_lin in _motion_subspace_world(m, kin, bid):
+                    f[iv] += sign * float(s_ang @ ang_w + s_lin @ lin_w)
+                bid = m.bodies[bid].parent
     return f
 
 

@@ -80,3 +80,147 @@ def scene_c5_pile(n_side: int = 4, n_div: int = 8, backend=None, bristle_every: 
         x[nq + body.v0:nq + body.v0 + 6] = [U(-1, 1) for _ in range(3)] + [U(-0.1, 0.1) for _ in range(3)]
     x[nq + m.nv:] = [U(-1e-4, 1e-4) for _ in range(6 * m.n_bristle)]
     return m, x
+
+
+def scene_c2_pencil(is_bristle: bool = True, backend=None):
+    """C2: the gripper-and-pencil scene of test/pencil.jl:23-33,185-236 (is_bristle = true variant): a 1-tet
+    half-space, two compliant ellipsoidal pads (eMesh_sphere(pad_rad, 4) scaled (2, 1, 2): 320 tets each) on
+    prismatic joints of an arm (prismatic z -> revolute y), a rigid box on the arm, and a 12-sided swept-mesh
+    pencil (48 triangles) on a floating joint.  Instructions, in the reference's order: pencil-pad_n and
+    pencil-pad_p (bristle: k_bar 8e4, tau 0.01, magic 1e-2; mu_d 0.5, chi 0.6), pencil-plane and pad_n-pad_p
+    (tet-tet, mu_d 0) regularized with v_tol 1e-5.  Returns (scenario, dict of body indices)."""
+    pad_rad, penci_length, penci_rad = 0.0035, 0.16, 0.0035
+    m = S.MechanismScenario()
+    c_prop = S.ContactProperties(1.0e6)
+    plane = G.transform(G.eMesh_half_plane(), R=0.6)
+    pads = []
+    for sgn in (-1.0, +1.0):
+        pad = G.as_tet_eMesh(G.eMesh_sphere(pad_rad, 4))
+        G.transform(pad, t=(0.0, sgn * (pad_rad + penci_rad), 0.0))
+        G.transform(pad, R=np.diag([2.0, 1.0, 2.0]))
+        pads.append(pad)
+    arm_box = G.as_tri_eMesh(G.eMesh_box(pad_rad * np.array([1.0, 7.0, 1.0]), pad_rad * np.array([0.0, -4.0, 8.0])))
+    pencil = G.as_tri_eMesh(G.create_swept_mesh(G.f_swept_triv, [0.0, 0.013, penci_length], [0.0, penci_rad, penci_rad], 12, True, rot_half=True))
+    G.transform(pencil, t=(0.0, 0.0, penci_rad))
+
+    id_plane = S.add_contact(m, "plane", G.as_tet_eMesh(plane), c_prop=c_prop)
+    b_tra_z = S.add_body(m, "tra_z", joint=S.Prismatic((0.0, 0.0, 1.0)))
+    b_rev_y = S.add_body(m, "rev_y", joint=S.Revolute((0.0, 1.0, 0.0)), body=b_tra_z)
+    S.add_contact(m, "rev_y", arm_box, body=b_rev_y)
+    b_pad_n, _, id_pad_n = S.add_body_contact(m, "pad_n", pads[0], c_prop=c_prop, joint=S.Prismatic((0.0, +1.0, 0.0)), body=b_rev_y)
+    b_pad_p, _, id_pad_p = S.add_body_contact(m, "pad_p", pads[1], c_prop=c_prop, joint=S.Prismatic((0.0, -1.0, 0.0)), body=b_rev_y)
+    b_penci, _, id_penci = S.add_body_contact(m, "name", pencil)
+    if is_bristle:
+        S.add_friction_bristle(m, id_penci, id_pad_n, mu_d=0.5, chi=0.6, k_bar=8.0e4, magic=1.0e-2, tau=0.01)
+        S.add_friction_bristle(m, id_penci, id_pad_p, mu_d=0.5, chi=0.6, k_bar=8.0e4, magic=1.0e-2, tau=0.01)
+    else:
+        S.add_friction_regularize(m, id_penci, id_pad_n, mu_d=0.5, chi=0.6, v_tol=1.0e-5)
+        S.add_friction_regularize(m, id_penci, id_pad_p, mu_d=0.5, chi=0.6, v_tol=1.0e-5)
+    S.add_friction_regularize(m, id_penci, id_plane, mu_d=0.5, chi=0.6, v_tol=1.0e-5)
+    S.add_friction_regularize(m, id_pad_n, id_pad_p, mu_d=0.0, chi=0.6, v_tol=1.0e-5)
+    S.finalize(m, backend)
+    bodies = dict(tra_z=b_tra_z, rev_y=b_rev_y, pad_n=b_pad_n, pad_p=b_pad_p, pencil=b_penci)
+    return m, bodies
+
+
+def pencil_sample_states(m, bodies, n: int = 8, seed: int = 0x5EED0C2):
+    """Sampled states along the pencil task (there is no integrator here): the
+    initial state of test/pencil.jl:225-228, the pencil gripped on the table, lifted, swung by the arm, and
+    the pads closed on each other; randomised velocities and bristle states.  Returns x[n][num_x]."""
+    u = _splitmix(seed)
+    U = lambda lo, hi: lo + (hi - lo) * u()
+    L, r = 0.16, 0.0035
+    rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]])
+    ry = lambda a: np.array([[np.cos(a), 0.0, np.sin(a)], [0.0, 1.0, 0.0], [-np.sin(a), 0.0, np.cos(a)]])
+    xs = []
+    for k in range(n):
+        mode = k % 4
+        m.q[:] = 0.0
+        m.v[:] = 0.0
+        if mode == 0:      # test/pencil.jl initial configuration: arm raised and turned, pencil lying on the table
+            z, th, grip = 0.10, np.pi / 4, 0.0
+            S.set_state_spq(m, bodies["pencil"], rot=rz(-np.pi / 2), trans=(-0.8 * L, 0.0, -U(0.0, 2e-4)))
+        elif mode == 1:    # arm lowered onto the pencil, pads squeezing it against the table
+            z, th, grip = r, 0.0, U(1e-4, 5e-4)
+            S.set_state_spq(m, bodies["pencil"], rot=rz(-np.pi / 2 + U(-0.002, 0.002)), trans=(-0.5 * L, U(-1e-4, 1e-4), -U(0.0, 2e-4)))
+        elif mode == 2:    # lifted and swung: the pencil moves with the arm frame
+            z, th, grip = 0.08, U(0.2, 1.2), U(1e-4, 5e-4)
+            Rw = ry(th)    # the pencil's frame expressed in the arm frame is RotZ(-pi/2) with its axis through the pads
+            S.set_state_spq(m, bodies["pencil"], rot=Rw @ rz(-np.pi / 2), trans=tuple(np.array([0.0, 0.0, z]) + Rw @ np.array([-0.4 * L, 0.0, -r])))
+        else:              # pencil away on the table, the pads pressed against each other (tet-tet contact)
+            z, th, grip = 0.05, U(-0.5, 0.5), r + U(1e-4, 4e-4)
+            S.set_state_spq(m, bodies["pencil"], rot=rz(U(-1, 1)), trans=(0.3, 0.1, -U(0.0, 2e-4)))
+        S.set_configuration(m, bodies["tra_z"], [z])
+        S.set_configuration(m, bodies["rev_y"], [th])
+        S.set_configuration(m, bodies["pad_n"], [grip])
+        S.set_configuration(m, bodies["pad_p"], [grip])
+        v_amp = 0.05 if (k // 4) % 2 else 0.002   # fast relative motion switches contacts off through the damping term
+        m.v[:] = [U(-v_amp, v_amp) for _ in range(m.nv)]
+        m.s[:] = [U(-2e-4, 2e-4) for _ in range(6 * m.n_bristle)]
+        xs.append(S.get_state(m).copy())
+    return np.array(xs)
+
+
+def eMesh_spoon_like(n_ring: int = 139, n_side: int = 18, length: float = 0.15) -> "G.eMesh":
+    """A closed spoon-shaped triangle surface with 2 * n_side * n_ring triangles (5004 for the defaults: the size of
+    the reference's test/data/spoon.obj, 2502 quads, which is reference data and is not copied here).  Elliptical
+    cross-sections swept along x: a narrow handle widening into a bowl; flat facets on the bottom (z = 0) and top."""
+    xs = np.linspace(-0.25 * length, 0.75 * length, n_ring)
+    half_w = 0.004 + 0.014 * np.exp(-((xs / (0.22 * length)) ** 2))        # bowl centred at x = 0
+    half_t = np.full(n_ring, 0.0015)
+    phi = (np.arange(n_side) + 0.5) * (2.0 * np.pi / n_side) - 0.5 * np.pi  # a facet, not a vertex, faces -z and +z
+    pts = [np.stack([np.full(n_side, x), a * np.cos(phi), b + b * np.sin(phi) / np.sin(phi).max()], axis=1) for x, a, b in zip(xs, half_w, half_t)]
+    pts = np.concatenate(pts + [np.array([[xs[0], 0.0, half_t[0]], [xs[-1], 0.0, half_t[-1]]])])
+    tri = []
+    ring = lambda i, j: i * n_side + (j % n_side)
+    for i in range(n_ring - 1):
+        for j in range(n_side):
+            a, b, c, d = ring(i, j), ring(i + 1, j), ring(i + 1, j + 1), ring(i, j + 1)
+            tri += [(a, b, c), (a, c, d)]
+    c0, c1 = n_ring * n_side, n_ring * n_side + 1
+    for j in range(n_side):
+        tri.append((c0, ring(0, j), ring(0, j + 1)))
+        tri.append((c1, ring(n_ring - 1, j + 1), ring(n_ring - 1, j)))
+    m = G.eMesh(pts, np.array(tri))
+    # outward orientation: flip everything if the signed volume is negative
+    p = m.point[m.tri]
+    if np.einsum("ij,ij->i", p[:, 0], np.cross(p[:, 1], p[:, 2])).sum() < 0.0:
+        m.tri = np.ascontiguousarray(m.tri[:, ::-1])
+    return m
+
+
+def scene_c2_spoon(backend=None):
+    """C2 (spoon): test/spoon.jl:23-54 re-expressed in the current API: a rigid 5004-triangle spoon
+    surface between a world-fixed compliant box and a compliant box on a z-prismatic joint (eMesh_box(0.02), 12
+    tets, E 1e6); two bristle instructions mu 0.2, chi 0.2, quadrature rule 1.  Returns (scenario, bodies)."""
+    rad_box = 0.02
+    m = S.MechanismScenario()
+    c_prop = S.ContactProperties(1.0e6)
+    box = G.as_tet_eMesh(G.eMesh_box(rad_box, (0.0, 0.0, -rad_box)))
+    id_lo = S.add_contact(m, "box_lo", box, c_prop=c_prop)
+    b_up, _, id_up = S.add_body_contact(m, "box_up", box.copy(), c_prop=c_prop, joint=S.Prismatic((0.0, 0.0, 1.0)))
+    b_spoon, _, id_spoon = S.add_body_contact(m, "spoon", eMesh_spoon_like())
+    S.add_friction_bristle(m, id_spoon, id_lo, mu_d=0.2, chi=0.2, n_quad_rule=1)
+    S.add_friction_bristle(m, id_spoon, id_up, mu_d=0.2, chi=0.2, n_quad_rule=1)
+    S.finalize(m, backend)
+    return m, dict(box_up=b_up, spoon=b_spoon)
+
+
+def spoon_sample_states(m, bodies, n: int = 6, seed: int = 0x5EED5B00):
+    """Sampled states: the spoon resting on / pressed into the lower box, the upper box above it (initial state of
+    test/spoon.jl: q_up = 0.10) or clamping it; small random twists and bristle states."""
+    u = _splitmix(seed)
+    U = lambda lo, hi: lo + (hi - lo) * u()
+    rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]])
+    xs = []
+    for k in range(n):
+        m.q[:] = 0.0
+        m.v[:] = 0.0
+        pen_lo = U(5e-5, 4e-4)
+        S.set_state_spq(m, bodies["spoon"], rot=rz(U(-0.3, 0.3)), trans=(U(-2e-3, 2e-3), U(-2e-3, 2e-3), -pen_lo))
+        q_up = 0.10 if k % 3 == 0 else 0.04 + 0.003 - pen_lo - U(5e-5, 4e-4)  # box_up spans [q - 0.04, q]; the spoon is 3 mm thick
+        S.set_configuration(m, bodies["box_up"], [q_up])
+        m.v[:] = [U(-0.003, 0.003) for _ in range(m.nv)]
+        m.s[:] = [U(-2e-4, 2e-4) for _ in range(6 * m.n_bristle)]
+        xs.append(S.get_state(m).copy())
+    return np.array(xs)

@@ -26,7 +26,7 @@ for r in rows[2:]:
     stalls = sorted(((int(float(v)), h) for h, v in zip(hdr, r) if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued") and v), reverse=True)
     print("  stalls:", ", ".join(f"{h.replace('smsp__pcsamp_warps_issue_stalled_', '')} {n}" for n, h in stalls[:7]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source=cuda,sass"], capture_output=True, text=True).stdout
-cur = None
+cur, fn = None, None
 agg = collections.defaultdict(lambda: [0, 0, 0])
 lines = {}
 for r in csv.reader(io.StringIO(src)):
@@ -35,20 +35,27 @@ for r in csv.reader(io.StringIO(src)):
     if r[0] == "File Path":
         cur = r[1].split("/")[-1]
         continue
-    if r[0] in ("Function Name", "Line No"):
+    if r[0] == "Function Name":
+        fn = r[1].split("(")[0].split("::")[-1].split("<")[0]
+        continue
+    if r[0] == "Line No":
         continue
     if len(r) > 8 and r[2] == "-" and r[0].isdigit():
         try:
             samp, inst, tinst = int(r[6] or 0), int(r[7] or 0), int(r[8] or 0)
         except ValueError:
             continue
-        agg[cur][0] += samp; agg[cur][1] += inst; agg[cur][2] += tinst
-        lines[(cur, r[0])] = (samp, inst, tinst, r[1][:90])
-tot = sum(v[0] for v in agg.values()) or 1
-toti = sum(v[1] for v in agg.values()) or 1
-print("by file (samples %, instructions %, active lanes per instruction):")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-    print(f"  {k:24s} {100 * v[0] / tot:5.1f}% {100 * v[1] / toti:5.1f}% {v[2] / max(v[1], 1):5.1f}")
-print("hottest lines (samples, instructions, lanes):")
-for (f, ln), (samp, inst, tinst, text) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:n_lines]:
-    print(f"  {samp:6d} {inst:10d} {tinst / max(inst, 1):5.1f}  {f}:{ln}  {text}")
+        a = agg[(fn, cur)]
+        a[0] += samp; a[1] += inst; a[2] += tinst
+        lines[(fn, cur, r[0])] = (samp, inst, tinst, r[1][:90])
+for kernel in sorted({k[0] for k in agg}):
+    sub = {k[1]: v for k, v in agg.items() if k[0] == kernel}
+    tot = sum(v[0] for v in sub.values()) or 1
+    toti = sum(v[1] for v in sub.values()) or 1
+    print(f"== {kernel}: by file (samples %, instructions %, active lanes per instruction):")
+    for k, v in sorted(sub.items(), key=lambda kv: -kv[1][0]):
+        print(f"  {k:24s} {100 * v[0] / tot:5.1f}% {100 * v[1] / toti:5.1f}% {v[2] / max(v[1], 1):5.1f}")
+    print("  hottest lines (samples %, instructions, lanes):")
+    sel = {k: v for k, v in lines.items() if k[0] == kernel}
+    for (_, f, ln), (samp, inst, tinst, text) in sorted(sel.items(), key=lambda kv: -kv[1][0])[:n_lines]:
+        print(f"  {100 * samp / tot:5.1f}% {inst:10d} {tinst / max(inst, 1):5.1f}  {f}:{ln}  {text}")

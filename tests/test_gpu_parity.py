@@ -495,3 +495,38 @@ def test_dual6_bristle_and_tet_tet():
         assert _rel7(g["wrench"][:, :2], c["wrench"][:, :2], 1e-3) <= TOL
         assert _rel7(g["wrench"][:, 2:], c["wrench"][:, 2:], 1e-3) <= 1e-5
         assert _rel7(g["sdot"], c["sdot"], 1e-3) <= 1e-3
+
+
+# ---- config C2: the pencil gripper and the spoon, bristle friction, sampled states ------------------------------
+def test_c2_pencil_bristle_sampled_states():
+    """test/pencil.jl with is_bristle = true: wrench / s-dot / pair-list parity on sampled
+    states of the task (the 1000-step Radau state parity needs the integrator and RigidBodyDynamics: out of scope)."""
+    from pfc_b200 import scenes
+    m_gpu, bodies = scenes.scene_c2_pencil(True, _ctx())
+    m_cpu, _ = scenes.scene_c2_pencil(True, orc.OracleContext())
+    xs = scenes.pencil_sample_states(m_gpu, bodies, 12)
+    n_contact = 0
+    for x in xs:
+        X, tw, s = S.boundary_arrays(m_gpu, x)
+        g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, m_gpu.n_bristle, 6), sdot_metric=True)
+        n_contact += int((c["flags"] & 1).sum())
+        # the generalized forces the reference would add (J' w through the arm's joints) agree as well
+        f_g = S.generalized_forces(m_gpu, x, g["wrench"][0])
+        f_c = S.generalized_forces(m_cpu, x, c["wrench"][0])
+        assert np.abs(f_g - f_c).max() <= TOL * max(np.abs(f_c).max(), 1e-300)
+    assert n_contact >= 16  # pad-pencil (bristle), pencil-plane and pad-pad (tet-tet) contacts are all exercised
+
+
+def test_c2_spoon_bristle_sampled_states():
+    """test/spoon.jl re-expressed (R5): 5004-triangle spoon surface clamped between two compliant boxes, two
+    bristle instructions, quadrature rule 1 (large-instruction path: 5004 x 12 leaf pairs)."""
+    from pfc_b200 import scenes
+    m_gpu, bodies = scenes.scene_c2_spoon(_ctx())
+    m_cpu, _ = scenes.scene_c2_spoon(orc.OracleContext())
+    xs = scenes.spoon_sample_states(m_gpu, bodies, 6)
+    n_contact = 0
+    for x in xs:
+        X, tw, s = S.boundary_arrays(m_gpu, x)
+        g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, m_gpu.n_bristle, 6), sdot_metric=True)
+        n_contact += int((c["flags"] & 1).sum())
+    assert n_contact >= 8

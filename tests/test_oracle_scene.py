@@ -281,3 +281,32 @@ def test_sdot_reproducibility_vs_lapack():
     assert n_contact > 10
     assert worst_w < 1e-5          # the friction part of the wrench goes through the same Kb^-1/2 (via Delta)
     assert 1e-9 < worst_s < 1e-3   # s-dot is not: LAPACK vs Jacobi differ far above 1e-9
+
+
+def test_c2_scenes_build_and_chain_kinematics():
+    """Config C2 host mirror: the swept-mesh pencil has the reference's 48 triangles (12 tip + 24 barrel + 12 cap after
+    remove_degenerate!), the spoon stand-in 5004; generalized forces through the arm chain (prismatic -> revolute ->
+    prismatic pads) equal a finite-difference of the contact power  f . v = sum_k w_k . twist_k."""
+    from pfc_b200 import scenes
+    octx = orc.OracleContext()
+    m, bodies = scenes.scene_c2_pencil(True, octx)
+    assert m.MeshCache[S.find_mesh_id(m, "name")].mesh.n_tri() == 48
+    assert m.MeshCache[S.find_mesh_id(m, "pad_n")].mesh.n_tet() == 320
+    assert [ci.friction_model.model for ci in m.ContactInstructions] == [1, 1, 0, 0]
+    xs = scenes.pencil_sample_states(m, bodies, 8)
+    n_checked = 0
+    for x in xs:
+        X, tw, s = S.boundary_arrays(m, x)
+        out = octx.eval_f64(X, tw, s.reshape(1, m.n_bristle, 6))
+        w = out["wrench"][0]
+        f = S.generalized_forces(m, x, w)
+        # power balance: the wrench on body 2 (in r2) times the relative twist of r2 w.r.t. r1 (in r2) summed over
+        # instructions equals f_generalized . v  (third law + J' w, non_friction.jl:267-286)
+        p_contact = float(sum(w[k] @ tw[0, k] for k in range(len(w))))
+        p_joint = float(f @ x[m.nq:m.nq + m.nv])
+        if np.abs(w).max() > 0:
+            assert abs(p_contact - p_joint) <= 1e-9 * max(abs(p_contact), np.abs(w).max() * np.abs(tw).max()), (p_contact, p_joint)
+            n_checked += 1
+    assert n_checked >= 6
+    m2, _ = scenes.scene_c2_spoon(octx.__class__())
+    assert m2.MeshCache[S.find_mesh_id(m2, "spoon")].mesh.n_tri() == 5004
