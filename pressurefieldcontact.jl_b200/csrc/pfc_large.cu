@@ -3,11 +3,15 @@
 //
 //   K1a broad_bfs_kernel   a few level-synchronous expansions of the node-pair frontier until there
 //                          are enough independent sub-problems (seeds) for the whole GPU
-//   K1b broad_dfs_kernel   persistent warps pull seeds from a global counter and run a warp-cooperative,
+//   K1b broad_dfs_kernel   persistent warps pull seeds from a global queue and run a warp-cooperative,
 //                          stack-based dual-tree traversal: the stack lives in shared memory, every
 //                          lane tests one node pair per iteration (bit-exact 15-axis SAT), children are
 //                          pushed with a warp prefix sum, leaf pairs are appended to the global pair
-//                          list with ONE atomicAdd per warp per iteration (warp-aggregated atomics)
+//                          list with ONE atomicAdd per warp per iteration (warp-aggregated atomics).
+//                          Contact patches are small compared with the meshes, so a few seeds own nearly
+//                          all of the work: a warp whose stack is deep while the queue runs dry DONATES
+//                          the oldest half of its stack (the sub-trees nearest the root) back to the
+//                          queue; idle warps keep polling until no seed is outstanding.
 //   K1c key + radix sort   the pair list arrives in nondeterministic order; each pair gets the key of
 //                          its position in the reference's recursion (src/obb/tree_types.jl:88-111):
 //                          the root-to-leaf turns of both leaves interleaved, tree 2's turn first
@@ -22,6 +26,7 @@
 // Reference: calcTriTetIntersections! + integrate_over! + yes_contact!/no_contact!
 // (/root/reference/src/contact_algorithms_non_friction.jl:70-143, src/contact_algorithms_friction.jl:50-143).
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <vector>
 
@@ -51,10 +56,19 @@ struct Counters {                 // device-resident
     unsigned int n_pairs;         // leaf pairs appended
     unsigned int overflow;        // bit0 frontier, bit1 pairs, bit2 stack
     unsigned int n_units;         // narrow-phase work units
+    unsigned int pad0[26];        // the polled queue words below get their own 128 B line (pollers must not slow the pair-list atomics)
+    unsigned int q_head;          // seed queue: next seed to hand out
+    unsigned int q_tail;          //             slots reserved (initial seeds + donations); a donated slot is readable once its tag is set
+    unsigned int n_seed0;         //             seeds the breadth-first levels left (readable without a tag)
+    int outstanding;              //             seeds queued or being traversed; 0 = traversal finished
     unsigned long long n_tests;   // node pairs tested (statistics)
+    unsigned long long n_donated; // seeds donated (statistics)
 };
 
-struct Seed { int prob; int a; int b; };   // prob = index into the large-problem list; a, b mesh-local node ids
+// prob = index into the large-problem list; a, b mesh-local node ids; tag = traversal epoch for donated seeds (0 otherwise).
+// Two 8-byte words: a donor stores (a, b), fences, then stores (prob, tag); a waiter polls (prob, tag).
+struct __align__(16) Seed { int prob; unsigned tag; int a; int b; };
+static_assert(offsetof(Counters, q_head) == 128, "queue words start a new 128 B line");
 
 PFC_D void load_xform_l(const double* __restrict__ X, Xform<double>& x) {
 #pragma unroll
@@ -101,10 +115,10 @@ PFC_D int expand_pair(const SceneDev& sc, const InsDev& ins, const double* Rab, 
 
 __global__ void init_frontier_kernel(LargeScene ls, long long n_env, Seed* frontier, Counters* cnt) {
     const long long n = n_env * ls.n_large;
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) frontier[p] = Seed{(int)p, 0, 0};
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) frontier[p] = Seed{(int)p, 0u, 0, 0};
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         cnt->frontier_n[0] = (unsigned)n; cnt->frontier_n[1] = 0; cnt->seed_head = 0; cnt->n_pairs = 0; cnt->overflow = 0; cnt->n_units = 0;
-        cnt->n_tests = 0;
+        cnt->n_tests = 0; cnt->n_donated = 0; cnt->q_head = 0; cnt->q_tail = 0; cnt->n_seed0 = 0; cnt->outstanding = 0;
     }
 }
 
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene 
         unsigned at = 0;
         if (lane == 31 && tot > 0) at = atomicAdd(&cnt->frontier_n[src ^ 1], (unsigned)tot);
         at = __shfl_sync(0xffffffffu, at, 31) + incl - n_child;
-        if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, ch[c].x, ch[c].y}; }
+        if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, 0u, ch[c].x, ch[c].y}; }
         else if (n_child > 0) atomicOr(&cnt->overflow, 1u);
         const unsigned leaf_mask = __ballot_sync(0xffffffffu, r < 0);
         if (leaf_mask) {
@@ -147,29 +161,69 @@ __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene 
     }
 }
 
-// K1b: warp-cooperative stack-based traversal of the seeds
-__global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, const Seed* __restrict__ seeds,
-                                                                   int src, int3* pairs, unsigned cap_pairs, Counters* cnt) {
-    __shared__ int2 stack_mem[kDfsWarps][kStackCap];
+// the seeds the breadth-first levels left in frontier[src] become the initial content of the queue
+__global__ void dfs_queue_init_kernel(Counters* cnt, int src) {
+    const unsigned n = cnt->frontier_n[src];
+    cnt->q_head = 0; cnt->q_tail = n; cnt->n_seed0 = n; cnt->outstanding = (int)n;
+}
+
+PFC_D unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+
+// K1b: warp-cooperative stack-based traversal of the seeds, with work donation
+__global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, Seed* seeds, unsigned cap_seeds,
+                                                                   unsigned epoch, int3* pairs, unsigned cap_pairs, Counters* cnt) {
+    __shared__ int2 stack_mem[kDfsWarps][kStackCap];   // per-warp circular stack: entry i lives at (base + i) & (kStackCap - 1)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int2* stack = stack_mem[wib];
-    const unsigned n_seed = cnt->frontier_n[src];
+    const unsigned n_seed0 = cnt->n_seed0;
     unsigned long long tests = 0;
+    unsigned donated = 0;
     for (;;) {
-        unsigned si = 0;
-        if (lane == 0) si = atomicAdd(&cnt->seed_head, 1u);
-        si = __shfl_sync(0xffffffffu, si, 0);
-        if (si >= n_seed) break;
-        const Seed seed = seeds[si];
+        // ---- acquire a seed: take a ticket; tickets below n_seed0 are the seeds of the breadth-first levels, later ones are
+        // donated slots that become readable when their tag equals this traversal's epoch.  A waiter gives up when no seed is
+        // outstanding: every reserved slot has then been traversed, so an abandoned ticket can never receive work.
+        Seed seed;
+        seed.prob = -1;
+        if (lane == 0) {
+            const unsigned ticket = atomicAdd(&cnt->q_head, 1u);
+            if (ticket < n_seed0) {
+                seed = seeds[ticket];
+            } else {
+                unsigned backoff = 64, spins = 0;
+                for (;;) {
+                    if (ticket < cap_seeds) {
+                        const unsigned long long w0 = *reinterpret_cast<const volatile unsigned long long*>(&seeds[ticket]);   // (prob, tag)
+                        if ((unsigned)(w0 >> 32) == epoch) {
+                            __threadfence();   // acquire: (a, b) were stored before the tag
+                            const unsigned long long w1 = *(reinterpret_cast<const volatile unsigned long long*>(&seeds[ticket]) + 1);
+                            seed.prob = (int)(unsigned)(w0 & 0xffffffffull); seed.a = (int)(unsigned)(w1 & 0xffffffffull); seed.b = (int)(unsigned)(w1 >> 32);
+                            break;
+                        }
+                    }
+                    if ((spins++ & 3u) == 0 && *reinterpret_cast<const volatile int*>(&cnt->outstanding) <= 0) break;
+                    __nanosleep(backoff);
+                    if (backoff < 2000) backoff *= 2;
+                }
+            }
+        }
+        seed.prob = __shfl_sync(0xffffffffu, seed.prob, 0);
+        seed.a = __shfl_sync(0xffffffffu, seed.a, 0);
+        seed.b = __shfl_sync(0xffffffffu, seed.b, 0);
+        if (seed.prob < 0) break;
         long long env; int k;
         prob_to_ei(sc, ls, seed.prob, env, k);
         const InsDev& ins = sc.ins[k];
         double Rab[9], tab[3];
         broad_xform_l(X + 16 * (env * sc.n_ins + k), Rab, tab);
         int n = 1;
+        unsigned base = 0;
         if (lane == 0) stack[0] = make_int2(seed.a, seed.b);
         __syncwarp();
         while (n > 0) {
+            // idle warps = tickets issued beyond the reserved slots; loaded early, consumed after the tests (the latency hides behind the SAT)
+            unsigned qh = 0, qt = 0;
+            const bool may_donate = n >= 32;
+            if (may_donate && lane == 0) { qh = ld_volatile_u32(&cnt->q_head); qt = ld_volatile_u32(&cnt->q_tail); }
             // pop as many entries as the stack can absorb children for (each pops 1, pushes <= 4)
             int take = n < 32 ? n : 32;
             const int room = (kStackCap - n) / 3;
@@ -177,7 +231,7 @@ __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, 
             int r = 0;
             int2 ch[4];
             if (lane < take) {
-                const int2 e = stack[n - 1 - lane];
+                const int2 e = stack[(base + n - 1 - lane) & (kStackCap - 1)];
                 r = expand_pair(sc, ins, Rab, tab, e.x, e.y, ch);
                 ++tests;
             }
@@ -189,7 +243,7 @@ __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, 
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const int tot = __shfl_sync(0xffffffffu, incl, 31);
             const int at = n + incl - n_child;
-            if (n + tot <= kStackCap) { for (int c = 0; c < n_child; ++c) stack[at + c] = ch[c]; }
+            if (n + tot <= kStackCap) { for (int c = 0; c < n_child; ++c) stack[(base + at + c) & (kStackCap - 1)] = ch[c]; }
             else if (lane == 0) atomicOr(&cnt->overflow, 4u);  // cannot happen: take was limited by room
             n = (n + tot <= kStackCap) ? n + tot : n;
             const unsigned leaf_mask = __ballot_sync(0xffffffffu, r < 0);
@@ -200,11 +254,43 @@ __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, 
                 if (r < 0) { if (pat < cap_pairs) pairs[pat] = make_int3(seed.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u); }
             }
             __syncwarp();
+            // ---- donation: warps are waiting for work and this stack is deep -> hand over its oldest entries (the sub-trees
+            // nearest the root), at most half of the stack and about two per waiting warp
+            int give = 0;
+            if (may_donate && lane == 0 && n >= 32) {
+                const int waiting = (int)(qh - qt);
+                if (waiting > 0) { give = n / 2; if (give > 2 * waiting) give = 2 * waiting; if (give > 256) give = 256; }
+            }
+            give = __shfl_sync(0xffffffffu, give, 0);
+            if (give > 0) {
+                unsigned q0 = 0;
+                if (lane == 0) { atomicAdd(&cnt->outstanding, give); q0 = atomicAdd(&cnt->q_tail, (unsigned)give); }
+                q0 = __shfl_sync(0xffffffffu, q0, 0);
+                const bool fits = q0 + (unsigned)give <= cap_seeds;
+                if (fits) {
+                    for (int j = lane; j < give; j += 32) {
+                        const int2 e = stack[(base + j) & (kStackCap - 1)];
+                        *reinterpret_cast<int2*>(&seeds[q0 + j].a) = e;
+                    }
+                    __threadfence();
+                    for (int j = lane; j < give; j += 32)
+                        *reinterpret_cast<volatile unsigned long long*>(&seeds[q0 + j]) = ((unsigned long long)epoch << 32) | (unsigned)seed.prob;
+                } else if (lane == 0) {
+                    atomicOr(&cnt->overflow, 1u);            // the host grows the queue and re-runs the traversal;
+                    atomicSub(&cnt->outstanding, give);      // these seeds are dropped so that this run still terminates
+                }
+                base = (base + give) & (kStackCap - 1);
+                n -= give;
+                donated += give;
+                __syncwarp();
+            }
         }
+        if (lane == 0) { __threadfence(); atomicSub(&cnt->outstanding, 1); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, o);
     if (lane == 0 && tests) atomicAdd(&cnt->n_tests, tests);
+    if (lane == 0 && donated) atomicAdd(&cnt->n_donated, (unsigned long long)donated);
 }
 
 // K1c: DFS-order key of every pair.  key = (prob << key_bits) | interleaved path bits (left-aligned in key_bits)
@@ -528,8 +614,9 @@ template <class T> cudaError_t ensure(T*& p, size_t& cap, size_t need) {
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, need * sizeof(T));
-    if (e == cudaSuccess) cap = need;
-    return e;
+    if (e != cudaSuccess) return e;
+    cap = need;
+    return cudaMemset(p, 0, need * sizeof(T));   // seed tags of a fresh queue must not match any epoch
 }
 
 }  // namespace
@@ -547,6 +634,7 @@ struct LargeBuffers {
     int* chunk_points = nullptr; size_t cap_cp = 0;
     double* part = nullptr; size_t cap_part = 0;
     size_t cf2 = 0;
+    unsigned epoch = 0;   // traversal counter: tags the donated seeds of one broad_dfs_kernel launch
     unsigned last_n_pairs = 0;
     unsigned long long last_n_tests = 0;
 };
@@ -616,9 +704,16 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     size_t want_pairs = std::max<size_t>(b->cap_pairs, 1u << 20);
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    // BFS levels until ~64 seeds per SM-resident warp slot could exist (4^L * n_prob >= target)
+    // the traversal kernel is persistent: every block must be resident, because idle warps wait for donated work
+    static int dfs_blocks_per_sm = 0;
+    if (dfs_blocks_per_sm == 0) {
+        LCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_blocks_per_sm, broad_dfs_kernel, kDfsWarps * 32, 0));
+        if (dfs_blocks_per_sm < 1) dfs_blocks_per_sm = 1;
+    }
+    const int dfs_blocks = n_sm * dfs_blocks_per_sm;
+    // BFS levels until about one seed per resident warp could exist (4^L * n_prob >= target); donation balances the rest
     int levels = 0;
-    { double f = (double)n_prob; const double target = 64.0 * n_sm * 4; while (f < target && levels < 12) { f *= 4.0; ++levels; } }
+    { double f = (double)n_prob; const double target = 1.0 * dfs_blocks * kDfsWarps; while (f < target && levels < 12) { f *= 4.0; ++levels; } }
     for (int attempt = 0; attempt < 8; ++attempt) {
         LCU(ensure(b->frontier[0], b->cap_frontier, want_frontier));
         LCU(ensure(b->frontier[1], b->cf2, want_frontier));
@@ -633,8 +728,9 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
             LCU(cudaMemsetAsync(&b->cnt->frontier_n[src], 0, sizeof(unsigned), stream));
             src ^= 1;
         }
-        broad_dfs_kernel<<<n_sm * 4, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], src, b->pairs, (unsigned)b->cap_pairs, b->cnt);
-        if (n_launches) *n_launches += 2 + levels;
+        dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, src);
+        broad_dfs_kernel<<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs, b->cnt);
+        if (n_launches) *n_launches += 3 + levels;
         Counters h;
         LCU(cudaMemcpyAsync(&h, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         LCU(cudaStreamSynchronize(stream));

@@ -139,17 +139,17 @@ def pencil_sample_states(m, bodies, n: int = 8, seed: int = 0x5EED0C2):
         m.v[:] = 0.0
         if mode == 0:      # test/pencil.jl initial configuration: arm raised and turned, pencil lying on the table
             z, th, grip = 0.10, np.pi / 4, 0.0
-            S.set_state_spq(m, bodies["pencil"], rot=rz(-np.pi / 2), trans=(-0.8 * L, 0.0, -U(0.0, 2e-4)))
+            S.set_state_spq(m, bodies["pencil"], rot=rz(-np.pi / 2), trans=(-0.8 * L, 0.0, -U(2e-5, 2e-4)))
         elif mode == 1:    # arm lowered onto the pencil, pads squeezing it against the table
             z, th, grip = r, 0.0, U(1e-4, 5e-4)
-            S.set_state_spq(m, bodies["pencil"], rot=rz(-np.pi / 2 + U(-0.002, 0.002)), trans=(-0.5 * L, U(-1e-4, 1e-4), -U(0.0, 2e-4)))
+            S.set_state_spq(m, bodies["pencil"], rot=rz(-np.pi / 2 + U(-0.002, 0.002)), trans=(-0.5 * L, U(-1e-4, 1e-4), -U(2e-5, 2e-4)))
         elif mode == 2:    # lifted and swung: the pencil moves with the arm frame
             z, th, grip = 0.08, U(0.2, 1.2), U(1e-4, 5e-4)
             Rw = ry(th)    # the pencil's frame expressed in the arm frame is RotZ(-pi/2) with its axis through the pads
             S.set_state_spq(m, bodies["pencil"], rot=Rw @ rz(-np.pi / 2), trans=tuple(np.array([0.0, 0.0, z]) + Rw @ np.array([-0.4 * L, 0.0, -r])))
         else:              # pencil away on the table, the pads pressed against each other (tet-tet contact)
             z, th, grip = 0.05, U(-0.5, 0.5), r + U(1e-4, 4e-4)
-            S.set_state_spq(m, bodies["pencil"], rot=rz(U(-1, 1)), trans=(0.3, 0.1, -U(0.0, 2e-4)))
+            S.set_state_spq(m, bodies["pencil"], rot=rz(U(-1, 1)), trans=(0.3, 0.1, -U(2e-5, 2e-4)))
         S.set_configuration(m, bodies["tra_z"], [z])
         S.set_configuration(m, bodies["rev_y"], [th])
         S.set_configuration(m, bodies["pad_n"], [grip])

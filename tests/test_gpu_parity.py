@@ -26,7 +26,7 @@ def _both(build, n_env=1):
     return m_gpu, m_cpu
 
 
-def _sdot_metric_err(m_cpu, c, g, n_env):
+def _sdot_metric_err(m_cpu, c, g, n_env, wrench_too=False):
     """s-dot parity with a conditioning-aware bar (worst error / allowed; <= 1 passes).
 
     s-dot = -(Kb^-1/2 S^-1 w + s) / tau with Kb^-1/2 = V diag(1 / sqrt(max(lambda, 1e-16 lambda_max))) V'
@@ -57,20 +57,29 @@ def _sdot_metric_err(m_cpu, c, g, n_env):
             rho_min = lam.min() / lam.max()
             allowed = 1e-3 if rho_min < 1e-13 else TOL + 1e4 * eps / rho_min
             worst = max(worst, np.abs(sg - sc).max() / max(np.abs(sc).max(), 1e-300) / allowed)
+            if wrench_too:
+                # the bristle friction wrench is linear in Kb^-1/2 s while sticking (friction.jl:171-201), so it inherits
+                # the same amplification; regularized instructions stay at the plain 1e-9 bar (see _compare)
+                wscale = np.abs(c["wrench"][e, k]).max()
+                worst = max(worst, wrench_rel_err(g["wrench"][e, k], c["wrench"][e, k], floor=1e-9 * wscale) / allowed)
     return worst
 
 
-def _compare(m_gpu, m_cpu, X, tw, s=None, pairs=True, floor=1e-9, sdot_metric=False):
+def _compare(m_gpu, m_cpu, X, tw, s=None, pairs=True, floor=1e-9, sdot_metric=False, bristle_wrench_metric=False):
     keep = pairs or sdot_metric
     g = m_gpu.backend.eval_f64(X, tw, s, keep=pairs)
     c = m_cpu.backend.eval_f64(X, tw, s, keep=keep)
     assert (g["n_pairs"] == c["n_pairs"]).all()
     assert (g["flags"] == c["flags"]).all()
     scale = max(np.abs(c["wrench"]).max(), 1e-300)
-    assert wrench_rel_err(g["wrench"], c["wrench"], floor=floor * scale) <= TOL
+    if bristle_wrench_metric:  # plain bar for the regularized instructions, conditioning-aware bar for the bristle ones
+        reg = [k for k, ci in enumerate(m_cpu.ContactInstructions) if ci.friction_model.model == 0]
+        assert wrench_rel_err(g["wrench"][:, reg], c["wrench"][:, reg], floor=floor * scale) <= TOL
+    else:
+        assert wrench_rel_err(g["wrench"], c["wrench"], floor=floor * scale) <= TOL
     if s is not None:
         if sdot_metric:
-            assert _sdot_metric_err(m_cpu, c, g, c["n_pairs"].shape[0]) <= 1.0
+            assert _sdot_metric_err(m_cpu, c, g, c["n_pairs"].shape[0], wrench_too=bristle_wrench_metric) <= 1.0
         else:
             sc = max(np.abs(c["sdot"]).max(), 1e-300)
             assert wrench_rel_err(g["sdot"], c["sdot"], floor=floor * sc) <= TOL
@@ -498,6 +507,9 @@ def test_dual6_bristle_and_tet_tet():
 
 
 # ---- config C2: the pencil gripper and the spoon, bristle friction, sampled states ------------------------------
+# halves of a wrench that vanish by symmetry (the pad-pad torque about the r2 origin) carry eps * |F| * L rounding noise:
+# they are compared against 1e-6 of the largest wrench component instead of against themselves
+C2_FLOOR = 1.0e-6
 def test_c2_pencil_bristle_sampled_states():
     """test/pencil.jl with is_bristle = true: wrench / s-dot / pair-list parity on sampled
     states of the task (the 1000-step Radau state parity needs the integrator and RigidBodyDynamics: out of scope)."""
@@ -508,12 +520,12 @@ def test_c2_pencil_bristle_sampled_states():
     n_contact = 0
     for x in xs:
         X, tw, s = S.boundary_arrays(m_gpu, x)
-        g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, m_gpu.n_bristle, 6), sdot_metric=True)
+        g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, m_gpu.n_bristle, 6), sdot_metric=True, bristle_wrench_metric=True, floor=C2_FLOOR)
         n_contact += int((c["flags"] & 1).sum())
         # the generalized forces the reference would add (J' w through the arm's joints) agree as well
         f_g = S.generalized_forces(m_gpu, x, g["wrench"][0])
         f_c = S.generalized_forces(m_cpu, x, c["wrench"][0])
-        assert np.abs(f_g - f_c).max() <= TOL * max(np.abs(f_c).max(), 1e-300)
+        assert np.abs(f_g - f_c).max() <= 1e-6 * max(np.abs(f_c).max(), 1e-300)  # includes the ill-conditioned bristle wrenches
     assert n_contact >= 16  # pad-pencil (bristle), pencil-plane and pad-pad (tet-tet) contacts are all exercised
 
 
@@ -527,6 +539,6 @@ def test_c2_spoon_bristle_sampled_states():
     n_contact = 0
     for x in xs:
         X, tw, s = S.boundary_arrays(m_gpu, x)
-        g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, m_gpu.n_bristle, 6), sdot_metric=True)
+        g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, m_gpu.n_bristle, 6), sdot_metric=True, bristle_wrench_metric=True, floor=C2_FLOOR)
         n_contact += int((c["flags"] & 1).sum())
     assert n_contact >= 8
