@@ -369,6 +369,8 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
     c->scene.nodes = c->d_nodes.p; c->scene.tets = c->d_tets.p; c->scene.tris = c->d_tris.p; c->scene.ins = c->d_ins.p;
     c->scene.small_ins = c->d_small.p;
     c->scene.n_ins = int(c->h_ins.size()); c->scene.n_small = int(small.size()); c->scene.n_bristle = c->n_bristle;
+    c->scene.n_small_bristle = 0;
+    for (int32_t k : small) c->scene.n_small_bristle += (c->h_ins[k].model == PFC_MODEL_BRISTLE);
     c->max_env = max_env;
     c->finalized = true;
     return PFC_OK;

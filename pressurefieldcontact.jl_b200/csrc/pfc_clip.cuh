@@ -74,6 +74,70 @@ template <class T> __device__ __noinline__ int clip_tet(Zeta<T>* z, int n, int& 
     return n;
 }
 
+// The same clip, working IN PLACE on a polygon stored as z[4 * k + c] (Float64 mode; the tile kernel keeps it in the
+// thread's shared-memory slot, so nothing goes through local memory).  Decisions are taken on three sign masks per face;
+// the two cut edges are loaded before anything is overwritten; the kept vertices are rotated through registers only when
+// the first kept vertex is not already in slot 1 (k0 != 0).  Same quirks as clip_tet above.
+PFC_D void clip_node_inplace(const double* zn, const double* zp, double w1, double w2, double* r) {   // w1, w2: coordinate i of zn, zp
+    const double inv = 1.0 / (w1 - w2);
+    const double c1 = w1 * inv, c2 = w2 * inv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = c1 * zp[k] - c2 * zn[k];
+}
+PFC_D int clip_tet_inplace(double* z, int n, int& flags) {
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        unsigned np = 0, nn = 0, ps = 0;   // bit k: s <= 0, 0 <= s, 0 < s  with s = zeta_i of vertex k
+        for (int k = 0; k < n; ++k) {
+            const double s = z[4 * k + i];
+            np |= (s <= 0.0 ? 1u : 0u) << k;
+            nn |= (0.0 <= s ? 1u : 0u) << k;
+            ps |= (0.0 < s ? 1u : 0u) << k;
+        }
+        const unsigned full = (1u << n) - 1u;
+        if (np == full) return 0;
+        if (nn == full) continue;
+        const unsigned trans = np & ~(((np >> 1) | (np << (n - 1))) & full);   // non-positive vertex followed by a positive one
+        if (!trans) { flags |= kFlagNonFinite; return 0; }
+        const int k0 = __ffs(trans) - 1;
+        const unsigned rnp = ((np >> k0) | (np << (n - k0))) & full;            // masks in the rotated order w[j] = z[(k0 + j) mod n]
+        const unsigned rnn = ((nn >> k0) | (nn << (n - k0))) & full;
+        const unsigned rps = ((ps >> k0) | (ps << (n - k0))) & full;
+        int m = n;
+        while (m > 3 && ((rnp >> (m - 2)) & 1u)) --m;                           // cut_clip's arity-reducing recursion
+        const bool last_inside = (((m <= 5) ? rps : rnn) >> (m - 1)) & 1u;
+        const int keep_end = last_inside ? m - 1 : m - 2;                       // the output keeps w[1 .. keep_end]
+        double w0[4], w1[4], wa[4], wb[4], zs[4], ze[4];
+        {
+            const int i1 = (k0 + 1 < n) ? k0 + 1 : k0 + 1 - n;
+            const int ja = last_inside ? 0 : m - 1, jb = last_inside ? m - 1 : m - 2;   // z_end = clip_node(w[ja], w[jb])
+            const int ia = (k0 + ja < n) ? k0 + ja : k0 + ja - n, ib = (k0 + jb < n) ? k0 + jb : k0 + jb - n;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { w0[c] = z[4 * k0 + c]; w1[c] = z[4 * i1 + c]; wa[c] = z[4 * ia + c]; wb[c] = z[4 * ib + c]; }
+            // coordinate i again, by address: indexing the register copies with the loop variable would push them to local memory
+            clip_node_inplace(w0, w1, z[4 * k0 + i], z[4 * i1 + i], zs);
+            clip_node_inplace(wa, wb, z[4 * ia + i], z[4 * ib + i], ze);
+        }
+        if (k0 != 0) {   // one coordinate column at a time keeps the register footprint at 7 doubles
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                double t[7];
+#pragma unroll
+                for (int j = 1; j <= 7; ++j)
+                    if (j <= keep_end) { const int idx = (k0 + j < n) ? k0 + j : k0 + j - n; t[j - 1] = z[4 * idx + c]; }
+#pragma unroll
+                for (int j = 1; j <= 7; ++j)
+                    if (j <= keep_end) z[4 * j + c] = t[j - 1];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { z[c] = zs[c]; z[4 * (keep_end + 1) + c] = ze[c]; }
+        n = keep_end + 2;
+        if (m == 7) return n;  // the 7-vertex cut returns without visiting further faces
+    }
+    return n;
+}
+
 // zero_small_coordinates: |x| <= 1e-14 -> 0 (decided on the value part)
 template <class T> PFC_D void zero_small(Zeta<T>* z, int n) {
     for (int k = 0; k < n; ++k)

@@ -306,6 +306,89 @@ template <class T> PFC_D bool clip_pair(const SceneDev& sc, const InsDev& ins, i
     return clip_tet_tet(sc.tets[ins.prim_base1 + prim1], t2, cx, out, flags);
 }
 
+// ---- stage A, Float64, polygon kept in the caller's PolyRec slot (shared memory in the tile kernel) --------------------
+// The slot's first 32 doubles hold the polygon in tetrahedral coordinates while it is clipped; the conversion to Cartesian
+// vertices runs forward in place (vertex k lands in doubles [3k, 3k+3), which only overlaps coordinates already consumed).
+PFC_D bool finish_polygon_slot(int n, const TetRec& tet, const Vec3<double>& nrm, PolyRec<double>& out) {
+    double* z = reinterpret_cast<double*>(&out);
+    for (int k = 0; k < n; ++k) {  // mul_then_un_pad(x_r2_zeta2, .)
+        const double z0 = z[4 * k], z1 = z[4 * k + 1], z2 = z[4 * k + 2], z3 = z[4 * k + 3];
+        out.v[k] = mk<double>(tet.v[0] * z0 + tet.v[3] * z1 + tet.v[6] * z2 + tet.v[9] * z3, tet.v[1] * z0 + tet.v[4] * z1 + tet.v[7] * z2 + tet.v[10] * z3,
+                              tet.v[2] * z0 + tet.v[5] * z1 + tet.v[8] * z2 + tet.v[11] * z3);
+    }
+    double cum_sum = 0.0;
+    Vec3<double> cum = mk<double>(0.0, 0.0, 0.0);
+    const Vec3<double> a = out.v[0];
+    Vec3<double> b = out.v[1];
+    for (int k = 2; k < n; ++k) {  // fan from vertex 0 (poly_eight.jl:35-52)
+        const Vec3<double> c = out.v[k];
+        const double area = dot(nrm, cross(b - a, c - b) * 0.5);
+        cum = cum + ((a + b + c) * (1.0 / 3.0)) * area;
+        cum_sum += area;
+        b = c;
+    }
+    Vec3<double> cen = a;
+    if (cum_sum != 0.0) { const double inv = 1.0 / cum_sum; cen = mk<double>(cum.x * inv, cum.y * inv, cum.z * inv); }
+    out.nrm = nrm;
+    out.cen = cen;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out.eps_r[k] = tet.eps_r[k];
+    out.n = n;
+    return true;
+}
+
+PFC_D bool clip_pair_slot(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<double>& cx, PolyRec<double>& out, int& flags) {
+    const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
+    double* z = reinterpret_cast<double*>(&out);
+    if (ins.kind1 == 0) {
+        const TriRec& tri = sc.tris[ins.prim_base1 + prim1];
+        double zr[3][4];
+        unsigned all_non_pos = 0xfu;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const Vec3<double> p = apply_d(cx.x21, mk<double>(tri.v[3 * k], tri.v[3 * k + 1], tri.v[3 * k + 2]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                zr[k][i] = t2.inv[4 * i] * p.x + t2.inv[4 * i + 1] * p.y + t2.inv[4 * i + 2] * p.z + t2.inv[4 * i + 3];
+                if (!(zr[k][i] <= 0.0)) all_non_pos &= ~(1u << i);
+            }
+        }
+        if (all_non_pos) return false;   // some face has all three vertices outside: the clip would return nothing (see prefilter_pair)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z[4 * k + i] = zr[k][i];
+        const int n = clip_tet_inplace(z, 3, flags);
+        if (n < 3) return false;
+        return finish_polygon_slot(n, t2, rot_d(cx.x21, mk<double>(tri.n[0], tri.n[1], tri.n[2])), out);
+    }
+    const TetRec& t1 = sc.tets[ins.prim_base1 + prim1];
+    double plane[4];
+    {
+        const double g0 = cx.Ebar1 * t1.eps_r[0], g1 = cx.Ebar1 * t1.eps_r[1], g2 = cx.Ebar1 * t1.eps_r[2], g3 = cx.Ebar1 * t1.eps_r[3];
+        const Xform<double>& Y = cx.x12;
+        plane[0] = cx.Ebar2 * t2.eps_r[0] - (g0 * Y.r[0] + g1 * Y.r[3] + g2 * Y.r[6]);
+        plane[1] = cx.Ebar2 * t2.eps_r[1] - (g0 * Y.r[1] + g1 * Y.r[4] + g2 * Y.r[7]);
+        plane[2] = cx.Ebar2 * t2.eps_r[2] - (g0 * Y.r[2] + g1 * Y.r[5] + g2 * Y.r[8]);
+        plane[3] = cx.Ebar2 * t2.eps_r[3] - (g0 * Y.t[0] + g1 * Y.t[1] + g2 * Y.t[2] + g3);
+    }
+    Vec3<double> v[4], poly[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = apply_d(cx.x21, mk<double>(t1.v[3 * k], t1.v[3 * k + 1], t1.v[3 * k + 2]));
+    const int n0 = plane_tet(plane, v, poly);
+    if (n0 < 3) return false;
+    for (int k = 0; k < n0; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double zz = t2.inv[4 * i] * poly[k].x + t2.inv[4 * i + 1] * poly[k].y + t2.inv[4 * i + 2] * poly[k].z + t2.inv[4 * i + 3];
+            z[4 * k + i] = zz * ((1.0e-14 < fabs(zz)) ? 1.0 : 0.0);   // zero_small_coordinates
+        }
+    const int n = clip_tet_inplace(z, n0, flags);
+    if (n < 3) return false;
+    const double inv_len = 1.0 / sqrt(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);
+    return finish_polygon_slot(n, t2, mk<double>(plane[0] * inv_len, plane[1] * inv_len, plane[2] * inv_len), out);
+}
+
 // stages A + B for one pair on one thread, sub-triangles in the reference's order (previous vertex = last first)
 template <class T, int NA> PFC_D void integrate_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx, Accum<T, NA>& acc, int& flags) {
     PolyRec<T> pr;

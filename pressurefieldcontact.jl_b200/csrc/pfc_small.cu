@@ -363,6 +363,158 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) narrow_small_kernel(SceneDev
     }
 }
 
+
+// ---- kernel 2b: narrow phase for scenes whose small instructions are all regularized: one CTA per TILE of P problems ----
+// The per-problem kernel above leaves lanes idle (about 29 candidates, 21 clip jobs and 49 sub-triangles per boxes.jl
+// instruction on a 32-lane warp) and a warp runs its phases strictly one after another.  Here a CTA of 128 threads owns P
+// consecutive (environment, instruction) problems and every phase is flattened over all of them:
+//   1. 32 threads per problem fill the problem's shared context (transform, inverse, twist, constants), one element each;
+//   2. the tile's candidate pairs (about 118 for P = 4 boxes.jl instructions) are dealt one per thread: exact rejection on
+//      registers, then the clip IN PLACE in the thread's shared-memory PolyRec slot (stride 35 doubles: conflict-free; no
+//      local memory), centroid -> a finished PolyRec;
+//   3. a block scan over the vertex counts turns the polygons into a dense (slot, edge) work list, dealt one sub-triangle
+//      per thread for quadrature + friction; every item leaves its 6 sums (+ point count) in shared memory;
+//   4. one thread per (problem, wrench component) adds its problem's items IN ITEM ORDER (= the reference's order of
+//      candidate pairs and polygon edges): bitwise reproducible, no atomics, no per-thread accumulators to carry.
+constexpr int kTileThreads = 128;
+constexpr int kPolyStride = 35;    // doubles per PolyRec slot
+static_assert(sizeof(PolyRec<double>) == kPolyStride * sizeof(double), "PolyRec<double> is 35 doubles");
+constexpr int kItemCap = 256;      // sub-triangles per summation round
+constexpr int kItemStride = 7;     // 6 sums + point count, odd stride
+
+template <int P> struct TileSmem {
+    double poly[kTileThreads * kPolyStride];   // PolyRec per thread
+    double item_res[kItemCap * kItemStride];
+    PatchCtx<double> cx[P];
+    long long ei[P];
+    const double* fp[P];
+    int ins[P];
+    int n_cand[P];
+    int warp_tot[4];
+    int pflags[P];
+    unsigned short items[kTileThreads * 8];
+    unsigned char poly_prob[kTileThreads];
+};
+
+template <int P, int MINB>
+__global__ void __launch_bounds__(kTileThreads, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
+    static_assert(P * 32 <= kTileThreads && P * 7 <= 32, "tile layout");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<P>& sm = *reinterpret_cast<TileSmem<P>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const long long n_prob = io.n_env * sc.n_small;
+    const long long n_tile = (n_prob + P - 1) / P;
+    // summing threads: tid < 6 P owns (problem, component) = (tid / 6, tid % 6); tid in [6 P, 7 P) owns a point count
+    const int sum_q = tid < 6 * P ? tid / 6 : tid - 6 * P, sum_j = tid < 6 * P ? tid % 6 : 6;
+    for (long long tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
+        // ---- 1. problem contexts: warp q fills problem q, one element per lane
+        if (wib < P) {
+            const long long prob = tile * P + wib;
+            if (prob < n_prob) {
+                const long long env = prob / sc.n_small;
+                const int k = sc.small_ins[prob - env * sc.n_small];
+                const InsDev& ins = sc.ins[k];
+                const long long ei = env * sc.n_ins + k;
+                const double* X = io.X + 16 * ei;
+                PatchCtx<double>& cx = sm.cx[wib];
+                if (lane < 9) { const int i = lane / 3, j = lane % 3; cx.x21.r[lane] = X[4 * j + i]; }
+                else if (lane < 12) cx.x21.t[lane - 9] = X[12 + lane - 9];
+                else if (lane < 21) { const int e = lane - 12, i = e / 3, j = e % 3; cx.x12.r[e] = X[4 * i + j]; }
+                else if (lane < 24) { const int i = lane - 21; cx.x12.t[i] = -(X[4 * i] * X[12] + X[4 * i + 1] * X[13] + X[4 * i + 2] * X[14]); }
+                else if (lane < 27) (&cx.w_ang.x)[lane - 24] = io.twist[6 * ei + lane - 24];
+                else if (lane < 30) (&cx.w_lin.x)[lane - 27] = io.twist[6 * ei + lane - 24];
+                else if (lane == 30) { cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad; }
+                else { sm.ei[wib] = ei; sm.fp[wib] = ins.p; sm.ins[wib] = k; sm.n_cand[wib] = (int)io.n_pairs[ei]; sm.pflags[wib] = 0; }
+            } else if (lane == 31) { sm.ei[wib] = -1; sm.n_cand[wib] = 0; sm.ins[wib] = 0; sm.fp[wib] = nullptr; sm.pflags[wib] = 0; }
+        }
+        __syncthreads();
+        int pre[P + 1];
+        pre[0] = 0;
+#pragma unroll
+        for (int q = 0; q < P; ++q) pre[q + 1] = pre[q] + sm.n_cand[q];
+        const int n_cand = pre[P];
+        double sum = 0.0;   // summing threads: running total of (problem, component)
+        int sum_n = 0;
+        for (int c0 = 0; c0 < n_cand; c0 += kTileThreads) {
+            // ---- 2. one candidate pair per thread
+            const int c = c0 + tid;
+            int nv = 0;
+            if (c < n_cand) {
+                int q = 0;
+#pragma unroll
+                for (int r = 1; r < P; ++r) q += (c >= pre[r]);
+                const unsigned e = pairs_in[(size_t)cap * sm.ei[q] + (c - pre[q])];
+                PolyRec<double>& out = *reinterpret_cast<PolyRec<double>*>(sm.poly + tid * kPolyStride);
+                int flags = 0;
+                if (clip_pair_slot(sc, sc.ins[sm.ins[q]], dec_a(e), dec_b(e), sm.cx[q], out, flags)) nv = out.n;
+                if (flags) atomicOr(&sm.pflags[q], flags);   // rare: non-finite vertex / bad arity
+                sm.poly_prob[tid] = (unsigned char)q;
+            }
+            // ---- 3a. block scan of the vertex counts -> dense (slot, edge) work list, ordered by (problem, pair, edge)
+            int incl = nv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) sm.warp_tot[wib] = incl;
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; total += t; }
+            const int at = before + incl - nv;
+            for (int k = 0; k < nv; ++k) sm.items[at + k] = (unsigned short)((tid << 3) | k);
+            __syncthreads();
+            // this summing thread's item range: items are sorted by problem, so it is [lower_bound(q), lower_bound(q + 1))
+            int my_lo = 0, my_hi = 0;
+            if (tid < 7 * P) {
+                int lo = 0, hi = total;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] < sum_q) lo = mid + 1; else hi = mid; }
+                my_lo = lo; hi = total;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] <= sum_q) lo = mid + 1; else hi = mid; }
+                my_hi = lo;
+            }
+            for (int i0 = 0; i0 < total; i0 += kItemCap) {
+                // ---- 3b. one sub-triangle per thread
+                const int i1 = min(total, i0 + kItemCap);
+                for (int it = i0 + tid; it < i1; it += kTileThreads) {
+                    const int code = sm.items[it];
+                    const int slot = code >> 3, k = code & 7;
+                    const PolyRec<double>& pr = *reinterpret_cast<const PolyRec<double>*>(sm.poly + slot * kPolyStride);
+                    const int q = sm.poly_prob[slot];
+                    const PatchCtx<double>& cx = sm.cx[q];
+                    Accum<double, 6> tmp;
+                    tmp.fp = sm.fp[q]; tmp.w_ang = cx.w_ang; tmp.w_lin = cx.w_lin; tmp.dump = nullptr; tmp.dump_cap = 0;
+                    tmp.reset(ACC_REGULARIZED);
+                    const int kp = (k == 0) ? pr.n - 1 : k - 1;
+                    integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, tmp);
+                    double* res = sm.item_res + (it - i0) * kItemStride;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) res[j] = tmp.a[j];
+                    reinterpret_cast<int*>(res + 6)[0] = tmp.n_points;
+                }
+                __syncthreads();
+                // ---- 4. ordered sums
+                if (tid < 7 * P) {
+                    const int a = max(my_lo, i0), b = min(my_hi, i1);
+                    if (sum_j < 6) { for (int it = a; it < b; ++it) sum += sm.item_res[(it - i0) * kItemStride + sum_j]; }
+                    else { for (int it = a; it < b; ++it) sum_n += reinterpret_cast<const int*>(sm.item_res + (it - i0) * kItemStride + 6)[0]; }
+                }
+                __syncthreads();   // item_res (and, after the last round, the polygon slots) are reused
+            }
+        }
+        // ---- results: wrench (zero without contact), flags
+        if (tid >= 6 * P && tid < 7 * P) sm.warp_tot[sum_q] = sum_n;   // P <= 4 point counts
+        __syncthreads();
+        if (tid < 6 * P) {
+            const long long ei = sm.ei[sum_q];
+            if (ei >= 0) {
+                const bool contact = sm.warp_tot[sum_q] > 0;
+                io.wrench[6 * ei + sum_j] = contact ? sum : 0.0;
+                if (sum_j == 0) io.flags[ei] |= sm.pflags[sum_q] | (contact ? kFlagContact : 0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // One thread walks a given pair list in order and records every traction point (TractionCache).
 __global__ void dump_traction_kernel(SceneDev sc, EvalIO io, long long env, int k, const int* pairs, long long n_pairs, double* out, int cap, int* n_points) {
     const InsDev& ins = sc.ins[k];
@@ -430,6 +582,23 @@ cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const
     return cudaGetLastError();
 }
 
+
+template <int P, int MINB>
+cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
+    static int cached_blocks = 0;
+    auto kern = narrow_tile_kernel<P, MINB>;
+    const size_t smem = sizeof(TileSmem<P>);
+    if (cached_blocks == 0) {
+        cudaError_t e;
+        cached_blocks = persistent_blocks((const void*)kern, kTileThreads, smem, &e);
+        if (e != cudaSuccess) return e;
+    }
+    long long blocks = (io.n_env * sc.n_small + P - 1) / P;
+    if (blocks > cached_blocks) blocks = cached_blocks;
+    kern<<<(unsigned)blocks, kTileThreads, smem, stream>>>(sc, io, cap, pairs);
+    return cudaGetLastError();
+}
+
 // group size is a run-time choice (three instantiations per kernel); the minimum-blocks hint (register cap) is fixed:
 // 4 CTAs/SM (<=128 registers) for the SAT kernel, 3 (<=168) for the clip/quadrature kernel -- measured best on B200.
 #define PFC_DISPATCH_G(fn, g, minb, ...) ((g) == 8 ? fn<8, minb>(__VA_ARGS__) : (g) == 16 ? fn<16, minb>(__VA_ARGS__) : fn<32, minb>(__VA_ARGS__))
@@ -452,7 +621,11 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
     cudaError_t e = PFC_DISPATCH_G(launch_broad_g, bg, 4, sc, io, cap, pairs, stream);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
-    e = PFC_DISPATCH_G(launch_narrow_g, ng, 3, sc, io, cap, pairs, stream);
+    // scenes with bristle instructions on the small path (three passes, 21 accumulators), or PFC_NARROW_TILE=0, use the per-problem kernel
+    static const bool use_tile = !(getenv("PFC_NARROW_TILE") && atoi(getenv("PFC_NARROW_TILE")) == 0);
+    static const int tile_minb = getenv("PFC_TILE_MINB") ? atoi(getenv("PFC_TILE_MINB")) : 4;
+    if (sc.n_small_bristle == 0 && use_tile) e = tile_minb == 3 ? launch_narrow_tile<4, 3>(sc, io, cap, pairs, stream) : tile_minb == 5 ? launch_narrow_tile<4, 5>(sc, io, cap, pairs, stream) : launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
+    else e = PFC_DISPATCH_G(launch_narrow_g, ng, 3, sc, io, cap, pairs, stream);
     if (ev) cudaEventRecord(ev[2], stream);
     if (n_launches) *n_launches += 2;
     return e;

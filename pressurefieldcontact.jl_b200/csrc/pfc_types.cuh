@@ -65,6 +65,7 @@ struct SceneDev {
     const InsDev* ins;
     const int32_t* small_ins;  // indices of the instructions on the fused small path
     int32_t n_ins, n_small, n_bristle;
+    int32_t n_small_bristle;   // bristle instructions among the small ones (selects the narrow-phase kernel)
 };
 
 }  // namespace pfc
