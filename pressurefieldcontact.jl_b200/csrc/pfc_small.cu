@@ -376,39 +376,39 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) narrow_small_kernel(SceneDev
 //      per thread for quadrature + friction; every item leaves its 6 sums (+ point count) in shared memory;
 //   4. one thread per (problem, wrench component) adds its problem's items IN ITEM ORDER (= the reference's order of
 //      candidate pairs and polygon edges): bitwise reproducible, no atomics, no per-thread accumulators to carry.
-constexpr int kTileThreads = 128;
 constexpr int kPolyStride = 35;    // doubles per PolyRec slot
 static_assert(sizeof(PolyRec<double>) == kPolyStride * sizeof(double), "PolyRec<double> is 35 doubles");
 constexpr int kItemCap = 256;      // sub-triangles per summation round
 constexpr int kItemStride = 7;     // 6 sums + point count, odd stride
 
-template <int P> struct TileSmem {
-    double poly[kTileThreads * kPolyStride];   // PolyRec per thread
+template <int P> struct TileSmem {   // P problems, P warps
+    static constexpr int kThreads = 32 * P;
+    double poly[kThreads * kPolyStride];   // PolyRec per thread
     double item_res[kItemCap * kItemStride];
     PatchCtx<double> cx[P];
     long long ei[P];
     const double* fp[P];
     int ins[P];
     int n_cand[P];
-    int warp_tot[4];
+    double tot[P][8];
+    int warp_tot[P];
     int pflags[P];
-    unsigned short items[kTileThreads * 8];
-    unsigned char poly_prob[kTileThreads];
+    unsigned short items[kThreads * 8];
+    unsigned char poly_prob[kThreads];
 };
 
 template <int P, int MINB>
-__global__ void __launch_bounds__(kTileThreads, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
-    static_assert(P * 32 <= kTileThreads && P * 7 <= 32, "tile layout");
+__global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
+    constexpr int kTileThreads = 32 * P;   // one warp per problem for the context and the sums
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<P>& sm = *reinterpret_cast<TileSmem<P>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const long long n_prob = io.n_env * sc.n_small;
     const long long n_tile = (n_prob + P - 1) / P;
-    // summing threads: tid < 6 P owns (problem, component) = (tid / 6, tid % 6); tid in [6 P, 7 P) owns a point count
-    const int sum_q = tid < 6 * P ? tid / 6 : tid - 6 * P, sum_j = tid < 6 * P ? tid % 6 : 6;
+    const int sum_q = wib;   // phase 4: warp q sums problem q
     for (long long tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
         // ---- 1. problem contexts: warp q fills problem q, one element per lane
-        if (wib < P) {
+        {
             const long long prob = tile * P + wib;
             if (prob < n_prob) {
                 const long long env = prob / sc.n_small;
@@ -433,8 +433,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) narrow_tile_kernel(SceneDe
 #pragma unroll
         for (int q = 0; q < P; ++q) pre[q + 1] = pre[q] + sm.n_cand[q];
         const int n_cand = pre[P];
-        double sum = 0.0;   // summing threads: running total of (problem, component)
-        int sum_n = 0;
+        if (lane < 8) sm.tot[wib][lane] = 0.0;   // running totals of problem wib: 6 sums + point count (warp-private)
         for (int c0 = 0; c0 < n_cand; c0 += kTileThreads) {
             // ---- 2. one candidate pair per thread
             const int c = c0 + tid;
@@ -458,13 +457,13 @@ __global__ void __launch_bounds__(kTileThreads, MINB) narrow_tile_kernel(SceneDe
             __syncthreads();
             int before = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; total += t; }
+            for (int w = 0; w < P; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; total += t; }
             const int at = before + incl - nv;
             for (int k = 0; k < nv; ++k) sm.items[at + k] = (unsigned short)((tid << 3) | k);
             __syncthreads();
             // this summing thread's item range: items are sorted by problem, so it is [lower_bound(q), lower_bound(q + 1))
             int my_lo = 0, my_hi = 0;
-            if (tid < 7 * P) {
+            {
                 int lo = 0, hi = total;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] < sum_q) lo = mid + 1; else hi = mid; }
                 my_lo = lo; hi = total;
@@ -491,24 +490,35 @@ __global__ void __launch_bounds__(kTileThreads, MINB) narrow_tile_kernel(SceneDe
                     reinterpret_cast<int*>(res + 6)[0] = tmp.n_points;
                 }
                 __syncthreads();
-                // ---- 4. ordered sums
-                if (tid < 7 * P) {
+                // ---- 4. fixed-order sums: lane l adds items a + l, a + l + 32, ... of its warp's problem, then a xor-butterfly
+                {
                     const int a = max(my_lo, i0), b = min(my_hi, i1);
-                    if (sum_j < 6) { for (int it = a; it < b; ++it) sum += sm.item_res[(it - i0) * kItemStride + sum_j]; }
-                    else { for (int it = a; it < b; ++it) sum_n += reinterpret_cast<const int*>(sm.item_res + (it - i0) * kItemStride + 6)[0]; }
+                    if (a < b) {   // warp-uniform
+                        double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                        int part_n = 0;
+                        for (int it = a + lane; it < b; it += 32) {
+                            const double* res = sm.item_res + (it - i0) * kItemStride;
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) part[j] += res[j];
+                            part_n += reinterpret_cast<const int*>(res + 6)[0];
+                        }
+                        double mine = (double)warp_sum_int(part_n);   // lane 6 keeps the point count
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) { const double t = warp_sum(part[j]); mine = (lane == j) ? t : mine; }
+                        if (lane < 7) sm.tot[sum_q][lane] += mine;
+                    }
                 }
                 __syncthreads();   // item_res (and, after the last round, the polygon slots) are reused
             }
         }
         // ---- results: wrench (zero without contact), flags
-        if (tid >= 6 * P && tid < 7 * P) sm.warp_tot[sum_q] = sum_n;   // P <= 4 point counts
-        __syncthreads();
-        if (tid < 6 * P) {
+        {
             const long long ei = sm.ei[sum_q];
             if (ei >= 0) {
-                const bool contact = sm.warp_tot[sum_q] > 0;
-                io.wrench[6 * ei + sum_j] = contact ? sum : 0.0;
-                if (sum_j == 0) io.flags[ei] |= sm.pflags[sum_q] | (contact ? kFlagContact : 0);
+                __syncwarp();
+                const bool contact = sm.tot[sum_q][6] > 0.0;
+                if (lane < 6) io.wrench[6 * ei + lane] = contact ? sm.tot[sum_q][lane] : 0.0;
+                if (lane == 6) io.flags[ei] |= sm.pflags[sum_q] | (contact ? kFlagContact : 0);
             }
         }
         __syncthreads();
@@ -590,12 +600,12 @@ cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, co
     const size_t smem = sizeof(TileSmem<P>);
     if (cached_blocks == 0) {
         cudaError_t e;
-        cached_blocks = persistent_blocks((const void*)kern, kTileThreads, smem, &e);
+        cached_blocks = persistent_blocks((const void*)kern, 32 * P, smem, &e);
         if (e != cudaSuccess) return e;
     }
     long long blocks = (io.n_env * sc.n_small + P - 1) / P;
     if (blocks > cached_blocks) blocks = cached_blocks;
-    kern<<<(unsigned)blocks, kTileThreads, smem, stream>>>(sc, io, cap, pairs);
+    kern<<<(unsigned)blocks, 32 * P, smem, stream>>>(sc, io, cap, pairs);
     return cudaGetLastError();
 }
 
@@ -624,7 +634,12 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
     // scenes with bristle instructions on the small path (three passes, 21 accumulators), or PFC_NARROW_TILE=0, use the per-problem kernel
     static const bool use_tile = !(getenv("PFC_NARROW_TILE") && atoi(getenv("PFC_NARROW_TILE")) == 0);
     static const int tile_minb = getenv("PFC_TILE_MINB") ? atoi(getenv("PFC_TILE_MINB")) : 4;
-    if (sc.n_small_bristle == 0 && use_tile) e = tile_minb == 3 ? launch_narrow_tile<4, 3>(sc, io, cap, pairs, stream) : tile_minb == 5 ? launch_narrow_tile<4, 5>(sc, io, cap, pairs, stream) : launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
+    static const int tile_p = getenv("PFC_TILE_P") ? atoi(getenv("PFC_TILE_P")) : 4;
+    if (sc.n_small_bristle == 0 && use_tile) {
+        if (tile_p == 2) e = tile_minb == 6 ? launch_narrow_tile<2, 6>(sc, io, cap, pairs, stream) : launch_narrow_tile<2, 8>(sc, io, cap, pairs, stream);
+        else if (tile_p == 8) e = launch_narrow_tile<8, 2>(sc, io, cap, pairs, stream);
+        else e = tile_minb == 3 ? launch_narrow_tile<4, 3>(sc, io, cap, pairs, stream) : launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
+    }
     else e = PFC_DISPATCH_G(launch_narrow_g, ng, 3, sc, io, cap, pairs, stream);
     if (ev) cudaEventRecord(ev[2], stream);
     if (n_launches) *n_launches += 2;
