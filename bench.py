@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# DRAM traffic of one narrow_tile_kernel launch on the 4096-environment workload, from the committed ncu capture
+NARROW_TRAFFIC_BYTES = 7568384 + 80384
+
 METRIC = "contact_wrench_evals_per_sec"
 UNIT = "evals/s"
 
@@ -291,8 +294,9 @@ def main():
                 "api": "pfc_eval_f64 (host pointers, pinned)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": narrow_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": narrow_tflops / fp64_peak if fp64_peak else None, "traffic": None,
-                     "kernel": "narrow_small_kernel (clip + quadrature + friction + fixed-order reduction), the dominant kernel of the step",
+                     "frac": narrow_tflops / fp64_peak if fp64_peak else None, "traffic": NARROW_TRAFFIC_BYTES,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_v5_small_kernels.md)",
+                     "kernel": "narrow_tile_kernel (clip + quadrature + friction + fixed-order sums), the dominant kernel of the step",
                      "kernel_ms": narrow_ms, "kernel_share_of_step": narrow_ms / (narrow_ms + broad_ms),
                      "flops_per_launch": work["flops_narrow"] / n_count * n_env,
                      "peak_source": "DFMA micro-benchmark in this process (pfc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
