@@ -46,6 +46,7 @@ def build_inputs(n_env, rank=0):
     # rank r gets environments [r * n_env, (r + 1) * n_env): seeds are a function of the global env index
     x_all = boxes_env_states(m, n_env, start=rank * n_env)
     X, tw, s = S.boundary_arrays(m, x_all)
+    m.x_all = np.ascontiguousarray(x_all)
     return m, np.ascontiguousarray(X), np.ascontiguousarray(tw)
 
 
@@ -175,8 +176,15 @@ def main():
     np_p = torch.zeros((n_env, n_ins), dtype=torch.int64).pin_memory()
     fl_p = torch.zeros((n_env, n_ins), dtype=torch.int32).pin_memory()
 
-    def step_e2e():
+    def step_e2e_boundary():
         ctx.eval_f64_ptr(n_env, X_p.data_ptr(), tw_p.data_ptr(), None, w_p.data_ptr(), None, np_p.data_ptr(), fl_p.data_ptr())
+
+    # state-level entry point: raw states in, generalized forces out (kinematics prologue and J' w epilogue on the device)
+    x_p = torch.from_numpy(m.x_all).pin_memory()
+    f_p = torch.zeros((n_env, m.nv), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        ctx.eval_state_f64_ptr(n_env, x_p.data_ptr(), f_p.data_ptr(), None, np_p.data_ptr(), fl_p.data_ptr())
 
     def barrier():
         if world > 1:
@@ -188,6 +196,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
         step_e2e()
+        step_e2e_boundary()
     ctx.sync()
 
     # ---- timed region 1: device-resident, CUDA events on the library's stream, L2 flushed between steps ----
@@ -212,6 +221,11 @@ def main():
             step_e2e()
         e2e_s = time.perf_counter() - t0
         barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step_e2e_boundary()
+        e2e_b_s = time.perf_counter() - t0
+        barrier()
     # per-kernel split (outside the timed regions): CUDA events recorded by the library between its two kernels
     ctx.set_timing(True)
     split = []
@@ -224,14 +238,16 @@ def main():
     broad_ms = float(np.median([a for a, _ in split]))
     narrow_ms = float(np.median([b for _, b in split]))
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, e2e_s, e2e_b_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
+        dev_ms, e2e_s, e2e_b_s = float(t[0]), float(t[1]), float(t[2])
 
     # correctness guard: the timed outputs are real (contacts found, finite wrench)
     w_host = w_d.cpu().numpy()
     assert np.isfinite(w_host).all() and int((fl_d.cpu().numpy() & 1).sum()) > n_env, "benchmark produced no contact work"
     assert np.array_equal(w_host, w_p.numpy()), "device-resident and host-pointer entry points disagree"
+    f_chk = S.generalized_forces(m, m.x_all[0], w_host[0])
+    assert np.abs(f_p.numpy()[0] - f_chk).max() <= 1e-9 * max(np.abs(f_chk).max(), 1e-300), "state-level entry point disagrees with J' w on the host"
 
     if rank != 0:
         if world > 1:
@@ -280,8 +296,10 @@ def main():
         octx_mt.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
     cpu_mt = cpu_sample * 5 / (time.perf_counter() - t0)
 
-    h2d = int(X_h.nbytes + tw_h.nbytes)
-    d2h = int(w_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
+    h2d = int(m.x_all.nbytes)
+    d2h = int(f_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
+    h2d_b = int(X_h.nbytes + tw_h.nbytes)
+    d2h_b = int(w_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -291,7 +309,10 @@ def main():
                    "l2": "256 MiB flush between timed steps", "parallelism": f"env-sharded x{world}, no collective"},
         "candidate_pairs_per_sec": pairs_per_eval * value,
         "e2e": {"value": evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "pfc_eval_f64 (host pointers, pinned)"},
+                "api": "pfc_eval_state_f64: pinned host states x[env][48] in, generalized forces f[env][24] + n_pairs + flags out; "
+                       "kinematics prologue and J' w epilogue on the device",
+                "boundary_level": {"value": evals / e2e_b_s, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                                   "ms_per_step": e2e_b_s / args.steps * 1e3, "api": "pfc_eval_f64: X_r2_r1 + twist in, wrenches out (host kinematics not timed)"}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": narrow_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": narrow_tflops / fp64_peak if fp64_peak else None, "traffic": NARROW_TRAFFIC_BYTES,

@@ -89,6 +89,22 @@ int pfc_eval_f64_device(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, cons
 int pfc_eval_dual6(pfc_ctx* ctx, int64_t n_env, const double* X_bp, const double* X7_r2_r1, const double* twist7_r2, const double* s7,
                    double* wrench7_r2, double* sdot7, int64_t* n_pairs, int32_t* flags);
 
+/* Device-side prologue / epilogue for scenes whose bodies are world-attached or float on SPQuatFloating joints (the batched MPC
+ * roll-out case).  pfc_set_bodies (after pfc_finalize) describes the mechanism: joint_type[b] 0 = world-attached, 1 = SPQuatFloating
+ * (q = [MRP(3); trans(3)], v = [omega(3); vel(3)] in the body frame, src/mechanism_scenario.jl:247-256); q0/v0 = offsets of the joint's
+ * coordinates; pose = joint pose on the world, 12 doubles per body (R row-major, then t) or NULL for identity; mesh_body[mesh] = body. */
+int pfc_set_bodies(pfc_ctx* ctx, int n_body, const int32_t* joint_type, const int32_t* q0, const int32_t* v0, const double* pose,
+                   const int32_t* mesh_body, int nq, int nv);
+/* forceAllElasticIntersections! including refreshBodyBodyTransform!/refreshBodyBodyCache! (src/contact_algorithms_non_friction.jl:103-134)
+ * and addGeneralizedForcesThirdLaw! (:267-286), for n_env states x = [q; v; s] (stride nq + nv + 6 n_bristle, src/extensions.jl:21-50):
+ *   f_generalized [env][nv]   sdot [env][bristle][6]   n_pairs / flags [env][ins] (may be NULL in the host version).  Host pointers. */
+int pfc_eval_state_f64(pfc_ctx* ctx, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags);
+/* Same on device buffers, asynchronous on the context's stream (f_generalized must be zero-initialised for world-attached dofs). */
+int pfc_eval_state_f64_device(pfc_ctx* ctx, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags);
+/* Debug / parity: the boundary arrays (X_r2_r1, twist_r2) the prologue computed and the per-instruction wrenches of the last
+ * host-pointer evaluation; any pointer may be NULL. */
+int pfc_get_boundary(pfc_ctx* ctx, int64_t n_env, double* X_r2_r1, double* twist_r2, double* wrench_r2);
+
 /* Debug / parity: keep the candidate-pair lists (TT_Cache, src/obb/tree_types.jl:32-50) of subsequent evaluations. */
 int pfc_set_debug(pfc_ctx* ctx, int keep_pairs);
 /* Pair list of (env, ins) from the last evaluation, in the reference's traversal order: pairs[2k] = primitive of mesh_1, pairs[2k+1] = of mesh_2. */

@@ -22,7 +22,7 @@ _vp = C.c_void_p
 SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
     "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_eval_sharded_begin", "pfc_eval_sharded_partials", "pfc_eval_sharded_step", "pfc_sync", "pfc_stream",
-    "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
+    "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
 ]
 
 
@@ -55,6 +55,10 @@ def lib():
         L.pfc_eval_sharded_begin.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         L.pfc_eval_sharded_partials.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]
         L.pfc_eval_sharded_step.argtypes = [_vp, C.POINTER(C.c_int)]
+        L.pfc_set_bodies.argtypes = [_vp, C.c_int, _i32, _i32, _i32, _vp, _i32, C.c_int, C.c_int]
+        L.pfc_eval_state_f64.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_eval_state_f64_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_get_boundary.argtypes = [_vp, C.c_int64, _vp, _vp, _vp]
         L.pfc_sync.argtypes = [_vp]
         L.pfc_stream.argtypes = [_vp]
         L.pfc_stream.restype = _vp
@@ -158,6 +162,38 @@ class Context:
     def eval_f64_device(self, n_env, X, twist, s, wrench, sdot, n_pairs, flags):
         """Device pointers given as integers; asynchronous on self.stream."""
         _check(lib().pfc_eval_f64_device(self._h, n_env, X, twist, s, wrench, sdot, n_pairs, flags))
+
+    # ---- state-level entry points: kinematics prologue and J' w epilogue on the device ---------------------
+    def set_bodies(self, joint_type, q0, v0, mesh_body, nq, nv, pose=None):
+        """joint_type[b]: 0 = world-attached, 1 = SPQuatFloating; pose: [n_body][12] (R row-major, t) or None."""
+        jt, q0a, v0a, mb = _a(joint_type, np.int32), _a(q0, np.int32), _a(v0, np.int32), _a(mesh_body, np.int32)
+        pose_a = None if pose is None else _a(pose).reshape(len(jt), 12)
+        _check(lib().pfc_set_bodies(self._h, len(jt), jt, q0a, v0a, _p(pose_a), mb, int(nq), int(nv)))
+        self.nq, self.nv = int(nq), int(nv)
+
+    def eval_state_f64(self, x):
+        """x[env][nq + nv + 6 n_bristle] (host) -> dict(f_generalized[env][nv], sdot, n_pairs, flags)."""
+        x = _a(x)
+        x = x.reshape(-1, self.nq + self.nv + 6 * self.n_bristle)
+        n_env, nb = x.shape[0], self.n_bristle
+        out = dict(f_generalized=np.zeros((n_env, self.nv)), sdot=np.zeros((n_env, nb, 6)) if nb else None,
+                   n_pairs=np.zeros((n_env, self.n_ins), np.int64), flags=np.zeros((n_env, self.n_ins), np.int32))
+        _check(lib().pfc_eval_state_f64(self._h, n_env, _p(x), _p(out["f_generalized"]), _p(out["sdot"]), _p(out["n_pairs"]), _p(out["flags"])))
+        return out
+
+    def eval_state_f64_ptr(self, n_env, x, f_generalized, sdot, n_pairs, flags):
+        """Host pointers given as integers (pinned buffers)."""
+        _check(lib().pfc_eval_state_f64(self._h, n_env, x, f_generalized, sdot, n_pairs, flags))
+
+    def eval_state_f64_device(self, n_env, x, f_generalized, sdot, n_pairs, flags):
+        """Device pointers given as integers; asynchronous on self.stream."""
+        _check(lib().pfc_eval_state_f64_device(self._h, n_env, x, f_generalized, sdot, n_pairs, flags))
+
+    def get_boundary(self, n_env):
+        """(X_r2_r1, twist_r2, wrench_r2) of the last evaluation as computed / consumed on the device."""
+        X, tw, w = np.zeros((n_env, self.n_ins, 16)), np.zeros((n_env, self.n_ins, 6)), np.zeros((n_env, self.n_ins, 6))
+        _check(lib().pfc_get_boundary(self._h, n_env, _p(X), _p(tw), _p(w)))
+        return X, tw, w
 
     def eval_sharded_begin(self, n_env, X, twist, s, wrench, sdot, n_pairs, flags):
         """Device pointers (integers).  See INTEGRATION.md for the protocol."""

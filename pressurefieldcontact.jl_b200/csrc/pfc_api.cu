@@ -101,6 +101,14 @@ struct pfc_ctx {
     DevBuf<double> d_X7, d_tw7, d_s7, d_w7, d_sd7;
     DevBuf<int32_t> d_large_index;
     int64_t lists_n_env = -1;   // n_env of the evaluation whose pair lists (d_small_pairs / large_buf, d_np, d_fl) are current
+    // device-side kinematics (pfc_set_bodies / pfc_eval_state_f64)
+    bool has_bodies = false;
+    std::vector<BodyDev> h_bodies;
+    std::vector<int> h_mesh_body;
+    DevBuf<BodyDev> d_bodies;
+    DevBuf<int> d_ins_body, d_body_ins_ptr, d_body_ins;
+    StateDev state{};
+    DevBuf<double> d_x, d_fgen;
     bool timing = false;
     cudaEvent_t ev[8] = {};
     bool ev_valid = false;
@@ -624,6 +632,113 @@ int pfc_get_traction(pfc_ctx* c, int64_t env, int ins, double* out, int64_t cap_
     const int m = std::min(np, cap);
     if (out && m > 0 && cap_points > 0) CU(cudaMemcpy(out, d_out.p, sizeof(double) * 8 * m, cudaMemcpyDeviceToHost));
     d_out.release(); d_n.release(); d_tmp.release();
+    return PFC_OK;
+}
+
+
+// ---- device-side prologue / epilogue (floating-joint scenes) ----------------------------------------------------
+int pfc_set_bodies(pfc_ctx* c, int n_body, const int32_t* joint_type, const int32_t* q0, const int32_t* v0, const double* pose,
+                   const int32_t* mesh_body, int nq, int nv) {
+    if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_set_bodies: call after pfc_finalize");
+    if (n_body < 1 || !joint_type || !q0 || !v0 || !mesh_body || nq < 0 || nv < 0) return fail(PFC_E_ARG, "pfc_set_bodies: bad argument");
+    c->h_bodies.assign(n_body, BodyDev{});
+    for (int b = 0; b < n_body; ++b) {
+        BodyDev& d = c->h_bodies[b];
+        if (joint_type[b] != 0 && joint_type[b] != 1)
+            return fail(PFC_E_ARG, "pfc_set_bodies: only world-attached bodies (0) and SPQuatFloating joints (1) are handled on the device; "
+                                   "use pfc_eval_f64 with host kinematics for other joints");
+        d.joint = joint_type[b]; d.q0 = q0[b]; d.v0 = v0[b];
+        if (d.joint == 1 && (d.q0 < 0 || d.q0 + 6 > nq || d.v0 < 0 || d.v0 + 6 > nv)) return fail(PFC_E_ARG, "pfc_set_bodies: joint offsets out of range");
+        for (int i = 0; i < 9; ++i) d.pose_R[i] = pose ? pose[12 * b + i] : (i % 4 == 0 ? 1.0 : 0.0);
+        for (int i = 0; i < 3; ++i) d.pose_t[i] = pose ? pose[12 * b + 9 + i] : 0.0;
+    }
+    const int n_mesh = int(c->mesh.size()), n_ins = int(c->ins.size());
+    c->h_mesh_body.assign(mesh_body, mesh_body + n_mesh);
+    for (int m = 0; m < n_mesh; ++m) if (mesh_body[m] < 0 || mesh_body[m] >= n_body) return fail(PFC_E_ARG, "pfc_set_bodies: mesh_body out of range");
+    std::vector<int> ins_body(2 * std::max(n_ins, 1)), ptr(n_body + 1, 0), lst;
+    for (int k = 0; k < n_ins; ++k) { ins_body[2 * k] = mesh_body[c->ins[k].mesh_1]; ins_body[2 * k + 1] = mesh_body[c->ins[k].mesh_2]; }
+    for (int b = 0; b < n_body; ++b) {   // Python / Julia order: for every instruction, body 2 first, then body 1
+        for (int k = 0; k < n_ins; ++k) {
+            if (ins_body[2 * k + 1] == b) lst.push_back((k << 1) | 1);
+            if (ins_body[2 * k] == b) lst.push_back((k << 1) | 0);
+        }
+        ptr[b + 1] = int(lst.size());
+    }
+    CU(cudaSetDevice(c->device));
+    CU(c->d_bodies.ensure(n_body)); CU(c->d_ins_body.ensure(ins_body.size())); CU(c->d_body_ins_ptr.ensure(ptr.size())); CU(c->d_body_ins.ensure(std::max<size_t>(lst.size(), 1)));
+    CU(cudaMemcpy(c->d_bodies.p, c->h_bodies.data(), sizeof(BodyDev) * n_body, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_ins_body.p, ins_body.data(), sizeof(int) * ins_body.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_body_ins_ptr.p, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+    if (!lst.empty()) CU(cudaMemcpy(c->d_body_ins.p, lst.data(), sizeof(int) * lst.size(), cudaMemcpyHostToDevice));
+    c->state.bodies = c->d_bodies.p; c->state.ins_body = c->d_ins_body.p; c->state.body_ins_ptr = c->d_body_ins_ptr.p; c->state.body_ins = c->d_body_ins.p;
+    c->state.n_body = n_body; c->state.nq = nq; c->state.nv = nv; c->state.n_x = nq + nv + 6 * c->n_bristle;
+    c->has_bodies = true;
+    return PFC_OK;
+}
+
+static int eval_state_device(pfc_ctx* c, int64_t n_env, const double* x, double* f_gen, double* sdot, long long* n_pairs, int* flags) {
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
+    CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni));
+    if (nb) CU(c->d_s.ensure(6 * ne * nb));
+    int nl = 0;
+    CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), x, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
+    EvalIO io{};
+    io.n_env = n_env; io.X = c->d_X.p; io.twist = c->d_tw.p; io.s = nb ? c->d_s.p : nullptr; io.wrench = c->d_w.p;
+    io.sdot = sdot; io.n_pairs = n_pairs; io.flags = flags;
+    int rc = eval_device(c, io);
+    if (rc != PFC_OK) return rc;
+    CU(launch_state_epilogue(c->state, n_env, int(ni), x, c->d_w.p, f_gen, c->stream, &nl));
+    c->launches += nl;
+    return PFC_OK;
+}
+
+int pfc_eval_state_f64_device(pfc_ctx* c, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized || !c->has_bodies) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: pfc_finalize and pfc_set_bodies first");
+    if (n_env < 0 || !x || !f_generalized || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: NULL buffer");
+    if (c->n_bristle > 0 && !sdot) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: bristle instructions need sdot");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    return eval_state_device(c, n_env, x, f_generalized, sdot, reinterpret_cast<long long*>(n_pairs), flags);
+}
+
+int pfc_eval_state_f64(pfc_ctx* c, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized || !c->has_bodies) return fail(PFC_E_ARG, "pfc_eval_state_f64: pfc_finalize and pfc_set_bodies first");
+    if (n_env < 0 || !x || !f_generalized) return fail(PFC_E_ARG, "pfc_eval_state_f64: NULL buffer");
+    if (c->n_bristle > 0 && !sdot) return fail(PFC_E_ARG, "pfc_eval_state_f64: bristle instructions need sdot");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
+    CU(c->d_x.ensure(ne * nx)); CU(c->d_fgen.ensure(std::max<size_t>(ne * nv, 1))); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+    if (nb) CU(c->d_sd.ensure(6 * ne * nb));
+    CU(cudaMemcpyAsync(c->d_x.p, x, sizeof(double) * ne * nx, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_fgen.p, 0, sizeof(double) * ne * nv, c->stream));
+    int rc = eval_state_device(c, n_env, c->d_x.p, c->d_fgen.p, nb ? c->d_sd.p : nullptr, c->d_np.p, c->d_fl.p);
+    if (rc != PFC_OK) return rc;
+    CU(cudaMemcpyAsync(f_generalized, c->d_fgen.p, sizeof(double) * ne * nv, cudaMemcpyDeviceToHost, c->stream));
+    if (nb) CU(cudaMemcpyAsync(sdot, c->d_sd.p, sizeof(double) * 6 * ne * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int32_t> fl_local;
+    int32_t* fl = flags;
+    if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
+    CU(cudaMemcpyAsync(fl, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->lists_n_env = n_env;
+    for (size_t k = 0; k < ne * ni; ++k) {
+        if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
+        if (fl[k] & PFC_FLAG_OVERFLOW) return fail(PFC_E_CAPACITY, "candidate-pair capacity exceeded");
+    }
+    return PFC_OK;
+}
+
+int pfc_get_boundary(pfc_ctx* c, int64_t n_env, double* X, double* twist, double* wrench) {
+    if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_get_boundary: context not finalized");
+    const size_t n = size_t(n_env) * size_t(c->scene.n_ins);
+    if (c->d_X.n < 16 * n || c->d_tw.n < 6 * n || c->d_w.n < 6 * n) return fail(PFC_E_ARG, "pfc_get_boundary: no evaluation of that size has run");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (X) CU(cudaMemcpy(X, c->d_X.p, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost));
+    if (twist) CU(cudaMemcpy(twist, c->d_tw.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost));
+    if (wrench) CU(cudaMemcpy(wrench, c->d_w.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost));
     return PFC_OK;
 }
 

@@ -38,4 +38,25 @@ cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long
 // FP64 DFMA throughput of the current device in TFLOP/s (best of a few bursts).
 cudaError_t measure_fp64_peak(cudaStream_t stream, double* tflops);
 
+
+// ---- device-side prologue / epilogue for floating-joint scenes (pfc_state.cu) ----
+struct BodyDev {
+    int joint;      // 0 = world-attached (no joint), 1 = SPQuatFloating
+    int q0, v0;     // offsets of the joint's coordinates in q and v
+    int pad;
+    double pose_R[9];   // joint pose on the world (row-major), pose_t
+    double pose_t[3];
+};
+struct StateDev {
+    const BodyDev* bodies;
+    const int* ins_body;       // [n_ins][2]: body of mesh_1, body of mesh_2
+    const int* body_ins_ptr;   // CSR over bodies: the instructions that touch a body, in instruction order ...
+    const int* body_ins;       // ... as (instruction << 1) | (1 if the body carries mesh_2)
+    int n_body, nq, nv, n_x;   // n_x = nq + nv + 6 n_bristle: stride of one environment's state
+};
+cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, double* X, double* twist, double* s,
+                                  cudaStream_t stream, int* n_launches);
+cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
+                                  int* n_launches);
+
 }  // namespace pfc

@@ -1,0 +1,181 @@
+// pfc_state.cu -- device-side prologue / epilogue of the contact-wrench evaluation for scenes whose bodies are
+// world-attached or float on SPQuatFloating joints (config C3 is such a scene).
+//
+//   prologue  state x = [q; v; s] per environment  ->  x_r2_r1 (4x4), twist of r2 w.r.t. r1 in r2, bristle state s
+//             (what refreshBodyBodyTransform! / refreshBodyBodyCache! compute through RigidBodyDynamics:
+//             /root/reference/src/contact_algorithms_non_friction.jl:103-134; joint layout q = [MRP(3); trans(3)],
+//             v = [omega(3); vel(3)] in the body frame: src/mechanism_scenario.jl:247-256)
+//   epilogue  per-instruction wrench (about the r2 origin, in r2, on body 2)  ->  f_generalized += J' w on body 2,
+//             -= J' w on body 1 (addGeneralizedForcesThirdLaw!, :267-286); every thread owns one body's six
+//             velocity coordinates and adds its instructions in instruction order, so the sums are reproducible.
+// With these two kernels a batched evaluation takes the raw states and returns generalized forces: the host does no
+// kinematics and moves 3.3x fewer bytes per environment.
+#include "pfc_launch.h"
+#include "pfc_math.cuh"
+
+namespace pfc {
+
+namespace {
+
+struct Frame { double R[9]; double t[3]; double ang[3]; double lin[3]; };   // transform_to_root, twist_wrt_world (about the world origin)
+
+// SPQuat / modified Rodrigues parameters -> rotation matrix (Rotations.jl: q = ((1 - a2) / (1 + a2), 2 p / (1 + a2)))
+PFC_D void mrp_to_rot(const double* p, double* R) {
+    const double a2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    const double inv = 1.0 / (a2 + 1.0);
+    const double w = (1.0 - a2) * inv, x = 2.0 * p[0] * inv, y = 2.0 * p[1] * inv, z = 2.0 * p[2] * inv;
+    R[0] = 1.0 - 2.0 * (y * y + z * z); R[1] = 2.0 * (x * y - w * z); R[2] = 2.0 * (x * z + w * y);
+    R[3] = 2.0 * (x * y + w * z); R[4] = 1.0 - 2.0 * (x * x + z * z); R[5] = 2.0 * (y * z - w * x);
+    R[6] = 2.0 * (x * z - w * y); R[7] = 2.0 * (y * z + w * x); R[8] = 1.0 - 2.0 * (x * x + y * y);
+}
+
+PFC_D void mat_vec(const double* R, const double* v, double* out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2];
+}
+PFC_D void mat_t_vec(const double* R, const double* v, double* out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = R[i] * v[0] + R[3 + i] * v[1] + R[6 + i] * v[2];
+}
+PFC_D void cross3(const double* a, const double* b, double* out) {
+    out[0] = a[1] * b[2] - a[2] * b[1]; out[1] = a[2] * b[0] - a[0] * b[2]; out[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+PFC_D void body_frame(const BodyDev& b, const double* __restrict__ q, const double* __restrict__ v, Frame& f, bool with_twist) {
+    if (b.joint == 0) {   // world-attached
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { f.t[i] = 0.0; f.ang[i] = 0.0; f.lin[i] = 0.0; }
+        return;
+    }
+    double Rj[9];
+    mrp_to_rot(q + b.q0, Rj);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) f.R[3 * i + j] = b.pose_R[3 * i] * Rj[j] + b.pose_R[3 * i + 1] * Rj[3 + j] + b.pose_R[3 * i + 2] * Rj[6 + j];
+    double tj[3] = {q[b.q0 + 3], q[b.q0 + 4], q[b.q0 + 5]};
+    mat_vec(b.pose_R, tj, f.t);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) f.t[i] += b.pose_t[i];
+    if (with_twist) {
+        const double om[3] = {v[b.v0], v[b.v0 + 1], v[b.v0 + 2]}, ve[3] = {v[b.v0 + 3], v[b.v0 + 4], v[b.v0 + 5]};
+        mat_vec(f.R, om, f.ang);
+        double rv[3], tx[3];
+        mat_vec(f.R, ve, rv);
+        cross3(f.t, f.ang, tx);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) f.lin[i] = rv[i] + tx[i];
+    }
+}
+
+// one thread per (environment, instruction): boundary arrays; one extra pass copies the bristle states
+__global__ void __launch_bounds__(128) state_prologue_kernel(StateDev sd, long long n_env, int n_ins, int n_bristle, const double* __restrict__ x,
+                                                             double* __restrict__ X, double* __restrict__ twist, double* __restrict__ s) {
+    const long long n = n_env * n_ins;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
+        const long long env = id / n_ins;
+        const int k = (int)(id - env * n_ins);
+        const double* q = x + env * sd.n_x;
+        const double* v = q + sd.nq;
+        Frame f1, f2;
+        body_frame(sd.bodies[sd.ins_body[2 * k]], q, v, f1, true);
+        body_frame(sd.bodies[sd.ins_body[2 * k + 1]], q, v, f2, true);
+        // x_r2_rw = inv(x_rw_r2);  x_r2_r1 = x_r2_rw * x_rw_r1   (non_friction.jl:109-113)
+        double t_inv[3], t21[3];
+        mat_t_vec(f2.R, f2.t, t_inv);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) t_inv[i] = -t_inv[i];
+        mat_t_vec(f2.R, f1.t, t21);
+        double* Xo = X + 16 * id;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Xo[4 * j + i] = f2.R[i] * f1.R[j] + f2.R[3 + i] * f1.R[3 + j] + f2.R[6 + i] * f1.R[6 + j];
+            Xo[12 + i] = t21[i] + t_inv[i];
+            Xo[4 * i + 3] = 0.0;
+        }
+        Xo[15] = 1.0;
+        // twist_r2_r1 = -twist_w_r1 + twist_w_r2 in world, then transform(., x_r2_rw)   (:125-128)
+        const double aw[3] = {f2.ang[0] - f1.ang[0], f2.ang[1] - f1.ang[1], f2.ang[2] - f1.ang[2]};
+        const double lw[3] = {f2.lin[0] - f1.lin[0], f2.lin[1] - f1.lin[1], f2.lin[2] - f1.lin[2]};
+        double ang[3], lin[3], tx[3];
+        mat_t_vec(f2.R, aw, ang);
+        mat_t_vec(f2.R, lw, lin);
+        cross3(t_inv, ang, tx);
+        double* two = twist + 6 * id;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { two[i] = ang[i]; two[3 + i] = lin[i] + tx[i]; }
+    }
+    const long long ns = n_env * 6 * n_bristle;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < ns; id += (long long)gridDim.x * blockDim.x) {
+        const long long env = id / (6 * n_bristle);
+        s[id] = x[env * sd.n_x + sd.nq + sd.nv + (id - env * 6 * n_bristle)];
+    }
+}
+
+// one thread per (environment, body)
+__global__ void __launch_bounds__(128) state_epilogue_kernel(StateDev sd, long long n_env, int n_ins, const double* __restrict__ x,
+                                                             const double* __restrict__ wrench, double* __restrict__ f_gen) {
+    const long long n = n_env * sd.n_body;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
+        const long long env = id / sd.n_body;
+        const int b = (int)(id - env * sd.n_body);
+        const BodyDev& body = sd.bodies[b];
+        if (body.joint == 0) continue;   // jac == nothing: world-attached meshes take no generalized force
+        const double* q = x + env * sd.n_x;
+        Frame fb;
+        body_frame(body, q, nullptr, fb, false);
+        double fa[3] = {0.0, 0.0, 0.0}, fl[3] = {0.0, 0.0, 0.0};
+        for (int e = sd.body_ins_ptr[b]; e < sd.body_ins_ptr[b + 1]; ++e) {
+            const int code = sd.body_ins[e];
+            const int k = code >> 1;
+            const double sign = (code & 1) ? 1.0 : -1.0;   // +J' w on body 2, -J' w on body 1
+            Frame f2;
+            const int b2 = sd.ins_body[2 * k + 1];
+            if (b2 == b) f2 = fb; else body_frame(sd.bodies[b2], q, nullptr, f2, false);
+            const double* w = wrench + 6 * (env * n_ins + k);
+            double lin_w[3], ang_w[3], tx[3];
+            mat_vec(f2.R, w + 3, lin_w);
+            mat_vec(f2.R, w, ang_w);
+            cross3(f2.t, lin_w, tx);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ang_w[i] += tx[i];
+            cross3(fb.t, lin_w, tx);
+            const double m[3] = {ang_w[0] - tx[0], ang_w[1] - tx[1], ang_w[2] - tx[2]};
+            double ja[3], jl[3];
+            mat_t_vec(fb.R, m, ja);
+            mat_t_vec(fb.R, lin_w, jl);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { fa[i] += sign * ja[i]; fl[i] += sign * jl[i]; }
+        }
+        double* fo = f_gen + env * sd.nv + body.v0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { fo[i] = fa[i]; fo[3 + i] = fl[i]; }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, double* X, double* twist, double* s,
+                                  cudaStream_t stream, int* n_launches) {
+    const long long n = n_env * n_ins;
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 127) / 128 < 148 * 16 ? (n + 127) / 128 : 148 * 16);
+    state_prologue_kernel<<<blocks, 128, 0, stream>>>(sd, n_env, n_ins, n_bristle, x, X, twist, s);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
+                                  int* n_launches) {
+    const long long n = n_env * sd.n_body;
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 127) / 128 < 148 * 16 ? (n + 127) / 128 : 148 * 16);
+    state_epilogue_kernel<<<blocks, 128, 0, stream>>>(sd, n_env, n_ins, x, wrench, f_gen);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace pfc

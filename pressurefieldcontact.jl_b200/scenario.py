@@ -33,7 +33,7 @@ __all__ = [
     "Regularized", "Bristle", "ContactProperties", "InertiaProperties", "ContactInstructions", "MeshCache", "Prismatic", "Revolute", "add_body",
     "SPQuatFloating", "MechanismScenario", "add_contact", "add_body_contact", "add_friction_regularize", "add_friction_bristle",
     "finalize", "set_state_spq", "set_configuration", "get_state", "num_x", "boundary_arrays", "boundary_arrays_dual6",
-    "force_all_elastic_intersections", "mrp_to_rotation", "rotation_to_mrp",
+    "force_all_elastic_intersections", "force_all_elastic_intersections_batch", "mrp_to_rotation", "rotation_to_mrp",
 ]
 
 
@@ -192,6 +192,7 @@ class MechanismScenario:
         self.backend = None
         self.finalized = False
         self.TT_Cache_n_pairs = None
+        self.device_kinematics = False
 
     # state sizes
     @property
@@ -309,6 +310,12 @@ def attach_backend(m: MechanismScenario, backend, max_env: int = 1) -> None:
         backend.add_instruction(ci.id_1, ci.id_2, ci.chi, fm.model, fm.params(), ci.n_quad_rule)
     backend.finalize(max_env)
     m.backend = backend
+    # device-side kinematics (pfc_set_bodies) when every body is world-attached or floats on the world
+    if hasattr(backend, "set_bodies") and all(b.joint is None or (isinstance(b.joint, SPQuatFloating) and b.parent == 0) for b in m.bodies):
+        pose = np.array([np.concatenate([b.pose_R.reshape(9), b.pose_t]) for b in m.bodies])
+        backend.set_bodies([0 if b.joint is None else 1 for b in m.bodies], [b.q0 for b in m.bodies], [b.v0 for b in m.bodies],
+                           [mc.body_id for mc in m.MeshCache], m.nq, m.nv, pose=pose)
+        m.device_kinematics = True
 
 
 # --------------------------------------------------------------------------------------------------
@@ -519,6 +526,14 @@ def generalized_forces(m: MechanismScenario, x: np.ndarray, wrench_r2: np.ndarra
                     f[iv] += sign * float(s_ang @ ang_w + s_lin @ lin_w)
                 bid = m.bodies[bid].parent
     return f
+
+
+def force_all_elastic_intersections_batch(m: MechanismScenario, x: np.ndarray):
+    """forceAllElasticIntersections! for a batch of states x[env][num_x] with kinematics and J' w on the device
+    (floating-joint scenes): dict(f_generalized[env][nv], sdot[env][n_bristle][6], n_pairs, flags)."""
+    if m.backend is None or not m.device_kinematics:
+        raise RuntimeError("the scene has joints the device prologue does not handle (or no CUDA backend): use force_all_elastic_intersections")
+    return m.backend.eval_state_f64(np.atleast_2d(np.asarray(x, dtype=np.float64)))
 
 
 def force_all_elastic_intersections(m: MechanismScenario, x: Optional[np.ndarray] = None):

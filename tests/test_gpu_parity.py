@@ -542,3 +542,53 @@ def test_c2_spoon_bristle_sampled_states():
         g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(1, m_gpu.n_bristle, 6), sdot_metric=True, bristle_wrench_metric=True, floor=C2_FLOOR)
         n_contact += int((c["flags"] & 1).sum())
     assert n_contact >= 8
+
+
+# ---- state-level entry point: kinematics prologue and J' w epilogue on the device ----------
+def test_state_entry_point_boxes_batch():
+    """pfc_eval_state_f64 on 256 boxes.jl environments: the boundary arrays the device computes from x agree with the host
+    mirror of RigidBodyDynamics (1e-13); fed to the oracle they give bit-exact pair counts / flags and wrenches within 1e-9;
+    the generalized forces equal addGeneralizedForcesThirdLaw! applied on the host to the oracle's wrenches."""
+    n_env = 256
+    m_gpu, m_cpu = _both(lambda b, n: scene_boxes(b, max_env=n)[0], n_env)
+    assert m_gpu.device_kinematics
+    x = boxes_env_states(m_gpu, n_env)
+    out = S.force_all_elastic_intersections_batch(m_gpu, x)
+    X_d, tw_d, w_d = m_gpu.backend.get_boundary(n_env)
+    X_h, tw_h, _ = S.boundary_arrays(m_gpu, x)
+    assert np.abs(X_d - X_h).max() <= 1e-13 and np.abs(tw_d - tw_h).max() <= 1e-13 * max(1.0, np.abs(tw_h).max())
+    c = m_cpu.backend.eval_f64(X_d, tw_d)
+    assert (out["n_pairs"] == c["n_pairs"]).all() and (out["flags"] == c["flags"]).all()
+    scale = np.abs(c["wrench"]).max()
+    assert wrench_rel_err(w_d, c["wrench"], floor=1e-9 * scale) <= TOL
+    f_ref = np.array([S.generalized_forces(m_cpu, x[e], c["wrench"][e]) for e in range(n_env)])
+    assert np.abs(out["f_generalized"] - f_ref).max() <= TOL * np.abs(f_ref).max()
+    assert (c["flags"] & 1).sum() > n_env
+    # same numbers as the boundary-level entry point fed with the device's own boundary arrays
+    g = m_gpu.backend.eval_f64(X_d, tw_d)
+    assert np.array_equal(g["wrench"], w_d)
+
+
+def test_state_entry_point_bristle_and_rejects_chains():
+    """Bristle states ride along in x (s-dot comes back); scenes with revolute / prismatic chains are refused."""
+    n_env = 32
+    m_gpu, m_cpu = _both(_normal_scene(2), n_env)
+    rng = np.random.default_rng(7)
+    x = np.zeros((n_env, S.num_x(m_gpu)))
+    for e in range(n_env):
+        x[e, 0:3] = rng.uniform(-0.03, 0.03, 3)
+        x[e, 3:6] = [rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), -rng.uniform(0.01, 0.1) * 0.05]
+        x[e, 6:12] = rng.uniform(-0.1, 0.1, 6)
+        x[e, 12:18] = rng.uniform(-1, 1, 6) * np.array([1e-3, 1e-3, 1e-3, 1e-5, 1e-5, 1e-5])
+    out = S.force_all_elastic_intersections_batch(m_gpu, x)
+    X_d, tw_d, w_d = m_gpu.backend.get_boundary(n_env)
+    c = m_cpu.backend.eval_f64(X_d, tw_d, x[:, 12:18].reshape(n_env, 1, 6))
+    assert (out["flags"] == c["flags"]).all() and (c["flags"] & 1).all()
+    assert wrench_rel_err(out["sdot"], c["sdot"], floor=1e-9 * np.abs(c["sdot"]).max()) <= TOL
+    f_ref = np.array([S.generalized_forces(m_cpu, x[e], c["wrench"][e]) for e in range(n_env)])
+    assert np.abs(out["f_generalized"] - f_ref).max() <= TOL * np.abs(f_ref).max()
+    from pfc_b200 import scenes
+    m_chain, _ = scenes.scene_c2_pencil(True, _ctx())
+    assert not m_chain.device_kinematics
+    with pytest.raises(RuntimeError):
+        S.force_all_elastic_intersections_batch(m_chain, S.get_state(m_chain))
