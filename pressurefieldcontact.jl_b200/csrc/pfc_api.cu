@@ -1,6 +1,8 @@
 // pfc_api.cu -- the C ABI of include/pfc.h: scene container, one-time upload, evaluation entry points.
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -71,6 +73,7 @@ struct pfc_ctx {
     DevBuf<TriRec> d_tris;
     DevBuf<InsDev> d_ins;
     DevBuf<int32_t> d_small;
+    DevBuf<int32_t> d_small_heavy;
     std::vector<InsDev> h_ins;
     SceneDev scene{};
     // per-batch staging (host-pointer entry points)
@@ -183,7 +186,7 @@ int pfc_destroy(pfc_ctx* c) {
     if (!c) return PFC_OK;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release();
+    c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release(); c->d_small_heavy.release();
     c->d_X.release(); c->d_tw.release(); c->d_s.release(); c->d_w.release(); c->d_sd.release(); c->d_np.release(); c->d_fl.release();
     c->d_dbg_pairs.release(); c->d_last_np.release(); c->d_small_pairs.release();
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -374,6 +377,22 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
     if (!tris.empty()) CU(cudaMemcpy(c->d_tris.p, tris.data(), tris.size() * sizeof(TriRec), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_ins.p, c->h_ins.data(), c->h_ins.size() * sizeof(InsDev), cudaMemcpyHostToDevice));
     if (!small.empty()) CU(cudaMemcpy(c->d_small.p, small.data(), small.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    {   // broad-phase scheduling order: instruction-major, the instructions with the largest trees first
+        std::vector<int32_t> heavy(small);
+        std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t a, int32_t b) {
+            return (long long)c->h_ins[a].n_leaf1 * c->h_ins[a].n_leaf2 > (long long)c->h_ins[b].n_leaf1 * c->h_ins[b].n_leaf2; });
+        CU(c->d_small_heavy.ensure(std::max<size_t>(heavy.size(), 1)));
+        if (!heavy.empty()) CU(cudaMemcpy(c->d_small_heavy.p, heavy.data(), heavy.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->scene.small_heavy_first = c->d_small_heavy.p;
+        int lo = INT32_MAX, hi = 0;
+        for (int32_t k : small) {
+            const InsDev& in = c->h_ins[k];
+            lo = std::min(lo, std::min(in.node_base1, in.node_base2));
+            hi = std::max(hi, std::max(in.node_base1 + 2 * in.n_leaf1 - 1, in.node_base2 + 2 * in.n_leaf2 - 1));
+        }
+        c->scene.small_node_lo = small.empty() ? 0 : lo;
+        c->scene.small_node_n = small.empty() ? 0 : hi - lo;
+    }
     c->scene.nodes = c->d_nodes.p; c->scene.tets = c->d_tets.p; c->scene.tris = c->d_tris.p; c->scene.ins = c->d_ins.p;
     c->scene.small_ins = c->d_small.p;
     c->scene.n_ins = int(c->h_ins.size()); c->scene.n_small = int(small.size()); c->scene.n_bristle = c->n_bristle;

@@ -105,8 +105,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) broad_small_kernel(SceneDev 
     const long long n_prob = io.n_env * sc.n_small;
     const long long stride = (long long)gridDim.x * WARPS * NG;
     for (long long prob = ((long long)blockIdx.x * WARPS + wib) * NG + grp; prob < n_prob; prob += stride) {
-        const long long env = prob / sc.n_small;
-        const int k = sc.small_ins[prob - env * sc.n_small];
+        // scheduling order: instruction-major, heaviest instruction first (the short problems fill the last, partial wave)
+        const long long j = prob / io.n_env;
+        const long long env = prob - j * io.n_env;
+        const int k = sc.small_heavy_first[j];
         const InsDev& ins = sc.ins[k];
         const long long ei = env * sc.n_ins + k;
         Xform<double> x21;
@@ -170,6 +172,201 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) broad_small_kernel(SceneDev 
         for (int o = G / 2; o > 0; o >>= 1) flags |= __shfl_xor_sync(gmask, flags, o, G);
         if (gl == 0) { io.n_pairs[ei] = n; io.flags[ei] = flags; }
         __syncwarp(gmask);
+    }
+}
+
+// ---- kernel 1b: broad phase, one WARP per tile of P problems, node table in shared memory ---------------------------
+// What limits the per-group kernel above is not the FP64 pipe but the L1 data pipe: every lane gathers its two 128 B node
+// records with its own vector loads, so one warp-wide load instruction touches 32 different lines and costs 32 wavefronts
+// for 16 useful bytes each (ncu: l1tex__data_pipe_lsu_wavefronts ~ 66 % of peak, profiles/r1_v7_*).  Here
+//   * the persistent CTA stages the node records of all small instructions ONCE in shared memory at an odd stride
+//     (17 doubles): a lane-private record read is then conflict-free, 2 wavefronts per 64-bit load instead of 32;
+//   * each warp owns a tile of P consecutive problems whose frontiers form ONE flattened array (problem-major, DFS order
+//     inside a problem), and every level runs in two phases:
+//       A. the OPEN node pairs (a compact work list of frontier slots) are tested one per lane, lanes dense: 15-axis SAT
+//          with exactly the arithmetic of the per-group kernel -> a result code per slot;
+//       B. an ordered rebuild over the whole frontier (integer work only): finished pairs are copied, hits are replaced by
+//          their children in the reference's visiting order, a warp scan gives the positions; the open children form the
+//          next work list.
+//     When no pair is open the frontier is exactly the reference's recursion order: no atomics, no sort, bit-exact lists.
+// Warps never synchronise with each other after the staging barrier.
+constexpr int kNodeStride = 17;        // doubles per staged node record (16 + 1 pad: odd, so lane-private records do not collide)
+constexpr int kNodeTabMax = 320;       // nodes staged at most (43.5 KB); larger scenes read the records from global memory
+template <int P> struct BroadTileLayout {
+    // per warp: double xf[P][12] | long long ei[P] | unsigned front[2][P * cap] | int pre[2][P + 1] | int ins[P] | u16 olist[2][P * cap] | u8 res[P * cap]
+    __host__ __device__ static size_t warp_bytes(int cap) {
+        const size_t b = sizeof(double) * P * 12 + sizeof(long long) * P + sizeof(unsigned) * 2 * P * cap + sizeof(int) * (2 * (P + 1) + P) +
+                         sizeof(unsigned short) * 2 * P * cap + (size_t)P * cap;
+        return (b + 15) / 16 * 16;
+    }
+    __host__ __device__ static size_t bytes(int cap, int n_warps, int n_stage) { return sizeof(double) * kNodeStride * n_stage + warp_bytes(cap) * n_warps; }
+};
+
+template <int P, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, EvalIO io, int cap, int n_stage, unsigned* __restrict__ pairs_out) {
+    constexpr int T = 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // ---- node table: staged once per (persistent) CTA
+    double* ntab_s = reinterpret_cast<double*>(smem_raw);
+    for (int j = threadIdx.x; j < n_stage * 16; j += 32 * NW) {
+        const int node = j >> 4, w = j & 15;
+        ntab_s[node * kNodeStride + w] = reinterpret_cast<const double*>(sc.nodes + sc.small_node_lo + node)[w];
+    }
+    __syncthreads();
+    const double* ntab = n_stage > 0 ? ntab_s - (size_t)kNodeStride * sc.small_node_lo : reinterpret_cast<const double*>(sc.nodes);
+    const int nstride = n_stage > 0 ? kNodeStride : 16;
+
+    unsigned char* wbase = smem_raw + sizeof(double) * kNodeStride * n_stage + BroadTileLayout<P>::warp_bytes(cap) * wib;
+    double* xf = reinterpret_cast<double*>(wbase);
+    long long* s_ei = reinterpret_cast<long long*>(xf + P * 12);
+    unsigned* front = reinterpret_cast<unsigned*>(s_ei + P);
+    int* pre = reinterpret_cast<int*>(front + 2 * (size_t)P * cap);   // pre[b][q + 1]: end of problem q's segment in frontier b
+    int* s_ins = pre + 2 * (P + 1);
+    unsigned short* olist = reinterpret_cast<unsigned short*>(s_ins + P);
+    unsigned char* res = reinterpret_cast<unsigned char*>(olist + 2 * (size_t)P * cap);
+    const int fcap = P * cap;
+    const long long n_prob = io.n_env * sc.n_small;
+    const long long n_tile = (n_prob + P - 1) / P;
+    for (long long tile = (long long)blockIdx.x * NW + wib; tile < n_tile; tile += (long long)gridDim.x * NW) {
+        // ---- 0. per-problem transform of the broad phase (x_r1_r2 = inverse of x_r2_r1, the reference's rounding): 16 lanes per problem
+        for (int j = lane; j < 16 * P; j += T) {
+            const int q = j >> 4, l = j & 15;
+            const long long prob = tile * P + q;
+            if (prob < n_prob) {
+                const long long jj = prob / io.n_env;   // scheduling order: instruction-major, heaviest instruction first
+                const long long env = prob - jj * io.n_env;
+                const int k = sc.small_heavy_first[jj];
+                const long long ei = env * sc.n_ins + k;
+                const double* X = io.X + 16 * ei;
+                if (l < 9) xf[12 * q + l] = X[4 * (l / 3) + l % 3];
+                else if (l < 12) { const int i = l - 9; xf[12 * q + l] = -add_(add_(mul_(X[4 * i], X[12]), mul_(X[4 * i + 1], X[13])), mul_(X[4 * i + 2], X[14])); }
+                else if (l == 12) { s_ei[q] = ei; s_ins[q] = k; front[q] = enc(0, 0); olist[q] = (unsigned short)q; }
+            } else if (l == 12) { s_ei[q] = -1; s_ins[q] = 0; }
+        }
+        const int n_valid = (int)((n_prob - tile * P) < P ? (n_prob - tile * P) : P);
+        for (int j = lane; j <= P; j += T) pre[j] = j < n_valid ? j : n_valid;
+        __syncwarp();
+        int cur = 0, n_open = n_valid;
+        int flags = 0;
+        unsigned dead = 0;   // problems whose frontier is empty (nobody writes their segment end any more); identical in every lane
+#pragma unroll
+        for (int q = 0; q < P; ++q) dead |= (q >= n_valid ? 1u : 0u) << q;
+        int pc[P + 1];
+        for (;;) {
+            const int* pcs = pre + cur * (P + 1);
+            int* pn = pre + (cur ^ 1) * (P + 1);
+            const unsigned* fc = front + (size_t)cur * fcap;
+            unsigned* fn = front + (size_t)(cur ^ 1) * fcap;
+            const unsigned short* olc = olist + (size_t)cur * fcap;
+            unsigned short* oln = olist + (size_t)(cur ^ 1) * fcap;
+            pc[0] = 0;
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                pc[q + 1] = ((dead >> q) & 1u) ? pc[q] : pcs[q + 1];
+                if (pc[q + 1] == pc[q]) dead |= 1u << q;
+            }
+            const int total = pc[P];
+            if (n_open == 0) break;
+            // ---- A. SAT on the open node pairs, one per lane
+            for (int j = lane; j < n_open; j += T) {
+                const int c = olc[j];
+                int q = 0;
+#pragma unroll
+                for (int r = 1; r < P; ++r) q += (c >= pc[r]);
+                const unsigned e = fc[c];
+                const int ia = dec_a(e), ib = dec_b(e);
+                const InsDev& ins = sc.ins[s_ins[q]];
+                const NodeRec& a = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base1 + ia));
+                const NodeRec& b = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base2 + ib));
+                SatA A;
+                sat_prepare_a(a, xf + 12 * q, xf + 12 * q + 9, A);
+                int code = 0;
+                if (sat_test(A, b)) code = (a.left < 0) ? ((b.left < 0) ? 1 : 2) : ((b.left < 0) ? 3 : 4);
+                res[c] = (unsigned char)code;
+            }
+            __syncwarp();
+            // ---- B. ordered rebuild: children replace their parent in place (reference order), open children form the next work list
+            int carry = 0;
+            for (int c0 = 0; c0 < total; c0 += T) {
+                const int c = c0 + lane;
+                int cnt = 0, ocnt = 0, q = 0;
+                unsigned ch0 = 0, ch1 = 0, ch2 = 0, ch3 = 0;
+                if (c < total) {
+#pragma unroll
+                    for (int r = 1; r < P; ++r) q += (c >= pc[r]);
+                    const unsigned e = fc[c];
+                    if (e & kDone) { cnt = 1; ch0 = e; }
+                    else {
+                        const int code = res[c];
+                        if (code) {
+                            const int ia = dec_a(e), ib = dec_b(e);
+                            const InsDev& ins = sc.ins[s_ins[q]];
+                            const NodeRec& a = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base1 + ia));
+                            const NodeRec& b = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base2 + ib));
+                            const int al = a.left, ar = a.right, bl = b.left, br = b.right;
+                            if (code == 1) { cnt = 1; ch0 = kDone | enc(ar, br); }
+                            else if (code == 2) { cnt = ocnt = 2; ch0 = enc(ia, bl); ch1 = enc(ia, br); }
+                            else if (code == 3) { cnt = ocnt = 2; ch0 = enc(al, ib); ch1 = enc(ar, ib); }
+                            else { cnt = ocnt = 4; ch0 = enc(al, bl); ch1 = enc(ar, bl); ch2 = enc(al, br); ch3 = enc(ar, br); }
+                        }
+                    }
+                }
+                const int mine = cnt | (ocnt << 16);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const int chunk_total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = carry + incl - mine;
+                const int at = excl & 0xffff, oat = excl >> 16;
+                if (at + cnt <= fcap) {
+                    if (cnt > 0) fn[at] = ch0;
+                    if (cnt > 1) fn[at + 1] = ch1;
+                    if (cnt > 2) { fn[at + 2] = ch2; fn[at + 3] = ch3; }
+                    for (int k = 0; k < ocnt; ++k) oln[oat + k] = (unsigned short)(at + k);
+                } else if (cnt > 0) flags |= kFlagOverflow;   // cannot happen: a frontier never holds more than n_leaf1 * n_leaf2 entries
+                if (c < total) {   // the last slot of problem q closes its segment (pc[] by a run-time index would go to local memory)
+                    int end_q = pc[P];
+#pragma unroll
+                    for (int r = 1; r < P; ++r) if (r == q + 1) end_q = pc[r];
+                    if (c + 1 == end_q) pn[q + 1] = min(at + cnt, fcap);
+                }
+                carry += chunk_total;
+            }
+            n_open = carry >> 16;
+            __syncwarp();
+            cur ^= 1;
+        }
+        // ---- results: pair lists (DFS order), counts, flags (pc[] holds the final segments)
+        {
+            const unsigned* fc = front + (size_t)cur * fcap;
+            const int total = pc[P];
+            for (int c = lane; c < total; c += T) {
+                int q = 0;
+#pragma unroll
+                for (int r = 1; r < P; ++r) q += (c >= pc[r]);
+                int beg_q = 0;
+#pragma unroll
+                for (int r = 1; r < P; ++r) if (r == q) beg_q = pc[r];
+                const int i = c - beg_q;
+                const unsigned e = fc[c];
+                if (i < cap) pairs_out[(size_t)cap * s_ei[q] + i] = e;
+                if (io.dbg_pairs && i < io.dbg_cap) {
+                    int* out = io.dbg_pairs + 2 * ((long long)io.dbg_cap * s_ei[q] + i);
+                    out[0] = dec_a(e); out[1] = dec_b(e);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+                if (lane == q && s_ei[q] >= 0) {
+                    const int n = pc[q + 1] - pc[q];
+                    io.n_pairs[s_ei[q]] = n < cap ? n : cap;
+                    io.flags[s_ei[q]] = flags;
+                }
+        }
+        __syncwarp();
     }
 }
 
@@ -572,6 +769,25 @@ cudaError_t launch_broad_g(const SceneDev& sc, const EvalIO& io, int cap, unsign
     return cudaGetLastError();
 }
 
+template <int P, int NW, int MINB>
+cudaError_t launch_broad_tile(const SceneDev& sc, const EvalIO& io, int cap, unsigned* pairs, cudaStream_t stream) {
+    static int cached_cap = -1, cached_stage = -1, cached_blocks = 0;
+    auto kern = broad_tile_kernel<P, NW, MINB>;
+    const int n_stage = sc.small_node_n <= kNodeTabMax ? sc.small_node_n : 0;
+    const size_t smem = BroadTileLayout<P>::bytes(cap, NW, n_stage);
+    if (cached_cap != cap || cached_stage != n_stage) {
+        cudaError_t e;
+        cached_blocks = persistent_blocks((const void*)kern, 32 * NW, smem, &e);
+        if (e != cudaSuccess) return e;
+        cached_cap = cap; cached_stage = n_stage;
+    }
+    const long long n_tile = (io.n_env * sc.n_small + P - 1) / P;
+    long long blocks = (n_tile + NW - 1) / NW;
+    if (blocks > cached_blocks) blocks = cached_blocks;
+    kern<<<(unsigned)blocks, 32 * NW, smem, stream>>>(sc, io, cap, n_stage, pairs);
+    return cudaGetLastError();
+}
+
 template <int G, int MINB>
 cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
     static int cached_cap[2] = {-1, -1}, cached_blocks[2] = {0, 0};
@@ -613,6 +829,17 @@ cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, co
 // 4 CTAs/SM (<=128 registers) for the SAT kernel, 3 (<=168) for the clip/quadrature kernel -- measured best on B200.
 #define PFC_DISPATCH_G(fn, g, minb, ...) ((g) == 8 ? fn<8, minb>(__VA_ARGS__) : (g) == 16 ? fn<16, minb>(__VA_ARGS__) : fn<32, minb>(__VA_ARGS__))
 
+// broad phase of the small path: the tile kernel (PFC_BROAD_TILE=0 selects the per-group kernel; experiments only)
+cudaError_t launch_broad(const SceneDev& sc, const EvalIO& io, int cap, int bg, unsigned* pairs, cudaStream_t stream) {
+    static const bool use_tile = !(getenv("PFC_BROAD_TILE") && atoi(getenv("PFC_BROAD_TILE")) == 0);
+    static const int tile_p = getenv("PFC_BROAD_P") ? atoi(getenv("PFC_BROAD_P")) : 4;
+    if (!use_tile) return PFC_DISPATCH_G(launch_broad_g, bg, 4, sc, io, cap, pairs, stream);
+    // measured on B200 (scripts/sweep_small.sh): 4 problems per warp, 8 warps per CTA, 2 CTAs per SM (124 registers) is the fastest;
+    // squeezing the SAT into 80-92 registers for more warps per SM costs more than the occupancy returns
+    if (tile_p == 2) return launch_broad_tile<2, 8, 2>(sc, io, cap, pairs, stream);
+    return launch_broad_tile<4, 8, 2>(sc, io, cap, pairs, stream);
+}
+
 }  // namespace
 
 // max_pairs: the largest n_leaf1 * n_leaf2 over the small instructions (frontier capacity needed);
@@ -628,7 +855,7 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
     if (const char* e = getenv("PFC_BROAD_G")) bg = atoi(e);
     if (const char* e = getenv("PFC_NARROW_G")) ng = atoi(e);
     if (ev) cudaEventRecord(ev[0], stream);
-    cudaError_t e = PFC_DISPATCH_G(launch_broad_g, bg, 4, sc, io, cap, pairs, stream);
+    cudaError_t e = launch_broad(sc, io, cap, bg, pairs, stream);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
     // scenes with bristle instructions on the small path (three passes, 21 accumulators), or PFC_NARROW_TILE=0, use the per-problem kernel
@@ -651,7 +878,7 @@ cudaError_t launch_broad_small_only(const SceneDev& sc, const EvalIO& io, int ma
     const int cap = small_cap(max_pairs);
     const int bg = cap <= 320 ? 16 : 32;
     if (n_launches) *n_launches += 1;
-    return PFC_DISPATCH_G(launch_broad_g, bg, 4, sc, io, cap, pairs, stream);
+    return launch_broad(sc, io, cap, bg, pairs, stream);
 }
 
 cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long env, int ins, const int* pairs, long long n_pairs, double* out,

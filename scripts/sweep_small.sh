@@ -1,2 +1,4 @@
-run() { python bench.py --steps 20 --warmup 3 --cpu-seconds 0.2 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step']*1000,1),'us', round(d['value']/1e6,2),'M/s')"; }
-for g in 8 16 32; do for b in 2 3 4; do echo -n "narrow G=$g MINB=$b (broad default): "; PFC_NARROW_G=$g PFC_NARROW_MINB=$b run; done; done
+# quick A/B of the small-path kernels on the bench workload (experiments only; env overrides are read once per process)
+run() { python bench.py --steps 30 --warmup 3 --cpu-seconds 0.2 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print(round(d['ms_per_step']*1000,1),'us step | broad', round(r['other_kernels']['broad_small_kernel']['kernel_ms']*1000,1), 'us | narrow', round(r['kernel_ms']*1000,1), 'us | e2e', round(d['e2e']['ms_per_step']*1000,1), 'us')"; }
+echo -n "broad per-group kernel: "; PFC_BROAD_TILE=0 run
+for p in 2 4; do echo -n "broad warp-tile kernel P=$p: "; PFC_BROAD_P=$p run; done
