@@ -101,6 +101,17 @@ int pfc_set_bodies(pfc_ctx* ctx, int n_body, const int32_t* joint_type, const in
 int pfc_eval_state_f64(pfc_ctx* ctx, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags);
 /* Same on device buffers, asynchronous on the context's stream (f_generalized must be zero-initialised for world-attached dofs). */
 int pfc_eval_state_f64_device(pfc_ctx* ctx, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags);
+/* calcXd! (src/contact_algorithms_non_friction.jl:18-38) on the device for the same class of scenes: mass_matrix!, dynamics_bias!,
+ * configuration_derivative!, forceAllElasticIntersections!, sum_all_forces! (:40-52) and the Cholesky solve.  pfc_set_dynamics (after
+ * pfc_set_bodies): spatial_inertia[body][36] = the body's 6x6 spatial inertia about its origin in the body frame, row-major,
+ * [angular; linear] ordering (newBodyFromInertia, src/body_inertia.jl:2-9; ignored for world-attached bodies); gravity[3] in the world frame
+ * (src/mechanism_scenario.jl:184).  The mass matrix of such a scene is block diagonal and constant, so it is factored once, here. */
+int pfc_set_dynamics(pfc_ctx* ctx, int n_body, const double* spatial_inertia, const double* gravity);
+/* x[env][n_x] -> xdot[env][n_x] = [q_dot; v_dot; s_dot] (copyto!, src/extensions.jl:40-50).  tau_ext[env][nv] = external generalized
+ * forces (the controller's tau_ext, :46-47) or NULL.  Host pointers; n_pairs / flags [env][ins] may be NULL. */
+int pfc_calcxd_f64(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags);
+/* Same on device buffers, asynchronous on the context's stream (xdot must be zero-initialised for world-attached coordinates). */
+int pfc_calcxd_f64_device(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags);
 /* Debug / parity: the boundary arrays (X_r2_r1, twist_r2) the prologue computed and the per-instruction wrenches of the last
  * host-pointer evaluation; any pointer may be NULL. */
 int pfc_get_boundary(pfc_ctx* ctx, int64_t n_env, double* X_r2_r1, double* twist_r2, double* wrench_r2);

@@ -22,7 +22,7 @@ _vp = C.c_void_p
 SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
     "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_eval_sharded_begin", "pfc_eval_sharded_partials", "pfc_eval_sharded_step", "pfc_sync", "pfc_stream",
-    "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
+    "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_set_dynamics", "pfc_calcxd_f64", "pfc_calcxd_f64_device", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
 ]
 
 
@@ -59,6 +59,9 @@ def lib():
         L.pfc_eval_state_f64.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
         L.pfc_eval_state_f64_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
         L.pfc_get_boundary.argtypes = [_vp, C.c_int64, _vp, _vp, _vp]
+        L.pfc_set_dynamics.argtypes = [_vp, C.c_int, _d, _d]
+        L.pfc_calcxd_f64.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_calcxd_f64_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
         L.pfc_sync.argtypes = [_vp]
         L.pfc_stream.argtypes = [_vp]
         L.pfc_stream.restype = _vp
@@ -188,6 +191,26 @@ class Context:
     def eval_state_f64_device(self, n_env, x, f_generalized, sdot, n_pairs, flags):
         """Device pointers given as integers; asynchronous on self.stream."""
         _check(lib().pfc_eval_state_f64_device(self._h, n_env, x, f_generalized, sdot, n_pairs, flags))
+
+    # ---- calcXd! on the device (floating-body scenes) ----------------------------------------------------------------
+    def set_dynamics(self, spatial_inertia, gravity):
+        """spatial_inertia[n_body][6][6] about the body origins in the body frames ([angular; linear]); gravity[3] in the world."""
+        H = _a(spatial_inertia).reshape(-1, 36)
+        _check(lib().pfc_set_dynamics(self._h, H.shape[0], H, _a(gravity).reshape(3)))
+
+    def calcxd_f64(self, x, tau_ext=None):
+        """x[env][n_x] (host) -> dict(xdot[env][n_x], n_pairs, flags)."""
+        nx = self.nq + self.nv + 6 * self.n_bristle
+        x = _a(x).reshape(-1, nx)
+        n_env = x.shape[0]
+        tau = None if tau_ext is None else _a(tau_ext).reshape(n_env, self.nv)
+        out = dict(xdot=np.zeros((n_env, nx)), n_pairs=np.zeros((n_env, self.n_ins), np.int64), flags=np.zeros((n_env, self.n_ins), np.int32))
+        _check(lib().pfc_calcxd_f64(self._h, n_env, _p(x), _p(tau), _p(out["xdot"]), _p(out["n_pairs"]), _p(out["flags"])))
+        return out
+
+    def calcxd_f64_device(self, n_env, x, tau_ext, xdot, n_pairs, flags):
+        """Device pointers given as integers; asynchronous on self.stream."""
+        _check(lib().pfc_calcxd_f64_device(self._h, n_env, x, tau_ext, xdot, n_pairs, flags))
 
     def get_boundary(self, n_env):
         """(X_r2_r1, twist_r2, wrench_r2) of the last evaluation as computed / consumed on the device."""

@@ -54,6 +54,15 @@ struct StateDev {
     const int* body_ins;       // ... as (instruction << 1) | (1 if the body carries mesh_2)
     int n_body, nq, nv, n_x;   // n_x = nq + nv + 6 n_bristle: stride of one environment's state
 };
+// rigid-body data for the device-side calcXd! (pfc_set_dynamics): per body the 6x6 spatial inertia about the body origin in the
+// body frame ([angular; linear], row-major) and its inverse; gravity in the world frame
+struct DynDev {
+    const double* H;      // [n_body][36]
+    const double* Hinv;   // [n_body][36]
+    double gravity[3];
+};
+cudaError_t launch_state_dynamics(const StateDev& sd, const DynDev& dd, long long n_env, int n_ins, int n_bristle, const double* x, const double* wrench,
+                                  const double* tau_ext, const double* sdot, double* xdot, cudaStream_t stream, int* n_launches);
 cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, double* X, double* twist, double* s,
                                   cudaStream_t stream, int* n_launches);
 cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,

@@ -115,6 +115,34 @@ __global__ void __launch_bounds__(128) state_prologue_kernel(StateDev sd, long l
     }
 }
 
+// J' w of every instruction that touches body b (addGeneralizedForcesThirdLaw!), summed in instruction order
+PFC_D void body_generalized_force(const StateDev& sd, int b, const Frame& fb, const double* __restrict__ q, const double* __restrict__ wrench_env, double* fa, double* fl) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { fa[i] = 0.0; fl[i] = 0.0; }
+    for (int e = sd.body_ins_ptr[b]; e < sd.body_ins_ptr[b + 1]; ++e) {
+        const int code = sd.body_ins[e];
+        const int k = code >> 1;
+        const double sign = (code & 1) ? 1.0 : -1.0;   // +J' w on body 2, -J' w on body 1
+        Frame f2;
+        const int b2 = sd.ins_body[2 * k + 1];
+        if (b2 == b) f2 = fb; else body_frame(sd.bodies[b2], q, nullptr, f2, false);
+        const double* w = wrench_env + 6 * k;
+        double lin_w[3], ang_w[3], tx[3];
+        mat_vec(f2.R, w + 3, lin_w);
+        mat_vec(f2.R, w, ang_w);
+        cross3(f2.t, lin_w, tx);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ang_w[i] += tx[i];
+        cross3(fb.t, lin_w, tx);
+        const double m[3] = {ang_w[0] - tx[0], ang_w[1] - tx[1], ang_w[2] - tx[2]};
+        double ja[3], jl[3];
+        mat_t_vec(fb.R, m, ja);
+        mat_t_vec(fb.R, lin_w, jl);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { fa[i] += sign * ja[i]; fl[i] += sign * jl[i]; }
+    }
+}
+
 // one thread per (environment, body)
 __global__ void __launch_bounds__(128) state_epilogue_kernel(StateDev sd, long long n_env, int n_ins, const double* __restrict__ x,
                                                              const double* __restrict__ wrench, double* __restrict__ f_gen) {
@@ -127,32 +155,84 @@ __global__ void __launch_bounds__(128) state_epilogue_kernel(StateDev sd, long l
         const double* q = x + env * sd.n_x;
         Frame fb;
         body_frame(body, q, nullptr, fb, false);
-        double fa[3] = {0.0, 0.0, 0.0}, fl[3] = {0.0, 0.0, 0.0};
-        for (int e = sd.body_ins_ptr[b]; e < sd.body_ins_ptr[b + 1]; ++e) {
-            const int code = sd.body_ins[e];
-            const int k = code >> 1;
-            const double sign = (code & 1) ? 1.0 : -1.0;   // +J' w on body 2, -J' w on body 1
-            Frame f2;
-            const int b2 = sd.ins_body[2 * k + 1];
-            if (b2 == b) f2 = fb; else body_frame(sd.bodies[b2], q, nullptr, f2, false);
-            const double* w = wrench + 6 * (env * n_ins + k);
-            double lin_w[3], ang_w[3], tx[3];
-            mat_vec(f2.R, w + 3, lin_w);
-            mat_vec(f2.R, w, ang_w);
-            cross3(f2.t, lin_w, tx);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) ang_w[i] += tx[i];
-            cross3(fb.t, lin_w, tx);
-            const double m[3] = {ang_w[0] - tx[0], ang_w[1] - tx[1], ang_w[2] - tx[2]};
-            double ja[3], jl[3];
-            mat_t_vec(fb.R, m, ja);
-            mat_t_vec(fb.R, lin_w, jl);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { fa[i] += sign * ja[i]; fl[i] += sign * jl[i]; }
-        }
+        double fa[3], fl[3];
+        body_generalized_force(sd, b, fb, q, wrench + 6 * env * n_ins, fa, fl);
         double* fo = f_gen + env * sd.nv + body.v0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) { fo[i] = fa[i]; fo[3 + i] = fl[i]; }
+    }
+}
+
+// calcXd! for floating bodies, one thread per (environment, body): J' w (as above), then
+//   v_dot = H^-1 (f + tau_ext - v x* (H v)) + [0; R' g]     (mass_matrix!, dynamics_bias!, cholesky!/ldiv!: non_friction.jl:23-35;
+//                                                            H is constant in the body frame, so its inverse is taken once, at pfc_set_dynamics)
+//   q_dot = [B(p) w; R u],  B(p) = ((1 - p'p) I + 2 [p]x + 2 p p') / 4                  (configuration_derivative!, SPQuatFloating)
+// and one extra pass copies s_dot behind [q_dot; v_dot] (copyto!, src/extensions.jl:40-50).
+__global__ void __launch_bounds__(128) state_dynamics_kernel(StateDev sd, DynDev dd, long long n_env, int n_ins, int n_bristle, const double* __restrict__ x,
+                                                             const double* __restrict__ wrench, const double* __restrict__ tau_ext,
+                                                             const double* __restrict__ sdot, double* __restrict__ xdot) {
+    const long long n = n_env * sd.n_body;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
+        const long long env = id / sd.n_body;
+        const int b = (int)(id - env * sd.n_body);
+        const BodyDev& body = sd.bodies[b];
+        if (body.joint == 0) continue;
+        const double* q = x + env * sd.n_x;
+        const double* v = q + sd.nq + body.v0;
+        Frame fb;
+        body_frame(body, q, nullptr, fb, false);
+        double f[6];
+        body_generalized_force(sd, b, fb, q, wrench + 6 * env * n_ins, f, f + 3);
+        if (tau_ext) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) f[i] += tau_ext[env * sd.nv + body.v0 + i];
+        }
+        const double* H = dd.H + 36 * b;
+        const double* Hi = dd.Hinv + 36 * b;
+        double h[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a += H[6 * i + j] * v[j];
+            h[i] = a;
+        }
+        double c1[3], c2[3], c3[3];
+        cross3(v, h, c1);          // w x n
+        cross3(v + 3, h + 3, c2);  // u x f
+        cross3(v, h + 3, c3);      // w x f
+        const double rhs[6] = {f[0] - (c1[0] + c2[0]), f[1] - (c1[1] + c2[1]), f[2] - (c1[2] + c2[2]), f[3] - c3[0], f[4] - c3[1], f[5] - c3[2]};
+        double vd[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a += Hi[6 * i + j] * rhs[j];
+            vd[i] = a;
+        }
+        // the joint rotation (without the pose on the world) takes the body-frame velocity to q_dot; gravity uses the full rotation
+        double Rj[9], g_b[3], qd_t[3];
+        mrp_to_rot(q + body.q0, Rj);
+        mat_t_vec(fb.R, dd.gravity, g_b);
+        const double u[3] = {v[3], v[4], v[5]};
+        mat_vec(Rj, u, qd_t);
+        const double* p = q + body.q0;
+        const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2], pw = p[0] * v[0] + p[1] * v[1] + p[2] * v[2];
+        double pxw[3];
+        cross3(p, v, pxw);
+        double* out = xdot + env * sd.n_x;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            out[body.q0 + i] = 0.25 * ((1.0 - pp) * v[i] + 2.0 * pxw[i] + 2.0 * p[i] * pw);
+            out[body.q0 + 3 + i] = qd_t[i];
+            out[sd.nq + body.v0 + i] = vd[i];
+            out[sd.nq + body.v0 + 3 + i] = vd[3 + i] + g_b[i];
+        }
+    }
+    const long long ns = n_env * 6 * n_bristle;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < ns; id += (long long)gridDim.x * blockDim.x) {
+        const long long env = id / (6 * n_bristle);
+        xdot[env * sd.n_x + sd.nq + sd.nv + (id - env * 6 * n_bristle)] = sdot[id];
     }
 }
 
@@ -178,4 +258,16 @@ cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins
     return cudaGetLastError();
 }
 
+}  // namespace pfc
+
+namespace pfc {
+cudaError_t launch_state_dynamics(const StateDev& sd, const DynDev& dd, long long n_env, int n_ins, int n_bristle, const double* x, const double* wrench,
+                                  const double* tau_ext, const double* sdot, double* xdot, cudaStream_t stream, int* n_launches) {
+    const long long n = n_env * sd.n_body;
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 127) / 128 < 148 * 16 ? (n + 127) / 128 : 148 * 16);
+    state_dynamics_kernel<<<blocks, 128, 0, stream>>>(sd, dd, n_env, n_ins, n_bristle, x, wrench, tau_ext, sdot, xdot);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
 }  // namespace pfc

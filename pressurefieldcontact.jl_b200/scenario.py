@@ -158,6 +158,7 @@ class Body:
     pose_R: np.ndarray = field(default_factory=lambda: np.eye(3))   # joint_pose on the parent body
     pose_t: np.ndarray = field(default_factory=lambda: np.zeros(3))
     parent: int = 0          # index of the parent body (0 = world); bodies are stored parents first
+    i_prop: Optional["InertiaProperties"] = None
 
 
 @dataclass
@@ -193,6 +194,7 @@ class MechanismScenario:
         self.finalized = False
         self.TT_Cache_n_pairs = None
         self.device_kinematics = False
+        self.device_dynamics = False
 
     # state sizes
     @property
@@ -250,6 +252,7 @@ def add_body_contact(m: MechanismScenario, name: str, e_mesh: eMesh, i_prop: Opt
                      c_prop: Optional[ContactProperties] = None, joint=None, tree: Optional[FlatTree] = None, body: Optional[int] = None):
     """add_body_contact! (src/mechanism_scenario.jl:279-289); ``body`` is the parent.  Returns (body, joint, id)."""
     new_body = add_body(m, name, joint, body=body)
+    m.bodies[new_body].i_prop = i_prop      # used by the caller-side dynamics (dynamics.py), not by the contact path
     mesh_id = add_contact(m, name, e_mesh, c_prop=c_prop, body=new_body, tree=tree)
     return new_body, m.bodies[new_body].joint, mesh_id
 
@@ -316,6 +319,17 @@ def attach_backend(m: MechanismScenario, backend, max_env: int = 1) -> None:
         backend.set_bodies([0 if b.joint is None else 1 for b in m.bodies], [b.q0 for b in m.bodies], [b.v0 for b in m.bodies],
                            [mc.body_id for mc in m.MeshCache], m.nq, m.nv, pose=pose)
         m.device_kinematics = True
+        # device-side calcXd! (pfc_set_dynamics) when every floating body carries one mesh with InertiaProperties
+        floating = [k for k, b in enumerate(m.bodies) if b.joint is not None]
+        if hasattr(backend, "set_dynamics") and floating and all(
+                m.bodies[k].i_prop is not None and sum(mc.body_id == k for mc in m.MeshCache) == 1 for k in floating):
+            from . import dynamics as _dyn
+            H = np.zeros((len(m.bodies), 6, 6))
+            for k in floating:
+                mesh = next(mc.mesh for mc in m.MeshCache if mc.body_id == k)
+                H[k] = _dyn.spatial_inertia(*_dyn.make_inertia_info(mesh, m.bodies[k].i_prop)[:3])
+            backend.set_dynamics(H, m.gravity)
+            m.device_dynamics = True
 
 
 # --------------------------------------------------------------------------------------------------

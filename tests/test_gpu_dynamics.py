@@ -1,0 +1,86 @@
+"""GPU tests of the rows that sit AFTER the contact-wrench path in the reference's call stack:
+pfc_calcxd_f64 (calcXd! on the device for floating-body scenes) against the host mirror fed by the CPU oracle, and
+"state parity over N Radau steps" (BASELINE.json configs[0]): the same adaptive Radau IIA integration of test/boxes.jl
+driven once by the CUDA library and once by the CPU oracle, through the same de / Dual-6 Jacobian-chunk interface."""
+import numpy as np
+import pytest
+
+import pfc_b200  # noqa: F401
+from helpers import boxes_env_states, scene_boxes
+from oracle import orc
+from pfc_b200 import dynamics as D
+from pfc_b200 import radau as R
+from pfc_b200 import scenario as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-9
+
+
+def _ctx():
+    from pfc_b200 import capi
+    return capi.Context(0)
+
+
+def test_calcxd_device_matches_host_mirror_with_oracle_contact():
+    """x_dot = [q_dot; v_dot; s_dot] of 256 boxes.jl environments: device (prologue, contact kernels, J' w, 6x6 solves, MRP rates)
+    against calcXd! restated on the host with the oracle's wrenches; each 3-vector of x_dot within 1e-9 of the reference's."""
+    n_env = 256
+    m_gpu = scene_boxes(_ctx(), max_env=n_env)[0]
+    m_cpu = scene_boxes(orc.OracleContext())[0]
+    assert m_gpu.device_dynamics
+    dyn = D.FloatingBodyDynamics(m_cpu)
+    x = boxes_env_states(m_gpu, n_env)
+    out = m_gpu.backend.calcxd_f64(x)
+    ref = np.array([dyn.calcXd(x[e]) for e in range(n_env)])
+    assert (out["flags"] & 1).sum() > n_env
+    for e in range(n_env):
+        for i in range(0, ref.shape[1], 3):
+            den = max(np.abs(ref[e, i:i + 3]).max(), 1e-9 * np.abs(ref[e]).max())
+            assert np.abs(out["xdot"][e, i:i + 3] - ref[e, i:i + 3]).max() <= TOL * den, (e, i)
+    # external generalized forces enter the right-hand side like the controller's tau_ext (sum_all_forces!)
+    rng = np.random.default_rng(5)
+    tau = rng.uniform(-1, 1, (n_env, m_gpu.nv))
+    out_t = m_gpu.backend.calcxd_f64(x, tau)
+    dv = out_t["xdot"][:, m_gpu.nq:] - out["xdot"][:, m_gpu.nq:]
+    for k, b in enumerate(m_cpu.bodies):
+        if b.joint is not None:
+            want = tau[:, b.v0:b.v0 + 6] @ dyn.Hinv[k].T
+            assert np.abs(dv[:, b.v0:b.v0 + 6] - want).max() <= 1e-9 * np.abs(want).max()
+    assert np.array_equal(out_t["xdot"][:, :m_gpu.nq], out["xdot"][:, :m_gpu.nq])
+
+
+def _integrate(backend, x0, n_steps, h_max=0.05):
+    m = scene_boxes(backend)[0]
+    dyn = D.FloatingBodyDynamics(m)
+    rr = R.makeRadauIntegrator(dyn, S.num_x(m), 1.0e-16, 2, 6)
+    rr.step.h_max = h_max
+    ts, xs = R.integrate_radau(rr, x0, t_final=1e9, max_steps=n_steps, after_step=lambda x: D.principal_value(m, x))
+    return ts, xs, rr, m
+
+
+@pytest.mark.parametrize("start", ["drop", "settled"])
+def test_state_parity_over_radau_steps(start):
+    """test/boxes.jl under the reference's integrator, CUDA backend vs oracle backend: the step-size sequences are identical
+    and the integrated states agree within 1e-9 relative (per 3-vector of the state) after every one of N steps.  'drop' is the
+    reference's own initial condition (boxes 3 r apart, spinning; the first contacts happen during the run); 'settled' starts
+    in contact."""
+    m0 = scene_boxes(None)[0]
+    if start == "drop":
+        x0, n_steps = S.get_state(m0), 120
+    else:
+        x0, n_steps = boxes_env_states(m0, 1)[0], 60
+    ts_g, xs_g, rr_g, m_g = _integrate(_ctx(), x0, n_steps)
+    ts_c, xs_c, rr_c, _ = _integrate(orc.OracleContext(), x0, n_steps)
+    assert len(ts_g) == len(ts_c) == n_steps + 1
+    assert (rr_g.n_de_float, rr_g.n_de_chunk) == (rr_c.n_de_float, rr_c.n_de_chunk)
+    assert np.abs(ts_g - ts_c).max() <= 1e-9 * ts_c[-1]
+    worst = 0.0
+    for k in range(1, n_steps + 1):
+        scale = np.abs(xs_c[k]).max()
+        for i in range(0, xs_c.shape[1], 3):
+            den = max(np.abs(xs_c[k, i:i + 3]).max(), 1e-6 * scale)
+            worst = max(worst, np.abs(xs_g[k, i:i + 3] - xs_c[k, i:i + 3]).max() / den)
+    assert worst <= TOL, worst
+    if start == "settled":
+        out = S.force_all_elastic_intersections(m_g, xs_g[-1])
+        assert (out["flags"] & 1).sum() >= 3     # still a stack in contact at the end
