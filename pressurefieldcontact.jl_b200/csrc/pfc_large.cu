@@ -97,9 +97,21 @@ PFC_D void prob_to_ei(const SceneDev& sc, const LargeScene& ls, int p, long long
 
 // Tests one node pair and classifies the outcome: returns the number of children (0, 2, 4) written to
 // ch[], or -1 for a leaf pair (prims in ch[0]); 0 also when the boxes are disjoint.
+// A 128 B node record as four 256-bit loads (sm_100: ld.global.v4.b64).  Every lane gathers its own two records, so each load
+// instruction touches 32 different lines; fewer, wider requests are what the L1 data pipe is short of here.
+PFC_D void load_node(const NodeRec* __restrict__ p, NodeRec& out) {
+    unsigned long long* o = reinterpret_cast<unsigned long long*>(&out);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];"
+                     : "=l"(o[4 * j]), "=l"(o[4 * j + 1]), "=l"(o[4 * j + 2]), "=l"(o[4 * j + 3])
+                     : "l"(reinterpret_cast<const char*>(p) + 32 * j));
+}
+
 PFC_D int expand_pair(const SceneDev& sc, const InsDev& ins, const double* Rab, const double* tab, int ia, int ib, int2* ch) {
-    const NodeRec& a = sc.nodes[ins.node_base1 + ia];
-    const NodeRec& b = sc.nodes[ins.node_base2 + ib];
+    NodeRec a, b;
+    load_node(sc.nodes + ins.node_base1 + ia, a);
+    load_node(sc.nodes + ins.node_base2 + ib, b);
     SatA A;
     sat_prepare_a(a, Rab, tab, A);
     if (!sat_test(A, b)) return 0;
@@ -315,8 +327,11 @@ __global__ void build_keys_kernel(SceneDev sc, LargeScene ls, const int3* __rest
     }
 }
 
-// ---- stable LSD radix sort, 8 bits per pass, one warp per 1024-element tile -------------------------------------
-constexpr int kTile = 1024;
+// ---- stable LSD radix sort, 8 bits per pass, one warp per 512-element tile ---------------------------------------
+// Per pass: (1) per-tile digit histograms, digit-major; (2) one block per digit scans its row of tile counts (exclusive) and
+// leaves the digit total; (3) every tile turns the 256 digit totals into digit bases with a warp scan, adds its row offsets and
+// scatters its keys in order (ranks inside a 32-key chunk from __match_any_sync), so the sort is stable.
+constexpr int kTile = 512;
 __global__ void __launch_bounds__(128) radix_hist_kernel(const unsigned long long* __restrict__ keys, unsigned n, int shift, unsigned* hist, unsigned n_tiles) {
     __shared__ unsigned h[4][256];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -325,62 +340,82 @@ __global__ void __launch_bounds__(128) radix_hist_kernel(const unsigned long lon
     __syncwarp();
     if (tile < n_tiles) {
         const unsigned beg = tile * kTile, end = min(beg + kTile, n);
-        for (unsigned i = beg + lane; i < end; i += 32) atomicAdd(&h[wib][(keys[i] >> shift) & 255u], 1u);
+        unsigned long long k[kTile / 32];
+#pragma unroll
+        for (int j = 0; j < kTile / 32; ++j) { const unsigned i = beg + 32 * j + lane; k[j] = i < end ? keys[i] : 0ull; }   // all loads in flight at once
+#pragma unroll
+        for (int j = 0; j < kTile / 32; ++j) if (beg + 32 * j + lane < end) atomicAdd(&h[wib][(k[j] >> shift) & 255u], 1u);
         __syncwarp();
-        for (int d = lane; d < 256; d += 32) hist[(size_t)d * n_tiles + tile] = h[wib][d];  // digit-major for the scan
+        for (int d = lane; d < 256; d += 32) hist[(size_t)d * n_tiles + tile] = h[wib][d];  // digit-major for the row scans
     }
 }
-// exclusive scan of hist[256 * n_tiles] by one block (n_tiles <= a few thousand)
-__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* hist, unsigned total) {
-    __shared__ unsigned warp_sums[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+// block d: exclusive scan of row d (n_tiles counts) in place, row total -> tot[d]
+__global__ void __launch_bounds__(256) radix_rowscan_kernel(unsigned* hist, unsigned n_tiles, unsigned* tot) {
+    __shared__ unsigned warp_sums[8];
+    __shared__ unsigned carry_s;
+    unsigned* row = hist + (size_t)blockIdx.x * n_tiles;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (unsigned base = 0; base < total; base += 1024) {
-        const unsigned i = base + threadIdx.x;
-        const unsigned v = i < total ? hist[i] : 0;
-        unsigned incl = v;
+    unsigned carry = 0;
+    constexpr int IT = 8;   // consecutive counts per thread
+    for (unsigned base = 0; base < n_tiles; base += 256 * IT) {
+        unsigned v[IT], s = 0;
+#pragma unroll
+        for (int j = 0; j < IT; ++j) { const unsigned i = base + threadIdx.x * IT + j; v[j] = i < n_tiles ? row[i] : 0u; s += v[j]; }
+        unsigned incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         if (lane == 31) warp_sums[w] = incl;
         __syncthreads();
-        if (w == 0) {
-            unsigned s = warp_sums[lane];
+        unsigned before = carry + incl - s, total = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-            warp_sums[lane] = s;  // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned before = carry + (w > 0 ? warp_sums[w - 1] : 0) + incl - v;
-        if (i < total) hist[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        for (int k = 0; k < 8; ++k) { const unsigned t = warp_sums[k]; if (k < w) before += t; total += t; }
+#pragma unroll
+        for (int j = 0; j < IT; ++j) { const unsigned i = base + threadIdx.x * IT + j; if (i < n_tiles) row[i] = before; before += v[j]; }
+        carry += total;
         __syncthreads();
     }
+    if (threadIdx.x == 0) tot[blockIdx.x] = carry;
+    (void)carry_s;
 }
 __global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned n, int shift,
-                                                            const unsigned* __restrict__ hist, unsigned n_tiles, unsigned long long* keys_out, unsigned* vals_out) {
+                                                            const unsigned* __restrict__ hist, const unsigned* __restrict__ tot, unsigned n_tiles,
+                                                            unsigned long long* keys_out, unsigned* vals_out) {
     __shared__ unsigned base[4][256];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned tile = blockIdx.x * 4 + wib;
     if (tile >= n_tiles) return;
-    for (int d = lane; d < 256; d += 32) base[wib][d] = hist[(size_t)d * n_tiles + tile];
+    {   // digit bases: exclusive prefix of the 256 digit totals (lane l owns digits 8 l .. 8 l + 7) + this tile's row offsets
+        unsigned t[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { t[j] = tot[8 * lane + j]; s += t[j]; }
+        unsigned incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        unsigned run = incl - s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { base[wib][8 * lane + j] = run + hist[(size_t)(8 * lane + j) * n_tiles + tile]; run += t[j]; }
+    }
     __syncwarp();
     const unsigned beg = tile * kTile, end = min(beg + kTile, n);
-    for (unsigned c = beg; c < end; c += 32) {  // chunks in order, lanes in order => stable
-        const unsigned i = c + lane;
-        const bool valid = i < end;
-        unsigned long long key = 0; unsigned val = 0; unsigned d = 256 + lane;  // invalid lanes get unique digits
-        if (valid) { key = keys_in[i]; val = vals_in[i]; d = (unsigned)((key >> shift) & 255u); }
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-        unsigned pos = 0;
-        if (valid) pos = base[wib][d] + rank;
-        __syncwarp();
-        if (valid && rank == (unsigned)__popc(peers) - 1) base[wib][d] = pos + 1;  // the last peer advances the digit's cursor
-        __syncwarp();
-        if (valid) { keys_out[pos] = key; vals_out[pos] = val; }
+    constexpr int B = 8;   // chunks whose keys are loaded together (the global-load latency is paid once per batch)
+    for (unsigned c0 = beg; c0 < end; c0 += 32 * B) {
+        unsigned long long kk[B]; unsigned vv[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) { const unsigned i = c0 + 32 * j + lane; const bool ok = i < end; kk[j] = ok ? keys_in[i] : 0ull; vv[j] = ok ? vals_in[i] : 0u; }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {   // chunks in order, lanes in order => stable
+            const unsigned i = c0 + 32 * j + lane;
+            const bool valid = i < end;
+            const unsigned d = valid ? (unsigned)((kk[j] >> shift) & 255u) : 256u + lane;  // invalid lanes get unique digits
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            unsigned pos = 0;
+            if (valid) pos = base[wib][d] + rank;
+            __syncwarp();
+            if (valid && rank == (unsigned)__popc(peers) - 1) base[wib][d] = pos + 1;  // the last peer advances the digit's cursor
+            __syncwarp();
+            if (valid) { keys_out[pos] = kk[j]; vals_out[pos] = vv[j]; }
+        }
     }
 }
 
@@ -756,7 +791,8 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
         LCU(ensure(b->vals[0], b->cap_vals, (size_t)n)); LCU(ensure(b->vals[1], b->cap_vals2, (size_t)n));
         LCU(ensure(b->sorted, b->cap_sorted, (size_t)n));
         const unsigned n_tiles = (n + kTile - 1) / kTile;
-        LCU(ensure(b->hist, b->cap_hist, (size_t)256 * n_tiles));
+        LCU(ensure(b->hist, b->cap_hist, (size_t)256 * n_tiles + 256));   // + the 256 digit totals
+        unsigned* tot = b->hist + (size_t)256 * n_tiles;
         const unsigned g = std::min<unsigned>((n + 255) / 256, (unsigned)n_sm * 16);
         build_keys_kernel<<<g, 256, 0, stream>>>(sc, ls, b->pairs, n, b->keys[0], b->vals[0]);
         int prob_bits = 0;
@@ -765,8 +801,8 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
         int cur = 0;
         for (int shift = 0; shift < total_bits; shift += 8) {
             radix_hist_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], n, shift, b->hist, n_tiles);
-            radix_scan_kernel<<<1, 1024, 0, stream>>>(b->hist, 256u * n_tiles);
-            radix_scatter_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->vals[cur], n, shift, b->hist, n_tiles, b->keys[cur ^ 1], b->vals[cur ^ 1]);
+            radix_rowscan_kernel<<<256, 256, 0, stream>>>(b->hist, n_tiles, tot);
+            radix_scatter_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->vals[cur], n, shift, b->hist, tot, n_tiles, b->keys[cur ^ 1], b->vals[cur ^ 1]);
             cur ^= 1;
             if (n_launches) *n_launches += 3;
         }

@@ -20,6 +20,22 @@ PFC_D double mul_(double a, double b) { return __dmul_rn(a, b); }
 PFC_D double add_(double a, double b) { return __dadd_rn(a, b); }
 PFC_D double sub_(double a, double b) { return __dadd_rn(a, -b); }
 
+// ---- wide gathers -----------------------------------------------------------------------------------------
+// Every lane gathers its own primitive / node record, so one load instruction touches up to 32 different lines and the L1 data
+// pipe pays per request, not per byte (ncu: l1tex__data_pipe_lsu_wavefronts is the busiest unit of the SAT and clip kernels).
+// sm_100 has 256-bit global loads (ld.global.v4.b64): 4x fewer requests than 64-bit loads for the same record.
+// p must be 32 B aligned; N = number of doubles, a multiple of 4.
+template <int N> PFC_D void load_wide(const double* __restrict__ p, double* out) {
+    static_assert(N % 4 == 0, "load_wide moves groups of 4 doubles");
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j) {
+        unsigned long long a, b, c, d;
+        asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p + 4 * j));
+        out[4 * j] = __longlong_as_double((long long)a); out[4 * j + 1] = __longlong_as_double((long long)b);
+        out[4 * j + 2] = __longlong_as_double((long long)c); out[4 * j + 3] = __longlong_as_double((long long)d);
+    }
+}
+
 // ---- Dual<N> ---------------------------------------------------------------------------------------------
 template <int N>
 struct Dual {

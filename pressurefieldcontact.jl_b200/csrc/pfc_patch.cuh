@@ -309,8 +309,10 @@ template <class T> PFC_D bool clip_pair(const SceneDev& sc, const InsDev& ins, i
 // ---- stage A, Float64, polygon kept in the caller's PolyRec slot (shared memory in the tile kernel) --------------------
 // The slot's first 32 doubles hold the polygon in tetrahedral coordinates while it is clipped; the conversion to Cartesian
 // vertices runs forward in place (vertex k lands in doubles [3k, 3k+3), which only overlaps coordinates already consumed).
-PFC_D bool finish_polygon_slot(int n, const TetRec& tet, const Vec3<double>& nrm, PolyRec<double>& out) {
+PFC_D bool finish_polygon_slot(int n, const TetRec& tet_g, const Vec3<double>& nrm, PolyRec<double>& out) {
     double* z = reinterpret_cast<double*>(&out);
+    struct { double v[12]; } tet;
+    load_wide<12>(tet_g.v, tet.v);
     for (int k = 0; k < n; ++k) {  // mul_then_un_pad(x_r2_zeta2, .)
         const double z0 = z[4 * k], z1 = z[4 * k + 1], z2 = z[4 * k + 2], z3 = z[4 * k + 3];
         out.v[k] = mk<double>(tet.v[0] * z0 + tet.v[3] * z1 + tet.v[6] * z2 + tet.v[9] * z3, tet.v[1] * z0 + tet.v[4] * z1 + tet.v[7] * z2 + tet.v[10] * z3,
@@ -331,8 +333,7 @@ PFC_D bool finish_polygon_slot(int n, const TetRec& tet, const Vec3<double>& nrm
     if (cum_sum != 0.0) { const double inv = 1.0 / cum_sum; cen = mk<double>(cum.x * inv, cum.y * inv, cum.z * inv); }
     out.nrm = nrm;
     out.cen = cen;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) out.eps_r[k] = tet.eps_r[k];
+    load_wide<4>(tet_g.eps_r, out.eps_r);
     out.n = n;
     return true;
 }
@@ -341,7 +342,10 @@ PFC_D bool clip_pair_slot(const SceneDev& sc, const InsDev& ins, int prim1, int 
     const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
     double* z = reinterpret_cast<double*>(&out);
     if (ins.kind1 == 0) {
-        const TriRec& tri = sc.tris[ins.prim_base1 + prim1];
+        struct { double v[9]; double n[3]; } tri;          // the whole TriRec (96 B) and the tet's inverse (128 B): 7 wide loads
+        struct { double inv[16]; } t2r;
+        load_wide<12>(sc.tris[ins.prim_base1 + prim1].v, tri.v);
+        load_wide<16>(t2.inv, t2r.inv);
         double zr[3][4];
         unsigned all_non_pos = 0xfu;
 #pragma unroll
@@ -349,7 +353,7 @@ PFC_D bool clip_pair_slot(const SceneDev& sc, const InsDev& ins, int prim1, int 
             const Vec3<double> p = apply_d(cx.x21, mk<double>(tri.v[3 * k], tri.v[3 * k + 1], tri.v[3 * k + 2]));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                zr[k][i] = t2.inv[4 * i] * p.x + t2.inv[4 * i + 1] * p.y + t2.inv[4 * i + 2] * p.z + t2.inv[4 * i + 3];
+                zr[k][i] = t2r.inv[4 * i] * p.x + t2r.inv[4 * i + 1] * p.y + t2r.inv[4 * i + 2] * p.z + t2r.inv[4 * i + 3];
                 if (!(zr[k][i] <= 0.0)) all_non_pos &= ~(1u << i);
             }
         }

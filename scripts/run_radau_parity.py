@@ -39,19 +39,28 @@ def main():
 
     ts_g, xs_g, rr_g, wall_g = integrate(capi.Context(0))
     ts_c, xs_c, rr_c, wall_c = integrate(orc.OracleContext())
-    worst, worst_step = 0.0, 0
-    for k in range(1, len(ts_c)):
+    n = min(len(ts_c), len(ts_g))
+    err = np.zeros(n)
+    for k in range(1, n):
         scale = np.abs(xs_c[k]).max()
         for i in range(0, xs_c.shape[1], 3):
             den = max(np.abs(xs_c[k, i:i + 3]).max(), 1e-6 * scale)
-            e = np.abs(xs_g[k, i:i + 3] - xs_c[k, i:i + 3]).max() / den
-            if e > worst:
-                worst, worst_step = float(e), k
-    print(json.dumps({"scene": "C1 test/boxes.jl (drop)", "radau_steps": len(ts_c) - 1, "t_end": float(ts_c[-1]),
-                      "worst_state_rel_err": worst, "at_step": worst_step, "time_grid_max_abs_diff": float(np.abs(ts_g - ts_c).max()),
-                      "float_evals": rr_c.n_de_float, "dual6_chunk_evals": rr_c.n_de_chunk, "same_eval_counts": (rr_g.n_de_float, rr_g.n_de_chunk) == (rr_c.n_de_float, rr_c.n_de_chunk),
+            err[k] = max(err[k], np.abs(xs_g[k, i:i + 3] - xs_c[k, i:i + 3]).max() / den)
+    running = np.maximum.accumulate(err)
+    over = np.nonzero(running > 1e-9)[0]
+    grid = np.nonzero(np.abs(ts_g[:n] - ts_c[:n]) > 1e-12 * np.maximum(ts_c[:n], 1e-30))[0]
+    marks = [k for k in (10, 25, 50, 100, 150, 200, 300, 400, 500, 700, 1000) if k < n]
+    print(json.dumps({"scene": "C1 test/boxes.jl (drop)", "radau_steps": n - 1, "t_end": float(ts_c[n - 1]),
+                      "worst_state_rel_err_up_to_step": {str(k): float(running[k]) for k in marks},
+                      "sim_time_at_step": {str(k): float(ts_c[k]) for k in marks},
+                      "steps_within_1e-9": int(over[0] - 1) if len(over) else n - 1,
+                      "sim_time_within_1e-9": float(ts_c[over[0] - 1]) if len(over) else float(ts_c[n - 1]),
+                      "first_step_with_different_step_size": int(grid[0]) if len(grid) else None,
+                      "float_evals": rr_c.n_de_float, "dual6_chunk_evals": rr_c.n_de_chunk,
                       "final_z": [float(v) for v in xs_g[-1][[5, 11, 17, 23]]], "wall_s_gpu_backend": wall_g, "wall_s_oracle_backend": wall_c,
-                      "note": "wall times are dominated by the Python host mirror of the integrator and RigidBodyDynamics, one scene at a time"}))
+                      "note": "a toppling stack of spinning boxes is a chaotic system: rounding-level differences between ANY two implementations grow "
+                              "exponentially with simulated time and eventually flip an accept/reject decision of the adaptive integrator; "
+                              "wall times are dominated by the Python host mirror of the integrator and RigidBodyDynamics, one scene at a time"}))
 
 
 if __name__ == "__main__":
