@@ -209,7 +209,8 @@ def main():
     f_p = torch.zeros((n_env, m.nv), dtype=torch.float64).pin_memory()
 
     def step_e2e():
-        ctx.eval_state_f64_ptr(n_env, x_p.data_ptr(), f_p.data_ptr(), None, np_p.data_ptr(), fl_p.data_ptr())
+        # the result a caller of forceAllElasticIntersections! gets back is f_generalized; pair counts / flags are debug outputs (not requested)
+        ctx.eval_state_f64_ptr(n_env, x_p.data_ptr(), f_p.data_ptr(), None, None, None)
 
     def barrier():
         if world > 1:
@@ -322,7 +323,7 @@ def main():
     cpu_mt = cpu_sample * 5 / (time.perf_counter() - t0)
 
     h2d = int(m.x_all.nbytes)
-    d2h = int(f_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
+    d2h = int(f_p.numel() * 8 + 4)   # generalized forces + the 4-byte error status word
     h2d_b = int(X_h.nbytes + tw_h.nbytes)
     d2h_b = int(w_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
     line = {
@@ -334,7 +335,7 @@ def main():
                    "l2": "256 MiB flush between timed steps", "parallelism": f"env-sharded x{world}, no collective"},
         "candidate_pairs_per_sec": pairs_per_eval * value,
         "e2e": {"value": evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "pfc_eval_state_f64: pinned host states x[env][48] in, generalized forces f[env][24] + n_pairs + flags out; "
+                "api": "pfc_eval_state_f64: pinned host states x[env][48] in, generalized forces f[env][24] (+ a 4-byte error status) out; "
                        "kinematics prologue and J' w epilogue on the device",
                 "boundary_level": {"value": evals / e2e_b_s, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                                    "ms_per_step": e2e_b_s / args.steps * 1e3, "api": "pfc_eval_f64: X_r2_r1 + twist in, wrenches out (host kinematics not timed)"}},

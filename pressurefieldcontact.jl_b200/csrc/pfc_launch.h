@@ -62,10 +62,12 @@ struct DynDev {
     double gravity[3];
 };
 cudaError_t launch_state_dynamics(const StateDev& sd, const DynDev& dd, long long n_env, int n_ins, int n_bristle, const double* x, const double* wrench,
-                                  const double* tau_ext, const double* sdot, double* xdot, cudaStream_t stream, int* n_launches);
+                                  const double* tau_ext, const double* sdot, double* xdot, cudaStream_t stream, int* n_launches,
+                                  const int* flags = nullptr, int* status = nullptr);
 cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, double* X, double* twist, double* s,
                                   cudaStream_t stream, int* n_launches);
+// flags / status (optional): OR the error bits of flags[n_env * n_ins] into *status (see or_error_flags)
 cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
-                                  int* n_launches);
+                                  int* n_launches, const int* flags = nullptr, int* status = nullptr);
 
 }  // namespace pfc

@@ -115,6 +115,16 @@ __global__ void __launch_bounds__(128) state_prologue_kernel(StateDev sd, long l
     }
 }
 
+// The error bits of the per-(environment, instruction) flags, OR-ed into one device word: the host-pointer entry points read
+// 4 bytes back instead of the whole flag array when the caller does not ask for it.
+PFC_D void or_error_flags(const int* __restrict__ flags, long long n, int* __restrict__ status) {
+    if (!status) return;
+    int bad = 0;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x)
+        bad |= flags[id] & (kFlagNonFinite | kFlagOverflow);
+    if (bad) atomicOr(status, bad);
+}
+
 // J' w of every instruction that touches body b (addGeneralizedForcesThirdLaw!), summed in instruction order
 PFC_D void body_generalized_force(const StateDev& sd, int b, const Frame& fb, const double* __restrict__ q, const double* __restrict__ wrench_env, double* fa, double* fl) {
 #pragma unroll
@@ -145,7 +155,9 @@ PFC_D void body_generalized_force(const StateDev& sd, int b, const Frame& fb, co
 
 // one thread per (environment, body)
 __global__ void __launch_bounds__(128) state_epilogue_kernel(StateDev sd, long long n_env, int n_ins, const double* __restrict__ x,
-                                                             const double* __restrict__ wrench, double* __restrict__ f_gen) {
+                                                             const double* __restrict__ wrench, double* __restrict__ f_gen,
+                                                             const int* __restrict__ flags, int* __restrict__ status) {
+    or_error_flags(flags, n_env * n_ins, status);
     const long long n = n_env * sd.n_body;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
         const long long env = id / sd.n_body;
@@ -170,7 +182,9 @@ __global__ void __launch_bounds__(128) state_epilogue_kernel(StateDev sd, long l
 // and one extra pass copies s_dot behind [q_dot; v_dot] (copyto!, src/extensions.jl:40-50).
 __global__ void __launch_bounds__(128) state_dynamics_kernel(StateDev sd, DynDev dd, long long n_env, int n_ins, int n_bristle, const double* __restrict__ x,
                                                              const double* __restrict__ wrench, const double* __restrict__ tau_ext,
-                                                             const double* __restrict__ sdot, double* __restrict__ xdot) {
+                                                             const double* __restrict__ sdot, double* __restrict__ xdot,
+                                                             const int* __restrict__ flags, int* __restrict__ status) {
+    or_error_flags(flags, n_env * n_ins, status);
     const long long n = n_env * sd.n_body;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
         const long long env = id / sd.n_body;
@@ -249,11 +263,11 @@ cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins
 }
 
 cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
-                                  int* n_launches) {
+                                  int* n_launches, const int* flags, int* status) {
     const long long n = n_env * sd.n_body;
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 127) / 128 < 148 * 16 ? (n + 127) / 128 : 148 * 16);
-    state_epilogue_kernel<<<blocks, 128, 0, stream>>>(sd, n_env, n_ins, x, wrench, f_gen);
+    state_epilogue_kernel<<<blocks, 128, 0, stream>>>(sd, n_env, n_ins, x, wrench, f_gen, flags, status);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
@@ -262,11 +276,11 @@ cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins
 
 namespace pfc {
 cudaError_t launch_state_dynamics(const StateDev& sd, const DynDev& dd, long long n_env, int n_ins, int n_bristle, const double* x, const double* wrench,
-                                  const double* tau_ext, const double* sdot, double* xdot, cudaStream_t stream, int* n_launches) {
+                                  const double* tau_ext, const double* sdot, double* xdot, cudaStream_t stream, int* n_launches, const int* flags, int* status) {
     const long long n = n_env * sd.n_body;
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 127) / 128 < 148 * 16 ? (n + 127) / 128 : 148 * 16);
-    state_dynamics_kernel<<<blocks, 128, 0, stream>>>(sd, dd, n_env, n_ins, n_bristle, x, wrench, tau_ext, sdot, xdot);
+    state_dynamics_kernel<<<blocks, 128, 0, stream>>>(sd, dd, n_env, n_ins, n_bristle, x, wrench, tau_ext, sdot, xdot, flags, status);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
