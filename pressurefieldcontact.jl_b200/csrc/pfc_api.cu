@@ -772,6 +772,94 @@ int pfc_eval_state_f64(pfc_ctx* c, int64_t n_env, const double* x, double* f_gen
     return status_end(c, n_env);
 }
 
+// inverse of a symmetric positive definite 6x6 by Cholesky (what the reference does per evaluation with cholesky!/ldiv!)
+static bool spd6_inverse(const double* H, double* inv) {
+    double L[36] = {0};
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double a = H[6 * i + j];
+            for (int k = 0; k < j; ++k) a -= L[6 * i + k] * L[6 * j + k];
+            if (i == j) { if (!(a > 0.0)) return false; L[6 * i + i] = std::sqrt(a); }
+            else L[6 * i + j] = a / L[6 * j + j];
+        }
+    for (int c = 0; c < 6; ++c) {   // solve L L' x = e_c
+        double y[6], x[6];
+        for (int i = 0; i < 6; ++i) { double a = (i == c) ? 1.0 : 0.0; for (int k = 0; k < i; ++k) a -= L[6 * i + k] * y[k]; y[i] = a / L[6 * i + i]; }
+        for (int i = 5; i >= 0; --i) { double a = y[i]; for (int k = i + 1; k < 6; ++k) a -= L[6 * k + i] * x[k]; x[i] = a / L[6 * i + i]; }
+        for (int i = 0; i < 6; ++i) inv[6 * i + c] = x[i];
+    }
+    return true;
+}
+
+int pfc_set_dynamics(pfc_ctx* c, int n_body, const double* spatial_inertia, const double* gravity) {
+    if (!c || !c->has_bodies) return fail(PFC_E_ARG, "pfc_set_dynamics: call after pfc_set_bodies");
+    if (n_body != c->state.n_body || !spatial_inertia || !gravity) return fail(PFC_E_ARG, "pfc_set_dynamics: bad argument");
+    std::vector<double> H(36 * size_t(n_body), 0.0), Hi(36 * size_t(n_body), 0.0);
+    for (int b = 0; b < n_body; ++b) {
+        if (c->h_bodies[b].joint == 0) continue;
+        for (int i = 0; i < 36; ++i) H[36 * b + i] = spatial_inertia[36 * b + i];
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < i; ++j)
+                if (std::fabs(H[36 * b + 6 * i + j] - H[36 * b + 6 * j + i]) > 1e-12 * (std::fabs(H[36 * b + 6 * i + i]) + std::fabs(H[36 * b + 6 * j + j])))
+                    return fail(PFC_E_ARG, "pfc_set_dynamics: spatial inertia is not symmetric");
+        if (!spd6_inverse(&H[36 * b], &Hi[36 * b])) return fail(PFC_E_ARG, "pfc_set_dynamics: spatial inertia is not positive definite");
+    }
+    CU(cudaSetDevice(c->device));
+    CU(c->d_H.ensure(H.size())); CU(c->d_Hinv.ensure(Hi.size()));
+    CU(cudaMemcpy(c->d_H.p, H.data(), sizeof(double) * H.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_Hinv.p, Hi.data(), sizeof(double) * Hi.size(), cudaMemcpyHostToDevice));
+    c->dyn.H = c->d_H.p; c->dyn.Hinv = c->d_Hinv.p;
+    for (int i = 0; i < 3; ++i) c->dyn.gravity[i] = gravity[i];
+    c->has_dynamics = true;
+    return PFC_OK;
+}
+
+static int calcxd_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* xdot, long long* n_pairs, int* flags, int* status = nullptr) {
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
+    CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni));
+    if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_sd.ensure(6 * ne * nb)); }
+    int nl = 0;
+    CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), x, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
+    EvalIO io{};
+    io.n_env = n_env; io.X = c->d_X.p; io.twist = c->d_tw.p; io.s = nb ? c->d_s.p : nullptr; io.wrench = c->d_w.p;
+    io.sdot = nb ? c->d_sd.p : nullptr; io.n_pairs = n_pairs; io.flags = flags;
+    int rc = eval_device(c, io);
+    if (rc != PFC_OK) return rc;
+    CU(launch_state_dynamics(c->state, c->dyn, n_env, int(ni), int(nb), x, c->d_w.p, tau_ext, nb ? c->d_sd.p : nullptr, xdot, c->stream, &nl, flags, status));
+    c->launches += nl;
+    return PFC_OK;
+}
+
+int pfc_calcxd_f64_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_f64_device: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
+    if (n_env < 0 || !x || !xdot || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_calcxd_f64_device: NULL buffer");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    return calcxd_device(c, n_env, x, tau_ext, xdot, reinterpret_cast<long long*>(n_pairs), flags);
+}
+
+int pfc_calcxd_f64(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_f64: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
+    if (n_env < 0 || !x || !xdot) return fail(PFC_E_ARG, "pfc_calcxd_f64: NULL buffer");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
+    CU(c->d_x.ensure(ne * nx)); CU(c->d_xdot.ensure(ne * nx)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+    CU(cudaMemcpyAsync(c->d_x.p, x, sizeof(double) * ne * nx, cudaMemcpyHostToDevice, c->stream));
+    if (tau_ext) {
+        CU(c->d_tau.ensure(std::max<size_t>(ne * nv, 1)));
+        CU(cudaMemcpyAsync(c->d_tau.p, tau_ext, sizeof(double) * ne * nv, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemsetAsync(c->d_xdot.p, 0, sizeof(double) * ne * nx, c->stream));
+    CU(status_begin(c));
+    int rc = calcxd_device(c, n_env, c->d_x.p, tau_ext ? c->d_tau.p : nullptr, c->d_xdot.p, c->d_np.p, c->d_fl.p, c->d_status.p);
+    if (rc != PFC_OK) return rc;
+    CU(cudaMemcpyAsync(xdot, c->d_xdot.p, sizeof(double) * ne * nx, cudaMemcpyDeviceToHost, c->stream));
+    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    if (flags) CU(cudaMemcpyAsync(flags, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    return status_end(c, n_env);
+}
+
 int pfc_get_boundary(pfc_ctx* c, int64_t n_env, double* X, double* twist, double* wrench) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_get_boundary: context not finalized");
     const size_t n = size_t(n_env) * size_t(c->scene.n_ins);
