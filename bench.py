@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # DRAM traffic of one narrow_tile_kernel launch on the 4096-environment workload, from the committed ncu capture
-NARROW_TRAFFIC_BYTES = 7568384 + 80384
+NARROW_TRAFFIC_BYTES = 6964480 + 28672   # profiles/r1_v10_narrow_tile_ncu.txt
 
 METRIC = "contact_wrench_evals_per_sec"
 UNIT = "evals/s"
@@ -113,6 +113,58 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
+def measure_large_scenes(device_index):
+    """Secondary numbers (not the headline): the metric's second half, candidate pairs per second, on the two single-large-scene
+    configurations -- C4 (sphere on slab, tet-tet, ~2 x 100 k tets) and C5 (64-body pile, ~0.9 M candidate tri-tet pairs per
+    evaluation).  Device-resident inputs, CUDA events on the library's stream, one environment, no L2 flush (the static scene is meant
+    to be L2-resident).  Traversal + compaction are reported against the measured HBM peak with SURVEY 8d's algorithmic bytes
+    (272 B per node pair visited, 12 B per pair emitted)."""
+    import torch
+    from pfc_b200 import capi, scenes
+    from pfc_b200 import scenario as S
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+    except Exception:
+        hbm_peak = 6650.0
+    out = {}
+    dev = torch.device("cuda", device_index)
+    for name, build in (("C4", lambda: scenes.scene_c4_sphere_on_slab(71, 79)), ("C5", lambda: scenes.scene_c5_pile(4, 24))):
+        try:
+            m, x = build()
+            ctx = capi.Context(device_index)
+            S.attach_backend(m, ctx)
+            X, tw, _ = S.boundary_arrays(m, x)
+            n_ins = ctx.n_ins
+            Xd, twd = torch.from_numpy(X).to(dev), torch.from_numpy(tw).to(dev)
+            w = torch.zeros((1, n_ins, 6), dtype=torch.float64, device=dev)
+            npairs = torch.zeros((1, n_ins), dtype=torch.int64, device=dev)
+            fl = torch.zeros((1, n_ins), dtype=torch.int32, device=dev)
+            stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+            step = lambda: ctx.eval_f64_device(1, Xd.data_ptr(), twd.data_ptr(), None, w.data_ptr(), None, npairs.data_ptr(), fl.data_ptr())
+            for _ in range(3):
+                step()
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0, reps = ctx.launch_count(), 10
+            e0.record(stream)
+            for _ in range(reps):
+                step()
+            e1.record(stream)
+            ctx.sync()
+            ms = e0.elapsed_time(e1) / reps
+            n_tests, n_pairs = ctx.counters()
+            gbs = (272 * n_tests + 12 * n_pairs) / (ms * 1e-3) * 1e-9
+            out[name] = {"ms_per_eval": ms, "candidate_pairs": int(n_pairs), "node_pairs_tested": int(n_tests), "instructions": n_ins,
+                         "candidate_pairs_per_sec": n_pairs / (ms * 1e-3), "contacts": int((fl.cpu().numpy() & 1).sum()),
+                         "kernel_launches_per_eval": int((ctx.launch_count() - l0) // reps),
+                         "broad_phase_roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                                  "bytes": "272 B per node pair visited + 12 B per pair emitted (SURVEY 8d); the scene is L2-resident"}}
+            ctx.close()
+        except Exception as exc:   # secondary measurement: never take the headline down with it
+            out[name] = {"error": repr(exc)}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia
     (not installable here, no Julia in the image), so this arm times the CPU oracle -- a literal C++
@@ -155,6 +207,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--impl", default="pfc", choices=["pfc", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-large", action="store_true", help="skip the secondary single-large-scene measurements (C4 / C5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -326,6 +379,7 @@ def main():
     d2h = int(f_p.numel() * 8 + 4)   # generalized forces + the 4-byte error status word
     h2d_b = int(X_h.nbytes + tw_h.nbytes)
     d2h_b = int(w_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
+    large = None if args.no_large else measure_large_scenes(local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -342,7 +396,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": narrow_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": narrow_tflops / fp64_peak if fp64_peak else None, "traffic": NARROW_TRAFFIC_BYTES,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_v5_small_kernels.md)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_v10_narrow_tile_ncu.txt)",
                      "kernel": "narrow_tile_kernel (clip + quadrature + friction + fixed-order sums), the dominant kernel of the step",
                      "kernel_ms": narrow_ms, "kernel_share_of_step": narrow_ms / (narrow_ms + broad_ms),
                      "flops_per_launch": work["flops_narrow"] / n_count * n_env,
@@ -360,6 +414,8 @@ def main():
                          "all_cores": {"value": cpu_mt, "cores": cores}},
         "clocks": clocks.summary(),
     }
+    if large is not None:
+        line["large_scenes"] = large
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
