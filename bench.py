@@ -379,6 +379,25 @@ def main():
     d2h = int(f_p.numel() * 8 + 4)   # generalized forces + the 4-byte error status word
     h2d_b = int(X_h.nbytes + tw_h.nbytes)
     d2h_b = int(w_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
+    # secondary: the Jacobian mode the integrator needs once per step (SURVEY 8d "Jacobian-chunk evals/s"): one Dual-6 chunk of calcXd!
+    # for the whole batch through pfc_calcxd_dual6, host buffers in and out (x in, x_dot + 6 partials out)
+    jac = None
+    try:
+        if getattr(m, "device_dynamics", False):
+            xd7 = np.zeros((n_env, m.x_all.shape[1], 7))
+            npj, flj = np.zeros((n_env, n_ins), np.int64), np.zeros((n_env, n_ins), np.int32)
+            lib = capi.lib()
+            call = lambda seed: capi._check(lib.pfc_calcxd_dual6(ctx._h, n_env, m.x_all.ctypes.data, None, seed, xd7.ctypes.data, npj.ctypes.data, flj.ctypes.data))
+            call(0)
+            t0 = time.perf_counter()
+            reps = 8
+            for k in range(reps):
+                call(6 * k)
+            dtj = (time.perf_counter() - t0) / reps
+            jac = {"value": n_env / dtj, "unit": "Dual-6 chunk evals/s", "ms_per_chunk_batch": dtj * 1e3, "api": "pfc_calcxd_dual6, pageable host buffers",
+                   "chunks_per_radau_step": int(np.ceil(m.x_all.shape[1] / 6))}
+    except Exception as exc:
+        jac = {"error": repr(exc)}
     large = None if args.no_large else measure_large_scenes(local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -414,6 +433,8 @@ def main():
                          "all_cores": {"value": cpu_mt, "cores": cores}},
         "clocks": clocks.summary(),
     }
+    if jac is not None:
+        line["jacobian_chunks"] = jac
     if large is not None:
         line["large_scenes"] = large
     print(json.dumps(line))

@@ -112,6 +112,12 @@ int pfc_set_dynamics(pfc_ctx* ctx, int n_body, const double* spatial_inertia, co
 int pfc_calcxd_f64(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags);
 /* Same on device buffers, asynchronous on the context's stream (xdot must be zero-initialised for world-attached coordinates). */
 int pfc_calcxd_f64_device(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags);
+/* calcXd! in Jacobian mode (Vector{Dual{Nothing,Float64,6}}: calcJacobian!, src/radau/radau_functions.jl:2-26) for the same scenes.
+ * x[env][n_x] are Float64 states; the 6 Dual seeds sit on x[seed_start .. seed_start + 6) (seed_indices!, :16-26).  xdot7[env][n_x][7] =
+ * value followed by the partials d xdot / d x[seed_start + k], k = 0..5 (write_indices!, :28-42, takes its columns of -J from them).
+ * The candidate pairs come from the Float64 state, like the reference (:94-101).  Host pointers; tau_ext / n_pairs / flags may be NULL. */
+int pfc_calcxd_dual6(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
+                     int32_t* flags);
 /* Debug / parity: the boundary arrays (X_r2_r1, twist_r2) the prologue computed and the per-instruction wrenches of the last
  * host-pointer evaluation; any pointer may be NULL. */
 int pfc_get_boundary(pfc_ctx* ctx, int64_t n_env, double* X_r2_r1, double* twist_r2, double* wrench_r2);

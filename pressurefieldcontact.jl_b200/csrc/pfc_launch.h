@@ -66,6 +66,12 @@ cudaError_t launch_state_dynamics(const StateDev& sd, const DynDev& dd, long lon
                                   const int* flags = nullptr, int* status = nullptr);
 cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, double* X, double* twist, double* s,
                                   cudaStream_t stream, int* n_launches);
+// Jacobian mode of the same kernels (Dual<6>, seeds on x[seed0 .. seed0 + 6)): every output scalar is 7 doubles (value, 6 partials)
+cudaError_t launch_state_prologue_dual6(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, int seed0, double* X7, double* twist7,
+                                        double* s7, cudaStream_t stream, int* n_launches);
+cudaError_t launch_state_dynamics_dual6(const StateDev& sd, const DynDev& dd, long long n_env, int n_ins, int n_bristle, const double* x, int seed0,
+                                        const double* wrench7, const double* tau_ext, const double* sdot7, double* xdot7, cudaStream_t stream,
+                                        int* n_launches, const int* flags = nullptr, int* status = nullptr);
 // flags / status (optional): OR the error bits of flags[n_env * n_ins] into *status (see or_error_flags)
 cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
                                   int* n_launches, const int* flags = nullptr, int* status = nullptr);

@@ -87,10 +87,15 @@ class FloatingBodyDynamics:
     """The ODE right-hand side x -> [q_dot; v_dot; s_dot] of a MechanismScenario whose bodies all float on the
     world (the reference's calcXd!), with the contact wrenches evaluated by m.backend."""
 
-    def __init__(self, m):
+    def __init__(self, m, device: bool = False):
+        """device=True: x_dot and its Jacobian chunks come from pfc_calcxd_f64 / pfc_calcxd_dual6 (everything on the GPU);
+        device=False: rigid-body terms on the host (this class), contact wrenches from m.backend at the boundary level."""
         if m.backend is None:
             raise RuntimeError("finalize(m, backend=...) first")
+        if device and not getattr(m, "device_dynamics", False):
+            raise RuntimeError("device=True needs a CUDA backend with pfc_set_dynamics (floating bodies with InertiaProperties)")
         self.m = m
+        self.device = device
         self.bodies = [b for b in m.bodies if b.joint is not None]
         for b in self.bodies:
             if not (isinstance(b.joint, S.SPQuatFloating) and b.parent == 0 and np.array_equal(b.pose_R, np.eye(3)) and not b.pose_t.any()):
@@ -151,6 +156,9 @@ class FloatingBodyDynamics:
 
     def calcXd(self, x, t: float = 0.0):
         x = np.asarray(x, dtype=np.float64)
+        if self.device:
+            self.n_float += 1
+            return self.m.backend.calcxd_f64(x)["xdot"][0]
         out = S.force_all_elastic_intersections(self.m, x)
         self.n_float += 1
         return self._assemble(x, out["wrench"], out["sdot"])
@@ -167,6 +175,10 @@ class FloatingBodyDynamics:
             raise ValueError("the device evaluates Jacobian chunks of 6 seeds (Dual{Nothing,Float64,6})")
         m = self.m
         x = np.asarray(x, dtype=np.float64)
+        if self.device:
+            self.n_chunk += 1
+            xd7 = m.backend.calcxd_dual6(x, i0)["xdot7"][0]
+            return xd7[:, 0].copy(), xd7[:, 1:1 + (i1 - i0)].copy()
         X0, X7, tw7, s7 = S.boundary_arrays_dual6(m, x, i0)
         out = m.backend.eval_dual6(X0, X7, tw7, s7 if m.n_bristle else None)
         self.n_chunk += 1

@@ -49,9 +49,31 @@ def test_calcxd_device_matches_host_mirror_with_oracle_contact():
     assert np.array_equal(out_t["xdot"][:, :m_gpu.nq], out["xdot"][:, :m_gpu.nq])
 
 
-def _integrate(backend, x0, n_steps, h_max=0.05):
+def test_calcxd_dual6_device_matches_host_mirror_with_oracle_contact():
+    """Jacobian chunks d x_dot / d x[6k : 6k + 6] of 16 boxes.jl environments, everything on the device (Dual-6 prologue, contact,
+    J' w, rigid-body terms), against the host mirror (complex-step rigid-body terms + the oracle's Dual-6 wrenches)."""
+    n_env = 16
+    m_gpu = scene_boxes(_ctx(), max_env=n_env)[0]
+    m_cpu = scene_boxes(orc.OracleContext())[0]
+    dyn = D.FloatingBodyDynamics(m_cpu)
+    x = boxes_env_states(m_gpu, n_env)
+    nx = S.num_x(m_gpu)
+    for i0 in range(0, nx, 6):
+        out = m_gpu.backend.calcxd_dual6(x, i0)
+        for e in range(n_env):
+            xx0, cols = dyn.de_jacobian_chunk(x[e], i0, i0 + 6)
+            g = out["xdot7"][e]
+            for i in range(0, nx, 3):
+                den = max(np.abs(xx0[i:i + 3]).max(), 1e-9 * np.abs(xx0).max())
+                assert np.abs(g[i:i + 3, 0] - xx0[i:i + 3]).max() <= TOL * den
+            for d in range(6):   # column by column: ||delta||_inf <= 1e-9 ||column||_inf (+ a floor for columns that vanish)
+                col = cols[:, d]
+                assert np.abs(g[:, 1 + d] - col).max() <= TOL * max(np.abs(col).max(), 1e-6 * np.abs(cols).max()), (i0, e, d)
+
+
+def _integrate(backend, x0, n_steps, h_max=0.05, device=False):
     m = scene_boxes(backend)[0]
-    dyn = D.FloatingBodyDynamics(m)
+    dyn = D.FloatingBodyDynamics(m, device=device)
     rr = R.makeRadauIntegrator(dyn, S.num_x(m), 1.0e-16, 2, 6)
     rr.step.h_max = h_max
     ts, xs = R.integrate_radau(rr, x0, t_final=1e9, max_steps=n_steps, after_step=lambda x: D.principal_value(m, x))
@@ -69,7 +91,7 @@ def test_state_parity_over_radau_steps(start):
         x0, n_steps = S.get_state(m0), 120
     else:
         x0, n_steps = boxes_env_states(m0, 1)[0], 60
-    ts_g, xs_g, rr_g, m_g = _integrate(_ctx(), x0, n_steps)
+    ts_g, xs_g, rr_g, m_g = _integrate(_ctx(), x0, n_steps, device=(start == "drop"))   # 'drop': calcXd! and its Jacobian entirely on the device
     ts_c, xs_c, rr_c, _ = _integrate(orc.OracleContext(), x0, n_steps)
     assert len(ts_g) == len(ts_c) == n_steps + 1
     assert (rr_g.n_de_float, rr_g.n_de_chunk) == (rr_c.n_de_float, rr_c.n_de_chunk)
