@@ -151,4 +151,63 @@ function calcXd_gpu!(xx::AbstractVector{T}, x::AbstractVector{T}, m::MechanismSc
     return nothing
 end
 
+# --- batched roll-outs of floating-body scenes: states in, x_dot (and Jacobian chunks) out, no host RigidBodyDynamics in the loop ---------
+"""
+    finalize_floating_gpu!(m)
+
+After `finalize_gpu!`: describes the mechanism to the device (`pfc_set_bodies`, `pfc_set_dynamics`).  Every non-root body must sit on an
+`SPQuatFloating` joint attached to the world (what `add_body_contact!` creates by default, src/mechanism_scenario.jl:279-289).
+"""
+function finalize_floating_gpu!(m::MechanismScenario)
+    ctx = CTX[m]
+    mech = m.float.state.mechanism
+    bs = collect(bodies(mech))
+    nb = length(bs)
+    jt = zeros(Int32, nb); q0 = zeros(Int32, nb); v0 = zeros(Int32, nb); pose = zeros(Float64, 12, nb); H = zeros(Float64, 36, nb)
+    for (k, b) in enumerate(bs)
+        pose[[1, 5, 9], k] .= 1.0
+        isroot(b, mech) && continue
+        j = joint_to_parent(b, mech)
+        (joint_type(j) isa SPQuatFloating && isroot(predecessor(j, mech), mech)) || error("finalize_floating_gpu!: only SPQuatFloating joints on the world")
+        jt[k] = 1
+        q0[k] = first(parentindexes(configuration(m.float.state, j))[1]) - 1
+        v0[k] = first(parentindexes(velocity(m.float.state, j))[1]) - 1
+        tf = joint_to_predecessor(j)                                         # joint pose on the world: R row-major, then t
+        pose[1:9, k] .= vec(transpose(rotation(tf))); pose[10:12, k] .= translation(tf)
+        I = spatial_inertia(b)                                               # about the body origin, body frame
+        c = I.cross_part; cx = [0 -c[3] c[2]; c[3] 0 -c[1]; -c[2] c[1] 0]
+        H[:, k] .= vec(transpose([Matrix(I.moment) cx; transpose(cx) I.mass * Matrix(1.0LinearAlgebra.I, 3, 3)]))
+    end
+    mesh_body = Int32[findfirst(b -> BodyID(b) == m.MeshCache[id].BodyID, bs) - 1 for id in m.mesh_ids]
+    nq, nv = num_positions(mech), num_velocities(mech)
+    GC.@preserve jt q0 v0 pose mesh_body check(ccall((:pfc_set_bodies, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Cint, Cint), ctx, nb, jt, q0, v0, pose, mesh_body, nq, nv))
+    g = Vector{Float64}(mech.gravitational_acceleration.v)
+    GC.@preserve H g check(ccall((:pfc_set_dynamics, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), ctx, nb, H, g))
+    return nothing
+end
+
+"forceAllElasticIntersections! for a batch of states `x[:, env]`: generalized forces `f[:, env]` and `sdot` (pfc_eval_state_f64)."
+function force_all_batch_gpu!(f::Matrix{Float64}, sdot::Matrix{Float64}, m::MechanismScenario, x::Matrix{Float64})
+    GC.@preserve x f sdot check(ccall((:pfc_eval_state_f64, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+        CTX[m], size(x, 2), x, f, isempty(sdot) ? C_NULL : pointer(sdot), C_NULL, C_NULL))
+    return nothing
+end
+
+"calcXd! for a batch of states `x[:, env]` entirely on the device (pfc_calcxd_f64)."
+function calcXd_batch_gpu!(xx::Matrix{Float64}, m::MechanismScenario, x::Matrix{Float64})
+    GC.@preserve x xx check(ccall((:pfc_calcxd_f64, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}), CTX[m], size(x, 2), x, C_NULL, xx, C_NULL, C_NULL))
+    return nothing
+end
+
+"One Jacobian chunk of calcXd! for a batch: `xx7[1, i, env]` = x_dot[i], `xx7[1 + k, i, env]` = d x_dot[i] / d x[seed + k] (seed is 1-based here)."
+function calcXd_chunk_batch_gpu!(xx7::Array{Float64,3}, m::MechanismScenario, x::Matrix{Float64}, seed::Integer)
+    GC.@preserve x xx7 check(ccall((:pfc_calcxd_dual6, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+        CTX[m], size(x, 2), x, C_NULL, seed - 1, xx7, C_NULL, C_NULL))
+    return nothing
+end
+
 end # module
