@@ -118,6 +118,10 @@ int pfc_calcxd_f64_device(pfc_ctx* ctx, int64_t n_env, const double* x, const do
  * The candidate pairs come from the Float64 state, like the reference (:94-101).  Host pointers; tau_ext / n_pairs / flags may be NULL. */
 int pfc_calcxd_dual6(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
                      int32_t* flags);
+/* Same on device buffers (none may be NULL except tau_ext), asynchronous on the context's stream; xdot7 must be zero-initialised for
+ * world-attached coordinates. */
+int pfc_calcxd_dual6_device(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
+                            int32_t* flags);
 /* Debug / parity: the boundary arrays (X_r2_r1, twist_r2) the prologue computed and the per-instruction wrenches of the last
  * host-pointer evaluation; any pointer may be NULL. */
 int pfc_get_boundary(pfc_ctx* ctx, int64_t n_env, double* X_r2_r1, double* twist_r2, double* wrench_r2);

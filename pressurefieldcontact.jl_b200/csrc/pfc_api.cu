@@ -116,6 +116,7 @@ struct pfc_ctx {
     bool has_dynamics = false;
     DevBuf<double> d_H, d_Hinv, d_xdot, d_tau;
     DevBuf<int> d_status;       // OR of the error flag bits of a state-level evaluation
+    bool large_index_dirty = true;   // d_large_index (instruction -> index in the large list) needs uploading
     int* h_status = nullptr;    // pinned
     DynDev dyn{};
     bool timing = false;
@@ -863,30 +864,18 @@ int pfc_calcxd_f64(pfc_ctx* c, int64_t n_env, const double* x, const double* tau
 // calcXd! in Jacobian mode for the same scenes: x (Float64) with Dual seeds on x[seed_start .. seed_start + 6) -> x_dot as 7 doubles per
 // entry (value, then d x_dot / d x[seed_start + k]).  Device pipeline: Float64 prologue + broad phase (the reference always traverses
 // with m.float), Dual prologue, Dual narrow phase / friction (pfc_dual.cu), Dual J' w and rigid-body terms.
-int pfc_calcxd_dual6(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs, int32_t* flags) {
-    if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_dual6: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
-    if (n_env < 0 || !x || !xdot7) return fail(PFC_E_ARG, "pfc_calcxd_dual6: NULL buffer");
-    if (seed_start < 0 || seed_start >= c->state.n_x) return fail(PFC_E_ARG, "pfc_calcxd_dual6: seed_start out of range");
-    if (n_env == 0) return PFC_OK;
-    CU(cudaSetDevice(c->device));
-    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
-    CU(c->d_x.ensure(ne * nx)); CU(c->d_xdot.ensure(7 * ne * nx)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+static int calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, long long* n_pairs,
+                               int* flags, int* status) {
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
     CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni));
     CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni));
     if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
-    CU(cudaMemcpyAsync(c->d_x.p, x, sizeof(double) * ne * nx, cudaMemcpyHostToDevice, c->stream));
-    if (tau_ext) {
-        CU(c->d_tau.ensure(std::max<size_t>(ne * nv, 1)));
-        CU(cudaMemcpyAsync(c->d_tau.p, tau_ext, sizeof(double) * ne * nv, cudaMemcpyHostToDevice, c->stream));
-    }
-    CU(cudaMemsetAsync(c->d_xdot.p, 0, sizeof(double) * 7 * ne * nx, c->stream));
-    CU(status_begin(c));
     int nl = 0;
     // Float64 boundary transforms -> candidate-pair lists
-    CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), c->d_x.p, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
+    CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), x, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
     {
         EvalIO io{};
-        io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
+        io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = n_pairs; io.flags = flags;
         if (c->scene.n_small > 0) {
             CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni));
             CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
@@ -896,24 +885,60 @@ int pfc_calcxd_dual6(pfc_ctx* c, int64_t n_env, const double* x, const double* t
             CU(large_write_counts(c->scene, c->large_scene, io, c->large_buf, c->stream));
             nl += 1;
         }
-        c->lists_n_env = n_env;
+        c->lists_n_env = -1;   // the lists belong to caller-owned count / flag arrays: not reusable by pfc_eval_dual6(X_bp = NULL)
     }
     // Dual boundary arrays, Dual contact wrenches, Dual rigid-body terms
-    CU(launch_state_prologue_dual6(c->state, n_env, int(ni), int(nb), c->d_x.p, seed_start, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl));
-    std::vector<int32_t> large_index(ni, -1);
-    for (size_t k = 0; k < c->large_ins_host.size(); ++k) large_index[c->large_ins_host[k]] = int32_t(k);
-    CU(c->d_large_index.ensure(ni));
-    CU(cudaMemcpyAsync(c->d_large_index.p, large_index.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice, c->stream));
-    CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p,
+    CU(launch_state_prologue_dual6(c->state, n_env, int(ni), int(nb), x, seed_start, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl));
+    if (c->d_large_index.n < ni || c->large_index_dirty) {
+        std::vector<int32_t> large_index(ni, -1);
+        for (size_t k = 0; k < c->large_ins_host.size(); ++k) large_index[c->large_ins_host[k]] = int32_t(k);
+        CU(c->d_large_index.ensure(ni));
+        CU(cudaMemcpyAsync(c->d_large_index.p, large_index.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));   // large_index is a stack vector
+        c->large_index_dirty = false;
+    }
+    CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags,
                          c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
                          c->large_scene.n_large, c->stream));
-    CU(launch_state_dynamics_dual6(c->state, c->dyn, n_env, int(ni), int(nb), c->d_x.p, seed_start, c->d_w7.p, tau_ext ? c->d_tau.p : nullptr,
-                                   nb ? c->d_sd7.p : nullptr, c->d_xdot.p, c->stream, &nl, c->d_fl.p, c->d_status.p));
+    CU(launch_state_dynamics_dual6(c->state, c->dyn, n_env, int(ni), int(nb), x, seed_start, c->d_w7.p, tau_ext, nb ? c->d_sd7.p : nullptr, xdot7,
+                                   c->stream, &nl, flags, status));
     c->launches += nl + 1;
+    return PFC_OK;
+}
+
+int pfc_calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
+                            int32_t* flags) {
+    if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
+    if (n_env < 0 || !x || !xdot7 || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: NULL buffer");
+    if (seed_start < 0 || seed_start >= c->state.n_x) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: seed_start out of range");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    return calcxd_dual6_device(c, n_env, x, tau_ext, seed_start, xdot7, reinterpret_cast<long long*>(n_pairs), flags, nullptr);
+}
+
+int pfc_calcxd_dual6(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_dual6: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
+    if (n_env < 0 || !x || !xdot7) return fail(PFC_E_ARG, "pfc_calcxd_dual6: NULL buffer");
+    if (seed_start < 0 || seed_start >= c->state.n_x) return fail(PFC_E_ARG, "pfc_calcxd_dual6: seed_start out of range");
+    if (n_env == 0) return PFC_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
+    CU(c->d_x.ensure(ne * nx)); CU(c->d_xdot.ensure(7 * ne * nx)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+    CU(cudaMemcpyAsync(c->d_x.p, x, sizeof(double) * ne * nx, cudaMemcpyHostToDevice, c->stream));
+    if (tau_ext) {
+        CU(c->d_tau.ensure(std::max<size_t>(ne * nv, 1)));
+        CU(cudaMemcpyAsync(c->d_tau.p, tau_ext, sizeof(double) * ne * nv, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemsetAsync(c->d_xdot.p, 0, sizeof(double) * 7 * ne * nx, c->stream));
+    CU(status_begin(c));
+    int rc = calcxd_dual6_device(c, n_env, c->d_x.p, tau_ext ? c->d_tau.p : nullptr, seed_start, c->d_xdot.p, c->d_np.p, c->d_fl.p, c->d_status.p);
+    if (rc != PFC_OK) return rc;
     CU(cudaMemcpyAsync(xdot7, c->d_xdot.p, sizeof(double) * 7 * ne * nx, cudaMemcpyDeviceToHost, c->stream));
     if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
     if (flags) CU(cudaMemcpyAsync(flags, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
-    return status_end(c, n_env);
+    int rc2 = status_end(c, n_env);
+    c->lists_n_env = -1;
+    return rc2;
 }
 
 int pfc_get_boundary(pfc_ctx* c, int64_t n_env, double* X, double* twist, double* wrench) {
