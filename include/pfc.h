@@ -122,6 +122,12 @@ int pfc_calcxd_dual6(pfc_ctx* ctx, int64_t n_env, const double* x, const double*
  * world-attached coordinates. */
 int pfc_calcxd_dual6_device(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
                             int32_t* flags);
+/* updateInvC! (src/radau/radau_functions.jl:88-99) for a batch: inv_c[m] = inverse(shift[m] I + neg_J[index ? index[m] : m]) for m < n_mat, where
+ * neg_J[e] is the real n x n matrix -J of environment e (row-major), shift[m] = h^-1 lambda_stage as (re, im), and inv_c[m] is n x n complex,
+ * row-major, interleaved (re, im) -- the layout of Julia's Matrix{ComplexF64} transposed / of a torch.complex128 tensor.  One CTA per matrix,
+ * Gauss-Jordan with partial pivoting in shared memory.  *info (optional) gets bit 0 if a pivot vanished.  Device pointers; asynchronous. */
+int pfc_radau_inv_c_device(pfc_ctx* ctx, int64_t n_mat, int n, const double* neg_J, const double* shift, const int32_t* index, double* inv_c,
+                           int32_t* info);
 /* Debug / parity: the boundary arrays (X_r2_r1, twist_r2) the prologue computed and the per-instruction wrenches of the last
  * host-pointer evaluation; any pointer may be NULL. */
 int pfc_get_boundary(pfc_ctx* ctx, int64_t n_env, double* X_r2_r1, double* twist_r2, double* wrench_r2);

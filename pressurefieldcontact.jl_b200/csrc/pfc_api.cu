@@ -941,6 +941,15 @@ int pfc_calcxd_dual6(pfc_ctx* c, int64_t n_env, const double* x, const double* t
     return rc2;
 }
 
+int pfc_radau_inv_c_device(pfc_ctx* c, int64_t n_mat, int n, const double* neg_J, const double* shift, const int32_t* index, double* inv_c, int32_t* info) {
+    if (!c) return fail(PFC_E_ARG, "pfc_radau_inv_c_device: NULL context");
+    if (n_mat < 0 || n < 1 || n > 96 || !neg_J || !shift || !inv_c) return fail(PFC_E_ARG, "pfc_radau_inv_c_device: bad argument (1 <= n <= 96)");
+    CU(cudaSetDevice(c->device));
+    CU(launch_radau_inv_c(n_mat, n, neg_J, shift, index, inv_c, info, c->stream));
+    c->launches += 1;
+    return PFC_OK;
+}
+
 int pfc_get_boundary(pfc_ctx* c, int64_t n_env, double* X, double* twist, double* wrench) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_get_boundary: context not finalized");
     const size_t n = size_t(n_env) * size_t(c->scene.n_ins);

@@ -109,19 +109,52 @@ struct PairSource {
     int n_large;
 };
 
+// value part of the Dual context: what the Float64 pass of the same evaluation works with
+PFC_D void value_ctx(const PatchCtx<D6>& cx, PatchCtx<double>& v) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { v.x21.r[i] = cx.x21.r[i].v; v.x12.r[i] = cx.x12.r[i].v; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { v.x21.t[i] = cx.x21.t[i].v; v.x12.t[i] = cx.x12.t[i].v; }
+    v.w_ang = mk<double>(cx.w_ang.x.v, cx.w_ang.y.v, cx.w_ang.z.v);
+    v.w_lin = mk<double>(cx.w_lin.x.v, cx.w_lin.y.v, cx.w_lin.z.v);
+    v.chi = cx.chi; v.Ebar1 = cx.Ebar1; v.Ebar2 = cx.Ebar2; v.n_quad = cx.n_quad;
+}
+
+// Two thirds of the candidate pairs clip to nothing.  Whether a pair survives is decided by value parts only (the clipper compares
+// values; the value part of every Dual operation used on the way is the Float64 operation), so the Float64 clip runs first and the
+// 7x more expensive Dual pipeline only sees the pairs that leave a polygon.
+PFC_D bool survives_f64(const SceneDev& sc, const InsDev& ins, int a, int b, const PatchCtx<double>& cxv) {
+    if (!prefilter_pair(sc, ins, a, b, cxv)) return false;
+    PolyRec<double> tmp;
+    int fl = 0;
+    const bool keep = clip_pair(sc, ins, a, b, cxv, tmp, fl);
+    return keep || fl != 0;   // error paths (non-finite vertex) are left to the Dual pass, which records the flag
+}
+
 template <int NA>
 PFC_D void run_pairs_dual(const SceneDev& sc, const InsDev& ins, const PairSource& ps, long long env, int k, long long ei, int n, int lane,
-                          const PatchCtx<D6>& cx, Accum<D6, NA>& acc, int& flags) {
+                          const PatchCtx<D6>& cx, const PatchCtx<double>& cxv, Accum<D6, NA>& acc, int& flags) {
     if (ins.small) {
         const unsigned* pl = ps.small_pairs + (size_t)ps.small_cap * ei;
-        for (int i = lane; i < n; i += 32) { const unsigned e = pl[i]; integrate_pair(sc, ins, int((e >> 15) & 0x7fffu), int(e & 0x7fffu), cx, acc, flags); }
+        for (int i = lane; i < n; i += 32) {
+            const unsigned e = pl[i];
+            const int a = int((e >> 15) & 0x7fffu), b = int(e & 0x7fffu);
+            if (survives_f64(sc, ins, a, b, cxv)) integrate_pair(sc, ins, a, b, cx, acc, flags);
+        }
     } else {
         const int3* pl = ps.large_sorted + ps.seg_start[env * ps.n_large + ps.large_index[k]];
-        for (int i = lane; i < n; i += 32) { const int3 e = pl[i]; integrate_pair(sc, ins, e.y, e.z, cx, acc, flags); }
+        for (int i = lane; i < n; i += 32) {
+            const int3 e = pl[i];
+            if (survives_f64(sc, ins, e.y, e.z, cxv)) integrate_pair(sc, ins, e.y, e.z, cx, acc, flags);
+        }
     }
 }
 
+// HB: the scene has bristle instructions (21 Dual accumulators, the three passes and the Dual matrix function are compiled in);
+// regularized-only scenes get a kernel with 6 accumulators and a fraction of the stack.
+template <bool HB>
 __global__ void __launch_bounds__(128) eval_dual6_kernel(SceneDev sc, DualIO io, PairSource ps) {
+    constexpr int NA = HB ? 21 : 6;
     const int lane = threadIdx.x & 31;
     const long long n_prob = io.n_env * sc.n_ins;
     for (long long ei = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); ei < n_prob; ei += (long long)gridDim.x * 4) {
@@ -133,7 +166,7 @@ __global__ void __launch_bounds__(128) eval_dual6_kernel(SceneDev sc, DualIO io,
         D6 w[6];
         for (int j = 0; j < 6; ++j) w[j] = D6(0.0);
         bool contact = false;
-        const bool bristle = ins.model == PFC_MODEL_BRISTLE;
+        const bool bristle = HB && ins.model == PFC_MODEL_BRISTLE;
         const double* sv = bristle ? io.s7 + 42 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
         double* sd = bristle ? io.sdot7 + 42 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
         if (n > 0) {
@@ -150,19 +183,21 @@ __global__ void __launch_bounds__(128) eval_dual6_kernel(SceneDev sc, DualIO io,
             cx.w_ang = mk<D6>(ld7(tw), ld7(tw + 7), ld7(tw + 14));
             cx.w_lin = mk<D6>(ld7(tw + 21), ld7(tw + 28), ld7(tw + 35));
             cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
-            Accum<D6, 21> acc;
+            PatchCtx<double> cxv;
+            value_ctx(cx, cxv);
+            Accum<D6, NA> acc;
             acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
             if (!bristle) {
                 acc.reset(ACC_REGULARIZED);
-                run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, acc, flags);
+                run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, cxv, acc, flags);
                 int pts = acc.n_points;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(0xffffffffu, pts, o);
                 contact = pts > 0;
                 for (int j = 0; j < 6; ++j) w[j] = warp_sum(acc.a[j]);
-            } else {
+            } else if constexpr (HB) {
                 acc.reset(ACC_COP);
-                run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, acc, flags);
+                run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, cxv, acc, flags);
                 int pts = acc.n_points;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(0xffffffffu, pts, o);
@@ -173,7 +208,7 @@ __global__ void __launch_bounds__(128) eval_dual6_kernel(SceneDev sc, DualIO io,
                     const Vec3<D6> cop = mk<D6>(c[7] / c[6], c[8] / c[6], c[9] / c[6]);
                     acc.cop = cop;
                     acc.reset(ACC_STIFFNESS);
-                    run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, acc, flags);
+                    run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, cxv, acc, flags);
                     D6 K21[21], Sinv[6], Kh[36], s[6];
                     for (int j = 0; j < 21; ++j) K21[j] = warp_sum(acc.a[j]) * ins.p[1];
                     decompose_K_dual(K21, ins.p[6], Sinv, Kh);  // every lane redundantly: identical inputs, no broadcast needed
@@ -184,7 +219,7 @@ __global__ void __launch_bounds__(128) eval_dual6_kernel(SceneDev sc, DualIO io,
                         acc.delta[i] = Sinv[i] * t;
                     }
                     acc.reset(ACC_BRISTLE);
-                    run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, acc, flags);
+                    run_pairs_dual(sc, ins, ps, env, k, ei, n, lane, cx, cxv, acc, flags);
                     D6 f[6];
                     for (int j = 0; j < 6; ++j) f[j] = warp_sum(acc.a[j]);
                     const Vec3<D6> shift = cross(cop, mk<D6>(f[3], f[4], f[5]));
@@ -235,7 +270,8 @@ cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double*
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const unsigned blocks = (unsigned)std::min<long long>((n_prob + 3) / 4, (long long)n_sm * 8);
-    eval_dual6_kernel<<<blocks, 128, 0, stream>>>(sc, io, ps);
+    if (sc.n_bristle > 0) eval_dual6_kernel<true><<<blocks, 128, 0, stream>>>(sc, io, ps);
+    else eval_dual6_kernel<false><<<blocks, 128, 0, stream>>>(sc, io, ps);
     return cudaGetLastError();
 }
 

@@ -76,4 +76,7 @@ cudaError_t launch_state_dynamics_dual6(const StateDev& sd, const DynDev& dd, lo
 cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
                                   int* n_launches, const int* flags = nullptr, int* status = nullptr);
 
+// Batched updateInvC! of the Radau step (pfc_radau.cu): inv_c[m] = inverse((shift[m]) I + neg_J[index ? index[m] : m]), n x n complex, interleaved
+cudaError_t launch_radau_inv_c(long long n_mat, int n, const double* neg_J, const double* shift, const int* index, double* inv_c, int* info, cudaStream_t stream);
+
 }  // namespace pfc

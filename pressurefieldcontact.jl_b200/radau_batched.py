@@ -5,8 +5,9 @@ advanced for a whole BATCH of independent environments with every array resident
 What runs where
   * stage evaluations F(X_stage): pfc_calcxd_f64_device  -- calcXd! for n_env x n_stage states in ONE launch sequence
   * Jacobian: ceil(NX / 6) calls of pfc_calcxd_dual6_device -- one Dual-6 chunk for all environments per call (calcJacobian!)
-  * (h^-1 lambda_i I - J)^-1 for every environment and stage: torch.linalg.inv on complex128 batches (cuSOLVER; library code for a
-    step that is not on the contact path -- the reference calls LAPACK getrf / getri here, radau_functions.jl:88-99)
+  * (h^-1 lambda_i I - J)^-1 for every environment and stage: pfc_radau_inv_c_device, one CTA per matrix, Gauss-Jordan with partial
+    pivoting in shared memory (the reference calls LAPACK getrf / getri here, radau_functions.jl:88-99; batched cuSOLVER through
+    torch.linalg.inv took 17.6 ms for 4096 48 x 48 matrices)
   * the Newton iteration, error estimate, step-size and order control: per-environment state vectors and masks, torch ops on the
     library's stream (radau_solve.jl:36-99, adaptive.jl) -- every environment follows exactly the decision sequence the
     single-scene integrator would take for it; environments that fail a step retry with their own smaller h while the others wait.
@@ -47,6 +48,7 @@ class BatchedRadau:
             self.Psi = torch.full((E,), 9999.0, dtype=f64, device=self.dev)
             self.t = torch.zeros(E, dtype=f64, device=self.dev)
             self.eye = torch.eye(self.NX, dtype=c128, device=self.dev)
+            self.info = torch.zeros(1, dtype=torch.int32, device=self.dev)   # bit 0: a pivot vanished in some inversion
         self.tol_newton, self.tol_a, self.tol_r, self.h_max, self.h_min, self.k_iter_max = tol_newton, 1.0e-4, 1.0e-4, h_max, 1.0e-8, 15
         self.n_ins = self.ctx.n_ins
         self.mrp_cols = torch.tensor([b.q0 for b in m.bodies if isinstance(b.joint, S.SPQuatFloating)], dtype=torch.int64, device=self.dev)
@@ -87,8 +89,14 @@ class BatchedRadau:
         s, n, NX = tab["s"], idx.numel(), self.NX
         h = self.h[idx]
         hinv = 1.0 / h
-        nJ = negJ[idx].to(torch.complex128)
-        invC = [torch.linalg.inv(nJ + (hinv * tab["lam"][i])[:, None, None] * self.eye) for i in range(s)]
+        # updateInvC!: (h^-1 lambda_i I - J)^-1 for every environment of the group and every stage, one CTA per matrix (pfc_radau.cu)
+        idx32 = idx.to(torch.int32).contiguous()
+        invC = []
+        for i in range(s):
+            shift = torch.view_as_real((hinv * tab["lam"][i]).to(torch.complex128)).contiguous()
+            out = torch.empty((n, NX, NX), dtype=torch.complex128, device=self.dev)
+            self.ctx.radau_inv_c_device(n, NX, negJ.data_ptr(), shift.data_ptr(), idx32.data_ptr(), out.data_ptr(), self.info.data_ptr())
+            invC.append(out)
         x0s = x0[idx]
         X = [x0s.clone() for _ in range(s)]
         active = torch.ones(n, dtype=torch.bool, device=self.dev)

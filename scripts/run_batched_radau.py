@@ -52,20 +52,31 @@ def main():
         ev[0].record(br.stream)
         br._jacobian(x)
         ev[1].record(br.stream)
-        br._calcxd(torch.cat([x, x, x], dim=0))
+        br._calcxd(x)
         ev[2].record(br.stream)
-        nJ = torch.randn((n_env, br.NX, br.NX), dtype=torch.complex128, device=br.dev) + 50 * br.eye
-        torch.linalg.inv(nJ)
+        f1_ms_marker = None
+        _, negJ = br._jacobian(x)
+        ev[2].record(br.stream)
+        shift = torch.view_as_real((1.0 / br.h * br.tab[0]["lam"][0]).to(torch.complex128)).contiguous()
+        invc = torch.empty((n_env, br.NX, br.NX), dtype=torch.complex128, device=br.dev)
+        m.backend.radau_inv_c_device(n_env, br.NX, negJ.data_ptr(), shift.data_ptr(), None, invc.data_ptr(), br.info.data_ptr())
         ev[3].record(br.stream)
         m.backend.sync()
-        jac_ms, f3_ms, inv_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+        ev4 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev4[0].record(br.stream)
+        br._calcxd(x)
+        ev4[1].record(br.stream)
+        m.backend.sync()
+        jac_ms, f3_ms, inv_ms = ev[0].elapsed_time(ev[1]), ev4[0].elapsed_time(ev4[1]), ev[2].elapsed_time(ev[3])
+        chk = torch.bmm(invc, (negJ.to(torch.complex128) + torch.view_as_complex(shift)[:, None, None] * br.eye)) - br.eye
+        inv_residual = float(chk.abs().max())
     assert torch.isfinite(x).all()
     out = {"scene": "C3 batch of test/boxes.jl", "n_env": n_env, "radau_steps": args.steps, "wall_s": wall,
            "env_steps_per_sec": n_env * args.steps / wall, "ms_per_batched_step": wall / args.steps * 1e3,
            "stage_states_per_step_per_env": (br.n_calcxd_states - c0) / (n_env * args.steps),
            "jacobian_chunks_per_step_per_env": (br.n_chunk_states - j0) / (n_env * args.steps),
            "newton_attempt_rounds_per_step": (br.n_attempts - a0) / args.steps,
-           "device_ms": {"jacobian_8_dual6_chunks": jac_ms, "calcxd_3_stages": f3_ms, "complex_inverse_one_stage": inv_ms},
+           "device_ms": {"jacobian_8_dual6_chunks": jac_ms, "calcxd_one_stage": f3_ms, "complex_inverse_one_stage": inv_ms}, "inverse_max_residual": inv_residual,
            "sim_time_mean": float(br.t.mean()), "rule_2_fraction": float((br.rule == 2).double().mean())}
     # the same integrator on the CPU oracle, one scene on one thread (what the reference does per environment)
     mc = scene_boxes(orc.OracleContext())[0]
