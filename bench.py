@@ -398,6 +398,28 @@ def main():
                    "chunks_per_radau_step": int(np.ceil(m.x_all.shape[1] / 6))}
     except Exception as exc:
         jac = {"error": repr(exc)}
+    # secondary: the reference's adaptive Radau IIA integrator for the whole batch with every array on the GPU (radau_batched.py)
+    rollout = None
+    try:
+        if getattr(m, "device_dynamics", False) and not args.no_large:
+            from pfc_b200.radau_batched import BatchedRadau
+            br = BatchedRadau(m, n_env, device_index=local_rank, h_max=0.05)
+            with torch.cuda.stream(br.stream):
+                xb = torch.from_numpy(m.x_all).to(dev)
+                for _ in range(2):
+                    xb, _ = br.step(xb)
+                ctx.sync()
+                t0 = time.perf_counter()
+                n_roll = 5
+                for _ in range(n_roll):
+                    xb, _ = br.step(xb)
+                ctx.sync()
+                dtr = (time.perf_counter() - t0) / n_roll
+            rollout = {"value": n_env / dtr, "unit": "environment Radau steps/s", "ms_per_batched_step": dtr * 1e3, "envs": n_env,
+                       "what": "adaptive Radau IIA (mirror of src/radau): 8 Dual-6 Jacobian chunks, per-environment complex inverses, Newton stage "
+                               "evaluations through pfc_calcxd_f64_device; per-environment step-size / order control"}
+    except Exception as exc:
+        rollout = {"error": repr(exc)}
     large = None if args.no_large else measure_large_scenes(local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -435,6 +457,8 @@ def main():
     }
     if jac is not None:
         line["jacobian_chunks"] = jac
+    if rollout is not None:
+        line["batched_radau"] = rollout
     if large is not None:
         line["large_scenes"] = large
     print(json.dumps(line))
