@@ -403,6 +403,7 @@ def main():
     try:
         if getattr(m, "device_dynamics", False) and not args.no_large:
             from pfc_b200.radau_batched import BatchedRadau
+            m.backend = ctx     # (the cpu_baseline leg above attached the oracle to the same scene description)
             br = BatchedRadau(m, n_env, device_index=local_rank, h_max=0.05)
             with torch.cuda.stream(br.stream):
                 xb = torch.from_numpy(m.x_all).to(dev)
