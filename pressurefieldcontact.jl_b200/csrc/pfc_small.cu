@@ -1,26 +1,20 @@
-// pfc_small.cu -- fused contact-wrench evaluation for small instructions: ONE WARP PER
-// (environment, contact instruction), everything on chip, one launch per batch.
+// pfc_small.cu -- contact-wrench evaluation for SMALL instructions (n_leaf1 * n_leaf2 <= 512), batched over environments:
+// everything on chip, two launches per batch.
 //
-// This is the batched-environments path (config C3: thousands of copies of test/boxes.jl).  What
-// the reference does per instruction in force_single_elastic_intersection!
-// (/root/reference/src/contact_algorithms_non_friction.jl:70-84) --
+// This is the batched-environments path (config C3: thousands of copies of test/boxes.jl).  What the reference does per
+// instruction in force_single_elastic_intersection! (/root/reference/src/contact_algorithms_non_friction.jl:70-84) --
 //   calcTriTetIntersections! (dual-tree traversal, src/obb/tree_types.jl:88-111)
 //   integrate_over!          (loop over candidate pairs, :136-143)
 //   yes_contact!/no_contact! (src/contact_algorithms_friction.jl:50-81, 119-143)
-// -- is done by two persistent-grid kernels (broad_small_kernel, narrow_small_kernel; split so that
-// the SAT-only kernel runs at high occupancy) in which a group of G lanes owns one instruction:
-//   1. Broad phase: warp-cooperative in-place expansion of the node-pair frontier held in shared
-//      memory.  Each round every lane tests one node pair (15-axis SAT, bit-exact) and the
-//      survivors' children replace it *in order* through a warp prefix sum, so when the frontier
-//      holds only leaf pairs it is exactly the reference's recursion (DFS) order -- no atomics, no
-//      sort, deterministic.
-//   2. Narrow phase in chunks of 32 candidate pairs: (A) each lane clips one pair and, if a polygon
-//      survives, leaves it in its shared-memory slot; (B) the chunk's (polygon, edge) sub-triangles
-//      are dealt out one per lane for quadrature + friction.  Most pairs die in (A); (B) keeps the
-//      lanes dense where the FLOPs are.
-//   3. Fixed-order xor-butterfly warp reduction of the per-lane partial sums (bitwise
-//      reproducible; no floating-point atomics).  Bristle friction runs the three passes of
-//      bristle_wrench_in_world with a warp reduction between passes.
+// -- is done by two persistent-grid kernels (split so that each runs at the occupancy its register needs allow):
+//   1. broad_tile_kernel    one warp per tile of 4 problems over a node table staged in shared memory: level-synchronous expansion
+//                           of a flattened frontier (SAT on the open pairs, lanes dense; ordered rebuild) that ends in exactly the
+//                           reference's recursion (DFS) order -- no atomics, no sort, deterministic, bit-exact pair lists;
+//   2. narrow_tile_kernel   one CTA per tile of 4 problems, every phase flattened over them: clip in place in shared-memory polygon
+//                           slots, (polygon, edge) sub-triangles dealt one per thread for quadrature + friction, per-problem sums in
+//                           item order (bitwise reproducible; no floating-point atomics);
+//      narrow_small_kernel  scenes with bristle instructions on this path: one warp per problem, the three passes of
+//                           bristle_wrench_in_world with a fixed-order butterfly reduction between passes.
 // HBM traffic per instruction is the boundary data only: 22 doubles in, 6 doubles + 2 words out.
 #include <cstdlib>
 
@@ -92,99 +86,16 @@ template <int G> PFC_D double group_sum(unsigned gmask, double x) {
     return x;
 }
 
-// ---- kernel 1: broad phase ------------------------------------------------------------------------------------
-// shared memory per warp: unsigned frontier[32/G][2][cap]
-template <int WARPS, int G, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) broad_small_kernel(SceneDev sc, EvalIO io, int cap, unsigned* __restrict__ pairs_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NG = 32 / G;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int grp = lane / G, gl = lane % G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-    unsigned* frontier = reinterpret_cast<unsigned*>(smem_raw) + (size_t)2 * cap * (wib * NG + grp);
-    const long long n_prob = io.n_env * sc.n_small;
-    const long long stride = (long long)gridDim.x * WARPS * NG;
-    for (long long prob = ((long long)blockIdx.x * WARPS + wib) * NG + grp; prob < n_prob; prob += stride) {
-        // scheduling order: instruction-major, heaviest instruction first (the short problems fill the last, partial wave)
-        const long long j = prob / io.n_env;
-        const long long env = prob - j * io.n_env;
-        const int k = sc.small_heavy_first[j];
-        const InsDev& ins = sc.ins[k];
-        const long long ei = env * sc.n_ins + k;
-        Xform<double> x21;
-        load_xform(io.X + 16 * ei, x21);
-        double Rab[9], tab[3];
-        broad_phase_xform(x21, Rab, tab);
-        unsigned* cur = frontier;
-        unsigned* nxt = frontier + cap;
-        int n = 1;
-        int flags = 0;
-        if (gl == 0) cur[0] = enc(0, 0);
-        __syncwarp(gmask);
-        for (;;) {
-            int n_out = 0;
-            bool open = false;
-            for (int base = 0; base < n; base += G) {
-                const int i = base + gl;
-                int cnt = 0;
-                unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-                if (i < n) {
-                    const unsigned e = cur[i];
-                    if (e & kDone) { cnt = 1; c0 = e; }
-                    else {
-                        const int ia = dec_a(e), ib = dec_b(e);
-                        const NodeRec& a = sc.nodes[ins.node_base1 + ia];
-                        const NodeRec& b = sc.nodes[ins.node_base2 + ib];
-                        SatA A;
-                        sat_prepare_a(a, Rab, tab, A);
-                        if (sat_test(A, b)) {
-                            const int al = a.left, ar = a.right, bl = b.left, br = b.right;
-                            if (al < 0) {
-                                if (bl < 0) { cnt = 1; c0 = kDone | enc(ar, br); }
-                                else { cnt = 2; c0 = enc(ia, bl); c1 = enc(ia, br); open = true; }
-                            } else if (bl < 0) { cnt = 2; c0 = enc(al, ib); c1 = enc(ar, ib); open = true; }
-                            else { cnt = 4; c0 = enc(al, bl); c1 = enc(ar, bl); c2 = enc(al, br); c3 = enc(ar, br); open = true; }
-                        }
-                    }
-                }
-                const int incl = group_incl_scan<G>(gmask, cnt, gl);
-                const int total = __shfl_sync(gmask, incl, G - 1, G);
-                const int at = n_out + incl - cnt;
-                if (at + cnt <= cap) {
-                    if (cnt > 0) nxt[at] = c0;
-                    if (cnt > 1) nxt[at + 1] = c1;
-                    if (cnt > 2) { nxt[at + 2] = c2; nxt[at + 3] = c3; }
-                } else if (cnt > 0) flags |= kFlagOverflow;
-                n_out += total;
-            }
-            __syncwarp(gmask);
-            unsigned* t = cur; cur = nxt; nxt = t;
-            n = n_out < cap ? n_out : cap;
-            if (!(__ballot_sync(gmask, open) & gmask)) break;
-        }
-        unsigned* po = pairs_out + (size_t)cap * ei;
-        for (int i = gl; i < n; i += G) po[i] = cur[i];
-        if (io.dbg_pairs) {
-            int* out = io.dbg_pairs + 2 * (long long)io.dbg_cap * ei;
-            for (int i = gl; i < n && i < io.dbg_cap; i += G) { out[2 * i] = dec_a(cur[i]); out[2 * i + 1] = dec_b(cur[i]); }
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) flags |= __shfl_xor_sync(gmask, flags, o, G);
-        if (gl == 0) { io.n_pairs[ei] = n; io.flags[ei] = flags; }
-        __syncwarp(gmask);
-    }
-}
-
-// ---- kernel 1b: broad phase, one WARP per tile of P problems, node table in shared memory ---------------------------
-// What limits the per-group kernel above is not the FP64 pipe but the L1 data pipe: every lane gathers its two 128 B node
-// records with its own vector loads, so one warp-wide load instruction touches 32 different lines and costs 32 wavefronts
+// ---- kernel 1: broad phase, one WARP per tile of P problems, node table in shared memory ----------------------------
+// What limited the first version of this kernel (one group of 16 lanes per problem, node records read from global memory) was
+// not the FP64 pipe but the L1 data pipe: every lane gathered its two 128 B node records with its own vector loads, so one warp-wide load instruction touched 32 different lines and cost 32 wavefronts
 // for 16 useful bytes each (ncu: l1tex__data_pipe_lsu_wavefronts ~ 66 % of peak, profiles/r1_v7_*).  Here
 //   * the persistent CTA stages the node records of all small instructions ONCE in shared memory at an odd stride
 //     (17 doubles): a lane-private record read is then conflict-free, 2 wavefronts per 64-bit load instead of 32;
 //   * each warp owns a tile of P consecutive problems whose frontiers form ONE flattened array (problem-major, DFS order
 //     inside a problem), and every level runs in two phases:
 //       A. the OPEN node pairs (a compact work list of frontier slots) are tested one per lane, lanes dense: 15-axis SAT
-//          with exactly the arithmetic of the per-group kernel -> a result code per slot;
+//          (pfc_sat.cuh: the reference's arithmetic, operation by operation) -> a result code per slot;
 //       B. an ordered rebuild over the whole frontier (integer work only): finished pairs are copied, hits are replaced by
 //          their children in the reference's visiting order, a warp scan gives the positions; the open children form the
 //          next work list.
@@ -751,24 +662,6 @@ int persistent_blocks(const void* kern, int threads, size_t smem, cudaError_t* e
     return n_sm * (per_sm > 0 ? per_sm : 1);
 }
 
-template <int G, int MINB>
-cudaError_t launch_broad_g(const SceneDev& sc, const EvalIO& io, int cap, unsigned* pairs, cudaStream_t stream) {
-    static int cached_cap = -1, cached_blocks = 0;
-    auto kern = broad_small_kernel<kSmallWarps, G, MINB>;
-    const size_t smem = sizeof(unsigned) * 2 * cap * kSmallWarps * (32 / G);
-    if (cached_cap != cap) {
-        cudaError_t e;
-        cached_blocks = persistent_blocks((const void*)kern, kSmallWarps * 32, smem, &e);
-        if (e != cudaSuccess) return e;
-        cached_cap = cap;
-    }
-    constexpr int per_block = kSmallWarps * (32 / G);
-    long long blocks = (io.n_env * sc.n_small + per_block - 1) / per_block;
-    if (blocks > cached_blocks) blocks = cached_blocks;
-    kern<<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
-    return cudaGetLastError();
-}
-
 template <int P, int NW, int MINB>
 cudaError_t launch_broad_tile(const SceneDev& sc, const EvalIO& io, int cap, unsigned* pairs, cudaStream_t stream) {
     static int cached_cap = -1, cached_stage = -1, cached_blocks = 0;
@@ -825,18 +718,9 @@ cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, co
     return cudaGetLastError();
 }
 
-// group size is a run-time choice (three instantiations per kernel); the minimum-blocks hint (register cap) is fixed:
-// 4 CTAs/SM (<=128 registers) for the SAT kernel, 3 (<=168) for the clip/quadrature kernel -- measured best on B200.
-#define PFC_DISPATCH_G(fn, g, minb, ...) ((g) == 8 ? fn<8, minb>(__VA_ARGS__) : (g) == 16 ? fn<16, minb>(__VA_ARGS__) : fn<32, minb>(__VA_ARGS__))
-
-// broad phase of the small path: the tile kernel (PFC_BROAD_TILE=0 selects the per-group kernel; experiments only)
-cudaError_t launch_broad(const SceneDev& sc, const EvalIO& io, int cap, int bg, unsigned* pairs, cudaStream_t stream) {
-    static const bool use_tile = !(getenv("PFC_BROAD_TILE") && atoi(getenv("PFC_BROAD_TILE")) == 0);
-    static const int tile_p = getenv("PFC_BROAD_P") ? atoi(getenv("PFC_BROAD_P")) : 4;
-    if (!use_tile) return PFC_DISPATCH_G(launch_broad_g, bg, 4, sc, io, cap, pairs, stream);
-    // measured on B200 (scripts/sweep_small.sh): 4 problems per warp, 8 warps per CTA, 2 CTAs per SM (124 registers) is the fastest;
-    // squeezing the SAT into 80-92 registers for more warps per SM costs more than the occupancy returns
-    if (tile_p == 2) return launch_broad_tile<2, 8, 2>(sc, io, cap, pairs, stream);
+// Broad phase of the small path.  Measured on B200 (4096 boxes.jl environments): 4 problems per warp, 8 warps per CTA, 2 CTAs per SM
+// (124 registers) is the fastest; squeezing the SAT into 80-92 registers for more warps per SM costs more than the occupancy returns.
+cudaError_t launch_broad(const SceneDev& sc, const EvalIO& io, int cap, unsigned* pairs, cudaStream_t stream) {
     return launch_broad_tile<4, 8, 2>(sc, io, cap, pairs, stream);
 }
 
@@ -850,24 +734,14 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
                                   cudaEvent_t* ev) {
     if (io.n_env * sc.n_small == 0) return cudaSuccess;
     const int cap = small_cap(max_pairs);
-    int bg = cap <= 320 ? 16 : 32, ng = 32;
-    // tuning overrides (experiments only)
-    if (const char* e = getenv("PFC_BROAD_G")) bg = atoi(e);
-    if (const char* e = getenv("PFC_NARROW_G")) ng = atoi(e);
     if (ev) cudaEventRecord(ev[0], stream);
-    cudaError_t e = launch_broad(sc, io, cap, bg, pairs, stream);
+    cudaError_t e = launch_broad(sc, io, cap, pairs, stream);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
-    // scenes with bristle instructions on the small path (three passes, 21 accumulators), or PFC_NARROW_TILE=0, use the per-problem kernel
-    static const bool use_tile = !(getenv("PFC_NARROW_TILE") && atoi(getenv("PFC_NARROW_TILE")) == 0);
-    static const int tile_minb = getenv("PFC_TILE_MINB") ? atoi(getenv("PFC_TILE_MINB")) : 4;
-    static const int tile_p = getenv("PFC_TILE_P") ? atoi(getenv("PFC_TILE_P")) : 4;
-    if (sc.n_small_bristle == 0 && use_tile) {
-        if (tile_p == 2) e = tile_minb == 6 ? launch_narrow_tile<2, 6>(sc, io, cap, pairs, stream) : launch_narrow_tile<2, 8>(sc, io, cap, pairs, stream);
-        else if (tile_p == 8) e = launch_narrow_tile<8, 2>(sc, io, cap, pairs, stream);
-        else e = tile_minb == 3 ? launch_narrow_tile<4, 3>(sc, io, cap, pairs, stream) : launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
-    }
-    else e = PFC_DISPATCH_G(launch_narrow_g, ng, 3, sc, io, cap, pairs, stream);
+    // regularized-only scenes: the tile kernel (4 problems per CTA, 4 CTAs per SM); scenes with bristle instructions on the small path
+    // (three passes, 21 accumulators): the warp-per-problem kernel (3 CTAs per SM at <= 168 registers)
+    if (sc.n_small_bristle == 0) e = launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
+    else e = launch_narrow_g<32, 3>(sc, io, cap, pairs, stream);
     if (ev) cudaEventRecord(ev[2], stream);
     if (n_launches) *n_launches += 2;
     return e;
@@ -875,10 +749,8 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
 
 cudaError_t launch_broad_small_only(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches) {
     if (io.n_env * sc.n_small == 0) return cudaSuccess;
-    const int cap = small_cap(max_pairs);
-    const int bg = cap <= 320 ? 16 : 32;
     if (n_launches) *n_launches += 1;
-    return launch_broad(sc, io, cap, bg, pairs, stream);
+    return launch_broad(sc, io, small_cap(max_pairs), pairs, stream);
 }
 
 cudaError_t launch_dump_traction(const SceneDev& sc, const EvalIO& io, long long env, int ins, const int* pairs, long long n_pairs, double* out,
