@@ -451,7 +451,9 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
 int pfc_eval_f64_device(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
                         int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_f64_device: context not finalized");
-    if (n_env < 0 || !X || !twist || !wrench || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_f64_device: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_eval_f64_device: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!X || !twist || !wrench || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_f64_device: NULL buffer");
     if (c->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_eval_f64_device: bristle instructions need s and sdot");
     CU(cudaSetDevice(c->device));
     EvalIO io{};
@@ -463,9 +465,10 @@ int pfc_eval_f64_device(pfc_ctx* c, int64_t n_env, const double* X, const double
 int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot, int64_t* n_pairs,
                  int32_t* flags) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_f64: context not finalized");
-    if (n_env < 0 || !X || !twist || !wrench) return fail(PFC_E_ARG, "pfc_eval_f64: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_eval_f64: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!X || !twist || !wrench) return fail(PFC_E_ARG, "pfc_eval_f64: NULL buffer");
     if (c->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_eval_f64: bristle instructions need s and sdot");
-    if (n_env == 0) return PFC_OK;
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
     CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni));
@@ -499,7 +502,9 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
 int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
                            int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: context not finalized");
-    if (n_env < 0 || !X || !twist || !wrench || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!X || !twist || !wrench || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: NULL buffer");
     if (c->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: bristle instructions need s and sdot");
     if (c->large_scene.n_large == 0) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: the scene has no large instruction to split");
     CU(cudaSetDevice(c->device));
@@ -550,9 +555,10 @@ int pfc_eval_sharded_step(pfc_ctx* c, int* more) {
 int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* X7, const double* twist7, const double* s7, double* wrench7,
                    double* sdot7, int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_dual6: context not finalized");
-    if (n_env < 0 || !X7 || !twist7 || !wrench7) return fail(PFC_E_ARG, "pfc_eval_dual6: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_eval_dual6: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!X7 || !twist7 || !wrench7) return fail(PFC_E_ARG, "pfc_eval_dual6: NULL buffer");
     if (c->n_bristle > 0 && (!s7 || !sdot7)) return fail(PFC_E_ARG, "pfc_eval_dual6: bristle instructions need s7 and sdot7");
-    if (n_env == 0) return PFC_OK;
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
     int nl = 0;
@@ -742,18 +748,20 @@ static int eval_state_device(pfc_ctx* c, int64_t n_env, const double* x, double*
 
 int pfc_eval_state_f64_device(pfc_ctx* c, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized || !c->has_bodies) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: pfc_finalize and pfc_set_bodies first");
-    if (n_env < 0 || !x || !f_generalized || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !f_generalized || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: NULL buffer");
     if (c->n_bristle > 0 && !sdot) return fail(PFC_E_ARG, "pfc_eval_state_f64_device: bristle instructions need sdot");
-    if (n_env == 0) return PFC_OK;
     CU(cudaSetDevice(c->device));
     return eval_state_device(c, n_env, x, f_generalized, sdot, reinterpret_cast<long long*>(n_pairs), flags);
 }
 
 int pfc_eval_state_f64(pfc_ctx* c, int64_t n_env, const double* x, double* f_generalized, double* sdot, int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized || !c->has_bodies) return fail(PFC_E_ARG, "pfc_eval_state_f64: pfc_finalize and pfc_set_bodies first");
-    if (n_env < 0 || !x || !f_generalized) return fail(PFC_E_ARG, "pfc_eval_state_f64: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_eval_state_f64: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !f_generalized) return fail(PFC_E_ARG, "pfc_eval_state_f64: NULL buffer");
     if (c->n_bristle > 0 && !sdot) return fail(PFC_E_ARG, "pfc_eval_state_f64: bristle instructions need sdot");
-    if (n_env == 0) return PFC_OK;
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
     CU(c->d_x.ensure(ne * nx)); CU(c->d_fgen.ensure(std::max<size_t>(ne * nv, 1))); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
@@ -833,16 +841,18 @@ static int calcxd_device(pfc_ctx* c, int64_t n_env, const double* x, const doubl
 
 int pfc_calcxd_f64_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_f64_device: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
-    if (n_env < 0 || !x || !xdot || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_calcxd_f64_device: NULL buffer");
-    if (n_env == 0) return PFC_OK;
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_calcxd_f64_device: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !xdot || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_calcxd_f64_device: NULL buffer");
     CU(cudaSetDevice(c->device));
     return calcxd_device(c, n_env, x, tau_ext, xdot, reinterpret_cast<long long*>(n_pairs), flags);
 }
 
 int pfc_calcxd_f64(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* xdot, int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_f64: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
-    if (n_env < 0 || !x || !xdot) return fail(PFC_E_ARG, "pfc_calcxd_f64: NULL buffer");
-    if (n_env == 0) return PFC_OK;
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_calcxd_f64: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !xdot) return fail(PFC_E_ARG, "pfc_calcxd_f64: NULL buffer");
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
     CU(c->d_x.ensure(ne * nx)); CU(c->d_xdot.ensure(ne * nx)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
@@ -909,18 +919,20 @@ static int calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const
 int pfc_calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
                             int32_t* flags) {
     if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
-    if (n_env < 0 || !x || !xdot7 || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !xdot7 || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: NULL buffer");
     if (seed_start < 0 || seed_start >= c->state.n_x) return fail(PFC_E_ARG, "pfc_calcxd_dual6_device: seed_start out of range");
-    if (n_env == 0) return PFC_OK;
     CU(cudaSetDevice(c->device));
     return calcxd_dual6_device(c, n_env, x, tau_ext, seed_start, xdot7, reinterpret_cast<long long*>(n_pairs), flags, nullptr);
 }
 
 int pfc_calcxd_dual6(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_dual6: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
-    if (n_env < 0 || !x || !xdot7) return fail(PFC_E_ARG, "pfc_calcxd_dual6: NULL buffer");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_calcxd_dual6: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !xdot7) return fail(PFC_E_ARG, "pfc_calcxd_dual6: NULL buffer");
     if (seed_start < 0 || seed_start >= c->state.n_x) return fail(PFC_E_ARG, "pfc_calcxd_dual6: seed_start out of range");
-    if (n_env == 0) return PFC_OK;
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
     CU(c->d_x.ensure(ne * nx)); CU(c->d_xdot.ensure(7 * ne * nx)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
