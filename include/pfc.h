@@ -122,6 +122,13 @@ int pfc_calcxd_dual6(pfc_ctx* ctx, int64_t n_env, const double* x, const double*
  * world-attached coordinates. */
 int pfc_calcxd_dual6_device(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
                             int32_t* flags);
+/* Refit of one mesh after its vertices moved (same connectivity, same tree topology), on the device: rebuilds the mesh's primitive records
+ * (triangle normals; inv([V; 1]) and the pressure gradient of every tetrahedron, src/contact_algorithms_non_friction.jl:145-164) and refits
+ * every box of its tree with the construction rules of eMesh_to_tree (leaves: fit_tri_obb / fit_tet_obb, src/obb/obb_construction.jl; internal
+ * nodes: OBB(a, b) of the children's axis-aligned boxes, src/obb/box_types.jl:11-15, bottom-up).  xyz[n_point][3] is a host pointer.
+ * Returns PFC_E_MESH for a non-finite vertex or an inverted tetrahedron (src/obb/obb_construction.jl:30). */
+int pfc_refit_mesh(pfc_ctx* ctx, int mesh_id, int64_t n_point, const double* xyz);
+
 /* updateInvC! (src/radau/radau_functions.jl:88-99) for a batch: inv_c[m] = inverse(shift[m] I + neg_J[index ? index[m] : m]) for m < n_mat, where
  * neg_J[e] is the real n x n matrix -J of environment e (row-major), shift[m] = h^-1 lambda_stage as (re, im), and inv_c[m] is n x n complex,
  * row-major, interleaved (re, im) -- the layout of Julia's Matrix{ComplexF64} transposed / of a torch.complex128 tensor.  One CTA per matrix,

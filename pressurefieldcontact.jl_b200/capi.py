@@ -22,7 +22,7 @@ _vp = C.c_void_p
 SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
     "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_eval_sharded_begin", "pfc_eval_sharded_partials", "pfc_eval_sharded_step", "pfc_sync", "pfc_stream",
-    "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_set_dynamics", "pfc_calcxd_f64", "pfc_calcxd_f64_device", "pfc_calcxd_dual6", "pfc_calcxd_dual6_device", "pfc_radau_inv_c_device", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
+    "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_set_dynamics", "pfc_calcxd_f64", "pfc_calcxd_f64_device", "pfc_calcxd_dual6", "pfc_calcxd_dual6_device", "pfc_radau_inv_c_device", "pfc_refit_mesh", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
         L.pfc_calcxd_f64_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
         L.pfc_calcxd_dual6.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, _vp]
         L.pfc_calcxd_dual6_device.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, _vp]
+        L.pfc_refit_mesh.argtypes = [_vp, C.c_int, C.c_int64, _d]
         L.pfc_radau_inv_c_device.argtypes = [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp, _vp]
         L.pfc_sync.argtypes = [_vp]
         L.pfc_stream.argtypes = [_vp]
@@ -224,6 +225,11 @@ class Context:
     def calcxd_dual6_device(self, n_env, x, tau_ext, seed_start, xdot7, n_pairs, flags):
         """Device pointers given as integers; asynchronous on self.stream."""
         _check(lib().pfc_calcxd_dual6_device(self._h, n_env, x, tau_ext, int(seed_start), xdot7, n_pairs, flags))
+
+    def refit_mesh(self, mesh_id: int, xyz):
+        """New vertex positions for mesh `mesh_id` (same connectivity): primitive records and every box of its tree are refitted on the device."""
+        xyz = _a(xyz).reshape(-1, 3)
+        _check(lib().pfc_refit_mesh(self._h, int(mesh_id), xyz.shape[0], xyz))
 
     def radau_inv_c_device(self, n_mat, n, neg_J, shift, index, inv_c, info=None):
         """Batched updateInvC!: device pointers given as integers; asynchronous on self.stream."""

@@ -116,6 +116,10 @@ struct pfc_ctx {
     bool has_dynamics = false;
     DevBuf<double> d_H, d_Hinv, d_xdot, d_tau;
     DevBuf<int> d_status;       // OR of the error flag bits of a state-level evaluation
+    // device-side refit (pfc_refit_mesh): per mesh, built on first use
+    struct RefitDev { DevBuf<int> idx; DevBuf<double> eps; DevBuf<int> level_nodes; std::vector<int> level_ptr; bool ready = false; };
+    std::vector<RefitDev> refit;
+    DevBuf<double> d_refit_xyz, d_refit_aabb;
     bool large_index_dirty = true;   // d_large_index (instruction -> index in the large list) needs uploading
     int* h_status = nullptr;    // pinned
     DynDev dyn{};
@@ -196,7 +200,8 @@ int pfc_destroy(pfc_ctx* c) {
     c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release(); c->d_small_heavy.release();
     c->d_X.release(); c->d_tw.release(); c->d_s.release(); c->d_w.release(); c->d_sd.release(); c->d_np.release(); c->d_fl.release();
     c->d_dbg_pairs.release(); c->d_last_np.release(); c->d_small_pairs.release();
-    c->d_H.release(); c->d_Hinv.release(); c->d_xdot.release(); c->d_tau.release(); c->d_status.release();
+    c->d_H.release(); c->d_Hinv.release(); c->d_xdot.release(); c->d_tau.release(); c->d_status.release(); c->d_refit_xyz.release(); c->d_refit_aabb.release();
+    for (auto& r : c->refit) { r.idx.release(); r.eps.release(); r.level_nodes.release(); }
     if (c->h_status) { cudaFreeHost(c->h_status); c->h_status = nullptr; }
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     c->d_large.release(); c->d_leaf_path.release(); c->d_leaf_depth.release();
@@ -951,6 +956,49 @@ int pfc_calcxd_dual6(pfc_ctx* c, int64_t n_env, const double* x, const double* t
     int rc2 = status_end(c, n_env);
     c->lists_n_env = -1;
     return rc2;
+}
+
+int pfc_refit_mesh(pfc_ctx* c, int mesh_id, int64_t n_point, const double* xyz) {
+    if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_refit_mesh: call after pfc_finalize");
+    if (mesh_id < 0 || mesh_id >= int(c->mesh.size()) || !xyz) return fail(PFC_E_ARG, "pfc_refit_mesh: bad argument");
+    HostMesh& m = c->mesh[mesh_id];
+    if (n_point != m.n_point) return fail(PFC_E_ARG, "pfc_refit_mesh: the number of points must not change (same connectivity)");
+    for (int64_t k = 0; k < 3 * n_point; ++k) if (!std::isfinite(xyz[k])) return fail(PFC_E_MESH, "pfc_refit_mesh: non-finite vertex");
+    CU(cudaSetDevice(c->device));
+    if (c->refit.size() < c->mesh.size()) c->refit.resize(c->mesh.size());
+    pfc_ctx::RefitDev& r = c->refit[mesh_id];
+    const int64_t n_node = int64_t(m.nodes.size());
+    if (!r.ready) {   // connectivity, eps and the internal nodes grouped by depth (pre-order: parents come first)
+        std::vector<int> depth(n_node, 0), order;
+        int max_depth = 0;
+        for (int64_t k = 0; k < n_node; ++k)
+            if (m.nodes[k].left >= 0) { depth[m.nodes[k].left] = depth[m.nodes[k].right] = depth[k] + 1; max_depth = std::max(max_depth, depth[k]); }
+        r.level_ptr.assign(max_depth + 2, 0);
+        for (int64_t k = 0; k < n_node; ++k) if (m.nodes[k].left >= 0) r.level_ptr[depth[k] + 1]++;
+        for (int l = 0; l <= max_depth; ++l) r.level_ptr[l + 1] += r.level_ptr[l];
+        order.resize(std::max<int>(r.level_ptr[max_depth + 1], 1));
+        std::vector<int> cursor(r.level_ptr.begin(), r.level_ptr.end() - 1);
+        for (int64_t k = 0; k < n_node; ++k) if (m.nodes[k].left >= 0) order[cursor[depth[k]]++] = int(k);
+        CU(r.idx.ensure(m.idx.size())); CU(r.level_nodes.ensure(order.size()));
+        CU(cudaMemcpy(r.idx.p, m.idx.data(), sizeof(int) * m.idx.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(r.level_nodes.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
+        if (m.kind == 1) { CU(r.eps.ensure(m.eps.size())); CU(cudaMemcpy(r.eps.p, m.eps.data(), sizeof(double) * m.eps.size(), cudaMemcpyHostToDevice)); }
+        r.ready = true;
+    }
+    CU(c->d_refit_xyz.ensure(3 * size_t(n_point))); CU(c->d_refit_aabb.ensure(6 * size_t(n_node)));
+    CU(cudaMemcpyAsync(c->d_refit_xyz.p, xyz, sizeof(double) * 3 * n_point, cudaMemcpyHostToDevice, c->stream));
+    CU(status_begin(c));
+    int nl = 0;
+    CU(launch_refit(m.kind, m.n_prim, n_node, r.idx.p, m.kind == 1 ? r.eps.p : nullptr, c->d_refit_xyz.p, m.kind == 0 ? c->d_tris.p + m.prim_base : nullptr,
+                    m.kind == 1 ? c->d_tets.p + m.prim_base : nullptr, c->d_nodes.p + m.node_base, c->d_refit_aabb.p, r.level_nodes.p, r.level_ptr.data(),
+                    int(r.level_ptr.size()) - 1, c->d_status.p, c->stream, &nl));
+    c->launches += nl;
+    CU(cudaMemcpyAsync(c->h_status, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->lists_n_env = -1;   // pair lists of earlier evaluations no longer describe this geometry
+    if (*c->h_status & 1) return fail(PFC_E_MESH, "pfc_refit_mesh: inverted or degenerate tetrahedron (the mesh's device records are undefined until a successful refit)");
+    m.xyz.assign(xyz, xyz + 3 * n_point);
+    return PFC_OK;
 }
 
 int pfc_radau_inv_c_device(pfc_ctx* c, int64_t n_mat, int n, const double* neg_J, const double* shift, const int32_t* index, double* inv_c, int32_t* info) {

@@ -76,6 +76,13 @@ cudaError_t launch_state_dynamics_dual6(const StateDev& sd, const DynDev& dd, lo
 cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
                                   int* n_launches, const int* flags = nullptr, int* status = nullptr);
 
+// Refit of one mesh after its vertices moved (pfc_refit.cu): primitive records, leaf boxes, internal boxes bottom-up.  idx / eps / xyz /
+// level_nodes are device arrays of the mesh; nodes / tris / tets point at the mesh's slices; level_ptr is a HOST array of n_level + 1
+// offsets into level_nodes (internal nodes grouped by depth); aabb is scratch of 6 n_node doubles; *err gets bit 0 for a bad tetrahedron.
+cudaError_t launch_refit(int kind, long long n_prim, long long n_node, const int* idx, const double* eps, const double* xyz, TriRec* tris, TetRec* tets,
+                         NodeRec* nodes, double* aabb, const int* level_nodes, const int* level_ptr, int n_level, int* err, cudaStream_t stream,
+                         int* n_launches);
+
 // Batched updateInvC! of the Radau step (pfc_radau.cu): inv_c[m] = inverse((shift[m]) I + neg_J[index ? index[m] : m]), n x n complex, interleaved
 cudaError_t launch_radau_inv_c(long long n_mat, int n, const double* neg_J, const double* shift, const int* index, double* inv_c, int* info, cudaStream_t stream);
 

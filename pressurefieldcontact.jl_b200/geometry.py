@@ -703,3 +703,34 @@ def _flatten(root: _Node, m: eMesh, prims: np.ndarray) -> FlatTree:
             left[k] = index[id(nd.a)]
             right[k] = index[id(nd.b)]
     return FlatTree(c, e, R, left, right, leaf_id)
+
+
+def refit_tree(tree: FlatTree, m: eMesh) -> FlatTree:
+    """The boxes of an existing tree for moved vertices (same connectivity, same topology), with the construction rules of eMesh_to_tree:
+    leaves get fit_tri_obb / fit_tet_obb (tight_fit_leaves!), internal nodes OBB(a, b) of their children's axis-aligned boxes, bottom-up,
+    the leaves entering with calc_obb of their vertices (recursive_top_down).  Host mirror of pfc_refit_mesh."""
+    prims = m.tri if m.is_tri else m.tet
+    n = tree.n_node
+    c, e, R = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 9))
+    lo, hi = np.zeros((n, 3)), np.zeros((n, 3))
+    leaf_nodes = np.nonzero(tree.leaf_id >= 0)[0]
+    pts = m.point[prims[tree.leaf_id[leaf_nodes]]]
+    lo[leaf_nodes], hi[leaf_nodes] = pts.min(axis=1), pts.max(axis=1)
+    cb, eb, Rb = fit_tri_obb_batch(pts) if m.is_tri else fit_tet_obb_batch(pts, m.eps[prims[tree.leaf_id[leaf_nodes]]])
+    c[leaf_nodes], e[leaf_nodes] = cb, eb
+    R[leaf_nodes] = np.transpose(Rb, (0, 2, 1)).reshape(-1, 9)
+    order = np.arange(n)
+    # children always come after their parent in the pre-order flattening _flatten produces; in general, order by depth
+    depth = np.zeros(n, dtype=np.int64)
+    for k in range(n):
+        if tree.left[k] >= 0:
+            if tree.left[k] < k or tree.right[k] < k:
+                raise ValueError("refit_tree expects a pre-order tree (parents before children)")
+            depth[tree.left[k]] = depth[tree.right[k]] = depth[k] + 1
+    for k in order[::-1]:
+        if tree.left[k] >= 0:
+            a, b = tree.left[k], tree.right[k]
+            lo[k], hi[k] = _merge_box(lo[a], hi[a], lo[b], hi[b])
+            c[k], e[k] = (hi[k] + lo[k]) * 0.5, (hi[k] - lo[k]) * 0.5
+            R[k] = np.eye(3).reshape(9)
+    return FlatTree(c, e, R, tree.left.copy(), tree.right.copy(), tree.leaf_id.copy())

@@ -332,6 +332,20 @@ def attach_backend(m: MechanismScenario, backend, max_env: int = 1) -> None:
             m.device_dynamics = True
 
 
+def refit_mesh(m: MechanismScenario, mesh_id: int, new_points) -> None:
+    """Moves the vertices of one mesh (same connectivity): the host description gets the refitted tree (geometry.refit_tree) and, with a
+    CUDA backend attached, the device refits its primitive records and boxes itself (pfc_refit_mesh) -- no re-upload of the scene."""
+    from .geometry import refit_tree
+    mc = m.MeshCache[mesh_id]
+    new_points = np.ascontiguousarray(new_points, dtype=np.float64).reshape(mc.mesh.point.shape)
+    mc.mesh = eMesh(point=new_points, tri=mc.mesh.tri, tet=mc.mesh.tet, eps=mc.mesh.eps)
+    mc.tree = refit_tree(mc.tree, mc.mesh)
+    if m.backend is not None:
+        if not hasattr(m.backend, "refit_mesh"):
+            raise RuntimeError("this backend has no refit: build a new scene from the moved mesh and its refitted tree")
+        m.backend.refit_mesh(mesh_id, new_points)
+
+
 # --------------------------------------------------------------------------------------------------
 # state
 # --------------------------------------------------------------------------------------------------
