@@ -210,4 +210,11 @@ function calcXd_chunk_batch_gpu!(xx7::Array{Float64,3}, m::MechanismScenario, x:
     return nothing
 end
 
+"Moved vertices of mesh `id` (same connectivity): the device rebuilds the mesh's primitive records and refits its tree (pfc_refit_mesh)."
+function refit_mesh_gpu!(m::MechanismScenario, id::MeshID, point::Vector{SVector{3,Float64}})
+    xyz = collect(Iterators.flatten(point))
+    GC.@preserve xyz check(ccall((:pfc_refit_mesh, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}), CTX[m], Int(id) - 1, length(point), xyz))
+    return nothing
+end
+
 end # module
