@@ -102,6 +102,8 @@ def test_ragged_scene_mixes_small_and_large_instructions():
     assert g["n_pairs"].max() > 200 and (g["n_pairs"] == 0).any() and (g["flags"] & 1).sum() >= 4   # ragged: empty lists next to long ones
     # regularized instructions at 1e-9; bristle wrenches carry the conditioning of K^(-1/2) (see test_gpu_parity._sdot_metric_err), 1e-6 here
     bristle = np.array([ci.friction_model.model == 1 for ci in m_gpu.ContactInstructions])
-    floor = 1e-9 * np.abs(c["wrench"]).max()
+    # halves of a wrench that nearly vanish by symmetry carry eps |F| L rounding noise: floor of 1e-6 of the largest component, as in
+    # test_gpu_parity.C2_FLOOR
+    floor = 1e-6 * np.abs(c["wrench"]).max()
     assert wrench_rel_err(g["wrench"][:, ~bristle], c["wrench"][:, ~bristle], floor=floor) <= 1e-9
     assert wrench_rel_err(g["wrench"][:, bristle], c["wrench"][:, bristle], floor=floor) <= 1e-6
