@@ -352,7 +352,6 @@ __global__ void __launch_bounds__(128) radix_hist_kernel(const unsigned long lon
 // block d: exclusive scan of row d (n_tiles counts) in place, row total -> tot[d]
 __global__ void __launch_bounds__(256) radix_rowscan_kernel(unsigned* hist, unsigned n_tiles, unsigned* tot) {
     __shared__ unsigned warp_sums[8];
-    __shared__ unsigned carry_s;
     unsigned* row = hist + (size_t)blockIdx.x * n_tiles;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned carry = 0;
@@ -375,7 +374,6 @@ __global__ void __launch_bounds__(256) radix_rowscan_kernel(unsigned* hist, unsi
         __syncthreads();
     }
     if (threadIdx.x == 0) tot[blockIdx.x] = carry;
-    (void)carry_s;
 }
 __global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned n, int shift,
                                                             const unsigned* __restrict__ hist, const unsigned* __restrict__ tot, unsigned n_tiles,

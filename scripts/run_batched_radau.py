@@ -54,7 +54,6 @@ def main():
         ev[1].record(br.stream)
         br._calcxd(x)
         ev[2].record(br.stream)
-        f1_ms_marker = None
         _, negJ = br._jacobian(x)
         ev[2].record(br.stream)
         shift = torch.view_as_real((1.0 / br.h * br.tab[0]["lam"][0]).to(torch.complex128)).contiguous()
