@@ -11,8 +11,7 @@
 // butterfly.  The 6x6 matrix function K̄^(-1/2) of the bristle model is differentiated analytically
 // (Daleckii-Krein), which is what differentiating through any converged eigen-solver yields.
 #include "pfc_bristle.cuh"
-#include "pfc_large.h"
-#include "pfc_patch.cuh"
+#include "pfc_dual.cuh"
 
 namespace pfc {
 
@@ -90,26 +89,6 @@ __device__ __noinline__ void decompose_K_dual(const D6* a21, double magic, D6* S
     }
 }
 
-struct DualIO {
-    long long n_env;
-    const double* X7;       // [env][ins][16][7]
-    const double* twist7;   // [env][ins][6][7]
-    const double* s7;       // [env][bristle][6][7]
-    double* wrench7;        // [env][ins][6][7]
-    double* sdot7;          // [env][bristle][6][7]
-    const long long* n_pairs;  // [env][ins] (from the Float64 broad phase)
-    int* flags;             // [env][ins]
-};
-
-// pair list access for both paths
-struct PairSource {
-    const unsigned* small_pairs; int small_cap;           // [env][ins][cap] packed (a << 15 | b)
-    const int3* large_sorted; const unsigned* seg_start;  // sorted (prob, a, b) + per-problem segment starts
-    const int32_t* large_index;                           // instruction -> index in the large list or -1
-    int n_large;
-};
-
-// value part of the Dual context: what the Float64 pass of the same evaluation works with
 PFC_D void value_ctx(const PatchCtx<D6>& cx, PatchCtx<double>& v) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) { v.x21.r[i] = cx.x21.r[i].v; v.x12.r[i] = cx.x12.r[i].v; }
@@ -120,19 +99,9 @@ PFC_D void value_ctx(const PatchCtx<D6>& cx, PatchCtx<double>& v) {
     v.chi = cx.chi; v.Ebar1 = cx.Ebar1; v.Ebar2 = cx.Ebar2; v.n_quad = cx.n_quad;
 }
 
-// Two thirds of the candidate pairs clip to nothing.  Whether a pair survives is decided by value parts only (the clipper compares
-// values; the value part of every Dual operation used on the way is the Float64 operation), so the Float64 clip runs first and the
-// 7x more expensive Dual pipeline only sees the pairs that leave a polygon.
-PFC_D bool survives_f64(const SceneDev& sc, const InsDev& ins, int a, int b, const PatchCtx<double>& cxv) {
-    if (!prefilter_pair(sc, ins, a, b, cxv)) return false;
-    PolyRec<double> tmp;
-    int fl = 0;
-    const bool keep = clip_pair(sc, ins, a, b, cxv, tmp, fl);
-    return keep || fl != 0;   // error paths (non-finite vertex) are left to the Dual pass, which records the flag
-}
-
+// not inlined: the bristle branch makes four passes over the pair list, and four inlined copies of the Dual<6> pipeline cost ptxas minutes
 template <int NA>
-PFC_D void run_pairs_dual(const SceneDev& sc, const InsDev& ins, const PairSource& ps, long long env, int k, long long ei, int n, int lane,
+__device__ __noinline__ void run_pairs_dual(const SceneDev& sc, const InsDev& ins, const PairSource& ps, long long env, int k, long long ei, int n, int lane,
                           const PatchCtx<D6>& cx, const PatchCtx<double>& cxv, Accum<D6, NA>& acc, int& flags) {
     if (ins.small) {
         const unsigned* pl = ps.small_pairs + (size_t)ps.small_cap * ei;
@@ -292,151 +261,6 @@ __global__ void __launch_bounds__(128) eval_dual6_kernel(SceneDev sc, DualIO io,
     }
 }
 
-// ---- regularized-only scenes: the 6 partials in three chunks of 2 ---------------------------------------------------------------
-// One sub-triangle on Dual<6> keeps ~240 doubles alive (its polygon, the twist, the accumulators, temporaries): twice the register
-// file per thread, so the kernel above spills ~9 KB per thread and runs out of DRAM bandwidth (ncu: 6 GB of local-memory traffic per
-// launch, 8 lanes of 32 busy).  A Dual<2> needs 3 doubles per scalar instead of 7: the same pipeline fits in registers, and carrying
-// the 6 partials as 3 independent (pair, chunk) items triples the number of busy lanes.  The value part is recomputed by every chunk
-// (9 instead of 7 units of work per pair); the three chunks of a pair produce bit-identical value parts, chunk 0's is the one stored.
-typedef Dual<2> D2;
-constexpr int kChunkSlots = 10;   // surviving pairs per round: 3 chunks x 10 pairs = 30 lanes
-
-struct Chunk3Smem {
-    PatchCtx<D2> cx[3];
-    double acc[30][19];   // per lane: 6 sums x (value, 2 partials), padded to an odd stride
-    int pts[30];
-    double wout[42];      // the instruction's wrench: 6 components x (value, 6 partials)
-};
-
-__global__ void __launch_bounds__(128) eval_dual6_chunked_kernel(SceneDev sc, DualIO io, PairSource ps) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Chunk3Smem& sm = reinterpret_cast<Chunk3Smem*>(smem_raw)[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const int chunk = lane / kChunkSlots, slot = lane - chunk * kChunkSlots;   // lanes 30, 31: chunk 3 = idle
-    const long long n_prob = io.n_env * sc.n_ins;
-    for (long long ei = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); ei < n_prob; ei += (long long)gridDim.x * 4) {
-        const long long env = ei / sc.n_ins;
-        const int k = int(ei - env * sc.n_ins);
-        const InsDev& ins = sc.ins[k];
-        const int n = (int)io.n_pairs[ei];
-        int flags = 0;
-        bool contact = false;
-        for (int j = lane; j < 42; j += 32) sm.wout[j] = 0.0;
-        if (n > 0) {
-            const double* Xp = io.X7 + 112 * ei;
-            const double* tw = io.twist7 + 42 * ei;
-            // is any input of this instruction seeded?  (lanes share the 18 x 6 partials)
-            bool mine = false;
-            for (int e = lane; e < 18 * 6; e += 32) {
-                const int sc_i = e / 6, q = e - sc_i * 6;
-                const double* base = sc_i < 12 ? Xp + 7 * (sc_i < 9 ? (4 * (sc_i % 3) + sc_i / 3) : (12 + sc_i - 9)) : tw + 7 * (sc_i - 12);
-                mine |= (base[1 + q] != 0.0);
-            }
-            const bool seeded = __any_sync(0xffffffffu, mine);
-            __syncwarp();
-            if (lane < 3) {   // chunk `lane`'s context: partials 2 lane and 2 lane + 1
-                PatchCtx<D2>& cx = sm.cx[lane];
-                auto ld = [&](const double* p7) { D2 r; r.v = p7[0]; r.p[0] = p7[1 + 2 * lane]; r.p[1] = p7[2 + 2 * lane]; return r; };
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) cx.x21.r[3 * i + j] = ld(Xp + 7 * (4 * j + i));
-                    cx.x21.t[i] = ld(Xp + 7 * (12 + i));
-                }
-                cx.x12 = inverse(cx.x21);
-                cx.w_ang = mk<D2>(ld(tw), ld(tw + 7), ld(tw + 14));
-                cx.w_lin = mk<D2>(ld(tw + 21), ld(tw + 28), ld(tw + 35));
-                cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
-            }
-            __syncwarp();
-            PatchCtx<double> cxv;
-            {
-                const PatchCtx<D2>& c0 = sm.cx[0];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) { cxv.x21.r[i] = c0.x21.r[i].v; cxv.x12.r[i] = c0.x12.r[i].v; }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) { cxv.x21.t[i] = c0.x21.t[i].v; cxv.x12.t[i] = c0.x12.t[i].v; }
-                cxv.w_ang = mk<double>(c0.w_ang.x.v, c0.w_ang.y.v, c0.w_ang.z.v);
-                cxv.w_lin = mk<double>(c0.w_lin.x.v, c0.w_lin.y.v, c0.w_lin.z.v);
-                cxv.chi = c0.chi; cxv.Ebar1 = c0.Ebar1; cxv.Ebar2 = c0.Ebar2; cxv.n_quad = c0.n_quad;
-            }
-            const unsigned* pl_s = ins.small ? ps.small_pairs + (size_t)ps.small_cap * ei : nullptr;
-            const int3* pl_l = ins.small ? nullptr : ps.large_sorted + ps.seg_start[env * ps.n_large + ps.large_index[k]];
-            if (!seeded) {   // Float64 evaluation (see eval_dual6_kernel)
-                Accum<double, 6> av;
-                av.fp = ins.p; av.w_ang = cxv.w_ang; av.w_lin = cxv.w_lin; av.dump = nullptr; av.dump_cap = 0;
-                av.reset(ACC_REGULARIZED);
-                for (int i = lane; i < n; i += 32) {
-                    int a, b;
-                    if (ins.small) { const unsigned e = pl_s[i]; a = int((e >> 15) & 0x7fffu); b = int(e & 0x7fffu); }
-                    else { const int3 e = pl_l[i]; a = e.y; b = e.z; }
-                    if (prefilter_pair(sc, ins, a, b, cxv)) integrate_pair(sc, ins, a, b, cxv, av, flags);
-                }
-                int pts = av.n_points;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(0xffffffffu, pts, o);
-                contact = pts > 0;
-                double wv[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) wv[j] = warp_sum(av.a[j]);
-                __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) sm.wout[7 * j] = wv[j];   // value slots; the partial slots stay 0
-                }
-            } else {
-                Accum<D2, 6> acc;
-                const PatchCtx<D2>& cx = sm.cx[chunk < 3 ? chunk : 0];
-                acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
-                acc.reset(ACC_REGULARIZED);
-                for (int base = 0; base < n; base += 32) {
-                    const int i = base + lane;
-                    int a = 0, b = 0;
-                    bool keep = false;
-                    if (i < n) {
-                        if (ins.small) { const unsigned e = pl_s[i]; a = int((e >> 15) & 0x7fffu); b = int(e & 0x7fffu); }
-                        else { const int3 e = pl_l[i]; a = e.y; b = e.z; }
-                        keep = survives_f64(sc, ins, a, b, cxv);
-                    }
-                    unsigned m = __ballot_sync(0xffffffffu, keep);
-                    while (m) {   // rounds of kChunkSlots survivors, each handled by three lanes (one per chunk of partials)
-                        const unsigned src = __fns(m, 0, slot + 1);            // the lane that holds survivor `slot` of this round
-                        const int pa = __shfl_sync(0xffffffffu, a, src & 31u), pb = __shfl_sync(0xffffffffu, b, src & 31u);
-                        if (chunk < 3 && src <= 31u) integrate_pair(sc, ins, pa, pb, cx, acc, flags);
-#pragma unroll 1
-                        for (int r = 0; r < kChunkSlots && m; ++r) m &= m - 1;
-                    }
-                }
-                // per-lane sums -> shared memory -> one lane per output scalar adds its ten contributions in slot order
-                __syncwarp();
-                if (lane < 30) {
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) { sm.acc[lane][3 * j] = acc.a[j].v; sm.acc[lane][3 * j + 1] = acc.a[j].p[0]; sm.acc[lane][3 * j + 2] = acc.a[j].p[1]; }
-                    sm.pts[lane] = acc.n_points;
-                }
-                __syncwarp();
-                int pts = 0;
-                for (int r = 0; r < kChunkSlots; ++r) pts += sm.pts[r];
-                contact = pts > 0;
-                for (int j = lane; j < 42; j += 32) {
-                    const int comp = j / 7, which = j - 7 * comp;
-                    const int c = which == 0 ? 0 : (which - 1) / 2, col = which == 0 ? 0 : 1 + (which - 1) % 2;
-                    double sum = 0.0;
-                    for (int r = 0; r < kChunkSlots; ++r) sum += sm.acc[c * kChunkSlots + r][3 * comp + col];
-                    sm.wout[j] = sum;
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o);
-        __syncwarp();
-        double* wo = io.wrench7 + 42 * ei;
-        for (int j = lane; j < 42; j += 32) wo[j] = contact ? sm.wout[j] : 0.0;
-        if (lane == 0) io.flags[ei] = (io.flags[ei] & ~kFlagContact) | flags | (contact ? kFlagContact : 0);
-        __syncwarp();
-    }
-}
-
 }  // namespace
 
 const unsigned* large_seg_start_ptr(const LargeBuffers* b);
@@ -453,10 +277,7 @@ cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double*
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const unsigned blocks = (unsigned)std::min<long long>((n_prob + 3) / 4, (long long)n_sm * 8);
     if (sc.n_bristle > 0) eval_dual6_kernel<true><<<blocks, 128, 0, stream>>>(sc, io, ps);
-    else {
-        const unsigned blocks_c = (unsigned)std::min<long long>((n_prob + 3) / 4, (long long)n_sm * 4);
-        eval_dual6_chunked_kernel<<<blocks_c, 128, sizeof(Chunk3Smem) * 4, stream>>>(sc, io, ps);
-    }
+    else return launch_eval_dual6_chunked(sc, io, ps, n_prob, n_sm, stream);
     return cudaGetLastError();
 }
 

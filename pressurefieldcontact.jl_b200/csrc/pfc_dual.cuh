@@ -1,0 +1,45 @@
+// pfc_dual.cuh -- declarations shared by the two translation units of the Jacobian mode (pfc_dual.cu: Dual<6> kernel for scenes with
+// bristle friction + the launcher; pfc_dual_chunked.cu: the Dual<2> x 3 kernel for regularized-only scenes).  ptxas needs minutes for
+// each of the two kernels; separate files let them compile in parallel.
+#pragma once
+#include "pfc_large.h"
+#include "pfc_patch.cuh"
+
+namespace pfc {
+
+struct DualIO {
+    long long n_env;
+    const double* X7;       // [env][ins][16][7]
+    const double* twist7;   // [env][ins][6][7]
+    const double* s7;       // [env][bristle][6][7]
+    double* wrench7;        // [env][ins][6][7]
+    double* sdot7;          // [env][bristle][6][7]
+    const long long* n_pairs;  // [env][ins] (from the Float64 broad phase)
+    int* flags;             // [env][ins]
+};
+
+// pair list access for both paths
+struct PairSource {
+    const unsigned* small_pairs; int small_cap;           // [env][ins][cap] packed (a << 15 | b)
+    const int3* large_sorted; const unsigned* seg_start;  // sorted (prob, a, b) + per-problem segment starts
+    const int32_t* large_index;                           // instruction -> index in the large list or -1
+    int n_large;
+};
+
+// value part of the Dual context: what the Float64 pass of the same evaluation works with
+
+// Two thirds of the candidate pairs clip to nothing.  Whether a pair survives is decided by value parts only (the clipper compares
+// values; the value part of every Dual operation used on the way is the Float64 operation), so the Float64 clip runs first and the
+// 7x more expensive Dual pipeline only sees the pairs that leave a polygon.
+PFC_D bool survives_f64(const SceneDev& sc, const InsDev& ins, int a, int b, const PatchCtx<double>& cxv) {
+    if (!prefilter_pair(sc, ins, a, b, cxv)) return false;
+    PolyRec<double> tmp;
+    int fl = 0;
+    const bool keep = clip_pair(sc, ins, a, b, cxv, tmp, fl);
+    return keep || fl != 0;   // error paths (non-finite vertex) are left to the Dual pass, which records the flag
+}
+
+// implemented in pfc_dual_chunked.cu
+cudaError_t launch_eval_dual6_chunked(const SceneDev& sc, const DualIO& io, const PairSource& ps, long long n_prob, int n_sm, cudaStream_t stream);
+
+}  // namespace pfc
