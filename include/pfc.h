@@ -146,12 +146,14 @@ int pfc_get_pairs(pfc_ctx* ctx, int64_t env, int ins, int32_t* pairs, int64_t ca
 /* TractionCache (src/mechanism_scenario.jl:51-58) of (env, ins) from the last evaluation: 8 doubles per point: n(3), r_cart(3), dA, p. */
 int pfc_get_traction(pfc_ctx* ctx, int64_t env, int ins, double* out, int64_t cap_points, int64_t* n_out);
 
-/* Multi-GPU for one very large scene: this context evaluates only slice `rank` of `world` of every
- * large instruction's sorted pair list; the caller sums wrench_r2 across ranks (NCCL allreduce). */
+/* Multi-GPU for one very large scene: this context traverses, lists and evaluates only the sub-trees of every large instruction's
+ * dual-tree recursion whose hash falls on `rank` of `world` (disjoint pair lists, no exchange before the sums); the caller sums the
+ * partial buffers across ranks (NCCL allreduce).  pfc_get_pairs then returns this rank's part of the list. */
 int pfc_set_shard(pfc_ctx* ctx, int rank, int world);
 /* Sharded evaluation protocol (device pointers, asynchronous on the context's stream):
- *   begin:    traversal + sort (every rank, identical) and stage 0 over this rank's slice of the 256-pair chunks;
- *   partials: the buffer the caller must sum over all ranks in place: count doubles (22 per (env, large instruction));
+ *   begin:    breadth-first levels (every rank), this rank's share of the traversal, sort, stage 0 over its own pairs;
+ *   partials: the buffer the caller must sum over all ranks in place: count doubles (23 per (env, large instruction): 21 sums,
+ *             traction-point count, pair count);
  *   step:     applies the summed buffer (wrench / bristle state) and, if the friction model needs another pass
  *             (bristle: centre of pressure -> stiffness -> friction), runs it and sets *more = 1. */
 int pfc_eval_sharded_begin(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2,

@@ -442,7 +442,7 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
         if (c->shard_world > 1) return fail(PFC_E_ARG, "this context is sharded: use pfc_eval_sharded_begin / _step");
         CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
         const int n_stage = scene_has_large_bristle(c) ? 3 : 1;
-        for (int st = 0; st < n_stage; ++st) CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, st, 0, 1, 0, c->stream, &nl));
+        for (int st = 0; st < n_stage; ++st) CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, st, 0, 0, c->stream, &nl));
     }
     c->launches += nl;
     c->last_X = io.X; c->last_tw = io.twist;
@@ -521,9 +521,9 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
         CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins));
         CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
     }
-    CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
-    // world == 1 still goes through the partial buffer so that the protocol is identical
-    CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, 0, c->shard_rank, c->shard_world, 0, c->stream, &nl));
+    // every rank runs the breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair lists
+    CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl, c->shard_rank, c->shard_world));
+    CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, 0, c->shard_world > 1, 0, c->stream, &nl));
     c->launches += nl;
     c->sharded_io = io;
     c->sharded_stage = 0;
@@ -544,10 +544,10 @@ int pfc_eval_sharded_step(pfc_ctx* c, int* more) {
     int nl = 0;
     const int n_stage = scene_has_large_bristle(c) ? 3 : 1;
     if (c->shard_world > 1)  // the caller has summed the partial buffer over the ranks: apply it
-        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, c->shard_rank, c->shard_world, 1, c->stream, &nl));
+        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, 1, 1, c->stream, &nl));
     if (c->sharded_stage + 1 < n_stage) {
         ++c->sharded_stage;
-        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, c->shard_rank, c->shard_world, 0, c->stream, &nl));
+        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, c->shard_world > 1, 0, c->stream, &nl));
         *more = 1;
     } else {
         c->sharded_stage = -1;

@@ -49,6 +49,7 @@ constexpr int kStackCap = 1024;   // node pairs per warp stack (8 KB)
 constexpr int kDfsWarps = 4;
 constexpr int kChunk = 256;       // pairs per reduction chunk (= narrow kernel block size)
 constexpr int kNA = 21;           // accumulator slots per chunk partial
+static_assert(kLargePartStride == kNA + 2, "partial record = kNA sums + point count + pair count");
 
 struct Counters {                 // device-resident
     unsigned int frontier_n[2];   // BFS ping-pong frontier sizes
@@ -135,8 +136,18 @@ __global__ void init_frontier_kernel(LargeScene ls, long long n_env, Seed* front
 }
 
 // K1a: one level of breadth-first expansion (order is irrelevant here: the sort restores it)
+// Multi-GPU split of one large scene: every rank runs the (cheap) breadth-first levels, then owns the seeds -- and the leaf pairs the
+// breadth-first levels emit directly -- whose hash falls on it.  A sub-tree is traversed by exactly one rank, so the pair lists of the
+// ranks are disjoint and their union is the full list; nothing is exchanged before the per-instruction partial sums.
+PFC_D unsigned item_hash(int prob, int a, int b) {
+    unsigned h = (unsigned)prob * 0x9E3779B1u ^ (unsigned)a * 0x85EBCA77u ^ (unsigned)b * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+
 __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, const Seed* __restrict__ in, Seed* out,
-                                                        int src, unsigned cap_frontier, int3* pairs, unsigned cap_pairs, Counters* cnt) {
+                                                        int src, unsigned cap_frontier, int3* pairs, unsigned cap_pairs, Counters* cnt,
+                                                        unsigned hrank, unsigned hworld) {
     const unsigned n = cnt->frontier_n[src];
     const int lane = threadIdx.x & 31;
     for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
@@ -163,12 +174,13 @@ __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene 
         at = __shfl_sync(0xffffffffu, at, 31) + incl - n_child;
         if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, 0u, ch[c].x, ch[c].y}; }
         else if (n_child > 0) atomicOr(&cnt->overflow, 1u);
-        const unsigned leaf_mask = __ballot_sync(0xffffffffu, r < 0);
+        const bool emit = r < 0 && (hworld == 1u || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
+        const unsigned leaf_mask = __ballot_sync(0xffffffffu, emit);
         if (leaf_mask) {
             unsigned pat = 0;
             if (lane == 0) pat = atomicAdd(&cnt->n_pairs, (unsigned)__popc(leaf_mask));
             pat = __shfl_sync(0xffffffffu, pat, 0) + __popc(leaf_mask & ((1u << lane) - 1u));
-            if (r < 0) { if (pat < cap_pairs) pairs[pat] = make_int3(s.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u); }
+            if (emit) { if (pat < cap_pairs) pairs[pat] = make_int3(s.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u); }
         }
     }
 }
@@ -183,7 +195,8 @@ PFC_D unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<con
 
 // K1b: warp-cooperative stack-based traversal of the seeds, with work donation
 __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, Seed* seeds, unsigned cap_seeds,
-                                                                   unsigned epoch, int3* pairs, unsigned cap_pairs, Counters* cnt) {
+                                                                   unsigned epoch, int3* pairs, unsigned cap_pairs, Counters* cnt, unsigned hrank,
+                                                                   unsigned hworld) {
     __shared__ int2 stack_mem[kDfsWarps][kStackCap];   // per-warp circular stack: entry i lives at (base + i) & (kStackCap - 1)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int2* stack = stack_mem[wib];
@@ -200,6 +213,10 @@ __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, 
             const unsigned ticket = atomicAdd(&cnt->q_head, 1u);
             if (ticket < n_seed0) {
                 seed = seeds[ticket];
+                if (hworld > 1u && item_hash(seed.prob, seed.a, seed.b) % hworld != hrank) {   // another rank's sub-tree
+                    atomicSub(&cnt->outstanding, 1);
+                    seed.prob = -2;
+                }
             } else {
                 unsigned backoff = 64, spins = 0;
                 for (;;) {
@@ -221,6 +238,7 @@ __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, 
         seed.prob = __shfl_sync(0xffffffffu, seed.prob, 0);
         seed.a = __shfl_sync(0xffffffffu, seed.a, 0);
         seed.b = __shfl_sync(0xffffffffu, seed.b, 0);
+        if (seed.prob == -2) continue;
         if (seed.prob < 0) break;
         long long env; int k;
         prob_to_ei(sc, ls, seed.prob, env, k);
@@ -555,8 +573,8 @@ __global__ void __launch_bounds__(128) finish_large_kernel(SceneDev sc, LargeSce
         int pts = 0;
         const int n_acc = bristle ? (stage == 1 ? 21 : (stage == 0 ? 10 : 6)) : 6;
         if (apply_parts) {  // sums were reduced across ranks by the caller: part_out[p][kNA + 1]
-            for (int j = 0; j < n_acc; ++j) sum[j] = part_out[(size_t)p * (kNA + 1) + j];
-            pts = (int)part_out[(size_t)p * (kNA + 1) + kNA];
+            for (int j = 0; j < n_acc; ++j) sum[j] = part_out[(size_t)p * kLargePartStride + j];
+            pts = (int)part_out[(size_t)p * kLargePartStride + kNA];
         } else {
             // lane l sums chunks l, l+32, ... of this problem in order; then a fixed butterfly
             unsigned c0 = unit_start[p], c1 = unit_start[p + 1];
@@ -571,11 +589,13 @@ __global__ void __launch_bounds__(128) finish_large_kernel(SceneDev sc, LargeSce
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(0xffffffffu, pts, o);
             if (part_out) {  // sharded: hand the partial sums to the caller and stop here
-                if (lane == 0) { for (int j = 0; j < kNA; ++j) part_out[(size_t)p * (kNA + 1) + j] = j < n_acc ? sum[j] : 0.0; part_out[(size_t)p * (kNA + 1) + kNA] = (double)pts; }
+                if (lane == 0) { for (int j = 0; j < kNA; ++j) part_out[(size_t)p * kLargePartStride + j] = j < n_acc ? sum[j] : 0.0; part_out[(size_t)p * kLargePartStride + kNA] = (double)pts;
+                                 part_out[(size_t)p * kLargePartStride + kNA + 1] = (double)(seg_end[p] - seg_start[p]); }
                 continue;
             }
         }
-        const long long n_pairs = (long long)seg_end[p] - (long long)seg_start[p];
+        // sharded: the ranks hold disjoint parts of the pair list; the count travels with the partial sums
+        const long long n_pairs = apply_parts ? (long long)part_out[(size_t)p * kLargePartStride + kNA + 1] : (long long)seg_end[p] - (long long)seg_start[p];
         double* wo = io.wrench + 6 * ei;
         if (!bristle) {
             if (lane == 0) {
@@ -727,7 +747,8 @@ cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const E
 // Broad phase + sort + segments.  Synchronises once (reads the pair count) so that capacities can
 // grow like the reference's VectorCache (src/obb/vector_cache.jl:11-15): on overflow the buffers are
 // doubled and the traversal is re-run.
-cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches) {
+cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches,
+                              int hash_rank, int hash_world) {
     const long long n_prob_ll = io.n_env * ls.n_large;
     if (n_prob_ll <= 0) return cudaSuccess;
     if (n_prob_ll > (1LL << 30)) return cudaErrorInvalidValue;
@@ -747,6 +768,9 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     // BFS levels until about one seed per resident warp could exist (4^L * n_prob >= target); donation balances the rest
     int levels = 0;
     { double f = (double)n_prob; const double target = 1.0 * dfs_blocks * kDfsWarps; while (f < target && levels < 12) { f *= 4.0; ++levels; } }
+    // split over several GPUs: a contact patch is small against the meshes, so a few sub-trees carry nearly all of the work; three more
+    // breadth-first levels make the hash-partitioned pieces ~64x finer, which is what balances the ranks (inside a GPU, donation does)
+    if (hash_world > 1) levels = std::min(levels + 3, 14);
     for (int attempt = 0; attempt < 8; ++attempt) {
         LCU(ensure(b->frontier[0], b->cap_frontier, want_frontier));
         LCU(ensure(b->frontier[1], b->cf2, want_frontier));
@@ -756,13 +780,14 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
         for (int l = 0; l < levels; ++l) {
             if (l > 0) { /* the level's output counter must start at zero */ }
             broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, ls, io.X, b->frontier[src], b->frontier[src ^ 1], src, (unsigned)b->cap_frontier, b->pairs,
-                                                         (unsigned)b->cap_pairs, b->cnt);
+                                                         (unsigned)b->cap_pairs, b->cnt, (unsigned)hash_rank, (unsigned)hash_world);
             // reset the consumed frontier's counter for its next use as an output
             LCU(cudaMemsetAsync(&b->cnt->frontier_n[src], 0, sizeof(unsigned), stream));
             src ^= 1;
         }
         dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, src);
-        broad_dfs_kernel<<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs, b->cnt);
+        broad_dfs_kernel<<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs, b->cnt,
+                                                                  (unsigned)hash_rank, (unsigned)hash_world);
         if (n_launches) *n_launches += 3 + levels;
         Counters h;
         LCU(cudaMemcpyAsync(&h, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -814,10 +839,11 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
 
 // Narrow phase + friction + reduction for the pair lists produced by large_broad_phase.
 // shard_world > 1: this context sums only its slice of the chunks and leaves per-problem partial sums
-// (kNA + 1 doubles each) in large_part_buffer() after each stage; the caller allreduces them and calls
+// (kLargePartStride doubles each) in large_part_buffer() after each stage; the caller allreduces them and calls
 // large_narrow_stage again with apply_parts = 1.
-cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int shard_rank, int shard_world,
+cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int partial_only,
                                int apply_parts, cudaStream_t stream, int* n_launches) {
+    const int shard_rank = 0, shard_world = 1;   // the pair list of a sharded context is already its own part (hash-partitioned traversal)
     const unsigned n_prob = (unsigned)(io.n_env * ls.n_large);
     if (n_prob == 0) return cudaSuccess;
     const unsigned n = b->last_n_pairs;
@@ -826,7 +852,7 @@ cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const E
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     LCU(ensure(b->chunk_out, b->cap_chunk, max_units * kNA));
     LCU(ensure(b->chunk_points, b->cap_cp, max_units));
-    if (shard_world > 1) LCU(ensure(b->part, b->cap_part, (size_t)n_prob * (kNA + 1)));
+    if (partial_only) LCU(ensure(b->part, b->cap_part, (size_t)n_prob * kLargePartStride));
     const int mode_reg = stage == 0 ? ACC_REGULARIZED : -1;
     const int mode_bri = stage == 0 ? ACC_COP : (stage == 1 ? ACC_STIFFNESS : ACC_BRISTLE);
     if (!apply_parts) {
@@ -837,7 +863,7 @@ cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const E
     }
     finish_large_kernel<<<std::min<unsigned>((n_prob + 3) / 4, (unsigned)n_sm * 8), 128, 0, stream>>>(
         sc, ls, io, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, stage, b->ps, b->chunk_out, b->chunk_points, b->prob_flags, (unsigned)shard_rank,
-        (unsigned)shard_world, (shard_world > 1) ? b->part : nullptr, apply_parts);
+        (unsigned)shard_world, partial_only ? b->part : nullptr, apply_parts);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -20,15 +20,19 @@ struct LargeBuffers;
 LargeBuffers* large_buffers_create();
 void large_buffers_destroy(LargeBuffers* b);
 
-cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches);
+// hash_rank / hash_world: multi-GPU split of one large scene -- this context traverses (and lists) only the sub-trees whose hash falls on it
+cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches,
+                              int hash_rank = 0, int hash_world = 1);
 // stage 0: regularized wrench / bristle centre of pressure; 1: bristle stiffness; 2: bristle friction
-cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int shard_rank, int shard_world,
+// partial_only: leave the per-problem partial sums (+ point and pair counts) in large_part_buffer() for the caller's allreduce;
+// apply_parts: the buffer holds the sums over all ranks -- finish the stage from it
+cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int partial_only,
                                int apply_parts, cudaStream_t stream, int* n_launches);
 cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream);
 unsigned large_last_pairs(const LargeBuffers* b);
 unsigned long long large_last_tests(const LargeBuffers* b);
-double* large_part_buffer(LargeBuffers* b);     // [n_problem][22] partial sums of the last stage (sharded mode)
-constexpr int kLargePartStride = 22;
+double* large_part_buffer(LargeBuffers* b);     // [n_problem][23]: 21 partial sums, point count, pair count of the last stage (sharded mode)
+constexpr int kLargePartStride = 23;
 cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, long long* n_out, cudaStream_t stream);
 
 // Jacobian mode (pfc_dual.cu): narrow phase + friction + reduction on Dual<6> over existing pair lists.

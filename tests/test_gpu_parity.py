@@ -372,8 +372,9 @@ def test_large_path_no_contact_and_empty():
 
 def test_sharded_large_scene_two_ranks_on_one_gpu():
     """The multi-GPU split of one large scene, emulated with two contexts (rank 0 and 1 of world 2) on
-    one GPU: each evaluates its slice of the chunks, the partial buffers are summed (what the NCCL
-    allreduce does), and both end with the same wrench / s-dot as the unsharded evaluation."""
+    one GPU: each traverses and evaluates the sub-trees whose hash falls on it (disjoint pair lists), the
+    partial buffers are summed (what the NCCL allreduce does), and both end with the same wrench / s-dot /
+    pair counts as the unsharded evaluation."""
     import torch
     from pfc_b200 import capi, parallel
     n_env = 2
@@ -404,7 +405,7 @@ def test_sharded_large_scene_two_ranks_on_one_gpu():
         for ctx, _ in ranks:
             ctx.sync()
             ptr, count = ctx.eval_sharded_partials()
-            assert count == 22 * n_env * 3
+            assert count == 23 * n_env * 3   # 21 sums + point count + pair count per (environment, large instruction)
             parts.append((ptr, count))
         # the "allreduce": sum the two device buffers and write the sum back into both
         import ctypes
@@ -425,7 +426,7 @@ def test_sharded_large_scene_two_ranks_on_one_gpu():
         ctx.sync()
         w = b["w"].cpu().numpy()
         scale = np.abs(full["wrench"]).max()
-        assert wrench_rel_err(w, full["wrench"], floor=1e-9 * scale) <= 1e-12   # same chunk sums, different association only
+        assert wrench_rel_err(w, full["wrench"], floor=1e-9 * scale) <= 1e-11   # same traction points, different association only
         assert (b["np_"].cpu().numpy() == full["n_pairs"]).all()
         assert ((b["fl"].cpu().numpy() & 1) == (full["flags"] & 1)).all()
         assert np.allclose(b["sd"].cpu().numpy(), full["sdot"], rtol=1e-6, atol=1e-9 * np.abs(full["sdot"]).max())
