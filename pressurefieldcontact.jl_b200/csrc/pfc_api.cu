@@ -120,6 +120,12 @@ struct pfc_ctx {
     struct RefitDev { DevBuf<int> idx; DevBuf<double> eps; DevBuf<int> level_nodes; std::vector<int> level_ptr; bool ready = false; };
     std::vector<RefitDev> refit;
     DevBuf<double> d_refit_xyz, d_refit_aabb;
+    // pinned staging arena for small host-pointer calls (a single scene moves a few hundred bytes per array: copying through pinned
+    // memory keeps every cudaMemcpyAsync truly asynchronous instead of the driver's staged, synchronising path for pageable memory)
+    unsigned char* h_arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
+    struct PendingOut { void* dst; const void* src; size_t bytes; };
+    std::vector<PendingOut> arena_out;
     bool large_index_dirty = true;   // d_large_index (instruction -> index in the large list) needs uploading
     int* h_status = nullptr;    // pinned
     DynDev dyn{};
@@ -203,6 +209,7 @@ int pfc_destroy(pfc_ctx* c) {
     c->d_H.release(); c->d_Hinv.release(); c->d_xdot.release(); c->d_tau.release(); c->d_status.release(); c->d_refit_xyz.release(); c->d_refit_aabb.release();
     for (auto& r : c->refit) { r.idx.release(); r.eps.release(); r.level_nodes.release(); }
     if (c->h_status) { cudaFreeHost(c->h_status); c->h_status = nullptr; }
+    if (c->h_arena) { cudaFreeHost(c->h_arena); c->h_arena = nullptr; }
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     c->d_large.release(); c->d_leaf_path.release(); c->d_leaf_depth.release();
     c->d_X7.release(); c->d_tw7.release(); c->d_s7.release(); c->d_w7.release(); c->d_sd7.release(); c->d_large_index.release();
@@ -453,6 +460,34 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
     return PFC_OK;
 }
 
+// ---- small host-pointer calls: copies through a pinned arena ----------------------------------------------------------------
+constexpr size_t kArenaBytes = 256 << 10;
+static void arena_reset(pfc_ctx* c) {
+    if (!c->h_arena && cudaHostAlloc(reinterpret_cast<void**>(&c->h_arena), kArenaBytes, cudaHostAllocDefault) == cudaSuccess) c->arena_cap = kArenaBytes;
+    c->arena_used = 0;
+    c->arena_out.clear();
+}
+static void* arena_take(pfc_ctx* c, size_t bytes) {
+    const size_t a = (c->arena_used + 63) & ~size_t(63);
+    if (!c->h_arena || a + bytes > c->arena_cap) return nullptr;
+    c->arena_used = a + bytes;
+    return c->h_arena + a;
+}
+// host -> device on the context's stream; small transfers go through the arena
+static cudaError_t copy_in(pfc_ctx* c, void* dev, const void* host, size_t bytes) {
+    if (void* p = arena_take(c, bytes)) { std::memcpy(p, host, bytes); host = p; }
+    return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream);
+}
+// device -> host; small transfers land in the arena and are handed to the caller's buffer by copy_out_finish (after the stream sync)
+static cudaError_t copy_out(pfc_ctx* c, void* host, const void* dev, size_t bytes) {
+    if (void* p = arena_take(c, bytes)) { c->arena_out.push_back({host, p, bytes}); host = p; }
+    return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream);
+}
+static void copy_out_finish(pfc_ctx* c) {
+    for (const auto& o : c->arena_out) std::memcpy(o.dst, o.src, o.bytes);
+    c->arena_out.clear();
+}
+
 int pfc_eval_f64_device(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
                         int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_f64_device: context not finalized");
@@ -479,22 +514,24 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
     CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni));
     CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
     if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_sd.ensure(6 * ne * nb)); }
-    CU(cudaMemcpyAsync(c->d_X.p, X, sizeof(double) * 16 * ne * ni, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_tw.p, twist, sizeof(double) * 6 * ne * ni, cudaMemcpyHostToDevice, c->stream));
-    if (nb) CU(cudaMemcpyAsync(c->d_s.p, s, sizeof(double) * 6 * ne * nb, cudaMemcpyHostToDevice, c->stream));
+    arena_reset(c);
+    CU(copy_in(c, c->d_X.p, X, sizeof(double) * 16 * ne * ni));
+    CU(copy_in(c, c->d_tw.p, twist, sizeof(double) * 6 * ne * ni));
+    if (nb) CU(copy_in(c, c->d_s.p, s, sizeof(double) * 6 * ne * nb));
     EvalIO io{};
     io.n_env = n_env; io.X = c->d_X.p; io.twist = c->d_tw.p; io.s = nb ? c->d_s.p : nullptr; io.wrench = c->d_w.p;
     io.sdot = nb ? c->d_sd.p : nullptr; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
     int rc = eval_device(c, io);
     if (rc != PFC_OK) return rc;
-    CU(cudaMemcpyAsync(wrench, c->d_w.p, sizeof(double) * 6 * ne * ni, cudaMemcpyDeviceToHost, c->stream));
-    if (nb) CU(cudaMemcpyAsync(sdot, c->d_sd.p, sizeof(double) * 6 * ne * nb, cudaMemcpyDeviceToHost, c->stream));
-    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    CU(copy_out(c, wrench, c->d_w.p, sizeof(double) * 6 * ne * ni));
+    if (nb) CU(copy_out(c, sdot, c->d_sd.p, sizeof(double) * 6 * ne * nb));
+    if (n_pairs) CU(copy_out(c, n_pairs, c->d_np.p, sizeof(long long) * ne * ni));
     std::vector<int32_t> fl_local;
     int32_t* fl = flags;
     if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
-    CU(cudaMemcpyAsync(fl, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    CU(copy_out(c, fl, c->d_fl.p, sizeof(int32_t) * ne * ni));
     CU(cudaStreamSynchronize(c->stream));
+    copy_out_finish(c);
     c->lists_n_env = n_env;  // d_np / d_fl / pair lists of this evaluation can be reused by pfc_eval_dual6(X_bp = NULL)
     for (size_t k = 0; k < ne * ni; ++k) {
         if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
@@ -567,9 +604,10 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
     int nl = 0;
+    arena_reset(c);
     if (X_bp) {  // traverse with the Float64 transform (calcTriTetIntersections! always uses m.float)
         CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
-        CU(cudaMemcpyAsync(c->d_X.p, X_bp, sizeof(double) * 16 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+        CU(copy_in(c, c->d_X.p, X_bp, sizeof(double) * 16 * ne * ni));
         EvalIO io{};
         io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
         if (c->scene.n_small > 0) {
@@ -587,25 +625,29 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     }
     CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni));
     if (nb) { CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
-    CU(cudaMemcpyAsync(c->d_X7.p, X7, sizeof(double) * 112 * ne * ni, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_tw7.p, twist7, sizeof(double) * 42 * ne * ni, cudaMemcpyHostToDevice, c->stream));
-    if (nb) CU(cudaMemcpyAsync(c->d_s7.p, s7, sizeof(double) * 42 * ne * nb, cudaMemcpyHostToDevice, c->stream));
-    std::vector<int32_t> large_index(ni, -1);
-    for (size_t k = 0; k < c->large_ins_host.size(); ++k) large_index[c->large_ins_host[k]] = int32_t(k);
-    CU(c->d_large_index.ensure(ni));
-    CU(cudaMemcpyAsync(c->d_large_index.p, large_index.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice, c->stream));
+    CU(copy_in(c, c->d_X7.p, X7, sizeof(double) * 112 * ne * ni));
+    CU(copy_in(c, c->d_tw7.p, twist7, sizeof(double) * 42 * ne * ni));
+    if (nb) CU(copy_in(c, c->d_s7.p, s7, sizeof(double) * 42 * ne * nb));
+    if (c->d_large_index.n < ni || c->large_index_dirty) {   // instruction -> index in the large list: static, uploaded once
+        std::vector<int32_t> large_index(ni, -1);
+        for (size_t k = 0; k < c->large_ins_host.size(); ++k) large_index[c->large_ins_host[k]] = int32_t(k);
+        CU(c->d_large_index.ensure(ni));
+        CU(cudaMemcpy(c->d_large_index.p, large_index.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice));
+        c->large_index_dirty = false;
+    }
     CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p,
                          c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
                          c->large_scene.n_large, c->stream));
     c->launches += nl + 1;
-    CU(cudaMemcpyAsync(wrench7, c->d_w7.p, sizeof(double) * 42 * ne * ni, cudaMemcpyDeviceToHost, c->stream));
-    if (nb) CU(cudaMemcpyAsync(sdot7, c->d_sd7.p, sizeof(double) * 42 * ne * nb, cudaMemcpyDeviceToHost, c->stream));
-    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    CU(copy_out(c, wrench7, c->d_w7.p, sizeof(double) * 42 * ne * ni));
+    if (nb) CU(copy_out(c, sdot7, c->d_sd7.p, sizeof(double) * 42 * ne * nb));
+    if (n_pairs) CU(copy_out(c, n_pairs, c->d_np.p, sizeof(long long) * ne * ni));
     std::vector<int32_t> fl_local;
     int32_t* fl = flags;
     if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
-    CU(cudaMemcpyAsync(fl, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    CU(copy_out(c, fl, c->d_fl.p, sizeof(int32_t) * ne * ni));
     CU(cudaStreamSynchronize(c->stream));
+    copy_out_finish(c);
     for (size_t k = 0; k < ne * ni; ++k)
         if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
     return PFC_OK;
