@@ -435,6 +435,31 @@ __global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long 
     }
 }
 
+// Short lists (a single small scene): one CTA sorts (key, value) in shared memory with a bitonic network instead of 5 x 3 launches of
+// the radix passes.  Keys are distinct (a key encodes both root-to-leaf paths), so stability is not needed.
+constexpr unsigned kSmallSort = 2048;   // beyond a few thousand keys the radix passes win (measured: 6 695 keys, 421 vs 363 us per evaluation)
+__global__ void __launch_bounds__(1024) small_sort_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned n,
+                                                          unsigned long long* keys_out, unsigned* vals_out) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    unsigned m = 1;
+    while (m < n) m <<= 1;
+    unsigned long long* k = reinterpret_cast<unsigned long long*>(sort_smem);
+    unsigned* v = reinterpret_cast<unsigned*>(k + m);
+    for (unsigned i = threadIdx.x; i < m; i += blockDim.x) { k[i] = i < n ? keys_in[i] : ~0ull; v[i] = i < n ? vals_in[i] : 0u; }
+    __syncthreads();
+    for (unsigned size = 2; size <= m; size <<= 1)
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = threadIdx.x; t < m / 2; t += blockDim.x) {
+                const unsigned lo = 2 * t - (t & (stride - 1)), hi = lo + stride;   // the t-th compare-exchange of this step
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; const unsigned tv = v[lo]; v[lo] = v[hi]; v[hi] = tv; }
+            }
+            __syncthreads();
+        }
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) { keys_out[i] = k[i]; vals_out[i] = v[i]; }
+}
+
 // sorted order -> (prob, a, b) arrays + per-problem segments
 __global__ void gather_sorted_kernel(const int3* __restrict__ pairs, const unsigned* __restrict__ vals, unsigned n, int3* sorted, unsigned* seg_start, unsigned* seg_end) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -822,6 +847,16 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
         while ((1ull << prob_bits) < (unsigned long long)n_prob) ++prob_bits;
         const int total_bits = ls.key_bits + prob_bits;
         int cur = 0;
+        if (n <= kSmallSort) {
+            unsigned m = 1;
+            while (m < n) m <<= 1;
+            const size_t smem = (size_t)m * (sizeof(unsigned long long) + sizeof(unsigned));
+            static bool configured = false;
+            if (!configured) { LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12))); configured = true; }
+            small_sort_kernel<<<1, 1024, smem, stream>>>(b->keys[0], b->vals[0], n, b->keys[1], b->vals[1]);
+            cur = 1;
+            if (n_launches) *n_launches += 1;
+        } else
         for (int shift = 0; shift < total_bits; shift += 8) {
             radix_hist_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], n, shift, b->hist, n_tiles);
             radix_rowscan_kernel<<<256, 256, 0, stream>>>(b->hist, n_tiles, tot);
