@@ -78,7 +78,9 @@ int pfc_eval_f64(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const doubl
                  int64_t* n_pairs, int32_t* flags);
 
 /* Same evaluation on buffers already resident in device memory (all pointers are device pointers,
- * none may be NULL except s/sdot without bristles); enqueued on the context's stream, asynchronous. */
+ * none may be NULL except s/sdot without bristles); enqueued on the context's stream.  Asynchronous for scenes whose instructions all
+ * take the small path (n_leaf_1 * n_leaf_2 <= 512, e.g. test/boxes.jl); scenes with large instructions synchronise the stream once
+ * inside the call: the candidate-pair count is read back to size the sort and to grow the pair buffers like the reference's VectorCache. */
 int pfc_eval_f64_device(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2,
                         double* sdot, int64_t* n_pairs, int32_t* flags);
 
