@@ -393,6 +393,72 @@ PFC_D bool clip_pair_slot(const SceneDev& sc, const InsDev& ins, int prim1, int 
     return finish_polygon_slot(n, t2, mk<double>(plane[0] * inv_len, plane[1] * inv_len, plane[2] * inv_len), out);
 }
 
+// ---- stage A split in two, for the tile kernel's compacted clip ---------------------------------------------------------
+// start_polygon_zeta: everything before the first face cut -- the start polygon (the triangle, or the plane/tet section) in
+// tetrahedral coordinates of tet 2, in REGISTERS (zr[4 * k + i]); returns its vertex count, 0 when the pair is rejected (same
+// tests, same arithmetic as clip_pair_slot).  pair_normal: the polygon normal, recomputed from the records after the clip.
+PFC_D int start_polygon_zeta(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<double>& cx, double* zr) {
+    const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
+    if (ins.kind1 == 0) {
+        struct { double v[9]; double n[3]; } tri;
+        struct { double inv[16]; } t2r;
+        load_wide<12>(sc.tris[ins.prim_base1 + prim1].v, tri.v);
+        load_wide<16>(t2.inv, t2r.inv);
+        unsigned all_non_pos = 0xfu;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const Vec3<double> p = apply_d(cx.x21, mk<double>(tri.v[3 * k], tri.v[3 * k + 1], tri.v[3 * k + 2]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                zr[4 * k + i] = t2r.inv[4 * i] * p.x + t2r.inv[4 * i + 1] * p.y + t2r.inv[4 * i + 2] * p.z + t2r.inv[4 * i + 3];
+                if (!(zr[4 * k + i] <= 0.0)) all_non_pos &= ~(1u << i);
+            }
+        }
+        return all_non_pos ? 0 : 3;
+    }
+    const TetRec& t1 = sc.tets[ins.prim_base1 + prim1];
+    double plane[4];
+    {
+        const double g0 = cx.Ebar1 * t1.eps_r[0], g1 = cx.Ebar1 * t1.eps_r[1], g2 = cx.Ebar1 * t1.eps_r[2], g3 = cx.Ebar1 * t1.eps_r[3];
+        const Xform<double>& Y = cx.x12;
+        plane[0] = cx.Ebar2 * t2.eps_r[0] - (g0 * Y.r[0] + g1 * Y.r[3] + g2 * Y.r[6]);
+        plane[1] = cx.Ebar2 * t2.eps_r[1] - (g0 * Y.r[1] + g1 * Y.r[4] + g2 * Y.r[7]);
+        plane[2] = cx.Ebar2 * t2.eps_r[2] - (g0 * Y.r[2] + g1 * Y.r[5] + g2 * Y.r[8]);
+        plane[3] = cx.Ebar2 * t2.eps_r[3] - (g0 * Y.t[0] + g1 * Y.t[1] + g2 * Y.t[2] + g3);
+    }
+    Vec3<double> v[4], poly[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = apply_d(cx.x21, mk<double>(t1.v[3 * k], t1.v[3 * k + 1], t1.v[3 * k + 2]));
+    const int n0 = plane_tet(plane, v, poly);
+    if (n0 < 3) return 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < n0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double zz = t2.inv[4 * i] * poly[k].x + t2.inv[4 * i + 1] * poly[k].y + t2.inv[4 * i + 2] * poly[k].z + t2.inv[4 * i + 3];
+                zr[4 * k + i] = zz * ((1.0e-14 < fabs(zz)) ? 1.0 : 0.0);   // zero_small_coordinates
+            }
+        }
+    return n0;
+}
+
+PFC_D Vec3<double> pair_normal(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<double>& cx) {
+    if (ins.kind1 == 0) {
+        const TriRec& tri = sc.tris[ins.prim_base1 + prim1];
+        return rot_d(cx.x21, mk<double>(tri.n[0], tri.n[1], tri.n[2]));
+    }
+    const TetRec& t1 = sc.tets[ins.prim_base1 + prim1];
+    const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
+    const double g0 = cx.Ebar1 * t1.eps_r[0], g1 = cx.Ebar1 * t1.eps_r[1], g2 = cx.Ebar1 * t1.eps_r[2];
+    const Xform<double>& Y = cx.x12;
+    const double p0 = cx.Ebar2 * t2.eps_r[0] - (g0 * Y.r[0] + g1 * Y.r[3] + g2 * Y.r[6]);
+    const double p1 = cx.Ebar2 * t2.eps_r[1] - (g0 * Y.r[1] + g1 * Y.r[4] + g2 * Y.r[7]);
+    const double p2 = cx.Ebar2 * t2.eps_r[2] - (g0 * Y.r[2] + g1 * Y.r[5] + g2 * Y.r[8]);
+    const double inv_len = 1.0 / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+    return mk<double>(p0 * inv_len, p1 * inv_len, p2 * inv_len);
+}
+
 // stages A + B for one pair on one thread, sub-triangles in the reference's order (previous vertex = last first)
 template <class T, int NA> PFC_D void integrate_pair(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<T>& cx, Accum<T, NA>& acc, int& flags) {
     PolyRec<T> pr;

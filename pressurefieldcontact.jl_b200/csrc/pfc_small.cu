@@ -503,7 +503,13 @@ template <int P> struct TileSmem {   // P problems, P warps
     int pflags[P];
     unsigned short items[kThreads * 8];
     unsigned char poly_prob[kThreads];
+    // compacted clip (narrow_tile_kernel): pair code and start-polygon size per occupied slot, friction parameters per problem
+    unsigned slot_pair[kThreads];
+    unsigned char slot_n[kThreads];
+    int resume_c;
+    double fpv[P][8];
 };
+static_assert(sizeof(TileSmem<4>) <= 56 * 1024, "4 CTAs per SM need <= 56 KB each");
 
 template <int P, int MINB>
 __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
@@ -633,6 +639,184 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
     }
 }
 
+// ---- kernel 2c: the tile kernel with a COMPACTED clip -------------------------------------------------------------------
+// Same phases as narrow_tile_kernel, but phase 2 is split: (2a) every candidate pair of the tile is taken up to its start polygon
+// in registers (start_polygon_zeta: about 3 of 10 pairs are rejected there); (2b) a block scan of the survivors packs them, in
+// candidate order, into the polygon slots; (2c) slot d is clipped by thread d.  The clip -- the most divergent part of the step --
+// then starts with all lanes of the leading warps busy, and a tile with more than 128 candidates (19 % of the settled boxes.jl
+// stacks) usually needs ONE clip / quadrature / summation round instead of two, because its survivors fit 128 slots.  When the
+// survivors of a round do not fit, the round after the clip starts again at the first candidate left out (rare).
+template <int P, int MINB>
+__global__ void __launch_bounds__(32 * P, MINB) narrow_tile_compact_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
+    constexpr int kTileThreads = 32 * P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<P>& sm = *reinterpret_cast<TileSmem<P>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const long long n_prob = io.n_env * sc.n_small;
+    const long long n_tile = (n_prob + P - 1) / P;
+    const int sum_q = wib;   // phase 4: warp q sums problem q
+    for (long long tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
+        // ---- 1. problem contexts: warp q fills problem q, one element per lane
+        {
+            const long long prob = tile * P + wib;
+            if (prob < n_prob) {
+                const long long env = prob / sc.n_small;
+                const int k = sc.small_ins[prob - env * sc.n_small];
+                const InsDev& ins = sc.ins[k];
+                const long long ei = env * sc.n_ins + k;
+                const double* X = io.X + 16 * ei;
+                PatchCtx<double>& cx = sm.cx[wib];
+                if (lane < 8) sm.fpv[wib][lane] = ins.p[lane];   // friction parameters: read per quadrature point, so keep them on chip
+                if (lane < 9) { const int i = lane / 3, j = lane % 3; cx.x21.r[lane] = X[4 * j + i]; }
+                else if (lane < 12) cx.x21.t[lane - 9] = X[12 + lane - 9];
+                else if (lane < 21) { const int e = lane - 12, i = e / 3, j = e % 3; cx.x12.r[e] = X[4 * i + j]; }
+                else if (lane < 24) { const int i = lane - 21; cx.x12.t[i] = -(X[4 * i] * X[12] + X[4 * i + 1] * X[13] + X[4 * i + 2] * X[14]); }
+                else if (lane < 27) (&cx.w_ang.x)[lane - 24] = io.twist[6 * ei + lane - 24];
+                else if (lane < 30) (&cx.w_lin.x)[lane - 27] = io.twist[6 * ei + lane - 24];
+                else if (lane == 30) { cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad; }
+                else { sm.ei[wib] = ei; sm.fp[wib] = sm.fpv[wib]; sm.ins[wib] = k; sm.n_cand[wib] = (int)io.n_pairs[ei]; sm.pflags[wib] = 0; }
+            } else if (lane == 31) { sm.ei[wib] = -1; sm.n_cand[wib] = 0; sm.ins[wib] = 0; sm.fp[wib] = nullptr; sm.pflags[wib] = 0; }
+        }
+        __syncthreads();
+        int pre[P + 1];
+        pre[0] = 0;
+#pragma unroll
+        for (int q = 0; q < P; ++q) pre[q + 1] = pre[q] + sm.n_cand[q];
+        const int n_cand = pre[P];
+        if (lane < 8) sm.tot[wib][lane] = 0.0;   // running totals of problem wib: 6 sums + point count (warp-private)
+        int filled = 0;          // occupied polygon slots (block-uniform)
+        int c0 = 0;              // first candidate of the next round (block-uniform)
+        while (true) {
+            // ---- 2a. one candidate pair per thread up to its start polygon (registers)
+            if (c0 < n_cand) {
+                const int c = c0 + tid;
+                double zr[16];
+                int n0 = 0, q = 0;
+                unsigned e = 0;
+                if (c < n_cand) {
+#pragma unroll
+                    for (int r = 1; r < P; ++r) q += (c >= pre[r]);
+                    e = pairs_in[(size_t)cap * sm.ei[q] + (c - pre[q])];
+                    n0 = start_polygon_zeta(sc, sc.ins[sm.ins[q]], dec_a(e), dec_b(e), sm.cx[q], zr);
+                }
+                // ---- 2b. block scan of the survivors -> slot numbers in candidate order
+                const unsigned alive = __ballot_sync(0xffffffffu, n0 > 0);
+                if (lane == 0) sm.warp_tot[wib] = __popc(alive);
+                __syncthreads();
+                int before = 0, round_total = 0;
+#pragma unroll
+                for (int w = 0; w < P; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; round_total += t; }
+                if (n0 > 0) {
+                    const int slot = filled + before + __popc(alive & ((1u << lane) - 1u));
+                    if (slot < kTileThreads) {
+                        double* z = sm.poly + slot * kPolyStride;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < 4 * n0) z[j] = zr[j];
+                        sm.slot_pair[slot] = e; sm.slot_n[slot] = (unsigned char)n0; sm.poly_prob[slot] = (unsigned char)q;
+                    } else if (slot == kTileThreads) sm.resume_c = c;   // the slots are full: the next round starts again at this candidate
+                }
+                __syncthreads();   // slots written, warp_tot read
+                if (filled + round_total > kTileThreads) { filled = kTileThreads; c0 = sm.resume_c; }
+                else { filled += round_total; c0 += kTileThreads; }
+            }
+            const bool last = c0 >= n_cand;
+            if (filled == 0) { if (last) break; continue; }
+            if (filled < kTileThreads && !last) continue;
+            const int batch_n = filled;
+            // ---- 2c. slot d is clipped in place by thread d, centroid -> a finished PolyRec
+            int nv = 0;
+            if (tid < batch_n) {
+                const int q = sm.poly_prob[tid];
+                const unsigned e = sm.slot_pair[tid];
+                PolyRec<double>& out = *reinterpret_cast<PolyRec<double>*>(sm.poly + tid * kPolyStride);
+                int flags = 0;
+                const int n = clip_tet_inplace(reinterpret_cast<double*>(&out), (int)sm.slot_n[tid], flags);
+                if (n >= 3) {
+                    const InsDev& ins = sc.ins[sm.ins[q]];
+                    finish_polygon_slot(n, sc.tets[ins.prim_base2 + dec_b(e)], pair_normal(sc, ins, dec_a(e), dec_b(e), sm.cx[q]), out);
+                    nv = n;
+                }
+                if (flags) atomicOr(&sm.pflags[q], flags);   // rare: non-finite vertex / bad arity
+            }
+            // ---- 3a. block scan of the vertex counts -> dense (slot, edge) work list, ordered by (problem, pair, edge)
+            int incl = nv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) sm.warp_tot[wib] = incl;
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < P; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; total += t; }
+            const int at = before + incl - nv;
+            for (int k = 0; k < nv; ++k) sm.items[at + k] = (unsigned short)((tid << 3) | k);
+            __syncthreads();
+            // this summing thread's item range: items are sorted by problem, so it is [lower_bound(q), lower_bound(q + 1))
+            int my_lo = 0, my_hi = 0;
+            {
+                int lo = 0, hi = total;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] < sum_q) lo = mid + 1; else hi = mid; }
+                my_lo = lo; hi = total;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] <= sum_q) lo = mid + 1; else hi = mid; }
+                my_hi = lo;
+            }
+            for (int i0 = 0; i0 < total; i0 += kItemCap) {
+                // ---- 3b. one sub-triangle per thread
+                const int i1 = min(total, i0 + kItemCap);
+                for (int it = i0 + tid; it < i1; it += kTileThreads) {
+                    const int code = sm.items[it];
+                    const int slot = code >> 3, k = code & 7;
+                    const PolyRec<double>& pr = *reinterpret_cast<const PolyRec<double>*>(sm.poly + slot * kPolyStride);
+                    const int q = sm.poly_prob[slot];
+                    const PatchCtx<double>& cx = sm.cx[q];
+                    Accum<double, 6> tmp;
+                    tmp.fp = sm.fpv[q]; tmp.w_ang = cx.w_ang; tmp.w_lin = cx.w_lin; tmp.dump = nullptr; tmp.dump_cap = 0;
+                    tmp.reset(ACC_REGULARIZED);
+                    const int kp = (k == 0) ? pr.n - 1 : k - 1;
+                    integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, tmp);
+                    double* res = sm.item_res + (it - i0) * kItemStride;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) res[j] = tmp.a[j];
+                    reinterpret_cast<int*>(res + 6)[0] = tmp.n_points;
+                }
+                __syncthreads();
+                // ---- 4. fixed-order sums: lane l adds items a + l, a + l + 32, ... of its warp's problem, then a xor-butterfly
+                {
+                    const int a = max(my_lo, i0), b = min(my_hi, i1);
+                    if (a < b) {   // warp-uniform
+                        double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                        int part_n = 0;
+                        for (int it = a + lane; it < b; it += 32) {
+                            const double* res = sm.item_res + (it - i0) * kItemStride;
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) part[j] += res[j];
+                            part_n += reinterpret_cast<const int*>(res + 6)[0];
+                        }
+                        double mine = (double)warp_sum_int(part_n);   // lane 6 keeps the point count
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) { const double t = warp_sum(part[j]); mine = (lane == j) ? t : mine; }
+                        if (lane < 7) sm.tot[sum_q][lane] += mine;
+                    }
+                }
+                __syncthreads();   // item_res (and, after the last round, the polygon slots) are reused
+            }
+            filled = 0;   // (with total == 0 the two barriers of 3a already separate the clip from the next round's slot writes)
+            if (last) break;
+        }
+        // ---- results: wrench (zero without contact), flags
+        {
+            const long long ei = sm.ei[sum_q];
+            if (ei >= 0) {
+                __syncwarp();
+                const bool contact = sm.tot[sum_q][6] > 0.0;
+                if (lane < 6) io.wrench[6 * ei + lane] = contact ? sm.tot[sum_q][lane] : 0.0;
+                if (lane == 6) io.flags[ei] |= sm.pflags[sum_q] | (contact ? kFlagContact : 0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // One thread walks a given pair list in order and records every traction point (TractionCache).
 __global__ void dump_traction_kernel(SceneDev sc, EvalIO io, long long env, int k, const int* pairs, long long n_pairs, double* out, int cap, int* n_points) {
     const InsDev& ins = sc.ins[k];
@@ -705,7 +889,8 @@ cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const
 template <int P, int MINB>
 cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
     static int cached_blocks = 0;
-    auto kern = narrow_tile_kernel<P, MINB>;
+    static const bool legacy = getenv("PFC_NARROW_TILE_LEGACY") != nullptr;   // A/B switch while the compacted clip is being measured
+    auto kern = legacy ? narrow_tile_kernel<P, MINB> : narrow_tile_compact_kernel<P, MINB>;
     const size_t smem = sizeof(TileSmem<P>);
     if (cached_blocks == 0) {
         cudaError_t e;
