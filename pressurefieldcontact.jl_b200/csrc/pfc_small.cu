@@ -477,13 +477,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) narrow_small_kernel(SceneDev
 // instruction on a 32-lane warp) and a warp runs its phases strictly one after another.  Here a CTA of 128 threads owns P
 // consecutive (environment, instruction) problems and every phase is flattened over all of them:
 //   1. 32 threads per problem fill the problem's shared context (transform, inverse, twist, constants), one element each;
-//   2. the tile's candidate pairs (about 118 for P = 4 boxes.jl instructions) are dealt one per thread: exact rejection on
-//      registers, then the clip IN PLACE in the thread's shared-memory PolyRec slot (stride 35 doubles: conflict-free; no
-//      local memory), centroid -> a finished PolyRec;
+//   2. the tile's candidate pairs (about 118 for P = 4 boxes.jl instructions) are dealt one per thread and taken up to their
+//      start polygon in REGISTERS (start_polygon_zeta: about 3 of 10 pairs are rejected there); a block scan packs the
+//      survivors, in candidate order, into the shared-memory PolyRec slots (stride 35 doubles: conflict-free; no local
+//      memory); slot d is clipped IN PLACE by thread d, centroid -> a finished PolyRec.  The clip -- the most divergent part
+//      of the step -- so starts with all lanes of the leading warps busy, and a tile with more than 128 candidates (19 % of
+//      the settled boxes.jl stacks) needs one clip / quadrature / summation round instead of two because its survivors fit
+//      the 128 slots (164 -> 144 us on 4096 environments).  When the survivors of a round do not fit, the round after the
+//      clip starts again at the first candidate left out (rare);
 //   3. a block scan over the vertex counts turns the polygons into a dense (slot, edge) work list, dealt one sub-triangle
 //      per thread for quadrature + friction; every item leaves its 6 sums (+ point count) in shared memory;
-//   4. one thread per (problem, wrench component) adds its problem's items IN ITEM ORDER (= the reference's order of
-//      candidate pairs and polygon edges): bitwise reproducible, no atomics, no per-thread accumulators to carry.
+//   4. one warp per problem adds its problem's items IN ITEM ORDER (= the reference's order of candidate pairs and polygon
+//      edges; lane-strided partials + xor-butterfly): bitwise reproducible, no atomics, no per-thread accumulators to carry.
+// Measured and rejected: one WARP per tile (32 slots per warp, __syncwarp only, per-lane register accumulators flushed by a
+// butterfly per problem) -- no barrier waits, but the sub-triangles of a 32-slot round split into per-problem segments that
+// fill 6 of 10 lanes: 196 us against 146 us for this kernel.  Fetching the next tile's boundary data (x_r2_r1, twist, pair count)
+// into registers one tile ahead: no change (145 us) -- the other three CTAs of the SM already cover that DRAM round trip.  Tiles of
+// 8 problems on 256 threads (2 CTAs per SM): 152 us against 141 us -- a barrier then waits for the slowest of 256 clips.
 constexpr int kPolyStride = 35;    // doubles per PolyRec slot
 static_assert(sizeof(PolyRec<double>) == kPolyStride * sizeof(double), "PolyRec<double> is 35 doubles");
 constexpr int kItemCap = 256;      // sub-triangles per summation round
@@ -503,151 +513,17 @@ template <int P> struct TileSmem {   // P problems, P warps
     int pflags[P];
     unsigned short items[kThreads * 8];
     unsigned char poly_prob[kThreads];
-    // compacted clip (narrow_tile_kernel): pair code and start-polygon size per occupied slot, friction parameters per problem
+    // pair code and start-polygon size per occupied slot, friction parameters per problem
     unsigned slot_pair[kThreads];
     unsigned char slot_n[kThreads];
     int resume_c;
+    int q_lo[P], q_hi[P];   // item range of each problem in the current round
     double fpv[P][8];
 };
 static_assert(sizeof(TileSmem<4>) <= 56 * 1024, "4 CTAs per SM need <= 56 KB each");
 
 template <int P, int MINB>
 __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
-    constexpr int kTileThreads = 32 * P;   // one warp per problem for the context and the sums
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem<P>& sm = *reinterpret_cast<TileSmem<P>*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const long long n_prob = io.n_env * sc.n_small;
-    const long long n_tile = (n_prob + P - 1) / P;
-    const int sum_q = wib;   // phase 4: warp q sums problem q
-    for (long long tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
-        // ---- 1. problem contexts: warp q fills problem q, one element per lane
-        {
-            const long long prob = tile * P + wib;
-            if (prob < n_prob) {
-                const long long env = prob / sc.n_small;
-                const int k = sc.small_ins[prob - env * sc.n_small];
-                const InsDev& ins = sc.ins[k];
-                const long long ei = env * sc.n_ins + k;
-                const double* X = io.X + 16 * ei;
-                PatchCtx<double>& cx = sm.cx[wib];
-                if (lane < 9) { const int i = lane / 3, j = lane % 3; cx.x21.r[lane] = X[4 * j + i]; }
-                else if (lane < 12) cx.x21.t[lane - 9] = X[12 + lane - 9];
-                else if (lane < 21) { const int e = lane - 12, i = e / 3, j = e % 3; cx.x12.r[e] = X[4 * i + j]; }
-                else if (lane < 24) { const int i = lane - 21; cx.x12.t[i] = -(X[4 * i] * X[12] + X[4 * i + 1] * X[13] + X[4 * i + 2] * X[14]); }
-                else if (lane < 27) (&cx.w_ang.x)[lane - 24] = io.twist[6 * ei + lane - 24];
-                else if (lane < 30) (&cx.w_lin.x)[lane - 27] = io.twist[6 * ei + lane - 24];
-                else if (lane == 30) { cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad; }
-                else { sm.ei[wib] = ei; sm.fp[wib] = ins.p; sm.ins[wib] = k; sm.n_cand[wib] = (int)io.n_pairs[ei]; sm.pflags[wib] = 0; }
-            } else if (lane == 31) { sm.ei[wib] = -1; sm.n_cand[wib] = 0; sm.ins[wib] = 0; sm.fp[wib] = nullptr; sm.pflags[wib] = 0; }
-        }
-        __syncthreads();
-        int pre[P + 1];
-        pre[0] = 0;
-#pragma unroll
-        for (int q = 0; q < P; ++q) pre[q + 1] = pre[q] + sm.n_cand[q];
-        const int n_cand = pre[P];
-        if (lane < 8) sm.tot[wib][lane] = 0.0;   // running totals of problem wib: 6 sums + point count (warp-private)
-        for (int c0 = 0; c0 < n_cand; c0 += kTileThreads) {
-            // ---- 2. one candidate pair per thread
-            const int c = c0 + tid;
-            int nv = 0;
-            if (c < n_cand) {
-                int q = 0;
-#pragma unroll
-                for (int r = 1; r < P; ++r) q += (c >= pre[r]);
-                const unsigned e = pairs_in[(size_t)cap * sm.ei[q] + (c - pre[q])];
-                PolyRec<double>& out = *reinterpret_cast<PolyRec<double>*>(sm.poly + tid * kPolyStride);
-                int flags = 0;
-                if (clip_pair_slot(sc, sc.ins[sm.ins[q]], dec_a(e), dec_b(e), sm.cx[q], out, flags)) nv = out.n;
-                if (flags) atomicOr(&sm.pflags[q], flags);   // rare: non-finite vertex / bad arity
-                sm.poly_prob[tid] = (unsigned char)q;
-            }
-            // ---- 3a. block scan of the vertex counts -> dense (slot, edge) work list, ordered by (problem, pair, edge)
-            int incl = nv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (lane == 31) sm.warp_tot[wib] = incl;
-            __syncthreads();
-            int before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < P; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; total += t; }
-            const int at = before + incl - nv;
-            for (int k = 0; k < nv; ++k) sm.items[at + k] = (unsigned short)((tid << 3) | k);
-            __syncthreads();
-            // this summing thread's item range: items are sorted by problem, so it is [lower_bound(q), lower_bound(q + 1))
-            int my_lo = 0, my_hi = 0;
-            {
-                int lo = 0, hi = total;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] < sum_q) lo = mid + 1; else hi = mid; }
-                my_lo = lo; hi = total;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] <= sum_q) lo = mid + 1; else hi = mid; }
-                my_hi = lo;
-            }
-            for (int i0 = 0; i0 < total; i0 += kItemCap) {
-                // ---- 3b. one sub-triangle per thread
-                const int i1 = min(total, i0 + kItemCap);
-                for (int it = i0 + tid; it < i1; it += kTileThreads) {
-                    const int code = sm.items[it];
-                    const int slot = code >> 3, k = code & 7;
-                    const PolyRec<double>& pr = *reinterpret_cast<const PolyRec<double>*>(sm.poly + slot * kPolyStride);
-                    const int q = sm.poly_prob[slot];
-                    const PatchCtx<double>& cx = sm.cx[q];
-                    Accum<double, 6> tmp;
-                    tmp.fp = sm.fp[q]; tmp.w_ang = cx.w_ang; tmp.w_lin = cx.w_lin; tmp.dump = nullptr; tmp.dump_cap = 0;
-                    tmp.reset(ACC_REGULARIZED);
-                    const int kp = (k == 0) ? pr.n - 1 : k - 1;
-                    integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, tmp);
-                    double* res = sm.item_res + (it - i0) * kItemStride;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) res[j] = tmp.a[j];
-                    reinterpret_cast<int*>(res + 6)[0] = tmp.n_points;
-                }
-                __syncthreads();
-                // ---- 4. fixed-order sums: lane l adds items a + l, a + l + 32, ... of its warp's problem, then a xor-butterfly
-                {
-                    const int a = max(my_lo, i0), b = min(my_hi, i1);
-                    if (a < b) {   // warp-uniform
-                        double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                        int part_n = 0;
-                        for (int it = a + lane; it < b; it += 32) {
-                            const double* res = sm.item_res + (it - i0) * kItemStride;
-#pragma unroll
-                            for (int j = 0; j < 6; ++j) part[j] += res[j];
-                            part_n += reinterpret_cast<const int*>(res + 6)[0];
-                        }
-                        double mine = (double)warp_sum_int(part_n);   // lane 6 keeps the point count
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) { const double t = warp_sum(part[j]); mine = (lane == j) ? t : mine; }
-                        if (lane < 7) sm.tot[sum_q][lane] += mine;
-                    }
-                }
-                __syncthreads();   // item_res (and, after the last round, the polygon slots) are reused
-            }
-        }
-        // ---- results: wrench (zero without contact), flags
-        {
-            const long long ei = sm.ei[sum_q];
-            if (ei >= 0) {
-                __syncwarp();
-                const bool contact = sm.tot[sum_q][6] > 0.0;
-                if (lane < 6) io.wrench[6 * ei + lane] = contact ? sm.tot[sum_q][lane] : 0.0;
-                if (lane == 6) io.flags[ei] |= sm.pflags[sum_q] | (contact ? kFlagContact : 0);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---- kernel 2c: the tile kernel with a COMPACTED clip -------------------------------------------------------------------
-// Same phases as narrow_tile_kernel, but phase 2 is split: (2a) every candidate pair of the tile is taken up to its start polygon
-// in registers (start_polygon_zeta: about 3 of 10 pairs are rejected there); (2b) a block scan of the survivors packs them, in
-// candidate order, into the polygon slots; (2c) slot d is clipped by thread d.  The clip -- the most divergent part of the step --
-// then starts with all lanes of the leading warps busy, and a tile with more than 128 candidates (19 % of the settled boxes.jl
-// stacks) usually needs ONE clip / quadrature / summation round instead of two, because its survivors fit 128 slots.  When the
-// survivors of a round do not fit, the round after the clip starts again at the first candidate left out (rare).
-template <int P, int MINB>
-__global__ void __launch_bounds__(32 * P, MINB) narrow_tile_compact_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
     constexpr int kTileThreads = 32 * P;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<P>& sm = *reinterpret_cast<TileSmem<P>*>(smem_raw);
@@ -665,14 +541,15 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_compact_kernel(Scene
                 const InsDev& ins = sc.ins[k];
                 const long long ei = env * sc.n_ins + k;
                 const double* X = io.X + 16 * ei;
+                const double* twist = io.twist + 6 * ei;
                 PatchCtx<double>& cx = sm.cx[wib];
                 if (lane < 8) sm.fpv[wib][lane] = ins.p[lane];   // friction parameters: read per quadrature point, so keep them on chip
                 if (lane < 9) { const int i = lane / 3, j = lane % 3; cx.x21.r[lane] = X[4 * j + i]; }
                 else if (lane < 12) cx.x21.t[lane - 9] = X[12 + lane - 9];
                 else if (lane < 21) { const int e = lane - 12, i = e / 3, j = e % 3; cx.x12.r[e] = X[4 * i + j]; }
                 else if (lane < 24) { const int i = lane - 21; cx.x12.t[i] = -(X[4 * i] * X[12] + X[4 * i + 1] * X[13] + X[4 * i + 2] * X[14]); }
-                else if (lane < 27) (&cx.w_ang.x)[lane - 24] = io.twist[6 * ei + lane - 24];
-                else if (lane < 30) (&cx.w_lin.x)[lane - 27] = io.twist[6 * ei + lane - 24];
+                else if (lane < 27) (&cx.w_ang.x)[lane - 24] = twist[lane - 24];
+                else if (lane < 30) (&cx.w_lin.x)[lane - 27] = twist[lane - 24];
                 else if (lane == 30) { cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad; }
                 else { sm.ei[wib] = ei; sm.fp[wib] = sm.fpv[wib]; sm.ins[wib] = k; sm.n_cand[wib] = (int)io.n_pairs[ei]; sm.pflags[wib] = 0; }
             } else if (lane == 31) { sm.ei[wib] = -1; sm.n_cand[wib] = 0; sm.ins[wib] = 0; sm.fp[wib] = nullptr; sm.pflags[wib] = 0; }
@@ -743,23 +620,21 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_compact_kernel(Scene
             int incl = nv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (lane == 31) sm.warp_tot[wib] = incl;
+            if (lane == 31) { sm.warp_tot[wib] = incl; sm.q_lo[wib] = 0; sm.q_hi[wib] = 0; }   // (a problem without slots sums nothing)
             __syncthreads();
             int before = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < P; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; total += t; }
             const int at = before + incl - nv;
             for (int k = 0; k < nv; ++k) sm.items[at + k] = (unsigned short)((tid << 3) | k);
-            __syncthreads();
-            // this summing thread's item range: items are sorted by problem, so it is [lower_bound(q), lower_bound(q + 1))
-            int my_lo = 0, my_hi = 0;
-            {
-                int lo = 0, hi = total;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] < sum_q) lo = mid + 1; else hi = mid; }
-                my_lo = lo; hi = total;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)sm.poly_prob[sm.items[mid] >> 3] <= sum_q) lo = mid + 1; else hi = mid; }
-                my_hi = lo;
+            if (tid < batch_n) {
+                const int q = sm.poly_prob[tid];
+                if (tid == 0 || (int)sm.poly_prob[tid - 1] != q) sm.q_lo[q] = at;
+                if (tid == batch_n - 1 || (int)sm.poly_prob[tid + 1] != q) sm.q_hi[q] = at + nv;
             }
+            __syncthreads();
+            // this summing warp's item range (items are sorted by problem): left by the first / last slot of its problem
+            const int my_lo = sm.q_lo[sum_q], my_hi = sm.q_hi[sum_q];
             for (int i0 = 0; i0 < total; i0 += kItemCap) {
                 // ---- 3b. one sub-triangle per thread
                 const int i1 = min(total, i0 + kItemCap);
@@ -889,8 +764,7 @@ cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const
 template <int P, int MINB>
 cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
     static int cached_blocks = 0;
-    static const bool legacy = getenv("PFC_NARROW_TILE_LEGACY") != nullptr;   // A/B switch while the compacted clip is being measured
-    auto kern = legacy ? narrow_tile_kernel<P, MINB> : narrow_tile_compact_kernel<P, MINB>;
+    auto kern = narrow_tile_kernel<P, MINB>;
     const size_t smem = sizeof(TileSmem<P>);
     if (cached_blocks == 0) {
         cudaError_t e;
