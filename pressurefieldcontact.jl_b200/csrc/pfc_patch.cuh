@@ -338,65 +338,10 @@ PFC_D bool finish_polygon_slot(int n, const TetRec& tet_g, const Vec3<double>& n
     return true;
 }
 
-PFC_D bool clip_pair_slot(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<double>& cx, PolyRec<double>& out, int& flags) {
-    const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
-    double* z = reinterpret_cast<double*>(&out);
-    if (ins.kind1 == 0) {
-        struct { double v[9]; double n[3]; } tri;          // the whole TriRec (96 B) and the tet's inverse (128 B): 7 wide loads
-        struct { double inv[16]; } t2r;
-        load_wide<12>(sc.tris[ins.prim_base1 + prim1].v, tri.v);
-        load_wide<16>(t2.inv, t2r.inv);
-        double zr[3][4];
-        unsigned all_non_pos = 0xfu;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const Vec3<double> p = apply_d(cx.x21, mk<double>(tri.v[3 * k], tri.v[3 * k + 1], tri.v[3 * k + 2]));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                zr[k][i] = t2r.inv[4 * i] * p.x + t2r.inv[4 * i + 1] * p.y + t2r.inv[4 * i + 2] * p.z + t2r.inv[4 * i + 3];
-                if (!(zr[k][i] <= 0.0)) all_non_pos &= ~(1u << i);
-            }
-        }
-        if (all_non_pos) return false;   // some face has all three vertices outside: the clip would return nothing (see prefilter_pair)
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) z[4 * k + i] = zr[k][i];
-        const int n = clip_tet_inplace(z, 3, flags);
-        if (n < 3) return false;
-        return finish_polygon_slot(n, t2, rot_d(cx.x21, mk<double>(tri.n[0], tri.n[1], tri.n[2])), out);
-    }
-    const TetRec& t1 = sc.tets[ins.prim_base1 + prim1];
-    double plane[4];
-    {
-        const double g0 = cx.Ebar1 * t1.eps_r[0], g1 = cx.Ebar1 * t1.eps_r[1], g2 = cx.Ebar1 * t1.eps_r[2], g3 = cx.Ebar1 * t1.eps_r[3];
-        const Xform<double>& Y = cx.x12;
-        plane[0] = cx.Ebar2 * t2.eps_r[0] - (g0 * Y.r[0] + g1 * Y.r[3] + g2 * Y.r[6]);
-        plane[1] = cx.Ebar2 * t2.eps_r[1] - (g0 * Y.r[1] + g1 * Y.r[4] + g2 * Y.r[7]);
-        plane[2] = cx.Ebar2 * t2.eps_r[2] - (g0 * Y.r[2] + g1 * Y.r[5] + g2 * Y.r[8]);
-        plane[3] = cx.Ebar2 * t2.eps_r[3] - (g0 * Y.t[0] + g1 * Y.t[1] + g2 * Y.t[2] + g3);
-    }
-    Vec3<double> v[4], poly[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = apply_d(cx.x21, mk<double>(t1.v[3 * k], t1.v[3 * k + 1], t1.v[3 * k + 2]));
-    const int n0 = plane_tet(plane, v, poly);
-    if (n0 < 3) return false;
-    for (int k = 0; k < n0; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double zz = t2.inv[4 * i] * poly[k].x + t2.inv[4 * i + 1] * poly[k].y + t2.inv[4 * i + 2] * poly[k].z + t2.inv[4 * i + 3];
-            z[4 * k + i] = zz * ((1.0e-14 < fabs(zz)) ? 1.0 : 0.0);   // zero_small_coordinates
-        }
-    const int n = clip_tet_inplace(z, n0, flags);
-    if (n < 3) return false;
-    const double inv_len = 1.0 / sqrt(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);
-    return finish_polygon_slot(n, t2, mk<double>(plane[0] * inv_len, plane[1] * inv_len, plane[2] * inv_len), out);
-}
-
 // ---- stage A split in two, for the tile kernel's compacted clip ---------------------------------------------------------
 // start_polygon_zeta: everything before the first face cut -- the start polygon (the triangle, or the plane/tet section) in
 // tetrahedral coordinates of tet 2, in REGISTERS (zr[4 * k + i]); returns its vertex count, 0 when the pair is rejected (same
-// tests, same arithmetic as clip_pair_slot).  pair_normal: the polygon normal, recomputed from the records after the clip.
+// tests, same arithmetic as clip_pair).  pair_normal: the polygon normal, recomputed from the records after the clip.
 PFC_D int start_polygon_zeta(const SceneDev& sc, const InsDev& ins, int prim1, int prim2, const PatchCtx<double>& cx, double* zr) {
     const TetRec& t2 = sc.tets[ins.prim_base2 + prim2];
     if (ins.kind1 == 0) {
