@@ -1,4 +1,5 @@
-"""CPU-only: the DEVICE source of the in-place polygon clip (csrc/pfc_clip.cuh: clip_node_inplace, clip_tet_inplace), compiled
+"""CPU-only: the DEVICE source of the polygon clips (csrc/pfc_clip.cuh: clip_node_inplace, clip_tet_inplace of the tile kernel;
+clip_node, clip_tet<T> of the large path and the Dual mode -- the latter must give the same bits as the in-place one), compiled
 for the host with g++ and run against the oracle's clip_in_tet_coordinates (oracle/pfc_oracle.hpp, which follows
 /root/reference/src/clip/static_clip.jl:7-201) on random 3- and 4-gons in tetrahedral coordinates -- vertices on faces (+-0.0),
 polygons fully inside / outside, NaNs.  Vertex counts, flags and every output coordinate must agree BIT FOR BIT: the device
@@ -30,6 +31,12 @@ namespace dev {
 namespace dev_div {
 %s
 }
+#define __device__
+#define __noinline__
+namespace dev_generic {   // the thread-private clip_tet<T> of the large path / Dual mode, T = double
+static inline double val(double x) { return x; }
+%s
+}
 int main(int argc, char** argv) {
     const long n_case = argc > 1 ? atol(argv[1]) : 1000000;
     std::mt19937_64 g(20261018);
@@ -59,7 +66,14 @@ int main(int argc, char** argv) {
         int flags = 0, flags_div = 0;
         const int n = dev::clip_tet_inplace(z, n0, flags);
         const int n_div = dev_div::clip_tet_inplace(z_div, n0, flags_div);
-        bool ok = (n == ref.n) && (((flags & kFlagNonFinite) != 0) == st.non_finite) && (n_div == ref.n) && (flags_div == flags);
+        dev_generic::Zeta<double> zg[9];
+        for (int k = 0; k < n0; ++k) for (int i = 0; i < 4; ++i) zg[k].c[i] = p.v[k][i];
+        int flags_g = 0;
+        const int n_g = dev_generic::clip_tet<double>(zg, n0, flags_g);
+        bool ok = (n == ref.n) && (((flags & kFlagNonFinite) != 0) == st.non_finite) && (n_div == ref.n) && (flags_div == flags) && (n_g == n) && (flags_g == flags);
+        for (int k = 0; ok && k < n; ++k)   // both device clips use the same reciprocal form: identical bits
+            for (int i = 0; i < 4; ++i)
+                if (std::memcmp(&zg[k].c[i], &z[4 * k + i], sizeof(double)) != 0 && !(zg[k].c[i] != zg[k].c[i] && z[4 * k + i] != z[4 * k + i])) ok = false;
         for (int k = 0; ok && k < n; ++k)
             for (int i = 0; i < 4; ++i) {
                 const double a = z[4 * k + i], a_div = z_div[4 * k + i], b = ref.v[k][i];
@@ -85,13 +99,20 @@ def _device_clip_source():
     return src[a:b]
 
 
+def _device_generic_clip_source():
+    src = open(os.path.join(ROOT, "pressurefieldcontact.jl_b200", "csrc", "pfc_clip.cuh")).read()
+    a = src.index("template <class T> struct Zeta")
+    b = src.index("// The same clip, working IN PLACE")
+    return src[a:b]
+
+
 def test_device_inplace_clip_matches_oracle_bitwise(tmp_path):
     cpp = tmp_path / "clip_host.cpp"
     dev = _device_clip_source()
     recip = "const double inv = 1.0 / (w1 - w2);\n    const double c1 = w1 * inv, c2 = w2 * inv;"
     assert recip in dev
     dev_div = dev.replace(recip, "const double sum_weight = w1 - w2;\n    const double c1 = w1 / sum_weight, c2 = w2 / sum_weight;")
-    cpp.write_text(HARNESS % (dev, dev_div))
+    cpp.write_text(HARNESS % (dev, dev_div, _device_generic_clip_source()))
     exe = tmp_path / "clip_host"
     # -ffp-contract=off as in oracle/Makefile: the clip has no muladd site in the reference
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "oracle"), "-o", str(exe), str(cpp)])
