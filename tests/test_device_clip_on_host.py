@@ -3,8 +3,8 @@ clip_node, clip_tet<T> of the large path and the Dual mode -- the latter must gi
 for the host with g++ and run against the oracle's clip_in_tet_coordinates (oracle/pfc_oracle.hpp, which follows
 /root/reference/src/clip/static_clip.jl:7-201) on random 3- and 4-gons in tetrahedral coordinates -- vertices on faces (+-0.0),
 polygons fully inside / outside, NaNs.  Vertex counts, flags and every output coordinate must agree BIT FOR BIT: the device
-version works in place on sign masks, rotates through registers and (since the cut-ordered loop) visits faces in a different
-control structure than the recursion it restates, so this pins its logic without a GPU.
+version works in place on sign masks and rotates through registers -- a different control structure than the recursion it
+restates -- so this pins its logic without a GPU.
 
 One deliberate deviation: weightPoly divides twice (w1 / (w1 - w2), w2 / (w1 - w2), src/math_kernel/utility.jl:21-26), the device
 multiplies by one reciprocal.  The harness therefore runs the device source twice: with the reciprocal replaced by the
