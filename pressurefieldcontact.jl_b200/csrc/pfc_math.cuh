@@ -27,6 +27,9 @@ PFC_D double sub_(double a, double b) { return __dadd_rn(a, -b); }
 // p must be 32 B aligned; N = number of doubles, a multiple of 4.
 template <int N> PFC_D void load_wide(const double* __restrict__ p, double* out) {
     static_assert(N % 4 == 0, "load_wide moves groups of 4 doubles");
+#ifdef PFC_HOST_CHECK   // tests/test_device_*_on_host.py compile the device headers with g++ (no PTX there)
+    for (int j = 0; j < N; ++j) out[j] = p[j];
+#else
 #pragma unroll
     for (int j = 0; j < N / 4; ++j) {
         unsigned long long a, b, c, d;
@@ -34,6 +37,7 @@ template <int N> PFC_D void load_wide(const double* __restrict__ p, double* out)
         out[4 * j] = __longlong_as_double((long long)a); out[4 * j + 1] = __longlong_as_double((long long)b);
         out[4 * j + 2] = __longlong_as_double((long long)c); out[4 * j + 3] = __longlong_as_double((long long)d);
     }
+#endif
 }
 
 // ---- Dual<N> ---------------------------------------------------------------------------------------------
