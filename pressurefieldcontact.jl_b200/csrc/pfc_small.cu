@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) narrow_small_kernel(SceneDev
 // fill 6 of 10 lanes: 196 us against 146 us for this kernel.  Fetching the next tile's boundary data (x_r2_r1, twist, pair count)
 // into registers one tile ahead: no change (145 us) -- the other three CTAs of the SM already cover that DRAM round trip.  Tiles of
 // 8 problems on 256 threads (2 CTAs per SM): 152 us against 141 us -- a barrier then waits for the slowest of 256 clips.
+// 3 CTAs per SM at 168 registers (no spills, 12 warps instead of 16): 151 us.
 constexpr int kPolyStride = 35;    // doubles per PolyRec slot
 static_assert(sizeof(PolyRec<double>) == kPolyStride * sizeof(double), "PolyRec<double> is 35 doubles");
 constexpr int kItemCap = 256;      // sub-triangles per summation round
