@@ -10,6 +10,9 @@ Both device routes are run:
 each with the accumulator in its traction-dump mode, and compared with the oracle's TractionCache list point by point: same
 number of points, normal / position / dA / pressure within 1e-10 (relative to the larger of 1 and the value; the device
 hoists per-tet inverses and uses one reciprocal in weightPoly, so the agreement is to rounding, not bitwise).
+The regularized-Coulomb wrench of every pair that touches (Accum::point in its regularized mode: both branches of the friction
+law) is compared with the oracle's yes_contact!(::Regularized) (src/contact_algorithms_friction.jl:13-30, 50-72) to 1e-10 of the
+torque / force magnitude.
 This is the GPU parity test's TractionCache check (tests/test_gpu_parity.py) restated where no GPU is needed."""
 import os
 import subprocess
@@ -63,7 +66,7 @@ int main(int argc, char** argv) {
     const long n_case = argc > 1 ? atol(argv[1]) : 100000;
     std::mt19937_64 g(4096);
     std::uniform_real_distribution<double> u(-1.0, 1.0), u01(0.0, 1.0);
-    long bad_tile = 0, bad_pair = 0, with_points = 0, n_points = 0, tet_tet = 0;
+    long bad_tile = 0, bad_pair = 0, with_points = 0, n_points = 0, tet_tet = 0, bad_wrench = 0, n_wrench = 0;
     for (long t = 0; t < n_case; ++t) {
         const int kind1 = (t % 3 == 0) ? 1 : 0;   // a third of the cases tet-tet
         const int n_quad_rule = (t % 2) ? 2 : 1;
@@ -163,6 +166,27 @@ int main(int argc, char** argv) {
             pfc::integrate_pair(sc, ins, 0, 0, cx, acc, flags);
             p_pair.n = acc.n_points;
         }
+        // ---- regularized Coulomb wrench of the pair (Accum::point in ACC_REGULARIZED) against yes_contact!(::Regularized)
+        if (!b.traction.empty()) {
+            const double v_c = (t % 4 == 1) ? 10.0 : 0.01 + 1.5 * u01(g);   // every point below v_c in a quarter of the cases
+            const orc::Regularized reg = orc::make_regularized(v_c, 0.3 + 0.5 * u01(g), 0.2);
+            const orc::V6<double> w_ref = orc::yes_contact_regularized(reg, b);
+            const double fp[8] = {reg.mu_s, reg.mu_d, reg.v_c, reg.v_mu_s, reg.v_mu_d, (reg.mu_d - reg.mu_s) / (reg.v_mu_d - reg.v_mu_s), 1.0 / reg.v_c, 0.0};
+            pfc::Accum<double, 6> acc;
+            acc.fp = fp; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
+            acc.reset(pfc::ACC_REGULARIZED);
+            int flags = 0;
+            pfc::integrate_pair(sc, ins, 0, 0, cx, acc, flags);
+            double scale_ang = 0.0, scale_lin = 0.0;
+            for (int i = 0; i < 3; ++i) { scale_ang = std::fmax(scale_ang, std::fabs(w_ref[i])); scale_lin = std::fmax(scale_lin, std::fabs(w_ref[3 + i])); }
+            bool ok_w = true;
+            for (int i = 0; i < 3; ++i) {
+                if (std::fabs(acc.a[i] - w_ref[i]) > 1.0e-10 * std::fmax(scale_ang, 1.0e-6)) ok_w = false;
+                if (std::fabs(acc.a[3 + i] - w_ref[3 + i]) > 1.0e-10 * std::fmax(scale_lin, 1.0e-6)) ok_w = false;
+            }
+            if (!ok_w && bad_wrench++ < 3) std::printf("regularized wrench differs in case %ld\n", t);
+            ++n_wrench;
+        }
         const bool ok_tile = same(p_tile, b.traction), ok_pair = same(p_pair, b.traction);
         if (!ok_tile && bad_tile++ < 3) std::printf("tile route differs in case %ld (kind1 %d): %d points vs %zu\n", t, kind1, p_tile.n, b.traction.size());
         if (!ok_pair && bad_pair++ < 3) std::printf("pair route differs in case %ld (kind1 %d): %d points vs %zu\n", t, kind1, p_pair.n, b.traction.size());
@@ -170,8 +194,9 @@ int main(int argc, char** argv) {
         n_points += (long)b.traction.size();
         tet_tet += kind1 && !b.traction.empty();
     }
-    std::printf("cases %ld bad_tile %ld bad_pair %ld with_points %ld points %ld tet_tet_with_points %ld\n", n_case, bad_tile, bad_pair, with_points, n_points, tet_tet);
-    return (bad_tile || bad_pair) ? 1 : 0;
+    std::printf("cases %ld bad_tile %ld bad_pair %ld with_points %ld points %ld tet_tet_with_points %ld wrenches %ld bad_wrench %ld\n", n_case, bad_tile, bad_pair,
+                with_points, n_points, tet_tet, n_wrench, bad_wrench);
+    return (bad_tile || bad_pair || bad_wrench) ? 1 : 0;
 }
 """
 
@@ -186,6 +211,6 @@ def test_device_narrow_phase_matches_oracle_point_by_point(tmp_path):
     sys.stdout.write(out.stdout)
     assert out.returncode == 0, out.stdout[-2000:]
     f = out.stdout.split()
-    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("bad_tile", "bad_pair", "with_points", "points", "tet_tet_with_points")}
-    assert stats["bad_tile"] == 0 and stats["bad_pair"] == 0
+    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("bad_tile", "bad_pair", "with_points", "points", "tet_tet_with_points", "wrenches", "bad_wrench")}
+    assert stats["bad_tile"] == 0 and stats["bad_pair"] == 0 and stats["bad_wrench"] == 0 and stats["wrenches"] > 5000
     assert stats["with_points"] > 5000 and stats["tet_tet_with_points"] > 500   # the cases do produce contact polygons of both kinds
