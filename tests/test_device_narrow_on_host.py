@@ -12,7 +12,8 @@ number of points, normal / position / dA / pressure within 1e-10 (relative to th
 hoists per-tet inverses and uses one reciprocal in weightPoly, so the agreement is to rounding, not bitwise).
 The regularized-Coulomb wrench of every pair that touches (Accum::point in its regularized mode: both branches of the friction
 law) is compared with the oracle's yes_contact!(::Regularized) (src/contact_algorithms_friction.jl:13-30, 50-72) to 1e-10 of the
-torque / force magnitude.
+torque / force magnitude -- and once more in Jacobian mode: pose and twist carry six random partials each, the device templates run on
+pfc::Dual<6>, the oracle on its own Dual<6>, and values and all partials of the wrench must agree to 1e-9 of the group's magnitude.
 This is the GPU parity test's TractionCache check (tests/test_gpu_parity.py) restated where no GPU is needed."""
 import os
 import subprocess
@@ -66,7 +67,7 @@ int main(int argc, char** argv) {
     const long n_case = argc > 1 ? atol(argv[1]) : 100000;
     std::mt19937_64 g(4096);
     std::uniform_real_distribution<double> u(-1.0, 1.0), u01(0.0, 1.0);
-    long bad_tile = 0, bad_pair = 0, with_points = 0, n_points = 0, tet_tet = 0, bad_wrench = 0, n_wrench = 0;
+    long bad_tile = 0, bad_pair = 0, with_points = 0, n_points = 0, tet_tet = 0, bad_wrench = 0, n_wrench = 0, bad_dual = 0;
     for (long t = 0; t < n_case; ++t) {
         const int kind1 = (t % 3 == 0) ? 1 : 0;   // a third of the cases tet-tet
         const int n_quad_rule = (t % 2) ? 2 : 1;
@@ -186,6 +187,39 @@ int main(int argc, char** argv) {
             }
             if (!ok_w && bad_wrench++ < 3) std::printf("regularized wrench differs in case %ld\n", t);
             ++n_wrench;
+            // ---- the same pair in Jacobian mode: pose and twist carry 6 random partials each (Dual<6> on both sides)
+            typedef orc::Dual<6> OD;
+            typedef pfc::Dual<6> PD;
+            orc::BodyBodyCache<OD> bd;
+            pfc::PatchCtx<PD> cd;
+            bd.quad = b.quad; bd.mesh_1 = &m1; bd.mesh_2 = &m2; bd.chi = chi; bd.Ebar = m2.Ebar;
+            auto seeded = [&](double v, OD& o, PD& d) { o = OD(v); d = PD(v); for (int k = 0; k < 6; ++k) { const double s = u(g); o.p[k] = s; d.p[k] = s; } };
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) seeded(R[3 * i + j], bd.x_r2_r1(i, j), cd.x21.r[3 * i + j]);
+                seeded(tr[i], bd.x_r2_r1(i, 3), cd.x21.t[i]);
+                bd.x_r2_r1(3, i) = OD(0.0);
+            }
+            bd.x_r2_r1(3, 3) = OD(1.0);
+            bd.x_r1_r2 = orc::inv_transform(bd.x_r2_r1);
+            cd.x12 = pfc::inverse(cd.x21);
+            for (int i = 0; i < 3; ++i) { seeded(tw[i], bd.twist_r2_r1_r2[i], (&cd.w_ang.x)[i]); seeded(tw[3 + i], bd.twist_r2_r1_r2[3 + i], (&cd.w_lin.x)[i]); }
+            cd.chi = chi; cd.Ebar1 = ins.Ebar1; cd.Ebar2 = ins.Ebar2; cd.n_quad = ins.n_quad;
+            if (kind1) orc::integrate_over_tet_tet(0, 0, bd); else orc::integrate_over_tri_tet(0, 0, bd);
+            const orc::V6<OD> wd_ref = orc::yes_contact_regularized(reg, bd);
+            pfc::Accum<PD, 6> accd;
+            accd.fp = fp; accd.w_ang = cd.w_ang; accd.w_lin = cd.w_lin; accd.dump = nullptr; accd.dump_cap = 0;
+            accd.reset(pfc::ACC_REGULARIZED);
+            pfc::integrate_pair(sc, ins, 0, 0, cd, accd, flags);
+            bool ok_d = (accd.n_points == (int)bd.traction.size());
+            for (int grp = 0; grp < 2 && ok_d; ++grp) {
+                double scale = 1.0e-6;
+                for (int i = 0; i < 3; ++i) { scale = std::fmax(scale, std::fabs(wd_ref[3 * grp + i].v)); for (int k = 0; k < 6; ++k) scale = std::fmax(scale, std::fabs(wd_ref[3 * grp + i].p[k])); }
+                for (int i = 0; i < 3; ++i) {
+                    if (std::fabs(accd.a[3 * grp + i].v - wd_ref[3 * grp + i].v) > 1.0e-9 * scale) ok_d = false;
+                    for (int k = 0; k < 6; ++k) if (std::fabs(accd.a[3 * grp + i].p[k] - wd_ref[3 * grp + i].p[k]) > 1.0e-9 * scale) ok_d = false;
+                }
+            }
+            if (!ok_d && bad_dual++ < 3) std::printf("Dual-6 wrench differs in case %ld (kind1 %d, %d points vs %zu)\n", t, kind1, accd.n_points, bd.traction.size());
         }
         const bool ok_tile = same(p_tile, b.traction), ok_pair = same(p_pair, b.traction);
         if (!ok_tile && bad_tile++ < 3) std::printf("tile route differs in case %ld (kind1 %d): %d points vs %zu\n", t, kind1, p_tile.n, b.traction.size());
@@ -194,9 +228,9 @@ int main(int argc, char** argv) {
         n_points += (long)b.traction.size();
         tet_tet += kind1 && !b.traction.empty();
     }
-    std::printf("cases %ld bad_tile %ld bad_pair %ld with_points %ld points %ld tet_tet_with_points %ld wrenches %ld bad_wrench %ld\n", n_case, bad_tile, bad_pair,
-                with_points, n_points, tet_tet, n_wrench, bad_wrench);
-    return (bad_tile || bad_pair || bad_wrench) ? 1 : 0;
+    std::printf("cases %ld bad_tile %ld bad_pair %ld with_points %ld points %ld tet_tet_with_points %ld wrenches %ld bad_wrench %ld bad_dual %ld\n", n_case, bad_tile, bad_pair,
+                with_points, n_points, tet_tet, n_wrench, bad_wrench, bad_dual);
+    return (bad_tile || bad_pair || bad_wrench || bad_dual) ? 1 : 0;
 }
 """
 
@@ -211,6 +245,6 @@ def test_device_narrow_phase_matches_oracle_point_by_point(tmp_path):
     sys.stdout.write(out.stdout)
     assert out.returncode == 0, out.stdout[-2000:]
     f = out.stdout.split()
-    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("bad_tile", "bad_pair", "with_points", "points", "tet_tet_with_points", "wrenches", "bad_wrench")}
-    assert stats["bad_tile"] == 0 and stats["bad_pair"] == 0 and stats["bad_wrench"] == 0 and stats["wrenches"] > 5000
+    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("bad_tile", "bad_pair", "with_points", "points", "tet_tet_with_points", "wrenches", "bad_wrench", "bad_dual")}
+    assert stats["bad_tile"] == 0 and stats["bad_pair"] == 0 and stats["bad_wrench"] == 0 and stats["bad_dual"] == 0 and stats["wrenches"] > 5000
     assert stats["with_points"] > 5000 and stats["tet_tet_with_points"] > 500   # the cases do produce contact polygons of both kinds
