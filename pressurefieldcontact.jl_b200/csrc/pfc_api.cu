@@ -441,7 +441,7 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
     } else { io.dbg_pairs = nullptr; io.dbg_cap = 0; }
     int nl = 0;
     if (c->scene.n_small > 0) {
-        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * n_ins));
+        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * n_ins + kSmallPairsSlack));
         CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, c->timing ? c->ev : nullptr));
         c->ev_valid = c->timing;
     }
@@ -555,7 +555,7 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
     io.n_pairs = reinterpret_cast<long long*>(n_pairs); io.flags = flags;
     int nl = 0;
     if (c->scene.n_small > 0) {  // small instructions are cheap: every rank evaluates them completely
-        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins));
+        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins + kSmallPairsSlack));
         CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
     }
     // every rank runs the breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair lists
@@ -611,7 +611,7 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
         EvalIO io{};
         io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
         if (c->scene.n_small > 0) {
-            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni));
+            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni + kSmallPairsSlack));
             CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
         }
         if (c->large_scene.n_large > 0) {
@@ -934,7 +934,7 @@ static int calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const
         EvalIO io{};
         io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = n_pairs; io.flags = flags;
         if (c->scene.n_small > 0) {
-            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni));
+            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni + kSmallPairsSlack));
             CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
         }
         if (c->large_scene.n_large > 0) {

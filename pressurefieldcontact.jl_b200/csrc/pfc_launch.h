@@ -23,6 +23,7 @@ constexpr int kSmallCap = 512;      // frontier / pair capacity of the fused sma
 constexpr int kSmallWarps = 4;      // warps (= instructions in flight) per CTA
 
 int small_cap(int max_pairs);
+constexpr int kSmallPairsSlack = 32;   // words after the pair lists: [0] is the narrow tile kernel's tile ticket (zeroed by the broad kernel)
 // ev: optional array of 3 events recorded before the broad kernel, between the two kernels and after the narrow kernel
 cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches,
                                   cudaEvent_t* ev = nullptr);

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
     constexpr int T = 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) pairs_out[(size_t)cap * io.n_env * sc.n_ins] = 0u;   // the narrow tile kernel's tile ticket
     // ---- node table: staged once per (persistent) CTA
     double* ntab_s = reinterpret_cast<double*>(smem_raw);
     for (int j = threadIdx.x; j < n_stage * 16; j += 32 * NW) {
@@ -519,12 +520,13 @@ template <int P> struct TileSmem {   // P problems, P warps
     unsigned char slot_n[kThreads];
     int resume_c;
     int q_lo[P], q_hi[P];   // item range of each problem in the current round
+    long long next_tile;    // drawn from the ticket counter by thread 0
     double fpv[P][8];
 };
 static_assert(sizeof(TileSmem<4>) <= 56 * 1024, "4 CTAs per SM need <= 56 KB each");
 
 template <int P, int MINB>
-__global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
+__global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in, unsigned* __restrict__ ticket) {
     constexpr int kTileThreads = 32 * P;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<P>& sm = *reinterpret_cast<TileSmem<P>*>(smem_raw);
@@ -532,7 +534,9 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
     const long long n_prob = io.n_env * sc.n_small;
     const long long n_tile = (n_prob + P - 1) / P;
     const int sum_q = wib;   // phase 4: warp q sums problem q
-    for (long long tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
+    // Tiles cost between half and twice the average (67 to 153 candidates per boxes.jl environment): after its first tile a CTA draws the
+    // next one from a ticket counter instead of striding (which CTA works on a tile does not change any result).
+    for (long long tile = blockIdx.x; tile < n_tile;) {
         // ---- 1. problem contexts: warp q fills problem q, one element per lane
         {
             const long long prob = tile * P + wib;
@@ -556,6 +560,7 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
             } else if (lane == 31) { sm.ei[wib] = -1; sm.n_cand[wib] = 0; sm.ins[wib] = 0; sm.fp[wib] = nullptr; sm.pflags[wib] = 0; }
         }
         __syncthreads();
+        if (tid == 0) sm.next_tile = (long long)gridDim.x + atomicAdd(ticket, 1u);   // read after the tile's last barrier
         int pre[P + 1];
         pre[0] = 0;
 #pragma unroll
@@ -690,6 +695,7 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
             }
         }
         __syncthreads();
+        tile = sm.next_tile;
     }
 }
 
@@ -774,7 +780,7 @@ cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, co
     }
     long long blocks = (io.n_env * sc.n_small + P - 1) / P;
     if (blocks > cached_blocks) blocks = cached_blocks;
-    kern<<<(unsigned)blocks, 32 * P, smem, stream>>>(sc, io, cap, pairs);
+    kern<<<(unsigned)blocks, 32 * P, smem, stream>>>(sc, io, cap, pairs, const_cast<unsigned*>(pairs) + (size_t)cap * io.n_env * sc.n_ins);
     return cudaGetLastError();
 }
 
