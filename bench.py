@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # DRAM traffic of one narrow_tile_kernel launch on the 4096-environment workload, from the committed ncu capture
-NARROW_TRAFFIC_BYTES = 9347328 + 2048   # profiles/r1_v15_narrow_tile_ncu.txt
+NARROW_TRAFFIC_BYTES = 9347840 + 4352   # profiles/r1_v17_narrow_tile_ncu.txt
 
 METRIC = "contact_wrench_evals_per_sec"
 UNIT = "evals/s"
@@ -438,7 +438,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": narrow_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": narrow_tflops / fp64_peak if fp64_peak else None, "traffic": NARROW_TRAFFIC_BYTES,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_v15_narrow_tile_ncu.txt)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_v17_narrow_tile_ncu.txt)",
                      "kernel": "narrow_tile_kernel (clip + quadrature + friction + fixed-order sums), the dominant kernel of the step",
                      "kernel_ms": narrow_ms, "kernel_share_of_step": narrow_ms / (narrow_ms + broad_ms),
                      "flops_per_launch": work["flops_narrow"] / n_count * n_env,
