@@ -22,7 +22,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CU(call)                                                                                          \
     do {                                                                                                  \
         cudaError_t e_ = (call);                                                                          \
-        if (e_ != cudaSuccess) return fail(PFC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? PFC_E_CAPACITY : PFC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
 struct HostMesh {
@@ -46,6 +46,12 @@ struct HostIns {
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }   // every buffer a context owns goes with it (pfc_destroy deletes the context on its device)
     cudaError_t ensure(size_t count) {
         if (count <= n) return cudaSuccess;
         if (p) cudaFree(p);
@@ -453,6 +459,9 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
     }
     c->launches += nl;
     c->last_X = io.X; c->last_tw = io.twist;
+    // the pair lists now belong to this evaluation: pfc_eval_dual6(X_bp = NULL) may reuse them only together with the library's own
+    // count / flag arrays (set again by the host-pointer entry points after a successful evaluation)
+    c->lists_n_env = -1;
     if (c->keep_pairs) {
         CU(c->d_last_np.ensure(size_t(io.n_env) * n_ins));
         CU(cudaMemcpyAsync(c->d_last_np.p, io.n_pairs, sizeof(long long) * io.n_env * n_ins, cudaMemcpyDeviceToDevice, c->stream));
@@ -564,6 +573,7 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
     c->launches += nl;
     c->sharded_io = io;
     c->sharded_stage = 0;
+    c->lists_n_env = -1;
     c->last_X = io.X; c->last_tw = io.twist;
     return PFC_OK;
 }
@@ -648,8 +658,10 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     CU(copy_out(c, fl, c->d_fl.p, sizeof(int32_t) * ne * ni));
     CU(cudaStreamSynchronize(c->stream));
     copy_out_finish(c);
-    for (size_t k = 0; k < ne * ni; ++k)
+    for (size_t k = 0; k < ne * ni; ++k) {
         if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
+        if (fl[k] & PFC_FLAG_OVERFLOW) return fail(PFC_E_CAPACITY, "candidate-pair capacity exceeded");
+    }
     return PFC_OK;
 }
 

@@ -340,7 +340,7 @@ __global__ void build_keys_kernel(SceneDev sc, LargeScene ls, const int3* __rest
             if (l < da) { key = (key << 1) | ((pa >> (da - 1 - l)) & 1ull); ++nb; }
         }
         key <<= (ls.key_bits - nb);  // left-align: keys of different lengths compare like the recursion order
-        keys[i] = ((unsigned long long)(unsigned)p.x << ls.key_bits) | key;
+        keys[i] = (ls.key_bits < 64 ? ((unsigned long long)(unsigned)p.x << ls.key_bits) : 0ull) | key;   // (64 key bits leave room for one problem only)
         vals[i] = i;
     }
 }
@@ -778,16 +778,27 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     if (n_prob_ll <= 0) return cudaSuccess;
     if (n_prob_ll > (1LL << 30)) return cudaErrorInvalidValue;
     const unsigned n_prob = (unsigned)n_prob_ll;
+    {   // the sort key is (problem, DFS key) in one 64-bit word: both parts must fit, or problems would alias
+        int prob_bits = 0;
+        while ((1ull << prob_bits) < (unsigned long long)n_prob) ++prob_bits;
+        if (ls.key_bits + prob_bits > 64) return cudaErrorMemoryAllocation;   // -> PFC_E_CAPACITY
+    }
     if (!b->cnt) LCU(cudaMalloc(&b->cnt, sizeof(Counters)));
     size_t want_frontier = std::max<size_t>(b->cap_frontier, std::max<size_t>(1u << 18, (size_t)n_prob * 4));
     size_t want_pairs = std::max<size_t>(b->cap_pairs, 1u << 20);
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     // the traversal kernel is persistent: every block must be resident, because idle warps wait for donated work
-    static int dfs_blocks_per_sm = 0;
-    if (dfs_blocks_per_sm == 0) {
-        LCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_blocks_per_sm, broad_dfs_kernel, kDfsWarps * 32, 0));
-        if (dfs_blocks_per_sm < 1) dfs_blocks_per_sm = 1;
+    int dfs_blocks_per_sm = 0;
+    {
+        struct Tag {};
+        std::lock_guard<std::mutex> g(launch_mutex());
+        LaunchSlot& sl = launch_slot<Tag>();
+        if (sl.blocks == 0) {
+            LCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sl.blocks, broad_dfs_kernel, kDfsWarps * 32, 0));
+            if (sl.blocks < 1) sl.blocks = 1;
+        }
+        dfs_blocks_per_sm = sl.blocks;
     }
     const int dfs_blocks = n_sm * dfs_blocks_per_sm;
     // BFS levels until about one seed per resident warp could exist (4^L * n_prob >= target); donation balances the rest
@@ -796,7 +807,8 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     // split over several GPUs: a contact patch is small against the meshes, so a few sub-trees carry nearly all of the work; three more
     // breadth-first levels make the hash-partitioned pieces ~64x finer, which is what balances the ranks (inside a GPU, donation does)
     if (hash_world > 1) levels = std::min(levels + 3, 14);
-    for (int attempt = 0; attempt < 8; ++attempt) {
+    bool done = false;
+    for (int attempt = 0; attempt < 12 && !done; ++attempt) {
         LCU(ensure(b->frontier[0], b->cap_frontier, want_frontier));
         LCU(ensure(b->frontier[1], b->cf2, want_frontier));
         LCU(ensure(b->pairs, b->cap_pairs, want_pairs));
@@ -818,12 +830,13 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
         LCU(cudaMemcpyAsync(&h, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         LCU(cudaStreamSynchronize(stream));
         if (h.overflow & 4u) return cudaErrorAssert;
-        if (h.overflow & 1u) { want_frontier *= 2; continue; }
+        if (h.overflow & 1u) { want_frontier = std::max<size_t>(want_frontier * 2, (size_t)std::max(h.frontier_n[0], std::max(h.frontier_n[1], h.q_tail)) + 1024); continue; }
         if (h.overflow & 2u) { want_pairs = std::max<size_t>(want_pairs * 2, (size_t)h.n_pairs + 1024); continue; }
         b->last_n_pairs = h.n_pairs;
         b->last_n_tests = h.n_tests;
-        break;
+        done = true;
     }
+    if (!done) return cudaErrorMemoryAllocation;   // every attempt overflowed: an error, not a truncated list (-> PFC_E_CAPACITY)
     const unsigned n = b->last_n_pairs;
     // segments + keys + sort
     LCU(ensure(b->seg_start, b->cap_seg, (size_t)n_prob + 1));
@@ -851,8 +864,12 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
             unsigned m = 1;
             while (m < n) m <<= 1;
             const size_t smem = (size_t)m * (sizeof(unsigned long long) + sizeof(unsigned));
-            static bool configured = false;
-            if (!configured) { LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12))); configured = true; }
+            {
+                struct Tag {};
+                std::lock_guard<std::mutex> g(launch_mutex());
+                LaunchSlot& sl = launch_slot<Tag>();
+                if (sl.key0 != 1) { LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12))); sl.key0 = 1; }
+            }
             small_sort_kernel<<<1, 1024, smem, stream>>>(b->keys[0], b->vals[0], n, b->keys[1], b->vals[1]);
             cur = 1;
             if (n_launches) *n_launches += 1;

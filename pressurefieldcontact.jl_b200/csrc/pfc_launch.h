@@ -2,9 +2,24 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "pfc_types.cuh"
 
 namespace pfc {
+
+// Launch-configuration cache.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and the persistent grid sizes depend on
+// the device's SM count, so what a launcher caches is keyed by (kernel family tag, variant, current device) -- several contexts on
+// different devices may live in one process (single-process multi-device, pfc_group) -- and guarded by one mutex.
+struct LaunchSlot { int key0 = -1, key1 = -1, blocks = 0; size_t smem = 0; };
+constexpr int kMaxLaunchDevices = 64;
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
+template <class Tag, int Variants = 1> inline LaunchSlot& launch_slot(int variant = 0) {   // call with launch_mutex() held
+    static LaunchSlot slots[kMaxLaunchDevices][Variants];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return slots[dev % kMaxLaunchDevices][variant];
+}
 
 struct EvalIO {
     long long n_env;

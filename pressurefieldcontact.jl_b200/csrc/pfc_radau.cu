@@ -96,11 +96,15 @@ __global__ void __launch_bounds__(256) radau_inv_c_kernel(int n, const double* _
 cudaError_t launch_radau_inv_c(long long n_mat, int n, const double* neg_J, const double* shift, const int* index, double* inv_c, int* info, cudaStream_t stream) {
     if (n_mat == 0) return cudaSuccess;
     const size_t smem = sizeof(cplx) * (size_t)n * (n + 1) + sizeof(int) * n;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(radau_inv_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
+    {
+        struct Tag {};
+        std::lock_guard<std::mutex> g(launch_mutex());
+        LaunchSlot& sl = launch_slot<Tag>();
+        if (smem > sl.smem) {
+            cudaError_t e = cudaFuncSetAttribute(radau_inv_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            sl.smem = smem;
+        }
     }
     radau_inv_c_kernel<<<(unsigned)n_mat, 256, smem, stream>>>(n, neg_J, shift, index, inv_c, info);
     return cudaGetLastError();

@@ -730,15 +730,21 @@ int persistent_blocks(const void* kern, int threads, size_t smem, cudaError_t* e
 
 template <int P, int NW, int MINB>
 cudaError_t launch_broad_tile(const SceneDev& sc, const EvalIO& io, int cap, unsigned* pairs, cudaStream_t stream) {
-    static int cached_cap = -1, cached_stage = -1, cached_blocks = 0;
+    struct Tag {};
     auto kern = broad_tile_kernel<P, NW, MINB>;
     const int n_stage = sc.small_node_n <= kNodeTabMax ? sc.small_node_n : 0;
     const size_t smem = BroadTileLayout<P>::bytes(cap, NW, n_stage);
-    if (cached_cap != cap || cached_stage != n_stage) {
-        cudaError_t e;
-        cached_blocks = persistent_blocks((const void*)kern, 32 * NW, smem, &e);
-        if (e != cudaSuccess) return e;
-        cached_cap = cap; cached_stage = n_stage;
+    int cached_blocks;
+    {
+        std::lock_guard<std::mutex> g(launch_mutex());
+        LaunchSlot& sl = launch_slot<Tag>();
+        if (sl.key0 != cap || sl.key1 != n_stage) {
+            cudaError_t e;
+            sl.blocks = persistent_blocks((const void*)kern, 32 * NW, smem, &e);
+            if (e != cudaSuccess) return e;
+            sl.key0 = cap; sl.key1 = n_stage;
+        }
+        cached_blocks = sl.blocks;
     }
     const long long n_tile = (io.n_env * sc.n_small + P - 1) / P;
     long long blocks = (n_tile + NW - 1) / NW;
@@ -749,19 +755,25 @@ cudaError_t launch_broad_tile(const SceneDev& sc, const EvalIO& io, int cap, uns
 
 template <int G, int MINB>
 cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
-    static int cached_cap[2] = {-1, -1}, cached_blocks[2] = {0, 0};
+    struct Tag {};
     const int hb = sc.n_bristle > 0 ? 1 : 0;
     const void* kern = hb ? (const void*)narrow_small_kernel<kSmallWarps, G, MINB, true> : (const void*)narrow_small_kernel<kSmallWarps, G, MINB, false>;
     const size_t smem = NarrowLayout<G>::bytes(cap) * kSmallWarps;
-    if (cached_cap[hb] != cap) {
-        cudaError_t e;
-        cached_blocks[hb] = persistent_blocks(kern, kSmallWarps * 32, smem, &e);
-        if (e != cudaSuccess) return e;
-        cached_cap[hb] = cap;
+    int cached_blocks;
+    {
+        std::lock_guard<std::mutex> g(launch_mutex());
+        LaunchSlot& sl = launch_slot<Tag, 2>(hb);
+        if (sl.key0 != cap) {
+            cudaError_t e;
+            sl.blocks = persistent_blocks(kern, kSmallWarps * 32, smem, &e);
+            if (e != cudaSuccess) return e;
+            sl.key0 = cap;
+        }
+        cached_blocks = sl.blocks;
     }
     constexpr int per_block = kSmallWarps * (32 / G);
     long long blocks = (io.n_env * sc.n_small + per_block - 1) / per_block;
-    if (blocks > cached_blocks[hb]) blocks = cached_blocks[hb];
+    if (blocks > cached_blocks) blocks = cached_blocks;
     if (hb) narrow_small_kernel<kSmallWarps, G, MINB, true><<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
     else narrow_small_kernel<kSmallWarps, G, MINB, false><<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
     return cudaGetLastError();
@@ -770,13 +782,19 @@ cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const
 
 template <int P, int MINB>
 cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
-    static int cached_blocks = 0;
+    struct Tag {};
     auto kern = narrow_tile_kernel<P, MINB>;
     const size_t smem = sizeof(TileSmem<P>);
-    if (cached_blocks == 0) {
-        cudaError_t e;
-        cached_blocks = persistent_blocks((const void*)kern, 32 * P, smem, &e);
-        if (e != cudaSuccess) return e;
+    int cached_blocks;
+    {
+        std::lock_guard<std::mutex> g(launch_mutex());
+        LaunchSlot& sl = launch_slot<Tag>();
+        if (sl.blocks == 0) {
+            cudaError_t e;
+            sl.blocks = persistent_blocks((const void*)kern, 32 * P, smem, &e);
+            if (e != cudaSuccess) return e;
+        }
+        cached_blocks = sl.blocks;
     }
     long long blocks = (io.n_env * sc.n_small + P - 1) / P;
     if (blocks > cached_blocks) blocks = cached_blocks;
