@@ -6,7 +6,10 @@ reference's test/boxes.jl scene (1-tet half-space + 4 boxes alternately rigid/tr
 compliant/tet, 4 regularized-friction contact instructions, quadrature rule 2) at randomized
 settled-stack states (tests/helpers.py::boxes_env_states).  One "step" = one pass of the hot
 path (forceAllElasticIntersections!, Float64 mode) over the whole batch; one "eval" = one
-environment.  Weak scaling: every GPU gets its own 4096 environments, no collective on the path.
+environment.  The headline at N GPUs is STRONG scaling -- the 4096 environments of BASELINE.json's configs[2] are split into
+contiguous ranges of 4096 / N per GPU (pressurefieldcontact.jl_b200/parallel.py::env_range), one process and one context per GPU,
+no collective on the path.  Secondary blocks of the same line: `weak` (4096 environments on every GPU) and `large_scenes` (C4 / C5:
+one very large scene; at N > 1 its candidate-pair lists are split over the N GPUs and the per-instruction partial sums cross NCCL).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
 
@@ -30,21 +33,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-# DRAM traffic of one narrow_tile_kernel launch on the 4096-environment workload, from the committed ncu capture
-NARROW_TRAFFIC_BYTES = 9347840 + 4352   # profiles/r1_v17_narrow_tile_ncu.txt
+WORKLOAD = "C3: {n} x test/boxes.jl environments (4 regularized-friction contact instructions each, quad rule 2), randomized settled-stack states"
+
+
+def narrow_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on this workload, from the committed
+    `ncu --set full` capture of this command (profiles/narrow_tile_traffic.json, written by profiles/ncu_summary.py); None when absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "narrow_tile_traffic.json")))
+        return int(t["dram_bytes_per_launch"]), t.get("source", "profiles/narrow_tile_traffic.json")
+    except Exception:
+        return None, None
 
 METRIC = "contact_wrench_evals_per_sec"
 UNIT = "evals/s"
 
 
-def build_inputs(n_env, rank=0):
-    """Scene description (host mirror) + boundary arrays for n_env environments of this rank."""
+def build_inputs(n_env, start=0):
+    """Scene description (host mirror) + boundary arrays for the environments [start, start + n_env) (seeds are a function of the
+    global environment index, so every partition of the batch sees the same states)."""
     import pfc_b200  # noqa: F401
     from helpers import boxes_env_states, scene_boxes, splitmix64  # noqa: F401
     from pfc_b200 import scenario as S
     m, _ = scene_boxes(None)
-    # rank r gets environments [r * n_env, (r + 1) * n_env): seeds are a function of the global env index
-    x_all = boxes_env_states(m, n_env, start=rank * n_env)
+    x_all = boxes_env_states(m, n_env, start=start)
     X, tw, s = S.boundary_arrays(m, x_all)
     m.x_all = np.ascontiguousarray(x_all)
     return m, np.ascontiguousarray(X), np.ascontiguousarray(tw)
@@ -113,14 +125,25 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
-def measure_large_scenes(device_index):
+class _RawCuda:
+    """A device pointer as a __cuda_array_interface__ object (float64 vector)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def measure_large_scenes(device_index, rank=0, world=1):
     """Secondary numbers (not the headline): the metric's second half, candidate pairs per second, on the two single-large-scene
     configurations -- C4 (sphere on slab, tet-tet, ~2 x 100 k tets) and C5 (64-body pile, ~0.9 M candidate tri-tet pairs per
     evaluation).  Device-resident inputs, CUDA events on the library's stream, one environment, no L2 flush (the static scene is meant
-    to be L2-resident).  Traversal + compaction are reported against the measured HBM peak with SURVEY 8d's algorithmic bytes
-    (272 B per node pair visited, 12 B per pair emitted)."""
+    to be L2-resident).  At world > 1 the scene is SPLIT over the GPUs (pfc_set_shard + the sharded protocol of include/pfc.h): every
+    rank runs the breadth-first levels, traverses / sorts / evaluates the sub-trees whose hash falls on it, and the per-instruction
+    partial sums (8 doubles each) are all-reduced over NCCL on the library's stream; the time is the max over ranks.  Traversal +
+    compaction are reported against the measured HBM peak with SURVEY 8d's algorithmic bytes (272 B per node pair visited, 12 B per pair
+    emitted)."""
     import torch
-    from pfc_b200 import capi, scenes
+    import torch.distributed as dist
+    from pfc_b200 import capi, parallel, scenes
     from pfc_b200 import scenario as S
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
@@ -133,6 +156,8 @@ def measure_large_scenes(device_index):
             m, x = build()
             ctx = capi.Context(device_index)
             S.attach_backend(m, ctx)
+            if world > 1:
+                ctx.set_shard(rank, world)
             X, tw, _ = S.boundary_arrays(m, x)
             n_ins = ctx.n_ins
             Xd, twd = torch.from_numpy(X).to(dev), torch.from_numpy(tw).to(dev)
@@ -140,25 +165,55 @@ def measure_large_scenes(device_index):
             npairs = torch.zeros((1, n_ins), dtype=torch.int64, device=dev)
             fl = torch.zeros((1, n_ins), dtype=torch.int32, device=dev)
             stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-            step = lambda: ctx.eval_f64_device(1, Xd.data_ptr(), twd.data_ptr(), None, w.data_ptr(), None, npairs.data_ptr(), fl.data_ptr())
+            n_exchange = [0]
+
+            def reduce_partials(ptr, count):
+                t = torch.as_tensor(_RawCuda(ptr, count), device=dev)
+                with torch.cuda.stream(stream):
+                    parallel.allreduce_sum_(t)
+
+            if world > 1:
+                def step():
+                    n_exchange[0] = parallel.eval_sharded(ctx, 1, Xd, twd, None, w, None, npairs, fl, reduce_partials)
+            else:
+                def step():
+                    ctx.eval_f64_device(1, Xd.data_ptr(), twd.data_ptr(), None, w.data_ptr(), None, npairs.data_ptr(), fl.data_ptr())
             for _ in range(3):
                 step()
             ctx.sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0, reps = ctx.launch_count(), 10
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             e0.record(stream)
             for _ in range(reps):
                 step()
             e1.record(stream)
             ctx.sync()
             ms = e0.elapsed_time(e1) / reps
-            n_tests, n_pairs = ctx.counters()
-            gbs = (272 * n_tests + 12 * n_pairs) / (ms * 1e-3) * 1e-9
-            out[name] = {"ms_per_eval": ms, "candidate_pairs": int(n_pairs), "node_pairs_tested": int(n_tests), "instructions": n_ins,
+            n_tests, n_listed = ctx.counters()
+            counts = torch.tensor([float(ms), float(n_tests), float(n_listed)], dtype=torch.float64, device=dev)
+            ms_min = ms
+            if world > 1:
+                mx = counts.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                mn = counts.clone()
+                dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+                ms, ms_min = float(mx[0]), float(mn[0])
+                n_tests, n_listed = int(counts[1]), int(counts[2])
+            n_pairs = int(npairs.sum().item())   # after the exchange every rank holds the full counts
+            gbs = (272 * n_tests + 12 * n_listed) / (ms * 1e-3) * 1e-9
+            out[name] = {"ms_per_eval": ms, "n_gpus": world, "candidate_pairs": n_pairs, "node_pairs_tested": int(n_tests), "instructions": n_ins,
                          "candidate_pairs_per_sec": n_pairs / (ms * 1e-3), "contacts": int((fl.cpu().numpy() & 1).sum()),
                          "kernel_launches_per_eval": int((ctx.launch_count() - l0) // reps),
-                         "broad_phase_roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                                  "bytes": "272 B per node pair visited + 12 B per pair emitted (SURVEY 8d); the scene is L2-resident"}}
+                         "broad_phase_roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak * world, "unit": "GB/s", "frac": gbs / (hbm_peak * world),
+                                                  "bytes": "272 B per node pair visited + 12 B per pair emitted (SURVEY 8d), summed over the ranks; the scene is L2-resident"}}
+            if world > 1:
+                out[name].update({"split": "hash-partitioned sub-trees of the dual-tree recursion, disjoint pair lists", "exchanges_per_eval": n_exchange[0],
+                                  "collective": "NCCL all_reduce(sum) of 8 doubles per large instruction on the library's stream",
+                                  "ms_fastest_rank": ms_min, "timing": "CUDA events on each rank's stream, max over ranks"})
             ctx.close()
         except Exception as exc:   # secondary measurement: never take the headline down with it
             out[name] = {"error": repr(exc)}
@@ -168,7 +223,7 @@ def measure_large_scenes(device_index):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia
     (not installable here, no Julia in the image), so this arm times the CPU oracle -- a literal C++
-    port of the same algorithm -- with all host threads, on the same workload, metric and unit."""
+    port of the same algorithm -- with all host threads, on the same workload (every step = all environments), metric and unit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -179,22 +234,20 @@ def run_reference(args):
     cores = orc.lib().orc_max_threads()
     ctx = orc.OracleContext(n_threads=cores)
     S.attach_backend(m, ctx)
-    # each step = a bounded sample of the workload: the first `sample` environments of the batch
-    sample = min(n_env, 1024)
-    Xs, tws = X[:sample], tw[:sample]
     for _ in range(args.warmup):
-        ctx.eval_f64(Xs, tws)
+        ctx.eval_f64(X, tw)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.eval_f64(Xs, tws)
+        ctx.eval_f64(X, tw)
     dt = time.perf_counter() - t0
-    v = sample * args.steps / dt
+    v = n_env * args.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"C3: {n_env} x test/boxes.jl environments (4 contact instructions each)", "envs_per_gpu": n_env},
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD.format(n=n_env), "envs": n_env, "instructions_per_env": 4},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} of the {n_env} environments per step, {args.steps} steps, C++ port of the Julia reference (Julia is not in the image)"},
+                         "sample": f"all {n_env} environments per step, {args.steps} steps, {cores} threads; C++ port of the Julia reference (Julia is not in the image; "
+                                   "the reference itself is single-threaded)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -204,7 +257,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--envs", type=int, default=4096, help="environments of the whole job (split over the GPUs)")
     ap.add_argument("--impl", default="pfc", choices=["pfc", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-large", action="store_true", help="skip the secondary single-large-scene measurements (C4 / C5)")
@@ -224,13 +277,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from pfc_b200 import capi
+    from pfc_b200 import capi, parallel
     from pfc_b200 import scenario as S
 
-    n_env = args.envs
-    m, X_h, tw_h = build_inputs(n_env, rank)
+    n_total = args.envs
+    lo, hi = parallel.env_range(n_total, rank, world)   # strong scaling: this rank's contiguous range of the job's environments
+    n_env = hi - lo
+    m, X_h, tw_h = build_inputs(n_env, lo)
     ctx = capi.Context(local_rank)
-    S.attach_backend(m, ctx, max_env=n_env)
+    S.attach_backend(m, ctx, max_env=n_total)
     n_ins = ctx.n_ins
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -270,7 +325,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    fp64_peak = ctx.measure_fp64_peak()
+    with ClockSampler(local_rank) as peak_clocks:
+        fp64_peak = ctx.measure_fp64_peak()
+        ctx.sync()
+    peak_clock = peak_clocks.summary()["sm_mhz"]
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -321,6 +379,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s, e2e_b_s = float(t[0]), float(t[1]), float(t[2])
 
+    # ---- secondary, N > 1: weak scaling (every GPU its own n_total environments; independent processes, no collective) ----
+    weak = None
+    if world > 1:
+        _, Xw_h, tww_h = build_inputs(n_total, rank * n_total)
+        Xw, tww = torch.from_numpy(Xw_h).to(dev), torch.from_numpy(tww_h).to(dev)
+        ww = torch.zeros((n_total, n_ins, 6), dtype=torch.float64, device=dev)
+        npw = torch.zeros((n_total, n_ins), dtype=torch.int64, device=dev)
+        flw = torch.zeros((n_total, n_ins), dtype=torch.int32, device=dev)
+        step_w = lambda: ctx.eval_f64_device(n_total, Xw.data_ptr(), tww.data_ptr(), None, ww.data_ptr(), None, npw.data_ptr(), flw.data_ptr())
+        for _ in range(3):
+            step_w()
+        n_w = max(args.steps // 4, 10)
+        w0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_w)]
+        w1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_w)]
+        barrier()
+        for k in range(n_w):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            w0[k].record(stream)
+            step_w()
+            w1[k].record(stream)
+        barrier()
+        tw_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(w0, w1))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tw_ms, op=dist.ReduceOp.MAX)
+        weak = {"value": n_total * world * n_w / (float(tw_ms[0]) * 1e-3), "unit": UNIT, "scaling": "weak", "envs_per_gpu": n_total, "steps": n_w,
+                "ms_per_step": float(tw_ms[0]) / n_w, "what": "device-resident, every GPU its own batch of the full size; no collective"}
+        del Xw, tww, ww, npw, flw
+
     # correctness guard: the timed outputs are real (contacts found, finite wrench)
     w_host = w_d.cpu().numpy()
     assert np.isfinite(w_host).all() and int((fl_d.cpu().numpy() & 1).sum()) > n_env, "benchmark produced no contact work"
@@ -328,12 +414,15 @@ def main():
     f_chk = S.generalized_forces(m, m.x_all[0], w_host[0])
     assert np.abs(f_p.numpy()[0] - f_chk).max() <= 1e-9 * max(np.abs(f_chk).max(), 1e-300), "state-level entry point disagrees with J' w on the host"
 
+    # secondary: one very large scene (C4 / C5); at N > 1 split over the GPUs with an NCCL exchange of the partial sums (all ranks take part)
+    large = None if args.no_large else measure_large_scenes(local_rank, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    evals = n_env * world * args.steps
+    evals = n_total * args.steps
     value = evals / (dev_ms * 1e-3)
     ms_per_step = dev_ms / args.steps
 
@@ -357,23 +446,29 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
 
-    cpu_sample = min(n_env, 1024)
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        octx.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
-        reps += 1
-        if time.perf_counter() - t0 > args.cpu_seconds or reps >= 200:
-            break
-    cpu_1 = cpu_sample * reps / (time.perf_counter() - t0)
-    cores = orc.lib().orc_max_threads()
-    octx_mt = orc.OracleContext(n_threads=cores)
-    S.attach_backend(m, octx_mt)
-    octx_mt.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
-    t0 = time.perf_counter()
-    for _ in range(5):
-        octx_mt.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
-    cpu_mt = cpu_sample * 5 / (time.perf_counter() - t0)
+    cpu_baseline = None
+    if world == 1:   # timed on rank 0 at N = 1 only
+        cpu_sample = min(n_env, 1024)
+        t0 = time.perf_counter()
+        cpu_reps = 0
+        while True:
+            octx.eval_f64(X_h[:cpu_sample], tw_h[:cpu_sample])
+            cpu_reps += 1
+            if time.perf_counter() - t0 > args.cpu_seconds or cpu_reps >= 200:
+                break
+        cpu_1 = cpu_sample * cpu_reps / (time.perf_counter() - t0)
+        cores = orc.lib().orc_max_threads()
+        octx_mt = orc.OracleContext(n_threads=cores)
+        S.attach_backend(m, octx_mt)
+        octx_mt.eval_f64(X_h, tw_h)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            octx_mt.eval_f64(X_h, tw_h)
+        cpu_mt = n_env * 3 / (time.perf_counter() - t0)
+        cpu_baseline = {"value": cpu_1, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"{cpu_sample} of the {n_env} environments x {cpu_reps} repetitions, single thread (the reference is single-threaded); "
+                                  "C++ port of the Julia reference, not Julia",
+                        "all_cores": {"value": cpu_mt, "cores": cores, "sample": f"all {n_env} environments x 3 repetitions"}}
 
     h2d = int(m.x_all.nbytes)
     d2h = int(f_p.numel() * 8 + 4)   # generalized forces + the 4-byte error status word
@@ -383,7 +478,7 @@ def main():
     # for the whole batch through pfc_calcxd_dual6, host buffers in and out (x in, x_dot + 6 partials out)
     jac = None
     try:
-        if getattr(m, "device_dynamics", False):
+        if getattr(m, "device_dynamics", False) and world == 1:
             xd7 = np.zeros((n_env, m.x_all.shape[1], 7))
             npj, flj = np.zeros((n_env, n_ins), np.int64), np.zeros((n_env, n_ins), np.int32)
             lib = capi.lib()
@@ -401,7 +496,7 @@ def main():
     # secondary: the reference's adaptive Radau IIA integrator for the whole batch with every array on the GPU (radau_batched.py)
     rollout = None
     try:
-        if getattr(m, "device_dynamics", False) and not args.no_large:
+        if getattr(m, "device_dynamics", False) and not args.no_large and world == 1:
             from pfc_b200.radau_batched import BatchedRadau
             m.backend = ctx     # (the cpu_baseline leg above attached the oracle to the same scene description)
             br = BatchedRadau(m, n_env, device_index=local_rank, h_max=0.05)
@@ -421,14 +516,14 @@ def main():
                                "evaluations through pfc_calcxd_f64_device; per-environment step-size / order control"}
     except Exception as exc:
         rollout = {"error": repr(exc)}
-    large = None if args.no_large else measure_large_scenes(local_rank)
+    traffic, traffic_src = narrow_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3: {n_env} x test/boxes.jl environments per GPU (4 regularized-friction contact instructions each, quad rule 2), "
-                               "randomized settled-stack states", "envs_per_gpu": n_env, "instructions_per_env": n_ins,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(n=n_total), "envs": n_total, "instructions_per_env": n_ins, "envs_per_gpu": n_env,
                    "candidate_pairs_per_eval": pairs_per_eval, "node_pairs_per_eval": node_pairs_per_eval,
-                   "l2": "256 MiB flush between timed steps", "parallelism": f"env-sharded x{world}, no collective"},
+                   "l2": "256 MiB flush between timed steps",
+                   "parallelism": f"contiguous environment ranges of {n_total} / {world} per GPU (one process and one context per GPU), no collective on the path"},
         "candidate_pairs_per_sec": pairs_per_eval * value,
         "e2e": {"value": evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
                 "api": "pfc_eval_state_f64: pinned host states x[env][48] in, generalized forces f[env][24] (+ a 4-byte error status) out; "
@@ -437,12 +532,13 @@ def main():
                                    "ms_per_step": e2e_b_s / args.steps * 1e3, "api": "pfc_eval_f64: X_r2_r1 + twist in, wrenches out (host kinematics not timed)"}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": narrow_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": narrow_tflops / fp64_peak if fp64_peak else None, "traffic": NARROW_TRAFFIC_BYTES,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_v17_narrow_tile_ncu.txt)",
+                     "frac": narrow_tflops / fp64_peak if fp64_peak else None, "traffic": traffic if (world == 1 and n_total == 4096) else None,
+                     "traffic_source": traffic_src,
                      "kernel": "narrow_tile_kernel (clip + quadrature + friction + fixed-order sums), the dominant kernel of the step",
                      "kernel_ms": narrow_ms, "kernel_share_of_step": narrow_ms / (narrow_ms + broad_ms),
                      "flops_per_launch": work["flops_narrow"] / n_count * n_env,
-                     "peak_source": "DFMA micro-benchmark in this process (pfc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                     "peak_source": "DFMA micro-benchmark in this process before the timed regions (pfc_measure_fp64_peak: best of 5 bursts of 148 x 8 CTAs x 256 "
+                                    "threads x 8 independent FMA chains); MEASURED_PEAKS.json has no FP64 entry", "peak_sm_mhz": peak_clock,
                      "other_kernels": {"broad_small_kernel": {"kernel_ms": broad_ms, "achieved": broad_tflops, "unit": "TFLOP/s",
                                                               "frac": broad_tflops / fp64_peak if fp64_peak else None,
                                                               "flops_per_launch": work["flops_broad"] / n_count * n_env}},
@@ -450,12 +546,11 @@ def main():
                      "hbm": {"achieved": bytes_per_eval * n_env / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": bytes_per_eval * n_env / (ms_per_step * 1e-3) * 1e-9 / hbm_peak, "bytes_per_eval": bytes_per_eval,
                              "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}},
-        "cpu_baseline": {"value": cpu_1, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{cpu_sample} of the {n_env} environments x {reps} repetitions, single thread (the reference is single-threaded); "
-                                   "C++ port of the Julia reference, not Julia",
-                         "all_cores": {"value": cpu_mt, "cores": cores}},
+        "cpu_baseline": cpu_baseline,
         "clocks": clocks.summary(),
     }
+    if weak is not None:
+        line["weak"] = weak
     if jac is not None:
         line["jacobian_chunks"] = jac
     if rollout is not None:

@@ -79,8 +79,9 @@ int pfc_eval_f64(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const doubl
 
 /* Same evaluation on buffers already resident in device memory (all pointers are device pointers,
  * none may be NULL except s/sdot without bristles); enqueued on the context's stream.  Asynchronous for scenes whose instructions all
- * take the small path (n_leaf_1 * n_leaf_2 <= 512, e.g. test/boxes.jl); scenes with large instructions synchronise the stream once
- * inside the call: the candidate-pair count is read back to size the sort and to grow the pair buffers like the reference's VectorCache. */
+ * take the small path (n_leaf_1 * n_leaf_2 <= 512, e.g. test/boxes.jl) and use regularized friction; scenes with large instructions
+ * synchronise the stream once inside the call (the candidate-pair count is read back to size the sort and to grow the pair buffers like
+ * the reference's VectorCache), and so do scenes with bristle instructions (the TractionCache buffer grows the same way). */
 int pfc_eval_f64_device(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2,
                         double* sdot, int64_t* n_pairs, int32_t* flags);
 
@@ -148,16 +149,17 @@ int pfc_get_pairs(pfc_ctx* ctx, int64_t env, int ins, int32_t* pairs, int64_t ca
 /* TractionCache (src/mechanism_scenario.jl:51-58) of (env, ins) from the last evaluation: 8 doubles per point: n(3), r_cart(3), dA, p. */
 int pfc_get_traction(pfc_ctx* ctx, int64_t env, int ins, double* out, int64_t cap_points, int64_t* n_out);
 
-/* Multi-GPU for one very large scene: this context traverses, lists and evaluates only the sub-trees of every large instruction's
- * dual-tree recursion whose hash falls on `rank` of `world` (disjoint pair lists, no exchange before the sums); the caller sums the
- * partial buffers across ranks (NCCL allreduce).  pfc_get_pairs then returns this rank's part of the list. */
+/* Multi-GPU for one very large scene: this context traverses, lists and evaluates only the sub-trees of every large REGULARIZED
+ * instruction's dual-tree recursion whose hash falls on `rank` of `world` (disjoint pair lists, no exchange before the sums); the partial
+ * sums are then reduced over the ranks.  Bristle instructions are never split: their sums run sequentially over the whole TractionCache
+ * list (the reference's order, src/contact_algorithms_friction.jl:147-201), so every rank lists and evaluates them completely and ends with
+ * identical bits.  pfc_get_pairs returns this rank's part of a split list. */
 int pfc_set_shard(pfc_ctx* ctx, int rank, int world);
-/* Sharded evaluation protocol (device pointers, asynchronous on the context's stream):
- *   begin:    breadth-first levels (every rank), this rank's share of the traversal, sort, stage 0 over its own pairs;
- *   partials: the buffer the caller must sum over all ranks in place: count doubles (23 per (env, large instruction): 21 sums,
+/* Sharded evaluation protocol (device pointers):
+ *   begin:    breadth-first levels (every rank), this rank's share of the traversal, sort, narrow phase over its own pairs;
+ *   partials: the buffer the caller must sum over all ranks in place: count doubles (8 per (env, large instruction): 6 wrench sums,
  *             traction-point count, pair count);
- *   step:     applies the summed buffer (wrench / bristle state) and, if the friction model needs another pass
- *             (bristle: centre of pressure -> stiffness -> friction), runs it and sets *more = 1. */
+ *   step:     applies the summed buffer (wrench, counts, flags); *more is always 0 (one exchange per evaluation). */
 int pfc_eval_sharded_begin(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2,
                            double* sdot, int64_t* n_pairs, int32_t* flags);
 int pfc_eval_sharded_partials(pfc_ctx* ctx, double** dev_ptr, int64_t* count);

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/pfc.h"
+#include "pfc_exact.h"
 #include "pfc_large.h"
 #include "pfc_launch.h"
 
@@ -104,6 +105,12 @@ struct pfc_ctx {
     LargeScene large_scene{};
     LargeBuffers* large_buf = nullptr;
     std::vector<int32_t> large_ins_host;
+    // reference-order pipeline of the bristle instructions (pfc_exact.cu)
+    DevBuf<double> d_tet_eps;
+    DevBuf<int32_t> d_bris_ins;
+    ExactScene exact_scene{};
+    ExactBuffers* exact_buf = nullptr;
+    bool has_large_bristle = false;
     int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
     EvalIO sharded_io{};
     // Jacobian mode staging + the pair lists it may reuse
@@ -132,7 +139,7 @@ struct pfc_ctx {
     size_t arena_cap = 0, arena_used = 0;
     struct PendingOut { void* dst; const void* src; size_t bytes; };
     std::vector<PendingOut> arena_out;
-    bool large_index_dirty = true;   // d_large_index (instruction -> index in the large list) needs uploading
+    bool large_index_dirty = true;
     int* h_status = nullptr;    // pinned
     DynDev dyn{};
     bool timing = false;
@@ -142,34 +149,35 @@ struct pfc_ctx {
 
 namespace {
 
-// inverse of A = [v0 v1 v2 v3; 1 1 1 1] (columns are the homogeneous vertices) by the adjugate,
-// using 2x2 sub-determinants; row-major output.
-bool invert_tet_matrix(const double v[12], double inv[16]) {
-    double a[16];  // row-major a[4*i+j]
-    for (int j = 0; j < 4; ++j) { a[0 + j] = v[3 * j]; a[4 + j] = v[3 * j + 1]; a[8 + j] = v[3 * j + 2]; a[12 + j] = 1.0; }
-    const double s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
-    const double s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
-    const double c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
-    const double c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
-    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+// inverse of A = [v0 v1 v2 v3; 1 1 1 1] (columns are the homogeneous vertices): the explicit adjugate / determinant formula for a 4x4
+// (what StaticArrays' inv(::SMatrix{4,4}) amounts to; the reference inverts per candidate pair, src/contact_algorithms_non_friction.jl:158-162).
+// The expression order is fixed -- every cofactor as a left-to-right sum of triple products of the column-major entries m[], then one
+// division and 16 scalings -- because the reference-order bristle path (pfc_exact.cuh) reproduces the reference's K matrix bit for bit
+// from these per-tetrahedron constants.  Row-major output.
+bool invert_tet_matrix(const double v[12], double out[16]) {
+    double m[16];  // column-major: m[4*c + r]
+    for (int c = 0; c < 4; ++c) { m[4 * c] = v[3 * c]; m[4 * c + 1] = v[3 * c + 1]; m[4 * c + 2] = v[3 * c + 2]; m[4 * c + 3] = 1.0; }
+    double inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
     if (!(det != 0.0) || !std::isfinite(det)) return false;
-    const double id = 1.0 / det;
-    inv[0] = (a[5] * c5 - a[6] * c4 + a[7] * c3) * id;
-    inv[1] = (-a[1] * c5 + a[2] * c4 - a[3] * c3) * id;
-    inv[2] = (a[13] * s5 - a[14] * s4 + a[15] * s3) * id;
-    inv[3] = (-a[9] * s5 + a[10] * s4 - a[11] * s3) * id;
-    inv[4] = (-a[4] * c5 + a[6] * c2 - a[7] * c1) * id;
-    inv[5] = (a[0] * c5 - a[2] * c2 + a[3] * c1) * id;
-    inv[6] = (-a[12] * s5 + a[14] * s2 - a[15] * s1) * id;
-    inv[7] = (a[8] * s5 - a[10] * s2 + a[11] * s1) * id;
-    inv[8] = (a[4] * c4 - a[5] * c2 + a[7] * c0) * id;
-    inv[9] = (-a[0] * c4 + a[1] * c2 - a[3] * c0) * id;
-    inv[10] = (a[12] * s4 - a[13] * s2 + a[15] * s0) * id;
-    inv[11] = (-a[8] * s4 + a[9] * s2 - a[11] * s0) * id;
-    inv[12] = (-a[4] * c3 + a[5] * c1 - a[6] * c0) * id;
-    inv[13] = (a[0] * c3 - a[1] * c1 + a[2] * c0) * id;
-    inv[14] = (-a[12] * s3 + a[13] * s1 - a[14] * s0) * id;
-    inv[15] = (a[8] * s3 - a[9] * s1 + a[10] * s0) * id;
+    const double idet = 1.0 / det;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[4 * r + c] = inv[4 * c + r] * idet;   // column-major adjugate -> row-major inverse
     return true;
 }
 
@@ -220,6 +228,7 @@ int pfc_destroy(pfc_ctx* c) {
     c->d_large.release(); c->d_leaf_path.release(); c->d_leaf_depth.release();
     c->d_X7.release(); c->d_tw7.release(); c->d_s7.release(); c->d_w7.release(); c->d_sd7.release(); c->d_large_index.release();
     large_buffers_destroy(c->large_buf);
+    exact_buffers_destroy(c->exact_buf);
     delete c;
     return PFC_OK;
 }
@@ -316,6 +325,7 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
     std::vector<NodeRec> nodes;
     std::vector<TetRec> tets;
     std::vector<TriRec> tris;
+    std::vector<double> tet_eps;   // per tetrahedron: the pressure-field value at its 4 vertices
     for (auto& m : c->mesh) {
         m.node_base = int(nodes.size());
         nodes.insert(nodes.end(), m.nodes.begin(), m.nodes.end());
@@ -332,6 +342,7 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
                 if (!invert_tet_matrix(t.v, t.inv)) return fail(PFC_E_MESH, "pfc_finalize: degenerate tetrahedron");
                 for (int j = 0; j < 4; ++j) t.eps_r[j] = e4[0] * t.inv[j] + e4[1] * t.inv[4 + j] + e4[2] * t.inv[8 + j] + e4[3] * t.inv[12 + j];
                 tets.push_back(t);
+                tet_eps.insert(tet_eps.end(), e4, e4 + 4);
             }
         } else {
             m.prim_base = int(tris.size());
@@ -425,14 +436,44 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
     c->scene.n_ins = int(c->h_ins.size()); c->scene.n_small = int(small.size()); c->scene.n_bristle = c->n_bristle;
     c->scene.n_small_bristle = 0;
     for (int32_t k : small) c->scene.n_small_bristle += (c->h_ins[k].model == PFC_MODEL_BRISTLE);
+    {   // bristle instructions: tables of the reference-order pipeline
+        std::vector<int32_t> bris, large_index(c->h_ins.size(), -1);
+        for (size_t k = 0; k < c->h_ins.size(); ++k) if (c->h_ins[k].model == PFC_MODEL_BRISTLE) bris.push_back(int32_t(k));
+        for (size_t k = 0; k < large.size(); ++k) large_index[large[k]] = int32_t(k);
+        CU(c->d_large_index.ensure(large_index.size()));
+        CU(cudaMemcpy(c->d_large_index.p, large_index.data(), sizeof(int32_t) * large_index.size(), cudaMemcpyHostToDevice));
+        c->large_index_dirty = false;
+        c->has_large_bristle = false;
+        for (int32_t k : large) c->has_large_bristle |= (c->h_ins[k].model == PFC_MODEL_BRISTLE);
+        if (!bris.empty()) {
+            CU(c->d_bris_ins.ensure(bris.size()));
+            CU(cudaMemcpy(c->d_bris_ins.p, bris.data(), sizeof(int32_t) * bris.size(), cudaMemcpyHostToDevice));
+            CU(c->d_tet_eps.ensure(std::max<size_t>(tet_eps.size(), 4)));
+            if (!tet_eps.empty()) CU(cudaMemcpy(c->d_tet_eps.p, tet_eps.data(), sizeof(double) * tet_eps.size(), cudaMemcpyHostToDevice));
+            if (!c->exact_buf) c->exact_buf = exact_buffers_create();
+        }
+        c->exact_scene.tet_eps = c->d_tet_eps.p; c->exact_scene.bris_ins = c->d_bris_ins.p; c->exact_scene.large_index = c->d_large_index.p;
+        c->exact_scene.n_bris = int32_t(bris.size()); c->exact_scene.skip_large = 0;
+    }
     c->max_env = max_env;
     c->finalized = true;
     return PFC_OK;
 }
 
-static bool scene_has_large_bristle(const pfc_ctx* c) {
-    for (int k : c->large_ins_host) if (c->h_ins[k].model == PFC_MODEL_BRISTLE) return true;
-    return false;
+// The bristle instructions of an evaluation, in the reference's operation order (pfc_exact.cu), from the pair lists the Float64 broad
+// phase left.  dual: Jacobian mode (every scalar of X / twist / s / wrench / sdot is 7 doubles).  skip_large: a sharded context keeps its
+// large bristle instructions on the partial-sum protocol.  Synchronises the stream once (see exact_bristle_eval).
+static int eval_bristle_exact(pfc_ctx* c, long long n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
+                              const long long* n_pairs, int* flags, int dual, bool skip_large, int* nl) {
+    if (c->exact_scene.n_bris == 0) return PFC_OK;
+    ExactIO xio{n_env, X, twist, s, wrench, sdot, n_pairs, flags};
+    ExactPairs ps{};
+    ps.small_pairs = c->d_small_pairs.p; ps.small_cap = small_cap(c->small_max_pairs);
+    if (c->large_scene.n_large > 0 && c->has_large_bristle && !skip_large) large_exact_view(c->large_buf, c->large_scene, n_env, ps);
+    ExactScene es = c->exact_scene;
+    es.skip_large = skip_large ? 1 : 0;
+    CU(exact_bristle_eval(c->scene, es, xio, ps, dual, c->exact_buf, c->stream, nl));
+    return PFC_OK;
 }
 
 static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
@@ -454,8 +495,11 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
     if (c->large_scene.n_large > 0) {
         if (c->shard_world > 1) return fail(PFC_E_ARG, "this context is sharded: use pfc_eval_sharded_begin / _step");
         CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
-        const int n_stage = scene_has_large_bristle(c) ? 3 : 1;
-        for (int st = 0; st < n_stage; ++st) CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, st, 0, 0, c->stream, &nl));
+        CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, 0, 0, c->stream, &nl));
+    }
+    {   // bristle instructions (small and large): reference-order pipeline
+        int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
+        if (rc != PFC_OK) return rc;
     }
     c->launches += nl;
     c->last_X = io.X; c->last_tw = io.twist;
@@ -567,9 +611,15 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
         CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins + kSmallPairsSlack));
         CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
     }
-    // every rank runs the breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair lists
+    // every rank runs the breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair lists.
+    // Bristle instructions are the exception: their sums run sequentially over the whole TractionCache list (pfc_exact.cuh), so every
+    // rank lists and evaluates them completely -- identical bits on every rank, nothing to exchange.
     CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl, c->shard_rank, c->shard_world));
-    CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, 0, c->shard_world > 1, 0, c->stream, &nl));
+    CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, c->shard_world > 1, 0, c->stream, &nl));
+    {
+        int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
+        if (rc != PFC_OK) return rc;
+    }
     c->launches += nl;
     c->sharded_io = io;
     c->sharded_stage = 0;
@@ -589,17 +639,10 @@ int pfc_eval_sharded_step(pfc_ctx* c, int* more) {
     if (!c || c->sharded_stage < 0 || !more) return fail(PFC_E_ARG, "pfc_eval_sharded_step: no sharded evaluation in flight");
     CU(cudaSetDevice(c->device));
     int nl = 0;
-    const int n_stage = scene_has_large_bristle(c) ? 3 : 1;
     if (c->shard_world > 1)  // the caller has summed the partial buffer over the ranks: apply it
-        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, 1, 1, c->stream, &nl));
-    if (c->sharded_stage + 1 < n_stage) {
-        ++c->sharded_stage;
-        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, c->sharded_stage, c->shard_world > 1, 0, c->stream, &nl));
-        *more = 1;
-    } else {
-        c->sharded_stage = -1;
-        *more = 0;
-    }
+        CU(large_narrow_stage(c->scene, c->large_scene, c->sharded_io, c->large_buf, 1, 1, c->stream, &nl));
+    c->sharded_stage = -1;   // one exchange per evaluation (regularized sums; bristle instructions are not split)
+    *more = 0;
     c->launches += nl;
     return PFC_OK;
 }
@@ -638,16 +681,13 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     CU(copy_in(c, c->d_X7.p, X7, sizeof(double) * 112 * ne * ni));
     CU(copy_in(c, c->d_tw7.p, twist7, sizeof(double) * 42 * ne * ni));
     if (nb) CU(copy_in(c, c->d_s7.p, s7, sizeof(double) * 42 * ne * nb));
-    if (c->d_large_index.n < ni || c->large_index_dirty) {   // instruction -> index in the large list: static, uploaded once
-        std::vector<int32_t> large_index(ni, -1);
-        for (size_t k = 0; k < c->large_ins_host.size(); ++k) large_index[c->large_ins_host[k]] = int32_t(k);
-        CU(c->d_large_index.ensure(ni));
-        CU(cudaMemcpy(c->d_large_index.p, large_index.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice));
-        c->large_index_dirty = false;
-    }
     CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p,
                          c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
                          c->large_scene.n_large, c->stream));
+    {   // bristle instructions on Duals, in the reference's operation order
+        int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p, 1, false, &nl);
+        if (rc != PFC_OK) return rc;
+    }
     c->launches += nl + 1;
     CU(copy_out(c, wrench7, c->d_w7.p, sizeof(double) * 42 * ne * ni));
     if (nb) CU(copy_out(c, sdot7, c->d_sd7.p, sizeof(double) * 42 * ne * nb));
@@ -958,17 +998,13 @@ static int calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const
     }
     // Dual boundary arrays, Dual contact wrenches, Dual rigid-body terms
     CU(launch_state_prologue_dual6(c->state, n_env, int(ni), int(nb), x, seed_start, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl));
-    if (c->d_large_index.n < ni || c->large_index_dirty) {
-        std::vector<int32_t> large_index(ni, -1);
-        for (size_t k = 0; k < c->large_ins_host.size(); ++k) large_index[c->large_ins_host[k]] = int32_t(k);
-        CU(c->d_large_index.ensure(ni));
-        CU(cudaMemcpyAsync(c->d_large_index.p, large_index.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));   // large_index is a stack vector
-        c->large_index_dirty = false;
-    }
     CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags,
                          c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
                          c->large_scene.n_large, c->stream));
+    {
+        int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags, 1, false, &nl);
+        if (rc != PFC_OK) return rc;
+    }
     CU(launch_state_dynamics_dual6(c->state, c->dyn, n_env, int(ni), int(nb), x, seed_start, c->d_w7.p, tau_ext, nb ? c->d_sd7.p : nullptr, xdot7,
                                    c->stream, &nl, flags, status));
     c->launches += nl + 1;

@@ -1,6 +1,4 @@
-// pfc_dual.cuh -- declarations shared by the two translation units of the Jacobian mode (pfc_dual.cu: Dual<6> kernel for scenes with
-// bristle friction + the launcher; pfc_dual_chunked.cu: the Dual<2> x 3 kernel for regularized-only scenes).  ptxas needs minutes for
-// each of the two kernels; separate files let them compile in parallel.
+// pfc_dual.cuh -- declarations of the Jacobian mode of the regularized-friction instructions (pfc_dual_chunked.cu).
 #pragma once
 #include "pfc_large.h"
 #include "pfc_patch.cuh"
@@ -38,8 +36,5 @@ PFC_D bool survives_f64(const SceneDev& sc, const InsDev& ins, int a, int b, con
     const bool keep = clip_pair(sc, ins, a, b, cxv, tmp, fl);
     return keep || fl != 0;   // error paths (non-finite vertex) are left to the Dual pass, which records the flag
 }
-
-// implemented in pfc_dual_chunked.cu
-cudaError_t launch_eval_dual6_chunked(const SceneDev& sc, const DualIO& io, const PairSource& ps, long long n_prob, int n_sm, cudaStream_t stream);
 
 }  // namespace pfc

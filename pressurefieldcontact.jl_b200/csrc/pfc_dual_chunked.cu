@@ -1,5 +1,11 @@
-// pfc_dual_chunked.cu -- Jacobian mode for regularized-only scenes: the 6 partials travel in three chunks of 2 (see pfc_dual.cu for the
-// mode itself and pfc_dual.cuh for the shared declarations).
+// pfc_dual_chunked.cu -- Jacobian mode of the regularized-friction instructions: the 6 partials travel in three chunks of 2.
+//
+// Radau obtains the Jacobian of the ODE right-hand side by forward-mode AD in chunks of 6
+// (/root/reference/src/radau/radau_functions.jl:2-26, N_chunk = 6 at src/mechanism_scenario.jl:181):
+// forceAllElasticIntersections! then runs on ForwardDiff.Dual{Nothing,Float64,6}, i.e. every scalar that depends on the state carries
+// its value and 6 partials, while the candidate-pair lists come from the Float64 state (calcTriTetIntersections! always uses m.float,
+// non_friction.jl:94-101).  The device code is the templated source of the Float64 path (pfc_clip.cuh, pfc_patch.cuh) on Dual<2>.
+// Bristle instructions are skipped here: pfc_exact.cu evaluates them on Dual<6> in the reference's operation order.
 #include <algorithm>
 
 #include "pfc_dual.cuh"
@@ -34,6 +40,7 @@ __global__ void __launch_bounds__(128) eval_dual6_chunked_kernel(SceneDev sc, Du
         const long long env = ei / sc.n_ins;
         const int k = int(ei - env * sc.n_ins);
         const InsDev& ins = sc.ins[k];
+        if (ins.model != PFC_MODEL_REGULARIZED) continue;   // bristle: pfc_exact.cu
         const int n = (int)io.n_pairs[ei];
         int flags = 0;
         bool contact = false;
@@ -78,7 +85,10 @@ __global__ void __launch_bounds__(128) eval_dual6_chunked_kernel(SceneDev sc, Du
             }
             const unsigned* pl_s = ins.small ? ps.small_pairs + (size_t)ps.small_cap * ei : nullptr;
             const int3* pl_l = ins.small ? nullptr : ps.large_sorted + ps.seg_start[env * ps.n_large + ps.large_index[k]];
-            if (!seeded) {   // Float64 evaluation (see eval_dual6_kernel)
+            // An instruction none of whose inputs depends on the seeded state entries (every partial of x_r2_r1 and the twist is zero -- e.g. the
+            // seeds sit on another body) has zero wrench partials: its Dual evaluation is the Float64 evaluation, 7x cheaper.  The reference
+            // evaluates such instructions on Duals all the same; the values agree to rounding.
+            if (!seeded) {
                 Accum<double, 6> av;
                 av.fp = ins.p; av.w_ang = cxv.w_ang; av.w_lin = cxv.w_lin; av.dump = nullptr; av.dump_cap = 0;
                 av.reset(ACC_REGULARIZED);
@@ -155,7 +165,18 @@ __global__ void __launch_bounds__(128) eval_dual6_chunked_kernel(SceneDev sc, Du
 
 }  // namespace
 
-cudaError_t launch_eval_dual6_chunked(const SceneDev& sc, const DualIO& io, const PairSource& ps, long long n_prob, int n_sm, cudaStream_t stream) {
+const unsigned* large_seg_start_ptr(const LargeBuffers* b);
+const int3* large_sorted_ptr(const LargeBuffers* b);
+
+cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double* X7, const double* twist7, const double* s7, double* wrench7, double* sdot7,
+                              const long long* n_pairs, int* flags, const unsigned* small_pairs, int small_cap, const LargeBuffers* lb,
+                              const int32_t* large_index, int n_large, cudaStream_t stream) {
+    DualIO io{n_env, X7, twist7, s7, wrench7, sdot7, n_pairs, flags};
+    PairSource ps{small_pairs, small_cap, lb ? large_sorted_ptr(lb) : nullptr, lb ? large_seg_start_ptr(lb) : nullptr, large_index, n_large};
+    const long long n_prob = n_env * sc.n_ins;
+    if (n_prob == 0) return cudaSuccess;
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const unsigned blocks = (unsigned)std::min<long long>((n_prob + 3) / 4, (long long)n_sm * 4);
     eval_dual6_chunked_kernel<<<blocks, 128, sizeof(Chunk3Smem) * 4, stream>>>(sc, io, ps);
     return cudaGetLastError();

@@ -18,10 +18,10 @@
 //                          (children are visited (1.1,2.1),(1.2,2.1),(1.1,2.2),(1.2,2.2)).  A stable
 //                          LSD radix sort on (problem, key) restores exactly the reference's order, so
 //                          the pair lists are bit-exact and every later sum has a fixed order.
-//   K2  narrow_large_kernel one thread per sorted pair (clip + quadrature + friction), fixed-order
-//                          block reduction per 256-pair chunk of a problem's segment
-//   K3  finish_large_kernel one warp per problem sums its chunk partials in order; bristle steps
-//                          (centre of pressure -> stiffness -> friction) run K2/K3 once per pass
+//   K2  narrow_large_kernel one thread per sorted pair of a regularized instruction (clip + quadrature +
+//                          friction), fixed-order block reduction per 256-pair chunk of a problem's segment
+//   K3  finish_large_kernel one warp per problem sums its chunk partials in order
+//   Bristle instructions keep their sorted lists; pfc_exact.cu evaluates them in the reference's operation order.
 //
 // Reference: calcTriTetIntersections! + integrate_over! + yes_contact!/no_contact!
 // (/root/reference/src/contact_algorithms_non_friction.jl:70-143, src/contact_algorithms_friction.jl:50-143).
@@ -30,7 +30,7 @@
 #include <cstdio>
 #include <vector>
 
-#include "pfc_bristle.cuh"
+#include "pfc_exact.h"
 #include "pfc_large.h"
 #include "pfc_patch.cuh"
 #include "pfc_sat.cuh"
@@ -48,7 +48,7 @@ namespace {
 constexpr int kStackCap = 1024;   // node pairs per warp stack (8 KB)
 constexpr int kDfsWarps = 4;
 constexpr int kChunk = 256;       // pairs per reduction chunk (= narrow kernel block size)
-constexpr int kNA = 21;           // accumulator slots per chunk partial
+constexpr int kNA = 6;            // accumulator slots per chunk partial (regularized wrench)
 static_assert(kLargePartStride == kNA + 2, "partial record = kNA sums + point count + pair count");
 
 struct Counters {                 // device-resident
@@ -139,6 +139,11 @@ __global__ void init_frontier_kernel(LargeScene ls, long long n_env, Seed* front
 // Multi-GPU split of one large scene: every rank runs the (cheap) breadth-first levels, then owns the seeds -- and the leaf pairs the
 // breadth-first levels emit directly -- whose hash falls on it.  A sub-tree is traversed by exactly one rank, so the pair lists of the
 // ranks are disjoint and their union is the full list; nothing is exchanged before the per-instruction partial sums.
+// Bristle instructions are not split: their sums must run sequentially over the WHOLE TractionCache list (pfc_exact.cuh), so every rank
+// lists and evaluates them completely (identical bits on every rank, nothing exchanged).
+PFC_D bool prob_is_split(const SceneDev& sc, const LargeScene& ls, int prob) {
+    return sc.ins[ls.large_ins[prob % ls.n_large]].model != PFC_MODEL_BRISTLE;
+}
 PFC_D unsigned item_hash(int prob, int a, int b) {
     unsigned h = (unsigned)prob * 0x9E3779B1u ^ (unsigned)a * 0x85EBCA77u ^ (unsigned)b * 0xC2B2AE3Du;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene 
         at = __shfl_sync(0xffffffffu, at, 31) + incl - n_child;
         if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, 0u, ch[c].x, ch[c].y}; }
         else if (n_child > 0) atomicOr(&cnt->overflow, 1u);
-        const bool emit = r < 0 && (hworld == 1u || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
+        const bool emit = r < 0 && (hworld == 1u || !prob_is_split(sc, ls, s.prob) || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
         const unsigned leaf_mask = __ballot_sync(0xffffffffu, emit);
         if (leaf_mask) {
             unsigned pat = 0;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, 
             const unsigned ticket = atomicAdd(&cnt->q_head, 1u);
             if (ticket < n_seed0) {
                 seed = seeds[ticket];
-                if (hworld > 1u && item_hash(seed.prob, seed.a, seed.b) % hworld != hrank) {   // another rank's sub-tree
+                if (hworld > 1u && prob_is_split(sc, ls, seed.prob) && item_hash(seed.prob, seed.a, seed.b) % hworld != hrank) {   // another rank's sub-tree
                     atomicSub(&cnt->outstanding, 1);
                     seed.prob = -2;
                 }
@@ -503,23 +508,17 @@ __global__ void __launch_bounds__(1024) units_scan_kernel(const unsigned* __rest
     (void)shard_rank; (void)shard_world;
 }
 
-// per-problem state carried between the bristle passes
-struct ProbState { double cop[3]; double delta[6]; double Sinv[6]; double Kh[36]; double c10[10]; int contact; int pad; };
-
-// K2: one thread per sorted pair; fixed-order block reduction per chunk
+// K2: one thread per sorted pair of a REGULARIZED instruction; fixed-order block reduction per chunk.  (Bristle instructions keep their
+// sorted pair lists and are evaluated by the reference-order pipeline, pfc_exact.cu.)
 __global__ void __launch_bounds__(kChunk) narrow_large_kernel(SceneDev sc, LargeScene ls, EvalIO io, const int3* __restrict__ sorted, const unsigned* __restrict__ seg_start,
                                                               const unsigned* __restrict__ seg_end, const unsigned* __restrict__ unit_start, unsigned n_prob,
-                                                              const Counters* cnt, int mode_reg, int mode_bristle, const ProbState* __restrict__ ps, double* chunk_out,
-                                                              int* chunk_points, int* prob_flags, unsigned shard_rank, unsigned shard_world) {
+                                                              const Counters* cnt, double* chunk_out, int* chunk_points, int* prob_flags) {
     __shared__ double red[kChunk / 32][kNA];
     __shared__ int red_pts[kChunk / 32];
     __shared__ int s_prob;
     const unsigned n_units = cnt->n_units;
-    // this rank's contiguous slice of the unit list (multi-GPU split of one large scene)
-    const unsigned u_beg = (unsigned)((unsigned long long)n_units * shard_rank / shard_world);
-    const unsigned u_end = (unsigned)((unsigned long long)n_units * (shard_rank + 1) / shard_world);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (unsigned u = u_beg + blockIdx.x; u < u_end; u += gridDim.x) {
+    for (unsigned u = blockIdx.x; u < n_units; u += gridDim.x) {
         if (threadIdx.x == 0) {  // unit -> problem by binary search in unit_start
             unsigned lo = 0, hi = n_prob;
             while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (unit_start[mid] <= u) lo = mid; else hi = mid; }
@@ -530,13 +529,13 @@ __global__ void __launch_bounds__(kChunk) narrow_large_kernel(SceneDev sc, Large
         long long env; int k;
         prob_to_ei(sc, ls, p, env, k);
         const InsDev& ins = sc.ins[k];
+        if (ins.model != PFC_MODEL_REGULARIZED) { __syncthreads(); continue; }   // (block-uniform)
         const long long ei = env * sc.n_ins + k;
-        const int mode = ins.model == PFC_MODEL_REGULARIZED ? mode_reg : mode_bristle;
         Accum<double, kNA> acc;
-        acc.reset(mode < 0 ? ACC_REGULARIZED : mode);
+        acc.reset(ACC_REGULARIZED);
         int flags = 0;
         const unsigned i = seg_start[p] + (u - unit_start[p]) * kChunk + threadIdx.x;
-        if (mode >= 0 && i < seg_end[p]) {
+        if (i < seg_end[p]) {
             PatchCtx<double> cx;
             load_xform_l(io.X + 16 * ei, cx.x21);
             cx.x12 = inverse(cx.x21);
@@ -545,23 +544,18 @@ __global__ void __launch_bounds__(kChunk) narrow_large_kernel(SceneDev sc, Large
             cx.w_lin = mk<double>(tw[3], tw[4], tw[5]);
             cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
             acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
-            if (mode == ACC_STIFFNESS || mode == ACC_BRISTLE) {
-                acc.cop = mk<double>(ps[p].cop[0], ps[p].cop[1], ps[p].cop[2]);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) acc.delta[j] = ps[p].delta[j];
-            }
             const int3 pr = sorted[i];
             integrate_pair(sc, ins, pr.y, pr.z, cx, acc, flags);
         }
         // fixed-order reduction: butterfly inside each warp, then warps 0..7 in order
-        const int n_acc = (mode == ACC_STIFFNESS) ? 21 : (mode == ACC_COP ? 10 : 6);
-        for (int j = 0; j < n_acc; ++j) { const double v = warp_sum(acc.a[j]); if (lane == 0) red[w][j] = v; }
+#pragma unroll
+        for (int j = 0; j < kNA; ++j) { const double v = warp_sum(acc.a[j]); if (lane == 0) red[w][j] = v; }
         int pts = acc.n_points;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { pts += __shfl_xor_sync(0xffffffffu, pts, o); flags |= __shfl_xor_sync(0xffffffffu, flags, o); }
         if (lane == 0) { red_pts[w] = pts; if (flags) atomicOr(&prob_flags[p], flags); }
         __syncthreads();
-        if (threadIdx.x < n_acc) {
+        if (threadIdx.x < kNA) {
             double s = red[0][threadIdx.x];
 #pragma unroll
             for (int ww = 1; ww < kChunk / 32; ++ww) s += red[ww][threadIdx.x];
@@ -572,110 +566,57 @@ __global__ void __launch_bounds__(kChunk) narrow_large_kernel(SceneDev sc, Large
     }
 }
 
-// K3: one warp per problem: ordered sum of its chunk partials, then the model-specific step.
-//   stage 0: regularized -> wrench;  bristle pass 1 (COP) -> cop, normal wrench
-//   stage 1: bristle pass 2 (STIFFNESS) -> K -> Sinv, Kh, delta
-//   stage 2: bristle pass 3 (BRISTLE) -> friction wrench, s-dot, total wrench
-// In sharded (multi-GPU) mode the chunk sums of the other ranks are missing: `partial_only` makes the
-// kernel write the raw per-problem partial sums to part_out for the caller's allreduce instead.
+// K3: one warp per problem: ordered sum of its chunk partials -> wrench, pair count, flags.
+// In sharded (multi-GPU) mode the chunk sums of the other ranks are missing: `part_out` makes the kernel write the raw per-problem
+// partial sums (6 sums, point count, pair count) for the caller's reduction over the ranks instead; `apply_parts` finishes from the
+// reduced buffer.  Bristle instructions only get their pair count published here (exact_bristle: pfc_exact.cu evaluates them).
 __global__ void __launch_bounds__(128) finish_large_kernel(SceneDev sc, LargeScene ls, EvalIO io, const unsigned* __restrict__ seg_start, const unsigned* __restrict__ seg_end,
-                                                           const unsigned* __restrict__ unit_start, unsigned n_prob, const Counters* cnt, int stage, ProbState* ps,
-                                                           const double* __restrict__ chunk_out, const int* __restrict__ chunk_points, const int* __restrict__ prob_flags,
-                                                           unsigned shard_rank, unsigned shard_world, double* part_out, int apply_parts) {
-    __shared__ double scratch[4][192];
+                                                           const unsigned* __restrict__ unit_start, unsigned n_prob, const double* __restrict__ chunk_out,
+                                                           const int* __restrict__ chunk_points, const int* __restrict__ prob_flags, double* part_out, int apply_parts) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned n_units = cnt->n_units;
-    const unsigned u_beg = (unsigned)((unsigned long long)n_units * shard_rank / shard_world);
-    const unsigned u_end = (unsigned)((unsigned long long)n_units * (shard_rank + 1) / shard_world);
     for (unsigned p = blockIdx.x * 4 + wib; p < n_prob; p += gridDim.x * 4) {
         long long env; int k;
         prob_to_ei(sc, ls, (int)p, env, k);
         const InsDev& ins = sc.ins[k];
         const long long ei = env * sc.n_ins + k;
-        const bool bristle = ins.model == PFC_MODEL_BRISTLE;
-        if (!bristle && stage > 0) continue;
+        if (ins.model == PFC_MODEL_BRISTLE) {   // never split over ranks: the list is complete here
+            if (lane == 0 && !apply_parts) { io.n_pairs[ei] = (long long)seg_end[p] - (long long)seg_start[p]; io.flags[ei] = prob_flags[p]; }
+            if (lane == 0 && part_out && !apply_parts) for (int j = 0; j < kLargePartStride; ++j) part_out[(size_t)p * kLargePartStride + j] = 0.0;
+            continue;
+        }
         double sum[kNA];
         int pts = 0;
-        const int n_acc = bristle ? (stage == 1 ? 21 : (stage == 0 ? 10 : 6)) : 6;
-        if (apply_parts) {  // sums were reduced across ranks by the caller: part_out[p][kNA + 1]
-            for (int j = 0; j < n_acc; ++j) sum[j] = part_out[(size_t)p * kLargePartStride + j];
+        if (apply_parts) {  // sums were reduced across ranks by the caller
+            for (int j = 0; j < kNA; ++j) sum[j] = part_out[(size_t)p * kLargePartStride + j];
             pts = (int)part_out[(size_t)p * kLargePartStride + kNA];
         } else {
             // lane l sums chunks l, l+32, ... of this problem in order; then a fixed butterfly
-            unsigned c0 = unit_start[p], c1 = unit_start[p + 1];
-            if (c0 < u_beg) c0 = u_beg;
-            if (c1 > u_end) c1 = u_end;
-            for (int j = 0; j < n_acc; ++j) sum[j] = 0.0;
+            const unsigned c0 = unit_start[p], c1 = unit_start[p + 1];
+            for (int j = 0; j < kNA; ++j) sum[j] = 0.0;
             for (unsigned c = c0 + lane; c < c1; c += 32) {
-                for (int j = 0; j < n_acc; ++j) sum[j] += chunk_out[(size_t)c * kNA + j];
+                for (int j = 0; j < kNA; ++j) sum[j] += chunk_out[(size_t)c * kNA + j];
                 pts += chunk_points[c];
             }
-            for (int j = 0; j < n_acc; ++j) sum[j] = warp_sum(sum[j]);
+            for (int j = 0; j < kNA; ++j) sum[j] = warp_sum(sum[j]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(0xffffffffu, pts, o);
             if (part_out) {  // sharded: hand the partial sums to the caller and stop here
-                if (lane == 0) { for (int j = 0; j < kNA; ++j) part_out[(size_t)p * kLargePartStride + j] = j < n_acc ? sum[j] : 0.0; part_out[(size_t)p * kLargePartStride + kNA] = (double)pts;
-                                 part_out[(size_t)p * kLargePartStride + kNA + 1] = (double)(seg_end[p] - seg_start[p]); }
+                if (lane == 0) {
+                    for (int j = 0; j < kNA; ++j) part_out[(size_t)p * kLargePartStride + j] = sum[j];
+                    part_out[(size_t)p * kLargePartStride + kNA] = (double)pts;
+                    part_out[(size_t)p * kLargePartStride + kNA + 1] = (double)(seg_end[p] - seg_start[p]);
+                }
                 continue;
             }
         }
         // sharded: the ranks hold disjoint parts of the pair list; the count travels with the partial sums
         const long long n_pairs = apply_parts ? (long long)part_out[(size_t)p * kLargePartStride + kNA + 1] : (long long)seg_end[p] - (long long)seg_start[p];
-        double* wo = io.wrench + 6 * ei;
-        if (!bristle) {
-            if (lane == 0) {
-                const bool contact = pts > 0;
-                for (int j = 0; j < 6; ++j) wo[j] = contact ? sum[j] : 0.0;
-                io.n_pairs[ei] = n_pairs;
-                io.flags[ei] = prob_flags[p] | (contact ? kFlagContact : 0);
-            }
-            continue;
-        }
-        const double* sv = io.s + 6 * ((long long)sc.n_bristle * env + ins.bristle_id);
-        double* sd = io.sdot + 6 * ((long long)sc.n_bristle * env + ins.bristle_id);
-        ProbState& st = ps[p];
-        if (stage == 0) {
-            if (lane == 0) {
-                const bool contact = pts > 0;
-                st.contact = contact;
-                io.n_pairs[ei] = n_pairs;
-                io.flags[ei] = prob_flags[p] | (contact ? kFlagContact : 0);
-                if (contact) {
-                    for (int j = 0; j < 10; ++j) st.c10[j] = sum[j];
-                    for (int j = 0; j < 3; ++j) st.cop[j] = sum[7 + j] / sum[6];
-                } else {  // no_contact!(::Bristle)
-                    const double ti = -(1.0 / ins.p[0]);
-                    for (int j = 0; j < 6; ++j) { wo[j] = 0.0; sd[j] = ti * sv[j]; }
-                }
-            }
-        } else if (stage == 1) {
-            if (lane == 0 && st.contact) {
-                double* scr = scratch[wib];
-                double* K21 = scr + 108;
-                for (int j = 0; j < 21; ++j) K21[j] = sum[j] * ins.p[1];
-                decompose_K(K21, ins.p[6], st.Sinv, st.Kh, scr);
-                for (int i = 0; i < 6; ++i) {
-                    double t = 0.0;
-                    for (int j = 0; j < 6; ++j) t += st.Kh[6 * i + j] * sv[j];
-                    st.delta[i] = st.Sinv[i] * t;
-                }
-            }
-        } else {
-            if (lane == 0 && st.contact) {
-                const double* c = st.c10;
-                const Vec3<double> cop = mk<double>(st.cop[0], st.cop[1], st.cop[2]);
-                const Vec3<double> shift = cross(cop, mk<double>(sum[3], sum[4], sum[5]));
-                wo[0] = c[0] + (sum[0] + shift.x); wo[1] = c[1] + (sum[1] + shift.y); wo[2] = c[2] + (sum[2] + shift.z);
-                wo[3] = c[3] + sum[3]; wo[4] = c[4] + sum[4]; wo[5] = c[5] + sum[5];
-                const double ti = -(1.0 / ins.p[0]);
-                double sw[6];
-                for (int i = 0; i < 6; ++i) sw[i] = st.Sinv[i] * sum[i];
-                for (int i = 0; i < 6; ++i) {
-                    double t = 0.0;
-                    for (int j = 0; j < 6; ++j) t += st.Kh[6 * i + j] * sw[j];
-                    sd[i] = ti * (t + sv[i]);
-                }
-            }
+        if (lane == 0) {
+            const bool contact = pts > 0;
+            double* wo = io.wrench + 6 * ei;
+            for (int j = 0; j < 6; ++j) wo[j] = contact ? sum[j] : 0.0;
+            io.n_pairs[ei] = n_pairs;
+            io.flags[ei] = prob_flags[p] | (contact ? kFlagContact : 0);
         }
     }
 }
@@ -706,7 +647,6 @@ struct LargeBuffers {
     unsigned long long* keys[2] = {nullptr, nullptr}; unsigned* vals[2] = {nullptr, nullptr}; size_t cap_keys = 0, cap_keys2 = 0, cap_vals = 0, cap_vals2 = 0, cap_sorted = 0;
     unsigned* hist = nullptr; size_t cap_hist = 0;
     unsigned* seg_start = nullptr; unsigned* seg_end = nullptr; unsigned* unit_start = nullptr; size_t cap_seg = 0, cap_seg2 = 0, cap_unit = 0;
-    ProbState* ps = nullptr; size_t cap_ps = 0;
     int* prob_flags = nullptr; size_t cap_pf = 0;
     double* chunk_out = nullptr; size_t cap_chunk = 0;
     int* chunk_points = nullptr; size_t cap_cp = 0;
@@ -722,7 +662,7 @@ void large_buffers_destroy(LargeBuffers* b) {
     if (!b) return;
     cudaFree(b->cnt); cudaFree(b->frontier[0]); cudaFree(b->frontier[1]); cudaFree(b->pairs); cudaFree(b->sorted);
     cudaFree(b->keys[0]); cudaFree(b->keys[1]); cudaFree(b->vals[0]); cudaFree(b->vals[1]); cudaFree(b->hist);
-    cudaFree(b->seg_start); cudaFree(b->seg_end); cudaFree(b->unit_start); cudaFree(b->ps); cudaFree(b->prob_flags);
+    cudaFree(b->seg_start); cudaFree(b->seg_end); cudaFree(b->unit_start); cudaFree(b->prob_flags);
     cudaFree(b->chunk_out); cudaFree(b->chunk_points); cudaFree(b->part);
     delete b;
 }
@@ -748,6 +688,13 @@ cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, 
     return cudaSuccess;
 }
 const int3* large_sorted_ptr(const LargeBuffers* b) { return b->sorted; }
+// what the reference-order bristle pipeline needs of the last broad phase
+void large_exact_view(const LargeBuffers* b, const LargeScene& ls, long long n_env, ExactPairs& ps) {
+    ps.sorted = b->sorted; ps.seg_start = b->seg_start; ps.seg_end = b->seg_end; ps.unit_start = b->unit_start;
+    ps.n_units = b->cnt ? &b->cnt->n_units : nullptr;
+    ps.large_ins = ls.large_ins; ps.n_large = ls.n_large;
+    ps.max_large_units = (size_t)(b->last_n_pairs / kChunk) + (size_t)(n_env * ls.n_large) + 1;
+}
 const unsigned* large_seg_start_ptr(const LargeBuffers* b) { return b->seg_start; }
 
 namespace {
@@ -843,7 +790,6 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     LCU(ensure(b->seg_end, b->cap_seg2, (size_t)n_prob + 1));
     LCU(ensure(b->unit_start, b->cap_unit, (size_t)n_prob + 2));
     LCU(ensure(b->prob_flags, b->cap_pf, (size_t)n_prob));
-    LCU(ensure(b->ps, b->cap_ps, (size_t)n_prob));
     init_segments_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(b->seg_start, b->seg_end, n_prob);
     zero_int_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(b->prob_flags, n_prob);
     if (n_launches) *n_launches += 2;
@@ -889,13 +835,11 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     return cudaGetLastError();
 }
 
-// Narrow phase + friction + reduction for the pair lists produced by large_broad_phase.
-// shard_world > 1: this context sums only its slice of the chunks and leaves per-problem partial sums
-// (kLargePartStride doubles each) in large_part_buffer() after each stage; the caller allreduces them and calls
-// large_narrow_stage again with apply_parts = 1.
-cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int partial_only,
-                               int apply_parts, cudaStream_t stream, int* n_launches) {
-    const int shard_rank = 0, shard_world = 1;   // the pair list of a sharded context is already its own part (hash-partitioned traversal)
+// Narrow phase + friction + reduction of the regularized instructions over the pair lists produced by large_broad_phase.
+// partial_only (sharded contexts): leave the per-problem partial sums (kLargePartStride doubles each) in large_part_buffer(); the caller
+// reduces them over the ranks and calls again with apply_parts = 1.
+cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int partial_only, int apply_parts,
+                               cudaStream_t stream, int* n_launches) {
     const unsigned n_prob = (unsigned)(io.n_env * ls.n_large);
     if (n_prob == 0) return cudaSuccess;
     const unsigned n = b->last_n_pairs;
@@ -905,17 +849,14 @@ cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const E
     LCU(ensure(b->chunk_out, b->cap_chunk, max_units * kNA));
     LCU(ensure(b->chunk_points, b->cap_cp, max_units));
     if (partial_only) LCU(ensure(b->part, b->cap_part, (size_t)n_prob * kLargePartStride));
-    const int mode_reg = stage == 0 ? ACC_REGULARIZED : -1;
-    const int mode_bri = stage == 0 ? ACC_COP : (stage == 1 ? ACC_STIFFNESS : ACC_BRISTLE);
     if (!apply_parts) {
         const unsigned grid = (unsigned)std::min<size_t>(max_units, (size_t)n_sm * 16);
-        narrow_large_kernel<<<grid, kChunk, 0, stream>>>(sc, ls, io, b->sorted, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, mode_reg, mode_bri, b->ps,
-                                                        b->chunk_out, b->chunk_points, b->prob_flags, (unsigned)shard_rank, (unsigned)shard_world);
+        narrow_large_kernel<<<grid, kChunk, 0, stream>>>(sc, ls, io, b->sorted, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, b->chunk_out, b->chunk_points,
+                                                        b->prob_flags);
         if (n_launches) *n_launches += 1;
     }
     finish_large_kernel<<<std::min<unsigned>((n_prob + 3) / 4, (unsigned)n_sm * 8), 128, 0, stream>>>(
-        sc, ls, io, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, stage, b->ps, b->chunk_out, b->chunk_points, b->prob_flags, (unsigned)shard_rank,
-        (unsigned)shard_world, partial_only ? b->part : nullptr, apply_parts);
+        sc, ls, io, b->seg_start, b->seg_end, b->unit_start, n_prob, b->chunk_out, b->chunk_points, b->prob_flags, partial_only ? b->part : nullptr, apply_parts);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -23,19 +23,21 @@ void large_buffers_destroy(LargeBuffers* b);
 // hash_rank / hash_world: multi-GPU split of one large scene -- this context traverses (and lists) only the sub-trees whose hash falls on it
 cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches,
                               int hash_rank = 0, int hash_world = 1);
-// stage 0: regularized wrench / bristle centre of pressure; 1: bristle stiffness; 2: bristle friction
-// partial_only: leave the per-problem partial sums (+ point and pair counts) in large_part_buffer() for the caller's allreduce;
-// apply_parts: the buffer holds the sums over all ranks -- finish the stage from it
-cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int stage, int partial_only,
-                               int apply_parts, cudaStream_t stream, int* n_launches);
+// regularized instructions over the lists of large_broad_phase (bristle instructions: pfc_exact.cu).
+// partial_only: leave the per-problem partial sums (+ point and pair counts) in large_part_buffer() for the caller's reduction over the ranks;
+// apply_parts: the buffer holds the sums over all ranks -- finish from it
+cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, int partial_only, int apply_parts,
+                               cudaStream_t stream, int* n_launches);
+struct ExactPairs;
+void large_exact_view(const LargeBuffers* b, const LargeScene& ls, long long n_env, ExactPairs& ps);
 cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream);
 unsigned large_last_pairs(const LargeBuffers* b);
 unsigned long long large_last_tests(const LargeBuffers* b);
-double* large_part_buffer(LargeBuffers* b);     // [n_problem][23]: 21 partial sums, point count, pair count of the last stage (sharded mode)
-constexpr int kLargePartStride = 23;
+double* large_part_buffer(LargeBuffers* b);     // [n_problem][8]: 6 partial sums, point count, pair count (sharded mode)
+constexpr int kLargePartStride = 8;
 cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, long long* n_out, cudaStream_t stream);
 
-// Jacobian mode (pfc_dual.cu): narrow phase + friction + reduction on Dual<6> over existing pair lists.
+// Jacobian mode of the regularized instructions (pfc_dual_chunked.cu): narrow phase + friction + reduction on Duals over existing pair lists.
 cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double* X7, const double* twist7, const double* s7, double* wrench7, double* sdot7,
                               const long long* n_pairs, int* flags, const unsigned* small_pairs, int small_cap, const LargeBuffers* lb,
                               const int32_t* large_index, int n_large, cudaStream_t stream);

@@ -35,7 +35,6 @@ struct EvalIO {
 };
 
 constexpr int kSmallCap = 512;      // frontier / pair capacity of the fused small path
-constexpr int kSmallWarps = 4;      // warps (= instructions in flight) per CTA
 
 int small_cap(int max_pairs);
 constexpr int kSmallPairsSlack = 32;   // words after the pair lists: [0] is the narrow tile kernel's tile ticket (zeroed by the broad kernel)

@@ -6,9 +6,7 @@
 //   polygon fan ........ integrate_over_polygon_patch!  :217-234,  centroid  src/clip/poly_eight.jl:35-52
 //   pressure law ....... fillTractionCacheInnerLoop!  :251-265
 //   regularized law .... traction / yes_contact!  src/contact_algorithms_friction.jl:13-30, 50-72
-//   bristle passes ..... normal_wrench_cop  src/contact_algorithms_normal.jl:17-34,
-//                        calc_patch_spatial_stiffness!  friction.jl:147-169,
-//                        calc_spatial_bristle_force  friction.jl:171-201, traction(::Bristle) :32-48
+//   (bristle friction: pfc_exact.cuh)
 // The reference materialises a TractionCache list between the narrow phase and friction; here
 // every quadrature point is consumed immediately by an accumulator (Accum::point) so nothing is
 // written to memory.  The work is split in two stages so that a warp can keep its lanes busy:
@@ -29,7 +27,7 @@ namespace pfc {
 #define PFC_QA 0.16666666666666674068
 #define PFC_QB 0.66666666666666651864
 
-enum AccMode { ACC_REGULARIZED = 0, ACC_COP = 1, ACC_STIFFNESS = 2, ACC_BRISTLE = 3, ACC_DUMP = 4 };
+enum AccMode { ACC_REGULARIZED = 0, ACC_DUMP = 4 };
 
 // per (environment, instruction) data in mode T
 template <class T> struct PatchCtx {
@@ -61,19 +59,16 @@ template <class T> PFC_D Vec3<T> sub_proj(const Vec3<T>& v, const Vec3<T>& n) { 
     return mk<T>(fma_(t, n.x, v.x), fma_(t, n.y, v.y), fma_(t, n.z, v.z));
 }
 
-template <class T, int NA = 21> struct Accum {
+// Consumer of the quadrature points of the REGULARIZED friction model (and of the debug dump).  Bristle instructions do not come
+// through here: pfc_exact.cuh evaluates them in the reference's operation order.
+template <class T, int NA = 6> struct Accum {
     int mode;
     int n_points;
-    T a[NA];  // 6 suffice for regularized-only scenes, 21 for the bristle stiffness pass
+    T a[NA];            // wrench sums: torque (0..2), force (3..5)
     const double* fp;   // friction parameters (InsDev::p)
     Vec3<T> w_ang, w_lin;
-    Vec3<T> cop;
-    T delta[6];         // bristle deformation (angular, linear)
     double* dump;       // ACC_DUMP: 8 doubles per point
     int dump_cap;
-
-    // constant-index access that stays in bounds when the unused modes are compiled for a small NA
-    PFC_D T& at(int i) { return a[i < NA ? i : NA - 1]; }
 
     PFC_D void reset(int m) {
         mode = m; n_points = 0;
@@ -99,60 +94,6 @@ template <class T, int NA = 21> struct Accum {
             const Vec3<T> tk = mk<T>(p_dA * n.x + vt.x * coef, p_dA * n.y + vt.y * coef, p_dA * n.z + vt.z * coef);
             const Vec3<T> m = cross(r, tk);
             a[0] += m.x; a[1] += m.y; a[2] += m.z; a[3] += tk.x; a[4] += tk.y; a[5] += tk.z;
-        } else if (NA >= 10 && mode == ACC_COP) {
-            const Vec3<T> lam = n * p_dA;
-            const Vec3<T> m = cross(r, lam);
-            at(0) += m.x; at(1) += m.y; at(2) += m.z; at(3) += lam.x; at(4) += lam.y; at(5) += lam.z;
-            at(6) += p_dA;
-            at(7) += p_dA * r.x; at(8) += p_dA * r.y; at(9) += p_dA * r.z;
-        } else if (NA >= 21 && mode == ACC_STIFFNESS) {
-            // K11 upper (0..5), K12 full row-major (6..14), K22 upper (15..20); k_bar applied by the caller
-            const Vec3<T> q = r - cop;
-            const Vec3<T> c = cross(q, n);
-            const T q0 = q.x * q.x, q1 = q.y * q.y, q2 = q.z * q.z;
-            // K11 -= p_dA * ([q]x^2 + c c')
-            at(0) -= p_dA * ((-q1 - q2) + c.x * c.x);
-            at(1) -= p_dA * (q.x * q.y + c.x * c.y);
-            at(2) -= p_dA * (q.x * q.z + c.x * c.z);
-            at(3) -= p_dA * ((-q0 - q2) + c.y * c.y);
-            at(4) -= p_dA * (q.y * q.z + c.y * c.z);
-            at(5) -= p_dA * ((-q0 - q1) + c.z * c.z);
-            // K12 += p_dA * ([q]x - c n')
-            at(6) += p_dA * (-(c.x * n.x));
-            at(7) += p_dA * (-q.z - c.x * n.y);
-            at(8) += p_dA * (q.y - c.x * n.z);
-            at(9) += p_dA * (q.z - c.y * n.x);
-            at(10) += p_dA * (-(c.y * n.y));
-            at(11) += p_dA * (-q.x - c.y * n.z);
-            at(12) += p_dA * (-q.y - c.z * n.x);
-            at(13) += p_dA * (q.x - c.z * n.y);
-            at(14) += p_dA * (-(c.z * n.z));
-            // K22 += p_dA * (I - n n')
-            at(15) += p_dA * (1.0 - n.x * n.x);
-            at(16) += p_dA * (-(n.x * n.y));
-            at(17) += p_dA * (-(n.x * n.z));
-            at(18) += p_dA * (1.0 - n.y * n.y);
-            at(19) += p_dA * (-(n.y * n.z));
-            at(20) += p_dA * (1.0 - n.z * n.z);
-        } else if (NA >= 21 && mode == ACC_BRISTLE) {
-            // fp: tau, k_bar, mu_s, mu_d, Ts_mu_s, Ts_mu_d, magic, slope
-            const Vec3<T> x2 = r - cop;
-            const Vec3<T> d_ang = mk<T>(delta[0], delta[1], delta[2]);
-            const Vec3<T> d_lin = mk<T>(delta[3], delta[4], delta[5]);
-            const Vec3<T> dl = d_lin + cross(d_ang, x2);
-            const Vec3<T> rd = w_lin + cross(w_ang, r);
-            const double tau = fp[0], nk = -fp[1], mu_s = fp[2];
-            Vec3<T> Ts = mk<T>((dl.x + rd.x * tau) * nk, (dl.y + rd.y * tau) * nk, (dl.z + rd.z * tau) * nk);
-            Ts = sub_proj(Ts, n);
-            const T mag2 = dot(Ts, Ts);
-            T coef = p_dA;
-            if (!(val(mag2) < mu_s * mu_s)) {
-                const T mag = sqrt_(mag2);
-                coef = (clamped_piecewise(mag, fp[4], fp[7], mu_s, fp[3]) / mag) * p_dA;
-            }
-            const Vec3<T> Tc = Ts * coef;
-            const Vec3<T> m = cross(x2, Tc);
-            at(0) += m.x; at(1) += m.y; at(2) += m.z; at(3) += Tc.x; at(4) += Tc.y; at(5) += Tc.z;
         } else {  // ACC_DUMP (debug / parity): n(3) r(3) dA p, values only
             if (n_points < dump_cap) {
                 double* o = dump + 8 * n_points;

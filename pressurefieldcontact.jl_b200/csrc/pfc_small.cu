@@ -13,12 +13,11 @@
 //   2. narrow_tile_kernel   one CTA per tile of 4 problems, every phase flattened over them: clip in place in shared-memory polygon
 //                           slots, (polygon, edge) sub-triangles dealt one per thread for quadrature + friction, per-problem sums in
 //                           item order (bitwise reproducible; no floating-point atomics);
-//      narrow_small_kernel  scenes with bristle instructions on this path: one warp per problem, the three passes of
-//                           bristle_wrench_in_world with a fixed-order butterfly reduction between passes.
+//   Bristle instructions on this path keep their pair lists from kernel 1 and are evaluated in the reference's operation order by
+//   pfc_exact.cu (TractionCache materialised, three sequential passes).
 // HBM traffic per instruction is the boundary data only: 22 doubles in, 6 doubles + 2 words out.
 #include <cstdlib>
 
-#include "pfc_bristle.cuh"
 #include "pfc_launch.h"
 #include "pfc_patch.cuh"
 #include "pfc_sat.cuh"
@@ -61,29 +60,6 @@ PFC_D void broad_phase_xform(const Xform<double>& x21, double* Rab, double* tab)
         for (int j = 0; j < 3; ++j) Rab[3 * i + j] = x21.r[3 * j + i];
         tab[i] = -add_(add_(mul_(x21.r[i], x21.t[0]), mul_(x21.r[3 + i], x21.t[1])), mul_(x21.r[6 + i], x21.t[2]));
     }
-}
-
-// A warp is split into 32 / G groups of G lanes; each group owns one (environment, instruction)
-// problem at a time.  Small frontiers (a 12 x 12-leaf box pair has at most 144 leaf pairs and
-// ~10-40 node pairs per level) leave most of a 32-lane warp idle; with G = 8 four problems share
-// the warp and the lanes stay dense.
-
-// group-restricted collectives (gmask = the lanes of this group; width-G shuffles stay inside the segment)
-template <int G> PFC_D int group_incl_scan(unsigned gmask, int x, int gl) {
-#pragma unroll
-    for (int o = 1; o < G; o <<= 1) { const int v = __shfl_up_sync(gmask, x, o, G); if (gl >= o) x += v; }
-    return x;
-}
-template <int G> PFC_D int group_sum_int(unsigned gmask, int x) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o, G);
-    return x;
-}
-// fixed-order xor-butterfly: every lane of the group ends with the same bits
-template <int G> PFC_D double group_sum(unsigned gmask, double x) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o, G);
-    return x;
 }
 
 // ---- kernel 1: broad phase, one WARP per tile of P problems, node table in shared memory ----------------------------
@@ -282,199 +258,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
     }
 }
 
-// ---- kernel 2: narrow phase + friction + reduction ---------------------------------------------------------------
-// Per group and accumulator pass:
-//   A1  every lane pre-filters pairs with an exact, cheap rejection test; survivors are compacted
-//       (in pair order) into a shared-memory list -- about 2/3 of the candidates die here;
-//   A2  G survivors at a time are clipped, one per lane, each leaving its polygon in its slot;
-//   B   the round's (polygon, edge) sub-triangles are dealt out one per lane for quadrature + friction.
-// shared memory per warp:  PolyRec poly[32] | PatchCtx cx[32/G] | double bris[32/G][42] |
-//                          unsigned short surv[32/G][cap] | unsigned char items[32/G][8*G]
-template <int G> struct NarrowLayout {
-    static constexpr int NG = 32 / G;
-    __host__ __device__ static size_t bytes(int cap) {
-        return sizeof(PolyRec<double>) * 32 + (sizeof(PatchCtx<double>) + sizeof(double) * 42 + sizeof(unsigned short) * cap + 8 * G) * NG;
-    }
-};
-template <int G> struct GroupSmem {
-    PolyRec<double>* poly;   // this group's G slots (stage A2 output, one per lane)
-    PatchCtx<double>* cx;    // transforms, twist and material constants of the group's instruction
-    double* bris;            // bristle: Sinv (6) + K̄^(-1/2) (36), kept across the friction pass
-    unsigned short* surv;    // indices (into the pair list) of the pairs that survive the pre-filter
-    unsigned char* items;    // stage B work list: (slot-in-group << 3) | edge
-};
-
-template <int G, int NA>
-PFC_D void run_pairs(const SceneDev& sc, const InsDev& ins, const GroupSmem<G>& sm, unsigned gmask, const unsigned* __restrict__ pairs, int n_surv, int gl,
-                     Accum<double, NA>& acc, int& flags) {
-    const PatchCtx<double>& cx = *sm.cx;
-    for (int base = 0; base < n_surv; base += G) {
-        const int i = base + gl;
-        int nv = 0;
-        if (i < n_surv) {
-            const unsigned e = pairs[sm.surv[i]];
-            if (clip_pair(sc, ins, dec_a(e), dec_b(e), cx, sm.poly[gl], flags)) nv = sm.poly[gl].n;
-        }
-        const int incl = group_incl_scan<G>(gmask, nv, gl);
-        const int total = __shfl_sync(gmask, incl, G - 1, G);
-        for (int k = 0; k < nv; ++k) sm.items[incl - nv + k] = (unsigned char)((gl << 3) | k);
-        __syncwarp(gmask);
-        for (int it = gl; it < total; it += G) {
-            const int code = sm.items[it];
-            const PolyRec<double>& pr = sm.poly[code >> 3];
-            const int k = code & 7;
-            const int kp = (k == 0) ? pr.n - 1 : k - 1;
-            integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, acc);
-        }
-        __syncwarp(gmask);
-    }
-}
-
-// HB: the scene has bristle instructions (21 accumulators and the 3-pass code are compiled in)
-template <int WARPS, int G, int MINB, bool HB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) narrow_small_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NG = 32 / G;
-    constexpr int NA = HB ? 21 : 6;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int grp = lane / G, gl = lane % G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-    GroupSmem<G> sm;
-    {
-        unsigned char* base = smem_raw + NarrowLayout<G>::bytes(cap) * wib;
-        sm.poly = reinterpret_cast<PolyRec<double>*>(base) + grp * G;
-        base += sizeof(PolyRec<double>) * 32;
-        sm.cx = reinterpret_cast<PatchCtx<double>*>(base) + grp;
-        base += sizeof(PatchCtx<double>) * NG;
-        sm.bris = reinterpret_cast<double*>(base) + 42 * grp;
-        base += sizeof(double) * 42 * NG;
-        sm.surv = reinterpret_cast<unsigned short*>(base) + (size_t)cap * grp;
-        base += sizeof(unsigned short) * cap * NG;
-        sm.items = base + 8 * G * grp;
-    }
-    const long long n_prob = io.n_env * sc.n_small;
-    const long long stride = (long long)gridDim.x * WARPS * NG;
-    for (long long prob = ((long long)blockIdx.x * WARPS + wib) * NG + grp; prob < n_prob; prob += stride) {
-        const long long env = prob / sc.n_small;
-        const int k = sc.small_ins[prob - env * sc.n_small];
-        const InsDev& ins = sc.ins[k];
-        const long long ei = env * sc.n_ins + k;
-        const int n = (int)io.n_pairs[ei];
-        int flags = 0;
-        const unsigned* cur = pairs_in + (size_t)cap * ei;
-
-        double w[6] = {0, 0, 0, 0, 0, 0};
-        bool contact = false;
-        const double* sv = (HB && ins.model == PFC_MODEL_BRISTLE) ? io.s + 6 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
-        double* sd = (HB && ins.model == PFC_MODEL_BRISTLE) ? io.sdot + 6 * ((long long)sc.n_bristle * env + ins.bristle_id) : nullptr;
-        int n_surv = 0;
-        if (n > 0) {
-            // the group's shared context (every lane would hold identical copies otherwise)
-            if (gl == 0) {
-                PatchCtx<double>& cx = *sm.cx;
-                load_xform(io.X + 16 * ei, cx.x21);
-                cx.x12 = inverse(cx.x21);
-                const double* tw = io.twist + 6 * ei;
-                cx.w_ang = mk<double>(tw[0], tw[1], tw[2]);
-                cx.w_lin = mk<double>(tw[3], tw[4], tw[5]);
-                cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
-            }
-            __syncwarp(gmask);
-            // A1: exact pre-filter + ordered compaction of the survivors
-            for (int base = 0; base < n; base += G) {
-                const int i = base + gl;
-                bool keep = false;
-                if (i < n) { const unsigned e = cur[i]; keep = prefilter_pair(sc, ins, dec_a(e), dec_b(e), *sm.cx); }
-                const unsigned m = __ballot_sync(gmask, keep) & gmask;
-                if (keep) sm.surv[n_surv + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
-                n_surv += __popc(m);
-            }
-            __syncwarp(gmask);
-        }
-        if (n_surv > 0) {
-            const PatchCtx<double>& cx = *sm.cx;
-            Accum<double, NA> acc;
-            acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
-            if (!HB || ins.model == PFC_MODEL_REGULARIZED) {
-                acc.reset(ACC_REGULARIZED);
-                run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
-                contact = group_sum_int<G>(gmask, acc.n_points) > 0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) w[j] = group_sum<G>(gmask, acc.a[j]);
-            } else if (HB) {
-                acc.reset(ACC_COP);
-                run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
-                contact = group_sum_int<G>(gmask, acc.n_points) > 0;
-                if (contact) {
-                    double c[10];
-#pragma unroll
-                    for (int j = 0; j < 10; ++j) c[j] = group_sum<G>(gmask, acc.at(j));
-                    const Vec3<double> cop = mk<double>(c[7] / c[6], c[8] / c[6], c[9] / c[6]);
-                    acc.cop = cop;
-                    acc.reset(ACC_STIFFNESS);
-                    run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
-                    // the group's first lane factors the 6x6 stiffness using the (now idle) polygon slots as scratch
-                    // (G slots x 35 doubles >= 129 doubles needs G >= 4)
-                    double* scr = reinterpret_cast<double*>(sm.poly);
-                    double* K21 = scr + 108;
-                    double* Sinv = sm.bris;
-                    double* Kh = sm.bris + 6;
-#pragma unroll
-                    for (int j = 0; j < 21; ++j) { const double v = group_sum<G>(gmask, acc.at(j)) * ins.p[1]; if (gl == 0) K21[j] = v; }
-                    if (gl == 0) decompose_K(K21, ins.p[6], Sinv, Kh, scr);
-                    __syncwarp(gmask);
-                    double s[6];
-                    for (int j = 0; j < 6; ++j) s[j] = sv[j];
-                    for (int i = 0; i < 6; ++i) {
-                        double t = 0.0;
-                        for (int j = 0; j < 6; ++j) t += Kh[6 * i + j] * s[j];
-                        acc.delta[i] = Sinv[i] * t;
-                    }
-                    acc.reset(ACC_BRISTLE);
-                    run_pairs<G, NA>(sc, ins, sm, gmask, cur, n_surv, gl, acc, flags);
-                    double f[6];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) f[j] = group_sum<G>(gmask, acc.a[j]);
-                    const Vec3<double> lin = mk<double>(f[3], f[4], f[5]);
-                    const Vec3<double> shift = cross(cop, lin);
-                    w[0] = c[0] + (f[0] + shift.x); w[1] = c[1] + (f[1] + shift.y); w[2] = c[2] + (f[2] + shift.z);
-                    w[3] = c[3] + f[3]; w[4] = c[4] + f[4]; w[5] = c[5] + f[5];
-                    if (gl == 0) {
-                        const double ti = -(1.0 / ins.p[0]);
-                        double sw[6];
-                        for (int i = 0; i < 6; ++i) sw[i] = Sinv[i] * f[i];
-                        for (int i = 0; i < 6; ++i) {
-                            double t = 0.0;
-                            for (int j = 0; j < 6; ++j) t += Kh[6 * i + j] * sw[j];
-                            sd[i] = ti * (t + s[i]);
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) flags |= __shfl_xor_sync(gmask, flags, o, G);
-        if (gl == 0) {
-            if (!contact) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) w[j] = 0.0;
-                if (HB && ins.model == PFC_MODEL_BRISTLE) {  // no_contact!(::Bristle)
-                    const double ti = -(1.0 / ins.p[0]);
-                    for (int j = 0; j < 6; ++j) sd[j] = ti * sv[j];
-                }
-            }
-            double* wo = io.wrench + 6 * ei;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) wo[j] = w[j];
-            io.flags[ei] |= flags | (contact ? kFlagContact : 0);
-        }
-        __syncwarp(gmask);
-    }
-}
-
-
-// ---- kernel 2b: narrow phase for scenes whose small instructions are all regularized: one CTA per TILE of P problems ----
-// The per-problem kernel above leaves lanes idle (about 29 candidates, 21 clip jobs and 49 sub-triangles per boxes.jl
+// ---- kernel 2: narrow phase of the regularized small instructions: one CTA per TILE of P problems ----
+// A warp-per-problem kernel leaves lanes idle (about 29 candidates, 21 clip jobs and 49 sub-triangles per boxes.jl
 // instruction on a 32-lane warp) and a warp runs its phases strictly one after another.  Here a CTA of 128 threads owns P
 // consecutive (environment, instruction) problems and every phase is flattened over all of them:
 //   1. 32 threads per problem fill the problem's shared context (transform, inverse, twist, constants), one element each;
@@ -540,9 +325,9 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
         // ---- 1. problem contexts: warp q fills problem q, one element per lane
         {
             const long long prob = tile * P + wib;
-            if (prob < n_prob) {
-                const long long env = prob / sc.n_small;
-                const int k = sc.small_ins[prob - env * sc.n_small];
+            const long long env = prob < n_prob ? prob / sc.n_small : 0;
+            const int k = prob < n_prob ? sc.small_ins[prob - env * sc.n_small] : 0;
+            if (prob < n_prob && sc.ins[k].model == PFC_MODEL_REGULARIZED) {   // (bristle instructions: pfc_exact.cu)
                 const InsDev& ins = sc.ins[k];
                 const long long ei = env * sc.n_ins + k;
                 const double* X = io.X + 16 * ei;
@@ -753,33 +538,6 @@ cudaError_t launch_broad_tile(const SceneDev& sc, const EvalIO& io, int cap, uns
     return cudaGetLastError();
 }
 
-template <int G, int MINB>
-cudaError_t launch_narrow_g(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
-    struct Tag {};
-    const int hb = sc.n_bristle > 0 ? 1 : 0;
-    const void* kern = hb ? (const void*)narrow_small_kernel<kSmallWarps, G, MINB, true> : (const void*)narrow_small_kernel<kSmallWarps, G, MINB, false>;
-    const size_t smem = NarrowLayout<G>::bytes(cap) * kSmallWarps;
-    int cached_blocks;
-    {
-        std::lock_guard<std::mutex> g(launch_mutex());
-        LaunchSlot& sl = launch_slot<Tag, 2>(hb);
-        if (sl.key0 != cap) {
-            cudaError_t e;
-            sl.blocks = persistent_blocks(kern, kSmallWarps * 32, smem, &e);
-            if (e != cudaSuccess) return e;
-            sl.key0 = cap;
-        }
-        cached_blocks = sl.blocks;
-    }
-    constexpr int per_block = kSmallWarps * (32 / G);
-    long long blocks = (io.n_env * sc.n_small + per_block - 1) / per_block;
-    if (blocks > cached_blocks) blocks = cached_blocks;
-    if (hb) narrow_small_kernel<kSmallWarps, G, MINB, true><<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
-    else narrow_small_kernel<kSmallWarps, G, MINB, false><<<(unsigned)blocks, kSmallWarps * 32, smem, stream>>>(sc, io, cap, pairs);
-    return cudaGetLastError();
-}
-
-
 template <int P, int MINB>
 cudaError_t launch_narrow_tile(const SceneDev& sc, const EvalIO& io, int cap, const unsigned* pairs, cudaStream_t stream) {
     struct Tag {};
@@ -824,10 +582,9 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
     cudaError_t e = launch_broad(sc, io, cap, pairs, stream);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
-    // regularized-only scenes: the tile kernel (4 problems per CTA, 4 CTAs per SM); scenes with bristle instructions on the small path
-    // (three passes, 21 accumulators): the warp-per-problem kernel (3 CTAs per SM at <= 168 registers)
-    if (sc.n_small_bristle == 0) e = launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
-    else e = launch_narrow_g<32, 3>(sc, io, cap, pairs, stream);
+    // regularized instructions: the tile kernel (4 problems per CTA, 4 CTAs per SM).  Bristle instructions are skipped here: they are
+    // evaluated in the reference's operation order by pfc_exact.cu from the pair lists the broad kernel left
+    e = launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
     if (ev) cudaEventRecord(ev[2], stream);
     if (n_launches) *n_launches += 2;
     return e;
