@@ -2,6 +2,8 @@
 built with the host mirror of the reference's scenario API."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import geometry as G
@@ -189,20 +191,40 @@ def eMesh_spoon_like(n_ring: int = 139, n_side: int = 18, length: float = 0.15) 
     return m
 
 
-def scene_c2_spoon(backend=None):
+SPOON_FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "spoon_mesh.npz")
+
+
+def eMesh_spoon_obj(path: str = SPOON_FIXTURE) -> "G.eMesh":
+    """The reference's own spoon (test/data/spoon.obj: 2504 vertices, 2502 quadrilaterals -> 5004 triangles), from the committed
+    vertex / face fixture (scripts/make_spoon_fixture.py), scaled by 0.01 as test/spoon.jl:37-38 does.  Every quadrilateral
+    (a, b, c, d) is split into (a, b, c), (a, c, d) -- the fan GeometryTypes' decompose uses when MeshIO hands FileIO.load's faces over
+    as triangles."""
+    d = np.load(path)
+    q = d["quads"].astype(np.int64)
+    tri = np.concatenate([q[:, [0, 1, 2]], q[:, [0, 2, 3]]], axis=1).reshape(-1, 3)   # the two triangles of a quad stay adjacent
+    return G.eMesh(d["vertices"] * 0.01, tri)
+
+
+def scene_c2_spoon(backend=None, real_mesh=None):
     """C2 (spoon): test/spoon.jl:23-54 re-expressed in the current API: a rigid 5004-triangle spoon
     surface between a world-fixed compliant box and a compliant box on a z-prismatic joint (eMesh_box(0.02), 12
-    tets, E 1e6); two bristle instructions mu 0.2, chi 0.2, quadrature rule 1.  Returns (scenario, bodies)."""
+    tets, E 1e6); two bristle instructions mu 0.2, chi 0.2, quadrature rule 1.  Returns (scenario, bodies).
+    real_mesh: True = the reference's spoon.obj (fixture), False = a swept stand-in of the same size, None = the fixture when present."""
+    if real_mesh is None:
+        real_mesh = os.path.exists(SPOON_FIXTURE)
     rad_box = 0.02
     m = S.MechanismScenario()
     c_prop = S.ContactProperties(1.0e6)
     box = G.as_tet_eMesh(G.eMesh_box(rad_box, (0.0, 0.0, -rad_box)))
     id_lo = S.add_contact(m, "box_lo", box, c_prop=c_prop)
     b_up, _, id_up = S.add_body_contact(m, "box_up", box.copy(), c_prop=c_prop, joint=S.Prismatic((0.0, 0.0, 1.0)))
-    b_spoon, _, id_spoon = S.add_body_contact(m, "spoon", eMesh_spoon_like())
+    spoon = eMesh_spoon_obj() if real_mesh else eMesh_spoon_like()
+    b_spoon, _, id_spoon = S.add_body_contact(m, "spoon", spoon)
     S.add_friction_bristle(m, id_spoon, id_lo, mu_d=0.2, chi=0.2, n_quad_rule=1)
     S.add_friction_bristle(m, id_spoon, id_up, mu_d=0.2, chi=0.2, n_quad_rule=1)
     S.finalize(m, backend)
+    m.spoon_is_real = bool(real_mesh)
+    m.spoon_points = spoon.point
     return m, dict(box_up=b_up, spoon=b_spoon)
 
 
@@ -212,11 +234,26 @@ def spoon_sample_states(m, bodies, n: int = 6, seed: int = 0x5EED5B00):
     u = _splitmix(seed)
     U = lambda lo, hi: lo + (hi - lo) * u()
     rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]])
+    rx90 = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, -1.0], [0.0, 1.0, 0.0]])   # RotX(pi / 2), test/spoon.jl:51
     xs = []
     for k in range(n):
         m.q[:] = 0.0
         m.v[:] = 0.0
         pen_lo = U(5e-5, 4e-4)
+        if getattr(m, "spoon_is_real", False):
+            # the reference's pose (RotX(pi/2), a little yaw and xy jitter); heights from the part of the spoon above the boxes' footprint
+            R = rz(U(-0.3, 0.3)) @ rx90
+            t_xy = np.array([U(-2e-3, 2e-3), U(-2e-3, 2e-3)])
+            w = m.spoon_points @ R.T
+            inside = (np.abs(w[:, 0] + t_xy[0]) < 0.02) & (np.abs(w[:, 1] + t_xy[1]) < 0.02)
+            z_lo, z_hi = w[inside, 2].min(), w[inside, 2].max()
+            S.set_state_spq(m, bodies["spoon"], rot=R, trans=(t_xy[0], t_xy[1], -z_lo - pen_lo))
+            q_up = 0.10 if k % 3 == 0 else 0.04 + (z_hi - z_lo) - pen_lo - U(5e-5, 4e-4)   # box_up spans [q - 0.04, q]
+            S.set_configuration(m, bodies["box_up"], [q_up])
+            m.v[:] = [U(-0.003, 0.003) for _ in range(m.nv)]
+            m.s[:] = [U(-2e-4, 2e-4) for _ in range(6 * m.n_bristle)]
+            xs.append(S.get_state(m).copy())
+            continue
         S.set_state_spq(m, bodies["spoon"], rot=rz(U(-0.3, 0.3)), trans=(U(-2e-3, 2e-3), U(-2e-3, 2e-3), -pen_lo))
         q_up = 0.10 if k % 3 == 0 else 0.04 + 0.003 - pen_lo - U(5e-5, 4e-4)  # box_up spans [q - 0.04, q]; the spoon is 3 mm thick
         S.set_configuration(m, bodies["box_up"], [q_up])
