@@ -271,17 +271,23 @@ int pfc_add_mesh(pfc_ctx* c, int kind, int64_t n_point, const double* xyz, int64
             nd.e[i] = node_e[3 * it.src + i];
             for (int j = 0; j < 3; ++j) nd.R[3 * i + j] = node_R[9 * it.src + 3 * j + i];  // column-major in, row-major stored
         }
-        if (it.parent_dst >= 0) { if (it.side == 0) m.nodes[it.parent_dst].left = dst; else m.nodes[it.parent_dst].right = dst; }
+        if (it.parent_dst >= 0) {   // pre-order: child 1 is the record after its parent (no link stored), child 2 is linked
+            if (it.side == 0) { if (dst != it.parent_dst + 1) return fail(PFC_E_MESH, "pfc_add_mesh: internal error (pre-order)"); }
+            else m.nodes[it.parent_dst].right = dst;
+        }
         const int32_t leaf = node_leaf_id[it.src];
         if (leaf >= 0) {
             if (leaf >= n_prim || m.leaf_depth[leaf] >= 0) return fail(PFC_E_MESH, "pfc_add_mesh: leaf ids are not a permutation of the primitives");
-            nd.left = -1; nd.right = leaf;
+            nd.kind = kNodeLeaf; nd.right = leaf;
             m.leaf_depth[leaf] = it.depth;
             m.leaf_path[leaf] = it.path;
             if (it.depth > m.depth) m.depth = it.depth;
         } else {
             if (it.depth >= 62) return fail(PFC_E_MESH, "pfc_add_mesh: tree deeper than 62 levels");
-            nd.left = nd.right = -1;
+            bool identity = true;   // internal boxes are merged axis-aligned boxes (src/obb/box_types.jl:11-15): the SAT skips the identity products
+            for (int i = 0; i < 9; ++i) identity = identity && (nd.R[i] == ((i % 4 == 0) ? 1.0 : 0.0));
+            nd.kind = identity ? kNodeInternalAabb : kNodeInternal;
+            nd.right = -1;
             stack.push_back({node_right[it.src], dst, 1, it.depth + 1, (it.path << 1) | 1u});
             stack.push_back({node_left[it.src], dst, 0, it.depth + 1, (it.path << 1)});
         }
@@ -476,7 +482,29 @@ static int eval_bristle_exact(pfc_ctx* c, long long n_env, const double* X, cons
     return PFC_OK;
 }
 
-static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
+// The large path and the bristle pipeline queue their work without a host round trip and size their buffers from earlier evaluations.
+// After an evaluation has been queued: one synchronisation, then the device-side counters say whether everything fit.  Returns 0 (it
+// did, or nothing growable was involved: no synchronisation then), 1 (capacities raised: queue the same evaluation again) or a
+// negative PFC_E_* code.
+static int evaluation_fits(pfc_ctx* c) {
+    const bool lg = c->large_buf != nullptr, ex = c->exact_buf != nullptr;
+    if (!lg && !ex) return 0;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(PFC_E_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    const int a = lg ? large_check(c->large_buf) : 0, b = ex ? exact_check(c->exact_buf) : 0;
+    if (a < 0 || b < 0) return fail(PFC_E_CAPACITY, "candidate-pair / traction buffers cannot be grown far enough");
+    return (a | b) ? 1 : 0;
+}
+#define PFC_REQUEUE_LOOP(body)                                                                                   \
+    for (int attempt_ = 0;; ++attempt_) {                                                                        \
+        body                                                                                                     \
+        const int fit_ = evaluation_fits(c);                                                                     \
+        if (fit_ < 0) return fit_;                                                                               \
+        if (fit_ == 0) break;                                                                                    \
+        if (attempt_ >= 8) return fail(PFC_E_CAPACITY, "candidate-pair / traction buffers kept overflowing");    \
+    }
+
+static int eval_device_once(pfc_ctx* c, const EvalIO& io_in) {
     EvalIO io = io_in;
     const int n_ins = c->scene.n_ins;
     if (c->keep_pairs) {
@@ -510,6 +538,11 @@ static int eval_device(pfc_ctx* c, const EvalIO& io_in) {
         CU(c->d_last_np.ensure(size_t(io.n_env) * n_ins));
         CU(cudaMemcpyAsync(c->d_last_np.p, io.n_pairs, sizeof(long long) * io.n_env * n_ins, cudaMemcpyDeviceToDevice, c->stream));
     }
+    return PFC_OK;
+}
+
+static int eval_device(pfc_ctx* c, const EvalIO& io) {
+    PFC_REQUEUE_LOOP({ const int rc_ = eval_device_once(c, io); if (rc_ != PFC_OK) return rc_; })
     return PFC_OK;
 }
 
@@ -606,24 +639,28 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
     EvalIO io{};
     io.n_env = n_env; io.X = X; io.twist = twist; io.s = s; io.wrench = wrench; io.sdot = sdot;
     io.n_pairs = reinterpret_cast<long long*>(n_pairs); io.flags = flags;
-    int nl = 0;
-    if (c->scene.n_small > 0) {  // small instructions are cheap: every rank evaluates them completely
-        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins + kSmallPairsSlack));
-        CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
-    }
-    // every rank runs the breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair lists.
-    // Bristle instructions are the exception: their sums run sequentially over the whole TractionCache list (pfc_exact.cuh), so every
-    // rank lists and evaluates them completely -- identical bits on every rank, nothing to exchange.
-    CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl, c->shard_rank, c->shard_world));
-    CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, c->shard_world > 1, 0, c->stream, &nl));
-    {
-        int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
-        if (rc != PFC_OK) return rc;
-    }
-    c->launches += nl;
+    // one synchronisation at the end of what was queued: the traversal's and the bristle pipeline's buffers grow after the fact
+    PFC_REQUEUE_LOOP({
+        int nl = 0;
+        if (c->scene.n_small > 0) {  // small instructions are cheap: every rank evaluates them completely
+            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins + kSmallPairsSlack));
+            CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
+        }
+        // every rank runs the breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair lists.
+        // Bristle instructions are the exception: their sums run sequentially over the whole TractionCache list (pfc_exact.cuh), so every
+        // rank lists and evaluates them completely -- identical bits on every rank, nothing to exchange.
+        CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl, c->shard_rank, c->shard_world));
+        CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, c->shard_world > 1, 0, c->stream, &nl));
+        {
+            int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
+            if (rc != PFC_OK) return rc;
+        }
+        c->launches += nl;
+    })
     c->sharded_io = io;
     c->sharded_stage = 0;
     c->lists_n_env = -1;
+    if (c->keep_pairs) c->dbg_n_env = n_env;   // (pfc_get_pairs: the large instructions' lists live in the large path's buffers)
     c->last_X = io.X; c->last_tw = io.twist;
     return PFC_OK;
 }
@@ -656,23 +693,10 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     if (c->n_bristle > 0 && (!s7 || !sdot7)) return fail(PFC_E_ARG, "pfc_eval_dual6: bristle instructions need s7 and sdot7");
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
-    int nl = 0;
     arena_reset(c);
     if (X_bp) {  // traverse with the Float64 transform (calcTriTetIntersections! always uses m.float)
         CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
         CU(copy_in(c, c->d_X.p, X_bp, sizeof(double) * 16 * ne * ni));
-        EvalIO io{};
-        io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
-        if (c->scene.n_small > 0) {
-            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni + kSmallPairsSlack));
-            CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
-        }
-        if (c->large_scene.n_large > 0) {
-            CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
-            CU(large_write_counts(c->scene, c->large_scene, io, c->large_buf, c->stream));
-            nl += 1;
-        }
-        c->lists_n_env = n_env;
     } else if (c->lists_n_env != n_env) {
         return fail(PFC_E_ARG, "pfc_eval_dual6: X_bp is NULL but no pair lists of a previous pfc_eval_f64 with the same n_env exist");
     }
@@ -681,14 +705,31 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     CU(copy_in(c, c->d_X7.p, X7, sizeof(double) * 112 * ne * ni));
     CU(copy_in(c, c->d_tw7.p, twist7, sizeof(double) * 42 * ne * ni));
     if (nb) CU(copy_in(c, c->d_s7.p, s7, sizeof(double) * 42 * ne * nb));
-    CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p,
-                         c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
-                         c->large_scene.n_large, c->stream));
-    {   // bristle instructions on Duals, in the reference's operation order
-        int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p, 1, false, &nl);
-        if (rc != PFC_OK) return rc;
-    }
-    c->launches += nl + 1;
+    PFC_REQUEUE_LOOP({
+        int nl = 0;
+        if (X_bp) {
+            EvalIO io{};
+            io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
+            if (c->scene.n_small > 0) {
+                CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni + kSmallPairsSlack));
+                CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
+            }
+            if (c->large_scene.n_large > 0) {
+                CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
+                CU(large_write_counts(c->scene, c->large_scene, io, c->large_buf, c->stream));
+                nl += 1;
+            }
+        }
+        CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p,
+                             c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
+                             c->large_scene.n_large, c->stream));
+        {   // bristle instructions on Duals, in the reference's operation order
+            int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p, 1, false, &nl);
+            if (rc != PFC_OK) return rc;
+        }
+        c->launches += nl + 1;
+    })
+    if (X_bp) c->lists_n_env = n_env;
     CU(copy_out(c, wrench7, c->d_w7.p, sizeof(double) * 42 * ne * ni));
     if (nb) CU(copy_out(c, sdot7, c->d_sd7.p, sizeof(double) * 42 * ne * nb));
     if (n_pairs) CU(copy_out(c, n_pairs, c->d_np.p, sizeof(long long) * ne * ni));
@@ -712,8 +753,9 @@ int pfc_set_debug(pfc_ctx* c, int keep_pairs) {
 }
 
 int pfc_get_pairs(pfc_ctx* c, int64_t env, int ins, int32_t* pairs, int64_t cap, int64_t* n_out) {
-    if (!c || !c->finalized || !c->keep_pairs || !c->d_dbg_pairs.p) return fail(PFC_E_ARG, "pfc_get_pairs: call pfc_set_debug(ctx, 1) before evaluating");
+    if (!c || !c->finalized || !c->keep_pairs) return fail(PFC_E_ARG, "pfc_get_pairs: call pfc_set_debug(ctx, 1) before evaluating");
     if (env < 0 || env >= c->dbg_n_env || ins < 0 || ins >= c->scene.n_ins) return fail(PFC_E_ARG, "pfc_get_pairs: index out of range");
+    if (c->h_ins[ins].small && !c->d_dbg_pairs.p) return fail(PFC_E_ARG, "pfc_get_pairs: call pfc_set_debug(ctx, 1) before evaluating");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     const int64_t ei = env * c->scene.n_ins + ins;
@@ -973,8 +1015,8 @@ int pfc_calcxd_f64(pfc_ctx* c, int64_t n_env, const double* x, const double* tau
 // calcXd! in Jacobian mode for the same scenes: x (Float64) with Dual seeds on x[seed_start .. seed_start + 6) -> x_dot as 7 doubles per
 // entry (value, then d x_dot / d x[seed_start + k]).  Device pipeline: Float64 prologue + broad phase (the reference always traverses
 // with m.float), Dual prologue, Dual narrow phase / friction (pfc_dual.cu), Dual J' w and rigid-body terms.
-static int calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, long long* n_pairs,
-                               int* flags, int* status) {
+static int calcxd_dual6_device_once(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, long long* n_pairs,
+                                    int* flags, int* status) {
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
     CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni));
     CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni));
@@ -1008,6 +1050,11 @@ static int calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const
     CU(launch_state_dynamics_dual6(c->state, c->dyn, n_env, int(ni), int(nb), x, seed_start, c->d_w7.p, tau_ext, nb ? c->d_sd7.p : nullptr, xdot7,
                                    c->stream, &nl, flags, status));
     c->launches += nl + 1;
+    return PFC_OK;
+}
+static int calcxd_dual6_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, long long* n_pairs,
+                               int* flags, int* status) {
+    PFC_REQUEUE_LOOP({ const int rc_ = calcxd_dual6_device_once(c, n_env, x, tau_ext, seed_start, xdot7, n_pairs, flags, status); if (rc_ != PFC_OK) return rc_; })
     return PFC_OK;
 }
 
@@ -1062,13 +1109,13 @@ int pfc_refit_mesh(pfc_ctx* c, int mesh_id, int64_t n_point, const double* xyz) 
         std::vector<int> depth(n_node, 0), order;
         int max_depth = 0;
         for (int64_t k = 0; k < n_node; ++k)
-            if (m.nodes[k].left >= 0) { depth[m.nodes[k].left] = depth[m.nodes[k].right] = depth[k] + 1; max_depth = std::max(max_depth, depth[k]); }
+            if (m.nodes[k].kind >= 0) { depth[k + 1] = depth[m.nodes[k].right] = depth[k] + 1; max_depth = std::max(max_depth, depth[k]); }
         r.level_ptr.assign(max_depth + 2, 0);
-        for (int64_t k = 0; k < n_node; ++k) if (m.nodes[k].left >= 0) r.level_ptr[depth[k] + 1]++;
+        for (int64_t k = 0; k < n_node; ++k) if (m.nodes[k].kind >= 0) r.level_ptr[depth[k] + 1]++;
         for (int l = 0; l <= max_depth; ++l) r.level_ptr[l + 1] += r.level_ptr[l];
         order.resize(std::max<int>(r.level_ptr[max_depth + 1], 1));
         std::vector<int> cursor(r.level_ptr.begin(), r.level_ptr.end() - 1);
-        for (int64_t k = 0; k < n_node; ++k) if (m.nodes[k].left >= 0) order[cursor[depth[k]]++] = int(k);
+        for (int64_t k = 0; k < n_node; ++k) if (m.nodes[k].kind >= 0) order[cursor[depth[k]]++] = int(k);
         CU(r.idx.ensure(m.idx.size())); CU(r.level_nodes.ensure(order.size()));
         CU(cudaMemcpy(r.idx.p, m.idx.data(), sizeof(int) * m.idx.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(r.level_nodes.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));

@@ -256,20 +256,27 @@ template <class T> cudaError_t ensure_buf(T*& p, size_t& cap, size_t need) {
 
 struct ExactBuffers {
     unsigned* ctr = nullptr;          // [0] points reserved so far, [1] overflow
+    unsigned* h_ctr = nullptr;        // pinned copy, read by exact_check() after the caller's synchronisation
+    bool check_pending = false;
     double* recs = nullptr; size_t cap_rec_doubles = 0;
     unsigned* unit_off = nullptr; size_t cap_off = 0;
     unsigned* unit_cnt = nullptr; size_t cap_cnt = 0;
     size_t want_points = 1u << 16;
+    size_t cap_points = 0;
     unsigned last_points = 0;
 };
 ExactBuffers* exact_buffers_create() { return new ExactBuffers(); }
 void exact_buffers_destroy(ExactBuffers* b) {
     if (!b) return;
     cudaFree(b->ctr); cudaFree(b->recs); cudaFree(b->unit_off); cudaFree(b->unit_cnt);
+    if (b->h_ctr) cudaFreeHost(b->h_ctr);
     delete b;
 }
 unsigned exact_last_points(const ExactBuffers* b) { return b->last_points; }
 
+// Queues the two kernels; nothing is read back here.  The TractionCache buffer grows like the reference's VectorCache
+// (src/obb/vector_cache.jl:11-15), after the fact: the caller synchronises once at the end of the evaluation it queued and asks
+// exact_check(), which raises the capacity to what the counter says was needed and tells the caller to queue the evaluation again.
 template <class T> static cudaError_t exact_eval_t(const SceneDev& sc, const ExactScene& es, const ExactIO& io, const ExactPairs& ps, ExactBuffers* b,
                                                    cudaStream_t stream, int* n_launches) {
     const long long n_prob = io.n_env * es.n_bris;
@@ -281,6 +288,7 @@ template <class T> static cudaError_t exact_eval_t(const SceneDev& sc, const Exa
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     if (!b->ctr) ECU(cudaMalloc(&b->ctr, 2 * sizeof(unsigned)));
+    if (!b->h_ctr) ECU(cudaHostAlloc(reinterpret_cast<void**>(&b->h_ctr), 2 * sizeof(unsigned), cudaHostAllocDefault));
     ECU(ensure_buf(b->unit_off, b->cap_off, n_unit_slots));
     ECU(ensure_buf(b->unit_cnt, b->cap_cnt, n_unit_slots));
     constexpr int PTS = nc == 1 ? 32 : 8;
@@ -292,30 +300,35 @@ template <class T> static cudaError_t exact_eval_t(const SceneDev& sc, const Exa
         LaunchSlot& sl = launch_slot<Tag, 2>(nc == 1 ? 0 : 1);
         if (sl.smem < smem) { ECU(cudaFuncSetAttribute(exact_bristle_kernel<T, PTS, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); sl.smem = smem; }
     }
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        const size_t cap_points = std::min<size_t>(b->want_points, 0xfffffff0u);
-        ECU(ensure_buf(b->recs, b->cap_rec_doubles, cap_points * 8 * 7));   // sized for the Jacobian mode: both modes share the buffer
-        ECU(cudaMemsetAsync(b->ctr, 0, 2 * sizeof(unsigned), stream));
-        const unsigned grid_p = (unsigned)std::min<size_t>(n_unit_slots, (size_t)n_sm * 8);
-        exact_points_kernel<T><<<grid_p, kUnit, 0, stream>>>(sc, es, io, ps, reinterpret_cast<ExRec<T>*>(b->recs), (unsigned)cap_points, b->ctr, b->unit_off, b->unit_cnt, U_s);
-        const unsigned grid_b = (unsigned)std::min<long long>((n_prob + WPB - 1) / WPB, (long long)n_sm * 8);
-        exact_bristle_kernel<T, PTS, WPB><<<grid_b, 32 * WPB, smem, stream>>>(sc, es, io, ps, reinterpret_cast<const ExRec<T>*>(b->recs), b->unit_off, b->unit_cnt, U_s);
-        if (n_launches) *n_launches += 2;
-        ECU(cudaGetLastError());
-        unsigned h[2] = {0, 0};
-        ECU(cudaMemcpyAsync(h, b->ctr, sizeof h, cudaMemcpyDeviceToHost, stream));
-        ECU(cudaStreamSynchronize(stream));   // the one synchronisation of a bristle evaluation: did the TractionCache buffer suffice?
-        b->last_points = h[0];
-        if (!h[1]) return cudaSuccess;
-        if (cap_points >= 0xfffffff0u) break;
-        b->want_points = (size_t)h[0] + (size_t)h[0] / 4 + 1024;   // the counter kept counting: the need is known exactly
-    }
-    return cudaErrorMemoryAllocation;
+    b->cap_points = std::min<size_t>(std::max(b->want_points, b->cap_points), 0xfffffff0u);
+    ECU(ensure_buf(b->recs, b->cap_rec_doubles, b->cap_points * 8 * 7));   // sized for the Jacobian mode: both modes share the buffer
+    ECU(cudaMemsetAsync(b->ctr, 0, 2 * sizeof(unsigned), stream));
+    const unsigned grid_p = (unsigned)std::min<size_t>(n_unit_slots, (size_t)n_sm * 8);
+    exact_points_kernel<T><<<grid_p, kUnit, 0, stream>>>(sc, es, io, ps, reinterpret_cast<ExRec<T>*>(b->recs), (unsigned)b->cap_points, b->ctr, b->unit_off, b->unit_cnt, U_s);
+    const unsigned grid_b = (unsigned)std::min<long long>((n_prob + WPB - 1) / WPB, (long long)n_sm * 8);
+    exact_bristle_kernel<T, PTS, WPB><<<grid_b, 32 * WPB, smem, stream>>>(sc, es, io, ps, reinterpret_cast<const ExRec<T>*>(b->recs), b->unit_off, b->unit_cnt, U_s);
+    if (n_launches) *n_launches += 2;
+    ECU(cudaGetLastError());
+    ECU(cudaMemcpyAsync(b->h_ctr, b->ctr, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    b->check_pending = true;
+    return cudaSuccess;
 }
 
 cudaError_t exact_bristle_eval(const SceneDev& sc, const ExactScene& es, const ExactIO& io, const ExactPairs& ps, int dual, ExactBuffers* b, cudaStream_t stream,
                                int* n_launches) {
     return dual ? exact_eval_t<X6>(sc, es, io, ps, b, stream, n_launches) : exact_eval_t<double>(sc, es, io, ps, b, stream, n_launches);
+}
+
+// After the caller synchronised the stream: 0 = the TractionCache buffer sufficed, 1 = it did not (capacity raised: queue the evaluation
+// again), -1 = it cannot be made large enough.
+int exact_check(ExactBuffers* b) {
+    if (!b || !b->check_pending) return 0;
+    b->check_pending = false;
+    b->last_points = b->h_ctr[0];
+    if (!b->h_ctr[1]) return 0;
+    if (b->cap_points >= 0xfffffff0u) return -1;
+    b->want_points = (size_t)b->h_ctr[0] + (size_t)b->h_ctr[0] / 4 + 1024;   // the counter kept counting: the need is known exactly
+    return 1;
 }
 
 }  // namespace pfc

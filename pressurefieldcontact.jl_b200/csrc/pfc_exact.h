@@ -38,8 +38,10 @@ struct ExactBuffers;
 ExactBuffers* exact_buffers_create();
 void exact_buffers_destroy(ExactBuffers* b);
 unsigned exact_last_points(const ExactBuffers* b);
-// Evaluates every bristle instruction of the scene (wrench, s-dot, contact flag).  Synchronises the stream once: the TractionCache
-// buffer grows like the reference's VectorCache (src/obb/vector_cache.jl:11-15) and the evaluation is repeated when it was too small.
+// Queues the evaluation of every bristle instruction of the scene (wrench, s-dot, contact flag) on the stream.  The TractionCache buffer
+// grows like the reference's VectorCache (src/obb/vector_cache.jl:11-15): after the caller synchronised the stream, exact_check() says
+// whether it sufficed (0), or was raised so that the evaluation must be queued again (1), or cannot be made large enough (-1).
+int exact_check(ExactBuffers* b);
 cudaError_t exact_bristle_eval(const SceneDev& sc, const ExactScene& es, const ExactIO& io, const ExactPairs& ps, int dual, ExactBuffers* b, cudaStream_t stream,
                                int* n_launches);
 

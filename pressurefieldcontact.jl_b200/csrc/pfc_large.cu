@@ -100,13 +100,21 @@ PFC_D void prob_to_ei(const SceneDev& sc, const LargeScene& ls, int p, long long
 // ch[], or -1 for a leaf pair (prims in ch[0]); 0 also when the boxes are disjoint.
 // A 128 B node record as four 256-bit loads (sm_100: ld.global.v4.b64).  Every lane gathers its own two records, so each load
 // instruction touches 32 different lines; fewer, wider requests are what the L1 data pipe is short of here.
+// Axis-aligned internal nodes (most of what a traversal of big trees visits) need only the first 64 B: centre, extents, links, kind.
 PFC_D void load_node(const NodeRec* __restrict__ p, NodeRec& out) {
     unsigned long long* o = reinterpret_cast<unsigned long long*>(&out);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 2; ++j)
         asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];"
                      : "=l"(o[4 * j]), "=l"(o[4 * j + 1]), "=l"(o[4 * j + 2]), "=l"(o[4 * j + 3])
                      : "l"(reinterpret_cast<const char*>(p) + 32 * j));
+    if (out.kind != kNodeInternalAabb) {
+#pragma unroll
+        for (int j = 2; j < 4; ++j)
+            asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];"
+                         : "=l"(o[4 * j]), "=l"(o[4 * j + 1]), "=l"(o[4 * j + 2]), "=l"(o[4 * j + 3])
+                         : "l"(reinterpret_cast<const char*>(p) + 32 * j));
+    }
 }
 
 PFC_D int expand_pair(const SceneDev& sc, const InsDev& ins, const double* Rab, const double* tab, int ia, int ib, int2* ch) {
@@ -116,12 +124,12 @@ PFC_D int expand_pair(const SceneDev& sc, const InsDev& ins, const double* Rab, 
     SatA A;
     sat_prepare_a(a, Rab, tab, A);
     if (!sat_test(A, b)) return 0;
-    const int al = a.left, ar = a.right, bl = b.left, br = b.right;
-    if (al < 0) {
-        if (bl < 0) { ch[0] = make_int2(ar, br); return -1; }
+    const int al = ia + 1, ar = a.right, bl = ib + 1, br = b.right;   // pre-order: child 1 is the next record
+    if (a.kind < 0) {
+        if (b.kind < 0) { ch[0] = make_int2(ar, br); return -1; }
         ch[0] = make_int2(ia, bl); ch[1] = make_int2(ia, br); return 2;
     }
-    if (bl < 0) { ch[0] = make_int2(al, ib); ch[1] = make_int2(ar, ib); return 2; }
+    if (b.kind < 0) { ch[0] = make_int2(al, ib); ch[1] = make_int2(ar, ib); return 2; }
     ch[0] = make_int2(al, bl); ch[1] = make_int2(ar, bl); ch[2] = make_int2(al, br); ch[3] = make_int2(ar, br);
     return 4;
 }
@@ -329,7 +337,12 @@ __global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, 
 }
 
 // K1c: DFS-order key of every pair.  key = (prob << key_bits) | interleaved path bits (left-aligned in key_bits)
-__global__ void build_keys_kernel(SceneDev sc, LargeScene ls, const int3* __restrict__ pairs, unsigned n, unsigned long long* keys, unsigned* vals) {
+// the number of pairs the traversal left (never more than the buffers hold: an overflowing evaluation is repeated by the host)
+PFC_D unsigned listed_pairs(const Counters* cnt, unsigned cap_pairs) { const unsigned n = cnt->n_pairs; return n < cap_pairs ? n : cap_pairs; }
+
+__global__ void build_keys_kernel(SceneDev sc, LargeScene ls, const int3* __restrict__ pairs, const Counters* cnt, unsigned cap_pairs, unsigned long long* keys,
+                                  unsigned* vals) {
+    const unsigned n = listed_pairs(cnt, cap_pairs);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int3 p = pairs[i];
         long long env; int k;
@@ -355,9 +368,16 @@ __global__ void build_keys_kernel(SceneDev sc, LargeScene ls, const int3* __rest
 // leaves the digit total; (3) every tile turns the 256 digit totals into digit bases with a warp scan, adds its row offsets and
 // scatters its keys in order (ranks inside a 32-key chunk from __match_any_sync), so the sort is stable.
 constexpr int kTile = 512;
-__global__ void __launch_bounds__(128) radix_hist_kernel(const unsigned long long* __restrict__ keys, unsigned n, int shift, unsigned* hist, unsigned n_tiles) {
+// (n comes from the device counter, so the whole evaluation is queued without a host round trip: grids are sized for the buffers'
+// capacity -- cap_tiles tiles -- and the tiles beyond the list return at once; lists of at most kSmallSort pairs go to small_sort_kernel)
+constexpr unsigned kSmallSort = 2048;   // beyond a few thousand keys the radix passes win (measured: 6 695 keys, 421 vs 363 us per evaluation)
+__global__ void __launch_bounds__(128) radix_hist_kernel(const unsigned long long* __restrict__ keys, const Counters* cnt, unsigned cap_pairs, int shift, unsigned* hist,
+                                                         unsigned cap_tiles) {
     __shared__ unsigned h[4][256];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned n = listed_pairs(cnt, cap_pairs);
+    if (n <= kSmallSort) return;
+    const unsigned n_tiles = (n + kTile - 1) / kTile;
     const unsigned tile = blockIdx.x * 4 + wib;
     for (int d = lane; d < 256; d += 32) h[wib][d] = 0;
     __syncwarp();
@@ -369,13 +389,16 @@ __global__ void __launch_bounds__(128) radix_hist_kernel(const unsigned long lon
 #pragma unroll
         for (int j = 0; j < kTile / 32; ++j) if (beg + 32 * j + lane < end) atomicAdd(&h[wib][(k[j] >> shift) & 255u], 1u);
         __syncwarp();
-        for (int d = lane; d < 256; d += 32) hist[(size_t)d * n_tiles + tile] = h[wib][d];  // digit-major for the row scans
+        for (int d = lane; d < 256; d += 32) hist[(size_t)d * cap_tiles + tile] = h[wib][d];  // digit-major for the row scans
     }
 }
 // block d: exclusive scan of row d (n_tiles counts) in place, row total -> tot[d]
-__global__ void __launch_bounds__(256) radix_rowscan_kernel(unsigned* hist, unsigned n_tiles, unsigned* tot) {
+__global__ void __launch_bounds__(256) radix_rowscan_kernel(unsigned* hist, const Counters* cnt, unsigned cap_pairs, unsigned cap_tiles, unsigned* tot) {
     __shared__ unsigned warp_sums[8];
-    unsigned* row = hist + (size_t)blockIdx.x * n_tiles;
+    const unsigned n = listed_pairs(cnt, cap_pairs);
+    if (n <= kSmallSort) return;
+    const unsigned n_tiles = (n + kTile - 1) / kTile;
+    unsigned* row = hist + (size_t)blockIdx.x * cap_tiles;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned carry = 0;
     constexpr int IT = 8;   // consecutive counts per thread
@@ -398,11 +421,14 @@ __global__ void __launch_bounds__(256) radix_rowscan_kernel(unsigned* hist, unsi
     }
     if (threadIdx.x == 0) tot[blockIdx.x] = carry;
 }
-__global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned n, int shift,
-                                                            const unsigned* __restrict__ hist, const unsigned* __restrict__ tot, unsigned n_tiles,
-                                                            unsigned long long* keys_out, unsigned* vals_out) {
+__global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in, const Counters* cnt,
+                                                            unsigned cap_pairs, int shift, const unsigned* __restrict__ hist, const unsigned* __restrict__ tot,
+                                                            unsigned cap_tiles, unsigned long long* keys_out, unsigned* vals_out) {
     __shared__ unsigned base[4][256];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned n = listed_pairs(cnt, cap_pairs);
+    if (n <= kSmallSort) return;
+    const unsigned n_tiles = (n + kTile - 1) / kTile;
     const unsigned tile = blockIdx.x * 4 + wib;
     if (tile >= n_tiles) return;
     {   // digit bases: exclusive prefix of the 256 digit totals (lane l owns digits 8 l .. 8 l + 7) + this tile's row offsets
@@ -414,7 +440,7 @@ __global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long 
         for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         unsigned run = incl - s;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { base[wib][8 * lane + j] = run + hist[(size_t)(8 * lane + j) * n_tiles + tile]; run += t[j]; }
+        for (int j = 0; j < 8; ++j) { base[wib][8 * lane + j] = run + hist[(size_t)(8 * lane + j) * cap_tiles + tile]; run += t[j]; }
     }
     __syncwarp();
     const unsigned beg = tile * kTile, end = min(beg + kTile, n);
@@ -442,10 +468,12 @@ __global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long 
 
 // Short lists (a single small scene): one CTA sorts (key, value) in shared memory with a bitonic network instead of 5 x 3 launches of
 // the radix passes.  Keys are distinct (a key encodes both root-to-leaf paths), so stability is not needed.
-constexpr unsigned kSmallSort = 2048;   // beyond a few thousand keys the radix passes win (measured: 6 695 keys, 421 vs 363 us per evaluation)
-__global__ void __launch_bounds__(1024) small_sort_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned n,
+// (may run in place: everything is read into shared memory before anything is written)
+__global__ void __launch_bounds__(1024) small_sort_kernel(const unsigned long long* keys_in, const unsigned* vals_in, const Counters* cnt, unsigned cap_pairs,
                                                           unsigned long long* keys_out, unsigned* vals_out) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
+    const unsigned n = listed_pairs(cnt, cap_pairs);
+    if (n == 0 || n > kSmallSort) return;
     unsigned m = 1;
     while (m < n) m <<= 1;
     unsigned long long* k = reinterpret_cast<unsigned long long*>(sort_smem);
@@ -466,7 +494,9 @@ __global__ void __launch_bounds__(1024) small_sort_kernel(const unsigned long lo
 }
 
 // sorted order -> (prob, a, b) arrays + per-problem segments
-__global__ void gather_sorted_kernel(const int3* __restrict__ pairs, const unsigned* __restrict__ vals, unsigned n, int3* sorted, unsigned* seg_start, unsigned* seg_end) {
+__global__ void gather_sorted_kernel(const int3* __restrict__ pairs, const unsigned* __restrict__ vals, const Counters* cnt, unsigned cap_pairs, int3* sorted,
+                                     unsigned* seg_start, unsigned* seg_end) {
+    const unsigned n = listed_pairs(cnt, cap_pairs);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int3 p = pairs[vals[i]];
         sorted[i] = p;
@@ -653,6 +683,9 @@ struct LargeBuffers {
     double* part = nullptr; size_t cap_part = 0;
     size_t cf2 = 0;
     unsigned epoch = 0;   // traversal counter: tags the donated seeds of one broad_dfs_kernel launch
+    Counters* h_cnt = nullptr;          // pinned copy of the counters of the last traversal
+    bool check_pending = false;         // a traversal has been queued whose counters have not been looked at yet
+    size_t want_frontier = 0, want_pairs = 0;
     unsigned last_n_pairs = 0;
     unsigned long long last_n_tests = 0;
 };
@@ -664,6 +697,7 @@ void large_buffers_destroy(LargeBuffers* b) {
     cudaFree(b->keys[0]); cudaFree(b->keys[1]); cudaFree(b->vals[0]); cudaFree(b->vals[1]); cudaFree(b->hist);
     cudaFree(b->seg_start); cudaFree(b->seg_end); cudaFree(b->unit_start); cudaFree(b->prob_flags);
     cudaFree(b->chunk_out); cudaFree(b->chunk_points); cudaFree(b->part);
+    if (b->h_cnt) cudaFreeHost(b->h_cnt);
     delete b;
 }
 
@@ -693,7 +727,7 @@ void large_exact_view(const LargeBuffers* b, const LargeScene& ls, long long n_e
     ps.sorted = b->sorted; ps.seg_start = b->seg_start; ps.seg_end = b->seg_end; ps.unit_start = b->unit_start;
     ps.n_units = b->cnt ? &b->cnt->n_units : nullptr;
     ps.large_ins = ls.large_ins; ps.n_large = ls.n_large;
-    ps.max_large_units = (size_t)(b->last_n_pairs / kChunk) + (size_t)(n_env * ls.n_large) + 1;
+    ps.max_large_units = (size_t)(b->cap_pairs / kChunk) + (size_t)(n_env * ls.n_large) + 1;
 }
 const unsigned* large_seg_start_ptr(const LargeBuffers* b) { return b->seg_start; }
 
@@ -716,23 +750,24 @@ cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const E
     return cudaGetLastError();
 }
 
-// Broad phase + sort + segments.  Synchronises once (reads the pair count) so that capacities can
-// grow like the reference's VectorCache (src/obb/vector_cache.jl:11-15): on overflow the buffers are
-// doubled and the traversal is re-run.
+// Broad phase + sort + segments, queued on the stream WITHOUT a host round trip: the pair count stays on the device (every later kernel
+// reads it from the counters), grids are sized for the buffers' capacity.  The capacities grow like the reference's VectorCache
+// (src/obb/vector_cache.jl:11-15), but after the fact: the counters are copied to pinned memory behind the traversal, the caller
+// synchronises once at the END of the evaluation it queued and asks large_check(), which doubles what overflowed and tells the caller
+// to queue the evaluation again.
 cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream, int* n_launches,
                               int hash_rank, int hash_world) {
     const long long n_prob_ll = io.n_env * ls.n_large;
     if (n_prob_ll <= 0) return cudaSuccess;
     if (n_prob_ll > (1LL << 30)) return cudaErrorInvalidValue;
     const unsigned n_prob = (unsigned)n_prob_ll;
-    {   // the sort key is (problem, DFS key) in one 64-bit word: both parts must fit, or problems would alias
-        int prob_bits = 0;
-        while ((1ull << prob_bits) < (unsigned long long)n_prob) ++prob_bits;
-        if (ls.key_bits + prob_bits > 64) return cudaErrorMemoryAllocation;   // -> PFC_E_CAPACITY
-    }
+    int prob_bits = 0;
+    while ((1ull << prob_bits) < (unsigned long long)n_prob) ++prob_bits;
+    if (ls.key_bits + prob_bits > 64) return cudaErrorMemoryAllocation;   // (problem, DFS key) must fit one 64-bit sort key -> PFC_E_CAPACITY
     if (!b->cnt) LCU(cudaMalloc(&b->cnt, sizeof(Counters)));
-    size_t want_frontier = std::max<size_t>(b->cap_frontier, std::max<size_t>(1u << 18, (size_t)n_prob * 4));
-    size_t want_pairs = std::max<size_t>(b->cap_pairs, 1u << 20);
+    if (!b->h_cnt) LCU(cudaHostAlloc(reinterpret_cast<void**>(&b->h_cnt), sizeof(Counters), cudaHostAllocDefault));
+    b->want_frontier = std::max<size_t>(b->want_frontier, std::max<size_t>(std::max<size_t>(b->cap_frontier, 1u << 18), (size_t)n_prob * 4));
+    b->want_pairs = std::max<size_t>(b->want_pairs, std::max<size_t>(b->cap_pairs, 1u << 20));
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     // the traversal kernel is persistent: every block must be resident, because idle warps wait for donated work
@@ -746,6 +781,9 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
             if (sl.blocks < 1) sl.blocks = 1;
         }
         dfs_blocks_per_sm = sl.blocks;
+        struct TagSort {};
+        LaunchSlot& ss = launch_slot<TagSort>();
+        if (ss.key0 != 1) { LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12))); ss.key0 = 1; }
     }
     const int dfs_blocks = n_sm * dfs_blocks_per_sm;
     // BFS levels until about one seed per resident warp could exist (4^L * n_prob >= target); donation balances the rest
@@ -754,85 +792,80 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     // split over several GPUs: a contact patch is small against the meshes, so a few sub-trees carry nearly all of the work; three more
     // breadth-first levels make the hash-partitioned pieces ~64x finer, which is what balances the ranks (inside a GPU, donation does)
     if (hash_world > 1) levels = std::min(levels + 3, 14);
-    bool done = false;
-    for (int attempt = 0; attempt < 12 && !done; ++attempt) {
-        LCU(ensure(b->frontier[0], b->cap_frontier, want_frontier));
-        LCU(ensure(b->frontier[1], b->cf2, want_frontier));
-        LCU(ensure(b->pairs, b->cap_pairs, want_pairs));
-        init_frontier_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(ls, io.n_env, b->frontier[0], b->cnt);
-        int src = 0;
-        for (int l = 0; l < levels; ++l) {
-            if (l > 0) { /* the level's output counter must start at zero */ }
-            broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, ls, io.X, b->frontier[src], b->frontier[src ^ 1], src, (unsigned)b->cap_frontier, b->pairs,
-                                                         (unsigned)b->cap_pairs, b->cnt, (unsigned)hash_rank, (unsigned)hash_world);
-            // reset the consumed frontier's counter for its next use as an output
-            LCU(cudaMemsetAsync(&b->cnt->frontier_n[src], 0, sizeof(unsigned), stream));
-            src ^= 1;
-        }
-        dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, src);
-        broad_dfs_kernel<<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs, b->cnt,
-                                                                  (unsigned)hash_rank, (unsigned)hash_world);
-        if (n_launches) *n_launches += 3 + levels;
-        Counters h;
-        LCU(cudaMemcpyAsync(&h, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        LCU(cudaStreamSynchronize(stream));
-        if (h.overflow & 4u) return cudaErrorAssert;
-        if (h.overflow & 1u) { want_frontier = std::max<size_t>(want_frontier * 2, (size_t)std::max(h.frontier_n[0], std::max(h.frontier_n[1], h.q_tail)) + 1024); continue; }
-        if (h.overflow & 2u) { want_pairs = std::max<size_t>(want_pairs * 2, (size_t)h.n_pairs + 1024); continue; }
-        b->last_n_pairs = h.n_pairs;
-        b->last_n_tests = h.n_tests;
-        done = true;
-    }
-    if (!done) return cudaErrorMemoryAllocation;   // every attempt overflowed: an error, not a truncated list (-> PFC_E_CAPACITY)
-    const unsigned n = b->last_n_pairs;
-    // segments + keys + sort
+    LCU(ensure(b->frontier[0], b->cap_frontier, b->want_frontier));
+    LCU(ensure(b->frontier[1], b->cf2, b->want_frontier));
+    LCU(ensure(b->pairs, b->cap_pairs, b->want_pairs));
+    const size_t cap = b->cap_pairs;
+    LCU(ensure(b->keys[0], b->cap_keys, cap)); LCU(ensure(b->keys[1], b->cap_keys2, cap));
+    LCU(ensure(b->vals[0], b->cap_vals, cap)); LCU(ensure(b->vals[1], b->cap_vals2, cap));
+    LCU(ensure(b->sorted, b->cap_sorted, cap));
+    const unsigned cap_tiles = (unsigned)((cap + kTile - 1) / kTile);
+    LCU(ensure(b->hist, b->cap_hist, (size_t)256 * cap_tiles + 256));   // + the 256 digit totals
     LCU(ensure(b->seg_start, b->cap_seg, (size_t)n_prob + 1));
     LCU(ensure(b->seg_end, b->cap_seg2, (size_t)n_prob + 1));
     LCU(ensure(b->unit_start, b->cap_unit, (size_t)n_prob + 2));
     LCU(ensure(b->prob_flags, b->cap_pf, (size_t)n_prob));
+    // ---- traversal
+    init_frontier_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(ls, io.n_env, b->frontier[0], b->cnt);
+    int src = 0;
+    for (int l = 0; l < levels; ++l) {
+        broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, ls, io.X, b->frontier[src], b->frontier[src ^ 1], src, (unsigned)b->cap_frontier, b->pairs,
+                                                     (unsigned)b->cap_pairs, b->cnt, (unsigned)hash_rank, (unsigned)hash_world);
+        // reset the consumed frontier's counter for its next use as an output
+        LCU(cudaMemsetAsync(&b->cnt->frontier_n[src], 0, sizeof(unsigned), stream));
+        src ^= 1;
+    }
+    dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, src);
+    broad_dfs_kernel<<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs, b->cnt,
+                                                              (unsigned)hash_rank, (unsigned)hash_world);
+    LCU(cudaMemcpyAsync(b->h_cnt, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));   // read by large_check() after the caller's synchronisation
+    b->check_pending = true;
+    if (n_launches) *n_launches += 3 + levels;
+    // ---- segments + keys + sort (n on the device)
     init_segments_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(b->seg_start, b->seg_end, n_prob);
     zero_int_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(b->prob_flags, n_prob);
-    if (n_launches) *n_launches += 2;
-    if (n > 0) {
-        LCU(ensure(b->keys[0], b->cap_keys, (size_t)n)); LCU(ensure(b->keys[1], b->cap_keys2, (size_t)n));
-        LCU(ensure(b->vals[0], b->cap_vals, (size_t)n)); LCU(ensure(b->vals[1], b->cap_vals2, (size_t)n));
-        LCU(ensure(b->sorted, b->cap_sorted, (size_t)n));
-        const unsigned n_tiles = (n + kTile - 1) / kTile;
-        LCU(ensure(b->hist, b->cap_hist, (size_t)256 * n_tiles + 256));   // + the 256 digit totals
-        unsigned* tot = b->hist + (size_t)256 * n_tiles;
-        const unsigned g = std::min<unsigned>((n + 255) / 256, (unsigned)n_sm * 16);
-        build_keys_kernel<<<g, 256, 0, stream>>>(sc, ls, b->pairs, n, b->keys[0], b->vals[0]);
-        int prob_bits = 0;
-        while ((1ull << prob_bits) < (unsigned long long)n_prob) ++prob_bits;
-        const int total_bits = ls.key_bits + prob_bits;
-        int cur = 0;
-        if (n <= kSmallSort) {
-            unsigned m = 1;
-            while (m < n) m <<= 1;
-            const size_t smem = (size_t)m * (sizeof(unsigned long long) + sizeof(unsigned));
-            {
-                struct Tag {};
-                std::lock_guard<std::mutex> g(launch_mutex());
-                LaunchSlot& sl = launch_slot<Tag>();
-                if (sl.key0 != 1) { LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12))); sl.key0 = 1; }
-            }
-            small_sort_kernel<<<1, 1024, smem, stream>>>(b->keys[0], b->vals[0], n, b->keys[1], b->vals[1]);
-            cur = 1;
-            if (n_launches) *n_launches += 1;
-        } else
-        for (int shift = 0; shift < total_bits; shift += 8) {
-            radix_hist_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], n, shift, b->hist, n_tiles);
-            radix_rowscan_kernel<<<256, 256, 0, stream>>>(b->hist, n_tiles, tot);
-            radix_scatter_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->vals[cur], n, shift, b->hist, tot, n_tiles, b->keys[cur ^ 1], b->vals[cur ^ 1]);
-            cur ^= 1;
-            if (n_launches) *n_launches += 3;
-        }
-        gather_sorted_kernel<<<g, 256, 0, stream>>>(b->pairs, b->vals[cur], n, b->sorted, b->seg_start, b->seg_end);
-        if (n_launches) *n_launches += 2;
+    unsigned* tot = b->hist + (size_t)256 * cap_tiles;
+    const unsigned g = std::min<unsigned>((unsigned)((cap + 255) / 256), (unsigned)n_sm * 16);
+    build_keys_kernel<<<g, 256, 0, stream>>>(sc, ls, b->pairs, b->cnt, (unsigned)cap, b->keys[0], b->vals[0]);
+    const int total_bits = ls.key_bits + prob_bits;
+    const int n_pass = (total_bits + 7) / 8;
+    const int fin = n_pass & 1;   // where the radix passes leave the sorted keys; short lists are sorted into the same buffer by one CTA
+    int cur = 0;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        radix_hist_kernel<<<(cap_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->cnt, (unsigned)cap, 8 * pass, b->hist, cap_tiles);
+        radix_rowscan_kernel<<<256, 256, 0, stream>>>(b->hist, b->cnt, (unsigned)cap, cap_tiles, tot);
+        radix_scatter_kernel<<<(cap_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->vals[cur], b->cnt, (unsigned)cap, 8 * pass, b->hist, tot, cap_tiles, b->keys[cur ^ 1],
+                                                                    b->vals[cur ^ 1]);
+        cur ^= 1;
     }
+    small_sort_kernel<<<1, 1024, kSmallSort * 12, stream>>>(b->keys[0], b->vals[0], b->cnt, (unsigned)cap, b->keys[fin], b->vals[fin]);
+    gather_sorted_kernel<<<g, 256, 0, stream>>>(b->pairs, b->vals[fin], b->cnt, (unsigned)cap, b->sorted, b->seg_start, b->seg_end);
     units_scan_kernel<<<1, 1024, 0, stream>>>(b->seg_start, b->seg_end, n_prob, b->unit_start, b->cnt, 0, 1);
-    if (n_launches) *n_launches += 1;
+    if (n_launches) *n_launches += 6 + 3 * n_pass;
     return cudaGetLastError();
+}
+
+// After the caller synchronised the stream: did the traversal queued by the last large_broad_phase fit its buffers?
+// 0 = yes; 1 = no, the capacities have been raised and the evaluation must be queued again; -1 = it cannot fit.
+int large_check(LargeBuffers* b) {
+    if (!b || !b->check_pending) return 0;
+    b->check_pending = false;
+    const Counters& h = *b->h_cnt;
+    if (h.overflow & 4u) return -1;
+    bool again = false;
+    if (h.overflow & 1u) {
+        const size_t need = (size_t)std::max(h.frontier_n[0], std::max(h.frontier_n[1], h.q_tail)) + 1024;
+        b->want_frontier = std::max<size_t>(b->cap_frontier * 2, need);
+        again = true;
+    }
+    if (h.overflow & 2u) {
+        b->want_pairs = std::max<size_t>(b->cap_pairs * 2, (size_t)h.n_pairs + 1024);   // the counter kept counting: the need is known
+        again = true;
+    }
+    if (again) return (b->want_pairs > (1ull << 31) || b->want_frontier > (1ull << 31)) ? -1 : 1;
+    b->last_n_pairs = h.n_pairs;
+    b->last_n_tests = h.n_tests;
+    return 0;
 }
 
 // Narrow phase + friction + reduction of the regularized instructions over the pair lists produced by large_broad_phase.
@@ -842,8 +875,7 @@ cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const E
                                cudaStream_t stream, int* n_launches) {
     const unsigned n_prob = (unsigned)(io.n_env * ls.n_large);
     if (n_prob == 0) return cudaSuccess;
-    const unsigned n = b->last_n_pairs;
-    const size_t max_units = (size_t)(n / kChunk) + n_prob + 1;
+    const size_t max_units = (size_t)(b->cap_pairs / kChunk) + n_prob + 1;   // (the pair count itself stays on the device)
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     LCU(ensure(b->chunk_out, b->cap_chunk, max_units * kNA));

@@ -30,6 +30,9 @@ cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const E
                                cudaStream_t stream, int* n_launches);
 struct ExactPairs;
 void large_exact_view(const LargeBuffers* b, const LargeScene& ls, long long n_env, ExactPairs& ps);
+// after the caller's stream synchronisation: 0 = the last traversal fit its buffers, 1 = it did not (capacities raised: queue the evaluation
+// again), -1 = it cannot fit
+int large_check(LargeBuffers* b);
 cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream);
 unsigned large_last_pairs(const LargeBuffers* b);
 unsigned long long large_last_tests(const LargeBuffers* b);

@@ -120,7 +120,7 @@ __global__ void refit_leaves_kernel(int kind, long long n_node, NodeRec* nodes, 
                                     const double* __restrict__ xyz, double* aabb) {
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_node; k += (long long)gridDim.x * blockDim.x) {
         NodeRec& nd = nodes[k];
-        if (nd.left >= 0) continue;
+        if (nd.kind >= 0) continue;
         const int prim = nd.right;
         const int w = kind == 0 ? 3 : 4;
         double p[4][3], ev[4] = {0, 0, 0, 0};
@@ -151,7 +151,7 @@ __global__ void refit_level_kernel(const int* __restrict__ level_nodes, int n, N
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const int k = level_nodes[t];
         NodeRec& nd = nodes[k];
-        const double* A = aabb + 6 * (long long)nd.left;
+        const double* A = aabb + 6 * (long long)(k + 1);   // pre-order: child 1 is the next record
         const double* B = aabb + 6 * (long long)nd.right;
         for (int i = 0; i < 3; ++i) {
             const double c1 = (A[3 + i] + A[i]) * 0.5, e1 = (A[3 + i] - A[i]) * 0.5, c2 = (B[3 + i] + B[i]) * 0.5, e2 = (B[3 + i] - B[i]) * 0.5;
@@ -160,6 +160,7 @@ __global__ void refit_level_kernel(const int* __restrict__ level_nodes, int n, N
             nd.c[i] = (hi + lo) * 0.5; nd.e[i] = (hi - lo) * 0.5;
             nd.R[3 * i] = i == 0 ? 1.0 : 0.0; nd.R[3 * i + 1] = i == 1 ? 1.0 : 0.0; nd.R[3 * i + 2] = i == 2 ? 1.0 : 0.0;
         }
+        nd.kind = kNodeInternalAabb;
     }
 }
 

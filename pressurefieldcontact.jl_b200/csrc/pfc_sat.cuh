@@ -16,7 +16,19 @@ namespace pfc {
 // M = inv(OBB_a) * X_a_b : the part of the composition that depends on node a only.
 struct SatA { double R[9]; double t[3]; double e[3]; };
 
-PFC_D void sat_prepare_a(const NodeRec& a, const double* __restrict__ Rab, const double* __restrict__ tab, SatA& out) {
+// Axis-aligned nodes (kind == kNodeInternalAabb: R == I exactly).  The reference multiplies by the identity all the same; with R = I every
+// product is x * 1 or x * (+-0) and every sum is x + (+-0), so the composed entries are the operands themselves -- bit for bit for finite
+// inputs, up to the sign of a zero, which neither fabs() nor '<' can see.  The identity products are therefore skipped (AABB = false keeps
+// the general path: tests/test_device_sat_on_host.py checks that both give the same boolean everywhere).
+template <bool AABB = true> PFC_D void sat_prepare_a(const NodeRec& a, const double* __restrict__ Rab, const double* __restrict__ tab, SatA& out) {
+    if (AABB && a.kind == kNodeInternalAabb) {   // inv(OBB_a) = [I, -c]
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out.R[k] = Rab[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out.t[i] = add_(tab[i], -a.c[i]);
+        out.e[0] = a.e[0]; out.e[1] = a.e[1]; out.e[2] = a.e[2];
+        return;
+    }
     // i_dh_a = [a.R' , (-a.R') * a.c]
     double mt[3];
 #pragma unroll
@@ -33,13 +45,15 @@ PFC_D void sat_prepare_a(const NodeRec& a, const double* __restrict__ Rab, const
 }
 
 // Rab/tab: row-major rotation and translation of x_r1_r2 (frame of tree 2 expressed in tree 1).
-PFC_D bool sat_test(const SatA& A, const NodeRec& b) {
+template <bool AABB = true> PFC_D bool sat_test(const SatA& A, const NodeRec& b) {
     double R[9], aR[9], t[3];
+    const bool b_aabb = AABB && b.kind == kNodeInternalAabb;   // OBB_b = [I, c]: the rotation product is the left operand itself
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            R[3 * i + j] = add_(add_(mul_(A.R[3 * i], b.R[0 + j]), mul_(A.R[3 * i + 1], b.R[3 + j])), mul_(A.R[3 * i + 2], b.R[6 + j]));
+            R[3 * i + j] = b_aabb ? A.R[3 * i + j]
+                                  : add_(add_(mul_(A.R[3 * i], b.R[0 + j]), mul_(A.R[3 * i + 1], b.R[3 + j])), mul_(A.R[3 * i + 2], b.R[6 + j]));
             aR[3 * i + j] = add_(fabs(R[3 * i + j]), 1.0e-14);
         }
         t[i] = add_(add_(add_(mul_(A.R[3 * i], b.c[0]), mul_(A.R[3 * i + 1], b.c[1])), mul_(A.R[3 * i + 2], b.c[2])), A.t[i]);

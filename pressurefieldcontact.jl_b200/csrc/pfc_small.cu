@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
                 SatA A;
                 sat_prepare_a(a, xf + 12 * q, xf + 12 * q + 9, A);
                 int code = 0;
-                if (sat_test(A, b)) code = (a.left < 0) ? ((b.left < 0) ? 1 : 2) : ((b.left < 0) ? 3 : 4);
+                if (sat_test(A, b)) code = (a.kind < 0) ? ((b.kind < 0) ? 1 : 2) : ((b.kind < 0) ? 3 : 4);
                 res[c] = (unsigned char)code;
             }
             __syncwarp();
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
                             const InsDev& ins = sc.ins[s_ins[q]];
                             const NodeRec& a = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base1 + ia));
                             const NodeRec& b = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base2 + ib));
-                            const int al = a.left, ar = a.right, bl = b.left, br = b.right;
+                            const int al = ia + 1, ar = a.right, bl = ib + 1, br = b.right;   // pre-order: child 1 is the next record
                             if (code == 1) { cnt = 1; ch0 = kDone | enc(ar, br); }
                             else if (code == 2) { cnt = ocnt = 2; ch0 = enc(ia, bl); ch1 = enc(ia, br); }
                             else if (code == 3) { cnt = ocnt = 2; ch0 = enc(al, ib); ch1 = enc(ar, ib); }

@@ -14,12 +14,17 @@
 
 namespace pfc {
 
+// Trees are stored PRE-ORDER (pfc_add_mesh re-flattens them), so child 1 of an internal node is the next record and needs no link.
+// Internal nodes are axis-aligned boxes merged from their children (R = I, src/obb/box_types.jl:11-15); only leaves carry a fitted
+// rotation.  The first 64 B of a record hold everything an axis-aligned node needs: the traversal loads the second half (the rest of
+// R) only for nodes whose kind says the rotation is not the identity.
+enum { kNodeLeaf = -1, kNodeInternal = 0, kNodeInternalAabb = 1 };
 struct NodeRec {
-    double R[9];   // row-major: R[3*i+j]
     double c[3];
     double e[3];
-    int32_t left;  // mesh-local node index of child 1, or -1 for a leaf
+    int32_t kind;  // kNodeLeaf, or kNodeInternal / kNodeInternalAabb (R == I exactly); child 1 of an internal node is this node + 1
     int32_t right; // mesh-local node index of child 2, or the 0-based primitive id for a leaf
+    double R[9];   // row-major: R[3*i+j]
 };
 static_assert(sizeof(NodeRec) == 128, "NodeRec must be one 128 B line");
 

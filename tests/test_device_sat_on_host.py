@@ -63,13 +63,19 @@ static bool oracle_says(const Case& c, double s) {
 static bool device_says(const Case& c, double s) {
     const double tab[3] = {s * c.dir[0], s * c.dir[1], s * c.dir[2]};
     pfc::SatA A;
-    pfc::sat_prepare_a(c.a, c.Rab, tab, A);
+    pfc::sat_prepare_a(c.a, c.Rab, tab, A);      // nodes flagged kNodeInternalAabb take the path that skips the identity products
     return pfc::sat_test(A, c.b);
+}
+static bool device_general_says(const Case& c, double s) {   // the same boxes through the general path (every product evaluated)
+    const double tab[3] = {s * c.dir[0], s * c.dir[1], s * c.dir[2]};
+    pfc::SatA A;
+    pfc::sat_prepare_a<false>(c.a, c.Rab, tab, A);
+    return pfc::sat_test<false>(A, c.b);
 }
 
 int main(int argc, char** argv) {
     const long n_case = argc > 1 ? atol(argv[1]) : 20000;
-    long bad = 0, n_eval = 0, n_boundary = 0, n_true = 0;
+    long bad = 0, n_eval = 0, n_boundary = 0, n_true = 0, n_aabb = 0, bad_special = 0;
     for (long k = 0; k < n_case; ++k) {
         Case c;
         std::memset(&c, 0, sizeof c);
@@ -77,10 +83,18 @@ int main(int argc, char** argv) {
         if (k % 5 == 0) { const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; std::memcpy(c.b.R, I, sizeof I); std::memcpy(c.Rab, I, sizeof I); std::memcpy(c.a.R, I, sizeof I); }   // axis-aligned: parallel edges, the 1e-14 guard decides
         for (int i = 0; i < 3; ++i) { c.a.c[i] = 0.2 * u(g); c.b.c[i] = 0.2 * u(g); c.a.e[i] = 0.05 + u01(g); c.b.e[i] = 0.05 + u01(g); c.dir[i] = u(g); }
         if (k % 7 == 0) c.b.e[k % 3] = 0.0;   // flat box (a triangle's leaf box)
+        // axis-aligned internal nodes (what the trees' internal boxes are): a, b or both carry R = I and the kind that lets the device skip
+        // the identity products; centres with +-0.0 and denormal components, a translation direction with a zero component
+        const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (k % 3 == 1 || k % 5 == 0) { std::memcpy(c.a.R, I9, sizeof I9); c.a.kind = pfc::kNodeInternalAabb; }
+        if (k % 3 == 2 || k % 5 == 0) { std::memcpy(c.b.R, I9, sizeof I9); c.b.kind = pfc::kNodeInternalAabb; }
+        if (k % 11 == 0) { c.a.c[k % 3] = (k % 2) ? 0.0 : -0.0; c.b.c[(k + 1) % 3] = 4.9e-324; c.dir[(k + 2) % 3] = 0.0; }
+        n_aabb += (c.a.kind == pfc::kNodeInternalAabb) || (c.b.kind == pfc::kNodeInternalAabb);
         auto check = [&](double s) {
             const bool o = oracle_says(c, s), d = device_says(c, s);
             ++n_eval; n_true += o;
             if (o != d && bad++ < 5) std::printf("case %ld at s = %.17g: oracle %d device %d\n", k, s, (int)o, (int)d);
+            if (d != device_general_says(c, s) && bad_special++ < 5) std::printf("case %ld at s = %.17g: the axis-aligned path and the general path differ\n", k, s);
         };
         for (int r = 0; r < 4; ++r) check(4.0 * u01(g));
         // bisect the flip along dir
@@ -92,8 +106,9 @@ int main(int argc, char** argv) {
         for (int r = 0; r < 4; ++r) s = std::nextafter(s, 0.0);
         for (int r = 0; r < 9; ++r) { check(s); s = std::nextafter(s, 32.0); }
     }
-    std::printf("cases %ld evaluations %ld boundaries %ld overlapping %ld bad %ld\n", n_case, n_eval, n_boundary, n_true, bad);
-    return bad != 0;
+    std::printf("cases %ld evaluations %ld boundaries %ld overlapping %ld bad %ld axis_aligned_cases %ld bad_special %ld\n", n_case, n_eval, n_boundary, n_true, bad, n_aabb,
+                bad_special);
+    return bad != 0 || bad_special != 0;
 }
 """
 
@@ -109,6 +124,6 @@ def test_device_sat_boolean_equals_oracle_everywhere(tmp_path):
     sys.stdout.write(out.stdout)
     assert out.returncode == 0, out.stdout[-2000:]
     f = out.stdout.split()
-    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("evaluations", "boundaries", "overlapping", "bad")}
-    assert stats["bad"] == 0
+    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("evaluations", "boundaries", "overlapping", "bad", "axis_aligned_cases", "bad_special")}
+    assert stats["bad"] == 0 and stats["bad_special"] == 0 and stats["axis_aligned_cases"] > 10000
     assert stats["boundaries"] > 10000 and stats["evaluations"] > 150000 and 0 < stats["overlapping"] < stats["evaluations"]
