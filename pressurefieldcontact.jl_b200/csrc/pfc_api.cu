@@ -409,6 +409,12 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
         c->large_scene.leaf_depth = c->d_leaf_depth.p;
         c->large_scene.n_large = int(large.size());
         c->large_scene.key_bits = large_key_bits;
+        c->large_scene.max_leaves = 0;
+        c->large_scene.max_depth = 0;
+        for (int32_t k : large) {
+            c->large_scene.max_leaves = std::max(c->large_scene.max_leaves, std::max(c->h_ins[k].n_leaf1, c->h_ins[k].n_leaf2));
+            c->large_scene.max_depth = std::max(c->large_scene.max_depth, std::max(c->mesh[c->ins[k].mesh_1].depth, c->mesh[c->ins[k].mesh_2].depth));
+        }
         if (!c->large_buf) c->large_buf = large_buffers_create();
     }
     CU(c->d_nodes.ensure(nodes.size()));

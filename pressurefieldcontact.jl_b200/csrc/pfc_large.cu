@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "pfc_exact.h"
@@ -51,8 +52,10 @@ constexpr int kChunk = 256;       // pairs per reduction chunk (= narrow kernel 
 constexpr int kNA = 6;            // accumulator slots per chunk partial (regularized wrench)
 static_assert(kLargePartStride == kNA + 2, "partial record = kNA sums + point count + pair count");
 
+constexpr int kMaxLevels = 132;   // breadth-first levels at most: two trees of depth <= 62 plus the roots (pfc_add_mesh rejects deeper trees)
 struct Counters {                 // device-resident
-    unsigned int frontier_n[2];   // BFS ping-pong frontier sizes
+    unsigned int frontier_max;    // largest frontier any breadth-first level asked for (sizes the buffers of a repeated evaluation)
+    unsigned int pad_a;
     unsigned int seed_head;       // next seed to hand out
     unsigned int n_pairs;         // leaf pairs appended
     unsigned int overflow;        // bit0 frontier, bit1 pairs, bit2 stack
@@ -64,6 +67,7 @@ struct Counters {                 // device-resident
     int outstanding;              //             seeds queued or being traversed; 0 = traversal finished
     unsigned long long n_tests;   // node pairs tested (statistics)
     unsigned long long n_donated; // seeds donated (statistics)
+    unsigned int level_n[kMaxLevels + 2];   // frontier size of every breadth-first level (level 0 = the root pairs)
 };
 
 // prob = index into the large-problem list; a, b mesh-local node ids; tag = traversal epoch for donated seeds (0 otherwise).
@@ -138,7 +142,9 @@ __global__ void init_frontier_kernel(LargeScene ls, long long n_env, Seed* front
     const long long n = n_env * ls.n_large;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) frontier[p] = Seed{(int)p, 0u, 0, 0};
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        cnt->frontier_n[0] = (unsigned)n; cnt->frontier_n[1] = 0; cnt->seed_head = 0; cnt->n_pairs = 0; cnt->overflow = 0; cnt->n_units = 0;
+        cnt->frontier_max = (unsigned)n; cnt->seed_head = 0; cnt->n_pairs = 0; cnt->overflow = 0; cnt->n_units = 0;
+        cnt->level_n[0] = (unsigned)n;
+        for (int l = 1; l < kMaxLevels + 2; ++l) cnt->level_n[l] = 0;
         cnt->n_tests = 0; cnt->n_donated = 0; cnt->q_head = 0; cnt->q_tail = 0; cnt->n_seed0 = 0; cnt->outstanding = 0;
     }
 }
@@ -159,15 +165,23 @@ PFC_D unsigned item_hash(int prob, int a, int b) {
 }
 
 __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, const Seed* __restrict__ in, Seed* out,
-                                                        int src, unsigned cap_frontier, int3* pairs, unsigned cap_pairs, Counters* cnt,
+                                                        int level, int split_level, unsigned cap_frontier, int3* pairs, unsigned cap_pairs, Counters* cnt,
                                                         unsigned hrank, unsigned hworld) {
-    const unsigned n = cnt->frontier_n[src];
+    const unsigned n_raw = cnt->level_n[level];
+    const unsigned n = n_raw < cap_frontier ? n_raw : cap_frontier;   // (an overflowing level is cut short; the host repeats the evaluation)
+    if (n == 0) return;
     const int lane = threadIdx.x & 31;
+    // Multi-GPU split: up to split_level every rank expands the same frontier; AT split_level a rank keeps only the children (sub-trees)
+    // whose hash falls on it; below, everything in its frontier is its own.  Leaf pairs found on the shared levels go to the rank their
+    // own hash names.
+    const bool shared = hworld > 1u && level <= split_level;
+    unsigned long long tests = 0;
     for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
         const unsigned i = base + lane;
         int r = 0;
         int2 ch[4];
         Seed s{};
+        bool split = false;
         if (i < n) {
             s = in[i];
             long long env; int k;
@@ -175,19 +189,27 @@ __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene 
             double Rab[9], tab[3];
             broad_xform_l(X + 16 * (env * sc.n_ins + k), Rab, tab);
             r = expand_pair(sc, sc.ins[k], Rab, tab, s.a, s.b, ch);
+            ++tests;
+            split = shared && prob_is_split(sc, ls, s.prob);
         }
         // warp-aggregated appends
-        const int n_child = r > 0 ? r : 0;
+        int n_child = r > 0 ? r : 0;
+        if (split && level == split_level) {   // keep this rank's sub-trees only
+            int kept = 0;
+            for (int c = 0; c < n_child; ++c)
+                if (item_hash(s.prob, ch[c].x, ch[c].y) % hworld == hrank) ch[kept++] = ch[c];
+            n_child = kept;
+        }
         int incl = n_child;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         const int tot = __shfl_sync(0xffffffffu, incl, 31);
         unsigned at = 0;
-        if (lane == 31 && tot > 0) at = atomicAdd(&cnt->frontier_n[src ^ 1], (unsigned)tot);
+        if (lane == 31 && tot > 0) { at = atomicAdd(&cnt->level_n[level + 1], (unsigned)tot); atomicMax(&cnt->frontier_max, at + (unsigned)tot); }
         at = __shfl_sync(0xffffffffu, at, 31) + incl - n_child;
         if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, 0u, ch[c].x, ch[c].y}; }
         else if (n_child > 0) atomicOr(&cnt->overflow, 1u);
-        const bool emit = r < 0 && (hworld == 1u || !prob_is_split(sc, ls, s.prob) || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
+        const bool emit = r < 0 && (!split || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
         const unsigned leaf_mask = __ballot_sync(0xffffffffu, emit);
         if (leaf_mask) {
             unsigned pat = 0;
@@ -196,18 +218,23 @@ __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene 
             if (emit) { if (pat < cap_pairs) pairs[pat] = make_int3(s.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u); }
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, o);
+    if (lane == 0 && tests) atomicAdd(&cnt->n_tests, tests);
 }
 
 // the seeds the breadth-first levels left in frontier[src] become the initial content of the queue
-__global__ void dfs_queue_init_kernel(Counters* cnt, int src) {
-    const unsigned n = cnt->frontier_n[src];
+__global__ void dfs_queue_init_kernel(Counters* cnt, int level, unsigned cap_frontier) {
+    const unsigned n_raw = cnt->level_n[level];
+    const unsigned n = n_raw < cap_frontier ? n_raw : cap_frontier;
     cnt->q_head = 0; cnt->q_tail = n; cnt->n_seed0 = n; cnt->outstanding = (int)n;
 }
 
 PFC_D unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
 
 // K1b: warp-cooperative stack-based traversal of the seeds, with work donation
-__global__ void __launch_bounds__(kDfsWarps * 32) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, Seed* seeds, unsigned cap_seeds,
+template <int MINB>
+__global__ void __launch_bounds__(kDfsWarps * 32, MINB) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, Seed* seeds, unsigned cap_seeds,
                                                                    unsigned epoch, int3* pairs, unsigned cap_pairs, Counters* cnt, unsigned hrank,
                                                                    unsigned hworld) {
     __shared__ int2 stack_mem[kDfsWarps][kStackCap];   // per-warp circular stack: entry i lives at (base + i) & (kStackCap - 1)
@@ -771,13 +798,14 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     // the traversal kernel is persistent: every block must be resident, because idle warps wait for donated work
+    static const int dfs_minb = getenv("PFC_DFS_MINB") ? atoi(getenv("PFC_DFS_MINB")) : 1;   // (experiment switch)
     int dfs_blocks_per_sm = 0;
     {
         struct Tag {};
         std::lock_guard<std::mutex> g(launch_mutex());
         LaunchSlot& sl = launch_slot<Tag>();
         if (sl.blocks == 0) {
-            LCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sl.blocks, broad_dfs_kernel, kDfsWarps * 32, 0));
+            LCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sl.blocks, dfs_minb == 4 ? broad_dfs_kernel<4> : (dfs_minb == 3 ? broad_dfs_kernel<3> : broad_dfs_kernel<1>), kDfsWarps * 32, 0));
             if (sl.blocks < 1) sl.blocks = 1;
         }
         dfs_blocks_per_sm = sl.blocks;
@@ -786,12 +814,24 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
         if (ss.key0 != 1) { LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12))); ss.key0 = 1; }
     }
     const int dfs_blocks = n_sm * dfs_blocks_per_sm;
-    // BFS levels until about one seed per resident warp could exist (4^L * n_prob >= target); donation balances the rest
+    // How the dual-tree recursion is walked.  Big scenes: LEVEL BY LEVEL to the leaves -- one launch per level of the recursion, one thread
+    // per node pair of the level's frontier, children appended to the next frontier with warp-aggregated atomics.  Every lane of the
+    // machine works on a node pair whatever the shape of the contact (a few instructions out of thousands carry all of the work in a
+    // pile; a contact patch is a small corner of two big trees), which the per-warp stacks of the depth-first kernel cannot offer: measured
+    // on the 64-body pile 1.78 ms (stack traversal from the root pairs, work donated between warps) against the level-by-level walk.
+    // The order the pairs are found in does not matter: the sort below restores the reference's order.
+    // Small scenes (one gripper pad against another): a few levels to get one seed per resident warp, then the stack traversal in
+    // ONE launch -- a launch per level would cost more than the work.
+    const bool by_level = ls.max_leaves >= 16384 || n_prob >= 64;
     int levels = 0;
     { double f = (double)n_prob; const double target = 1.0 * dfs_blocks * kDfsWarps; while (f < target && levels < 12) { f *= 4.0; ++levels; } }
     // split over several GPUs: a contact patch is small against the meshes, so a few sub-trees carry nearly all of the work; three more
-    // breadth-first levels make the hash-partitioned pieces ~64x finer, which is what balances the ranks (inside a GPU, donation does)
+    // breadth-first levels make the hash-partitioned pieces ~64x finer, which is what balances the ranks
     if (hash_world > 1) levels = std::min(levels + 3, 14);
+    const int split_level = levels - 1;             // the level whose children are dealt to the ranks by hash
+    // (a level descends both trees until one of them is at a leaf, then the other alone: a leaf pair at depths (d1, d2) is reached at
+    // level max(d1, d2), so max_depth + 1 levels test every pair of the recursion)
+    if (by_level) levels = std::max(levels, std::min(ls.max_depth + 1, kMaxLevels));
     LCU(ensure(b->frontier[0], b->cap_frontier, b->want_frontier));
     LCU(ensure(b->frontier[1], b->cf2, b->want_frontier));
     LCU(ensure(b->pairs, b->cap_pairs, b->want_pairs));
@@ -809,15 +849,21 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     init_frontier_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(ls, io.n_env, b->frontier[0], b->cnt);
     int src = 0;
     for (int l = 0; l < levels; ++l) {
-        broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, ls, io.X, b->frontier[src], b->frontier[src ^ 1], src, (unsigned)b->cap_frontier, b->pairs,
+        broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, ls, io.X, b->frontier[src], b->frontier[src ^ 1], l, split_level, (unsigned)b->cap_frontier, b->pairs,
                                                      (unsigned)b->cap_pairs, b->cnt, (unsigned)hash_rank, (unsigned)hash_world);
-        // reset the consumed frontier's counter for its next use as an output
-        LCU(cudaMemsetAsync(&b->cnt->frontier_n[src], 0, sizeof(unsigned), stream));
         src ^= 1;
     }
-    dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, src);
-    broad_dfs_kernel<<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs, b->cnt,
-                                                              (unsigned)hash_rank, (unsigned)hash_world);
+    // what the levels left (nothing, when they ran to the leaves) is traversed with per-warp stacks; the split has been made by then
+    dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, levels, (unsigned)b->cap_frontier);
+    if (dfs_minb == 4)
+        broad_dfs_kernel<4><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs,
+                                                                     b->cnt, 0u, 1u);
+    else if (dfs_minb == 3)
+        broad_dfs_kernel<3><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs,
+                                                                     b->cnt, 0u, 1u);
+    else
+        broad_dfs_kernel<1><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs,
+                                                                     b->cnt, 0u, 1u);
     LCU(cudaMemcpyAsync(b->h_cnt, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));   // read by large_check() after the caller's synchronisation
     b->check_pending = true;
     if (n_launches) *n_launches += 3 + levels;
@@ -854,8 +900,8 @@ int large_check(LargeBuffers* b) {
     if (h.overflow & 4u) return -1;
     bool again = false;
     if (h.overflow & 1u) {
-        const size_t need = (size_t)std::max(h.frontier_n[0], std::max(h.frontier_n[1], h.q_tail)) + 1024;
-        b->want_frontier = std::max<size_t>(b->cap_frontier * 2, need);
+        const size_t need = (size_t)std::max(h.frontier_max, h.q_tail) + 1024;   // (levels below an overflowing one were cut short: leave room)
+        b->want_frontier = std::max<size_t>(b->cap_frontier * 2, need * 2);
         again = true;
     }
     if (h.overflow & 2u) {

@@ -14,6 +14,8 @@ struct LargeScene {
     const unsigned char* leaf_depth;      // per primitive: depth of its leaf
     int32_t n_large;
     int32_t key_bits;                     // max over large instructions of depth(tree 1) + depth(tree 2)
+    int32_t max_leaves;                   // max over large instructions of max(n_leaf 1, n_leaf 2)
+    int32_t max_depth;                    // max over large instructions of max(depth(tree 1), depth(tree 2))
 };
 
 struct LargeBuffers;

@@ -167,10 +167,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
                 const InsDev& ins = sc.ins[s_ins[q]];
                 const NodeRec& a = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base1 + ia));
                 const NodeRec& b = *reinterpret_cast<const NodeRec*>(ntab + (size_t)nstride * (ins.node_base2 + ib));
+                // (the general path for every node: skipping the identity products of axis-aligned nodes, as the large path's traversal does,
+                // makes the lanes of a work list diverge by node kind here -- measured 88 us against 84 us on 4096 environments)
                 SatA A;
-                sat_prepare_a(a, xf + 12 * q, xf + 12 * q + 9, A);
+                sat_prepare_a<false>(a, xf + 12 * q, xf + 12 * q + 9, A);
                 int code = 0;
-                if (sat_test(A, b)) code = (a.kind < 0) ? ((b.kind < 0) ? 1 : 2) : ((b.kind < 0) ? 3 : 4);
+                if (sat_test<false>(A, b)) code = (a.kind < 0) ? ((b.kind < 0) ? 1 : 2) : ((b.kind < 0) ? 3 : 4);
                 res[c] = (unsigned char)code;
             }
             __syncwarp();
