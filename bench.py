@@ -137,8 +137,9 @@ def measure_large_scenes(device_index, rank=0, world=1):
     configurations -- C4 (sphere on slab, tet-tet, ~2 x 100 k tets) and C5 (64-body pile, ~0.9 M candidate tri-tet pairs per
     evaluation).  Device-resident inputs, CUDA events on the library's stream, one environment, no L2 flush (the static scene is meant
     to be L2-resident).  At world > 1 the scene is SPLIT over the GPUs (pfc_set_shard + the sharded protocol of include/pfc.h): every
-    rank runs the breadth-first levels, traverses / sorts / evaluates the sub-trees whose hash falls on it, and the per-instruction
-    partial sums (8 doubles each) are all-reduced over NCCL on the library's stream; the time is the max over ranks.  Traversal +
+    rank runs the shared breadth-first levels, traverses / sorts / evaluates the sub-trees whose hash falls on it, and the per-instruction
+    partial sums (8 doubles each) are all-gathered over the library's own NCCL communicator and added in rank order
+    (pfc_eval_sharded_f64_device); the time is the max over ranks.  Traversal +
     compaction are reported against the measured HBM peak with SURVEY 8d's algorithmic bytes (272 B per node pair visited, 12 B per pair
     emitted)."""
     import torch
@@ -156,8 +157,10 @@ def measure_large_scenes(device_index, rank=0, world=1):
             m, x = build()
             ctx = capi.Context(device_index)
             S.attach_backend(m, ctx)
-            if world > 1:
-                ctx.set_shard(rank, world)
+            if world > 1:   # the library owns the exchange: NCCL communicator from an id handed over by rank 0
+                uid = [capi.Context.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                ctx.comm_init_rank(uid[0], rank, world)
             X, tw, _ = S.boundary_arrays(m, x)
             n_ins = ctx.n_ins
             Xd, twd = torch.from_numpy(X).to(dev), torch.from_numpy(tw).to(dev)
@@ -165,16 +168,9 @@ def measure_large_scenes(device_index, rank=0, world=1):
             npairs = torch.zeros((1, n_ins), dtype=torch.int64, device=dev)
             fl = torch.zeros((1, n_ins), dtype=torch.int32, device=dev)
             stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-            n_exchange = [0]
-
-            def reduce_partials(ptr, count):
-                t = torch.as_tensor(_RawCuda(ptr, count), device=dev)
-                with torch.cuda.stream(stream):
-                    parallel.allreduce_sum_(t)
-
             if world > 1:
                 def step():
-                    n_exchange[0] = parallel.eval_sharded(ctx, 1, Xd, twd, None, w, None, npairs, fl, reduce_partials)
+                    ctx.eval_sharded_f64_device(1, Xd.data_ptr(), twd.data_ptr(), None, w.data_ptr(), None, npairs.data_ptr(), fl.data_ptr())
             else:
                 def step():
                     ctx.eval_f64_device(1, Xd.data_ptr(), twd.data_ptr(), None, w.data_ptr(), None, npairs.data_ptr(), fl.data_ptr())
@@ -211,8 +207,8 @@ def measure_large_scenes(device_index, rank=0, world=1):
                          "broad_phase_roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak * world, "unit": "GB/s", "frac": gbs / (hbm_peak * world),
                                                   "bytes": "272 B per node pair visited + 12 B per pair emitted (SURVEY 8d), summed over the ranks; the scene is L2-resident"}}
             if world > 1:
-                out[name].update({"split": "hash-partitioned sub-trees of the dual-tree recursion, disjoint pair lists", "exchanges_per_eval": n_exchange[0],
-                                  "collective": "NCCL all_reduce(sum) of 8 doubles per large instruction on the library's stream",
+                out[name].update({"split": "hash-partitioned sub-trees of the dual-tree recursion, disjoint pair lists", "exchanges_per_eval": 1,
+                                  "collective": "library-owned NCCL communicator (pfc_comm_init_rank): all-gather of 8 doubles per large instruction + rank-order sum, on the library's stream",
                                   "ms_fastest_rank": ms_min, "timing": "CUDA events on each rank's stream, max over ranks"})
             ctx.close()
         except Exception as exc:   # secondary measurement: never take the headline down with it

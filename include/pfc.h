@@ -32,6 +32,7 @@ extern "C" {
 #endif
 
 typedef struct pfc_ctx pfc_ctx;
+typedef struct pfc_group pfc_group;   /* several contexts (one per GPU) sharing one scene and one library-owned NCCL communicator */
 
 enum {
     PFC_OK = 0,
@@ -164,6 +165,36 @@ int pfc_eval_sharded_begin(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, c
                            double* sdot, int64_t* n_pairs, int32_t* flags);
 int pfc_eval_sharded_partials(pfc_ctx* ctx, double** dev_ptr, int64_t* count);
 int pfc_eval_sharded_step(pfc_ctx* ctx, int* more);
+
+/* The same evaluation with the exchange done by the library (SURVEY.md section 8b "pfc_group"): a Julia caller cannot issue NCCL calls, so
+ * the library owns the communicator.  The ranks' partial sums are ALL-GATHERED over NCCL (NVLink / NVSwitch) and added in rank order on
+ * every rank, so all ranks -- and repeated runs -- end with the same bits (an all-reduce leaves the association to the collective).
+ * NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the host program already loaded, else the system's).
+ *
+ * One process per GPU (MPI / torchrun-style launchers): rank 0 calls pfc_comm_unique_id and hands the 128 bytes to the other ranks by any
+ * means; every rank then calls pfc_comm_init_rank (which also makes the context rank `rank` of `world`, like pfc_set_shard) and evaluates
+ * with pfc_eval_sharded_f64_device (device pointers, as pfc_eval_sharded_begin; queued on the context's stream after one
+ * synchronisation for the buffer check; every rank ends with the full wrenches, counts and flags). */
+int pfc_comm_unique_id(void* id128);
+int pfc_comm_init_rank(pfc_ctx* ctx, const void* id128, int rank, int world);
+int pfc_eval_sharded_f64_device(pfc_ctx* ctx, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2,
+                                double* sdot, int64_t* n_pairs, int32_t* flags);
+/* One process, several GPUs (what a single Julia process drives): pfc_group_create makes one context per listed device and one
+ * communicator over them (ncclCommInitAll).  The scene is described once -- pfc_group_add_mesh / _add_instruction / _finalize forward to
+ * every context -- and pfc_group_eval_f64 is forceAllElasticIntersections! with the large instructions' candidate-pair lists split over
+ * the devices (host pointers in and out, exactly like pfc_eval_f64; synchronous at return).  pfc_group_ctx(g, r) is device r's context
+ * (e.g. for pfc_get_pairs, which returns that rank's part of a split list). */
+int pfc_group_create(int n_dev, const int* devices, pfc_group** out);
+int pfc_group_destroy(pfc_group* g);
+int pfc_group_size(pfc_group* g);
+pfc_ctx* pfc_group_ctx(pfc_group* g, int rank);
+int pfc_group_add_mesh(pfc_group* g, int kind, int64_t n_point, const double* xyz, int64_t n_prim, const int32_t* idx, const double* eps, double Ebar,
+                       int64_t n_node, const double* node_c, const double* node_e, const double* node_R, const int32_t* node_left,
+                       const int32_t* node_right, const int32_t* node_leaf_id, int* mesh_id_out);
+int pfc_group_add_instruction(pfc_group* g, int mesh_1, int mesh_2, double chi, int model, const double* params, int n_quad_rule, int* ins_id_out);
+int pfc_group_finalize(pfc_group* g, int64_t max_env);
+int pfc_group_eval_f64(pfc_group* g, int64_t n_env, const double* X_r2_r1, const double* twist_r2, const double* s, double* wrench_r2, double* sdot,
+                       int64_t* n_pairs, int32_t* flags);
 
 /* Plumbing */
 int pfc_sync(pfc_ctx* ctx);

@@ -217,4 +217,44 @@ function refit_mesh_gpu!(m::MechanismScenario, id::MeshID, point::Vector{SVector
     return nothing
 end
 
+# ---- one very large scene split over several GPUs of this process: the library owns the NCCL communicator (pfc_group) ----------------
+"Creates a group over `devices` (0-based CUDA ordinals) and uploads the scene of `m` to every device (the walk of finalize_gpu!)."
+function finalize_group_gpu!(m::MechanismScenario, devices::Vector{Int32})
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pfc_group_create, LIB), Cint, (Cint, Ptr{Int32}, Ref{Ptr{Cvoid}}), length(devices), devices, ref))
+    g = ref[]
+    for id in m.mesh_ids
+        mc = m.MeshCache[id]
+        eM = mc.mesh
+        xyz = collect(Iterators.flatten(eM.point))
+        is_tet = eM.tet !== nothing
+        idx = Int32.(collect(Iterators.flatten(is_tet ? eM.tet : eM.tri)) .- 1)
+        c, e, R, l, r, leaf = flatten(get_tree(mc))
+        eps_ptr = is_tet ? pointer(eM.ϵ) : Ptr{Float64}(C_NULL)
+        out = Ref{Cint}(-1)
+        GC.@preserve xyz idx c e R l r leaf eM check(ccall((:pfc_group_add_mesh, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Cint}),
+            g, is_tet ? 1 : 0, length(eM.point), xyz, is_tet ? length(eM.tet) : length(eM.tri), idx, eps_ptr,
+            is_tet ? get_c_prop(mc).Ē : 0.0, length(l), c, e, R, l, r, leaf, out))
+    end
+    for ci in m.ContactInstructions
+        fm = ci.FrictionModel
+        model, params = fm isa Regularized ? (0, [fm.μs, fm.μd, fm.v_c]) : (1, [fm.τ, fm.k̄, fm.μs, fm.μd, fm.magic])
+        n_quad_rule = length(ci.quad.w) == 1 ? 1 : 2
+        check(ccall((:pfc_group_add_instruction, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Float64, Cint, Ptr{Float64}, Cint, Ptr{Cint}),
+            g, Int(ci.id_1) - 1, Int(ci.id_2) - 1, ci.χ, model, params, n_quad_rule, C_NULL))
+    end
+    check(ccall((:pfc_group_finalize, LIB), Cint, (Ptr{Cvoid}, Int64), g, 1))
+    return g
+end
+
+"forceAllElasticIntersections! with the candidate-pair lists split over the group's GPUs: same arrays as pfc_eval_f64."
+function eval_group_gpu!(g::Ptr{Cvoid}, X::Matrix{Float64}, tw::Matrix{Float64}, s, w::Matrix{Float64}, sdot)
+    GC.@preserve X tw s w sdot check(ccall((:pfc_group_eval_f64, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+        g, 1, X, tw, s === nothing ? C_NULL : pointer(s), w, sdot === nothing ? C_NULL : pointer(sdot), C_NULL, C_NULL))
+    return nothing
+end
+
 end # module

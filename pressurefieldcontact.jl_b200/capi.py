@@ -23,6 +23,8 @@ SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
     "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_eval_sharded_begin", "pfc_eval_sharded_partials", "pfc_eval_sharded_step", "pfc_sync", "pfc_stream",
     "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_set_dynamics", "pfc_calcxd_f64", "pfc_calcxd_f64_device", "pfc_calcxd_dual6", "pfc_calcxd_dual6_device", "pfc_radau_inv_c_device", "pfc_refit_mesh", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
+    "pfc_comm_unique_id", "pfc_comm_init_rank", "pfc_eval_sharded_f64_device", "pfc_group_create", "pfc_group_destroy", "pfc_group_size", "pfc_group_ctx",
+    "pfc_group_add_mesh", "pfc_group_add_instruction", "pfc_group_finalize", "pfc_group_eval_f64",
 ]
 
 
@@ -66,6 +68,19 @@ def lib():
         L.pfc_calcxd_dual6_device.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, _vp]
         L.pfc_refit_mesh.argtypes = [_vp, C.c_int, C.c_int64, _d]
         L.pfc_radau_inv_c_device.argtypes = [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_comm_unique_id.argtypes = [_vp]
+        L.pfc_comm_init_rank.argtypes = [_vp, _vp, C.c_int, C.c_int]
+        L.pfc_eval_sharded_f64_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_group_create.argtypes = [C.c_int, _i32, C.POINTER(_vp)]
+        L.pfc_group_destroy.argtypes = [_vp]
+        L.pfc_group_size.argtypes = [_vp]
+        L.pfc_group_ctx.argtypes = [_vp, C.c_int]
+        L.pfc_group_ctx.restype = _vp
+        L.pfc_group_add_mesh.argtypes = [_vp, C.c_int, C.c_int64, _d, C.c_int64, _i32, _vp, C.c_double, C.c_int64, _d, _d, _d, _i32, _i32, _i32,
+                                         C.POINTER(C.c_int)]
+        L.pfc_group_add_instruction.argtypes = [_vp, C.c_int, C.c_int, C.c_double, C.c_int, _d, C.c_int, C.POINTER(C.c_int)]
+        L.pfc_group_finalize.argtypes = [_vp, C.c_int64]
+        L.pfc_group_eval_f64.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         L.pfc_sync.argtypes = [_vp]
         L.pfc_stream.argtypes = [_vp]
         L.pfc_stream.restype = _vp
@@ -259,6 +274,21 @@ class Context:
         _check(lib().pfc_eval_sharded_step(self._h, C.byref(more)))
         return bool(more.value)
 
+    # ---- library-owned exchange (one process per GPU) ------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().pfc_comm_unique_id(C.cast(buf, _vp)))
+        return buf.raw
+
+    def comm_init_rank(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _check(lib().pfc_comm_init_rank(self._h, C.cast(buf, _vp), rank, world))
+
+    def eval_sharded_f64_device(self, n_env, X, twist, s, wrench, sdot, n_pairs, flags):
+        """Device pointers; this rank's share of the evaluation, the all-gather of the partial sums and their application, on self.stream."""
+        _check(lib().pfc_eval_sharded_f64_device(self._h, n_env, X, twist, s, wrench, sdot, n_pairs, flags))
+
     def eval_dual6(self, X_bp, X7, twist7, s7=None):
         n_env = _a(X7).reshape(-1, self.n_ins, 16, 7).shape[0]
         X7 = _a(X7).reshape(n_env, self.n_ins, 16, 7)
@@ -315,3 +345,61 @@ class Context:
         a, b = C.c_int64(0), C.c_int64(0)
         _check(lib().pfc_counters(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class Group:
+    """pfc_group: one process, one context per listed GPU, one library-owned NCCL communicator; the scene is described once and
+    pfc_group_eval_f64 splits the large instructions' candidate-pair lists over the devices (same add_mesh / add_instruction /
+    finalize / eval_f64 surface as Context, so scenario.attach_backend works on it)."""
+    name = "cuda-group"
+
+    def __init__(self, devices):
+        self._h = _vp()
+        dev = _a(list(devices), np.int32)
+        _check(lib().pfc_group_create(len(dev), dev, C.byref(self._h)))
+        self.n_ins = 0
+        self.n_bristle = 0
+        self.size = int(lib().pfc_group_size(self._h))
+
+    def close(self):
+        if self._h:
+            lib().pfc_group_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_mesh(self, kind, xyz, idx, eps, Ebar, tree) -> int:
+        xyz = _a(xyz).reshape(-1, 3)
+        idx = _a(idx, np.int32)
+        eps_a = None if eps is None else _a(eps)
+        out = C.c_int(-1)
+        _check(lib().pfc_group_add_mesh(self._h, kind, len(xyz), xyz, len(idx), idx, _p(eps_a), float(Ebar or 0.0), tree.n_node, _a(tree.c), _a(tree.e),
+                                        _a(tree.R), _a(tree.left, np.int32), _a(tree.right, np.int32), _a(tree.leaf_id, np.int32), C.byref(out)))
+        return out.value
+
+    def add_instruction(self, mesh_1, mesh_2, chi, model, params, n_quad_rule) -> int:
+        out = C.c_int(-1)
+        _check(lib().pfc_group_add_instruction(self._h, mesh_1, mesh_2, float(chi), model, _a(params), n_quad_rule, C.byref(out)))
+        self.n_ins = out.value + 1
+        if model == 1:
+            self.n_bristle += 1
+        return out.value
+
+    def finalize(self, max_env: int = 1):
+        _check(lib().pfc_group_finalize(self._h, max_env))
+
+    def eval_f64(self, X, twist, s=None, keep=False, out=None):
+        X = _a(X).reshape(-1, self.n_ins, 16)
+        n_env = X.shape[0]
+        twist = _a(twist).reshape(n_env, self.n_ins, 6)
+        nb = self.n_bristle
+        s_a = _a(s).reshape(n_env, nb, 6) if nb else None
+        if out is None:
+            out = dict(wrench=np.zeros((n_env, self.n_ins, 6)), sdot=np.zeros((n_env, nb, 6)) if nb else None,
+                       n_pairs=np.zeros((n_env, self.n_ins), np.int64), flags=np.zeros((n_env, self.n_ins), np.int32))
+        _check(lib().pfc_group_eval_f64(self._h, n_env, _p(X), _p(twist), _p(s_a), _p(out["wrench"]), _p(out["sdot"]), _p(out["n_pairs"]), _p(out["flags"])))
+        return out

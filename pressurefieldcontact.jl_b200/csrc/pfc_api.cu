@@ -1,4 +1,7 @@
 // pfc_api.cu -- the C ABI of include/pfc.h: scene container, one-time upload, evaluation entry points.
+#include <dlfcn.h>
+#include <nccl.h>   // declarations only: the library is loaded at run time (nccl_api), so libpfc_b200.so has no link-time dependency on it
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -43,6 +46,57 @@ struct HostIns {
     int mesh_1, mesh_2, model, n_quad_rule, bristle_id;
     double chi, params[5];
 };
+
+// ---- NCCL, resolved at run time ------------------------------------------------------------------------------------------------
+// dlopen("libnccl.so.2") picks up the copy a host program has already loaded (PyTorch ships its own under the same soname), else
+// the system's.  Only what the per-instruction partial sums of a split scene need: communicator set-up and all-gather.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool ok() const { return handle && error.empty(); }
+};
+NcclApi& nccl_api() {
+    static NcclApi a = [] {
+        NcclApi n;
+        n.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!n.handle) n.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!n.handle) { n.error = std::string("NCCL is not available: ") + dlerror(); return n; }
+        auto sym = [&](const char* name) { void* p = dlsym(n.handle, name); if (!p && n.error.empty()) n.error = std::string("NCCL symbol missing: ") + name; return p; };
+        n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(sym("ncclGetUniqueId"));
+        n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(sym("ncclCommInitRank"));
+        n.CommInitAll = reinterpret_cast<decltype(n.CommInitAll)>(sym("ncclCommInitAll"));
+        n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(sym("ncclCommDestroy"));
+        n.AllGather = reinterpret_cast<decltype(n.AllGather)>(sym("ncclAllGather"));
+        n.GroupStart = reinterpret_cast<decltype(n.GroupStart)>(sym("ncclGroupStart"));
+        n.GroupEnd = reinterpret_cast<decltype(n.GroupEnd)>(sym("ncclGroupEnd"));
+        n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
+        return n;
+    }();
+    return a;
+}
+#define NC(call)                                                                                                               \
+    do {                                                                                                                       \
+        ncclResult_t r_ = (call);                                                                                              \
+        if (r_ != ncclSuccess) return fail(PFC_E_CUDA, std::string(#call) + ": " + nccl_api().GetErrorString(r_));            \
+    } while (0)
+
+// out[i] = ((g[0][i] + g[1][i]) + g[2][i]) + ... : the ranks' partial sums added in RANK ORDER on every rank, so all ranks end with the
+// same bits whatever order the network delivered them in (an all-reduce leaves the association to the collective's algorithm)
+__global__ void sum_ranks_kernel(const double* __restrict__ gathered, int world, long long count, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        double a = gathered[i];
+        for (int r = 1; r < world; ++r) a += gathered[(long long)r * count + i];
+        out[i] = a;
+    }
+}
 
 template <class T> struct DevBuf {
     T* p = nullptr;
@@ -111,6 +165,8 @@ struct pfc_ctx {
     ExactScene exact_scene{};
     ExactBuffers* exact_buf = nullptr;
     bool has_large_bristle = false;
+    ncclComm_t comm = nullptr;   // library-owned communicator of a split scene (pfc_comm_init_rank / pfc_group_create)
+    DevBuf<double> d_gather;     // [world][count]: the ranks' partial sums after the all-gather
     int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
     EvalIO sharded_io{};
     // Jacobian mode staging + the pair lists it may reuse
@@ -216,7 +272,9 @@ int pfc_create(int device, pfc_ctx** out) {
 int pfc_destroy(pfc_ctx* c) {
     if (!c) return PFC_OK;
     cudaSetDevice(c->device);
-    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl_api().ok()) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
+    if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release(); c->d_small_heavy.release();
     c->d_X.release(); c->d_tw.release(); c->d_s.release(); c->d_w.release(); c->d_sd.release(); c->d_np.release(); c->d_fl.release();
     c->d_dbg_pairs.release(); c->d_last_np.release(); c->d_small_pairs.release();
@@ -633,6 +691,29 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
 }
 
 // ---- one large scene split over several GPUs ------------------------------------------------------------------
+// queues this rank's share of a split evaluation (no synchronisation; evaluation_fits() must be asked afterwards)
+static int sharded_enqueue(pfc_ctx* c, const EvalIO& io) {
+    int nl = 0;
+    if (c->scene.n_small > 0) {  // small instructions are cheap: every rank evaluates them completely
+        CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins + kSmallPairsSlack));
+        CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
+    }
+    // every rank runs the shared breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair
+    // lists.  Bristle instructions are the exception: their sums run sequentially over the whole TractionCache list (pfc_exact.cuh), so
+    // every rank lists and evaluates them completely -- identical bits on every rank, nothing to exchange.
+    CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl, c->shard_rank, c->shard_world));
+    CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, c->shard_world > 1, 0, c->stream, &nl));
+    int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
+    if (rc != PFC_OK) return rc;
+    c->launches += nl;
+    c->sharded_io = io;
+    c->sharded_stage = 0;
+    c->lists_n_env = -1;
+    if (c->keep_pairs) c->dbg_n_env = io.n_env;   // (pfc_get_pairs: the large instructions' lists live in the large path's buffers)
+    c->last_X = io.X; c->last_tw = io.twist;
+    return PFC_OK;
+}
+
 int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
                            int64_t* n_pairs, int32_t* flags) {
     if (!c || !c->finalized) return fail(PFC_E_ARG, "pfc_eval_sharded_begin: context not finalized");
@@ -646,28 +727,7 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
     io.n_env = n_env; io.X = X; io.twist = twist; io.s = s; io.wrench = wrench; io.sdot = sdot;
     io.n_pairs = reinterpret_cast<long long*>(n_pairs); io.flags = flags;
     // one synchronisation at the end of what was queued: the traversal's and the bristle pipeline's buffers grow after the fact
-    PFC_REQUEUE_LOOP({
-        int nl = 0;
-        if (c->scene.n_small > 0) {  // small instructions are cheap: every rank evaluates them completely
-            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * c->scene.n_ins + kSmallPairsSlack));
-            CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, nullptr));
-        }
-        // every rank runs the breadth-first levels, then traverses and lists only the sub-trees whose hash falls on it: disjoint pair lists.
-        // Bristle instructions are the exception: their sums run sequentially over the whole TractionCache list (pfc_exact.cuh), so every
-        // rank lists and evaluates them completely -- identical bits on every rank, nothing to exchange.
-        CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl, c->shard_rank, c->shard_world));
-        CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, c->shard_world > 1, 0, c->stream, &nl));
-        {
-            int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
-            if (rc != PFC_OK) return rc;
-        }
-        c->launches += nl;
-    })
-    c->sharded_io = io;
-    c->sharded_stage = 0;
-    c->lists_n_env = -1;
-    if (c->keep_pairs) c->dbg_n_env = n_env;   // (pfc_get_pairs: the large instructions' lists live in the large path's buffers)
-    c->last_X = io.X; c->last_tw = io.twist;
+    PFC_REQUEUE_LOOP({ const int rc_ = sharded_enqueue(c, io); if (rc_ != PFC_OK) return rc_; })
     return PFC_OK;
 }
 
@@ -687,6 +747,187 @@ int pfc_eval_sharded_step(pfc_ctx* c, int* more) {
     c->sharded_stage = -1;   // one exchange per evaluation (regularized sums; bristle instructions are not split)
     *more = 0;
     c->launches += nl;
+    return PFC_OK;
+}
+
+// ---- library-owned collective (SURVEY.md section 8b "pfc_group") -------------------------------------------------------------
+// The exchange of a split scene: every rank's per-instruction partial sums (8 doubles per large instruction) are ALL-GATHERED over NCCL
+// and added in rank order by sum_ranks_kernel, so every rank holds the same bits; then the sums are applied.  All on the context's stream.
+static int sharded_exchange_and_finish(pfc_ctx* c) {
+    NcclApi& n = nccl_api();
+    const long long count = (long long)kLargePartStride * c->sharded_io.n_env * c->large_scene.n_large;
+    if (c->shard_world > 1) {
+        double* part = large_part_buffer(c->large_buf);
+        CU(c->d_gather.ensure(size_t(count) * c->shard_world));
+        NC(n.AllGather(part, c->d_gather.p, size_t(count), ncclDouble, c->comm, c->stream));
+        sum_ranks_kernel<<<(unsigned)std::min<long long>((count + 255) / 256, 1024), 256, 0, c->stream>>>(c->d_gather.p, c->shard_world, count, part);
+        CU(cudaGetLastError());
+        c->launches += 1;
+    }
+    int more = 0;
+    return pfc_eval_sharded_step(c, &more);
+}
+
+int pfc_comm_unique_id(void* id128) {
+    if (!id128) return fail(PFC_E_ARG, "pfc_comm_unique_id: NULL buffer");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(PFC_E_CUDA, n.error);
+    static_assert(sizeof(ncclUniqueId) == 128, "the unique id is handed over as 128 bytes");
+    NC(n.GetUniqueId(reinterpret_cast<ncclUniqueId*>(id128)));
+    return PFC_OK;
+}
+
+int pfc_comm_init_rank(pfc_ctx* c, const void* id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(PFC_E_ARG, "pfc_comm_init_rank: bad argument");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(PFC_E_CUDA, n.error);
+    CU(cudaSetDevice(c->device));
+    if (c->comm) { n.CommDestroy(c->comm); c->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    NC(n.CommInitRank(&c->comm, world, id, rank));
+    c->shard_rank = rank; c->shard_world = world;
+    return PFC_OK;
+}
+
+int pfc_eval_sharded_f64_device(pfc_ctx* c, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
+                                int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->comm) return fail(PFC_E_ARG, "pfc_eval_sharded_f64_device: pfc_comm_init_rank (or pfc_group_create) first");
+    int rc = pfc_eval_sharded_begin(c, n_env, X, twist, s, wrench, sdot, n_pairs, flags);
+    if (rc != PFC_OK || n_env == 0) return rc;
+    return sharded_exchange_and_finish(c);
+}
+
+struct pfc_group {
+    std::vector<pfc_ctx*> ctx;
+};
+
+int pfc_group_create(int n_dev, const int* devices, pfc_group** out) {
+    if (n_dev < 1 || !devices || !out) return fail(PFC_E_ARG, "pfc_group_create: bad argument");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(PFC_E_CUDA, n.error);
+    pfc_group* g = new pfc_group();
+    for (int r = 0; r < n_dev; ++r) {
+        pfc_ctx* c = nullptr;
+        const int rc = pfc_create(devices[r], &c);
+        if (rc != PFC_OK) { for (pfc_ctx* x : g->ctx) pfc_destroy(x); delete g; return rc; }
+        c->shard_rank = r; c->shard_world = n_dev;
+        g->ctx.push_back(c);
+    }
+    std::vector<ncclComm_t> comms(n_dev);
+    ncclResult_t r_ = n.CommInitAll(comms.data(), n_dev, devices);   // one process, one communicator rank per device
+    if (r_ != ncclSuccess) { for (pfc_ctx* x : g->ctx) pfc_destroy(x); delete g; return fail(PFC_E_CUDA, std::string("ncclCommInitAll: ") + n.GetErrorString(r_)); }
+    for (int r = 0; r < n_dev; ++r) g->ctx[r]->comm = comms[r];
+    *out = g;
+    return PFC_OK;
+}
+int pfc_group_destroy(pfc_group* g) {
+    if (!g) return PFC_OK;
+    for (pfc_ctx* c : g->ctx) pfc_destroy(c);
+    delete g;
+    return PFC_OK;
+}
+int pfc_group_size(pfc_group* g) { return g ? int(g->ctx.size()) : 0; }
+pfc_ctx* pfc_group_ctx(pfc_group* g, int rank) { return (g && rank >= 0 && rank < int(g->ctx.size())) ? g->ctx[rank] : nullptr; }
+
+// scene description: the same calls on every device of the group
+int pfc_group_add_mesh(pfc_group* g, int kind, int64_t n_point, const double* xyz, int64_t n_prim, const int32_t* idx, const double* eps, double Ebar,
+                       int64_t n_node, const double* node_c, const double* node_e, const double* node_R, const int32_t* node_left,
+                       const int32_t* node_right, const int32_t* node_leaf_id, int* mesh_id_out) {
+    if (!g) return fail(PFC_E_ARG, "pfc_group_add_mesh: NULL group");
+    for (pfc_ctx* c : g->ctx) {
+        const int rc = pfc_add_mesh(c, kind, n_point, xyz, n_prim, idx, eps, Ebar, n_node, node_c, node_e, node_R, node_left, node_right, node_leaf_id, mesh_id_out);
+        if (rc != PFC_OK) return rc;
+    }
+    return PFC_OK;
+}
+int pfc_group_add_instruction(pfc_group* g, int mesh_1, int mesh_2, double chi, int model, const double* params, int n_quad_rule, int* ins_id_out) {
+    if (!g) return fail(PFC_E_ARG, "pfc_group_add_instruction: NULL group");
+    for (pfc_ctx* c : g->ctx) { const int rc = pfc_add_instruction(c, mesh_1, mesh_2, chi, model, params, n_quad_rule, ins_id_out); if (rc != PFC_OK) return rc; }
+    return PFC_OK;
+}
+int pfc_group_finalize(pfc_group* g, int64_t max_env) {
+    if (!g) return fail(PFC_E_ARG, "pfc_group_finalize: NULL group");
+    for (pfc_ctx* c : g->ctx) { const int rc = pfc_finalize(c, max_env); if (rc != PFC_OK) return rc; }
+    return PFC_OK;
+}
+
+// forceAllElasticIntersections! for a scene split over the group's devices.  Host pointers, as pfc_eval_f64; synchronous at return.
+int pfc_group_eval_f64(pfc_group* g, int64_t n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot, int64_t* n_pairs,
+                       int32_t* flags) {
+    if (!g || g->ctx.empty()) return fail(PFC_E_ARG, "pfc_group_eval_f64: NULL group");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_group_eval_f64: negative n_env");
+    if (n_env == 0) return PFC_OK;
+    if (!X || !twist || !wrench) return fail(PFC_E_ARG, "pfc_group_eval_f64: NULL buffer");
+    pfc_ctx* c0 = g->ctx[0];
+    if (!c0->finalized) return fail(PFC_E_ARG, "pfc_group_eval_f64: pfc_group_finalize first");
+    if (c0->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_group_eval_f64: bristle instructions need s and sdot");
+    if (g->ctx.size() == 1 || c0->large_scene.n_large == 0)   // nothing to split: the plain evaluation on the first device
+        return pfc_eval_f64(c0, n_env, X, twist, s, wrench, sdot, n_pairs, flags);
+    NcclApi& n = nccl_api();
+    const size_t ne = size_t(n_env), ni = size_t(c0->scene.n_ins), nb = size_t(c0->n_bristle);
+    std::vector<EvalIO> ios(g->ctx.size());
+    // 1. every device: inputs in, its share of the traversal / narrow phase queued
+    for (size_t r = 0; r < g->ctx.size(); ++r) {
+        pfc_ctx* c = g->ctx[r];
+        CU(cudaSetDevice(c->device));
+        CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+        if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_sd.ensure(6 * ne * nb)); }
+        CU(cudaMemcpyAsync(c->d_X.p, X, sizeof(double) * 16 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_tw.p, twist, sizeof(double) * 6 * ne * ni, cudaMemcpyHostToDevice, c->stream));
+        if (nb) CU(cudaMemcpyAsync(c->d_s.p, s, sizeof(double) * 6 * ne * nb, cudaMemcpyHostToDevice, c->stream));
+        EvalIO& io = ios[r];
+        io = EvalIO{};
+        io.n_env = n_env; io.X = c->d_X.p; io.twist = c->d_tw.p; io.s = nb ? c->d_s.p : nullptr; io.wrench = c->d_w.p; io.sdot = nb ? c->d_sd.p : nullptr;
+        io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
+        const int rc = sharded_enqueue(c, io);
+        if (rc != PFC_OK) return rc;
+    }
+    // 2. did everything fit?  (a device whose buffers overflowed repeats its own share; the others wait at the exchange)
+    for (size_t r = 0; r < g->ctx.size(); ++r) {
+        pfc_ctx* c = g->ctx[r];
+        CU(cudaSetDevice(c->device));
+        for (int attempt = 0;; ++attempt) {
+            const int fit = evaluation_fits(c);
+            if (fit < 0) return fit;
+            if (fit == 0) break;
+            if (attempt >= 8) return fail(PFC_E_CAPACITY, "candidate-pair / traction buffers kept overflowing");
+            const int rc = sharded_enqueue(c, ios[r]);
+            if (rc != PFC_OK) return rc;
+        }
+    }
+    // 3. the exchange: all-gather of the partial sums, rank-order sum, apply
+    const long long count = (long long)kLargePartStride * n_env * c0->large_scene.n_large;
+    for (pfc_ctx* c : g->ctx) { CU(cudaSetDevice(c->device)); CU(c->d_gather.ensure(size_t(count) * g->ctx.size())); }
+    NC(n.GroupStart());
+    for (pfc_ctx* c : g->ctx) {
+        const ncclResult_t r_ = n.AllGather(large_part_buffer(c->large_buf), c->d_gather.p, size_t(count), ncclDouble, c->comm, c->stream);
+        if (r_ != ncclSuccess) { n.GroupEnd(); return fail(PFC_E_CUDA, std::string("ncclAllGather: ") + n.GetErrorString(r_)); }
+    }
+    NC(n.GroupEnd());
+    for (pfc_ctx* c : g->ctx) {
+        CU(cudaSetDevice(c->device));
+        sum_ranks_kernel<<<(unsigned)std::min<long long>((count + 255) / 256, 1024), 256, 0, c->stream>>>(c->d_gather.p, c->shard_world, count, large_part_buffer(c->large_buf));
+        CU(cudaGetLastError());
+        c->launches += 1;
+        int more = 0;
+        const int rc = pfc_eval_sharded_step(c, &more);
+        if (rc != PFC_OK) return rc;
+    }
+    // 4. results: every device holds the same wrench; the first one hands them over
+    CU(cudaSetDevice(c0->device));
+    CU(cudaMemcpyAsync(wrench, c0->d_w.p, sizeof(double) * 6 * ne * ni, cudaMemcpyDeviceToHost, c0->stream));
+    if (nb) CU(cudaMemcpyAsync(sdot, c0->d_sd.p, sizeof(double) * 6 * ne * nb, cudaMemcpyDeviceToHost, c0->stream));
+    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c0->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c0->stream));
+    std::vector<int32_t> fl_local;
+    int32_t* fl = flags;
+    if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
+    CU(cudaMemcpyAsync(fl, c0->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c0->stream));
+    for (pfc_ctx* c : g->ctx) { CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); }
+    for (size_t k = 0; k < ne * ni; ++k) {
+        if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
+        if (fl[k] & PFC_FLAG_OVERFLOW) return fail(PFC_E_CAPACITY, "candidate-pair capacity exceeded");
+    }
     return PFC_OK;
 }
 

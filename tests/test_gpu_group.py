@@ -1,0 +1,45 @@
+"""The library-owned collective (pfc_group: one process, one context per GPU, one NCCL communicator): a scene with large instructions
+split over the visible GPUs gives the same wrench as the unsplit evaluation (<= 1e-11: same traction points, another association),
+exact pair counts and flags, identical bits run after run (all-gather + rank-order sum), and a bristle instruction -- never split --
+bit-identical to the single-GPU result.  On a one-GPU box the group has one device (no exchange); run with `gpurun --gpus 2` for the
+real thing."""
+import numpy as np
+import pytest
+
+import pfc_b200  # noqa: F401
+from helpers import wrench_rel_err
+from pfc_b200 import capi, scenes
+from pfc_b200 import scenario as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_dev():
+    import torch
+    return min(torch.cuda.device_count(), 4)
+
+
+@pytest.mark.parametrize("scene", ["C4", "C5-bristle"])
+def test_group_eval_matches_single_gpu(scene):
+    build = (lambda: scenes.scene_c4_sphere_on_slab(24, 27)) if scene == "C4" else (lambda: scenes.scene_c5_pile(3, 8, bristle_every=7))
+    m1, x = build()
+    one = capi.Context(0)
+    S.attach_backend(m1, one)
+    X, tw, s = S.boundary_arrays(m1, x)
+    nb = one.n_bristle
+    s_arr = s.reshape(1, nb, 6) if nb else None
+    ref = one.eval_f64(X, tw, s_arr)
+    m2, _ = build()
+    grp = capi.Group(list(range(_n_dev())))
+    S.attach_backend(m2, grp)
+    a = grp.eval_f64(X, tw, s_arr)
+    b = grp.eval_f64(X, tw, s_arr)
+    assert np.array_equal(a["n_pairs"], ref["n_pairs"]) and np.array_equal(a["flags"], ref["flags"])
+    assert wrench_rel_err(a["wrench"], ref["wrench"], floor=1e-9 * np.abs(ref["wrench"]).max()) <= 1e-11
+    assert a["wrench"].tobytes() == b["wrench"].tobytes()          # reproducible: fixed rank order of the sum
+    if nb:
+        bristle = np.array([ci.friction_model.model == 1 for ci in m1.ContactInstructions])
+        assert np.array_equal(a["wrench"][:, bristle], ref["wrench"][:, bristle])   # bristle instructions are not split: same bits
+        assert np.array_equal(a["sdot"], ref["sdot"])
+    assert (ref["flags"] & 1).sum() > 0
+    grp.close()
