@@ -665,6 +665,9 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
     CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
     if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_sd.ensure(6 * ne * nb)); }
     arena_reset(c);
+    // (Measured and rejected: letting the kernels of a single small scene read X / twist straight from the pinned arena and write the
+    // wrenches into it -- zero-copy over PCIe instead of five cudaMemcpyAsync calls: no gain on test/boxes.jl (69 vs 67 us per call), and
+    // scenes whose large instructions re-read X in every thread got slower, 316 -> 402 us on the spoon.)
     CU(copy_in(c, c->d_X.p, X, sizeof(double) * 16 * ne * ni));
     CU(copy_in(c, c->d_tw.p, twist, sizeof(double) * 6 * ne * ni));
     if (nb) CU(copy_in(c, c->d_s.p, s, sizeof(double) * 6 * ne * nb));

@@ -106,26 +106,30 @@ template <class T, int NA = 6> struct Accum {
 };
 
 // ---- stage B: one sub-triangle (v1, v2, centroid) of a contact polygon ------------------------------------
+template <class T, int NA> PFC_D void quad_point(const Vec3<T>& v1, const Vec3<T>& v2, const Vec3<T>& cen, const Vec3<T>& nrm, double g0, double g1, double g2,
+                                                 double g3, double za, double zb, double zc, const T& dA, const PatchCtx<T>& cx, Accum<T, NA>& acc) {
+    const Vec3<T> r = mk<T>(v1.x * za + v2.x * zb + cen.x * zc, v1.y * za + v2.y * zb + cen.y * zc, v1.z * za + v2.z * zb + cen.z * zc);
+    T eps = fma_(g0, r.x, g3);
+    eps = fma_(g1, r.y, eps);
+    eps = fma_(g2, r.z, eps);
+    const Vec3<T> rd = cx.w_lin + cross(cx.w_ang, r);
+    const T ee = -(g0 * rd.x + g1 * rd.y + g2 * rd.z);
+    T damp = 1.0 + cx.chi * ee;
+    if (val(damp) < 0.0) damp = T(0.0);
+    const T p = eps * cx.Ebar2 * damp;
+    if (0.0 < val(p)) acc.point(nrm, r, dA, p);
+}
 template <class T, int NA> PFC_D void integrate_subtri(const Vec3<T>& v1, const Vec3<T>& v2, const Vec3<T>& cen, const Vec3<T>& nrm, const double* eps_r,
                                                        const PatchCtx<T>& cx, Accum<T, NA>& acc) {
     const T area = dot(nrm, cross(v2 - v1, cen - v2) * 0.5);
     if (!(0.0 < val(area))) return;
     const double g0 = eps_r[0], g1 = eps_r[1], g2 = eps_r[2], g3 = eps_r[3];
-    for (int q = 0; q < cx.n_quad; ++q) {
-        double za, zb, zc, w;
-        if (cx.n_quad == 1) { za = zb = zc = PFC_Q1; w = 1.0; }
-        else { za = (q == 1) ? PFC_QB : PFC_QA; zb = (q == 0) ? PFC_QB : PFC_QA; zc = (q == 2) ? PFC_QB : PFC_QA; w = PFC_Q1; }
-        const Vec3<T> r = mk<T>(v1.x * za + v2.x * zb + cen.x * zc, v1.y * za + v2.y * zb + cen.y * zc, v1.z * za + v2.z * zb + cen.z * zc);
-        T eps = fma_(g0, r.x, g3);
-        eps = fma_(g1, r.y, eps);
-        eps = fma_(g2, r.z, eps);
-        const Vec3<T> rd = cx.w_lin + cross(cx.w_ang, r);
-        const T ee = -(g0 * rd.x + g1 * rd.y + g2 * rd.z);
-        T damp = 1.0 + cx.chi * ee;
-        if (val(damp) < 0.0) damp = T(0.0);
-        const T p = eps * cx.Ebar2 * damp;
-        if (0.0 < val(p)) acc.point(nrm, r, w * area, p);
-    }
+    if (cx.n_quad == 1) { quad_point(v1, v2, cen, nrm, g0, g1, g2, g3, PFC_Q1, PFC_Q1, PFC_Q1, area * 1.0, cx, acc); return; }
+    // rule 2: three points, written out so that their (independent) dependency chains can be interleaved by the scheduler
+    const T dA = area * PFC_Q1;
+    quad_point(v1, v2, cen, nrm, g0, g1, g2, g3, PFC_QA, PFC_QB, PFC_QA, dA, cx, acc);
+    quad_point(v1, v2, cen, nrm, g0, g1, g2, g3, PFC_QB, PFC_QA, PFC_QA, dA, cx, acc);
+    quad_point(v1, v2, cen, nrm, g0, g1, g2, g3, PFC_QA, PFC_QA, PFC_QB, dA, cx, acc);
 }
 
 // polygon in tetrahedral coordinates of tet 2 -> Cartesian vertices in r2 + area-weighted centroid

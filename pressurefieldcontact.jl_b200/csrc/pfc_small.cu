@@ -364,9 +364,10 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
                 int n0 = 0, q = 0;
                 unsigned e = 0;
                 if (c < n_cand) {
+                    int first = 0;   // first candidate of problem q (pre[] by a run-time index would go to local memory)
 #pragma unroll
-                    for (int r = 1; r < P; ++r) q += (c >= pre[r]);
-                    e = pairs_in[(size_t)cap * sm.ei[q] + (c - pre[q])];
+                    for (int r = 1; r < P; ++r) { const bool ge = c >= pre[r]; q += ge; first = ge ? pre[r] : first; }
+                    e = pairs_in[(size_t)cap * sm.ei[q] + (c - first)];
                     n0 = start_polygon_zeta(sc, sc.ins[sm.ins[q]], dec_a(e), dec_b(e), sm.cx[q], zr);
                 }
                 // ---- 2b. block scan of the survivors -> slot numbers in candidate order
