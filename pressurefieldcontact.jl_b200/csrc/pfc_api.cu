@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -109,6 +110,7 @@ template <class T> struct DevBuf {
     ~DevBuf() { release(); }   // every buffer a context owns goes with it (pfc_destroy deletes the context on its device)
     cudaError_t ensure(size_t count) {
         if (count <= n) return cudaSuccess;
+        alloc_generation()++;
         if (p) cudaFree(p);
         p = nullptr; n = 0;
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
@@ -165,6 +167,14 @@ struct pfc_ctx {
     ExactScene exact_scene{};
     ExactBuffers* exact_buf = nullptr;
     bool has_large_bristle = false;
+    // CUDA graph of the last evaluation's launch sequence (scenes with large / bristle instructions queue dozens of short kernels)
+    struct GraphCache {
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long key = 0, gen = ~0ull;   // what was evaluated (entry point, batch size, buffers) and the allocation generation then
+        bool seen = false;                          // the same evaluation ran eagerly once: everything it needs is allocated
+        int launches = 0;
+        bool disabled = false;
+    } graph;
     ncclComm_t comm = nullptr;   // library-owned communicator of a split scene (pfc_comm_init_rank / pfc_group_create)
     DevBuf<double> d_gather;     // [world][count]: the ranks' partial sums after the all-gather
     int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
@@ -273,6 +283,7 @@ int pfc_destroy(pfc_ctx* c) {
     if (!c) return PFC_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->graph.exec) { cudaGraphExecDestroy(c->graph.exec); c->graph.exec = nullptr; }
     if (c->comm && nccl_api().ok()) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release(); c->d_small_heavy.release();
@@ -605,9 +616,70 @@ static int eval_device_once(pfc_ctx* c, const EvalIO& io_in) {
     return PFC_OK;
 }
 
+// Scenes with large or bristle instructions queue dozens of short kernels per evaluation (breadth-first levels, radix passes, ...): once
+// the same evaluation -- same entry point, batch size and buffers, nothing reallocated since -- has run eagerly, its launch sequence is
+// captured into a CUDA graph and replayed (one launch instead of ~45; the kernels read every data-dependent size from the device).
+// enqueue() must queue one complete evaluation on c->stream and return PFC_OK.
+static int run_evaluation(pfc_ctx* c, unsigned long long key, const std::function<int()>& enqueue) {
+    pfc_ctx::GraphCache& g = c->graph;
+    const bool want_graph = !g.disabled && !c->timing && !c->keep_pairs && (c->large_buf || c->exact_buf);
+    for (int attempt = 0;; ++attempt) {
+        const unsigned long long gen = alloc_generation().load();
+        bool replayed = false;
+        if (want_graph && attempt == 0 && g.key == key && g.gen == gen) {
+            if (g.exec) {
+                if (cudaGraphLaunch(g.exec, c->stream) == cudaSuccess) { replayed = true; c->launches += g.launches; }
+                else { cudaGetLastError(); cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.disabled = true; }
+            } else if (g.seen) {   // second identical evaluation: capture it
+                cudaGraph_t graph = nullptr;
+                const long long l0 = c->launches;
+                if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int rc = enqueue();
+                    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+                    if (rc == PFC_OK && e == cudaSuccess && graph && alloc_generation().load() == gen &&
+                        cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess && cudaGraphLaunch(g.exec, c->stream) == cudaSuccess) {
+                        g.launches = int(c->launches - l0);
+                        replayed = true;
+                    } else {
+                        cudaGetLastError();
+                        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+                        g.disabled = true;   // this context's evaluations do not capture: stay eager
+                        c->launches = l0;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                } else { cudaGetLastError(); g.disabled = true; }
+            }
+        }
+        if (replayed) {
+            large_mark_pending(c->large_buf);
+            exact_mark_pending(c->exact_buf);
+        } else {
+            const int rc = enqueue();
+            if (rc != PFC_OK) return rc;
+            if (want_graph) {
+                if (g.key != key || g.gen != alloc_generation().load()) { if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } g.seen = false; }
+                g.key = key; g.gen = alloc_generation().load(); g.seen = true;
+            }
+        }
+        const int fit = evaluation_fits(c);
+        if (fit < 0) return fit;
+        if (fit == 0) return PFC_OK;
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }   // buffers grow: the captured pointers are stale
+        g.seen = false; g.gen = ~0ull;
+        if (attempt >= 8) return fail(PFC_E_CAPACITY, "candidate-pair / traction buffers kept overflowing");
+    }
+}
+static unsigned long long eval_key(int kind, const pfc_ctx* c, const EvalIO& io) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ull; };
+    mix((unsigned long long)kind); mix((unsigned long long)io.n_env); mix((unsigned long long)(uintptr_t)io.X); mix((unsigned long long)(uintptr_t)io.twist);
+    mix((unsigned long long)(uintptr_t)io.s); mix((unsigned long long)(uintptr_t)io.wrench); mix((unsigned long long)(uintptr_t)io.sdot);
+    mix((unsigned long long)(uintptr_t)io.n_pairs); mix((unsigned long long)(uintptr_t)io.flags); mix((unsigned long long)c->shard_rank * 64 + c->shard_world);
+    return h ? h : 1;
+}
+
 static int eval_device(pfc_ctx* c, const EvalIO& io) {
-    PFC_REQUEUE_LOOP({ const int rc_ = eval_device_once(c, io); if (rc_ != PFC_OK) return rc_; })
-    return PFC_OK;
+    return run_evaluation(c, eval_key(1, c, io), [&]() { return eval_device_once(c, io); });
 }
 
 // ---- small host-pointer calls: copies through a pinned arena ----------------------------------------------------------------
@@ -730,8 +802,7 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
     io.n_env = n_env; io.X = X; io.twist = twist; io.s = s; io.wrench = wrench; io.sdot = sdot;
     io.n_pairs = reinterpret_cast<long long*>(n_pairs); io.flags = flags;
     // one synchronisation at the end of what was queued: the traversal's and the bristle pipeline's buffers grow after the fact
-    PFC_REQUEUE_LOOP({ const int rc_ = sharded_enqueue(c, io); if (rc_ != PFC_OK) return rc_; })
-    return PFC_OK;
+    return run_evaluation(c, eval_key(2, c, io), [&]() { return sharded_enqueue(c, io); });
 }
 
 int pfc_eval_sharded_partials(pfc_ctx* c, double** dev_ptr, int64_t* count) {

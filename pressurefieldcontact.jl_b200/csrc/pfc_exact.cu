@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(32 * WPB) exact_bristle_kernel(SceneDev sc, Ex
 
 template <class T> cudaError_t ensure_buf(T*& p, size_t& cap, size_t need) {
     if (need <= cap) return cudaSuccess;
+    alloc_generation()++;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, need * sizeof(T));
@@ -321,6 +322,7 @@ cudaError_t exact_bristle_eval(const SceneDev& sc, const ExactScene& es, const E
 
 // After the caller synchronised the stream: 0 = the TractionCache buffer sufficed, 1 = it did not (capacity raised: queue the evaluation
 // again), -1 = it cannot be made large enough.
+void exact_mark_pending(ExactBuffers* b) { if (b && b->h_ctr) b->check_pending = true; }
 int exact_check(ExactBuffers* b) {
     if (!b || !b->check_pending) return 0;
     b->check_pending = false;

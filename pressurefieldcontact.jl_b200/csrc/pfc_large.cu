@@ -55,7 +55,7 @@ static_assert(kLargePartStride == kNA + 2, "partial record = kNA sums + point co
 constexpr int kMaxLevels = 132;   // breadth-first levels at most: two trees of depth <= 62 plus the roots (pfc_add_mesh rejects deeper trees)
 struct Counters {                 // device-resident
     unsigned int frontier_max;    // largest frontier any breadth-first level asked for (sizes the buffers of a repeated evaluation)
-    unsigned int pad_a;
+    unsigned int epoch;           // evaluation counter (kept across evaluations): tags the seeds donated during one traversal
     unsigned int seed_head;       // next seed to hand out
     unsigned int n_pairs;         // leaf pairs appended
     unsigned int overflow;        // bit0 frontier, bit1 pairs, bit2 stack
@@ -142,6 +142,7 @@ __global__ void init_frontier_kernel(LargeScene ls, long long n_env, Seed* front
     const long long n = n_env * ls.n_large;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) frontier[p] = Seed{(int)p, 0u, 0, 0};
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt->epoch += 1;   // (on the device, so that a captured CUDA graph of the evaluation can be replayed)
         cnt->frontier_max = (unsigned)n; cnt->seed_head = 0; cnt->n_pairs = 0; cnt->overflow = 0; cnt->n_units = 0;
         cnt->level_n[0] = (unsigned)n;
         for (int l = 1; l < kMaxLevels + 2; ++l) cnt->level_n[l] = 0;
@@ -235,9 +236,10 @@ PFC_D unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<con
 // K1b: warp-cooperative stack-based traversal of the seeds, with work donation
 template <int MINB>
 __global__ void __launch_bounds__(kDfsWarps * 32, MINB) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, Seed* seeds, unsigned cap_seeds,
-                                                                   unsigned epoch, int3* pairs, unsigned cap_pairs, Counters* cnt, unsigned hrank,
+                                                                   int3* pairs, unsigned cap_pairs, Counters* cnt, unsigned hrank,
                                                                    unsigned hworld) {
     __shared__ int2 stack_mem[kDfsWarps][kStackCap];   // per-warp circular stack: entry i lives at (base + i) & (kStackCap - 1)
+    const unsigned epoch = cnt->epoch;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int2* stack = stack_mem[wib];
     const unsigned n_seed0 = cnt->n_seed0;
@@ -687,6 +689,7 @@ __global__ void init_segments_kernel(unsigned* seg_start, unsigned* seg_end, uns
 
 template <class T> cudaError_t ensure(T*& p, size_t& cap, size_t need) {
     if (need <= cap) return cudaSuccess;
+    alloc_generation()++;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, need * sizeof(T));
@@ -709,7 +712,6 @@ struct LargeBuffers {
     int* chunk_points = nullptr; size_t cap_cp = 0;
     double* part = nullptr; size_t cap_part = 0;
     size_t cf2 = 0;
-    unsigned epoch = 0;   // traversal counter: tags the donated seeds of one broad_dfs_kernel launch
     Counters* h_cnt = nullptr;          // pinned copy of the counters of the last traversal
     bool check_pending = false;         // a traversal has been queued whose counters have not been looked at yet
     size_t want_frontier = 0, want_pairs = 0;
@@ -791,7 +793,7 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     int prob_bits = 0;
     while ((1ull << prob_bits) < (unsigned long long)n_prob) ++prob_bits;
     if (ls.key_bits + prob_bits > 64) return cudaErrorMemoryAllocation;   // (problem, DFS key) must fit one 64-bit sort key -> PFC_E_CAPACITY
-    if (!b->cnt) LCU(cudaMalloc(&b->cnt, sizeof(Counters)));
+    if (!b->cnt) { LCU(cudaMalloc(&b->cnt, sizeof(Counters))); LCU(cudaMemset(b->cnt, 0, sizeof(Counters))); }
     if (!b->h_cnt) LCU(cudaHostAlloc(reinterpret_cast<void**>(&b->h_cnt), sizeof(Counters), cudaHostAllocDefault));
     b->want_frontier = std::max<size_t>(b->want_frontier, std::max<size_t>(std::max<size_t>(b->cap_frontier, 1u << 18), (size_t)n_prob * 4));
     b->want_pairs = std::max<size_t>(b->want_pairs, std::max<size_t>(b->cap_pairs, 1u << 20));
@@ -856,13 +858,13 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     // what the levels left (nothing, when they ran to the leaves) is traversed with per-warp stacks; the split has been made by then
     dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, levels, (unsigned)b->cap_frontier);
     if (dfs_minb == 4)
-        broad_dfs_kernel<4><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs,
+        broad_dfs_kernel<4><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
                                                                      b->cnt, 0u, 1u);
     else if (dfs_minb == 3)
-        broad_dfs_kernel<3><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs,
+        broad_dfs_kernel<3><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
                                                                      b->cnt, 0u, 1u);
     else
-        broad_dfs_kernel<1><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, ++b->epoch, b->pairs, (unsigned)b->cap_pairs,
+        broad_dfs_kernel<1><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
                                                                      b->cnt, 0u, 1u);
     LCU(cudaMemcpyAsync(b->h_cnt, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));   // read by large_check() after the caller's synchronisation
     b->check_pending = true;
@@ -893,6 +895,8 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
 
 // After the caller synchronised the stream: did the traversal queued by the last large_broad_phase fit its buffers?
 // 0 = yes; 1 = no, the capacities have been raised and the evaluation must be queued again; -1 = it cannot fit.
+// a replayed CUDA graph of an evaluation contains the traversal and the copy of its counters: they must be looked at again
+void large_mark_pending(LargeBuffers* b) { if (b && b->h_cnt) b->check_pending = true; }
 int large_check(LargeBuffers* b) {
     if (!b || !b->check_pending) return 0;
     b->check_pending = false;

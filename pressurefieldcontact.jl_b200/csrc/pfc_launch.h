@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "pfc_types.cuh"
@@ -11,6 +12,10 @@ namespace pfc {
 // Launch-configuration cache.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and the persistent grid sizes depend on
 // the device's SM count, so what a launcher caches is keyed by (kernel family tag, variant, current device) -- several contexts on
 // different devices may live in one process (single-process multi-device, pfc_group) -- and guarded by one mutex.
+// Counts device (re)allocations of the growable buffers: a captured CUDA graph of an evaluation holds raw pointers, so it is only replayed
+// while this number is what it was at capture time.
+inline std::atomic<unsigned long long>& alloc_generation() { static std::atomic<unsigned long long> g{0}; return g; }
+
 struct LaunchSlot { int key0 = -1, key1 = -1, blocks = 0; size_t smem = 0; };
 constexpr int kMaxLaunchDevices = 64;
 inline std::mutex& launch_mutex() { static std::mutex m; return m; }
