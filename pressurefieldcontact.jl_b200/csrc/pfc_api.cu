@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -153,6 +154,11 @@ struct pfc_ctx {
     int64_t launches = 0;
     int shard_rank = 0, shard_world = 1;
     int small_max_pairs = 1;
+    int n_mid = 0;                       // instructions on the small path whose pair-list slot can overflow (see build_tables)
+    std::vector<char> force_large;       // instructions moved to the large path after such an overflow
+    DevBuf<int> d_ins_overflow;
+    int* h_ins_overflow = nullptr;       // pinned
+    bool mid_check_pending = false;
     DevBuf<unsigned> d_small_pairs;  // broad -> narrow pair lists of the small path: [env][ins][cap]
     // large path
     DevBuf<int32_t> d_large;
@@ -292,6 +298,7 @@ int pfc_destroy(pfc_ctx* c) {
     c->d_H.release(); c->d_Hinv.release(); c->d_xdot.release(); c->d_tau.release(); c->d_status.release(); c->d_refit_xyz.release(); c->d_refit_aabb.release();
     for (auto& r : c->refit) { r.idx.release(); r.eps.release(); r.level_nodes.release(); }
     if (c->h_status) { cudaFreeHost(c->h_status); c->h_status = nullptr; }
+    if (c->h_ins_overflow) { cudaFreeHost(c->h_ins_overflow); c->h_ins_overflow = nullptr; }
     if (c->h_arena) { cudaFreeHost(c->h_arena); c->h_arena = nullptr; }
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     c->d_large.release(); c->d_leaf_path.release(); c->d_leaf_depth.release();
@@ -392,6 +399,115 @@ int pfc_add_instruction(pfc_ctx* c, int mesh_1, int mesh_2, double chi, int mode
     return PFC_OK;
 }
 
+// Which path every instruction takes, and the device tables that follow from it.
+//   small  n_leaf1 * n_leaf2 <= 512: broad and narrow phase on chip, two launches per batch; the pair list cannot outgrow its slot.
+//   mid    both trees <= kMidLeaves leaves (gripper pads, coarse spheres): the same two kernels with a frontier / pair-list slot of
+//          kMidCap entries -- contact patches touch a small corner of such trees.  A frontier that outgrows the slot raises a per-instruction
+//          flag; the host then moves the instruction to the large path for good (force_large) and repeats the evaluation.
+//   large  everything else: the multi-kernel pipeline of pfc_large.cu.
+constexpr int kMidLeaves = 1024;
+constexpr int kMidCap = 1024;
+static int build_tables(pfc_ctx* c) {
+    const long long mid_leaves = getenv("PFC_MID_LEAVES") ? atoll(getenv("PFC_MID_LEAVES")) : kMidLeaves;   // (0: tests that want the large path on small trees)
+    c->h_ins.clear();
+    std::vector<int32_t> small, large;
+    int large_key_bits = 0;
+    c->small_max_pairs = 1;
+    c->n_mid = 0;
+    for (size_t k = 0; k < c->ins.size(); ++k) {
+        const HostIns& h = c->ins[k];
+        const HostMesh& m1 = c->mesh[h.mesh_1];
+        const HostMesh& m2 = c->mesh[h.mesh_2];
+        InsDev d{};
+        d.kind1 = m1.kind; d.model = h.model; d.n_quad = h.n_quad_rule == 1 ? 1 : 3; d.bristle_id = h.bristle_id;
+        d.node_base1 = m1.node_base; d.node_base2 = m2.node_base; d.prim_base1 = m1.prim_base; d.prim_base2 = m2.prim_base;
+        d.n_leaf1 = int(m1.n_prim); d.n_leaf2 = int(m2.n_prim);
+        d.key_bits = m1.depth + m2.depth;
+        if (d.key_bits > 64) return fail(PFC_E_MESH, "pfc_finalize: tree depths sum to more than 64 levels");
+        const bool fits_slot = m1.n_prim * m2.n_prim <= kSmallCap;
+        const bool mid = !fits_slot && m1.n_prim <= mid_leaves && m2.n_prim <= mid_leaves && !c->force_large[k];
+        d.small = (fits_slot || mid) ? 1 : 0;
+        d.chi = h.chi; d.Ebar1 = m1.kind == 1 ? m1.Ebar : 0.0; d.Ebar2 = m2.Ebar;
+        if (h.model == 0) { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = 2 * h.params[2]; d.p[4] = 3 * h.params[2];
+            d.p[5] = (d.p[1] - d.p[0]) / (d.p[4] - d.p[3]); d.p[6] = 1.0 / d.p[2]; }
+        else { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = h.params[3]; d.p[4] = 2 * h.params[2]; d.p[5] = 3 * h.params[2]; d.p[6] = h.params[4];
+            d.p[7] = (d.p[3] - d.p[2]) / (d.p[5] - d.p[4]); }
+        d.path_base1 = m1.path_base; d.path_base2 = m2.path_base;
+        if (d.small) {
+            small.push_back(int32_t(k));
+            c->small_max_pairs = std::max(c->small_max_pairs, mid ? kMidCap : int(m1.n_prim * m2.n_prim));
+            c->n_mid += mid;
+        } else { large.push_back(int32_t(k)); large_key_bits = std::max(large_key_bits, d.key_bits); }
+        c->h_ins.push_back(d);
+    }
+    c->large_ins_host = large;
+    c->large_scene = LargeScene{};
+    if (!large.empty()) {
+        CU(c->d_large.ensure(large.size()));
+        CU(cudaMemcpy(c->d_large.p, large.data(), large.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->large_scene.large_ins = c->d_large.p;
+        c->large_scene.leaf_path = c->d_leaf_path.p;
+        c->large_scene.leaf_depth = c->d_leaf_depth.p;
+        c->large_scene.n_large = int(large.size());
+        c->large_scene.key_bits = large_key_bits;
+        for (int32_t k : large) {
+            c->large_scene.max_leaves = std::max(c->large_scene.max_leaves, std::max(c->h_ins[k].n_leaf1, c->h_ins[k].n_leaf2));
+            c->large_scene.max_depth = std::max(c->large_scene.max_depth, std::max(c->mesh[c->ins[k].mesh_1].depth, c->mesh[c->ins[k].mesh_2].depth));
+        }
+        if (!c->large_buf) c->large_buf = large_buffers_create();
+    }
+    CU(c->d_ins.ensure(c->h_ins.size()));
+    CU(c->d_small.ensure(std::max<size_t>(small.size(), 1)));
+    CU(cudaMemcpy(c->d_ins.p, c->h_ins.data(), c->h_ins.size() * sizeof(InsDev), cudaMemcpyHostToDevice));
+    if (!small.empty()) CU(cudaMemcpy(c->d_small.p, small.data(), small.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    {   // broad-phase scheduling order: instruction-major, the instructions with the largest trees first
+        std::vector<int32_t> heavy(small);
+        std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t a, int32_t b) {
+            return (long long)c->h_ins[a].n_leaf1 * c->h_ins[a].n_leaf2 > (long long)c->h_ins[b].n_leaf1 * c->h_ins[b].n_leaf2; });
+        CU(c->d_small_heavy.ensure(std::max<size_t>(heavy.size(), 1)));
+        if (!heavy.empty()) CU(cudaMemcpy(c->d_small_heavy.p, heavy.data(), heavy.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->scene.small_heavy_first = c->d_small_heavy.p;
+        int lo = INT32_MAX, hi = 0;
+        for (int32_t k : small) {
+            const InsDev& in = c->h_ins[k];
+            lo = std::min(lo, std::min(in.node_base1, in.node_base2));
+            hi = std::max(hi, std::max(in.node_base1 + 2 * in.n_leaf1 - 1, in.node_base2 + 2 * in.n_leaf2 - 1));
+        }
+        c->scene.small_node_lo = small.empty() ? 0 : lo;
+        c->scene.small_node_n = small.empty() ? 0 : hi - lo;
+    }
+    if (c->n_mid > 0) {   // per-instruction overflow marks of the mid instructions
+        CU(c->d_ins_overflow.ensure(c->h_ins.size()));
+        CU(cudaMemset(c->d_ins_overflow.p, 0, sizeof(int) * c->h_ins.size()));
+        if (!c->h_ins_overflow) CU(cudaHostAlloc(reinterpret_cast<void**>(&c->h_ins_overflow), sizeof(int) * std::max<size_t>(c->h_ins.size(), 1), cudaHostAllocDefault));
+    }
+    c->scene.nodes = c->d_nodes.p; c->scene.tets = c->d_tets.p; c->scene.tris = c->d_tris.p; c->scene.ins = c->d_ins.p;
+    c->scene.small_ins = c->d_small.p;
+    c->scene.ins_overflow = c->n_mid > 0 ? c->d_ins_overflow.p : nullptr;
+    c->scene.n_ins = int(c->h_ins.size()); c->scene.n_small = int(small.size()); c->scene.n_bristle = c->n_bristle;
+    c->scene.n_small_bristle = 0;
+    for (int32_t k : small) c->scene.n_small_bristle += (c->h_ins[k].model == PFC_MODEL_BRISTLE);
+    {   // bristle instructions: tables of the reference-order pipeline
+        std::vector<int32_t> bris, large_index(c->h_ins.size(), -1);
+        for (size_t k = 0; k < c->h_ins.size(); ++k) if (c->h_ins[k].model == PFC_MODEL_BRISTLE) bris.push_back(int32_t(k));
+        for (size_t k = 0; k < large.size(); ++k) large_index[large[k]] = int32_t(k);
+        CU(c->d_large_index.ensure(large_index.size()));
+        CU(cudaMemcpy(c->d_large_index.p, large_index.data(), sizeof(int32_t) * large_index.size(), cudaMemcpyHostToDevice));
+        c->large_index_dirty = false;
+        c->has_large_bristle = false;
+        for (int32_t k : large) c->has_large_bristle |= (c->h_ins[k].model == PFC_MODEL_BRISTLE);
+        if (!bris.empty()) {
+            CU(c->d_bris_ins.ensure(bris.size()));
+            CU(cudaMemcpy(c->d_bris_ins.p, bris.data(), sizeof(int32_t) * bris.size(), cudaMemcpyHostToDevice));
+            if (!c->exact_buf) c->exact_buf = exact_buffers_create();
+        }
+        c->exact_scene.tet_eps = c->d_tet_eps.p; c->exact_scene.bris_ins = c->d_bris_ins.p; c->exact_scene.large_index = c->d_large_index.p;
+        c->exact_scene.n_bris = int32_t(bris.size()); c->exact_scene.skip_large = 0;
+    }
+    alloc_generation()++;   // (a captured evaluation graph holds the old tables' launch sequence)
+    return PFC_OK;
+}
+
 int pfc_finalize(pfc_ctx* c, int64_t max_env) {
     if (!c || c->finalized) return fail(PFC_E_ARG, "pfc_finalize: context missing or already finalized");
     if (c->ins.empty()) return fail(PFC_E_ARG, "pfc_finalize: no contact instructions");
@@ -434,107 +550,30 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
             }
         }
     }
-    c->h_ins.clear();
-    std::vector<int32_t> small, large;
-    int large_key_bits = 0;
-    std::vector<unsigned long long> leaf_path;
-    std::vector<unsigned char> leaf_depth;
-    for (auto& m : c->mesh) {
-        m.path_base = int(leaf_path.size());
-        for (int64_t k = 0; k < m.n_prim; ++k) { leaf_path.push_back(m.leaf_path[k]); leaf_depth.push_back((unsigned char)m.leaf_depth[k]); }
-    }
-    for (size_t k = 0; k < c->ins.size(); ++k) {
-        const HostIns& h = c->ins[k];
-        const HostMesh& m1 = c->mesh[h.mesh_1];
-        const HostMesh& m2 = c->mesh[h.mesh_2];
-        InsDev d{};
-        d.kind1 = m1.kind; d.model = h.model; d.n_quad = h.n_quad_rule == 1 ? 1 : 3; d.bristle_id = h.bristle_id;
-        d.node_base1 = m1.node_base; d.node_base2 = m2.node_base; d.prim_base1 = m1.prim_base; d.prim_base2 = m2.prim_base;
-        d.n_leaf1 = int(m1.n_prim); d.n_leaf2 = int(m2.n_prim);
-        d.key_bits = m1.depth + m2.depth;
-        if (d.key_bits > 64) return fail(PFC_E_MESH, "pfc_finalize: tree depths sum to more than 64 levels");
-        d.small = (m1.n_prim * m2.n_prim <= kSmallCap && m1.n_prim < 16384 && m2.n_prim < 16384) ? 1 : 0;
-        d.chi = h.chi; d.Ebar1 = m1.kind == 1 ? m1.Ebar : 0.0; d.Ebar2 = m2.Ebar;
-        if (h.model == 0) { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = 2 * h.params[2]; d.p[4] = 3 * h.params[2];
-            d.p[5] = (d.p[1] - d.p[0]) / (d.p[4] - d.p[3]); d.p[6] = 1.0 / d.p[2]; }
-        else { d.p[0] = h.params[0]; d.p[1] = h.params[1]; d.p[2] = h.params[2]; d.p[3] = h.params[3]; d.p[4] = 2 * h.params[2]; d.p[5] = 3 * h.params[2]; d.p[6] = h.params[4];
-            d.p[7] = (d.p[3] - d.p[2]) / (d.p[5] - d.p[4]); }
-        d.path_base1 = m1.path_base; d.path_base2 = m2.path_base;
-        if (d.small) { small.push_back(int32_t(k)); c->small_max_pairs = std::max(c->small_max_pairs, int(m1.n_prim * m2.n_prim)); }
-        else { large.push_back(int32_t(k)); large_key_bits = std::max(large_key_bits, d.key_bits); }
-        c->h_ins.push_back(d);
-    }
-    // large path tables: per-primitive leaf paths (DFS keys) for every mesh
-    c->large_ins_host = large;
-    if (!large.empty()) {
-        CU(c->d_large.ensure(large.size()));
-        CU(cudaMemcpy(c->d_large.p, large.data(), large.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CU(c->d_leaf_path.ensure(leaf_path.size()));
-        CU(c->d_leaf_depth.ensure(leaf_depth.size()));
+    {   // per-primitive leaf paths (the DFS keys of the large path) for every mesh: uploaded whether or not an instruction needs them yet
+        std::vector<unsigned long long> leaf_path;
+        std::vector<unsigned char> leaf_depth;
+        for (auto& m : c->mesh) {
+            m.path_base = int(leaf_path.size());
+            for (int64_t k = 0; k < m.n_prim; ++k) { leaf_path.push_back(m.leaf_path[k]); leaf_depth.push_back((unsigned char)m.leaf_depth[k]); }
+        }
+        CU(c->d_leaf_path.ensure(std::max<size_t>(leaf_path.size(), 1)));
+        CU(c->d_leaf_depth.ensure(std::max<size_t>(leaf_depth.size(), 1)));
         CU(cudaMemcpy(c->d_leaf_path.p, leaf_path.data(), leaf_path.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_leaf_depth.p, leaf_depth.data(), leaf_depth.size(), cudaMemcpyHostToDevice));
-        c->large_scene.large_ins = c->d_large.p;
-        c->large_scene.leaf_path = c->d_leaf_path.p;
-        c->large_scene.leaf_depth = c->d_leaf_depth.p;
-        c->large_scene.n_large = int(large.size());
-        c->large_scene.key_bits = large_key_bits;
-        c->large_scene.max_leaves = 0;
-        c->large_scene.max_depth = 0;
-        for (int32_t k : large) {
-            c->large_scene.max_leaves = std::max(c->large_scene.max_leaves, std::max(c->h_ins[k].n_leaf1, c->h_ins[k].n_leaf2));
-            c->large_scene.max_depth = std::max(c->large_scene.max_depth, std::max(c->mesh[c->ins[k].mesh_1].depth, c->mesh[c->ins[k].mesh_2].depth));
-        }
-        if (!c->large_buf) c->large_buf = large_buffers_create();
     }
     CU(c->d_nodes.ensure(nodes.size()));
     CU(c->d_tets.ensure(std::max<size_t>(tets.size(), 1)));
     CU(c->d_tris.ensure(std::max<size_t>(tris.size(), 1)));
-    CU(c->d_ins.ensure(c->h_ins.size()));
-    CU(c->d_small.ensure(std::max<size_t>(small.size(), 1)));
     CU(cudaMemcpy(c->d_nodes.p, nodes.data(), nodes.size() * sizeof(NodeRec), cudaMemcpyHostToDevice));
     if (!tets.empty()) CU(cudaMemcpy(c->d_tets.p, tets.data(), tets.size() * sizeof(TetRec), cudaMemcpyHostToDevice));
     if (!tris.empty()) CU(cudaMemcpy(c->d_tris.p, tris.data(), tris.size() * sizeof(TriRec), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_ins.p, c->h_ins.data(), c->h_ins.size() * sizeof(InsDev), cudaMemcpyHostToDevice));
-    if (!small.empty()) CU(cudaMemcpy(c->d_small.p, small.data(), small.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    {   // broad-phase scheduling order: instruction-major, the instructions with the largest trees first
-        std::vector<int32_t> heavy(small);
-        std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t a, int32_t b) {
-            return (long long)c->h_ins[a].n_leaf1 * c->h_ins[a].n_leaf2 > (long long)c->h_ins[b].n_leaf1 * c->h_ins[b].n_leaf2; });
-        CU(c->d_small_heavy.ensure(std::max<size_t>(heavy.size(), 1)));
-        if (!heavy.empty()) CU(cudaMemcpy(c->d_small_heavy.p, heavy.data(), heavy.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        c->scene.small_heavy_first = c->d_small_heavy.p;
-        int lo = INT32_MAX, hi = 0;
-        for (int32_t k : small) {
-            const InsDev& in = c->h_ins[k];
-            lo = std::min(lo, std::min(in.node_base1, in.node_base2));
-            hi = std::max(hi, std::max(in.node_base1 + 2 * in.n_leaf1 - 1, in.node_base2 + 2 * in.n_leaf2 - 1));
-        }
-        c->scene.small_node_lo = small.empty() ? 0 : lo;
-        c->scene.small_node_n = small.empty() ? 0 : hi - lo;
-    }
-    c->scene.nodes = c->d_nodes.p; c->scene.tets = c->d_tets.p; c->scene.tris = c->d_tris.p; c->scene.ins = c->d_ins.p;
-    c->scene.small_ins = c->d_small.p;
-    c->scene.n_ins = int(c->h_ins.size()); c->scene.n_small = int(small.size()); c->scene.n_bristle = c->n_bristle;
-    c->scene.n_small_bristle = 0;
-    for (int32_t k : small) c->scene.n_small_bristle += (c->h_ins[k].model == PFC_MODEL_BRISTLE);
-    {   // bristle instructions: tables of the reference-order pipeline
-        std::vector<int32_t> bris, large_index(c->h_ins.size(), -1);
-        for (size_t k = 0; k < c->h_ins.size(); ++k) if (c->h_ins[k].model == PFC_MODEL_BRISTLE) bris.push_back(int32_t(k));
-        for (size_t k = 0; k < large.size(); ++k) large_index[large[k]] = int32_t(k);
-        CU(c->d_large_index.ensure(large_index.size()));
-        CU(cudaMemcpy(c->d_large_index.p, large_index.data(), sizeof(int32_t) * large_index.size(), cudaMemcpyHostToDevice));
-        c->large_index_dirty = false;
-        c->has_large_bristle = false;
-        for (int32_t k : large) c->has_large_bristle |= (c->h_ins[k].model == PFC_MODEL_BRISTLE);
-        if (!bris.empty()) {
-            CU(c->d_bris_ins.ensure(bris.size()));
-            CU(cudaMemcpy(c->d_bris_ins.p, bris.data(), sizeof(int32_t) * bris.size(), cudaMemcpyHostToDevice));
-            CU(c->d_tet_eps.ensure(std::max<size_t>(tet_eps.size(), 4)));
-            if (!tet_eps.empty()) CU(cudaMemcpy(c->d_tet_eps.p, tet_eps.data(), sizeof(double) * tet_eps.size(), cudaMemcpyHostToDevice));
-            if (!c->exact_buf) c->exact_buf = exact_buffers_create();
-        }
-        c->exact_scene.tet_eps = c->d_tet_eps.p; c->exact_scene.bris_ins = c->d_bris_ins.p; c->exact_scene.large_index = c->d_large_index.p;
-        c->exact_scene.n_bris = int32_t(bris.size()); c->exact_scene.skip_large = 0;
+    CU(c->d_tet_eps.ensure(std::max<size_t>(tet_eps.size(), 4)));
+    if (!tet_eps.empty()) CU(cudaMemcpy(c->d_tet_eps.p, tet_eps.data(), sizeof(double) * tet_eps.size(), cudaMemcpyHostToDevice));
+    c->force_large.assign(c->ins.size(), 0);
+    {
+        const int rc = build_tables(c);
+        if (rc != PFC_OK) return rc;
     }
     c->max_env = max_env;
     c->finalized = true;
@@ -561,11 +600,24 @@ static int eval_bristle_exact(pfc_ctx* c, long long n_env, const double* X, cons
 // After an evaluation has been queued: one synchronisation, then the device-side counters say whether everything fit.  Returns 0 (it
 // did, or nothing growable was involved: no synchronisation then), 1 (capacities raised: queue the same evaluation again) or a
 // negative PFC_E_* code.
+static int build_tables(pfc_ctx* c);
 static int evaluation_fits(pfc_ctx* c) {
-    const bool lg = c->large_buf != nullptr, ex = c->exact_buf != nullptr;
-    if (!lg && !ex) return 0;
+    const bool lg = c->large_buf != nullptr, ex = c->exact_buf != nullptr, mid = c->n_mid > 0;
+    if (!lg && !ex && !mid) return 0;
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(PFC_E_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    int m = 0;
+    if (mid && c->mid_check_pending) {   // a mid-size instruction outgrew its on-chip slot: it takes the large path from now on
+        c->mid_check_pending = false;
+        for (size_t k = 0; k < c->h_ins.size(); ++k)
+            if (c->h_ins_overflow[k]) { c->force_large[k] = 1; m = 1; }
+        if (m) {
+            const int rc = build_tables(c);
+            if (rc != PFC_OK) return rc;
+            large_mark_clear(c->large_buf); exact_mark_clear(c->exact_buf);   // the evaluation is repeated as a whole
+            return 1;
+        }
+    }
     const int a = lg ? large_check(c->large_buf) : 0, b = ex ? exact_check(c->exact_buf) : 0;
     if (a < 0 || b < 0) return fail(PFC_E_CAPACITY, "candidate-pair / traction buffers cannot be grown far enough");
     return (a | b) ? 1 : 0;
@@ -583,7 +635,7 @@ static int eval_device_once(pfc_ctx* c, const EvalIO& io_in) {
     EvalIO io = io_in;
     const int n_ins = c->scene.n_ins;
     if (c->keep_pairs) {
-        c->dbg_cap = kSmallCap;
+        c->dbg_cap = std::max(kSmallCap, small_cap(c->small_max_pairs));
         CU(c->d_dbg_pairs.ensure(size_t(2) * c->dbg_cap * io.n_env * n_ins));
         io.dbg_pairs = c->d_dbg_pairs.p;
         io.dbg_cap = c->dbg_cap;
@@ -603,6 +655,10 @@ static int eval_device_once(pfc_ctx* c, const EvalIO& io_in) {
     {   // bristle instructions (small and large): reference-order pipeline
         int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
         if (rc != PFC_OK) return rc;
+    }
+    if (c->n_mid > 0) {
+        CU(cudaMemcpyAsync(c->h_ins_overflow, c->d_ins_overflow.p, sizeof(int) * c->h_ins.size(), cudaMemcpyDeviceToHost, c->stream));
+        c->mid_check_pending = true;
     }
     c->launches += nl;
     c->last_X = io.X; c->last_tw = io.twist;
@@ -653,6 +709,7 @@ static int run_evaluation(pfc_ctx* c, unsigned long long key, const std::functio
         if (replayed) {
             large_mark_pending(c->large_buf);
             exact_mark_pending(c->exact_buf);
+            if (c->n_mid > 0) c->mid_check_pending = true;
         } else {
             const int rc = enqueue();
             if (rc != PFC_OK) return rc;
@@ -780,6 +837,10 @@ static int sharded_enqueue(pfc_ctx* c, const EvalIO& io) {
     CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, c->shard_world > 1, 0, c->stream, &nl));
     int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
     if (rc != PFC_OK) return rc;
+    if (c->n_mid > 0) {
+        CU(cudaMemcpyAsync(c->h_ins_overflow, c->d_ins_overflow.p, sizeof(int) * c->h_ins.size(), cudaMemcpyDeviceToHost, c->stream));
+        c->mid_check_pending = true;
+    }
     c->launches += nl;
     c->sharded_io = io;
     c->sharded_stage = 0;

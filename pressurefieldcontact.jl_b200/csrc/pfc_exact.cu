@@ -322,6 +322,7 @@ cudaError_t exact_bristle_eval(const SceneDev& sc, const ExactScene& es, const E
 
 // After the caller synchronised the stream: 0 = the TractionCache buffer sufficed, 1 = it did not (capacity raised: queue the evaluation
 // again), -1 = it cannot be made large enough.
+void exact_mark_clear(ExactBuffers* b) { if (b) b->check_pending = false; }
 void exact_mark_pending(ExactBuffers* b) { if (b && b->h_ctr) b->check_pending = true; }
 int exact_check(ExactBuffers* b) {
     if (!b || !b->check_pending) return 0;

@@ -42,7 +42,8 @@ unsigned exact_last_points(const ExactBuffers* b);
 // grows like the reference's VectorCache (src/obb/vector_cache.jl:11-15): after the caller synchronised the stream, exact_check() says
 // whether it sufficed (0), or was raised so that the evaluation must be queued again (1), or cannot be made large enough (-1).
 int exact_check(ExactBuffers* b);
-void exact_mark_pending(ExactBuffers* b);   // after replaying a captured evaluation
+void exact_mark_pending(ExactBuffers* b);
+void exact_mark_clear(ExactBuffers* b);   // after replaying a captured evaluation
 cudaError_t exact_bristle_eval(const SceneDev& sc, const ExactScene& es, const ExactIO& io, const ExactPairs& ps, int dual, ExactBuffers* b, cudaStream_t stream,
                                int* n_launches);
 

@@ -498,10 +498,13 @@ __global__ void __launch_bounds__(128) radix_scatter_kernel(const unsigned long 
 // Short lists (a single small scene): one CTA sorts (key, value) in shared memory with a bitonic network instead of 5 x 3 launches of
 // the radix passes.  Keys are distinct (a key encodes both root-to-leaf paths), so stability is not needed.
 // (may run in place: everything is read into shared memory before anything is written)
-__global__ void __launch_bounds__(1024) small_sort_kernel(const unsigned long long* keys_in, const unsigned* vals_in, const Counters* cnt, unsigned cap_pairs,
-                                                          unsigned long long* keys_out, unsigned* vals_out) {
+// radix_queued = 0: the host left the radix passes out (the previous evaluation's list was short); a list that turns out longer raises
+// overflow bit 8 and the host repeats the evaluation with the passes queued.
+__global__ void __launch_bounds__(1024) small_sort_kernel(const unsigned long long* keys_in, const unsigned* vals_in, Counters* cnt, unsigned cap_pairs,
+                                                          unsigned long long* keys_out, unsigned* vals_out, int radix_queued) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     const unsigned n = listed_pairs(cnt, cap_pairs);
+    if (n > kSmallSort && !radix_queued && threadIdx.x == 0) atomicOr(&cnt->overflow, 8u);
     if (n == 0 || n > kSmallSort) return;
     unsigned m = 1;
     while (m < n) m <<= 1;
@@ -567,60 +570,158 @@ __global__ void __launch_bounds__(1024) units_scan_kernel(const unsigned* __rest
     (void)shard_rank; (void)shard_world;
 }
 
-// K2: one thread per sorted pair of a REGULARIZED instruction; fixed-order block reduction per chunk.  (Bristle instructions keep their
-// sorted pair lists and are evaluated by the reference-order pipeline, pfc_exact.cu.)
-__global__ void __launch_bounds__(kChunk) narrow_large_kernel(SceneDev sc, LargeScene ls, EvalIO io, const int3* __restrict__ sorted, const unsigned* __restrict__ seg_start,
-                                                              const unsigned* __restrict__ seg_end, const unsigned* __restrict__ unit_start, unsigned n_prob,
-                                                              const Counters* cnt, double* chunk_out, int* chunk_points, int* prob_flags) {
-    __shared__ double red[kChunk / 32][kNA];
-    __shared__ int red_pts[kChunk / 32];
-    __shared__ int s_prob;
+// K2: narrow phase of the REGULARIZED instructions, one CTA per unit of 256 sorted pairs of one problem, in the phases of the small path's
+// tile kernel (pfc_small.cu) so that the divergent clip and the dense quadrature each get full warps:
+//   1. one candidate pair per thread up to its start polygon in registers (exact rejection);
+//   2. block scan: the survivors are packed, in pair order, into shared-memory polygon slots; slot d is clipped in place by thread d;
+//   3. block scan of the vertex counts -> dense (slot, edge) list, one sub-triangle per thread (quadrature, pressure law, friction);
+//   4. the unit's 6 sums + point count in item order by one warp (lane-strided partials + xor-butterfly: bitwise reproducible).
+// (Bristle instructions keep their sorted pair lists and are evaluated by the reference-order pipeline, pfc_exact.cu.)
+// The first version ran one thread per pair through clip + all sub-triangles: 12.7 of 32 lanes busy, 389 us for the 0.9 M pairs of C5.
+constexpr int kLPolyStride = 35;
+static_assert(sizeof(PolyRec<double>) == kLPolyStride * sizeof(double), "PolyRec<double> is 35 doubles");
+struct NarrowLargeSmem {
+    double poly[kChunk * kLPolyStride];
+    double item_res[kChunk * 7];
+    PatchCtx<double> cx;
+    double fpv[8];
+    double tot[8];
+    unsigned short items[kChunk * 8];
+    int2 slot_pair[kChunk];
+    unsigned char slot_n[kChunk];
+    int warp_tot[kChunk / 32];
+    int s_prob;
+    int pflags;
+};
+
+__global__ void __launch_bounds__(kChunk, 2) narrow_large_kernel(SceneDev sc, LargeScene ls, EvalIO io, const int3* __restrict__ sorted, const unsigned* __restrict__ seg_start,
+                                                                 const unsigned* __restrict__ seg_end, const unsigned* __restrict__ unit_start, unsigned n_prob,
+                                                                 const Counters* cnt, double* chunk_out, int* chunk_points, int* prob_flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NarrowLargeSmem& sm = *reinterpret_cast<NarrowLargeSmem*>(smem_raw);
     const unsigned n_units = cnt->n_units;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    constexpr int NW = kChunk / 32;
     for (unsigned u = blockIdx.x; u < n_units; u += gridDim.x) {
-        if (threadIdx.x == 0) {  // unit -> problem by binary search in unit_start
+        if (tid == 0) {  // unit -> problem by binary search in unit_start
             unsigned lo = 0, hi = n_prob;
             while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (unit_start[mid] <= u) lo = mid; else hi = mid; }
-            s_prob = (int)lo;
+            sm.s_prob = (int)lo;
+            sm.pflags = 0;
         }
         __syncthreads();
-        const int p = s_prob;
+        const int p = sm.s_prob;
         long long env; int k;
         prob_to_ei(sc, ls, p, env, k);
         const InsDev& ins = sc.ins[k];
         if (ins.model != PFC_MODEL_REGULARIZED) { __syncthreads(); continue; }   // (block-uniform)
         const long long ei = env * sc.n_ins + k;
-        Accum<double, kNA> acc;
-        acc.reset(ACC_REGULARIZED);
-        int flags = 0;
-        const unsigned i = seg_start[p] + (u - unit_start[p]) * kChunk + threadIdx.x;
-        if (i < seg_end[p]) {
-            PatchCtx<double> cx;
-            load_xform_l(io.X + 16 * ei, cx.x21);
-            cx.x12 = inverse(cx.x21);
-            const double* tw = io.twist + 6 * ei;
-            cx.w_ang = mk<double>(tw[0], tw[1], tw[2]);
-            cx.w_lin = mk<double>(tw[3], tw[4], tw[5]);
-            cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
-            acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
-            const int3 pr = sorted[i];
-            integrate_pair(sc, ins, pr.y, pr.z, cx, acc, flags);
+        // ---- context: one element per lane of warp 0
+        if (wib == 0) {
+            const double* X = io.X + 16 * ei;
+            const double* twist = io.twist + 6 * ei;
+            PatchCtx<double>& cx = sm.cx;
+            if (lane < 8) sm.fpv[lane] = ins.p[lane];
+            if (lane < 9) { const int i = lane / 3, j = lane % 3; cx.x21.r[lane] = X[4 * j + i]; }
+            else if (lane < 12) cx.x21.t[lane - 9] = X[12 + lane - 9];
+            else if (lane < 21) { const int e = lane - 12, i = e / 3, j = e % 3; cx.x12.r[e] = X[4 * i + j]; }
+            else if (lane < 24) { const int i = lane - 21; cx.x12.t[i] = -(X[4 * i] * X[12] + X[4 * i + 1] * X[13] + X[4 * i + 2] * X[14]); }
+            else if (lane < 27) (&cx.w_ang.x)[lane - 24] = twist[lane - 24];
+            else if (lane < 30) (&cx.w_lin.x)[lane - 27] = twist[lane - 24];
+            else if (lane == 30) { cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad; }
+            if (lane < 8) sm.tot[lane] = 0.0;
         }
-        // fixed-order reduction: butterfly inside each warp, then warps 0..7 in order
-#pragma unroll
-        for (int j = 0; j < kNA; ++j) { const double v = warp_sum(acc.a[j]); if (lane == 0) red[w][j] = v; }
-        int pts = acc.n_points;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { pts += __shfl_xor_sync(0xffffffffu, pts, o); flags |= __shfl_xor_sync(0xffffffffu, flags, o); }
-        if (lane == 0) { red_pts[w] = pts; if (flags) atomicOr(&prob_flags[p], flags); }
         __syncthreads();
-        if (threadIdx.x < kNA) {
-            double s = red[0][threadIdx.x];
-#pragma unroll
-            for (int ww = 1; ww < kChunk / 32; ++ww) s += red[ww][threadIdx.x];
-            chunk_out[(size_t)u * kNA + threadIdx.x] = s;
+        // ---- 1. start polygons
+        const unsigned i = seg_start[p] + (u - unit_start[p]) * kChunk + tid;
+        double zr[16];
+        int n0 = 0;
+        int3 pr = make_int3(0, 0, 0);
+        if (i < seg_end[p]) {
+            pr = sorted[i];
+            n0 = start_polygon_zeta(sc, ins, pr.y, pr.z, sm.cx, zr);
         }
-        if (threadIdx.x == 0) { int s = 0; for (int ww = 0; ww < kChunk / 32; ++ww) s += red_pts[ww]; chunk_points[u] = s; }
+        // ---- 2. survivors -> slots in pair order; clip in place
+        const unsigned alive = __ballot_sync(0xffffffffu, n0 > 0);
+        if (lane == 0) sm.warp_tot[wib] = __popc(alive);
+        __syncthreads();
+        int before = 0, n_slot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; n_slot += t; }
+        if (n0 > 0) {
+            const int slot = before + __popc(alive & ((1u << lane) - 1u));
+            double* z = sm.poly + slot * kLPolyStride;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < 4 * n0) z[j] = zr[j];
+            sm.slot_pair[slot] = make_int2(pr.y, pr.z); sm.slot_n[slot] = (unsigned char)n0;
+        }
+        __syncthreads();
+        int nv = 0;
+        if (tid < n_slot) {
+            const int2 e = sm.slot_pair[tid];
+            PolyRec<double>& out = *reinterpret_cast<PolyRec<double>*>(sm.poly + tid * kLPolyStride);
+            int flags = 0;
+            const int n = clip_tet_inplace(reinterpret_cast<double*>(&out), (int)sm.slot_n[tid], flags);
+            if (n >= 3) {
+                finish_polygon_slot(n, sc.tets[ins.prim_base2 + e.y], pair_normal(sc, ins, e.x, e.y, sm.cx), out);
+                nv = n;
+            }
+            if (flags) atomicOr(&sm.pflags, flags);
+        }
+        // ---- 3. (slot, edge) items
+        int incl = nv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        __syncthreads();   // warp_tot of step 2 has been read
+        if (lane == 31) sm.warp_tot[wib] = incl;
+        __syncthreads();
+        int ibefore = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { const int t = sm.warp_tot[w]; if (w < wib) ibefore += t; total += t; }
+        const int at = ibefore + incl - nv;
+        for (int q = 0; q < nv; ++q) sm.items[at + q] = (unsigned short)((tid << 3) | q);
+        __syncthreads();
+        for (int i0 = 0; i0 < total; i0 += kChunk) {
+            const int i1 = min(total, i0 + kChunk);
+            const int it = i0 + tid;
+            if (it < i1) {
+                const int code = sm.items[it];
+                const int slot = code >> 3, q = code & 7;
+                const PolyRec<double>& prc = *reinterpret_cast<const PolyRec<double>*>(sm.poly + slot * kLPolyStride);
+                Accum<double, 6> tmp;
+                tmp.fp = sm.fpv; tmp.w_ang = sm.cx.w_ang; tmp.w_lin = sm.cx.w_lin; tmp.dump = nullptr; tmp.dump_cap = 0;
+                tmp.reset(ACC_REGULARIZED);
+                const int qp = (q == 0) ? prc.n - 1 : q - 1;
+                integrate_subtri(prc.v[qp], prc.v[q], prc.cen, prc.nrm, prc.eps_r, sm.cx, tmp);
+                double* res = sm.item_res + tid * 7;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) res[j] = tmp.a[j];
+                reinterpret_cast<int*>(res + 6)[0] = tmp.n_points;
+            }
+            __syncthreads();
+            // ---- 4. the round's items in order: lane l adds items l, l + 32, ..., then a xor-butterfly
+            if (wib == 0) {
+                double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                int part_n = 0;
+                for (int j = lane; j < i1 - i0; j += 32) {
+                    const double* res = sm.item_res + j * 7;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) part[c] += res[c];
+                    part_n += reinterpret_cast<const int*>(res + 6)[0];
+                }
+                int pn = part_n;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) pn += __shfl_xor_sync(0xffffffffu, pn, o);
+                double mine = (double)pn;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { const double t = warp_sum(part[c]); mine = (lane == c) ? t : mine; }
+                if (lane < 7) sm.tot[lane] += mine;
+            }
+            __syncthreads();
+        }
+        if (tid < kNA) chunk_out[(size_t)u * kNA + tid] = sm.tot[tid];
+        if (tid == 0) { chunk_points[u] = (int)sm.tot[6]; if (sm.pflags) atomicOr(&prob_flags[p], sm.pflags); }
         __syncthreads();
     }
 }
@@ -715,6 +816,7 @@ struct LargeBuffers {
     Counters* h_cnt = nullptr;          // pinned copy of the counters of the last traversal
     bool check_pending = false;         // a traversal has been queued whose counters have not been looked at yet
     size_t want_frontier = 0, want_pairs = 0;
+    bool force_radix = false, radix_wanted = true;
     unsigned last_n_pairs = 0;
     unsigned long long last_n_tests = 0;
 };
@@ -878,24 +980,28 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     const int total_bits = ls.key_bits + prob_bits;
     const int n_pass = (total_bits + 7) / 8;
     const int fin = n_pass & 1;   // where the radix passes leave the sorted keys; short lists are sorted into the same buffer by one CTA
+    // single small scenes: when the previous evaluation listed few pairs the 3 x n_pass radix launches (which would all return at once) are
+    // left out; small_sort_kernel raises a flag if the list is long after all
+    const bool radix_queued = b->radix_wanted;   // (decided by large_check after the previous evaluation)
     int cur = 0;
-    for (int pass = 0; pass < n_pass; ++pass) {
+    for (int pass = 0; pass < n_pass && radix_queued; ++pass) {
         radix_hist_kernel<<<(cap_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->cnt, (unsigned)cap, 8 * pass, b->hist, cap_tiles);
         radix_rowscan_kernel<<<256, 256, 0, stream>>>(b->hist, b->cnt, (unsigned)cap, cap_tiles, tot);
         radix_scatter_kernel<<<(cap_tiles + 3) / 4, 128, 0, stream>>>(b->keys[cur], b->vals[cur], b->cnt, (unsigned)cap, 8 * pass, b->hist, tot, cap_tiles, b->keys[cur ^ 1],
                                                                     b->vals[cur ^ 1]);
         cur ^= 1;
     }
-    small_sort_kernel<<<1, 1024, kSmallSort * 12, stream>>>(b->keys[0], b->vals[0], b->cnt, (unsigned)cap, b->keys[fin], b->vals[fin]);
+    small_sort_kernel<<<1, 1024, kSmallSort * 12, stream>>>(b->keys[0], b->vals[0], b->cnt, (unsigned)cap, b->keys[fin], b->vals[fin], radix_queued ? 1 : 0);
     gather_sorted_kernel<<<g, 256, 0, stream>>>(b->pairs, b->vals[fin], b->cnt, (unsigned)cap, b->sorted, b->seg_start, b->seg_end);
     units_scan_kernel<<<1, 1024, 0, stream>>>(b->seg_start, b->seg_end, n_prob, b->unit_start, b->cnt, 0, 1);
-    if (n_launches) *n_launches += 6 + 3 * n_pass;
+    if (n_launches) *n_launches += 6 + (radix_queued ? 3 * n_pass : 0);
     return cudaGetLastError();
 }
 
 // After the caller synchronised the stream: did the traversal queued by the last large_broad_phase fit its buffers?
 // 0 = yes; 1 = no, the capacities have been raised and the evaluation must be queued again; -1 = it cannot fit.
 // a replayed CUDA graph of an evaluation contains the traversal and the copy of its counters: they must be looked at again
+void large_mark_clear(LargeBuffers* b) { if (b) b->check_pending = false; }
 void large_mark_pending(LargeBuffers* b) { if (b && b->h_cnt) b->check_pending = true; }
 int large_check(LargeBuffers* b) {
     if (!b || !b->check_pending) return 0;
@@ -903,6 +1009,7 @@ int large_check(LargeBuffers* b) {
     const Counters& h = *b->h_cnt;
     if (h.overflow & 4u) return -1;
     bool again = false;
+    if (h.overflow & 8u) { b->force_radix = true; b->radix_wanted = true; alloc_generation()++; again = true; }   // the list outgrew the one-CTA sort
     if (h.overflow & 1u) {
         const size_t need = (size_t)std::max(h.frontier_max, h.q_tail) + 1024;   // (levels below an overflowing one were cut short: leave room)
         b->want_frontier = std::max<size_t>(b->cap_frontier * 2, need * 2);
@@ -915,6 +1022,8 @@ int large_check(LargeBuffers* b) {
     if (again) return (b->want_pairs > (1ull << 31) || b->want_frontier > (1ull << 31)) ? -1 : 1;
     b->last_n_pairs = h.n_pairs;
     b->last_n_tests = h.n_tests;
+    const bool want = b->force_radix || h.n_pairs > kSmallSort / 2;
+    if (want != b->radix_wanted) { b->radix_wanted = want; alloc_generation()++; }   // the launch sequence changes: a captured graph of it is stale
     return 0;
 }
 
@@ -932,9 +1041,15 @@ cudaError_t large_narrow_stage(const SceneDev& sc, const LargeScene& ls, const E
     LCU(ensure(b->chunk_points, b->cap_cp, max_units));
     if (partial_only) LCU(ensure(b->part, b->cap_part, (size_t)n_prob * kLargePartStride));
     if (!apply_parts) {
-        const unsigned grid = (unsigned)std::min<size_t>(max_units, (size_t)n_sm * 16);
-        narrow_large_kernel<<<grid, kChunk, 0, stream>>>(sc, ls, io, b->sorted, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, b->chunk_out, b->chunk_points,
-                                                        b->prob_flags);
+        {
+            struct Tag {};
+            std::lock_guard<std::mutex> g(launch_mutex());
+            LaunchSlot& sl = launch_slot<Tag>();
+            if (sl.key0 != 1) { LCU(cudaFuncSetAttribute(narrow_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowLargeSmem))); sl.key0 = 1; }
+        }
+        const unsigned grid = (unsigned)std::min<size_t>(max_units, (size_t)n_sm * 2);   // persistent: 2 CTAs per SM (93 KB of shared memory each)
+        narrow_large_kernel<<<grid, kChunk, sizeof(NarrowLargeSmem), stream>>>(sc, ls, io, b->sorted, b->seg_start, b->seg_end, b->unit_start, n_prob, b->cnt, b->chunk_out,
+                                                                               b->chunk_points, b->prob_flags);
         if (n_launches) *n_launches += 1;
     }
     finish_large_kernel<<<std::min<unsigned>((n_prob + 3) / 4, (unsigned)n_sm * 8), 128, 0, stream>>>(

@@ -35,7 +35,8 @@ void large_exact_view(const LargeBuffers* b, const LargeScene& ls, long long n_e
 // after the caller's stream synchronisation: 0 = the last traversal fit its buffers, 1 = it did not (capacities raised: queue the evaluation
 // again), -1 = it cannot fit
 int large_check(LargeBuffers* b);
-void large_mark_pending(LargeBuffers* b);   // after replaying a captured evaluation
+void large_mark_pending(LargeBuffers* b);
+void large_mark_clear(LargeBuffers* b);   // after replaying a captured evaluation
 cudaError_t large_write_counts(const SceneDev& sc, const LargeScene& ls, const EvalIO& io, LargeBuffers* b, cudaStream_t stream);
 unsigned large_last_pairs(const LargeBuffers* b);
 unsigned long long large_last_tests(const LargeBuffers* b);

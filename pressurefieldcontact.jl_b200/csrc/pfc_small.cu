@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
         __syncwarp();
         int cur = 0, n_open = n_valid;
         int flags = 0;
+        bool tile_overflow = false;   // warp-uniform
         unsigned dead = 0;   // problems whose frontier is empty (nobody writes their segment end any more); identical in every lane
 #pragma unroll
         for (int q = 0; q < P; ++q) dead |= (q >= n_valid ? 1u : 0u) << q;
@@ -214,7 +215,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
                     if (cnt > 1) fn[at + 1] = ch1;
                     if (cnt > 2) { fn[at + 2] = ch2; fn[at + 3] = ch3; }
                     for (int k = 0; k < ocnt; ++k) oln[oat + k] = (unsigned short)(at + k);
-                } else if (cnt > 0) flags |= kFlagOverflow;   // cannot happen: a frontier never holds more than n_leaf1 * n_leaf2 entries
+                }
+                // only instructions whose slot is smaller than n_leaf1 * n_leaf2 (mid-size trees) can overflow it: the tile is given up --
+                // the host moves the instruction to the large path and repeats the evaluation
+                tile_overflow |= __any_sync(0xffffffffu, cnt > 0 && at + cnt > fcap);
                 if (c < total) {   // the last slot of problem q closes its segment (pc[] by a run-time index would go to local memory)
                     int end_q = pc[P];
 #pragma unroll
@@ -226,6 +230,18 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
             n_open = carry >> 16;
             __syncwarp();
             cur ^= 1;
+            if (tile_overflow) break;
+        }
+        if (tile_overflow) {
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+                if (lane == q && s_ei[q] >= 0) {
+                    io.n_pairs[s_ei[q]] = 0;
+                    io.flags[s_ei[q]] = kFlagOverflow;
+                    if (sc.ins_overflow) sc.ins_overflow[s_ins[q]] = 1;
+                }
+            __syncwarp();
+            continue;
         }
         // ---- results: pair lists (DFS order), counts, flags (pc[] holds the final segments)
         {
@@ -253,6 +269,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
                 if (lane == q && s_ei[q] >= 0) {
                     const int n = pc[q + 1] - pc[q];
                     io.n_pairs[s_ei[q]] = n < cap ? n : cap;
+                    if (n > cap && sc.ins_overflow) { sc.ins_overflow[s_ins[q]] = 1; flags |= kFlagOverflow; }
                     io.flags[s_ei[q]] = flags;
                 }
         }
@@ -574,7 +591,8 @@ cudaError_t launch_broad(const SceneDev& sc, const EvalIO& io, int cap, unsigned
     const long long n_prob = io.n_env * sc.n_small;
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    const int p = broad_p_env ? broad_p_env : (n_prob <= 16LL * n_sm ? 1 : (n_prob <= 32LL * n_sm ? 2 : 4));
+    int p = broad_p_env ? broad_p_env : (n_prob <= 16LL * n_sm ? 1 : (n_prob <= 32LL * n_sm ? 2 : 4));
+    if (cap > 256) p = 1;   // slots of kMidCap entries (mid-size trees): the frontiers of one problem per warp are what fits in shared memory
     if (p == 1) return launch_broad_tile<1, 8, 2>(sc, io, cap, pairs, stream);
     if (p == 2) return launch_broad_tile<2, 8, 2>(sc, io, cap, pairs, stream);
     return launch_broad_tile<4, 8, 2>(sc, io, cap, pairs, stream);

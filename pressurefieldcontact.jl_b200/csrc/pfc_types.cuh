@@ -72,6 +72,7 @@ struct SceneDev {
     const int32_t* small_heavy_first;  // the same instructions ordered by n_leaf1 * n_leaf2, largest first (broad-phase scheduling order)
     int32_t n_ins, n_small, n_bristle;
     int32_t n_small_bristle;   // bristle instructions among the small ones (selects the narrow-phase kernel)
+    int32_t* ins_overflow;     // per instruction: set when a small-path pair-list / frontier slot was too small (nullptr when none can be)
     int32_t small_node_lo, small_node_n;  // range of the node array that holds the trees of the small instructions (staged in shared memory when it fits)
 };
 

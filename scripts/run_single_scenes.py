@@ -31,7 +31,7 @@ def main():
     builders = {
         "C1 boxes (settled stack)": lambda b: (scene_boxes(b)[0], None),
         "C2 pencil (bristle)": lambda b: scenes.scene_c2_pencil(True, b),
-        "C2 spoon stand-in (bristle)": lambda b: scenes.scene_c2_spoon(b),
+        "C2 spoon (test/data/spoon.obj, bristle)": lambda b: scenes.scene_c2_spoon(b),
     }
     for name, build in builders.items():
         m_g, bodies = build(capi.Context(0))

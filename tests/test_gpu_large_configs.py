@@ -120,10 +120,11 @@ def test_sharded_split_matches_the_unsharded_evaluation(scene, world):
     assert all(x == bits[0] for x in bits)         # every rank ends with the same bits
 
 
-def test_sort_key_capacity_is_an_error_not_a_wrong_answer():
+def test_sort_key_capacity_is_an_error_not_a_wrong_answer(monkeypatch):
     """Advisor finding: the sort key packs (problem, DFS key) in 64 bits.  Two caterpillar trees of depth 31 need 62 key bits; with 8
     environments (3 problem bits) the key does not fit: the call must fail with PFC_E_CAPACITY instead of aliasing problems."""
     from pfc_b200 import geometry as G
+    monkeypatch.setenv("PFC_MID_LEAVES", "0")      # 32-leaf trees would take the on-chip path: this test is about the large path's sort key
 
     def caterpillar_tet_mesh(n):
         # n thin tetrahedra in a row; the tree is a chain: node = (leaf k, rest)

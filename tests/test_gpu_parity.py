@@ -241,7 +241,14 @@ def test_determinism_bitwise():
     assert (a["wrench"].view(np.int64) == b["wrench"].view(np.int64)).all()
 
 
-# ---- large path (stack-based traversal + DFS-key sort + per-pair narrow phase) ------------------------
+# ---- large path (traversal + DFS-key sort + per-pair narrow phase) ------------------------
+@pytest.fixture
+def force_large_path(monkeypatch):
+    """Trees of a few hundred leaves normally take the on-chip path with a bounded pair-list slot (build_tables in csrc/pfc_api.cu);
+    these tests are about the multi-kernel large path, so that class is switched off while their scenes are built."""
+    monkeypatch.setenv("PFC_MID_LEAVES", "0")
+
+
 def _sphere_scene(n_div_a=4, n_div_b=3, with_small=True):
     def build(backend, n_env):
         m = S.MechanismScenario()
@@ -280,7 +287,7 @@ def _sphere_states(m, n_env, seed, with_small=True):
     return x
 
 
-def test_large_path_spheres():
+def test_large_path_spheres(force_large_path):
     """Instructions too big for the on-chip path (320 x 180 and 320 x 320 leaf pairs): the pair lists
     must come back in exactly the reference's traversal order after the DFS-key sort."""
     n_env = 6
@@ -298,7 +305,7 @@ def test_large_path_spheres():
     assert np.allclose(tg, tc, rtol=1e-9, atol=1e-12 * np.abs(tc).max())
 
 
-def test_large_path_many_envs_deterministic():
+def test_large_path_many_envs_deterministic(force_large_path):
     """Large path over a batch of environments; two runs are bitwise identical although the traversal
     appends pairs with atomics (the sort and the fixed-order reductions remove the nondeterminism)."""
     n_env = 48
@@ -313,7 +320,7 @@ def test_large_path_many_envs_deterministic():
     assert b == int(c["n_pairs"].sum()) and a > b
 
 
-def test_large_path_no_contact_and_empty():
+def test_large_path_no_contact_and_empty(force_large_path):
     """Far-apart bodies: the root boxes are disjoint, pair lists are empty, wrenches zero, bristle s-dot = -s / tau."""
     n_env = 3
     m_gpu, m_cpu = _both(_sphere_scene(2, 2, with_small=False), n_env)
@@ -325,7 +332,7 @@ def test_large_path_no_contact_and_empty():
     assert (g["n_pairs"] == 0).all() and (g["wrench"] == 0).all()
 
 
-def test_sharded_large_scene_two_ranks_on_one_gpu():
+def test_sharded_large_scene_two_ranks_on_one_gpu(force_large_path):
     """The multi-GPU split of one large scene, emulated with two contexts (rank 0 and 1 of world 2) on
     one GPU: each traverses and evaluates the sub-trees whose hash falls on it (disjoint pair lists), the
     partial buffers are summed (what the NCCL allreduce does), and both end with the same wrench / s-dot /
@@ -547,3 +554,27 @@ def test_state_entry_point_bristle_and_rejects_chains():
     assert not m_chain.device_kinematics
     with pytest.raises(RuntimeError):
         S.force_all_elastic_intersections_batch(m_chain, S.get_state(m_chain))
+
+
+# ---- mid-size trees on the on-chip path, and what happens when their pair-list slot is too small -------------------------
+def test_mid_size_instructions_take_the_small_path_and_overflow_moves_them_to_the_large_path():
+    """Spheres of 320 / 180 primitives: 57 600 possible leaf pairs, far more than the 1024-entry slot of the on-chip path, but a
+    contact patch lists a few hundred.  (1) Shallow contacts: evaluated by the two small-path kernels (the large path's counters stay
+    zero), results equal to the oracle's.  (2) A deep overlap (sphere inside sphere) overflows the slot: the library moves the
+    instruction to the large path and repeats the evaluation by itself -- same parity bars, and from then on the large path runs."""
+    n_env = 4
+    m_gpu, m_cpu = _both(_sphere_scene(3, 2, with_small=False), n_env)      # 180 / 80 primitives: 14 400 possible leaf pairs
+    x = _sphere_states(m_gpu, n_env, 31, with_small=False)
+    X, tw, s = S.boundary_arrays(m_gpu, x)
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
+    assert 0 < c["n_pairs"].max() < 512 and (c["flags"] & 1).sum() >= n_env
+    assert m_gpu.backend.counters() == (0, 0)          # nothing went through the large path
+    m_gpu, m_cpu = _both(_sphere_scene(4, 3, with_small=False), n_env)      # 320 / 180 primitives
+    x = _sphere_states(m_gpu, n_env, 31, with_small=False)
+    x[:, 3:6] = [0.0, 0.0, 0.012]                       # both spheres almost concentric with the ground sphere: thousands of candidate pairs
+    x[:, 9:12] = [0.0, 0.004, -0.01]
+    X, tw, s = S.boundary_arrays(m_gpu, x)
+    g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
+    assert c["n_pairs"].max() > 1024
+    n_tests, n_large_pairs = m_gpu.backend.counters()
+    assert n_large_pairs > 1024 and n_tests > n_large_pairs   # the overflowing instructions now run on the large path
