@@ -162,6 +162,7 @@ template <class T, int PTS> struct BristleSmem {
     T D2[6];
     T s[6];
     T twist[6];
+    PatchScratch<T> scr;
 };
 
 template <class T, int PTS, int WPB>
@@ -219,13 +220,12 @@ __global__ void __launch_bounds__(32 * WPB) exact_bristle_kernel(SceneDev sc, Ex
                         __syncwarp();
                     }
                 }
-                if (lane == 0) {
+                if (pass == 1) bristle_after_stiffness(sm.acc, bf, sm.s, sm.Sinv, sm.Kh, sm.D2, sm.scr, Coop{lane});   // every lane: the eigen-decomposition is dealt to the warp
+                else if (lane == 0) {
                     if (pass == 0) {
                         for (int j = 0; j < 10; ++j) sm.s10[j] = sm.acc[j];
                         const X3<T> cop = xdivide(x3<T>(sm.acc[7], sm.acc[8], sm.acc[9]), sm.acc[6]);
                         sm.cop[0] = cop[0]; sm.cop[1] = cop[1]; sm.cop[2] = cop[2];
-                    } else if (pass == 1) {
-                        bristle_after_stiffness(sm.acc, bf, sm.s, sm.Sinv, sm.Kh, sm.D2);
                     } else {
                         T w[6], sd[6];
                         bristle_finish(sm.s10, sm.acc, x3<T>(sm.cop[0], sm.cop[1], sm.cop[2]), bf, sm.s, sm.Sinv, sm.Kh, w, sd);

@@ -392,70 +392,102 @@ template <class T> PFC_XHD void terms_friction(const BristleP& bf, const X3<T>& 
     t[0] = Tc[0]; t[1] = Tc[1]; t[2] = Tc[2]; t[3] = m[0]; t[4] = m[1]; t[5] = m[2];
 }
 
-// ---- 6 x 6 symmetric eigen-decomposition: cyclic Jacobi, run to convergence --------------------------------------------------------
+// ---- warp-cooperative execution of the patch-level steps ---------------------------------------------------------------------------
+// The 6 x 6 eigen-decomposition is a few thousand dependent FP64 operations: on one lane it was most of a bristle evaluation.  The loops
+// over independent matrix elements are dealt to the lanes of the warp that owns the patch (`for (k = co.lane; k < 6; k += co.n)`),
+// which changes who computes an element, never how: the host check compiles the same source with one "lane" doing every index.
+#ifdef PFC_HOST_CHECK
+struct Coop { static constexpr int lane = 0; static constexpr int n = 1; void sync() const {} };
+#else
+struct Coop { int lane; static constexpr int n = 32; __device__ void sync() const { __syncwarp(); } };
+#endif
+template <class T> struct PatchScratch {   // shared by the lanes (shared memory on the device)
+    double A[6][6], V[6][6], lam[6], g[6], f[6], fp[6], floor_;
+    int clamped[6], m;
+    T Kbar[6][6];
+};
+
+// 6 x 6 symmetric eigen-decomposition: cyclic Jacobi, run to convergence
 // (the reference calls LAPACK / GenericLinearAlgebra, neither under /root/reference; only V f(L) V' is consumed, friction.jl:85-96)
-static __device__ __noinline__ void jacobi6_exact(double (*A)[6], double (*V)[6], double* lam) {
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) V[i][j] = (i == j ? 1.0 : 0.0);
+template <class C> PFC_XD_ void jacobi6_exact(double (*A)[6], double (*V)[6], double* lam, const C& co) {
+    for (int e = co.lane; e < 36; e += C::n) V[e / 6][e % 6] = (e / 6 == e % 6 ? 1.0 : 0.0);
+    co.sync();
     for (int sweep = 0; sweep < 64; ++sweep) {
-        double off = 0.0, diag = 0.0;
+        double off = 0.0, diag = 0.0;   // (every lane: same operands, same order, same bits)
         for (int i = 0; i < 6; ++i) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < 6; ++j) off += A[i][j] * A[i][j]; }
         if (off == 0.0 || off <= 1.0e-44 * diag) break;
         for (int p = 0; p < 5; ++p)
             for (int q = p + 1; q < 6; ++q) {
-                if (A[p][q] == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
                 const double t = (theta >= 0.0) ? 1.0 / (theta + sqrt(1.0 + theta * theta)) : -1.0 / (-theta + sqrt(1.0 + theta * theta));
                 const double c = 1.0 / sqrt(1.0 + t * t);
                 const double s = t * c;
-                for (int k = 0; k < 6; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
-                for (int k = 0; k < 6; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
-                for (int k = 0; k < 6; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+                co.sync();   // every lane has read A[p][q], A[p][p], A[q][q]
+                for (int k = co.lane; k < 6; k += C::n) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+                co.sync();
+                for (int k = co.lane; k < 6; k += C::n) {
+                    const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
+                    const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+                }
+                co.sync();
             }
     }
-    for (int i = 0; i < 6; ++i) lam[i] = A[i][i];
+    for (int i = co.lane; i < 6; i += C::n) lam[i] = A[i][i];
+    co.sync();
 }
 
-// calc_K̄_sqrt_inv (friction.jl:85-96).  Kbar: upper triangle read (Hermitian wrapper).  Float64.
-static __device__ __noinline__ void kbar_sqrt_inv(const double (*Kbar)[6], double (*out)[6]) {
-    double A[6][6], V[6][6], lam[6];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) A[i][j] = (i <= j) ? Kbar[i][j] : Kbar[j][i];
-    jacobi6_exact(A, V, lam);
-    double max_sig = lam[0];
-    for (int k = 1; k < 6; ++k) max_sig = fmax(max_sig, lam[k]);
-    double sig[6];
-    for (int k = 0; k < 6; ++k) sig[k] = 1.0 / sqrt(xmax(lam[k], max_sig * 1.0e-16));
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-            double acc = 0.0;
-            for (int k = 0; k < 6; ++k) acc += (V[i][k] * sig[k]) * V[j][k];
-            out[i][j] = acc;
-        }
+// calc_K̄_sqrt_inv (friction.jl:85-96).  scr.Kbar: upper triangle read (Hermitian wrapper).  Float64.
+template <class C> PFC_XD_ void kbar_sqrt_inv(PatchScratch<double>& scr, double (*out)[6], const C& co) {
+    for (int e = co.lane; e < 36; e += C::n) { const int i = e / 6, j = e % 6; scr.A[i][j] = (i <= j) ? scr.Kbar[i][j] : scr.Kbar[j][i]; }
+    co.sync();
+    jacobi6_exact(scr.A, scr.V, scr.lam, co);
+    if (co.lane == 0) {
+        double max_sig = scr.lam[0];
+        for (int k = 1; k < 6; ++k) max_sig = fmax(max_sig, scr.lam[k]);
+        for (int k = 0; k < 6; ++k) scr.f[k] = 1.0 / sqrt(xmax(scr.lam[k], max_sig * 1.0e-16));
+    }
+    co.sync();
+    for (int e = co.lane; e < 36; e += C::n) {
+        const int i = e / 6, j = e % 6;
+        double acc = 0.0;
+        for (int k = 0; k < 6; ++k) acc += (scr.V[i][k] * scr.f[k]) * scr.V[j][k];
+        out[i][j] = acc;
+    }
+    co.sync();
 }
 // Dual mode: the partials of V f(L) V' are the first-order perturbation of that matrix function (Daleckii-Krein), which is what
-// differentiating through a converged generic eigen-solver yields wherever the result is differentiable.
-template <int N> static __device__ __noinline__ void kbar_sqrt_inv(const XD<N> (*Kbar)[6], XD<N> (*out)[6]) {
-    double A[6][6], V[6][6], lam[6];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) A[i][j] = (i <= j) ? Kbar[i][j].v : Kbar[j][i].v;
-    jacobi6_exact(A, V, lam);
-    int m = 0;
-    for (int k = 1; k < 6; ++k) if (lam[k] > lam[m]) m = k;
-    const double floor_ = lam[m] * 1.0e-16;
-    bool clamped[6]; double g[6], f[6], fp[6];
-    for (int k = 0; k < 6; ++k) {
-        clamped[k] = !(floor_ < lam[k]);
-        g[k] = clamped[k] ? floor_ : lam[k];
-        f[k] = 1.0 / sqrt(g[k]);
-        fp[k] = -0.5 * f[k] / g[k];
-    }
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-            double acc = 0.0;
-            for (int k = 0; k < 6; ++k) acc += (V[i][k] * f[k]) * V[j][k];
-            out[i][j] = XD<N>(acc);
+// differentiating through a converged generic eigen-solver yields wherever the result is differentiable.  One lane per partial.
+template <int N, class C> PFC_XD_ void kbar_sqrt_inv(PatchScratch<XD<N>>& scr, XD<N> (*out)[6], const C& co) {
+    for (int e = co.lane; e < 36; e += C::n) { const int i = e / 6, j = e % 6; scr.A[i][j] = (i <= j) ? scr.Kbar[i][j].v : scr.Kbar[j][i].v; }
+    co.sync();
+    jacobi6_exact(scr.A, scr.V, scr.lam, co);
+    if (co.lane == 0) {
+        int m = 0;
+        for (int k = 1; k < 6; ++k) if (scr.lam[k] > scr.lam[m]) m = k;
+        scr.m = m;
+        scr.floor_ = scr.lam[m] * 1.0e-16;
+        for (int k = 0; k < 6; ++k) {
+            scr.clamped[k] = !(scr.floor_ < scr.lam[k]);
+            scr.g[k] = scr.clamped[k] ? scr.floor_ : scr.lam[k];
+            scr.f[k] = 1.0 / sqrt(scr.g[k]);
+            scr.fp[k] = -0.5 * scr.f[k] / scr.g[k];
         }
-    for (int d = 0; d < N; ++d) {
+    }
+    co.sync();
+    for (int e = co.lane; e < 36; e += C::n) {
+        const int i = e / 6, j = e % 6;
+        double acc = 0.0;
+        for (int k = 0; k < 6; ++k) acc += (scr.V[i][k] * scr.f[k]) * scr.V[j][k];
+        out[i][j] = XD<N>(acc);
+    }
+    co.sync();
+    const double (*V)[6] = scr.V;
+    const double* lam = scr.lam; const double* f = scr.f; const double* fp = scr.fp; const int* clamped = scr.clamped; const int m = scr.m;
+    for (int d = co.lane; d < N; d += C::n) {
         double dA[6][6], tmp[6][6], B[6][6], G[6][6];
-        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) dA[i][j] = (i <= j) ? Kbar[i][j].p[d] : Kbar[j][i].p[d];
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) dA[i][j] = (i <= j) ? scr.Kbar[i][j].p[d] : scr.Kbar[j][i].p[d];
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += dA[i][k] * V[k][j]; tmp[i][j] = a; }
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += V[k][i] * tmp[k][j]; B[i][j] = a; }
         for (int i = 0; i < 6; ++i)
@@ -470,35 +502,40 @@ template <int N> static __device__ __noinline__ void kbar_sqrt_inv(const XD<N> (
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += V[i][k] * G[k][j]; tmp[i][j] = a; }
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += tmp[i][k] * V[j][k]; out[i][j].p[d] = a; }
     }
+    co.sync();
 }
 
-// The patch-level part of yes_contact!(::Bristle) (friction.jl:119-143) between the passes.
+// The patch-level part of yes_contact!(::Bristle) (friction.jl:119-143) between the passes; called by every lane of the patch's warp.
 //   after pass 2:  K (from the 27 sums) -> decompose_K! -> Sinv, Kh = K̄^(-1/2), Delta2 = Sinv .* (Kh * s)
-template <class T> __device__ __noinline__ void bristle_after_stiffness(const T* sum27, const BristleP& bf, const T* s, T* Sinv, T (*Kh)[6], T* Delta2) {
-    T K[6][6];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            K[i][j] = sum27[18 + 3 * i + j] * bf.k_bar;          // K11
-            K[3 + i][j] = sum27[9 + 3 * j + i] * bf.k_bar;       // K12'
-            K[i][3 + j] = sum27[9 + 3 * i + j] * bf.k_bar;       // K12
-            K[3 + i][3 + j] = sum27[3 * i + j] * bf.k_bar;       // K22
-        }
-    T Kf[6][6];   // Hermitian wrapper: the upper triangle is what is read
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Kf[i][j] = (i <= j) ? K[i][j] : K[j][i];
-    const T t_1 = Kf[0][0] + Kf[1][1] + Kf[2][2];
-    const T t_2 = Kf[3][3] + Kf[4][4] + Kf[5][5];
-    const T s_1 = 1.0 / xsqrt(t_1);
-    for (int k = 0; k < 3; ++k) Sinv[k] = s_1 * bf.magic;
-    const T s_2 = 1.0 / xsqrt(t_2);
-    for (int k = 3; k < 6; ++k) Sinv[k] = s_2;
-    T Kbar[6][6];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Kbar[i][j] = Sinv[i] * Kf[i][j] * Sinv[j];
-    kbar_sqrt_inv(Kbar, Kh);
-    for (int i = 0; i < 6; ++i) {
+template <class T, class C> PFC_XD_ void bristle_after_stiffness(const T* sum27, const BristleP& bf, const T* s, T* Sinv, T (*Kh)[6], T* Delta2, PatchScratch<T>& scr,
+                                                                const C& co) {
+    if (co.lane == 0) {
+        T K[6][6];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                K[i][j] = sum27[18 + 3 * i + j] * bf.k_bar;          // K11
+                K[3 + i][j] = sum27[9 + 3 * j + i] * bf.k_bar;       // K12'
+                K[i][3 + j] = sum27[9 + 3 * i + j] * bf.k_bar;       // K12
+                K[3 + i][3 + j] = sum27[3 * i + j] * bf.k_bar;       // K22
+            }
+        T Kf[6][6];   // Hermitian wrapper: the upper triangle is what is read
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Kf[i][j] = (i <= j) ? K[i][j] : K[j][i];
+        const T t_1 = Kf[0][0] + Kf[1][1] + Kf[2][2];
+        const T t_2 = Kf[3][3] + Kf[4][4] + Kf[5][5];
+        const T s_1 = 1.0 / xsqrt(t_1);
+        for (int k = 0; k < 3; ++k) Sinv[k] = s_1 * bf.magic;
+        const T s_2 = 1.0 / xsqrt(t_2);
+        for (int k = 3; k < 6; ++k) Sinv[k] = s_2;
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) scr.Kbar[i][j] = Sinv[i] * Kf[i][j] * Sinv[j];
+    }
+    co.sync();
+    kbar_sqrt_inv(scr, Kh, co);
+    for (int i = co.lane; i < 6; i += C::n) {
         T acc = T(0.0);
         for (int j = 0; j < 6; ++j) acc = acc + Kh[i][j] * s[j];
         Delta2[i] = Sinv[i] * acc;
     }
+    co.sync();
 }
 //   after pass 3: friction wrench about the cop (lin, ang sums) -> wrench about the r2 origin, s-dot
 template <class T> __device__ __noinline__ void bristle_finish(const T* sum10, const T* sum6, const X3<T>& cop, const BristleP& bf, const T* s, const T* Sinv,

@@ -33,7 +33,11 @@ def main():
         "C2 pencil (bristle)": lambda b: scenes.scene_c2_pencil(True, b),
         "C2 spoon (test/data/spoon.obj, bristle)": lambda b: scenes.scene_c2_spoon(b),
     }
+    only = sys.argv[1] if len(sys.argv) > 1 else ""      # e.g. "pencil": that scene only (for profiling)
+    reps_gpu = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     for name, build in builders.items():
+        if only and only not in name:
+            continue
         m_g, bodies = build(capi.Context(0))
         m_c, _ = build(orc.OracleContext())
         if name.startswith("C1"):
@@ -44,7 +48,7 @@ def main():
             x = scenes.spoon_sample_states(m_g, bodies, n=2)[1]
         X, tw, s = S.boundary_arrays(m_g, x)
         s = s.reshape(1, m_g.n_bristle, 6) if m_g.n_bristle else None
-        g_rate, g = rate(m_g.backend, X, tw, s, 300)
+        g_rate, g = rate(m_g.backend, X, tw, s, reps_gpu)
         c_rate, c = rate(m_c.backend, X, tw, s, 20)
         assert np.array_equal(g["n_pairs"], c["n_pairs"])
         res[name] = {"gpu_evals_per_sec": g_rate, "gpu_us_per_eval": 1e6 / g_rate, "oracle_1_thread_evals_per_sec": c_rate,

@@ -174,7 +174,8 @@ int main(int argc, char** argv) {
             for (auto& r : got) { ex::terms_stiffness(r.n, ex::x3(r.pt.r[0], r.pt.r[1], r.pt.r[2]), r.pt.dA, r.pt.p, cop, tt);
                 for (int k = 0; k < 18; ++k) s27[k] = s27[k] + tt[k]; for (int k = 18; k < 27; ++k) s27[k] = s27[k] - tt[k]; }
             double Sinv[6], Kh[6][6], D2[6], w[6], sdot[6];
-            ex::bristle_after_stiffness(s27, bp, sx, Sinv, Kh, D2);
+            ex::PatchScratch<double> scr;
+            ex::bristle_after_stiffness(s27, bp, sx, Sinv, Kh, D2, scr, ex::Coop());
             for (auto& r : got) { ex::terms_friction(bp, r.n, ex::x3(r.pt.r[0], r.pt.r[1], r.pt.r[2]), r.pt.dA, r.pt.p, cop, D2, cx.twist, tt); for (int k = 0; k < 6; ++k) s6[k] = s6[k] + tt[k]; }
             ex::bristle_finish(s10, s6, cop, bp, sx, Sinv, Kh, w, sdot);
             bool okp = true;
@@ -192,7 +193,8 @@ int main(int argc, char** argv) {
             for (auto& r : gotd) { ex::terms_stiffness(r.n, ex::x3(r.pt.r[0], r.pt.r[1], r.pt.r[2]), r.pt.dA, r.pt.p, cop, tt);
                 for (int k = 0; k < 18; ++k) s27[k] = s27[k] + tt[k]; for (int k = 18; k < 27; ++k) s27[k] = s27[k] - tt[k]; }
             XD6 Sinv[6], Kh[6][6], D2[6], w[6], sdot[6];
-            ex::bristle_after_stiffness(s27, bp, sx, Sinv, Kh, D2);
+            ex::PatchScratch<XD6> scr;
+            ex::bristle_after_stiffness(s27, bp, sx, Sinv, Kh, D2, scr, ex::Coop());
             for (auto& r : gotd) { ex::terms_friction(bp, r.n, ex::x3(r.pt.r[0], r.pt.r[1], r.pt.r[2]), r.pt.dA, r.pt.p, cop, D2, cd.twist, tt); for (int k = 0; k < 6; ++k) s6[k] = s6[k] + tt[k]; }
             ex::bristle_finish(s10, s6, cop, bp, sx, Sinv, Kh, w, sdot);
             bool okp = true;

@@ -562,9 +562,9 @@ def test_mid_size_instructions_take_the_small_path_and_overflow_moves_them_to_th
     contact patch lists a few hundred.  (1) Shallow contacts: evaluated by the two small-path kernels (the large path's counters stay
     zero), results equal to the oracle's.  (2) A deep overlap (sphere inside sphere) overflows the slot: the library moves the
     instruction to the large path and repeats the evaluation by itself -- same parity bars, and from then on the large path runs."""
-    n_env = 4
+    n_env = 3
     m_gpu, m_cpu = _both(_sphere_scene(3, 2, with_small=False), n_env)      # 180 / 80 primitives: 14 400 possible leaf pairs
-    x = _sphere_states(m_gpu, n_env, 31, with_small=False)
+    x = _sphere_states(m_gpu, n_env + 1, 31, with_small=False)[1:]          # (the first sample is a deep contact: 513 pairs, a frontier beyond the slot)
     X, tw, s = S.boundary_arrays(m_gpu, x)
     g, c = _compare(m_gpu, m_cpu, X, tw, s.reshape(n_env, 1, 6))
     assert 0 < c["n_pairs"].max() < 512 and (c["flags"] & 1).sum() >= n_env
