@@ -188,7 +188,10 @@ struct pfc_ctx {
     // Jacobian mode staging + the pair lists it may reuse
     DevBuf<double> d_X7, d_tw7, d_s7, d_w7, d_sd7;
     DevBuf<int32_t> d_large_index;
-    int64_t lists_n_env = -1;   // n_env of the evaluation whose pair lists (d_small_pairs / large_buf, d_np, d_fl) are current
+    int64_t lists_n_env = -1;   // n_env of the evaluation whose pair lists (d_small_pairs / large_buf, lists_np, lists_fl) are current
+    long long* lists_np = nullptr;   // where that evaluation left its pair counts / flags (d_np / d_fl, or the packed block of a small call)
+    int* lists_fl = nullptr;
+    DevBuf<unsigned char> d_pack_in, d_pack_out;   // small host-pointer calls: all inputs / all outputs in one block each (one copy each way)
     // device-side kinematics (pfc_set_bodies / pfc_eval_state_f64)
     bool has_bodies = false;
     std::vector<BodyDev> h_bodies;
@@ -790,30 +793,57 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
     if (c->n_bristle > 0 && (!s || !sdot)) return fail(PFC_E_ARG, "pfc_eval_f64: bristle instructions need s and sdot");
     CU(cudaSetDevice(c->device));
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
-    CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni));
-    CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
-    if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_sd.ensure(6 * ne * nb)); }
     arena_reset(c);
     // (Measured and rejected: letting the kernels of a single small scene read X / twist straight from the pinned arena and write the
     // wrenches into it -- zero-copy over PCIe instead of five cudaMemcpyAsync calls: no gain on test/boxes.jl (69 vs 67 us per call), and
     // scenes whose large instructions re-read X in every thread got slower, 316 -> 402 us on the spoon.)
-    CU(copy_in(c, c->d_X.p, X, sizeof(double) * 16 * ne * ni));
-    CU(copy_in(c, c->d_tw.p, twist, sizeof(double) * 6 * ne * ni));
-    if (nb) CU(copy_in(c, c->d_s.p, s, sizeof(double) * 6 * ne * nb));
+    const size_t bX = sizeof(double) * 16 * ne * ni, bT = sizeof(double) * 6 * ne * ni, bS = sizeof(double) * 6 * ne * nb;
+    const size_t bW = bT, bD = bS, bN = sizeof(long long) * ne * ni, bF = (sizeof(int32_t) * ne * ni + 7) & ~size_t(7);
     EvalIO io{};
-    io.n_env = n_env; io.X = c->d_X.p; io.twist = c->d_tw.p; io.s = nb ? c->d_s.p : nullptr; io.wrench = c->d_w.p;
-    io.sdot = nb ? c->d_sd.p : nullptr; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
-    int rc = eval_device(c, io);
-    if (rc != PFC_OK) return rc;
-    CU(copy_out(c, wrench, c->d_w.p, sizeof(double) * 6 * ne * ni));
-    if (nb) CU(copy_out(c, sdot, c->d_sd.p, sizeof(double) * 6 * ne * nb));
-    if (n_pairs) CU(copy_out(c, n_pairs, c->d_np.p, sizeof(long long) * ne * ni));
+    io.n_env = n_env;
     std::vector<int32_t> fl_local;
     int32_t* fl = flags;
     if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
-    CU(copy_out(c, fl, c->d_fl.p, sizeof(int32_t) * ne * ni));
-    CU(cudaStreamSynchronize(c->stream));
-    copy_out_finish(c);
+    unsigned char* h_in = (bX + bT + bS + bW + bD + bN + bF <= 32768) ? static_cast<unsigned char*>(arena_take(c, bX + bT + bS)) : nullptr;
+    unsigned char* h_out = h_in ? static_cast<unsigned char*>(arena_take(c, bW + bD + bN + bF)) : nullptr;
+    if (h_in && h_out) {
+        // One small scene per call (the reference's own use: Radau on a single scene): every input in one block and every output in one
+        // block, so the call costs one copy each way instead of three in and four out (each a few microseconds of copy-engine latency).
+        CU(c->d_pack_in.ensure(bX + bT + bS)); CU(c->d_pack_out.ensure(bW + bD + bN + bF));
+        std::memcpy(h_in, X, bX); std::memcpy(h_in + bX, twist, bT);
+        if (nb) std::memcpy(h_in + bX + bT, s, bS);
+        CU(cudaMemcpyAsync(c->d_pack_in.p, h_in, bX + bT + bS, cudaMemcpyHostToDevice, c->stream));
+        unsigned char* di = c->d_pack_in.p; unsigned char* dn = c->d_pack_out.p;
+        io.X = reinterpret_cast<const double*>(di); io.twist = reinterpret_cast<const double*>(di + bX); io.s = nb ? reinterpret_cast<const double*>(di + bX + bT) : nullptr;
+        io.wrench = reinterpret_cast<double*>(dn); io.sdot = nb ? reinterpret_cast<double*>(dn + bW) : nullptr;
+        io.n_pairs = reinterpret_cast<long long*>(dn + bW + bD); io.flags = reinterpret_cast<int*>(dn + bW + bD + bN);
+        int rc = eval_device(c, io);
+        if (rc != PFC_OK) return rc;
+        CU(cudaMemcpyAsync(h_out, dn, bW + bD + bN + bF, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        std::memcpy(wrench, h_out, bW);
+        if (nb) std::memcpy(sdot, h_out + bW, bD);
+        if (n_pairs) std::memcpy(n_pairs, h_out + bW + bD, bN);
+        std::memcpy(fl, h_out + bW + bD + bN, sizeof(int32_t) * ne * ni);
+    } else {
+        CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni)); CU(c->d_w.ensure(6 * ne * ni));
+        CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+        if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_sd.ensure(6 * ne * nb)); }
+        CU(copy_in(c, c->d_X.p, X, bX));
+        CU(copy_in(c, c->d_tw.p, twist, bT));
+        if (nb) CU(copy_in(c, c->d_s.p, s, bS));
+        io.X = c->d_X.p; io.twist = c->d_tw.p; io.s = nb ? c->d_s.p : nullptr; io.wrench = c->d_w.p;
+        io.sdot = nb ? c->d_sd.p : nullptr; io.n_pairs = c->d_np.p; io.flags = c->d_fl.p;
+        int rc = eval_device(c, io);
+        if (rc != PFC_OK) return rc;
+        CU(copy_out(c, wrench, c->d_w.p, bW));
+        if (nb) CU(copy_out(c, sdot, c->d_sd.p, bD));
+        if (n_pairs) CU(copy_out(c, n_pairs, c->d_np.p, bN));
+        CU(copy_out(c, fl, c->d_fl.p, sizeof(int32_t) * ne * ni));
+        CU(cudaStreamSynchronize(c->stream));
+        copy_out_finish(c);
+    }
+    c->lists_np = io.n_pairs; c->lists_fl = io.flags;
     c->lists_n_env = n_env;  // d_np / d_fl / pair lists of this evaluation can be reused by pfc_eval_dual6(X_bp = NULL)
     for (size_t k = 0; k < ne * ni; ++k) {
         if (fl[k] & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
@@ -1079,7 +1109,7 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     if (X_bp) {  // traverse with the Float64 transform (calcTriTetIntersections! always uses m.float)
         CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
         CU(copy_in(c, c->d_X.p, X_bp, sizeof(double) * 16 * ne * ni));
-    } else if (c->lists_n_env != n_env) {
+    } else if (c->lists_n_env != n_env || !c->lists_np || !c->lists_fl) {
         return fail(PFC_E_ARG, "pfc_eval_dual6: X_bp is NULL but no pair lists of a previous pfc_eval_f64 with the same n_env exist");
     }
     CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni));
@@ -1087,6 +1117,9 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     CU(copy_in(c, c->d_X7.p, X7, sizeof(double) * 112 * ne * ni));
     CU(copy_in(c, c->d_tw7.p, twist7, sizeof(double) * 42 * ne * ni));
     if (nb) CU(copy_in(c, c->d_s7.p, s7, sizeof(double) * 42 * ne * nb));
+    // pair counts / flags: this call's own traversal, or where the previous Float64 evaluation left them
+    long long* const np_d = X_bp ? c->d_np.p : c->lists_np;
+    int* const fl_d = X_bp ? c->d_fl.p : c->lists_fl;
     PFC_REQUEUE_LOOP({
         int nl = 0;
         if (X_bp) {
@@ -1102,23 +1135,23 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
                 nl += 1;
             }
         }
-        CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p,
+        CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, np_d, fl_d,
                              c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
                              c->large_scene.n_large, c->stream));
         {   // bristle instructions on Duals, in the reference's operation order
-            int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, c->d_np.p, c->d_fl.p, 1, false, &nl);
+            int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, np_d, fl_d, 1, false, &nl);
             if (rc != PFC_OK) return rc;
         }
         c->launches += nl + 1;
     })
-    if (X_bp) c->lists_n_env = n_env;
+    if (X_bp) { c->lists_n_env = n_env; c->lists_np = c->d_np.p; c->lists_fl = c->d_fl.p; }
     CU(copy_out(c, wrench7, c->d_w7.p, sizeof(double) * 42 * ne * ni));
     if (nb) CU(copy_out(c, sdot7, c->d_sd7.p, sizeof(double) * 42 * ne * nb));
-    if (n_pairs) CU(copy_out(c, n_pairs, c->d_np.p, sizeof(long long) * ne * ni));
+    if (n_pairs) CU(copy_out(c, n_pairs, np_d, sizeof(long long) * ne * ni));
     std::vector<int32_t> fl_local;
     int32_t* fl = flags;
     if (!fl) { fl_local.resize(ne * ni); fl = fl_local.data(); }
-    CU(copy_out(c, fl, c->d_fl.p, sizeof(int32_t) * ne * ni));
+    CU(copy_out(c, fl, fl_d, sizeof(int32_t) * ne * ni));
     CU(cudaStreamSynchronize(c->stream));
     copy_out_finish(c);
     for (size_t k = 0; k < ne * ni; ++k) {
@@ -1243,7 +1276,7 @@ static cudaError_t status_begin(pfc_ctx* c) {
 static int status_end(pfc_ctx* c, int64_t n_env) {
     CU(cudaMemcpyAsync(c->h_status, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->lists_n_env = n_env;
+    c->lists_n_env = n_env; c->lists_np = c->d_np.p; c->lists_fl = c->d_fl.p;
     if (*c->h_status & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
     if (*c->h_status & PFC_FLAG_OVERFLOW) return fail(PFC_E_CAPACITY, "candidate-pair capacity exceeded");
     return PFC_OK;
