@@ -470,23 +470,38 @@ def main():
     d2h = int(f_p.numel() * 8 + 4)   # generalized forces + the 4-byte error status word
     h2d_b = int(X_h.nbytes + tw_h.nbytes)
     d2h_b = int(w_p.numel() * 8 + np_p.numel() * 8 + fl_p.numel() * 4)
-    # secondary: the Jacobian mode the integrator needs once per step (SURVEY 8d "Jacobian-chunk evals/s"): one Dual-6 chunk of calcXd!
-    # for the whole batch through pfc_calcxd_dual6, host buffers in and out (x in, x_dot + 6 partials out)
+    # secondary: the Jacobian mode the integrator needs once per step (SURVEY 8d "Jacobian-chunk evals/s"): the WHOLE Jacobian of calcXd!
+    # for the batch through pfc_calcxd_jacobian_device (one broad phase, all ceil(n_x / 6) Dual-6 chunks side by side), device buffers,
+    # timed with CUDA events; beside it the same Jacobian as ceil(n_x / 6) calls of pfc_calcxd_dual6_device (what round 1 did)
     jac = None
     try:
         if getattr(m, "device_dynamics", False) and world == 1:
-            xd7 = np.zeros((n_env, m.x_all.shape[1], 7))
-            npj, flj = np.zeros((n_env, n_ins), np.int64), np.zeros((n_env, n_ins), np.int32)
-            lib = capi.lib()
-            call = lambda seed: capi._check(lib.pfc_calcxd_dual6(ctx._h, n_env, m.x_all.ctypes.data, None, seed, xd7.ctypes.data, npj.ctypes.data, flj.ctypes.data))
-            call(0)
-            t0 = time.perf_counter()
-            reps = 8
-            for k in range(reps):
-                call(6 * k)
-            dtj = (time.perf_counter() - t0) / reps
-            jac = {"value": n_env / dtj, "unit": "Dual-6 chunk evals/s", "ms_per_chunk_batch": dtj * 1e3, "api": "pfc_calcxd_dual6, pageable host buffers",
-                   "chunks_per_radau_step": int(np.ceil(m.x_all.shape[1] / 6))}
+            nx = m.x_all.shape[1]
+            n_chunk = int(np.ceil(nx / 6))
+            x_d = torch.from_numpy(m.x_all).to(dev)
+            jac_d = torch.empty((n_env, nx, nx), dtype=torch.float64, device=dev)
+            xd_d = torch.empty((n_env, nx), dtype=torch.float64, device=dev)
+            xd7_d = torch.zeros((n_env, nx, 7), dtype=torch.float64, device=dev)
+            npj = torch.zeros((n_env, n_ins), dtype=torch.int64, device=dev)
+            flj = torch.zeros((n_env, n_ins), dtype=torch.int32, device=dev)
+            torch.cuda.synchronize(dev)   # the fills above ran on torch's stream, the library has its own
+            whole = lambda: ctx.calcxd_jacobian_device(n_env, x_d.data_ptr(), None, jac_d.data_ptr(), xd_d.data_ptr(), npj.data_ptr(), flj.data_ptr())
+            def chunked():
+                for k in range(n_chunk):
+                    ctx.calcxd_dual6_device(n_env, x_d.data_ptr(), None, 6 * k, xd7_d.data_ptr(), npj.data_ptr(), flj.data_ptr())
+            times = {}
+            for name, fn in (("whole", whole), ("chunk_calls", chunked)):
+                fn(); ctx.sync()
+                reps = 5
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    fn()
+                ctx.sync()
+                times[name] = (time.perf_counter() - t0) / reps
+            jac = {"value": n_env * n_chunk / times["whole"], "unit": "Dual-6 chunk evals/s", "ms_per_jacobian_batch": times["whole"] * 1e3,
+                   "api": "pfc_calcxd_jacobian_device: x[env][n_x] -> jac[env][n_x][n_x] + x_dot, device buffers",
+                   "chunks_per_jacobian": n_chunk, "n_x": int(nx),
+                   "as_chunk_calls_ms": times["chunk_calls"] * 1e3}
     except Exception as exc:
         jac = {"error": repr(exc)}
     # secondary: the reference's adaptive Radau IIA integrator for the whole batch with every array on the GPU (radau_batched.py)
@@ -548,7 +563,7 @@ def main():
     if weak is not None:
         line["weak"] = weak
     if jac is not None:
-        line["jacobian_chunks"] = jac
+        line["jacobian"] = jac
     if rollout is not None:
         line["batched_radau"] = rollout
     if large is not None:

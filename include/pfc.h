@@ -126,6 +126,17 @@ int pfc_calcxd_dual6(pfc_ctx* ctx, int64_t n_env, const double* x, const double*
  * world-attached coordinates. */
 int pfc_calcxd_dual6_device(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, int seed_start, double* xdot7, int64_t* n_pairs,
                             int32_t* flags);
+/* The whole Jacobian of calcXd! in one call (calcJacobian!, src/radau/radau_functions.jl:2-26: ceil(n_x / 6) Dual-6 passes of calcXd!).
+ * jac[env][n_x][n_x], row-major: jac[env][i][j] = d xdot_i / d x_j (calcJacobian! stores its negative: J = -jac).  xdot[env][n_x] (may be
+ * NULL) receives calcXd!(x) itself, the value part of the first pass.  The Float64 kinematics and the broad phase run once (the reference
+ * repeats the traversal in every pass, on the same Float64 state: non_friction.jl:94-101) and the seed chunks run side by side as a grid
+ * axis of the Dual kernels, so the result equals ceil(n_x / 6) calls of pfc_calcxd_dual6 bit for bit.  Host pointers; tau_ext / xdot /
+ * n_pairs / flags may be NULL. */
+int pfc_calcxd_jacobian(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, double* jac, double* xdot, int64_t* n_pairs,
+                        int32_t* flags);
+/* Same on device buffers (tau_ext and xdot may be NULL), asynchronous on the context's stream.  Every entry of jac / xdot is written. */
+int pfc_calcxd_jacobian_device(pfc_ctx* ctx, int64_t n_env, const double* x, const double* tau_ext, double* jac, double* xdot, int64_t* n_pairs,
+                               int32_t* flags);
 /* Refit of one mesh after its vertices moved (same connectivity, same tree topology), on the device: rebuilds the mesh's primitive records
  * (triangle normals; inv([V; 1]) and the pressure gradient of every tetrahedron, src/contact_algorithms_non_friction.jl:145-164) and refits
  * every box of its tree with the construction rules of eMesh_to_tree (leaves: fit_tri_obb / fit_tet_obb, src/obb/obb_construction.jl; internal

@@ -210,6 +210,15 @@ function calcXd_chunk_batch_gpu!(xx7::Array{Float64,3}, m::MechanismScenario, x:
     return nothing
 end
 
+"The whole Jacobian of calcXd! for a batch in one call: `jac[j, i, env]` = d x_dot[i] / d x[j] (the C layout is row-major [env][i][j]);
+`xx[:, env]` = calcXd!(x[:, env]).  calcJacobian! (src/radau/radau_functions.jl:2-26) stores `-transpose(jac[:, :, env])`."
+function calcJacobian_batch_gpu!(jac::Array{Float64,3}, xx::Matrix{Float64}, m::MechanismScenario, x::Matrix{Float64})
+    GC.@preserve x xx jac check(ccall((:pfc_calcxd_jacobian, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+        CTX[m], size(x, 2), x, C_NULL, jac, xx, C_NULL, C_NULL))
+    return nothing
+end
+
 "Moved vertices of mesh `id` (same connectivity): the device rebuilds the mesh's primitive records and refits its tree (pfc_refit_mesh)."
 function refit_mesh_gpu!(m::MechanismScenario, id::MeshID, point::Vector{SVector{3,Float64}})
     xyz = collect(Iterators.flatten(point))

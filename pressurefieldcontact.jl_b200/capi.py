@@ -22,7 +22,7 @@ _vp = C.c_void_p
 SYMBOLS = [
     "pfc_create", "pfc_destroy", "pfc_add_mesh", "pfc_add_instruction", "pfc_finalize", "pfc_eval_f64", "pfc_eval_f64_device",
     "pfc_eval_dual6", "pfc_set_debug", "pfc_get_pairs", "pfc_get_traction", "pfc_set_shard", "pfc_eval_sharded_begin", "pfc_eval_sharded_partials", "pfc_eval_sharded_step", "pfc_sync", "pfc_stream",
-    "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_set_dynamics", "pfc_calcxd_f64", "pfc_calcxd_f64_device", "pfc_calcxd_dual6", "pfc_calcxd_dual6_device", "pfc_radau_inv_c_device", "pfc_refit_mesh", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
+    "pfc_set_bodies", "pfc_eval_state_f64", "pfc_eval_state_f64_device", "pfc_get_boundary", "pfc_set_dynamics", "pfc_calcxd_f64", "pfc_calcxd_f64_device", "pfc_calcxd_dual6", "pfc_calcxd_dual6_device", "pfc_calcxd_jacobian", "pfc_calcxd_jacobian_device", "pfc_radau_inv_c_device", "pfc_refit_mesh", "pfc_launch_count", "pfc_counters", "pfc_measure_fp64_peak", "pfc_set_timing", "pfc_kernel_times", "pfc_last_error", "pfc_version",
     "pfc_comm_unique_id", "pfc_comm_init_rank", "pfc_eval_sharded_f64_device", "pfc_group_create", "pfc_group_destroy", "pfc_group_size", "pfc_group_ctx",
     "pfc_group_add_mesh", "pfc_group_add_instruction", "pfc_group_finalize", "pfc_group_eval_f64",
 ]
@@ -66,6 +66,8 @@ def lib():
         L.pfc_calcxd_f64_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]
         L.pfc_calcxd_dual6.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, _vp]
         L.pfc_calcxd_dual6_device.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, _vp]
+        L.pfc_calcxd_jacobian.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.pfc_calcxd_jacobian_device.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]
         L.pfc_refit_mesh.argtypes = [_vp, C.c_int, C.c_int64, _d]
         L.pfc_radau_inv_c_device.argtypes = [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp, _vp]
         L.pfc_comm_unique_id.argtypes = [_vp]
@@ -240,6 +242,21 @@ class Context:
     def calcxd_dual6_device(self, n_env, x, tau_ext, seed_start, xdot7, n_pairs, flags):
         """Device pointers given as integers; asynchronous on self.stream."""
         _check(lib().pfc_calcxd_dual6_device(self._h, n_env, x, tau_ext, int(seed_start), xdot7, n_pairs, flags))
+
+    def calcxd_jacobian(self, x, tau_ext=None):
+        """The whole Jacobian of calcXd! in one call: x[env][n_x] (host) -> dict(jac[env][n_x][n_x] = d xdot_i / d x_j, xdot, n_pairs, flags)."""
+        nx = self.nq + self.nv + 6 * self.n_bristle
+        x = _a(x).reshape(-1, nx)
+        n_env = x.shape[0]
+        tau = None if tau_ext is None else _a(tau_ext).reshape(n_env, self.nv)
+        out = dict(jac=np.zeros((n_env, nx, nx)), xdot=np.zeros((n_env, nx)), n_pairs=np.zeros((n_env, self.n_ins), np.int64),
+                   flags=np.zeros((n_env, self.n_ins), np.int32))
+        _check(lib().pfc_calcxd_jacobian(self._h, n_env, _p(x), _p(tau), _p(out["jac"]), _p(out["xdot"]), _p(out["n_pairs"]), _p(out["flags"])))
+        return out
+
+    def calcxd_jacobian_device(self, n_env, x, tau_ext, jac, xdot, n_pairs, flags):
+        """Device pointers given as integers (tau_ext / xdot may be None); asynchronous on self.stream."""
+        _check(lib().pfc_calcxd_jacobian_device(self._h, n_env, x, tau_ext, jac, xdot, n_pairs, flags))
 
     def refit_mesh(self, mesh_id: int, xyz):
         """New vertex positions for mesh `mesh_id` (same connectivity): primitive records and every box of its tree are refitted on the device."""

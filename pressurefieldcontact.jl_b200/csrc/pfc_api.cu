@@ -186,7 +186,7 @@ struct pfc_ctx {
     int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
     EvalIO sharded_io{};
     // Jacobian mode staging + the pair lists it may reuse
-    DevBuf<double> d_X7, d_tw7, d_s7, d_w7, d_sd7;
+    DevBuf<double> d_X7, d_tw7, d_s7, d_w7, d_sd7, d_jac;
     DevBuf<int32_t> d_large_index;
     int64_t lists_n_env = -1;   // n_env of the evaluation whose pair lists (d_small_pairs / large_buf, lists_np, lists_fl) are current
     long long* lists_np = nullptr;   // where that evaluation left its pair counts / flags (d_np / d_fl, or the packed block of a small call)
@@ -1503,6 +1503,97 @@ int pfc_calcxd_dual6(pfc_ctx* c, int64_t n_env, const double* x, const double* t
     int rc = calcxd_dual6_device(c, n_env, c->d_x.p, tau_ext ? c->d_tau.p : nullptr, seed_start, c->d_xdot.p, c->d_np.p, c->d_fl.p, c->d_status.p);
     if (rc != PFC_OK) return rc;
     CU(cudaMemcpyAsync(xdot7, c->d_xdot.p, sizeof(double) * 7 * ne * nx, cudaMemcpyDeviceToHost, c->stream));
+    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    if (flags) CU(cudaMemcpyAsync(flags, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+    int rc2 = status_end(c, n_env);
+    c->lists_n_env = -1;
+    return rc2;
+}
+
+// The whole Jacobian of calcXd! (calcJacobian!, /root/reference/src/radau/radau_functions.jl:2-26: ceil(n_x / 6) passes of calcXd! on
+// Dual{6} states, the candidate-pair lists always from the Float64 state).  Here the Float64 kinematics and the broad phase run ONCE; the
+// seed chunks are a grid axis of the Dual kernels ("environment" (g, env) = chunk g of real environment env) as far as the work space
+// allows, and the rigid-body kernel writes the partials straight into jac[env][row][col].  Scenes with bristle instructions go chunk by
+// chunk (their reference-order pipeline is sized per real environment) but still share the broad phase.
+static int jacobian_device_once(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* jac, double* xdot, long long* n_pairs,
+                                int* flags, int* status) {
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle), nx = size_t(c->state.n_x);
+    const int n_chunk = int((nx + 5) / 6);
+    // chunks per pass: all of them if the Dual boundary arrays (196 doubles per (chunk, environment, instruction)) stay below 1 GiB
+    int G = 1;
+    if (nb == 0) G = int(std::max<size_t>(1, std::min<size_t>(size_t(n_chunk), (size_t(1) << 30) / std::max<size_t>(1, ne * ni * 196 * sizeof(double)))));
+    const size_t nv_env = ne * size_t(G);
+    CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni));
+    CU(c->d_X7.ensure(112 * nv_env * ni)); CU(c->d_tw7.ensure(42 * nv_env * ni)); CU(c->d_w7.ensure(42 * nv_env * ni));
+    if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
+    int nl = 0;
+    CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), x, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
+    {
+        EvalIO io{};
+        io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = n_pairs; io.flags = flags;
+        if (c->scene.n_small > 0) {
+            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni + kSmallPairsSlack));
+            CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
+        }
+        if (c->large_scene.n_large > 0) {
+            CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
+            CU(large_write_counts(c->scene, c->large_scene, io, c->large_buf, c->stream));
+            nl += 1;
+        }
+        c->lists_n_env = -1;
+    }
+    for (int g0 = 0; g0 < n_chunk; g0 += G) {
+        const int g = std::min(G, n_chunk - g0);
+        const long long n_virtual = n_env * g;
+        CU(launch_state_prologue_dual6(c->state, n_virtual, int(ni), int(nb), x, 6 * g0, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl, n_env));
+        CU(launch_eval_dual6(c->scene, n_virtual, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags,
+                             c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
+                             c->large_scene.n_large, c->stream, n_env));
+        nl += 1;
+        if (nb) {
+            int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, c->d_s7.p, c->d_w7.p, c->d_sd7.p, n_pairs, flags, 1, false, &nl);
+            if (rc != PFC_OK) return rc;
+        }
+        CU(launch_state_dynamics_dual6(c->state, c->dyn, n_virtual, int(ni), int(nb), x, 6 * g0, c->d_w7.p, tau_ext, nb ? c->d_sd7.p : nullptr,
+                                       g0 == 0 ? xdot : nullptr, c->stream, &nl, flags, status, n_env, jac));
+    }
+    c->launches += nl;
+    return PFC_OK;
+}
+static int jacobian_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* jac, double* xdot, long long* n_pairs, int* flags,
+                           int* status) {
+    PFC_REQUEUE_LOOP({ const int rc_ = jacobian_device_once(c, n_env, x, tau_ext, jac, xdot, n_pairs, flags, status); if (rc_ != PFC_OK) return rc_; })
+    return PFC_OK;
+}
+
+int pfc_calcxd_jacobian_device(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* jac, double* xdot, int64_t* n_pairs,
+                               int32_t* flags) {
+    if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_jacobian_device: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_calcxd_jacobian_device: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !jac || !n_pairs || !flags) return fail(PFC_E_ARG, "pfc_calcxd_jacobian_device: NULL buffer");
+    CU(cudaSetDevice(c->device));
+    return jacobian_device(c, n_env, x, tau_ext, jac, xdot, reinterpret_cast<long long*>(n_pairs), flags, nullptr);
+}
+
+int pfc_calcxd_jacobian(pfc_ctx* c, int64_t n_env, const double* x, const double* tau_ext, double* jac, double* xdot, int64_t* n_pairs, int32_t* flags) {
+    if (!c || !c->finalized || !c->has_dynamics) return fail(PFC_E_ARG, "pfc_calcxd_jacobian: pfc_finalize, pfc_set_bodies and pfc_set_dynamics first");
+    if (n_env < 0) return fail(PFC_E_ARG, "pfc_calcxd_jacobian: negative n_env");
+    if (n_env == 0) return PFC_OK;   // an empty batch is a no-op whatever the pointers are
+    if (!x || !jac) return fail(PFC_E_ARG, "pfc_calcxd_jacobian: NULL buffer");
+    CU(cudaSetDevice(c->device));
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
+    CU(c->d_x.ensure(ne * nx)); CU(c->d_jac.ensure(ne * nx * nx)); CU(c->d_xdot.ensure(ne * nx)); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
+    CU(cudaMemcpyAsync(c->d_x.p, x, sizeof(double) * ne * nx, cudaMemcpyHostToDevice, c->stream));
+    if (tau_ext) {
+        CU(c->d_tau.ensure(std::max<size_t>(ne * nv, 1)));
+        CU(cudaMemcpyAsync(c->d_tau.p, tau_ext, sizeof(double) * ne * nv, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(status_begin(c));
+    int rc = jacobian_device(c, n_env, c->d_x.p, tau_ext ? c->d_tau.p : nullptr, c->d_jac.p, c->d_xdot.p, c->d_np.p, c->d_fl.p, c->d_status.p);
+    if (rc != PFC_OK) return rc;
+    CU(cudaMemcpyAsync(jac, c->d_jac.p, sizeof(double) * ne * nx * nx, cudaMemcpyDeviceToHost, c->stream));
+    if (xdot) CU(cudaMemcpyAsync(xdot, c->d_xdot.p, sizeof(double) * ne * nx, cudaMemcpyDeviceToHost, c->stream));
     if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
     if (flags) CU(cudaMemcpyAsync(flags, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
     int rc2 = status_end(c, n_env);

@@ -14,6 +14,8 @@ struct DualIO {
     double* sdot7;          // [env][bristle][6][7]
     const long long* n_pairs;  // [env][ins] (from the Float64 broad phase)
     int* flags;             // [env][ins]
+    long long n_real;       // whole-Jacobian mode: the n_env "environments" are n_env / n_real seed chunks of n_real real ones
+                            // (chunk-major); pair lists, counts and flags exist once per REAL environment.  Otherwise = n_env.
 };
 
 // pair list access for both paths

@@ -37,11 +37,12 @@ __global__ void __launch_bounds__(128) eval_dual6_chunked_kernel(SceneDev sc, Du
     const int chunk = lane / kChunkSlots, slot = lane - chunk * kChunkSlots;   // lanes 30, 31: chunk 3 = idle
     const long long n_prob = io.n_env * sc.n_ins;
     for (long long ei = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); ei < n_prob; ei += (long long)gridDim.x * 4) {
-        const long long env = ei / sc.n_ins;
-        const int k = int(ei - env * sc.n_ins);
+        const long long env_v = ei / sc.n_ins;
+        const int k = int(ei - env_v * sc.n_ins);
+        const long long env = env_v % io.n_real, er = env * sc.n_ins + k;   // the real environment whose pair list this problem reads
         const InsDev& ins = sc.ins[k];
         if (ins.model != PFC_MODEL_REGULARIZED) continue;   // bristle: pfc_exact.cu
-        const int n = (int)io.n_pairs[ei];
+        const int n = (int)io.n_pairs[er];
         int flags = 0;
         bool contact = false;
         for (int j = lane; j < 42; j += 32) sm.wout[j] = 0.0;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(128) eval_dual6_chunked_kernel(SceneDev sc, Du
                 cxv.w_lin = mk<double>(c0.w_lin.x.v, c0.w_lin.y.v, c0.w_lin.z.v);
                 cxv.chi = c0.chi; cxv.Ebar1 = c0.Ebar1; cxv.Ebar2 = c0.Ebar2; cxv.n_quad = c0.n_quad;
             }
-            const unsigned* pl_s = ins.small ? ps.small_pairs + (size_t)ps.small_cap * ei : nullptr;
+            const unsigned* pl_s = ins.small ? ps.small_pairs + (size_t)ps.small_cap * er : nullptr;
             const int3* pl_l = ins.small ? nullptr : ps.large_sorted + ps.seg_start[env * ps.n_large + ps.large_index[k]];
             // An instruction none of whose inputs depends on the seeded state entries (every partial of x_r2_r1 and the twist is zero -- e.g. the
             // seeds sit on another body) has zero wrench partials: its Dual evaluation is the Float64 evaluation, 7x cheaper.  The reference
@@ -158,7 +159,10 @@ __global__ void __launch_bounds__(128) eval_dual6_chunked_kernel(SceneDev sc, Du
         __syncwarp();
         double* wo = io.wrench7 + 42 * ei;
         for (int j = lane; j < 42; j += 32) wo[j] = contact ? sm.wout[j] : 0.0;
-        if (lane == 0) io.flags[ei] = (io.flags[ei] & ~kFlagContact) | flags | (contact ? kFlagContact : 0);
+        if (lane == 0) {
+            if (io.n_real == io.n_env) io.flags[er] = (io.flags[er] & ~kFlagContact) | flags | (contact ? kFlagContact : 0);
+            else if (flags | (contact ? kFlagContact : 0)) atomicOr(&io.flags[er], flags | (contact ? kFlagContact : 0));   // several chunks share the word
+        }
         __syncwarp();
     }
 }
@@ -170,8 +174,8 @@ const int3* large_sorted_ptr(const LargeBuffers* b);
 
 cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double* X7, const double* twist7, const double* s7, double* wrench7, double* sdot7,
                               const long long* n_pairs, int* flags, const unsigned* small_pairs, int small_cap, const LargeBuffers* lb,
-                              const int32_t* large_index, int n_large, cudaStream_t stream) {
-    DualIO io{n_env, X7, twist7, s7, wrench7, sdot7, n_pairs, flags};
+                              const int32_t* large_index, int n_large, cudaStream_t stream, long long n_real) {
+    DualIO io{n_env, X7, twist7, s7, wrench7, sdot7, n_pairs, flags, n_real > 0 ? n_real : n_env};
     PairSource ps{small_pairs, small_cap, lb ? large_sorted_ptr(lb) : nullptr, lb ? large_seg_start_ptr(lb) : nullptr, large_index, n_large};
     const long long n_prob = n_env * sc.n_ins;
     if (n_prob == 0) return cudaSuccess;

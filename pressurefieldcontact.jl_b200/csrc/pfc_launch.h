@@ -88,10 +88,12 @@ cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins
                                   cudaStream_t stream, int* n_launches);
 // Jacobian mode of the same kernels (Dual<6>, seeds on x[seed0 .. seed0 + 6)): every output scalar is 7 doubles (value, 6 partials)
 cudaError_t launch_state_prologue_dual6(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, int seed0, double* X7, double* twist7,
-                                        double* s7, cudaStream_t stream, int* n_launches);
+                                        double* s7, cudaStream_t stream, int* n_launches, long long n_real = 0);
 cudaError_t launch_state_dynamics_dual6(const StateDev& sd, const DynDev& dd, long long n_env, int n_ins, int n_bristle, const double* x, int seed0,
                                         const double* wrench7, const double* tau_ext, const double* sdot7, double* xdot7, cudaStream_t stream,
-                                        int* n_launches, const int* flags = nullptr, int* status = nullptr);
+                                        int* n_launches, const int* flags = nullptr, int* status = nullptr, long long n_real = 0, double* jac = nullptr);
+// (n_real > 0: whole-Jacobian mode -- the n_env entries are n_env / n_real seed chunks of n_real real environments, chunk-major, chunk g
+//  seeded on x[seed0 + 6 g ..); with jac the partials go to jac[env][row][seed + k] (row-major n_x x n_x) and chunk 0's values to xdot7[env][row])
 // flags / status (optional): OR the error bits of flags[n_env * n_ins] into *status (see or_error_flags)
 cudaError_t launch_state_epilogue(const StateDev& sd, long long n_env, int n_ins, const double* x, const double* wrench, double* f_gen, cudaStream_t stream,
                                   int* n_launches, const int* flags = nullptr, int* status = nullptr);

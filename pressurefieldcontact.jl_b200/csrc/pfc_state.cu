@@ -109,13 +109,16 @@ template <class T> PFC_D void body_frame(const BodyDev& b, const StateRead<T>& x
 
 // one thread per (environment, instruction): boundary arrays; one extra pass copies the bristle states
 template <class T>
-__global__ void __launch_bounds__(128) state_prologue_kernel(StateDev sd, long long n_env, int n_ins, int n_bristle, const double* __restrict__ x, int seed0,
-                                                             double* __restrict__ X, double* __restrict__ twist, double* __restrict__ s) {
+__global__ void __launch_bounds__(128) state_prologue_kernel(StateDev sd, long long n_env, long long n_real, int n_ins, int n_bristle,
+                                                             const double* __restrict__ x, int seed0, double* __restrict__ X, double* __restrict__ twist,
+                                                             double* __restrict__ s) {
+    // n_env = n_chunk * n_real "environments", chunk-major: entry (chunk, env) reads the state of real environment env with the seeds
+    // on x[seed0 + 6 chunk ..) -- the whole-Jacobian mode; n_real == n_env otherwise
     const long long n = n_env * n_ins;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
         const long long env = id / n_ins;
         const int k = (int)(id - env * n_ins);
-        const StateRead<T> xr{x + env * sd.n_x, seed0};
+        const StateRead<T> xr{x + (env % n_real) * sd.n_x, seed0 + 6 * (int)(env / n_real)};
         Frame<T> f1, f2;
         body_frame(sd.bodies[sd.ins_body[2 * k]], xr, sd.nq, f1, true);
         body_frame(sd.bodies[sd.ins_body[2 * k + 1]], xr, sd.nq, f2, true);
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(128) state_prologue_kernel(StateDev sd, long l
     const long long ns = n_env * 6 * n_bristle;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < ns; id += (long long)gridDim.x * blockDim.x) {
         const long long env = id / (6 * n_bristle);
-        const StateRead<T> xr{x + env * sd.n_x, seed0};
+        const StateRead<T> xr{x + (env % n_real) * sd.n_x, seed0 + 6 * (int)(env / n_real)};
         store_scalar(s, id, xr(sd.nq + sd.nv + (int)(id - env * 6 * n_bristle)));
     }
 }
@@ -220,20 +223,36 @@ __global__ void __launch_bounds__(128) state_epilogue_kernel(StateDev sd, long l
 //   q_dot = [B(p) w; R u],  B(p) = ((1 - p'p) I + 2 [p]x + 2 p p') / 4                  (configuration_derivative!, SPQuatFloating)
 // and one extra pass copies s_dot behind [q_dot; v_dot] (copyto!, src/extensions.jl:40-50).
 // wrench / sdot / xdot hold 1 (double) or 7 (Dual<6>: value, 6 partials) doubles per scalar.
+// Where row `row` of x_dot goes.  Plain mode: xdot[env][row] (1 or 7 doubles).  Whole-Jacobian mode (jac != nullptr, Dual only): the
+// partials are columns seed .. seed + 5 of jac[env][row][.] (row-major n_x x n_x per environment, the layout of calcJacobian!'s
+// `jac`, /root/reference/src/radau/radau_functions.jl:2-26) and chunk 0 also writes the value to xdot[env][row] when asked to.
+struct XdotOut { double* xdot; double* jac; int n_x; };
+PFC_D void emit_row(const XdotOut& o, long long env_real, int row, int seed, bool first_chunk, double v) { o.xdot[env_real * o.n_x + row] = v; (void)seed; (void)first_chunk; }
+PFC_D void emit_row(const XdotOut& o, long long env_real, int row, int seed, bool first_chunk, const D6& v) {
+    if (!o.jac) { store_scalar(o.xdot, env_real * o.n_x + row, v); return; }
+    double* j = o.jac + ((size_t)env_real * o.n_x + row) * o.n_x;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (seed + k < o.n_x) j[seed + k] = v.p[k];
+    if (first_chunk && o.xdot) o.xdot[env_real * o.n_x + row] = v.v;
+}
+
 template <class T>
-__global__ void __launch_bounds__(128) state_dynamics_kernel(StateDev sd, DynDev dd, long long n_env, int n_ins, int n_bristle, const double* __restrict__ x,
-                                                             int seed0, const double* __restrict__ wrench, const double* __restrict__ tau_ext,
-                                                             const double* __restrict__ sdot, double* __restrict__ xdot,
+__global__ void __launch_bounds__(128) state_dynamics_kernel(StateDev sd, DynDev dd, long long n_env, long long n_real, int n_ins, int n_bristle,
+                                                             const double* __restrict__ x, int seed0, const double* __restrict__ wrench,
+                                                             const double* __restrict__ tau_ext, const double* __restrict__ sdot, XdotOut out,
                                                              const int* __restrict__ flags, int* __restrict__ status) {
     constexpr int W = sizeof(T) / sizeof(double);   // doubles per scalar
-    or_error_flags(flags, n_env * n_ins, status);
+    or_error_flags(flags, n_real * n_ins, status);
     const long long n = n_env * sd.n_body;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
-        const long long env = id / sd.n_body;
+        const long long env = id / sd.n_body;           // (chunk, real environment), chunk-major
         const int b = (int)(id - env * sd.n_body);
         const BodyDev& body = sd.bodies[b];
         if (body.joint == 0) continue;
-        const StateRead<T> xr{x + env * sd.n_x, seed0};
+        const long long er = env % n_real;
+        const int seed = seed0 + 6 * (int)(env / n_real);
+        const bool first = env < n_real;
+        const StateRead<T> xr{x + er * sd.n_x, seed};
         T v[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) v[i] = xr(sd.nq + body.v0 + i);
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(128) state_dynamics_kernel(StateDev sd, DynDev
         body_generalized_force(sd, b, fb, xr, wrench + (size_t)W * 6 * env * n_ins, f, f + 3);
         if (tau_ext) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) f[i] = f[i] + tau_ext[env * sd.nv + body.v0 + i];
+            for (int i = 0; i < 6; ++i) f[i] = f[i] + tau_ext[er * sd.nv + body.v0 + i];
         }
         const double* H = dd.H + 36 * b;
         const double* Hi = dd.Hinv + 36 * b;
@@ -278,21 +297,19 @@ __global__ void __launch_bounds__(128) state_dynamics_kernel(StateDev sd, DynDev
         const T pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2], pw = p[0] * v[0] + p[1] * v[1] + p[2] * v[2];
         T pxw[3];
         cross3(p, v, pxw);
-        const long long o = env * sd.n_x;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            store_scalar(xdot, o + body.q0 + i, ((1.0 - pp) * v[i] + 2.0 * pxw[i] + 2.0 * p[i] * pw) * 0.25);
-            store_scalar(xdot, o + body.q0 + 3 + i, qd_t[i]);
-            store_scalar(xdot, o + sd.nq + body.v0 + i, vd[i]);
-            store_scalar(xdot, o + sd.nq + body.v0 + 3 + i, vd[3 + i] + g_b[i]);
+            emit_row(out, er, body.q0 + i, seed, first, ((1.0 - pp) * v[i] + 2.0 * pxw[i] + 2.0 * p[i] * pw) * 0.25);
+            emit_row(out, er, body.q0 + 3 + i, seed, first, qd_t[i]);
+            emit_row(out, er, sd.nq + body.v0 + i, seed, first, vd[i]);
+            emit_row(out, er, sd.nq + body.v0 + 3 + i, seed, first, vd[3 + i] + g_b[i]);
         }
     }
     const long long ns = n_env * 6 * n_bristle;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < ns; id += (long long)gridDim.x * blockDim.x) {
         const long long env = id / (6 * n_bristle);
-        const long long dst = env * sd.n_x + sd.nq + sd.nv + (id - env * 6 * n_bristle);
-#pragma unroll
-        for (int k = 0; k < W; ++k) xdot[W * dst + k] = sdot[W * id + k];
+        emit_row(out, env % n_real, sd.nq + sd.nv + (int)(id - env * 6 * n_bristle), seed0 + 6 * (int)(env / n_real), env < n_real,
+                 load_scalar(sdot, id, (T*)nullptr));
     }
 }
 
@@ -304,16 +321,16 @@ cudaError_t launch_state_prologue(const StateDev& sd, long long n_env, int n_ins
                                   cudaStream_t stream, int* n_launches) {
     const long long n = n_env * n_ins;
     if (n == 0) return cudaSuccess;
-    state_prologue_kernel<double><<<state_blocks(n), 128, 0, stream>>>(sd, n_env, n_ins, n_bristle, x, 0, X, twist, s);
+    state_prologue_kernel<double><<<state_blocks(n), 128, 0, stream>>>(sd, n_env, n_env, n_ins, n_bristle, x, 0, X, twist, s);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_state_prologue_dual6(const StateDev& sd, long long n_env, int n_ins, int n_bristle, const double* x, int seed0, double* X7, double* twist7,
-                                        double* s7, cudaStream_t stream, int* n_launches) {
+                                        double* s7, cudaStream_t stream, int* n_launches, long long n_real) {
     const long long n = n_env * n_ins;
     if (n == 0) return cudaSuccess;
-    state_prologue_kernel<D6><<<state_blocks(n), 128, 0, stream>>>(sd, n_env, n_ins, n_bristle, x, seed0, X7, twist7, s7);
+    state_prologue_kernel<D6><<<state_blocks(n), 128, 0, stream>>>(sd, n_env, n_real > 0 ? n_real : n_env, n_ins, n_bristle, x, seed0, X7, twist7, s7);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
@@ -331,17 +348,18 @@ cudaError_t launch_state_dynamics(const StateDev& sd, const DynDev& dd, long lon
                                   const double* tau_ext, const double* sdot, double* xdot, cudaStream_t stream, int* n_launches, const int* flags, int* status) {
     const long long n = n_env * sd.n_body;
     if (n == 0) return cudaSuccess;
-    state_dynamics_kernel<double><<<state_blocks(n), 128, 0, stream>>>(sd, dd, n_env, n_ins, n_bristle, x, 0, wrench, tau_ext, sdot, xdot, flags, status);
+    state_dynamics_kernel<double><<<state_blocks(n), 128, 0, stream>>>(sd, dd, n_env, n_env, n_ins, n_bristle, x, 0, wrench, tau_ext, sdot, XdotOut{xdot, nullptr, sd.n_x}, flags, status);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_state_dynamics_dual6(const StateDev& sd, const DynDev& dd, long long n_env, int n_ins, int n_bristle, const double* x, int seed0,
                                         const double* wrench7, const double* tau_ext, const double* sdot7, double* xdot7, cudaStream_t stream,
-                                        int* n_launches, const int* flags, int* status) {
+                                        int* n_launches, const int* flags, int* status, long long n_real, double* jac) {
     const long long n = n_env * sd.n_body;
     if (n == 0) return cudaSuccess;
-    state_dynamics_kernel<D6><<<state_blocks(n), 128, 0, stream>>>(sd, dd, n_env, n_ins, n_bristle, x, seed0, wrench7, tau_ext, sdot7, xdot7, flags, status);
+    state_dynamics_kernel<D6><<<state_blocks(n), 128, 0, stream>>>(sd, dd, n_env, n_real > 0 ? n_real : n_env, n_ins, n_bristle, x, seed0, wrench7, tau_ext, sdot7,
+                                                                   XdotOut{xdot7, jac, sd.n_x}, flags, status);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

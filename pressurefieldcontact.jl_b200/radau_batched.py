@@ -4,7 +4,7 @@ advanced for a whole BATCH of independent environments with every array resident
 
 What runs where
   * stage evaluations F(X_stage): pfc_calcxd_f64_device  -- calcXd! for n_env x n_stage states in ONE launch sequence
-  * Jacobian: ceil(NX / 6) calls of pfc_calcxd_dual6_device -- one Dual-6 chunk for all environments per call (calcJacobian!)
+  * Jacobian: one call of pfc_calcxd_jacobian_device -- all ceil(NX / 6) Dual-6 chunks of all environments (calcJacobian!)
   * (h^-1 lambda_i I - J)^-1 for every environment and stage: pfc_radau_inv_c_device, one CTA per matrix, Gauss-Jordan with partial
     pivoting in shared memory (the reference calls LAPACK getrf / getri here, radau_functions.jl:88-99; batched cuSOLVER through
     torch.linalg.inv took 17.6 ms for 4096 48 x 48 matrices)
@@ -53,7 +53,7 @@ class BatchedRadau:
         self.n_ins = self.ctx.n_ins
         self.mrp_cols = torch.tensor([b.q0 for b in m.bodies if isinstance(b.joint, S.SPQuatFloating)], dtype=torch.int64, device=self.dev)
         self.n_calcxd_states = 0     # states pushed through pfc_calcxd_f64_device
-        self.n_chunk_states = 0      # states pushed through pfc_calcxd_dual6_device
+        self.n_chunk_states = 0      # (state, chunk) pairs pushed through pfc_calcxd_jacobian_device
         self.n_attempts = 0
 
     # ---- device entry points ------------------------------------------------------------------------------------------
@@ -71,17 +71,15 @@ class BatchedRadau:
     def _jacobian(self, x0: torch.Tensor):
         """calcJacobian! (radau_functions.jl:1-14) for every environment: (xx_0 [E, NX], -J [E, NX, NX])."""
         E, NX = x0.shape
-        negJ = torch.empty((E, NX, NX), dtype=torch.float64, device=self.dev)
         x0 = x0.contiguous()
-        xd7 = torch.zeros((E, NX, 7), dtype=torch.float64, device=self.dev)
+        jac = torch.empty((E, NX, NX), dtype=torch.float64, device=self.dev)
+        xx0 = torch.empty((E, NX), dtype=torch.float64, device=self.dev)
         npairs = torch.empty((E, self.n_ins), dtype=torch.int64, device=self.dev)
         flags = torch.empty((E, self.n_ins), dtype=torch.int32, device=self.dev)
-        for i0 in range(0, NX, 6):
-            i1 = min(i0 + 6, NX)
-            self.ctx.calcxd_dual6_device(E, x0.data_ptr(), None, i0, xd7.data_ptr(), npairs.data_ptr(), flags.data_ptr())
-            self.n_chunk_states += E
-            negJ[:, :, i0:i1] = -xd7[:, :, 1:1 + (i1 - i0)]
-        return xd7[:, :, 0].clone(), negJ
+        # one call: Float64 kinematics + broad phase once, every seed chunk side by side in the Dual kernels (pfc_calcxd_jacobian_device)
+        self.ctx.calcxd_jacobian_device(E, x0.data_ptr(), None, jac.data_ptr(), xx0.data_ptr(), npairs.data_ptr(), flags.data_ptr())
+        self.n_chunk_states += E * ((NX + 5) // 6)
+        return xx0, jac.neg_()
 
     # ---- one Newton attempt for the environments idx, all on rule `rule` -----------------------------------------------------
     def _newton(self, rule: int, idx: torch.Tensor, x0: torch.Tensor, xx_0: torch.Tensor, negJ: torch.Tensor):

@@ -65,8 +65,9 @@ def wrench_rel_err(w, w_ref, floor=0.0):
 
 
 # ---- reference scenes ------------------------------------------------------------------------------
-def scene_boxes(backend=None, max_env=1):
-    """test/boxes.jl:18-45 (config C1): plane + 4 boxes alternately rigid (tri) / compliant (tet)."""
+def scene_boxes(backend=None, max_env=1, bristle=False):
+    """test/boxes.jl:18-45 (config C1): plane + 4 boxes alternately rigid (tri) / compliant (tet).  bristle=True: the box_1-box_2 and
+    box_3-box_4 instructions use bristle friction instead (12 more state entries), for tests of the paths bristle scenes take."""
     r = 0.05
     c_prop = S.ContactProperties(1.0e6)
     i_c, i_r = S.InertiaProperties(400.0), S.InertiaProperties(400.0, d=r)
@@ -78,9 +79,11 @@ def scene_boxes(backend=None, max_env=1):
     b3 = S.add_body_contact(m, "box_3", G.as_tri_eMesh(box), i_prop=i_r)
     b4 = S.add_body_contact(m, "box_4", G.as_tet_eMesh(box), i_prop=i_c, c_prop=c_prop)
     S.add_friction_regularize(m, id_plane, b1[2], mu_d=0.0, chi=2.2, n_quad_rule=2)
-    S.add_friction_regularize(m, b1[2], b2[2], mu_d=0.2, chi=0.2, n_quad_rule=2)
+    add_12_34 = (lambda a, c: S.add_friction_bristle(m, a, c, mu_d=0.2, chi=0.2, k_bar=2.0e4, tau=0.05, n_quad_rule=2)) if bristle else (
+        lambda a, c: S.add_friction_regularize(m, a, c, mu_d=0.2, chi=0.2, n_quad_rule=2))
+    add_12_34(b1[2], b2[2])
     S.add_friction_regularize(m, b2[2], b3[2], mu_d=0.2, chi=0.2, n_quad_rule=2)
-    S.add_friction_regularize(m, b3[2], b4[2], mu_d=0.2, chi=0.2, n_quad_rule=2)
+    add_12_34(b3[2], b4[2])
     S.finalize(m, backend, max_env)
     for k, b in enumerate((b1, b2, b3, b4)):
         S.set_state_spq(m, b[0], trans=(0.0, 0.0, (2 + 3 * k) * r), w=(0.0, 0.0, float(k + 1)))
@@ -124,4 +127,5 @@ def boxes_env_states(m, n_env, r=0.05, start=0):
             vel = [U(-0.1, 0.1) for _ in range(3)]
             X[e, b.q0:b.q0 + 6] = mrp + xy + [z]
             X[e, nq + b.v0:nq + b.v0 + 6] = om + vel
+        X[e, nq + m.nv:] = [U(-1e-4, 1e-4) for _ in range(6 * m.n_bristle)]
     return X

@@ -71,6 +71,45 @@ def test_calcxd_dual6_device_matches_host_mirror_with_oracle_contact():
                 assert np.abs(g[:, 1 + d] - col).max() <= TOL * max(np.abs(col).max(), 1e-6 * np.abs(cols).max()), (i0, e, d)
 
 
+@pytest.mark.parametrize("bristle", [False, True])
+def test_whole_jacobian_equals_its_chunks_bit_for_bit(bristle):
+    """pfc_calcxd_jacobian (one Float64 broad phase, the seed chunks as a grid axis of the Dual kernels; bristle scenes chunk by chunk over
+    the shared pair lists) against ceil(n_x / 6) calls of pfc_calcxd_dual6: the same bits, value and partials; then against the host
+    mirror + oracle like the chunk test.  n_x = 48 (8 chunks) and, with two bristle instructions, 60 (10 chunks)."""
+    n_env = 12
+    m_gpu = scene_boxes(_ctx(), max_env=n_env, bristle=bristle)[0]
+    x = boxes_env_states(m_gpu, n_env)
+    nx = S.num_x(m_gpu)
+    assert nx == (60 if bristle else 48)
+    rng = np.random.default_rng(11)
+    tau = rng.uniform(-1, 1, (n_env, m_gpu.nv))
+    whole = m_gpu.backend.calcxd_jacobian(x, tau)
+    assert (whole["flags"] & 1).any()
+    for i0 in range(0, nx, 6):
+        i1 = min(i0 + 6, nx)
+        chunk = m_gpu.backend.calcxd_dual6(x, i0, tau)
+        assert np.array_equal(whole["jac"][:, :, i0:i1], chunk["xdot7"][:, :, 1:1 + (i1 - i0)]), i0
+        if i0 == 0:   # x_dot is the value part of the first pass (an instruction none of whose bodies is seeded is summed in Float64 order:
+            assert np.array_equal(whole["xdot"], chunk["xdot7"][:, :, 0])   # the value parts of different passes differ by rounding)
+        else:
+            assert np.abs(whole["xdot"] - chunk["xdot7"][:, :, 0]).max() <= 1e-12 * np.abs(whole["xdot"]).max()
+        assert np.array_equal(whole["n_pairs"], chunk["n_pairs"]) and np.array_equal(whole["flags"], chunk["flags"])
+    # and the Float64 evaluation agrees with the value part (same pair lists; Dual value parts are Float64 operations)
+    plain = m_gpu.backend.calcxd_f64(x, tau)
+    assert np.abs(plain["xdot"] - whole["xdot"]).max() <= 1e-9 * np.abs(plain["xdot"]).max()
+    # against the host mirror (complex-step rigid-body terms + the oracle's Dual-6 wrenches), two environments (tau_ext is additive: the
+    # partials do not depend on it)
+    m_cpu = scene_boxes(orc.OracleContext(), bristle=bristle)[0]
+    dyn = D.FloatingBodyDynamics(m_cpu)
+    for e in (0, n_env - 1):
+        for i0 in range(0, nx, 6):
+            i1 = min(i0 + 6, nx)
+            _, cols = dyn.de_jacobian_chunk(x[e], i0, i1)
+            for d in range(i1 - i0):
+                col = cols[:, d]
+                assert np.abs(whole["jac"][e, :, i0 + d] - col).max() <= TOL * max(np.abs(col).max(), 1e-6 * np.abs(cols).max()), (e, i0, d)
+
+
 def _integrate(backend, x0, n_steps, h_max=0.05, device=False):
     m = scene_boxes(backend)[0]
     dyn = D.FloatingBodyDynamics(m, device=device)
