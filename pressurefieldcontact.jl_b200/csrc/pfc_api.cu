@@ -187,6 +187,7 @@ struct pfc_ctx {
     EvalIO sharded_io{};
     // Jacobian mode staging + the pair lists it may reuse
     DevBuf<double> d_X7, d_tw7, d_s7, d_w7, d_sd7, d_jac;
+    DevBuf<unsigned> d_dual_ticket;   // tile ticket of the Dual kernel
     DevBuf<int32_t> d_large_index;
     int64_t lists_n_env = -1;   // n_env of the evaluation whose pair lists (d_small_pairs / large_buf, lists_np, lists_fl) are current
     long long* lists_np = nullptr;   // where that evaluation left its pair counts / flags (d_np / d_fl, or the packed block of a small call)
@@ -1112,7 +1113,7 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
     } else if (c->lists_n_env != n_env || !c->lists_np || !c->lists_fl) {
         return fail(PFC_E_ARG, "pfc_eval_dual6: X_bp is NULL but no pair lists of a previous pfc_eval_f64 with the same n_env exist");
     }
-    CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni));
+    CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni)); CU(c->d_dual_ticket.ensure(1));
     if (nb) { CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
     CU(copy_in(c, c->d_X7.p, X7, sizeof(double) * 112 * ne * ni));
     CU(copy_in(c, c->d_tw7.p, twist7, sizeof(double) * 42 * ne * ni));
@@ -1137,7 +1138,7 @@ int pfc_eval_dual6(pfc_ctx* c, int64_t n_env, const double* X_bp, const double* 
         }
         CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, np_d, fl_d,
                              c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
-                             c->large_scene.n_large, c->stream));
+                             c->large_scene.n_large, c->stream, c->d_dual_ticket.p));
         {   // bristle instructions on Duals, in the reference's operation order
             int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, np_d, fl_d, 1, false, &nl);
             if (rc != PFC_OK) return rc;
@@ -1434,7 +1435,7 @@ static int calcxd_dual6_device_once(pfc_ctx* c, int64_t n_env, const double* x, 
                                     int* flags, int* status) {
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle);
     CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni));
-    CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni));
+    CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni)); CU(c->d_dual_ticket.ensure(1));
     if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
     int nl = 0;
     // Float64 boundary transforms -> candidate-pair lists
@@ -1457,7 +1458,7 @@ static int calcxd_dual6_device_once(pfc_ctx* c, int64_t n_env, const double* x, 
     CU(launch_state_prologue_dual6(c->state, n_env, int(ni), int(nb), x, seed_start, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl));
     CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags,
                          c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
-                         c->large_scene.n_large, c->stream));
+                         c->large_scene.n_large, c->stream, c->d_dual_ticket.p));
     {
         int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags, 1, false, &nl);
         if (rc != PFC_OK) return rc;
@@ -1524,7 +1525,7 @@ static int jacobian_device_once(pfc_ctx* c, int64_t n_env, const double* x, cons
     if (nb == 0) G = int(std::max<size_t>(1, std::min<size_t>(size_t(n_chunk), (size_t(1) << 30) / std::max<size_t>(1, ne * ni * 196 * sizeof(double)))));
     const size_t nv_env = ne * size_t(G);
     CU(c->d_X.ensure(16 * ne * ni)); CU(c->d_tw.ensure(6 * ne * ni));
-    CU(c->d_X7.ensure(112 * nv_env * ni)); CU(c->d_tw7.ensure(42 * nv_env * ni)); CU(c->d_w7.ensure(42 * nv_env * ni));
+    CU(c->d_X7.ensure(112 * nv_env * ni)); CU(c->d_tw7.ensure(42 * nv_env * ni)); CU(c->d_w7.ensure(42 * nv_env * ni)); CU(c->d_dual_ticket.ensure(1));
     if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
     int nl = 0;
     CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), x, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
@@ -1548,7 +1549,7 @@ static int jacobian_device_once(pfc_ctx* c, int64_t n_env, const double* x, cons
         CU(launch_state_prologue_dual6(c->state, n_virtual, int(ni), int(nb), x, 6 * g0, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl, n_env));
         CU(launch_eval_dual6(c->scene, n_virtual, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags,
                              c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
-                             c->large_scene.n_large, c->stream, n_env));
+                             c->large_scene.n_large, c->stream, c->d_dual_ticket.p, n_env));
         nl += 1;
         if (nb) {
             int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, c->d_s7.p, c->d_w7.p, c->d_sd7.p, n_pairs, flags, 1, false, &nl);

@@ -47,6 +47,6 @@ cudaError_t large_get_pairs(LargeBuffers* b, int prob, int* out, long long cap, 
 // Jacobian mode of the regularized instructions (pfc_dual_chunked.cu): narrow phase + friction + reduction on Duals over existing pair lists.
 cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double* X7, const double* twist7, const double* s7, double* wrench7, double* sdot7,
                               const long long* n_pairs, int* flags, const unsigned* small_pairs, int small_cap, const LargeBuffers* lb,
-                              const int32_t* large_index, int n_large, cudaStream_t stream, long long n_real = 0);
+                              const int32_t* large_index, int n_large, cudaStream_t stream, unsigned* ticket, long long n_real = 0);
 
 }  // namespace pfc

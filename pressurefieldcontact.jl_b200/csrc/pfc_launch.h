@@ -42,6 +42,7 @@ struct EvalIO {
 constexpr int kSmallCap = 512;      // frontier / pair capacity of the fused small path
 
 int small_cap(int max_pairs);
+int persistent_blocks(const void* kern, int threads, size_t smem, cudaError_t* err);   // resident CTAs of a persistent kernel on the current device (pfc_small.cu)
 constexpr int kSmallPairsSlack = 32;   // words after the pair lists: [0] is the narrow tile kernel's tile ticket (zeroed by the broad kernel)
 // ev: optional array of 3 events recorded before the broad kernel, between the two kernels and after the narrow kernel
 cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches,

@@ -523,6 +523,8 @@ __global__ void dump_traction_kernel(SceneDev sc, EvalIO io, long long env, int 
     *n_points = acc.n_points;
 }
 
+}  // namespace
+
 int persistent_blocks(const void* kern, int threads, size_t smem, cudaError_t* err) {
     int per_sm = 0, dev = 0, n_sm = 0;
     *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -532,6 +534,8 @@ int persistent_blocks(const void* kern, int threads, size_t smem, cudaError_t* e
     *err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     return n_sm * (per_sm > 0 ? per_sm : 1);
 }
+
+namespace {
 
 template <int P, int NW, int MINB>
 cudaError_t launch_broad_tile(const SceneDev& sc, const EvalIO& io, int cap, unsigned* pairs, cudaStream_t stream) {
