@@ -188,6 +188,8 @@ struct pfc_ctx {
     // Jacobian mode staging + the pair lists it may reuse
     DevBuf<double> d_X7, d_tw7, d_s7, d_w7, d_sd7, d_jac;
     DevBuf<unsigned> d_dual_ticket;   // tile ticket of the Dual kernel
+    DevBuf<unsigned> d_surv;          // Jacobian mode: pairs that survive the Float64 clip [env][ins][cap]
+    DevBuf<int> d_surv_n;
     DevBuf<int32_t> d_large_index;
     int64_t lists_n_env = -1;   // n_env of the evaluation whose pair lists (d_small_pairs / large_buf, lists_np, lists_fl) are current
     long long* lists_np = nullptr;   // where that evaluation left its pair counts / flags (d_np / d_fl, or the packed block of a small call)
@@ -1428,6 +1430,37 @@ int pfc_calcxd_f64(pfc_ctx* c, int64_t n_env, const double* x, const double* tau
     return status_end(c, n_env);
 }
 
+// The Float64 part the seed chunks of a Jacobian share: candidate-pair lists, the wrenches of the regularized instructions (problems whose
+// inputs do not depend on a chunk's seeds copy them) and, for the small instructions, the pairs that survive the Float64 clip.
+// Expects the Float64 boundary arrays in c->d_X / c->d_tw.
+static int dual_shared_f64(pfc_ctx* c, int64_t n_env, long long* n_pairs, int* flags, DualShared* sh, int* nl) {
+    const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins);
+    CU(c->d_w.ensure(6 * ne * ni));
+    EvalIO io{};
+    io.n_env = n_env; io.X = c->d_X.p; io.twist = c->d_tw.p; io.wrench = c->d_w.p; io.n_pairs = n_pairs; io.flags = flags;
+    sh->surv_pairs = nullptr; sh->surv_n = nullptr; sh->w_f64 = c->d_w.p;
+    if (c->scene.n_small > 0) {
+        const int cap = small_cap(c->small_max_pairs);
+        CU(c->d_small_pairs.ensure(size_t(cap) * ne * ni + kSmallPairsSlack));
+        CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, nl, nullptr));
+        CU(c->d_surv.ensure(size_t(cap) * ne * ni)); CU(c->d_surv_n.ensure(ne * ni));
+        CU(launch_dual_prefilter(c->scene, n_env, c->d_X.p, n_pairs, c->d_small_pairs.p, cap, c->d_surv.p, c->d_surv_n.p, c->stream));
+        *nl += 1;
+        sh->surv_pairs = c->d_surv.p; sh->surv_n = c->d_surv_n.p;
+    }
+    if (c->large_scene.n_large > 0) {
+        if (c->shard_world > 1) return fail(PFC_E_ARG, "this context is sharded: the Jacobian mode needs an unsharded context");
+        CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, nl));
+        CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, 0, 0, c->stream, nl));
+    }
+    if (c->n_mid > 0) {
+        CU(cudaMemcpyAsync(c->h_ins_overflow, c->d_ins_overflow.p, sizeof(int) * c->h_ins.size(), cudaMemcpyDeviceToHost, c->stream));
+        c->mid_check_pending = true;
+    }
+    c->lists_n_env = -1;   // the lists belong to caller-owned count / flag arrays: not reusable by pfc_eval_dual6(X_bp = NULL)
+    return PFC_OK;
+}
+
 // calcXd! in Jacobian mode for the same scenes: x (Float64) with Dual seeds on x[seed_start .. seed_start + 6) -> x_dot as 7 doubles per
 // entry (value, then d x_dot / d x[seed_start + k]).  Device pipeline: Float64 prologue + broad phase (the reference always traverses
 // with m.float), Dual prologue, Dual narrow phase / friction (pfc_dual.cu), Dual J' w and rigid-body terms.
@@ -1438,27 +1471,15 @@ static int calcxd_dual6_device_once(pfc_ctx* c, int64_t n_env, const double* x, 
     CU(c->d_X7.ensure(112 * ne * ni)); CU(c->d_tw7.ensure(42 * ne * ni)); CU(c->d_w7.ensure(42 * ne * ni)); CU(c->d_dual_ticket.ensure(1));
     if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
     int nl = 0;
-    // Float64 boundary transforms -> candidate-pair lists
+    // Float64 boundary arrays -> candidate-pair lists, Float64 wrenches, survivors of the Float64 clip
     CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), x, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
-    {
-        EvalIO io{};
-        io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = n_pairs; io.flags = flags;
-        if (c->scene.n_small > 0) {
-            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni + kSmallPairsSlack));
-            CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
-        }
-        if (c->large_scene.n_large > 0) {
-            CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
-            CU(large_write_counts(c->scene, c->large_scene, io, c->large_buf, c->stream));
-            nl += 1;
-        }
-        c->lists_n_env = -1;   // the lists belong to caller-owned count / flag arrays: not reusable by pfc_eval_dual6(X_bp = NULL)
-    }
+    DualShared shared{};
+    { const int rc = dual_shared_f64(c, n_env, n_pairs, flags, &shared, &nl); if (rc != PFC_OK) return rc; }
     // Dual boundary arrays, Dual contact wrenches, Dual rigid-body terms
     CU(launch_state_prologue_dual6(c->state, n_env, int(ni), int(nb), x, seed_start, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl));
     CU(launch_eval_dual6(c->scene, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags,
                          c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
-                         c->large_scene.n_large, c->stream, c->d_dual_ticket.p));
+                         c->large_scene.n_large, c->stream, c->d_dual_ticket.p, 0, &shared));
     {
         int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags, 1, false, &nl);
         if (rc != PFC_OK) return rc;
@@ -1529,27 +1550,15 @@ static int jacobian_device_once(pfc_ctx* c, int64_t n_env, const double* x, cons
     if (nb) { CU(c->d_s.ensure(6 * ne * nb)); CU(c->d_s7.ensure(42 * ne * nb)); CU(c->d_sd7.ensure(42 * ne * nb)); }
     int nl = 0;
     CU(launch_state_prologue(c->state, n_env, int(ni), int(nb), x, c->d_X.p, c->d_tw.p, nb ? c->d_s.p : nullptr, c->stream, &nl));
-    {
-        EvalIO io{};
-        io.n_env = n_env; io.X = c->d_X.p; io.n_pairs = n_pairs; io.flags = flags;
-        if (c->scene.n_small > 0) {
-            CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * ne * ni + kSmallPairsSlack));
-            CU(launch_broad_small_only(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl));
-        }
-        if (c->large_scene.n_large > 0) {
-            CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
-            CU(large_write_counts(c->scene, c->large_scene, io, c->large_buf, c->stream));
-            nl += 1;
-        }
-        c->lists_n_env = -1;
-    }
+    DualShared shared{};
+    { const int rc = dual_shared_f64(c, n_env, n_pairs, flags, &shared, &nl); if (rc != PFC_OK) return rc; }
     for (int g0 = 0; g0 < n_chunk; g0 += G) {
         const int g = std::min(G, n_chunk - g0);
         const long long n_virtual = n_env * g;
         CU(launch_state_prologue_dual6(c->state, n_virtual, int(ni), int(nb), x, 6 * g0, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->stream, &nl, n_env));
         CU(launch_eval_dual6(c->scene, n_virtual, c->d_X7.p, c->d_tw7.p, nb ? c->d_s7.p : nullptr, c->d_w7.p, nb ? c->d_sd7.p : nullptr, n_pairs, flags,
                              c->d_small_pairs.p, small_cap(c->small_max_pairs), c->large_scene.n_large > 0 ? c->large_buf : nullptr, c->d_large_index.p,
-                             c->large_scene.n_large, c->stream, c->d_dual_ticket.p, n_env));
+                             c->large_scene.n_large, c->stream, c->d_dual_ticket.p, n_env, &shared));
         nl += 1;
         if (nb) {
             int rc = eval_bristle_exact(c, n_env, c->d_X7.p, c->d_tw7.p, c->d_s7.p, c->d_w7.p, c->d_sd7.p, n_pairs, flags, 1, false, &nl);

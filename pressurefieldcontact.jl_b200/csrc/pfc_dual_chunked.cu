@@ -35,7 +35,7 @@ namespace {
 typedef Dual<2> D2;
 constexpr int kDP = 8;            // problems per tile
 constexpr int kDT = 128;          // threads per CTA
-constexpr int kResStride = 19;    // 6 sums x (value, 2 partials) + point count, odd stride
+constexpr int kResStride = 43;    // per item: the 42 output scalars [7 comp + (0 = value, 1 + d = partial d)] + point count, odd stride
 constexpr int kTotStride = 43;    // 42 output scalars + point count
 
 struct DualTileSmem {
@@ -46,7 +46,7 @@ struct DualTileSmem {
     long long ei[kDP], er[kDP];   // problem index among the (chunk, env, ins) entries / among the real (env, ins) ones; ei = -1: nothing to do
     const unsigned* pl_s[kDP];
     const int3* pl_l[kDP];
-    int ins[kDP], seeded[kDP], pflags[kDP];
+    int ins[kDP], seeded[kDP], pflags[kDP], prefiltered[kDP], copied[kDP];
     int pre[kDP + 1];             // candidates before problem q
     int surv_a[kDT], surv_b[kDT];
     int item_off[kDT + 1];
@@ -72,6 +72,47 @@ PFC_D int block_scan_excl(int v, int* warp_tot, int& total) {
     return before + incl - v;
 }
 
+// Float64 clip of every candidate pair of the small regularized instructions, once per REAL (environment, instruction): the survivors,
+// packed in candidate order, are what every seed chunk of the Jacobian works on (two thirds of the candidates clip to nothing).  One warp
+// per problem, 32 candidates per pass.
+__global__ void __launch_bounds__(128) dual_prefilter_kernel(SceneDev sc, long long n_env, const double* __restrict__ X, const long long* __restrict__ n_pairs,
+                                                             const unsigned* __restrict__ pairs, int cap, unsigned* __restrict__ surv, int* __restrict__ surv_n) {
+    const int lane = threadIdx.x & 31;
+    const long long n_prob = n_env * sc.n_ins;
+    for (long long ei = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); ei < n_prob; ei += (long long)gridDim.x * 4) {
+        const int k = int(ei % sc.n_ins);
+        const InsDev& ins = sc.ins[k];
+        if (!ins.small || ins.model != PFC_MODEL_REGULARIZED) { if (lane == 0) surv_n[ei] = 0; continue; }
+        const int n = (int)n_pairs[ei];
+        PatchCtx<double> cx;
+        {
+            const double* Xe = X + 16 * ei;   // col-major 4x4 -> row-major rotation + translation
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) cx.x21.r[3 * i + j] = Xe[4 * j + i];
+                cx.x21.t[i] = Xe[12 + i];
+            }
+        }
+        cx.x12 = inverse(cx.x21);
+        cx.w_ang = mk<double>(0.0, 0.0, 0.0); cx.w_lin = cx.w_ang;
+        cx.chi = ins.chi; cx.Ebar1 = ins.Ebar1; cx.Ebar2 = ins.Ebar2; cx.n_quad = ins.n_quad;
+        const unsigned* in = pairs + (size_t)cap * ei;
+        unsigned* out = surv + (size_t)cap * ei;
+        int kept = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            unsigned e = 0;
+            bool keep = false;
+            if (i < n) { e = in[i]; keep = survives_f64(sc, ins, int((e >> 15) & 0x7fffu), int(e & 0x7fffu), cx); }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) out[kept + __popc(m & ((1u << lane) - 1u))] = e;
+            kept += __popc(m);
+        }
+        if (lane == 0) surv_n[ei] = kept;
+    }
+}
+
 __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualIO io, PairSource ps, unsigned* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DualTileSmem& sm = *reinterpret_cast<DualTileSmem*>(smem_raw);
@@ -92,13 +133,14 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
                     active = true;
                     const double* Xp = io.X7 + 112 * ei;
                     const double* tw = io.twist7 + 42 * ei;
-                    bool mine = false;   // is any input of this instruction seeded?  (lanes share the 18 x 6 partials)
+                    bool mine_x = false, mine_t = false;   // does the transform / the twist depend on the seeds?  (lanes share the 18 x 6 partials)
                     for (int e = lane; e < 18 * 6; e += 32) {
                         const int sc_i = e / 6, d = e - sc_i * 6;
                         const double* base = sc_i < 12 ? Xp + 7 * (sc_i < 9 ? (4 * (sc_i % 3) + sc_i / 3) : (12 + sc_i - 9)) : tw + 7 * (sc_i - 12);
-                        mine |= (base[1 + d] != 0.0);
+                        const bool nz = base[1 + d] != 0.0;
+                        if (sc_i < 12) mine_x |= nz; else mine_t |= nz;
                     }
-                    const bool seeded = __any_sync(0xffffffffu, mine);
+                    const int seeded = __any_sync(0xffffffffu, mine_x) ? 2 : (__any_sync(0xffffffffu, mine_t) ? 1 : 0);
                     if (lane < 3) {   // chunk `lane`'s context: partials 2 lane and 2 lane + 1
                         PatchCtx<D2>& cx = sm.cx[q][lane];
                         auto ld = [&](const double* p7) { D2 r; r.v = p7[0]; r.p[0] = p7[1 + 2 * lane]; r.p[1] = p7[2 + 2 * lane]; return r; };
@@ -124,14 +166,17 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
                         cxv.w_ang = mk<double>(c0.w_ang.x.v, c0.w_ang.y.v, c0.w_ang.z.v);
                         cxv.w_lin = mk<double>(c0.w_lin.x.v, c0.w_lin.y.v, c0.w_lin.z.v);
                         cxv.chi = c0.chi; cxv.Ebar1 = c0.Ebar1; cxv.Ebar2 = c0.Ebar2; cxv.n_quad = c0.n_quad;
-                        sm.ei[q] = ei; sm.er[q] = er; sm.ins[q] = k; sm.seeded[q] = seeded ? 1 : 0; sm.pflags[q] = 0;
-                        sm.pre[q + 1] = (int)io.n_pairs[er];   // turned into a prefix below
-                        sm.pl_s[q] = ins.small ? ps.small_pairs + (size_t)ps.small_cap * er : nullptr;
+                        sm.ei[q] = ei; sm.er[q] = er; sm.ins[q] = k; sm.seeded[q] = seeded; sm.pflags[q] = 0;
+                        const bool pf = ins.small && ps.surv_pairs;       // survivors of the Float64 clip are listed already
+                        const bool cp = seeded == 0 && ps.w_f64;          // nothing to differentiate and the values exist: copy them
+                        sm.prefiltered[q] = pf ? 1 : 0; sm.copied[q] = cp ? 1 : 0;
+                        sm.pre[q + 1] = cp ? 0 : (pf ? ps.surv_n[er] : (int)io.n_pairs[er]);   // turned into a prefix below
+                        sm.pl_s[q] = ins.small ? (pf ? ps.surv_pairs : ps.small_pairs) + (size_t)ps.small_cap * er : nullptr;
                         sm.pl_l[q] = ins.small ? nullptr : ps.large_sorted + ps.seg_start[env * ps.n_large + ps.large_index[k]];
                     }
                 }
             }
-            if (!active && lane == 0) { sm.ei[q] = -1; sm.er[q] = 0; sm.ins[q] = 0; sm.seeded[q] = 0; sm.pflags[q] = 0; sm.pre[q + 1] = 0; sm.pl_s[q] = nullptr; sm.pl_l[q] = nullptr; }
+            if (!active && lane == 0) { sm.ei[q] = -1; sm.er[q] = 0; sm.ins[q] = 0; sm.seeded[q] = 0; sm.pflags[q] = 0; sm.pre[q + 1] = 0; sm.pl_s[q] = nullptr; sm.pl_l[q] = nullptr; sm.prefiltered[q] = 0; sm.copied[q] = 0; }
             for (int j = lane; j <= kTotStride; j += 32) sm.tot[q][j] = 0.0;
         }
         __syncthreads();
@@ -153,7 +198,7 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
                 const int i = c - sm.pre[q];
                 if (sm.pl_s[q]) { const unsigned e = sm.pl_s[q][i]; a = int((e >> 15) & 0x7fffu); b = int(e & 0x7fffu); }
                 else { const int3 e = sm.pl_l[q][i]; a = e.y; b = e.z; }
-                keep = survives_f64(sc, sc.ins[sm.ins[q]], a, b, sm.cxv[q]);
+                keep = sm.prefiltered[q] ? true : survives_f64(sc, sc.ins[sm.ins[q]], a, b, sm.cxv[q]);
             }
             int n_surv;
             const int slot = block_scan_excl(keep ? 1 : 0, sm.warp_tot, n_surv);
@@ -163,7 +208,7 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
             if (n_surv == 0) continue;   // block-uniform
             // ---- 3a. items: 3 per survivor of a seeded problem, 1 otherwise
             int n_items;
-            const int mine_n = tid < n_surv ? (sm.seeded[sm.surv_q[tid]] ? 3 : 1) : 0;
+            const int mine_n = tid < n_surv ? (sm.seeded[sm.surv_q[tid]] == 2 ? 3 : 1) : 0;
             const int off = block_scan_excl(mine_n, sm.warp_tot, n_items);
             if (tid < n_surv) {
                 sm.item_off[tid] = off;
@@ -184,26 +229,50 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
                     const InsDev& ins = sc.ins[sm.ins[sq]];
                     double* res = sm.res + tid * kResStride;
                     int flags = 0, pts;
-                    if (sm.seeded[sq]) {
+                    if (sm.seeded[sq] == 2) {          // the transform carries partials: the whole pair on Dual<2>, this item's 2 partials
                         const PatchCtx<D2>& cx = sm.cx[sq][chunk];
                         Accum<D2, 6> acc;
                         acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
                         acc.reset(ACC_REGULARIZED);
                         integrate_pair(sc, ins, sm.surv_a[lo], sm.surv_b[lo], cx, acc, flags);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) { res[3 * j] = acc.a[j].v; res[3 * j + 1] = acc.a[j].p[0]; res[3 * j + 2] = acc.a[j].p[1]; }
+                        for (int j = 0; j < 6; ++j) { res[7 * j] = acc.a[j].v; res[7 * j + 1 + 2 * chunk] = acc.a[j].p[0]; res[7 * j + 2 + 2 * chunk] = acc.a[j].p[1]; }
                         pts = acc.n_points;
-                    } else {
+                    } else if (sm.seeded[sq] == 1) {   // only the twist does: Float64 polygon, the three chunks of partials one after another
+                        const PatchCtx<double>& cxv = sm.cxv[sq];
+                        PolyRec<double> pr;
+                        pts = 0;
+                        const bool hit = clip_pair(sc, ins, sm.surv_a[lo], sm.surv_b[lo], cxv, pr, flags);
+#pragma unroll 1
+                        for (int c3 = 0; c3 < 3; ++c3) {
+                            const PatchCtx<D2>& cx = sm.cx[sq][c3];
+                            TwistAcc<2> acc;
+                            acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.n_points = 0;
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) acc.a[j] = D2(0.0);
+                            if (hit) {
+                                Vec3<double> v2 = pr.v[pr.n - 1];
+                                for (int k = 0; k < pr.n; ++k) {
+                                    const Vec3<double> v1 = v2;
+                                    v2 = pr.v[k];
+                                    integrate_subtri_tw(v1, v2, pr.cen, pr.nrm, pr.eps_r, cxv.chi, cxv.Ebar2, cxv.n_quad, acc);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) { res[7 * j] = acc.a[j].v; res[7 * j + 1 + 2 * c3] = acc.a[j].p[0]; res[7 * j + 2 + 2 * c3] = acc.a[j].p[1]; }
+                            pts = acc.n_points;
+                        }
+                    } else {                            // nothing does: the Float64 evaluation
                         const PatchCtx<double>& cx = sm.cxv[sq];
                         Accum<double, 6> acc;
                         acc.fp = ins.p; acc.w_ang = cx.w_ang; acc.w_lin = cx.w_lin; acc.dump = nullptr; acc.dump_cap = 0;
                         acc.reset(ACC_REGULARIZED);
                         integrate_pair(sc, ins, sm.surv_a[lo], sm.surv_b[lo], cx, acc, flags);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) res[3 * j] = acc.a[j];
+                        for (int j = 0; j < 6; ++j) res[7 * j] = acc.a[j];
                         pts = acc.n_points;
                     }
-                    res[18] = (double)pts;
+                    res[42] = (double)pts;
                     if (flags) atomicOr(&sm.pflags[sq], flags);
                 }
                 __syncthreads();
@@ -213,18 +282,15 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
                     const int lo = sm.q_lo[oq], a_ = max(lo, i0), b_ = min(sm.q_hi[oq], i1);
                     if (a_ >= b_) continue;
                     double sum = sm.tot[oq][j];
-                    if (sm.seeded[oq]) {
-                        // item (survivor k, chunk c) sits at lo + 3 k + c; scalar j = 7 comp + which: which 0 = value (chunk 0), else partial which - 1
-                        const int comp = j / 7, which = j - 7 * comp;
-                        const int c_ = (j == 42 || which == 0) ? 0 : (which - 1) >> 1;
-                        const int col = j == 42 ? 18 : 3 * comp + (which == 0 ? 0 : 1 + ((which - 1) & 1));
-                        int first = a_ + ((c_ - (a_ - lo)) % 3 + 3) % 3;
-                        for (int it2 = first; it2 < b_; it2 += 3) sum += sm.res[(it2 - i0) * kResStride + col];
+                    const int which = j == 42 ? 0 : j % 7;
+                    if (sm.seeded[oq] == 2) {
+                        // item (survivor k, chunk c) sits at lo + 3 k + c; the value and the point count come from chunk 0, partial d from chunk d / 2
+                        const int c_ = which == 0 ? 0 : (which - 1) >> 1;
+                        const int first = a_ + ((c_ - (a_ - lo)) % 3 + 3) % 3;
+                        for (int it2 = first; it2 < b_; it2 += 3) sum += sm.res[(it2 - i0) * kResStride + j];
                     } else {
-                        const int comp = j / 7, which = j - 7 * comp;
-                        if (j != 42 && which != 0) continue;   // partials of an instruction that does not depend on the seeds: 0
-                        const int col = j == 42 ? 18 : 3 * comp;
-                        for (int it2 = a_; it2 < b_; ++it2) sum += sm.res[(it2 - i0) * kResStride + col];
+                        if (sm.seeded[oq] == 0 && which != 0) continue;   // partials of an instruction that does not depend on the seeds: 0
+                        for (int it2 = a_; it2 < b_; ++it2) sum += sm.res[(it2 - i0) * kResStride + j];
                     }
                     sm.tot[oq][j] = sum;
                 }
@@ -234,9 +300,11 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
         // ---- results: wrench (zero without contact), flags
         for (int o = tid; o < kDP * 42; o += kDT) {
             const int q = o / 42, j = o - 42 * q;
-            if (sm.ei[q] >= 0) io.wrench7[42 * sm.ei[q] + j] = sm.tot[q][42] > 0.0 ? sm.tot[q][j] : 0.0;
+            if (sm.ei[q] < 0) continue;
+            if (sm.copied[q]) io.wrench7[42 * sm.ei[q] + j] = (j % 7 == 0) ? ps.w_f64[6 * sm.er[q] + j / 7] : 0.0;   // (zero without contact already)
+            else io.wrench7[42 * sm.ei[q] + j] = sm.tot[q][42] > 0.0 ? sm.tot[q][j] : 0.0;
         }
-        if (tid < kDP && sm.ei[tid] >= 0) {
+        if (tid < kDP && sm.ei[tid] >= 0 && !sm.copied[tid]) {   // (a copied problem's contact flag was set by the Float64 evaluation)
             const int fl = sm.pflags[tid] | (sm.tot[tid][42] > 0.0 ? kFlagContact : 0);
             int* f = &io.flags[sm.er[tid]];
             if (io.n_real == io.n_env) *f = (*f & ~kFlagContact) | fl;
@@ -254,9 +322,10 @@ const int3* large_sorted_ptr(const LargeBuffers* b);
 
 cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double* X7, const double* twist7, const double* s7, double* wrench7, double* sdot7,
                               const long long* n_pairs, int* flags, const unsigned* small_pairs, int small_cap, const LargeBuffers* lb,
-                              const int32_t* large_index, int n_large, cudaStream_t stream, unsigned* ticket, long long n_real) {
+                              const int32_t* large_index, int n_large, cudaStream_t stream, unsigned* ticket, long long n_real, const DualShared* shared) {
     DualIO io{n_env, X7, twist7, s7, wrench7, sdot7, n_pairs, flags, n_real > 0 ? n_real : n_env};
-    PairSource ps{small_pairs, small_cap, lb ? large_sorted_ptr(lb) : nullptr, lb ? large_seg_start_ptr(lb) : nullptr, large_index, n_large};
+    PairSource ps{small_pairs, small_cap, lb ? large_sorted_ptr(lb) : nullptr, lb ? large_seg_start_ptr(lb) : nullptr, large_index, n_large,
+                  shared ? shared->surv_pairs : nullptr, shared ? shared->surv_n : nullptr, shared ? shared->w_f64 : nullptr};
     const long long n_prob = n_env * sc.n_ins;
     if (n_prob == 0) return cudaSuccess;
     struct DualTileTag {};
@@ -276,6 +345,18 @@ cudaError_t launch_eval_dual6(const SceneDev& sc, long long n_env, const double*
     err = cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream);   // the tile ticket of this launch (owned by the calling context)
     if (err != cudaSuccess) return err;
     eval_dual6_tile_kernel<<<blocks, kDT, sizeof(DualTileSmem), stream>>>(sc, io, ps, ticket);
+    return cudaGetLastError();
+}
+
+
+cudaError_t launch_dual_prefilter(const SceneDev& sc, long long n_env, const double* X, const long long* n_pairs, const unsigned* small_pairs, int small_cap,
+                                  unsigned* surv_pairs, int* surv_n, cudaStream_t stream) {
+    const long long n_prob = n_env * sc.n_ins;
+    if (n_prob == 0) return cudaSuccess;
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const unsigned blocks = (unsigned)std::min<long long>((n_prob + 3) / 4, (long long)n_sm * 8);
+    dual_prefilter_kernel<<<blocks, 128, 0, stream>>>(sc, n_env, X, n_pairs, small_pairs, small_cap, surv_pairs, surv_n);
     return cudaGetLastError();
 }
 
