@@ -31,6 +31,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda_pipeline_primitives.h>
+
 #include "pfc_exact.h"
 #include "pfc_large.h"
 #include "pfc_patch.cuh"
@@ -121,26 +123,49 @@ PFC_D void load_node(const NodeRec* __restrict__ p, NodeRec& out) {
     }
 }
 
-PFC_D int expand_pair(const SceneDev& sc, const InsDev& ins, const double* Rab, const double* tab, int ia, int ib, int2* ch) {
+// What a traversal thread needs to know about its problem, one 128 B record per (environment, large instruction), written once per
+// evaluation by init_frontier_kernel: the transform of frame a into frame b as the SAT wants it, the two trees' offsets in the node
+// array, whether the multi-GPU split applies.  A seed names its nodes by their GLOBAL index in the node array, so a thread can fetch
+// both node records straight after its seed -- side by side with the problem record instead of behind three dependent look-ups
+// (problem -> instruction -> node base / transform -> node).
+struct __align__(16) ProbRec { double Rab[9]; double tab[3]; int base1, base2, split, pad_; double pad2_; };
+static_assert(sizeof(ProbRec) == 128, "ProbRec is one 128 B line");
+
+// ga, gb: global node indices; children / leaf primitives in ch[] (children as global indices, primitives as mesh-local ids)
+PFC_D int expand_nodes(const NodeRec& a, const NodeRec& b, int base1, int base2, const double* Rab, const double* tab, int ga, int gb, int2* ch);
+PFC_D int expand_pair(const NodeRec* __restrict__ nodes, int base1, int base2, const double* Rab, const double* tab, int ga, int gb, int2* ch) {
     NodeRec a, b;
-    load_node(sc.nodes + ins.node_base1 + ia, a);
-    load_node(sc.nodes + ins.node_base2 + ib, b);
+    load_node(nodes + ga, a);
+    load_node(nodes + gb, b);
+    return expand_nodes(a, b, base1, base2, Rab, tab, ga, gb, ch);
+}
+PFC_D int expand_nodes(const NodeRec& a, const NodeRec& b, int base1, int base2, const double* Rab, const double* tab, int ga, int gb, int2* ch) {
     SatA A;
     sat_prepare_a(a, Rab, tab, A);
     if (!sat_test(A, b)) return 0;
-    const int al = ia + 1, ar = a.right, bl = ib + 1, br = b.right;   // pre-order: child 1 is the next record
     if (a.kind < 0) {
-        if (b.kind < 0) { ch[0] = make_int2(ar, br); return -1; }
-        ch[0] = make_int2(ia, bl); ch[1] = make_int2(ia, br); return 2;
+        if (b.kind < 0) { ch[0] = make_int2(a.right, b.right); return -1; }   // (a leaf's `right` is its primitive)
+        ch[0] = make_int2(ga, gb + 1); ch[1] = make_int2(ga, base2 + b.right); return 2;
     }
-    if (b.kind < 0) { ch[0] = make_int2(al, ib); ch[1] = make_int2(ar, ib); return 2; }
+    const int al = ga + 1, ar = base1 + a.right;   // pre-order: child 1 is the next record
+    if (b.kind < 0) { ch[0] = make_int2(al, gb); ch[1] = make_int2(ar, gb); return 2; }
+    const int bl = gb + 1, br = base2 + b.right;
     ch[0] = make_int2(al, bl); ch[1] = make_int2(ar, bl); ch[2] = make_int2(al, br); ch[3] = make_int2(ar, br);
     return 4;
 }
 
-__global__ void init_frontier_kernel(LargeScene ls, long long n_env, Seed* frontier, Counters* cnt) {
+__global__ void init_frontier_kernel(SceneDev sc, LargeScene ls, long long n_env, const double* __restrict__ X, Seed* frontier, ProbRec* ptab, Counters* cnt) {
     const long long n = n_env * ls.n_large;
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) frontier[p] = Seed{(int)p, 0u, 0, 0};
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        long long env; int k;
+        prob_to_ei(sc, ls, (int)p, env, k);
+        const InsDev& ins = sc.ins[k];
+        ProbRec r;
+        broad_xform_l(X + 16 * (env * sc.n_ins + k), r.Rab, r.tab);
+        r.base1 = ins.node_base1; r.base2 = ins.node_base2; r.split = ins.model != PFC_MODEL_BRISTLE ? 1 : 0; r.pad_ = 0; r.pad2_ = 0.0;
+        ptab[p] = r;
+        frontier[p] = Seed{(int)p, 0u, ins.node_base1, ins.node_base2};   // the two roots
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         cnt->epoch += 1;   // (on the device, so that a captured CUDA graph of the evaluation can be replayed)
         cnt->frontier_max = (unsigned)n; cnt->seed_head = 0; cnt->n_pairs = 0; cnt->overflow = 0; cnt->n_units = 0;
@@ -165,35 +190,36 @@ PFC_D unsigned item_hash(int prob, int a, int b) {
     return h;
 }
 
-__global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, const Seed* __restrict__ in, Seed* out,
+__global__ void __launch_bounds__(256, 2) broad_bfs_kernel(SceneDev sc, const ProbRec* __restrict__ ptab, const Seed* __restrict__ in, Seed* out,
                                                         int level, int split_level, unsigned cap_frontier, int3* pairs, unsigned cap_pairs, Counters* cnt,
                                                         unsigned hrank, unsigned hworld) {
     const unsigned n_raw = cnt->level_n[level];
     const unsigned n = n_raw < cap_frontier ? n_raw : cap_frontier;   // (an overflowing level is cut short; the host repeats the evaluation)
     if (n == 0) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // Multi-GPU split: up to split_level every rank expands the same frontier; AT split_level a rank keeps only the children (sub-trees)
     // whose hash falls on it; below, everything in its frontier is its own.  Leaf pairs found on the shared levels go to the rank their
     // own hash names.
     const bool shared = hworld > 1u && level <= split_level;
+    // Space in the next frontier and in the pair list is reserved once per CTA and iteration (block scan of the child / leaf counts, two
+    // atomics by one thread): a big level has ~150 k warps' worth of node pairs, and one atomic per warp on the same two counters made
+    // the level's duration the L2's same-address atomic rate (~2 per ns), not the tests.
+    __shared__ unsigned warp_child[8], warp_leaf[8], base_child, base_leaf;
     unsigned long long tests = 0;
-    for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
-        const unsigned i = base + lane;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {   // CTA-uniform trip count
+        const unsigned i = base + threadIdx.x;
         int r = 0;
         int2 ch[4];
         Seed s{};
         bool split = false;
         if (i < n) {
             s = in[i];
-            long long env; int k;
-            prob_to_ei(sc, ls, s.prob, env, k);
-            double Rab[9], tab[3];
-            broad_xform_l(X + 16 * (env * sc.n_ins + k), Rab, tab);
-            r = expand_pair(sc, sc.ins[k], Rab, tab, s.a, s.b, ch);
+            const ProbRec& pr = ptab[s.prob];
+            r = expand_pair(sc.nodes, pr.base1, pr.base2, pr.Rab, pr.tab, s.a, s.b, ch);
             ++tests;
-            split = shared && prob_is_split(sc, ls, s.prob);
+            split = shared && pr.split;
         }
-        // warp-aggregated appends
         int n_child = r > 0 ? r : 0;
         if (split && level == split_level) {   // keep this rank's sub-trees only
             int kept = 0;
@@ -201,22 +227,27 @@ __global__ void __launch_bounds__(256) broad_bfs_kernel(SceneDev sc, LargeScene 
                 if (item_hash(s.prob, ch[c].x, ch[c].y) % hworld == hrank) ch[kept++] = ch[c];
             n_child = kept;
         }
-        int incl = n_child;
+        const bool emit = r < 0 && (!split || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
+        // block scan of (children, leaf pairs): children in the low 16 bits of one word, leaves in the high 16
+        unsigned incl = (unsigned)n_child | (emit ? 0x10000u : 0u);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned at = 0;
-        if (lane == 31 && tot > 0) { at = atomicAdd(&cnt->level_n[level + 1], (unsigned)tot); atomicMax(&cnt->frontier_max, at + (unsigned)tot); }
-        at = __shfl_sync(0xffffffffu, at, 31) + incl - n_child;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) { warp_child[wib] = incl & 0xffffu; warp_leaf[wib] = incl >> 16; }
+        __syncthreads();
+        unsigned before_c = 0, before_l = 0, tot_c = 0, tot_l = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const unsigned c = warp_child[w], l = warp_leaf[w]; if (w < wib) { before_c += c; before_l += l; } tot_c += c; tot_l += l; }
+        if (threadIdx.x == 0) {
+            base_child = tot_c ? atomicAdd(&cnt->level_n[level + 1], tot_c) : 0u;
+            base_leaf = tot_l ? atomicAdd(&cnt->n_pairs, tot_l) : 0u;
+        }
+        __syncthreads();
+        const unsigned at = base_child + before_c + (incl & 0xffffu) - (unsigned)n_child;
         if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, 0u, ch[c].x, ch[c].y}; }
         else if (n_child > 0) atomicOr(&cnt->overflow, 1u);
-        const bool emit = r < 0 && (!split || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
-        const unsigned leaf_mask = __ballot_sync(0xffffffffu, emit);
-        if (leaf_mask) {
-            unsigned pat = 0;
-            if (lane == 0) pat = atomicAdd(&cnt->n_pairs, (unsigned)__popc(leaf_mask));
-            pat = __shfl_sync(0xffffffffu, pat, 0) + __popc(leaf_mask & ((1u << lane) - 1u));
-            if (emit) { if (pat < cap_pairs) pairs[pat] = make_int3(s.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u); }
+        if (emit) {
+            const unsigned pat = base_leaf + before_l + (incl >> 16) - 1u;
+            if (pat < cap_pairs) pairs[pat] = make_int3(s.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u);
         }
     }
 #pragma unroll
@@ -235,7 +266,7 @@ PFC_D unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<con
 
 // K1b: warp-cooperative stack-based traversal of the seeds, with work donation
 template <int MINB>
-__global__ void __launch_bounds__(kDfsWarps * 32, MINB) broad_dfs_kernel(SceneDev sc, LargeScene ls, const double* __restrict__ X, Seed* seeds, unsigned cap_seeds,
+__global__ void __launch_bounds__(kDfsWarps * 32, MINB) broad_dfs_kernel(SceneDev sc, const ProbRec* __restrict__ ptab, Seed* seeds, unsigned cap_seeds,
                                                                    int3* pairs, unsigned cap_pairs, Counters* cnt, unsigned hrank,
                                                                    unsigned hworld) {
     __shared__ int2 stack_mem[kDfsWarps][kStackCap];   // per-warp circular stack: entry i lives at (base + i) & (kStackCap - 1)
@@ -255,7 +286,7 @@ __global__ void __launch_bounds__(kDfsWarps * 32, MINB) broad_dfs_kernel(SceneDe
             const unsigned ticket = atomicAdd(&cnt->q_head, 1u);
             if (ticket < n_seed0) {
                 seed = seeds[ticket];
-                if (hworld > 1u && prob_is_split(sc, ls, seed.prob) && item_hash(seed.prob, seed.a, seed.b) % hworld != hrank) {   // another rank's sub-tree
+                if (hworld > 1u && ptab[seed.prob].split && item_hash(seed.prob, seed.a, seed.b) % hworld != hrank) {   // another rank's sub-tree
                     atomicSub(&cnt->outstanding, 1);
                     seed.prob = -2;
                 }
@@ -282,11 +313,16 @@ __global__ void __launch_bounds__(kDfsWarps * 32, MINB) broad_dfs_kernel(SceneDe
         seed.b = __shfl_sync(0xffffffffu, seed.b, 0);
         if (seed.prob == -2) continue;
         if (seed.prob < 0) break;
-        long long env; int k;
-        prob_to_ei(sc, ls, seed.prob, env, k);
-        const InsDev& ins = sc.ins[k];
         double Rab[9], tab[3];
-        broad_xform_l(X + 16 * (env * sc.n_ins + k), Rab, tab);
+        int base1, base2;
+        {
+            const ProbRec& pr = ptab[seed.prob];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rab[i] = pr.Rab[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tab[i] = pr.tab[i];
+            base1 = pr.base1; base2 = pr.base2;
+        }
         int n = 1;
         unsigned base = 0;
         if (lane == 0) stack[0] = make_int2(seed.a, seed.b);
@@ -304,7 +340,7 @@ __global__ void __launch_bounds__(kDfsWarps * 32, MINB) broad_dfs_kernel(SceneDe
             int2 ch[4];
             if (lane < take) {
                 const int2 e = stack[(base + n - 1 - lane) & (kStackCap - 1)];
-                r = expand_pair(sc, ins, Rab, tab, e.x, e.y, ch);
+                r = expand_pair(sc.nodes, base1, base2, Rab, tab, e.x, e.y, ch);
                 ++tests;
             }
             __syncwarp();
@@ -809,6 +845,7 @@ struct LargeBuffers {
     unsigned* hist = nullptr; size_t cap_hist = 0;
     unsigned* seg_start = nullptr; unsigned* seg_end = nullptr; unsigned* unit_start = nullptr; size_t cap_seg = 0, cap_seg2 = 0, cap_unit = 0;
     int* prob_flags = nullptr; size_t cap_pf = 0;
+    ProbRec* ptab = nullptr; size_t cap_ptab = 0;
     double* chunk_out = nullptr; size_t cap_chunk = 0;
     int* chunk_points = nullptr; size_t cap_cp = 0;
     double* part = nullptr; size_t cap_part = 0;
@@ -826,7 +863,7 @@ void large_buffers_destroy(LargeBuffers* b) {
     if (!b) return;
     cudaFree(b->cnt); cudaFree(b->frontier[0]); cudaFree(b->frontier[1]); cudaFree(b->pairs); cudaFree(b->sorted);
     cudaFree(b->keys[0]); cudaFree(b->keys[1]); cudaFree(b->vals[0]); cudaFree(b->vals[1]); cudaFree(b->hist);
-    cudaFree(b->seg_start); cudaFree(b->seg_end); cudaFree(b->unit_start); cudaFree(b->prob_flags);
+    cudaFree(b->seg_start); cudaFree(b->seg_end); cudaFree(b->unit_start); cudaFree(b->prob_flags); cudaFree(b->ptab);
     cudaFree(b->chunk_out); cudaFree(b->chunk_points); cudaFree(b->part);
     if (b->h_cnt) cudaFreeHost(b->h_cnt);
     delete b;
@@ -915,7 +952,10 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
         dfs_blocks_per_sm = sl.blocks;
         struct TagSort {};
         LaunchSlot& ss = launch_slot<TagSort>();
-        if (ss.key0 != 1) { LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12))); ss.key0 = 1; }
+        if (ss.key0 != 1) {
+            LCU(cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSort * 12)));
+            ss.key0 = 1;
+        }
     }
     const int dfs_blocks = n_sm * dfs_blocks_per_sm;
     // How the dual-tree recursion is walked.  Big scenes: LEVEL BY LEVEL to the leaves -- one launch per level of the recursion, one thread
@@ -949,24 +989,25 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     LCU(ensure(b->seg_end, b->cap_seg2, (size_t)n_prob + 1));
     LCU(ensure(b->unit_start, b->cap_unit, (size_t)n_prob + 2));
     LCU(ensure(b->prob_flags, b->cap_pf, (size_t)n_prob));
+    LCU(ensure(b->ptab, b->cap_ptab, (size_t)n_prob));
     // ---- traversal
-    init_frontier_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(ls, io.n_env, b->frontier[0], b->cnt);
+    init_frontier_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(sc, ls, io.n_env, io.X, b->frontier[0], b->ptab, b->cnt);
     int src = 0;
     for (int l = 0; l < levels; ++l) {
-        broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, ls, io.X, b->frontier[src], b->frontier[src ^ 1], l, split_level, (unsigned)b->cap_frontier, b->pairs,
+        broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, b->ptab, b->frontier[src], b->frontier[src ^ 1], l, split_level, (unsigned)b->cap_frontier, b->pairs,
                                                      (unsigned)b->cap_pairs, b->cnt, (unsigned)hash_rank, (unsigned)hash_world);
         src ^= 1;
     }
     // what the levels left (nothing, when they ran to the leaves) is traversed with per-warp stacks; the split has been made by then
     dfs_queue_init_kernel<<<1, 1, 0, stream>>>(b->cnt, levels, (unsigned)b->cap_frontier);
     if (dfs_minb == 4)
-        broad_dfs_kernel<4><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
+        broad_dfs_kernel<4><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, b->ptab, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
                                                                      b->cnt, 0u, 1u);
     else if (dfs_minb == 3)
-        broad_dfs_kernel<3><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
+        broad_dfs_kernel<3><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, b->ptab, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
                                                                      b->cnt, 0u, 1u);
     else
-        broad_dfs_kernel<1><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, ls, io.X, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
+        broad_dfs_kernel<1><<<dfs_blocks, kDfsWarps * 32, 0, stream>>>(sc, b->ptab, b->frontier[src], (unsigned)b->cap_frontier, b->pairs, (unsigned)b->cap_pairs,
                                                                      b->cnt, 0u, 1u);
     LCU(cudaMemcpyAsync(b->h_cnt, b->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, stream));   // read by large_check() after the caller's synchronisation
     b->check_pending = true;
@@ -1011,7 +1052,9 @@ int large_check(LargeBuffers* b) {
     bool again = false;
     if (h.overflow & 8u) { b->force_radix = true; b->radix_wanted = true; alloc_generation()++; again = true; }   // the list outgrew the one-CTA sort
     if (h.overflow & 1u) {
-        const size_t need = (size_t)std::max(h.frontier_max, h.q_tail) + 1024;   // (levels below an overflowing one were cut short: leave room)
+        unsigned level_max = h.frontier_max;   // the level counters kept counting past the capacity: the need of the levels that ran is known
+        for (int l = 0; l < kMaxLevels + 2; ++l) level_max = std::max(level_max, h.level_n[l]);
+        const size_t need = (size_t)std::max(level_max, h.q_tail) + 1024;   // (levels below an overflowing one were cut short: leave room)
         b->want_frontier = std::max<size_t>(b->cap_frontier * 2, need * 2);
         again = true;
     }
