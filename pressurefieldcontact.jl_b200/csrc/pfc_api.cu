@@ -896,7 +896,15 @@ int pfc_eval_sharded_begin(pfc_ctx* c, int64_t n_env, const double* X, const dou
     io.n_env = n_env; io.X = X; io.twist = twist; io.s = s; io.wrench = wrench; io.sdot = sdot;
     io.n_pairs = reinterpret_cast<long long*>(n_pairs); io.flags = flags;
     // one synchronisation at the end of what was queued: the traversal's and the bristle pipeline's buffers grow after the fact
-    return run_evaluation(c, eval_key(2, c, io), [&]() { return sharded_enqueue(c, io); });
+    const int rc = run_evaluation(c, eval_key(2, c, io), [&]() { return sharded_enqueue(c, io); });
+    if (rc != PFC_OK) return rc;
+    // host-side state of the evaluation in flight (a replayed CUDA graph does not pass through sharded_enqueue)
+    c->sharded_io = io;
+    c->sharded_stage = 0;
+    c->lists_n_env = -1;
+    if (c->keep_pairs) c->dbg_n_env = io.n_env;
+    c->last_X = io.X; c->last_tw = io.twist;
+    return PFC_OK;
 }
 
 int pfc_eval_sharded_partials(pfc_ctx* c, double** dev_ptr, int64_t* count) {

@@ -37,6 +37,9 @@ def test_group_eval_matches_single_gpu(scene):
     assert np.array_equal(a["n_pairs"], ref["n_pairs"]) and np.array_equal(a["flags"], ref["flags"])
     assert wrench_rel_err(a["wrench"], ref["wrench"], floor=1e-9 * np.abs(ref["wrench"]).max()) <= 1e-11
     assert a["wrench"].tobytes() == b["wrench"].tobytes()          # reproducible: fixed rank order of the sum
+    for _ in range(3):                                             # from the third identical call on the evaluation is a replayed CUDA graph
+        c = grp.eval_f64(X, tw, s_arr)
+        assert c["wrench"].tobytes() == a["wrench"].tobytes() and np.array_equal(c["n_pairs"], ref["n_pairs"])
     if nb:
         bristle = np.array([ci.friction_model.model == 1 for ci in m1.ContactInstructions])
         assert np.array_equal(a["wrench"][:, bristle], ref["wrench"][:, bristle])   # bristle instructions are not split: same bits
