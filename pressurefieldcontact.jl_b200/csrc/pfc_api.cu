@@ -180,7 +180,7 @@ struct pfc_ctx {
         bool seen = false;                          // the same evaluation ran eagerly once: everything it needs is allocated
         int launches = 0;
         bool disabled = false;
-    } graph;
+    } graph, graph_host;   // graph: one device-level evaluation of a many-kernel scene; graph_host: a whole host-pointer call of a small-path scene
     ncclComm_t comm = nullptr;   // library-owned communicator of a split scene (pfc_comm_init_rank / pfc_group_create)
     DevBuf<double> d_gather;     // [world][count]: the ranks' partial sums after the all-gather
     int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
@@ -296,6 +296,7 @@ int pfc_destroy(pfc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph.exec) { cudaGraphExecDestroy(c->graph.exec); c->graph.exec = nullptr; }
+    if (c->graph_host.exec) { cudaGraphExecDestroy(c->graph_host.exec); c->graph_host.exec = nullptr; }
     if (c->comm && nccl_api().ok()) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release(); c->d_small_heavy.release();
@@ -1284,8 +1285,8 @@ static cudaError_t status_begin(pfc_ctx* c) {
     if (!c->h_status) { e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_status), sizeof(int), cudaHostAllocDefault); if (e != cudaSuccess) return e; }
     return cudaMemsetAsync(c->d_status.p, 0, sizeof(int), c->stream);
 }
-static int status_end(pfc_ctx* c, int64_t n_env) {
-    CU(cudaMemcpyAsync(c->h_status, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+static int status_end(pfc_ctx* c, int64_t n_env, bool copy_status = true) {
+    if (copy_status) CU(cudaMemcpyAsync(c->h_status, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->lists_n_env = n_env; c->lists_np = c->d_np.p; c->lists_fl = c->d_fl.p;
     if (*c->h_status & PFC_FLAG_NONFINITE) return fail(PFC_E_NONFINITE, "Non-finite vertex likely");
@@ -1333,19 +1334,71 @@ int pfc_eval_state_f64(pfc_ctx* c, int64_t n_env, const double* x, double* f_gen
     const size_t ne = size_t(n_env), ni = size_t(c->scene.n_ins), nb = size_t(c->n_bristle), nx = size_t(c->state.n_x), nv = size_t(c->state.nv);
     CU(c->d_x.ensure(ne * nx)); CU(c->d_fgen.ensure(std::max<size_t>(ne * nv, 1))); CU(c->d_np.ensure(ne * ni)); CU(c->d_fl.ensure(ne * ni));
     if (nb) CU(c->d_sd.ensure(6 * ne * nb));
-    CU(status_begin(c));
-    CU(cudaMemsetAsync(c->d_fgen.p, 0, sizeof(double) * ne * nv, c->stream));
-    // (Splitting the batch in two and overlapping the copies of one half with the kernels of the other was measured on B200 and is
-    // slower -- 379 vs 325 us for 4096 environments: half-size grids no longer fill the GPU and the extra launches / events cost more
-    // than the ~50 us of copies they hide.)
-    CU(cudaMemcpyAsync(c->d_x.p, x, sizeof(double) * ne * nx, cudaMemcpyHostToDevice, c->stream));
-    int rc = eval_state_device(c, n_env, c->d_x.p, c->d_fgen.p, nb ? c->d_sd.p : nullptr, c->d_np.p, c->d_fl.p, c->d_status.p);
-    if (rc != PFC_OK) return rc;
-    CU(cudaMemcpyAsync(f_generalized, c->d_fgen.p, sizeof(double) * ne * nv, cudaMemcpyDeviceToHost, c->stream));
-    if (nb) CU(cudaMemcpyAsync(sdot, c->d_sd.p, sizeof(double) * 6 * ne * nb, cudaMemcpyDeviceToHost, c->stream));
-    if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
-    if (flags) CU(cudaMemcpyAsync(flags, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
-    return status_end(c, n_env);
+    // everything the call queues: status word, inputs in, kernels, outputs out (the caller synchronises in status_end)
+    auto enqueue = [&]() -> int {
+        CU(status_begin(c));
+        CU(cudaMemsetAsync(c->d_fgen.p, 0, sizeof(double) * ne * nv, c->stream));
+        // (Splitting the batch in two and overlapping the copies of one half with the kernels of the other was measured on B200 and is
+        // slower -- 379 vs 325 us for 4096 environments: half-size grids no longer fill the GPU and the extra launches / events cost more
+        // than the ~50 us of copies they hide.)
+        CU(cudaMemcpyAsync(c->d_x.p, x, sizeof(double) * ne * nx, cudaMemcpyHostToDevice, c->stream));
+        int rc = eval_state_device(c, n_env, c->d_x.p, c->d_fgen.p, nb ? c->d_sd.p : nullptr, c->d_np.p, c->d_fl.p, c->d_status.p);
+        if (rc != PFC_OK) return rc;
+        CU(cudaMemcpyAsync(f_generalized, c->d_fgen.p, sizeof(double) * ne * nv, cudaMemcpyDeviceToHost, c->stream));
+        if (nb) CU(cudaMemcpyAsync(sdot, c->d_sd.p, sizeof(double) * 6 * ne * nb, cudaMemcpyDeviceToHost, c->stream));
+        if (n_pairs) CU(cudaMemcpyAsync(n_pairs, c->d_np.p, sizeof(long long) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+        if (flags) CU(cudaMemcpyAsync(flags, c->d_fl.p, sizeof(int32_t) * ne * ni, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_status, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        return PFC_OK;
+    };
+    // A small-path scene queues nine short operations per call; launched one by one the GPU waits for the host between them (the
+    // copies and kernels of a 512-environment batch last 3-30 us each).  When the same call -- same batch size, same caller buffers,
+    // nothing reallocated since -- comes again, its operations are captured into a CUDA graph and replayed with one launch.  (Pageable
+    // caller buffers cannot be captured: the capture fails once and the context stays with plain launches.)
+    pfc_ctx::GraphCache& g = c->graph_host;
+    static const bool host_graph_off = getenv("PFC_NO_HOST_GRAPH") != nullptr;   // (experiment switch)
+    const bool graphable = !host_graph_off && !g.disabled && !c->timing && !c->keep_pairs && !c->large_buf && !c->exact_buf && c->n_mid == 0;
+    bool done = false;
+    if (graphable) {
+        unsigned long long key = 1469598103934665603ull;
+        auto mix = [&](unsigned long long v) { key ^= v; key *= 1099511628211ull; };
+        mix(5ull); mix((unsigned long long)n_env); mix((unsigned long long)(uintptr_t)x); mix((unsigned long long)(uintptr_t)f_generalized);
+        mix((unsigned long long)(uintptr_t)sdot); mix((unsigned long long)(uintptr_t)n_pairs); mix((unsigned long long)(uintptr_t)flags);
+        const unsigned long long gen = alloc_generation().load();
+        if (g.key == key && g.gen == gen) {
+            if (g.exec) {
+                if (cudaGraphLaunch(g.exec, c->stream) == cudaSuccess) { done = true; c->launches += g.launches; }
+                else { cudaGetLastError(); cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.disabled = true; }
+            } else if (g.seen) {
+                cudaGraph_t graph = nullptr;
+                const long long l0 = c->launches;
+                if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int rc = enqueue();
+                    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+                    if (rc == PFC_OK && e == cudaSuccess && graph && alloc_generation().load() == gen &&
+                        cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess && cudaGraphLaunch(g.exec, c->stream) == cudaSuccess) {
+                        g.launches = int(c->launches - l0);
+                        done = true;
+                    } else {
+                        cudaGetLastError();
+                        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+                        g.disabled = true;
+                        c->launches = l0;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                } else { cudaGetLastError(); g.disabled = true; }
+            }
+        }
+        if (!done) {
+            const int rc = enqueue();
+            if (rc != PFC_OK) return rc;
+            done = true;
+            if (g.exec && (g.key != key || g.gen != alloc_generation().load())) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            g.key = key; g.gen = alloc_generation().load(); g.seen = true;   // everything this call needs is allocated now: the next identical one is captured
+        }
+    }
+    if (!done) { const int rc = enqueue(); if (rc != PFC_OK) return rc; }
+    return status_end(c, n_env, false);
 }
 
 // inverse of a symmetric positive definite 6x6 by Cholesky (what the reference does per evaluation with cholesky!/ldiv!)
