@@ -180,7 +180,7 @@ struct pfc_ctx {
         bool seen = false;                          // the same evaluation ran eagerly once: everything it needs is allocated
         int launches = 0;
         bool disabled = false;
-    } graph, graph_host;   // graph: one device-level evaluation of a many-kernel scene; graph_host: a whole host-pointer call of a small-path scene
+    } graph, graph_host, graph_pack;   // graph: one device-level evaluation of a many-kernel scene; graph_host: a whole host-pointer call of a small-path scene
     ncclComm_t comm = nullptr;   // library-owned communicator of a split scene (pfc_comm_init_rank / pfc_group_create)
     DevBuf<double> d_gather;     // [world][count]: the ranks' partial sums after the all-gather
     int sharded_stage = -1;   // >= 0 while a sharded evaluation is in flight
@@ -297,6 +297,7 @@ int pfc_destroy(pfc_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph.exec) { cudaGraphExecDestroy(c->graph.exec); c->graph.exec = nullptr; }
     if (c->graph_host.exec) { cudaGraphExecDestroy(c->graph_host.exec); c->graph_host.exec = nullptr; }
+    if (c->graph_pack.exec) { cudaGraphExecDestroy(c->graph_pack.exec); c->graph_pack.exec = nullptr; }
     if (c->comm && nccl_api().ok()) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tets.release(); c->d_tris.release(); c->d_ins.release(); c->d_small.release(); c->d_small_heavy.release();
@@ -746,6 +747,45 @@ static int eval_device(pfc_ctx* c, const EvalIO& io) {
     return run_evaluation(c, eval_key(1, c, io), [&]() { return eval_device_once(c, io); });
 }
 
+// A small-path scene queues a handful of short operations per host-pointer call (copies in, two to four kernels, copies out); launched
+// one by one the GPU waits for the host between them (the copies and kernels of a 512-environment batch last 3-30 us each).  When the same
+// call -- same batch size, same buffers, nothing reallocated since -- comes again, its operations are captured into a CUDA graph and
+// replayed with one launch.  (Pageable caller buffers cannot be captured: the capture fails once and the context stays with plain
+// launches.)  Scenes with large / mid-size / bristle instructions are left to run_evaluation: their evaluations synchronise to check
+// buffer sizes.  enqueue() queues the whole call on c->stream (no synchronisation) and returns PFC_OK.
+static int run_host_call(pfc_ctx* c, pfc_ctx::GraphCache& g, unsigned long long key, const std::function<int()>& enqueue) {
+    static const bool host_graph_off = getenv("PFC_NO_HOST_GRAPH") != nullptr;   // (experiment switch)
+    const bool graphable = !host_graph_off && !g.disabled && !c->timing && !c->keep_pairs && !c->large_buf && !c->exact_buf && c->n_mid == 0;
+    if (!graphable) return enqueue();
+    const unsigned long long gen = alloc_generation().load();
+    if (g.key == key && g.gen == gen) {
+        if (g.exec) {
+            if (cudaGraphLaunch(g.exec, c->stream) == cudaSuccess) { c->launches += g.launches; return PFC_OK; }
+            cudaGetLastError(); cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.disabled = true;
+        } else if (g.seen) {
+            cudaGraph_t graph = nullptr;
+            const long long l0 = c->launches;
+            if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = enqueue();
+                const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+                bool ok = rc == PFC_OK && e == cudaSuccess && graph && alloc_generation().load() == gen && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess &&
+                          cudaGraphLaunch(g.exec, c->stream) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) { g.launches = int(c->launches - l0); return PFC_OK; }
+                cudaGetLastError();
+                if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+                g.disabled = true;
+                c->launches = l0;
+            } else { cudaGetLastError(); g.disabled = true; }
+        }
+    }
+    const int rc = enqueue();
+    if (rc != PFC_OK) return rc;
+    if (g.exec && (g.key != key || g.gen != alloc_generation().load())) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    g.key = key; g.gen = alloc_generation().load(); g.seen = true;   // everything this call needs is allocated now: the next identical one is captured
+    return PFC_OK;
+}
+
 // ---- small host-pointer calls: copies through a pinned arena ----------------------------------------------------------------
 constexpr size_t kArenaBytes = 256 << 10;
 static void arena_reset(pfc_ctx* c) {
@@ -816,14 +856,22 @@ int pfc_eval_f64(pfc_ctx* c, int64_t n_env, const double* X, const double* twist
         CU(c->d_pack_in.ensure(bX + bT + bS)); CU(c->d_pack_out.ensure(bW + bD + bN + bF));
         std::memcpy(h_in, X, bX); std::memcpy(h_in + bX, twist, bT);
         if (nb) std::memcpy(h_in + bX + bT, s, bS);
-        CU(cudaMemcpyAsync(c->d_pack_in.p, h_in, bX + bT + bS, cudaMemcpyHostToDevice, c->stream));
         unsigned char* di = c->d_pack_in.p; unsigned char* dn = c->d_pack_out.p;
         io.X = reinterpret_cast<const double*>(di); io.twist = reinterpret_cast<const double*>(di + bX); io.s = nb ? reinterpret_cast<const double*>(di + bX + bT) : nullptr;
         io.wrench = reinterpret_cast<double*>(dn); io.sdot = nb ? reinterpret_cast<double*>(dn + bW) : nullptr;
         io.n_pairs = reinterpret_cast<long long*>(dn + bW + bD); io.flags = reinterpret_cast<int*>(dn + bW + bD + bN);
-        int rc = eval_device(c, io);
-        if (rc != PFC_OK) return rc;
-        CU(cudaMemcpyAsync(h_out, dn, bW + bD + bN + bF, cudaMemcpyDeviceToHost, c->stream));
+        auto enqueue = [&]() -> int {
+            CU(cudaMemcpyAsync(c->d_pack_in.p, h_in, bX + bT + bS, cudaMemcpyHostToDevice, c->stream));
+            const int rc = eval_device(c, io);
+            if (rc != PFC_OK) return rc;
+            CU(cudaMemcpyAsync(h_out, dn, bW + bD + bN + bF, cudaMemcpyDeviceToHost, c->stream));
+            return PFC_OK;
+        };
+        unsigned long long key = 1469598103934665603ull;
+        auto mix = [&](unsigned long long v) { key ^= v; key *= 1099511628211ull; };
+        mix(6ull); mix((unsigned long long)n_env); mix((unsigned long long)(uintptr_t)h_in); mix((unsigned long long)(uintptr_t)h_out);
+        mix((unsigned long long)(uintptr_t)di); mix((unsigned long long)(uintptr_t)dn);
+        { const int rc = run_host_call(c, c->graph_pack, key, enqueue); if (rc != PFC_OK) return rc; }
         CU(cudaStreamSynchronize(c->stream));
         std::memcpy(wrench, h_out, bW);
         if (nb) std::memcpy(sdot, h_out + bW, bD);
@@ -1351,53 +1399,11 @@ int pfc_eval_state_f64(pfc_ctx* c, int64_t n_env, const double* x, double* f_gen
         CU(cudaMemcpyAsync(c->h_status, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         return PFC_OK;
     };
-    // A small-path scene queues nine short operations per call; launched one by one the GPU waits for the host between them (the
-    // copies and kernels of a 512-environment batch last 3-30 us each).  When the same call -- same batch size, same caller buffers,
-    // nothing reallocated since -- comes again, its operations are captured into a CUDA graph and replayed with one launch.  (Pageable
-    // caller buffers cannot be captured: the capture fails once and the context stays with plain launches.)
-    pfc_ctx::GraphCache& g = c->graph_host;
-    static const bool host_graph_off = getenv("PFC_NO_HOST_GRAPH") != nullptr;   // (experiment switch)
-    const bool graphable = !host_graph_off && !g.disabled && !c->timing && !c->keep_pairs && !c->large_buf && !c->exact_buf && c->n_mid == 0;
-    bool done = false;
-    if (graphable) {
-        unsigned long long key = 1469598103934665603ull;
-        auto mix = [&](unsigned long long v) { key ^= v; key *= 1099511628211ull; };
-        mix(5ull); mix((unsigned long long)n_env); mix((unsigned long long)(uintptr_t)x); mix((unsigned long long)(uintptr_t)f_generalized);
-        mix((unsigned long long)(uintptr_t)sdot); mix((unsigned long long)(uintptr_t)n_pairs); mix((unsigned long long)(uintptr_t)flags);
-        const unsigned long long gen = alloc_generation().load();
-        if (g.key == key && g.gen == gen) {
-            if (g.exec) {
-                if (cudaGraphLaunch(g.exec, c->stream) == cudaSuccess) { done = true; c->launches += g.launches; }
-                else { cudaGetLastError(); cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.disabled = true; }
-            } else if (g.seen) {
-                cudaGraph_t graph = nullptr;
-                const long long l0 = c->launches;
-                if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                    const int rc = enqueue();
-                    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-                    if (rc == PFC_OK && e == cudaSuccess && graph && alloc_generation().load() == gen &&
-                        cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess && cudaGraphLaunch(g.exec, c->stream) == cudaSuccess) {
-                        g.launches = int(c->launches - l0);
-                        done = true;
-                    } else {
-                        cudaGetLastError();
-                        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-                        g.disabled = true;
-                        c->launches = l0;
-                    }
-                    if (graph) cudaGraphDestroy(graph);
-                } else { cudaGetLastError(); g.disabled = true; }
-            }
-        }
-        if (!done) {
-            const int rc = enqueue();
-            if (rc != PFC_OK) return rc;
-            done = true;
-            if (g.exec && (g.key != key || g.gen != alloc_generation().load())) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-            g.key = key; g.gen = alloc_generation().load(); g.seen = true;   // everything this call needs is allocated now: the next identical one is captured
-        }
-    }
-    if (!done) { const int rc = enqueue(); if (rc != PFC_OK) return rc; }
+    unsigned long long key = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { key ^= v; key *= 1099511628211ull; };
+    mix(5ull); mix((unsigned long long)n_env); mix((unsigned long long)(uintptr_t)x); mix((unsigned long long)(uintptr_t)f_generalized);
+    mix((unsigned long long)(uintptr_t)sdot); mix((unsigned long long)(uintptr_t)n_pairs); mix((unsigned long long)(uintptr_t)flags);
+    { const int rc = run_host_call(c, c->graph_host, key, enqueue); if (rc != PFC_OK) return rc; }
     return status_end(c, n_env, false);
 }
 
