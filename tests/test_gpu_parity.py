@@ -531,6 +531,29 @@ def test_state_entry_point_boxes_batch():
     assert np.array_equal(g["wrench"], w_d)
 
 
+def test_state_entry_point_replayed_graph_follows_the_inputs():
+    """From its third identical invocation (same batch size, same pinned caller buffers) pfc_eval_state_f64 is a replayed CUDA graph:
+    the results must follow the CONTENT of the buffers, call after call, and equal what a fresh context computes from the same states."""
+    import torch
+    n_env = 64
+    m_gpu = scene_boxes(_ctx(), max_env=n_env)[0]
+    m_ref = scene_boxes(_ctx(), max_env=n_env)[0]
+    nx = S.num_x(m_gpu)
+    x_p = torch.zeros((n_env, nx), dtype=torch.float64).pin_memory()
+    f_p = torch.zeros((n_env, m_gpu.nv), dtype=torch.float64).pin_memory()
+    np_p = torch.zeros((n_env, 4), dtype=torch.int64).pin_memory()
+    fl_p = torch.zeros((n_env, 4), dtype=torch.int32).pin_memory()
+    for it in range(6):
+        x = boxes_env_states(m_gpu, n_env, start=1000 * it)     # other states every call, same buffers
+        x_p.copy_(torch.from_numpy(x))
+        f_p.fill_(float("nan"))
+        m_gpu.backend.eval_state_f64_ptr(n_env, x_p.data_ptr(), f_p.data_ptr(), None, np_p.data_ptr(), fl_p.data_ptr())
+        want = S.force_all_elastic_intersections_batch(m_ref, x)   # numpy path: new buffers every call, never a graph
+        assert np.array_equal(f_p.numpy(), want["f_generalized"]), it
+        assert np.array_equal(np_p.numpy(), want["n_pairs"]) and np.array_equal(fl_p.numpy(), want["flags"])
+    assert (fl_p.numpy() & 1).any()
+
+
 def test_state_entry_point_bristle_and_rejects_chains():
     """Bristle states ride along in x (s-dot comes back); scenes with revolute / prismatic chains are refused."""
     n_env = 32
