@@ -292,14 +292,17 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
 //      clip starts again at the first candidate left out (rare);
 //   3. a block scan over the vertex counts turns the polygons into a dense (slot, edge) work list, dealt one sub-triangle
 //      per thread for quadrature + friction; every item leaves its 6 sums (+ point count) in shared memory;
-//   4. one warp per problem adds its problem's items IN ITEM ORDER (= the reference's order of candidate pairs and polygon
-//      edges; lane-strided partials + xor-butterfly): bitwise reproducible, no atomics, no per-thread accumulators to carry.
+//   4. the items are ordered by problem, so a warp's 32 items belong to one to three problems: per problem a masked xor-butterfly
+//      over the warp into the warp's running sums, added in warp order at the end of the tile: a fixed item -> lane assignment and
+//      a fixed tree, bitwise reproducible, no atomics, no per-item results in shared memory, no barrier between the rounds.
 // Measured and rejected: one WARP per tile (32 slots per warp, __syncwarp only, per-lane register accumulators flushed by a
 // butterfly per problem) -- no barrier waits, but the sub-triangles of a 32-slot round split into per-problem segments that
 // fill 6 of 10 lanes: 196 us against 146 us for this kernel.  Fetching the next tile's boundary data (x_r2_r1, twist, pair count)
 // into registers one tile ahead: no change (145 us) -- the other three CTAs of the SM already cover that DRAM round trip.  Tiles of
 // 8 problems on 256 threads (2 CTAs per SM): 152 us against 141 us -- a barrier then waits for the slowest of 256 clips.
-// 3 CTAs per SM at 168 registers (no spills, 12 warps instead of 16): 151 us.
+// 3 CTAs per SM at 168 registers (no spills, 12 warps instead of 16): 151 us.  5 CTAs per SM (96 registers, 360 B of spills; possible
+// since the per-item results left shared memory: 41 KB per CTA): 152 us against 135 us -- the kernel wants its 128 registers more than
+// a fifth CTA.
 constexpr int kPolyStride = 35;    // doubles per PolyRec slot
 static_assert(sizeof(PolyRec<double>) == kPolyStride * sizeof(double), "PolyRec<double> is 35 doubles");
 constexpr int kItemCap = 256;      // sub-triangles per summation round
@@ -308,13 +311,12 @@ constexpr int kItemStride = 7;     // 6 sums + point count, odd stride
 template <int P> struct TileSmem {   // P problems, P warps
     static constexpr int kThreads = 32 * P;
     double poly[kThreads * kPolyStride];   // PolyRec per thread
-    double item_res[kItemCap * kItemStride];
     PatchCtx<double> cx[P];
     long long ei[P];
     const double* fp[P];
     int ins[P];
     int n_cand[P];
-    double tot[P][8];
+    double wtot[P][P][8];   // [warp][problem]: running sums of the warp's items of the problem (6 sums + point count)
     int warp_tot[P];
     int pflags[P];
     unsigned short items[kThreads * 8];
@@ -323,11 +325,10 @@ template <int P> struct TileSmem {   // P problems, P warps
     unsigned slot_pair[kThreads];
     unsigned char slot_n[kThreads];
     int resume_c;
-    int q_lo[P], q_hi[P];   // item range of each problem in the current round
     long long next_tile;    // drawn from the ticket counter by thread 0
     double fpv[P][8];
 };
-static_assert(sizeof(TileSmem<4>) <= 56 * 1024, "4 CTAs per SM need <= 56 KB each");
+static_assert(sizeof(TileSmem<4>) <= 45 * 1024, "5 CTAs per SM need <= 45 KB each");
 
 template <int P, int MINB>
 __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, EvalIO io, int cap, const unsigned* __restrict__ pairs_in, unsigned* __restrict__ ticket) {
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
 #pragma unroll
         for (int q = 0; q < P; ++q) pre[q + 1] = pre[q] + sm.n_cand[q];
         const int n_cand = pre[P];
-        if (lane < 8) sm.tot[wib][lane] = 0.0;   // running totals of problem wib: 6 sums + point count (warp-private)
+        for (int j = lane; j < P * 8; j += 32) sm.wtot[wib][j >> 3][j & 7] = 0.0;   // this warp's running sums (warp-private)
         int filled = 0;          // occupied polygon slots (block-uniform)
         int c0 = 0;              // first candidate of the next round (block-uniform)
         while (true) {
@@ -431,71 +432,64 @@ __global__ void __launch_bounds__(32 * P, MINB) narrow_tile_kernel(SceneDev sc, 
             int incl = nv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (lane == 31) { sm.warp_tot[wib] = incl; sm.q_lo[wib] = 0; sm.q_hi[wib] = 0; }   // (a problem without slots sums nothing)
+            if (lane == 31) sm.warp_tot[wib] = incl;
             __syncthreads();
             int before = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < P; ++w) { const int t = sm.warp_tot[w]; if (w < wib) before += t; total += t; }
             const int at = before + incl - nv;
             for (int k = 0; k < nv; ++k) sm.items[at + k] = (unsigned short)((tid << 3) | k);
-            if (tid < batch_n) {
-                const int q = sm.poly_prob[tid];
-                if (tid == 0 || (int)sm.poly_prob[tid - 1] != q) sm.q_lo[q] = at;
-                if (tid == batch_n - 1 || (int)sm.poly_prob[tid + 1] != q) sm.q_hi[q] = at + nv;
-            }
             __syncthreads();
-            // this summing warp's item range (items are sorted by problem): left by the first / last slot of its problem
-            const int my_lo = sm.q_lo[sum_q], my_hi = sm.q_hi[sum_q];
-            for (int i0 = 0; i0 < total; i0 += kItemCap) {
-                // ---- 3b. one sub-triangle per thread
-                const int i1 = min(total, i0 + kItemCap);
-                for (int it = i0 + tid; it < i1; it += kTileThreads) {
+            // ---- 3b. one sub-triangle per thread; 4. sums: the items are ordered by problem, so a warp's 32 items belong to one to three
+            // problems: per problem a masked xor-butterfly over the warp, lane j keeps sum j and adds it to the warp's running sum of that
+            // problem (fixed item -> lane assignment, fixed tree: bitwise reproducible; no per-item results in shared memory, no barrier)
+            for (int i0 = 0; i0 < total; i0 += kTileThreads) {
+                const int it = i0 + tid;
+                double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                int npts = 0, q = -1;
+                if (it < total) {
                     const int code = sm.items[it];
                     const int slot = code >> 3, k = code & 7;
                     const PolyRec<double>& pr = *reinterpret_cast<const PolyRec<double>*>(sm.poly + slot * kPolyStride);
-                    const int q = sm.poly_prob[slot];
+                    q = sm.poly_prob[slot];
                     const PatchCtx<double>& cx = sm.cx[q];
                     Accum<double, 6> tmp;
                     tmp.fp = sm.fpv[q]; tmp.w_ang = cx.w_ang; tmp.w_lin = cx.w_lin; tmp.dump = nullptr; tmp.dump_cap = 0;
                     tmp.reset(ACC_REGULARIZED);
                     const int kp = (k == 0) ? pr.n - 1 : k - 1;
                     integrate_subtri(pr.v[kp], pr.v[k], pr.cen, pr.nrm, pr.eps_r, cx, tmp);
-                    double* res = sm.item_res + (it - i0) * kItemStride;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) res[j] = tmp.a[j];
-                    reinterpret_cast<int*>(res + 6)[0] = tmp.n_points;
+                    for (int j = 0; j < 6; ++j) a6[j] = tmp.a[j];
+                    npts = tmp.n_points;
                 }
-                __syncthreads();
-                // ---- 4. fixed-order sums: lane l adds items a + l, a + l + 32, ... of its warp's problem, then a xor-butterfly
-                {
-                    const int a = max(my_lo, i0), b = min(my_hi, i1);
-                    if (a < b) {   // warp-uniform
-                        double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                        int part_n = 0;
-                        for (int it = a + lane; it < b; it += 32) {
-                            const double* res = sm.item_res + (it - i0) * kItemStride;
+                const unsigned act = __ballot_sync(0xffffffffu, it < total);
+                if (act) {   // warp-uniform
+                    const int q_first = __shfl_sync(0xffffffffu, q, __ffs(act) - 1), q_last = __shfl_sync(0xffffffffu, q, 31 - __clz(act));
+                    for (int qq = q_first; qq <= q_last; ++qq) {
+                        const bool mine_q = q == qq;
+                        double mine = (double)warp_sum_int(mine_q ? npts : 0);   // lane 6 keeps the point count
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) part[j] += res[j];
-                            part_n += reinterpret_cast<const int*>(res + 6)[0];
-                        }
-                        double mine = (double)warp_sum_int(part_n);   // lane 6 keeps the point count
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) { const double t = warp_sum(part[j]); mine = (lane == j) ? t : mine; }
-                        if (lane < 7) sm.tot[sum_q][lane] += mine;
+                        for (int j = 0; j < 6; ++j) { const double t = warp_sum(mine_q ? a6[j] : 0.0); mine = (lane == j) ? t : mine; }
+                        if (lane < 7) sm.wtot[wib][qq][lane] += mine;
                     }
                 }
-                __syncthreads();   // item_res (and, after the last round, the polygon slots) are reused
             }
+            __syncthreads();   // the polygon slots are reused by the next round
             filled = 0;   // (with total == 0 the two barriers of 3a already separate the clip from the next round's slot writes)
             if (last) break;
         }
-        // ---- results: wrench (zero without contact), flags
+        // ---- results: the warps' running sums of problem sum_q added in warp order; wrench (zero without contact), flags
+        __syncthreads();   // every warp's running sums are final (a tile without candidates comes here straight from the zeroing)
         {
             const long long ei = sm.ei[sum_q];
             if (ei >= 0) {
-                __syncwarp();
-                const bool contact = sm.tot[sum_q][6] > 0.0;
-                if (lane < 6) io.wrench[6 * ei + lane] = contact ? sm.tot[sum_q][lane] : 0.0;
+                double t = 0.0;
+                if (lane < 7) {
+#pragma unroll
+                    for (int w = 0; w < P; ++w) t += sm.wtot[w][sum_q][lane];
+                }
+                const bool contact = __shfl_sync(0xffffffffu, t, 6) > 0.0;
+                if (lane < 6) io.wrench[6 * ei + lane] = contact ? t : 0.0;
                 if (lane == 6) io.flags[ei] |= sm.pflags[sum_q] | (contact ? kFlagContact : 0);
             }
         }
@@ -625,7 +619,10 @@ cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_
         static const int tile_p = getenv("PFC_TILE_P") ? atoi(getenv("PFC_TILE_P")) : 4;   // (experiment switch)
         if (tile_p == 1) e = launch_narrow_tile<1, 16>(sc, io, cap, pairs, stream);
         else if (tile_p == 2) e = launch_narrow_tile<2, 8>(sc, io, cap, pairs, stream);
-        else e = launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
+        else {
+            static const int minb = getenv("PFC_TILE_MINB") ? atoi(getenv("PFC_TILE_MINB")) : 4;   // (experiment switch)
+            e = minb == 5 ? launch_narrow_tile<4, 5>(sc, io, cap, pairs, stream) : launch_narrow_tile<4, 4>(sc, io, cap, pairs, stream);
+        }
     }
     if (ev) cudaEventRecord(ev[2], stream);
     if (n_launches) *n_launches += 2;
