@@ -971,7 +971,8 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     { double f = (double)n_prob; const double target = 1.0 * dfs_blocks * kDfsWarps; while (f < target && levels < 12) { f *= 4.0; ++levels; } }
     // split over several GPUs: a contact patch is small against the meshes, so a few sub-trees carry nearly all of the work; three more
     // breadth-first levels make the hash-partitioned pieces ~64x finer, which is what balances the ranks
-    if (hash_world > 1) levels = std::min(levels + 3, 14);
+    static const int split_extra = getenv("PFC_SPLIT_EXTRA") ? atoi(getenv("PFC_SPLIT_EXTRA")) : 3;   // (experiment switch)
+    if (hash_world > 1) levels = std::min(levels + split_extra, 16);
     const int split_level = levels - 1;             // the level whose children are dealt to the ranks by hash
     // (a level descends both trees until one of them is at a leaf, then the other alone: a leaf pair at depths (d1, d2) is reached at
     // level max(d1, d2), so max_depth + 1 levels test every pair of the recursion)
