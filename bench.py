@@ -504,6 +504,34 @@ def main():
                    "as_chunk_calls_ms": times["chunk_calls"] * 1e3}
     except Exception as exc:
         jac = {"error": repr(exc)}
+    # secondary: the reference's own call pattern -- ONE test/boxes.jl scene per call (Radau on a single scene calls
+    # forceAllElasticIntersections! once per stage evaluation): latency of pfc_eval_f64 with pageable host arrays, beside the CPU port
+    latency = None
+    try:
+        if world == 1:
+            from helpers import boxes_env_states as _bes, scene_boxes as _sb
+            from pfc_b200 import scenario as _S
+            lat_ctx = capi.Context(local_rank)
+            m1 = _sb(lat_ctx)[0]
+            X1, tw1, _ = _S.boundary_arrays(m1, _bes(m1, 1)[0])
+            lat_ctx.eval_f64(X1, tw1, None)
+            reps = 300
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                lat_ctx.eval_f64(X1, tw1, None)
+            gpu_us = (time.perf_counter() - t0) / reps * 1e6
+            o1 = orc.OracleContext(n_threads=1)
+            m1c = _sb(o1)[0]
+            o1.eval_f64(X1, tw1, None)
+            t0 = time.perf_counter()
+            for _ in range(50):
+                o1.eval_f64(X1, tw1, None)
+            cpu_us = (time.perf_counter() - t0) / 50 * 1e6
+            latency = {"workload": "C1: one test/boxes.jl scene (settled stack) per call", "us_per_call": gpu_us, "api": "pfc_eval_f64 (host arrays, synchronous; through ctypes)",
+                       "cpu_port_us_per_call": cpu_us, "cpu_port": "C++ port of the Julia reference, 1 thread"}
+            del m1c
+    except Exception as exc:
+        latency = {"error": repr(exc)}
     # secondary: the reference's adaptive Radau IIA integrator for the whole batch with every array on the GPU (radau_batched.py)
     rollout = None
     try:
@@ -566,6 +594,8 @@ def main():
         line["jacobian"] = jac
     if rollout is not None:
         line["batched_radau"] = rollout
+    if latency is not None:
+        line["latency"] = latency
     if large is not None:
         line["large_scenes"] = large
     print(json.dumps(line))
