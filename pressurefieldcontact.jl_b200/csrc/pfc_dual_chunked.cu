@@ -33,7 +33,8 @@ namespace {
 //   4. one thread per (problem, output scalar) adds its items in candidate order (sequential, fixed order: reproducible, no atomics).
 // The warp-per-problem kernel this replaces left 19 of 32 lanes idle and 3 of 8 resident warps without work (ncu, round 1).
 typedef Dual<2> D2;
-constexpr int kDP = 8;            // problems per tile
+constexpr int kDP = 16;           // problems per tile (boxes.jl: four environments' instructions of one seed chunk, ~240 items on 128 threads;
+                                  // measured 8 / 16 / 20 problems: 5.08 / 4.54 / 4.82 ms for the whole Jacobian of 4096 environments)
 constexpr int kDT = 128;          // threads per CTA
 constexpr int kResStride = 43;    // per item: the 42 output scalars [7 comp + (0 = value, 1 + d = partial d)] + point count, odd stride
 constexpr int kTotStride = 43;    // 42 output scalars + point count
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
     const long long n_prob = io.n_env * sc.n_ins;
     const long long n_tile = (n_prob + kDP - 1) / kDP;
     for (long long tile = blockIdx.x; tile < n_tile;) {
-        // ---- 1. contexts: warp w fills problems w, w + 4
+        // ---- 1. contexts: warp w fills problems w, w + 4, ...
         for (int q = wib; q < kDP; q += kDT / 32) {
             const long long ei = tile * kDP + q;
             bool active = false;
