@@ -126,6 +126,8 @@ template <class T> struct DevBuf {
 struct pfc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                 // bristle pipeline beside the regularized narrow phase (eval_device_once)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool finalized = false;
     std::vector<HostMesh> mesh;
     std::vector<HostIns> ins;
@@ -296,6 +298,9 @@ int pfc_destroy(pfc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph.exec) { cudaGraphExecDestroy(c->graph.exec); c->graph.exec = nullptr; }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->graph_host.exec) { cudaGraphExecDestroy(c->graph_host.exec); c->graph_host.exec = nullptr; }
     if (c->graph_pack.exec) { cudaGraphExecDestroy(c->graph_pack.exec); c->graph_pack.exec = nullptr; }
     if (c->comm && nccl_api().ok()) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
@@ -592,7 +597,7 @@ int pfc_finalize(pfc_ctx* c, int64_t max_env) {
 // phase left.  dual: Jacobian mode (every scalar of X / twist / s / wrench / sdot is 7 doubles).  skip_large: a sharded context keeps its
 // large bristle instructions on the partial-sum protocol.  Synchronises the stream once (see exact_bristle_eval).
 static int eval_bristle_exact(pfc_ctx* c, long long n_env, const double* X, const double* twist, const double* s, double* wrench, double* sdot,
-                              const long long* n_pairs, int* flags, int dual, bool skip_large, int* nl) {
+                              const long long* n_pairs, int* flags, int dual, bool skip_large, int* nl, cudaStream_t stream = nullptr) {
     if (c->exact_scene.n_bris == 0) return PFC_OK;
     ExactIO xio{n_env, X, twist, s, wrench, sdot, n_pairs, flags};
     ExactPairs ps{};
@@ -600,7 +605,7 @@ static int eval_bristle_exact(pfc_ctx* c, long long n_env, const double* X, cons
     if (c->large_scene.n_large > 0 && c->has_large_bristle && !skip_large) large_exact_view(c->large_buf, c->large_scene, n_env, ps);
     ExactScene es = c->exact_scene;
     es.skip_large = skip_large ? 1 : 0;
-    CU(exact_bristle_eval(c->scene, es, xio, ps, dual, c->exact_buf, c->stream, nl));
+    CU(exact_bristle_eval(c->scene, es, xio, ps, dual, c->exact_buf, stream ? stream : c->stream, nl));
     return PFC_OK;
 }
 
@@ -650,17 +655,35 @@ static int eval_device_once(pfc_ctx* c, const EvalIO& io_in) {
         c->dbg_n_env = io.n_env;
     } else { io.dbg_pairs = nullptr; io.dbg_cap = 0; }
     int nl = 0;
+    // Scenes that mix bristle and regularized instructions on the small path (test/pencil.jl): once the pair lists exist, the bristle
+    // pipeline (reference-order points + patch passes, two long single-warp kernels) and the regularized narrow phase are independent
+    // (disjoint instructions, disjoint outputs): the bristle pipeline runs on a second stream beside the narrow kernel.  Not when large
+    // bristle instructions exist (their counts are published by the large path's finish kernel).
+    const bool beside = c->exact_scene.n_bris > 0 && c->scene.n_small > 0 && !c->has_large_bristle && !c->timing && c->n_bristle < c->scene.n_ins;
+    if (beside && !c->stream2) {
+        CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
     if (c->scene.n_small > 0) {
         CU(c->d_small_pairs.ensure(size_t(small_cap(c->small_max_pairs)) * io.n_env * n_ins + kSmallPairsSlack));
-        CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, c->timing ? c->ev : nullptr));
+        CU(launch_eval_small_f64(c->scene, io, c->small_max_pairs, c->d_small_pairs.p, c->stream, &nl, c->timing ? c->ev : nullptr, beside ? c->ev_fork : nullptr));
         c->ev_valid = c->timing;
+    }
+    if (beside) {
+        CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl, c->stream2);
+        if (rc != PFC_OK) return rc;
+        CU(cudaEventRecord(c->ev_join, c->stream2));
     }
     if (c->large_scene.n_large > 0) {
         if (c->shard_world > 1) return fail(PFC_E_ARG, "this context is sharded: use pfc_eval_sharded_begin / _step");
         CU(large_broad_phase(c->scene, c->large_scene, io, c->large_buf, c->stream, &nl));
         CU(large_narrow_stage(c->scene, c->large_scene, io, c->large_buf, 0, 0, c->stream, &nl));
     }
-    {   // bristle instructions (small and large): reference-order pipeline
+    if (beside) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    } else {   // bristle instructions (small and large): reference-order pipeline
         int rc = eval_bristle_exact(c, io.n_env, io.X, io.twist, io.s, io.wrench, io.sdot, io.n_pairs, io.flags, 0, false, &nl);
         if (rc != PFC_OK) return rc;
     }

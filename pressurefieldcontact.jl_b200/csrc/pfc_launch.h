@@ -46,7 +46,7 @@ int persistent_blocks(const void* kern, int threads, size_t smem, cudaError_t* e
 constexpr int kSmallPairsSlack = 32;   // words after the pair lists: [0] is the narrow tile kernel's tile ticket (zeroed by the broad kernel)
 // ev: optional array of 3 events recorded before the broad kernel, between the two kernels and after the narrow kernel
 cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches,
-                                  cudaEvent_t* ev = nullptr);
+                                  cudaEvent_t* ev = nullptr, cudaEvent_t after_broad = nullptr);
 
 // broad phase of the small path only (Jacobian mode re-traverses with the Float64 state, then evaluates on Duals)
 cudaError_t launch_broad_small_only(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches);

@@ -603,13 +603,14 @@ cudaError_t launch_broad(const SceneDev& sc, const EvalIO& io, int cap, unsigned
 int small_cap(int max_pairs) { return ((max_pairs > 1 ? max_pairs : 1) + 31) / 32 * 32; }
 
 cudaError_t launch_eval_small_f64(const SceneDev& sc, const EvalIO& io, int max_pairs, unsigned* pairs, cudaStream_t stream, int* n_launches,
-                                  cudaEvent_t* ev) {
+                                  cudaEvent_t* ev, cudaEvent_t after_broad) {
     if (io.n_env * sc.n_small == 0) return cudaSuccess;
     const int cap = small_cap(max_pairs);
     if (ev) cudaEventRecord(ev[0], stream);
     cudaError_t e = launch_broad(sc, io, cap, pairs, stream);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
+    if (after_broad) cudaEventRecord(after_broad, stream);   // the pair lists exist: what only needs them may start on another stream
     // regularized instructions: the tile kernel (4 problems per CTA, 4 CTAs per SM).  Bristle instructions are skipped here: they are
     // evaluated in the reference's operation order by pfc_exact.cu from the pair lists the broad kernel left
     {
