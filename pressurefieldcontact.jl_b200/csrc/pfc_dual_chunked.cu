@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
                         if (sc_i < 12) mine_x |= nz; else mine_t |= nz;
                     }
                     const int seeded = __any_sync(0xffffffffu, mine_x) ? 2 : (__any_sync(0xffffffffu, mine_t) ? 1 : 0);
-                    if (lane < 3) {   // chunk `lane`'s context: partials 2 lane and 2 lane + 1
+                    const bool copy_only = seeded == 0 && ps.w_f64;   // nothing to differentiate and the values exist: no contexts needed
+                    if (lane < 3 && !copy_only) {   // chunk `lane`'s context: partials 2 lane and 2 lane + 1
                         PatchCtx<D2>& cx = sm.cx[q][lane];
                         auto ld = [&](const double* p7) { D2 r; r.v = p7[0]; r.p[0] = p7[1 + 2 * lane]; r.p[1] = p7[2 + 2 * lane]; return r; };
 #pragma unroll
@@ -158,15 +159,17 @@ __global__ void __launch_bounds__(kDT) eval_dual6_tile_kernel(SceneDev sc, DualI
                     }
                     __syncwarp();
                     if (lane == 0) {
-                        const PatchCtx<D2>& c0 = sm.cx[q][0];
-                        PatchCtx<double>& cxv = sm.cxv[q];
+                        if (!copy_only) {
+                            const PatchCtx<D2>& c0 = sm.cx[q][0];
+                            PatchCtx<double>& cxv = sm.cxv[q];
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) { cxv.x21.r[i] = c0.x21.r[i].v; cxv.x12.r[i] = c0.x12.r[i].v; }
+                            for (int i = 0; i < 9; ++i) { cxv.x21.r[i] = c0.x21.r[i].v; cxv.x12.r[i] = c0.x12.r[i].v; }
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) { cxv.x21.t[i] = c0.x21.t[i].v; cxv.x12.t[i] = c0.x12.t[i].v; }
-                        cxv.w_ang = mk<double>(c0.w_ang.x.v, c0.w_ang.y.v, c0.w_ang.z.v);
-                        cxv.w_lin = mk<double>(c0.w_lin.x.v, c0.w_lin.y.v, c0.w_lin.z.v);
-                        cxv.chi = c0.chi; cxv.Ebar1 = c0.Ebar1; cxv.Ebar2 = c0.Ebar2; cxv.n_quad = c0.n_quad;
+                            for (int i = 0; i < 3; ++i) { cxv.x21.t[i] = c0.x21.t[i].v; cxv.x12.t[i] = c0.x12.t[i].v; }
+                            cxv.w_ang = mk<double>(c0.w_ang.x.v, c0.w_ang.y.v, c0.w_ang.z.v);
+                            cxv.w_lin = mk<double>(c0.w_lin.x.v, c0.w_lin.y.v, c0.w_lin.z.v);
+                            cxv.chi = c0.chi; cxv.Ebar1 = c0.Ebar1; cxv.Ebar2 = c0.Ebar2; cxv.n_quad = c0.n_quad;
+                        }
                         sm.ei[q] = ei; sm.er[q] = er; sm.ins[q] = k; sm.seeded[q] = seeded; sm.pflags[q] = 0;
                         const bool pf = ins.small && ps.surv_pairs;       // survivors of the Float64 clip are listed already
                         const bool cp = seeded == 0 && ps.w_f64;          // nothing to differentiate and the values exist: copy them
