@@ -51,6 +51,32 @@ def test_c5_pile_full_size():
     assert c["n_pairs"].sum() > 850000 and (c["flags"] & 1).sum() > 100
 
 
+def test_replayed_graph_of_a_many_kernel_scene_follows_the_inputs():
+    """Scenes with large or bristle instructions replay a captured CUDA graph from their third identical evaluation on (same batch size,
+    same device buffers).  The pile with bristle instructions, evaluated six times with OTHER states in the same buffers -- other pair
+    counts, other contacts: every result equals what a fresh context (first evaluation: never a graph) computes from the same state."""
+    m, x0 = scenes.scene_c5_pile(3, 8, bristle_every=7)
+    ctx = capi.Context(0)
+    S.attach_backend(m, ctx)
+    nb = ctx.n_bristle
+    rng = np.random.default_rng(42)
+    counts = set()
+    for it in range(6):
+        x = x0.copy()
+        x[:m.nq] += rng.uniform(-0.004, 0.004, m.nq)            # nudged poses: other pair lists
+        X, tw, s = S.boundary_arrays(m, x)
+        s_arr = s.reshape(1, nb, 6)
+        got = ctx.eval_f64(X, tw, s_arr)
+        m2, _ = scenes.scene_c5_pile(3, 8, bristle_every=7)
+        fresh = capi.Context(0)
+        S.attach_backend(m2, fresh)
+        want = fresh.eval_f64(X, tw, s_arr)
+        assert np.array_equal(got["n_pairs"], want["n_pairs"]) and np.array_equal(got["flags"], want["flags"]), it
+        assert got["wrench"].tobytes() == want["wrench"].tobytes() and got["sdot"].tobytes() == want["sdot"].tobytes(), it
+        counts.add(int(got["n_pairs"].sum()))
+    assert len(counts) > 1
+
+
 def _sharded_on_one_gpu(build, world):
     """Returns (unsharded result, per-rank results after the exchange, per-rank pair lists of every instruction)."""
     import torch
