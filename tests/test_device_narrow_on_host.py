@@ -14,6 +14,8 @@ The regularized-Coulomb wrench of every pair that touches (Accum::point in its r
 law) is compared with the oracle's yes_contact!(::Regularized) (src/contact_algorithms_friction.jl:13-30, 50-72) to 1e-10 of the
 torque / force magnitude -- and once more in Jacobian mode: pose and twist carry six random partials each, the device templates run on
 pfc::Dual<6>, the oracle on its own Dual<6>, and values and all partials of the wrench must agree to 1e-9 of the group's magnitude.
+A third variant seeds the twist only (the velocity chunks of a Jacobian): the device's Float64-polygon / Dual-twist route
+(pfc_twist.cuh) against the oracle's all-Dual evaluation with zero pose partials, same bar.
 This is the GPU parity test's TractionCache check (tests/test_gpu_parity.py) restated where no GPU is needed."""
 import os
 import subprocess
@@ -46,6 +48,7 @@ static inline double __longlong_as_double(long long x) { double d; std::memcpy(&
 static inline long long __double_as_longlong(double x) { long long d; std::memcpy(&d, &x, 8); return d; }
 #define PFC_HOST_CHECK 1
 #include "pfc_patch.cuh"
+#include "pfc_twist.cuh"
 
 using orc::V3; using orc::V4; using orc::M4;
 
@@ -67,7 +70,7 @@ int main(int argc, char** argv) {
     const long n_case = argc > 1 ? atol(argv[1]) : 100000;
     std::mt19937_64 g(4096);
     std::uniform_real_distribution<double> u(-1.0, 1.0), u01(0.0, 1.0);
-    long bad_tile = 0, bad_pair = 0, with_points = 0, n_points = 0, tet_tet = 0, bad_wrench = 0, n_wrench = 0, bad_dual = 0;
+    long bad_tile = 0, bad_pair = 0, with_points = 0, n_points = 0, tet_tet = 0, bad_wrench = 0, n_wrench = 0, bad_dual = 0, bad_twist = 0;
     for (long t = 0; t < n_case; ++t) {
         const int kind1 = (t % 3 == 0) ? 1 : 0;   // a third of the cases tet-tet
         const int n_quad_rule = (t % 2) ? 2 : 1;
@@ -220,6 +223,36 @@ int main(int argc, char** argv) {
                 }
             }
             if (!ok_d && bad_dual++ < 3) std::printf("Dual-6 wrench differs in case %ld (kind1 %d, %d points vs %zu)\n", t, kind1, accd.n_points, bd.traction.size());
+            // ---- and with seeds on the twist only (velocity seeds of the Jacobian): the device keeps the polygon in Float64 and runs
+            // the twist-dependent part on Duals (pfc_twist.cuh); the oracle runs everything on Dual<6> with zero pose partials
+            {
+                orc::BodyBodyCache<OD> bt;
+                bt.quad = b.quad; bt.mesh_1 = &m1; bt.mesh_2 = &m2; bt.chi = chi; bt.Ebar = m2.Ebar;
+                for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) bt.x_r2_r1(i, j) = OD(bd.x_r2_r1(i, j).v);
+                bt.x_r1_r2 = orc::inv_transform(bt.x_r2_r1);
+                pfc::TwistAcc<6> tacc;
+                for (int i = 0; i < 3; ++i) { seeded(tw[i], bt.twist_r2_r1_r2[i], (&tacc.w_ang.x)[i]); seeded(tw[3 + i], bt.twist_r2_r1_r2[3 + i], (&tacc.w_lin.x)[i]); }
+                if (kind1) orc::integrate_over_tet_tet(0, 0, bt); else orc::integrate_over_tri_tet(0, 0, bt);
+                const orc::V6<OD> wt_ref = orc::yes_contact_regularized(reg, bt);
+                tacc.fp = fp; tacc.n_points = 0;
+                for (int j = 0; j < 6; ++j) tacc.a[j] = PD(0.0);
+                pfc::PolyRec<double> pr;
+                int fl2 = 0;
+                if (pfc::clip_pair(sc, ins, 0, 0, cx, pr, fl2)) {
+                    pfc::Vec3<double> v2 = pr.v[pr.n - 1];
+                    for (int k = 0; k < pr.n; ++k) { const pfc::Vec3<double> v1 = v2; v2 = pr.v[k]; pfc::integrate_subtri_tw(v1, v2, pr.cen, pr.nrm, pr.eps_r, cx.chi, cx.Ebar2, cx.n_quad, tacc); }
+                }
+                bool ok_t = (tacc.n_points == (int)bt.traction.size());
+                for (int grp = 0; grp < 2 && ok_t; ++grp) {
+                    double scale = 1.0e-6;
+                    for (int i = 0; i < 3; ++i) { scale = std::fmax(scale, std::fabs(wt_ref[3 * grp + i].v)); for (int k = 0; k < 6; ++k) scale = std::fmax(scale, std::fabs(wt_ref[3 * grp + i].p[k])); }
+                    for (int i = 0; i < 3; ++i) {
+                        if (std::fabs(tacc.a[3 * grp + i].v - wt_ref[3 * grp + i].v) > 1.0e-9 * scale) ok_t = false;
+                        for (int k = 0; k < 6; ++k) if (std::fabs(tacc.a[3 * grp + i].p[k] - wt_ref[3 * grp + i].p[k]) > 1.0e-9 * scale) ok_t = false;
+                    }
+                }
+                if (!ok_t && bad_twist++ < 3) std::printf("twist-seeded wrench differs in case %ld (kind1 %d, %d points vs %zu)\n", t, kind1, tacc.n_points, bt.traction.size());
+            }
         }
         const bool ok_tile = same(p_tile, b.traction), ok_pair = same(p_pair, b.traction);
         if (!ok_tile && bad_tile++ < 3) std::printf("tile route differs in case %ld (kind1 %d): %d points vs %zu\n", t, kind1, p_tile.n, b.traction.size());
@@ -228,9 +261,9 @@ int main(int argc, char** argv) {
         n_points += (long)b.traction.size();
         tet_tet += kind1 && !b.traction.empty();
     }
-    std::printf("cases %ld bad_tile %ld bad_pair %ld with_points %ld points %ld tet_tet_with_points %ld wrenches %ld bad_wrench %ld bad_dual %ld\n", n_case, bad_tile, bad_pair,
-                with_points, n_points, tet_tet, n_wrench, bad_wrench, bad_dual);
-    return (bad_tile || bad_pair || bad_wrench || bad_dual) ? 1 : 0;
+    std::printf("cases %ld bad_tile %ld bad_pair %ld with_points %ld points %ld tet_tet_with_points %ld wrenches %ld bad_wrench %ld bad_dual %ld bad_twist %ld\n", n_case, bad_tile, bad_pair,
+                with_points, n_points, tet_tet, n_wrench, bad_wrench, bad_dual, bad_twist);
+    return (bad_tile || bad_pair || bad_wrench || bad_dual || bad_twist) ? 1 : 0;
 }
 """
 
@@ -245,6 +278,6 @@ def test_device_narrow_phase_matches_oracle_point_by_point(tmp_path):
     sys.stdout.write(out.stdout)
     assert out.returncode == 0, out.stdout[-2000:]
     f = out.stdout.split()
-    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("bad_tile", "bad_pair", "with_points", "points", "tet_tet_with_points", "wrenches", "bad_wrench", "bad_dual")}
-    assert stats["bad_tile"] == 0 and stats["bad_pair"] == 0 and stats["bad_wrench"] == 0 and stats["bad_dual"] == 0 and stats["wrenches"] > 5000
+    stats = {f[i]: int(f[i + 1]) for i in range(0, len(f) - 1) if f[i] in ("bad_tile", "bad_pair", "with_points", "points", "tet_tet_with_points", "wrenches", "bad_wrench", "bad_dual", "bad_twist")}
+    assert stats["bad_tile"] == 0 and stats["bad_pair"] == 0 and stats["bad_wrench"] == 0 and stats["bad_dual"] == 0 and stats["bad_twist"] == 0 and stats["wrenches"] > 5000
     assert stats["with_points"] > 5000 and stats["tet_tet_with_points"] > 500   # the cases do produce contact polygons of both kinds
