@@ -25,11 +25,14 @@ namespace {
 // A CTA of 128 threads owns a TILE of kDP consecutive problems ((chunk, environment, instruction) in whole-Jacobian mode) and every
 // phase is flattened over the tile, like narrow_tile_kernel:
 //   1. problem contexts: Dual<2> transforms / twists of the three chunks, the Float64 value context, "is any input seeded?";
-//   2. the tile's candidate pairs are dealt one per thread for the Float64 clip (two thirds clip to nothing; decisions are value-only);
-//      a block scan packs the survivors in candidate order;
-//   3. survivors of seeded problems become 3 work items (one per chunk of partials) on Dual<2>, survivors of problems none of whose
-//      inputs depends on the seeds (the seeds sit on another body: 18 of 32 (instruction, chunk) pairs of boxes.jl) ONE Float64 item;
-//      items are dealt one per thread, 6 sums (x 3 doubles) + point count per item go to shared memory;
+//   2. the tile's candidate pairs are dealt one per thread for the Float64 clip (two thirds clip to nothing; decisions are value-only)
+//      -- or come already filtered from dual_prefilter_kernel, once per evaluation for all seed chunks; a block scan packs the
+//      survivors in candidate order;
+//   3. survivors of problems whose TRANSFORM depends on the seeds become 3 work items (one per chunk of partials), the whole pair on
+//      Dual<2>; survivors of problems whose twist alone does (velocity seeds) ONE item: Float64 polygon, the twist-dependent part on
+//      Dual<2> three times (pfc_twist.cuh); problems none of whose inputs depends on the seeds (the seeds sit on another body: 18 of 32
+//      (instruction, chunk) pairs of boxes.jl) copy the Float64 wrench of the same evaluation when the caller has it (one Float64 item
+//      per survivor otherwise); items are dealt one per thread, their 42 output scalars + point count go to shared memory;
 //   4. one thread per (problem, output scalar) adds its items in candidate order (sequential, fixed order: reproducible, no atomics).
 // The warp-per-problem kernel this replaces left 19 of 32 lanes idle and 3 of 8 resident warps without work (ncu, round 1).
 typedef Dual<2> D2;

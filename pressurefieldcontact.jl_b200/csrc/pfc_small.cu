@@ -305,8 +305,6 @@ __global__ void __launch_bounds__(32 * NW, MINB) broad_tile_kernel(SceneDev sc, 
 // a fifth CTA.
 constexpr int kPolyStride = 35;    // doubles per PolyRec slot
 static_assert(sizeof(PolyRec<double>) == kPolyStride * sizeof(double), "PolyRec<double> is 35 doubles");
-constexpr int kItemCap = 256;      // sub-triangles per summation round
-constexpr int kItemStride = 7;     // 6 sums + point count, odd stride
 
 template <int P> struct TileSmem {   // P problems, P warps
     static constexpr int kThreads = 32 * P;
