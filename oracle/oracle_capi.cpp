@@ -347,4 +347,44 @@ int64_t orc_get_traction(void* h, int64_t env, int ins, double* out, int64_t cap
 
 int orc_max_threads() { unsigned n = std::thread::hardware_concurrency(); return n ? int(n) : 1; }
 
+
+// Small kernels of the path behind one entry point, for the restated unit tests of the reference (tests/test_oracle_units.py):
+//   0 weightPoly(p1, p2, w1, w2)            in: p1[3] p2[3] w1 w2                 out: r[3]       (src/math_kernel/utility.jl:21-26)
+//   1 vec_sub_vec_proj(v, n)                in: v[3] n[3]                         out: r[3]       (vector_projections.jl:2-7)
+//   2 a_dot_one_pad_b(a, b)                 in: a[4] b[3]                         out: r[1]       (vector_projections.jl:9-13)
+//   3 triangle kernels                      in: v1[3] v2[3] v3[3]                 out: area, centroid[3], normal[3]   (geometry_kernel.jl:3-10)
+//   4 getTriQuadRule(n)                     in: n                                 out: n_point, w[3], zeta[3][3]      (src/clip/quadrature.jl:21-41)
+//   5 basic_dh algebra                      in: R[9] (row-major) t[3] p[3]        out: dh*p [3], inv(dh)*(dh*p) [3], (dh*dh)*p [3]   (basic_dh.jl)
+int orc_kat(int which, const double* in, double* out) {
+    if (which == 0) {
+        V3<double> r = weightPoly(mk3<double>(in[0], in[1], in[2]), mk3<double>(in[3], in[4], in[5]), in[6], in[7]);
+        for (int i = 0; i < 3; ++i) out[i] = r[i];
+    } else if (which == 1) {
+        V3<double> r = vec_sub_vec_proj(mk3<double>(in[0], in[1], in[2]), mk3<double>(in[3], in[4], in[5]));
+        for (int i = 0; i < 3; ++i) out[i] = r[i];
+    } else if (which == 2) {
+        V4<double> a; for (int i = 0; i < 4; ++i) a[i] = in[i];
+        out[0] = a_dot_one_pad_b(a, mk3<double>(in[4], in[5], in[6]));
+    } else if (which == 3) {
+        const V3<double> v1 = mk3<double>(in[0], in[1], in[2]), v2 = mk3<double>(in[3], in[4], in[5]), v3 = mk3<double>(in[6], in[7], in[8]);
+        const V3<double> n = triangleNormal(v1, v2, v3), c = centroid3(v1, v2, v3);
+        out[0] = triangle_area(v1, v2, v3, n);
+        for (int i = 0; i < 3; ++i) { out[1 + i] = c[i]; out[4 + i] = n[i]; }
+    } else if (which == 4) {
+        const TriQuadRule q = getTriQuadRule(int(in[0]));
+        out[0] = q.n;
+        for (int k = 0; k < 3; ++k) { out[1 + k] = q.w[k]; for (int i = 0; i < 3; ++i) out[4 + 3 * k + i] = q.zeta[k][i]; }
+    } else if (which == 5) {
+        M3<double> R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = in[3 * i + j];
+        const V3<double> t = mk3<double>(in[9], in[10], in[11]);
+        const M4<double> dh = basic_dh<double>(R, t);
+        V4<double> p; for (int i = 0; i < 3; ++i) p[i] = in[12 + i]; p[3] = 1.0;
+        const V4<double> q1 = mul4v<double, double, double>(dh, p);
+        const V4<double> q2 = mul4v<double, double, double>(inv_transform(dh), q1);
+        const V4<double> q3 = mul4v<double, double, double>(mul44<double, double, double>(dh, dh), p);
+        for (int i = 0; i < 3; ++i) { out[i] = q1[i]; out[3 + i] = q2[i]; out[6 + i] = q3[i]; }
+    } else return -1;
+    return 0;
+}
+
 }  // extern "C"

@@ -40,6 +40,8 @@ def lib():
         L.orc_clip_plane_tet.argtypes = [_d, _d, _d]
         L.orc_poly_centroid.restype = C.c_double
         L.orc_poly_centroid.argtypes = [C.c_int, _d, _d, _d]
+        L.orc_kat.restype = C.c_int
+        L.orc_kat.argtypes = [C.c_int, _d, _d]
         L.orc_zero_small_coordinates.restype = None
         L.orc_zero_small_coordinates.argtypes = [C.c_int, _d]
         L.orc_calc_clamped_piecewise.restype = C.c_double
@@ -129,6 +131,15 @@ def poly_centroid(v, nhat):
     c = np.zeros(3)
     area = lib().orc_poly_centroid(len(v), v, _a(nhat), c)
     return area, c
+
+
+def kat(which: int, values, n_out: int):
+    """Small kernels of the path (oracle_capi.cpp::orc_kat): which 0 weightPoly, 1 vec_sub_vec_proj, 2 a_dot_one_pad_b, 3 triangle kernels,
+    4 getTriQuadRule, 5 basic_dh algebra."""
+    out = np.zeros(n_out)
+    if lib().orc_kat(int(which), _a(values).ravel(), out) != 0:
+        raise ValueError("orc_kat: unknown kernel")
+    return out
 
 
 def zero_small_coordinates(zeta):

@@ -321,3 +321,66 @@ def test_inv44_and_obb_fit_against_numpy():
         c2, e2, R2 = G.fit_tri_obb(tet[:3])
         assert np.allclose(c, c2) and np.allclose(e, e2) and np.allclose(R, R2)
         assert abs(e[2]) < 1e-14  # a triangle's box is flat
+
+
+# ---- the reference's remaining unit tests of kernels ON the path, restated on the oracle (through oracle_capi.cpp::orc_kat) ----------
+def test_weight_poly_known_answers():
+    """test/test_math_kernel/test_utility.jl:9-15 (weightPoly, src/math_kernel/utility.jl:21-26): the three exact cases."""
+    p1, p2 = np.array([1.0, 2.0, 3.0]), np.array([2.0, 3.0, 4.0])
+    assert np.array_equal(orc.kat(0, [*p1, *p2, 1.0, 0.0], 3), p2)
+    assert np.array_equal(orc.kat(0, [*p1, *p2, 0.0, 1.0], 3), p1)
+    assert np.array_equal(orc.kat(0, [*p1, *p2, -0.7, 0.7], 3), (p1 + p2) * 0.5)
+
+
+def test_vector_projections_known_answers():
+    """test/test_math_kernel/test_vector_projections.jl:1-25: vec_sub_vec_proj and a_dot_one_pad_b, exact cases."""
+    n = [0.0, 0.0, 1.0]
+    assert np.array_equal(orc.kat(1, [1.0, 0.0, 0.0, *n], 3), [1.0, 0.0, 0.0])
+    assert np.array_equal(orc.kat(1, [*n, *n], 3), [0.0, 0.0, 0.0])
+    assert np.array_equal(orc.kat(1, [0.0, 1.0, 1.0, *n], 3), [0.0, 1.0, 0.0])
+    a = [1.0, 2.0, 3.0, 4.0]
+    assert orc.kat(2, [*a, 2.0, 0.0, 0.0], 1)[0] == 6.0
+    assert orc.kat(2, [*a, 1.0, 2.0, 0.0], 1)[0] == 9.0
+    assert orc.kat(2, [*a, 1.0, 2.0, 3.0], 1)[0] == 18.0
+
+
+def test_triangle_kernels_known_answers():
+    """test/test_math_kernel/test_geometry_kernel.jl:6-16: area 1/2, centroid (1/3, 1/3, 0), normal (0, 0, 1) of the unit right triangle;
+    the tetrahedron cases (:18-25) through orc_tet_volume: volume 1/6."""
+    out = orc.kat(3, [0, 0, 0, 1, 0, 0, 0, 1, 0], 7)
+    assert abs(out[0] - 0.5) <= 1e-15
+    assert np.allclose(out[1:4], [1 / 3, 1 / 3, 0.0], rtol=0, atol=1e-16)
+    assert np.allclose(out[4:7], [0.0, 0.0, 1.0], rtol=0, atol=1e-16)
+    tet = np.ascontiguousarray([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+    assert abs(abs(orc.lib().orc_tet_volume(tet)) - 1 / 6) <= 1e-16
+
+
+def test_quadrature_rules_properties():
+    """test/test_clip/test_quadrature.jl:1-21 for the two triangle rules the path uses (n_quad_rule 1 and 2, src/clip/quadrature.jl:21-41):
+    weights sum to 1, every point's barycentric coordinates sum to 1, the weighted points average to the centroid, and the three points
+    of rule 2 are permutations of one another."""
+    for rule, n_point in ((1, 1), (2, 3)):
+        out = orc.kat(4, [rule], 13)
+        n = int(out[0])
+        assert n == n_point
+        w, zeta = out[1:1 + n], out[4:13].reshape(3, 3)[:n]
+        assert abs(w.sum() - 1.0) <= 1e-15
+        assert np.abs(zeta.sum(axis=1) - 1.0).max() <= 1e-15
+        assert np.abs((w[:, None] * zeta).sum(axis=0) - 1 / 3).max() <= 1e-15
+    z2 = np.sort(orc.kat(4, [2], 13)[4:13].reshape(3, 3), axis=1)
+    assert np.array_equal(z2[0], z2[1]) and np.array_equal(z2[1], z2[2])
+
+
+def test_basic_dh_algebra():
+    """test/test_math_kernel/test_basic_dh.jl:56-75 (inverse, multiply, dh_vector_mul) on the oracle's homogeneous-transform helpers, the
+    ones BB_BB_intersect composes (src/obb/bb_intersection.jl:2-12)."""
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        t, p = rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3)
+        out = orc.kat(5, [*q.reshape(9), *t, *p], 9)
+        assert np.abs(out[0:3] - (q @ p + t)).max() <= 1e-15 * 4          # dh_vector_mul(dh, p) == R p + t
+        assert np.abs(out[3:6] - p).max() <= 1e-14                         # inv(dh) * dh == I
+        assert np.abs(out[6:9] - (q @ (q @ p + t) + t)).max() <= 1e-14     # (dh * dh).mat == dh.mat * dh.mat
