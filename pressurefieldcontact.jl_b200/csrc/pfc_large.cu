@@ -192,7 +192,7 @@ PFC_D unsigned item_hash(int prob, int a, int b) {
 
 __global__ void __launch_bounds__(256, 2) broad_bfs_kernel(SceneDev sc, const ProbRec* __restrict__ ptab, const Seed* __restrict__ in, Seed* out,
                                                         int level, int split_level, unsigned cap_frontier, int3* pairs, unsigned cap_pairs, Counters* cnt,
-                                                        unsigned hrank, unsigned hworld) {
+                                                        unsigned hrank, unsigned hworld, unsigned per_warp_from) {
     const unsigned n_raw = cnt->level_n[level];
     const unsigned n = n_raw < cap_frontier ? n_raw : cap_frontier;   // (an overflowing level is cut short; the host repeats the evaluation)
     if (n == 0) return;
@@ -201,12 +201,16 @@ __global__ void __launch_bounds__(256, 2) broad_bfs_kernel(SceneDev sc, const Pr
     // whose hash falls on it; below, everything in its frontier is its own.  Leaf pairs found on the shared levels go to the rank their
     // own hash names.
     const bool shared = hworld > 1u && level <= split_level;
-    // Space in the next frontier and in the pair list is reserved once per CTA and iteration (block scan of the child / leaf counts, two
-    // atomics by one thread): a big level has ~150 k warps' worth of node pairs, and one atomic per warp on the same two counters made
-    // the level's duration the L2's same-address atomic rate (~2 per ns), not the tests.
+    // Space in the next frontier and in the pair list is reserved with ONE atomic per counter and reservation (the high-water mark the
+    // first version also kept with an atomicMax is read off the level counters by the host): same-address atomics retire at ~2 ns each,
+    // and a level's duration was three of them per warp.  Levels below per_warp_from entries reserve once per CTA and iteration (block
+    // scan, two barriers: C4's levels of <= 1 M node pairs, 0.397 -> 0.384 ms); bigger levels once per warp without a barrier (C5's two
+    // levels of 5 M node pairs: 373 / 364 -> ~300 us each; C5 1.45 -> 1.28 ms).  Measured thresholds 0 / 1 M / 3 M / never: C5 1.297 /
+    // 1.277 / 1.289 / 1.453 ms, C4 0.397 / 0.384 / 0.385 / 0.385 ms.
     __shared__ unsigned warp_child[8], warp_leaf[8], base_child, base_leaf;
     unsigned long long tests = 0;
     const unsigned stride = gridDim.x * blockDim.x;
+    const bool per_warp = n >= per_warp_from;
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {   // CTA-uniform trip count
         const unsigned i = base + threadIdx.x;
         int r = 0;
@@ -228,25 +232,38 @@ __global__ void __launch_bounds__(256, 2) broad_bfs_kernel(SceneDev sc, const Pr
             n_child = kept;
         }
         const bool emit = r < 0 && (!split || item_hash(s.prob, ch[0].x, ch[0].y) % hworld == hrank);
-        // block scan of (children, leaf pairs): children in the low 16 bits of one word, leaves in the high 16
+        // scan of (children, leaf pairs): children in the low 16 bits of one word, leaves in the high 16
         unsigned incl = (unsigned)n_child | (emit ? 0x10000u : 0u);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) { warp_child[wib] = incl & 0xffffu; warp_leaf[wib] = incl >> 16; }
-        __syncthreads();
-        unsigned before_c = 0, before_l = 0, tot_c = 0, tot_l = 0;
+        unsigned at, pat;
+        if (per_warp) {   // (grid-uniform) one reservation per warp, no barrier
+            const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned bc = 0, bl = 0;
+            if (lane == 31) {
+                if (tot & 0xffffu) bc = atomicAdd(&cnt->level_n[level + 1], tot & 0xffffu);
+                if (tot >> 16) bl = atomicAdd(&cnt->n_pairs, tot >> 16);
+            }
+            bc = __shfl_sync(0xffffffffu, bc, 31); bl = __shfl_sync(0xffffffffu, bl, 31);
+            at = bc + (incl & 0xffffu) - (unsigned)n_child;
+            pat = bl + (incl >> 16) - 1u;
+        } else {
+            if (lane == 31) { warp_child[wib] = incl & 0xffffu; warp_leaf[wib] = incl >> 16; }
+            __syncthreads();
+            unsigned before_c = 0, before_l = 0, tot_c = 0, tot_l = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { const unsigned c = warp_child[w], l = warp_leaf[w]; if (w < wib) { before_c += c; before_l += l; } tot_c += c; tot_l += l; }
-        if (threadIdx.x == 0) {
-            base_child = tot_c ? atomicAdd(&cnt->level_n[level + 1], tot_c) : 0u;
-            base_leaf = tot_l ? atomicAdd(&cnt->n_pairs, tot_l) : 0u;
+            for (int w = 0; w < 8; ++w) { const unsigned c = warp_child[w], l = warp_leaf[w]; if (w < wib) { before_c += c; before_l += l; } tot_c += c; tot_l += l; }
+            if (threadIdx.x == 0) {
+                base_child = tot_c ? atomicAdd(&cnt->level_n[level + 1], tot_c) : 0u;
+                base_leaf = tot_l ? atomicAdd(&cnt->n_pairs, tot_l) : 0u;
+            }
+            __syncthreads();
+            at = base_child + before_c + (incl & 0xffffu) - (unsigned)n_child;
+            pat = base_leaf + before_l + (incl >> 16) - 1u;
         }
-        __syncthreads();
-        const unsigned at = base_child + before_c + (incl & 0xffffu) - (unsigned)n_child;
         if (at + n_child <= cap_frontier) { for (int c = 0; c < n_child; ++c) out[at + c] = Seed{s.prob, 0u, ch[c].x, ch[c].y}; }
         else if (n_child > 0) atomicOr(&cnt->overflow, 1u);
         if (emit) {
-            const unsigned pat = base_leaf + before_l + (incl >> 16) - 1u;
             if (pat < cap_pairs) pairs[pat] = make_int3(s.prob, ch[0].x, ch[0].y); else atomicOr(&cnt->overflow, 2u);
         }
     }
@@ -994,9 +1011,10 @@ cudaError_t large_broad_phase(const SceneDev& sc, const LargeScene& ls, const Ev
     // ---- traversal
     init_frontier_kernel<<<std::min<unsigned>((n_prob + 255) / 256, 1024), 256, 0, stream>>>(sc, ls, io.n_env, io.X, b->frontier[0], b->ptab, b->cnt);
     int src = 0;
+    static const unsigned per_warp_from = getenv("PFC_BFS_PER_WARP_FROM") ? (unsigned)atoll(getenv("PFC_BFS_PER_WARP_FROM")) : (1u << 20);   // (experiment switch)
     for (int l = 0; l < levels; ++l) {
         broad_bfs_kernel<<<n_sm * 8, 256, 0, stream>>>(sc, b->ptab, b->frontier[src], b->frontier[src ^ 1], l, split_level, (unsigned)b->cap_frontier, b->pairs,
-                                                     (unsigned)b->cap_pairs, b->cnt, (unsigned)hash_rank, (unsigned)hash_world);
+                                                     (unsigned)b->cap_pairs, b->cnt, (unsigned)hash_rank, (unsigned)hash_world, per_warp_from);
         src ^= 1;
     }
     // what the levels left (nothing, when they ran to the leaves) is traversed with per-warp stacks; the split has been made by then
